@@ -1,0 +1,149 @@
+/*
+ * rave_b200 -- C ABI of the B200-native (sm_100a) waveform hot path of acids-ircam/RAVE.
+ *
+ * The reference has no FFI: its hot path is issued through ATen library calls
+ * (F.pad + F.conv1d / F.conv_transpose1d / nn.Conv2d -> cuDNN).  Each entry point below
+ * replaces one of those call sites; the reference-side binding a maintainer would add is the
+ * ctypes stub in rave_b200/_lib.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed for the duration of the stream-ordered call;
+ *     the library owns no tensors and never synchronises the host;
+ *   - tensors are dense row-major fp32 "NCL": x[b][c][t] at (b*C + c)*L + t, unless stated;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = success, non-zero = failure, message via rave_b200_last_error();
+ *   - re-entrant across streams (no global mutable state except the last-error string).
+ *
+ * Activation codes (the `activation(dim)` module that precedes almost every conv,
+ * rave/blocks.py:56,90,528,614): 0 = none, 1 = LeakyReLU(slope), 2 = Snake(alpha[C]).
+ */
+#ifndef RAVE_B200_H
+#define RAVE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAVE_ACT_NONE 0
+#define RAVE_ACT_LEAKY 1
+#define RAVE_ACT_SNAKE 2
+
+/* precision modes of the tensor-core conv engine */
+#define RAVE_PREC_FP32 0 /* CUDA-core fp32 FMA: parity mode (<=1e-5 rel-L2 vs the fp32 CPU oracle) */
+#define RAVE_PREC_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
+#define RAVE_PREC_TF32 2 /* tcgen05 kind::tf32, fp32 operands read as tf32 */
+
+int rave_b200_version(void);
+const char *rave_b200_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+unsigned long long rave_b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * PQMF (replaces CachedPQMF.forward / .inverse, rave/pqmf.py:279-294, and their autograd).
+ *
+ * analysis:  y[b][k][n] = sgn(k,n) * sum_{j<ntaps} taps[k][j] * x[b][16 n + j - pad_l]
+ *            x: [B][T], taps: [16][ntaps] (ntaps <= 528), y: [B][16][Lout];
+ *            sgn = -1 for odd k and even n when flip_sign != 0 (reverse_half, pqmf.py:13-17).
+ * synthesis: out[b][16 t + 15 - m] = scale * sum_{c<16} sum_{j<K} w[m][c][j] * sgn(c,tau) * x[b][c][tau],
+ *            tau = t + j - pad_l;  x: [B][16][L], w: [16][16][K] (K <= 33), out: [B][16 L].
+ *            (conv 16->16, *M, channel flip and channel->time interleave of pqmf.py:288-294 fused.)
+ * The backward of each is the other with re-indexed taps (done by the host wrapper).
+ * Only n_band == 16 (every shipped config, configs/v1.gin:15) has a device kernel.
+ * ------------------------------------------------------------------------------------------- */
+int rave_pqmf_analysis_fwd(const float *x, const float *taps, float *y, int B, int T, int Lout,
+                           int ntaps, int pad_l, int flip_sign, void *stream);
+int rave_pqmf_synthesis_fwd(const float *x, const float *w, float *out, int B, int L, int K,
+                            int pad_l, float scale, int flip_sign, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * conv1d family, fp32 CUDA-core path (replaces cc.Conv1d.forward = F.pad + F.conv1d,
+ * cached_conv [EXT] via rave/blocks.py:96-108,538-592,637-692 and nn.Conv1d/Conv2d(k,1) in
+ * rave/discriminator.py:99-111, plus the autograd of those calls).
+ *
+ * gather ("conv forward" form; also the input-gradient of a transposed conv):
+ *   out[b][m][l] = bias[m] + res[b][m][l]
+ *                + sum_{c<Cs} sum_{k<K} W(m,c,k) * act(src[b][c][l*stride + k*dil - pad_l])
+ *   then, if post_act != 0:  out *= act'(post_x[b][m][l])      (chain rule through a pre-activation)
+ *   W(m,c,k) = w[m*ws_m + c*ws_c + k];  src: [B][Cs][Ls];  out: [B][Cm][Lo].
+ *
+ * scatter ("transposed" form: conv input-gradient, ConvTranspose1d forward):
+ *   out[b][m][t] = bias[m] + res[b][m][t]
+ *                + sum_{c<Cs} sum_{k<K} W(m,c,k) * act(src[b][c][q/stride]),  q = t + pad_l - k*dil,
+ *                  terms kept only where q >= 0, q % stride == 0 and q/stride < Ls
+ *   then the same optional post factor.
+ *
+ * act codes: see top.  `alpha` is the Snake alpha of the source channels (act == 2).
+ * ------------------------------------------------------------------------------------------- */
+int rave_conv1d_gather_f32(const float *src, const float *w, const float *bias, const float *res,
+                           float *out, int B, int Cs, int Ls, int Cm, int Lo, int K, int stride,
+                           int dil, int pad_l, long ws_m, long ws_c, int act, float slope,
+                           const float *alpha, int post_act, float post_slope, const float *post_x,
+                           const float *post_alpha, void *stream);
+int rave_conv1d_scatter_f32(const float *src, const float *w, const float *bias, const float *res,
+                            float *out, int B, int Cs, int Ls, int Cm, int Lo, int K, int stride,
+                            int dil, int pad_l, long ws_m, long ws_c, int act, float slope,
+                            const float *alpha, int post_act, float post_slope, const float *post_x,
+                            const float *post_alpha, void *stream);
+
+/* weight gradient:
+ *   dw[a*os_a + c*os_c + k] = sum_b sum_{l<Lp} actP(P[b][a][l]) * actQ(Q[b][c][l*stride + k*dil - pad_l])
+ *   P: [B][Ca][Lp] (indexed at l), Q: [B][Cc][Lq] (indexed at the shifted position).
+ *   For Conv1d: P = dy, Q = x (act on Q).  For ConvTranspose1d: P = x (act on P), Q = dy.
+ *   `workspace` must hold rave_conv1d_wgrad_workspace_bytes(...) bytes; the split-K partials are
+ *   reduced in a fixed order (deterministic). */
+size_t rave_conv1d_wgrad_workspace_bytes(int B, int Ca, int Cc, int Lp, int K);
+int rave_conv1d_wgrad_f32(const float *P, const float *Q, float *dw, int B, int Ca, int Lp, int Cc,
+                          int Lq, int K, int stride, int dil, int pad_l, long os_a, long os_c,
+                          int act_p, int act_q, float slope, const float *alpha, void *workspace,
+                          void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * weight norm (replaces torch._weight_norm, rave/blocks.py:15-22): w = g * v / ||v||, the norm
+ * over all dims but 0.  v: [C0][R], g: [C0], w: [C0][R], norm_out: [C0] (saved for backward).
+ * backward: dv = (g/n) * (dw - v * <dw,v>/n^2),  dg = <dw,v>/n.
+ * ------------------------------------------------------------------------------------------- */
+int rave_weight_norm_fwd(const float *v, const float *g, float *w, float *norm_out, int C0, int R,
+                         void *stream);
+int rave_weight_norm_bwd(const float *dw, const float *v, const float *g, const float *norm,
+                         float *dv, float *dg, int C0, int R, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * elementwise pieces that are not absorbed by a conv prologue/epilogue
+ * ------------------------------------------------------------------------------------------- */
+/* y = act(x); x,y: [B][C][L] */
+int rave_act_fwd(const float *x, float *y, int B, int C, int L, int act, float slope,
+                 const float *alpha, void *stream);
+/* dx = dy * act'(x); for Snake also dalpha[c] = sum_{b,t} dy * d act/d alpha (dalpha: [C], overwritten) */
+int rave_act_bwd(const float *dy, const float *x, float *dx, float *dalpha, int B, int C, int L,
+                 int act, float slope, const float *alpha, void *stream);
+/* GeneratorV2 tail (rave/blocks.py:704-711): y[b][c][t] = tanh(x[b][c][t] * sigmoid(x[b][C+c][t])); x: [B][2C][L] */
+int rave_am_tanh_fwd(const float *x, float *y, int B, int C, int L, void *stream);
+int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, int L, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * tensor-core conv engine (tcgen05 + TMEM + TMA), implicit GEMM, time on the MMA M axis:
+ *   D[l][co] = sum_k sum_ci A_k[l][ci] * W_k[co][ci],  A_k = shifted view of act-ed input.
+ * See DESIGN.md section "tcgen05 conv engine".  Operands are bf16 (prec 1).  Input `xa` is the
+ * ALREADY ACTIVATED operand tensor [B][Cin][Lin] in bf16 produced by the previous kernel's
+ * epilogue; `wt` is the tap-major bf16 weight [K][Cout][Cin].  Epilogue: + bias, + res (fp32),
+ * write `out_f32` (optional), write `out_act_bf16` = act(out) (optional).
+ * ------------------------------------------------------------------------------------------- */
+int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dil);
+int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bias, const float *res,
+                       float *out_f32, void *out_act_bf16, int B, int Cin, int Lin, int Cout, int Lout,
+                       int K, int stride, int dil, int pad_l, int act, float slope, void *stream);
+/* fp32 -> bf16 operand preparation: y = bf16(act(x)) */
+int rave_act_to_bf16(const float *x, void *y_bf16, int B, int C, int L, int act, float slope,
+                     const float *alpha, void *stream);
+/* weight re-layout: w[Cout][Cin][K] fp32 (or transposed-conv [Cin][Cout][K] with transpose=1)
+ * -> wt[K][Cout][Cin] bf16 */
+int rave_weight_to_tapmajor_bf16(const float *w, void *wt_bf16, int Cout, int Cin, int K, int transpose,
+                                 int flip, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAVE_B200_H */

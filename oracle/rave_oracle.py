@@ -556,3 +556,51 @@ def v2_small_config(**kw) -> ArchConfig:
     base = dict(capacity=48, ratios=(4, 2, 2, 2))
     base.update(kw)
     return ArchConfig(**base)
+
+
+# ----------------------------------------------------------------------------------
+# CPU training-step arithmetic (bench.py cpu_baseline / --impl reference) ----------
+# ----------------------------------------------------------------------------------
+
+
+def train_step_losses(x: Tensor, sd, cfg: ArchConfig, eps: Tensor, warmed_up: bool = True,
+                      beta: float = 1.0, fm_weight: float = 20.0):
+    """Forward arithmetic of RAVE.training_step (rave/model.py:292-399) for the v2 family,
+    returning (loss_gen_total, loss_dis).  Quirk D1 (weights applied twice) included."""
+    hk = sd["pqmf.hk"]
+    x_mb = pqmf_encode(x, hk, cfg.pad_mode)
+    z = encoder_v2(x_mb, sd, "encoder.encoder.", cfg)
+    if warmed_up:
+        z = z.detach()                                   # blocks.py:743-744
+    zs, reg = reparametrize(z, eps)
+    y_mb = generator_v2(zs, sd, "decoder.", cfg)
+    y = pqmf_decode(y_mb, hk, cfg.n_channels, cfg.pad_mode)
+    losses = {
+        "multiband_spectral_distance": audio_distance_v1(x_mb, y_mb),
+        "fullband_spectral_distance": audio_distance_v1(x, y),
+        "regularization": reg * beta,
+    }
+    loss_dis = torch.zeros(())
+    if warmed_up:
+        feats = combine_discriminators_v2(torch.cat([x, y], 0), sd)
+        fm, loss_dis, loss_adv = gan_losses(feats, 1, True)
+        losses["feature_matching"] = fm_weight * fm
+        losses["adversarial"] = loss_adv
+    weights = {"feature_matching": fm_weight}
+    total = sum(v * weights.get(k, 1.0) for k, v in losses.items())
+    return total, loss_dis
+
+
+def train_step_cpu(x: Tensor, sd, cfg: ArchConfig, eps: Tensor, dis_step: bool):
+    """One forward+backward of the reference's phase-2 step on CPU via autograd (no optimiser
+    state: the timing baseline counts the same fwd+bwd work the GPU arm does)."""
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and not k.startswith("pqmf."))
+              for k, v in sd.items()}
+    total, loss_dis = train_step_losses(x, params, cfg, eps, True)
+    if dis_step:
+        ps = [v for k, v in params.items() if k.startswith("discriminator.") and v.requires_grad]
+        grads = torch.autograd.grad(loss_dis, ps, allow_unused=True)
+    else:
+        ps = [v for k, v in params.items() if k.startswith("decoder.") and v.requires_grad]
+        grads = torch.autograd.grad(total, ps, allow_unused=True)
+    return total.detach(), loss_dis.detach(), grads

@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI declared in include/rave_b200.h.
+
+This is the stub a maintainer of the reference would add: every device
+computation of the hot path goes through one of these entry points.  There is NO fallback: if
+`librave_b200.so` is missing, or a tensor is not on a CUDA device, the call raises.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_long, c_size_t, c_ulonglong, c_void_p, c_char_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librave_b200.so")
+
+_P, _I, _F, _L = c_void_p, c_int, c_float, c_long
+
+# name -> (restype, argtypes); must list every symbol of include/rave_b200.h
+SIGNATURES = {
+    "rave_b200_version": (c_int, []),
+    "rave_b200_last_error": (c_char_p, []),
+    "rave_b200_launch_count": (c_ulonglong, []),
+    "rave_pqmf_analysis_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "rave_pqmf_synthesis_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "rave_conv1d_gather_f32": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L,
+                                       _I, _F, _P, _I, _F, _P, _P, _P]),
+    "rave_conv1d_scatter_f32": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L,
+                                        _I, _F, _P, _I, _F, _P, _P, _P]),
+    "rave_conv1d_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I]),
+    "rave_conv1d_wgrad_f32": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _I, _I,
+                                      _F, _P, _P, _P]),
+    "rave_weight_norm_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "rave_weight_norm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "rave_act_fwd": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P]),
+    "rave_act_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
+    "rave_am_tanh_fwd": (c_int, [_P, _P, _I, _I, _I, _P]),
+    "rave_am_tanh_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "rave_conv1d_tc_supported": (c_int, [_I, _I, _I, _I, _I]),
+    "rave_conv1d_tc_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "rave_act_to_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P]),
+    "rave_weight_to_tapmajor_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+}
+
+_lib = None
+
+
+class RaveB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load librave_b200.so (once). Raises if it has not been built: there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RaveB200Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(rave_b200 has no CPU or PyTorch fallback)")
+    import torch  # noqa: F401  (makes libcudart.so.12 resident before our library asks for it)
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().rave_b200_last_error().decode()
+
+
+def launch_count() -> int:
+    return int(load().rave_b200_launch_count())
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point; non-zero -> RuntimeError with the library's message."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RaveB200Error(f"{name} failed (rc={rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Refuses host tensors: no CPU fallback."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RaveB200Error("rave_b200 ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RaveB200Error("rave_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,388 @@
+"""Encoder / generator / latent-head modules -- the module surface of rave/blocks.py with the
+arithmetic on librave_b200.so.
+
+Class names, constructor arguments, sub-module layout (hence `state_dict` keys: SURVEY.md
+App. B.3) and call signatures follow the reference so that `RAVE(...)` can be assembled from the
+same bindings; `forward` never touches an ATen conv: every `activation -> conv (-> + skip)` group
+is one kernel launch (see cc.CachedSequential / Residual).
+"""
+from typing import Callable, Optional, Sequence, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.utils.weight_norm import WeightNorm
+
+from . import cc, ops
+from ._lib import RaveB200Error
+
+
+# ---------------------------------------------------------------------------------------------
+# normalization (rave/blocks.py:15-22; configs/v1.gin:41 binds mode='weight_norm')
+# ---------------------------------------------------------------------------------------------
+
+class _config:
+    normalization_mode = "weight_norm"
+
+
+class CudaWeightNorm(WeightNorm):
+    """torch.nn.utils.weight_norm's hook object with `compute_weight` on our kernel.  Being a
+    `WeightNorm` instance keeps `torch.nn.utils.remove_weight_norm` working
+    (tests/test_configs.py:87-89, scripts/export.py:561-563)."""
+
+    def compute_weight(self, module):
+        g = getattr(module, self.name + "_g")
+        v = getattr(module, self.name + "_v")
+        return ops.weight_norm(v, g)
+
+    @staticmethod
+    def apply(module, name: str = "weight", dim: int = 0):
+        if dim != 0:
+            raise RaveB200Error("weight_norm: only dim=0 is on the hot path")
+        for hook in module._forward_pre_hooks.values():
+            if isinstance(hook, WeightNorm) and hook.name == name:
+                raise RuntimeError(f"Cannot register two weight_norm hooks on the same parameter {name}")
+        fn = CudaWeightNorm(name, dim)
+        weight = getattr(module, name)
+        del module._parameters[name]
+        with torch.no_grad():
+            g = torch.norm_except_dim(weight, 2, dim)   # initialisation only (g = ||v||)
+        module.register_parameter(name + "_g", nn.Parameter(g.data))
+        module.register_parameter(name + "_v", nn.Parameter(weight.data))
+        setattr(module, name, weight.data)               # w == v at init; recomputed every forward
+        module.register_forward_pre_hook(fn)
+        return fn
+
+
+def weight_norm(module: nn.Module, name: str = "weight", dim: int = 0) -> nn.Module:
+    CudaWeightNorm.apply(module, name, dim)
+    return module
+
+
+def normalization(module: nn.Module, mode: Optional[str] = None):
+    mode = mode if mode is not None else _config.normalization_mode
+    if mode == "identity":
+        return module
+    elif mode == "weight_norm":
+        return weight_norm(module)
+    raise Exception(f"Normalization mode {mode} not supported")
+
+
+# ---------------------------------------------------------------------------------------------
+# activations
+# ---------------------------------------------------------------------------------------------
+
+class Snake(nn.Module):
+    """x + sin^2(alpha x) / (alpha + 1e-9), alpha [dim, 1] (rave/blocks.py:852-860)."""
+
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(dim, 1))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.activation(x, ops.ACT_SNAKE, 0.0, self.alpha.reshape(-1))
+
+
+def leaky_relu(dim: int, alpha: float):
+    return nn.LeakyReLU(alpha)
+
+
+def _default_activation(dim):
+    return nn.LeakyReLU(.2)
+
+
+class AdaptiveInstanceNormalization(nn.Module):
+    """Identity in training (rave/blocks.py:901-902); holds the reference's buffers so that v3
+    state_dicts load (the running statistics are only used by the export-time style transfer)."""
+
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        for s in ("x", "y"):
+            self.register_buffer(f"mean_{s}", torch.zeros(cc.MAX_BATCH_SIZE, dim, 1))
+            self.register_buffer(f"std_{s}", torch.ones(cc.MAX_BATCH_SIZE, dim, 1))
+            self.register_buffer(f"learn_{s}", torch.zeros(1))
+            self.register_buffer(f"num_update_{s}", torch.zeros(1))
+
+    def update(self, target, source, num_updates):
+        bs = source.shape[0]
+        target[:bs] += (source - target[:bs]) / (num_updates + 1)
+
+    def reset_x(self):
+        self.mean_x.zero_()
+        self.std_x.zero_().add_(1)
+        self.num_update_x.zero_()
+
+    def reset_y(self):
+        self.mean_y.zero_()
+        self.std_y.zero_().add_(1)
+        self.num_update_y.zero_()
+
+    def transfer(self, x):
+        bs = x.shape[0]
+        x = (x - self.mean_x[:bs]) / (self.std_x[:bs] + 1e-5)
+        return x * self.std_y[:bs] + self.mean_y[:bs]
+
+    def forward(self, x):
+        if self.training:
+            return x
+        if self.learn_y:
+            self.update(self.mean_y, x.mean(-1, keepdim=True), self.num_update_y)
+            self.update(self.std_y, x.std(-1, keepdim=True), self.num_update_y)
+            self.num_update_y += 1
+            return x
+        if self.learn_x:
+            self.update(self.mean_x, x.mean(-1, keepdim=True), self.num_update_x)
+            self.update(self.std_x, x.std(-1, keepdim=True), self.num_update_x)
+            self.num_update_x += 1
+        if self.num_update_x and self.num_update_y:
+            x = self.transfer(x)
+        return x
+
+
+# ---------------------------------------------------------------------------------------------
+# residual dilated units (rave/blocks.py:31-45, 83-112)
+# ---------------------------------------------------------------------------------------------
+
+class Residual(nn.Module):
+    """x + module(x).  When `module` is a DilatedUnit the skip add is fused into the epilogue of
+    the unit's last conv kernel."""
+
+    def __init__(self, module, cumulative_delay=0):
+        super().__init__()
+        additional_delay = module.cumulative_delay
+        self.aligned = cc.AlignBranches(module, nn.Identity(), delays=[additional_delay, 0])
+        self.cumulative_delay = additional_delay + cumulative_delay
+
+    def forward(self, x):
+        module = self.aligned.branches[0]
+        if isinstance(module, DilatedUnit):
+            return module(x, res=x)
+        x_net, x_res = self.aligned(x)
+        return x_net + x_res
+
+
+class DilatedUnit(nn.Module):
+    """act -> Conv1d(dim, dim, k, dilation) -> act -> Conv1d(dim, dim, 1)."""
+
+    def __init__(self, dim: int, kernel_size: int, dilation: int,
+                 activation: Callable[[int], nn.Module] = _default_activation) -> None:
+        super().__init__()
+        net = [
+            activation(dim),
+            normalization(cc.Conv1d(dim, dim, kernel_size=kernel_size, dilation=dilation,
+                                    padding=cc.get_padding(kernel_size, dilation=dilation))),
+            activation(dim),
+            normalization(cc.Conv1d(dim, dim, kernel_size=1)),
+        ]
+        self.net = cc.CachedSequential(*net)
+        self.cumulative_delay = net[1].cumulative_delay
+
+    def forward(self, x: torch.Tensor, res: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.net(x, res=res)
+
+
+def normalize_dilations(dilations, ratios):
+    if isinstance(dilations[0], int):
+        dilations = [dilations for _ in ratios]
+    return dilations
+
+
+# ---------------------------------------------------------------------------------------------
+# EncoderV2 / GeneratorV2 (rave/blocks.py:514-714)
+# ---------------------------------------------------------------------------------------------
+
+class EncoderV2(nn.Module):
+
+    def __init__(self, data_size: Union[int, None], capacity: int, ratios: Sequence[int],
+                 latent_size: int, n_out: int, kernel_size: int, dilations: Sequence[int],
+                 keep_dim: bool = False, recurrent_layer: Optional[Callable[[], nn.Module]] = None,
+                 n_channels: int = 1,
+                 activation: Callable[[int], nn.Module] = _default_activation,
+                 adain: Optional[Callable[[int], nn.Module]] = None, spectrogram=None,
+                 unit_activation: Optional[Callable[[int], nn.Module]] = None) -> None:
+        super().__init__()
+        dilations_list = normalize_dilations(dilations, ratios)
+        data_size = data_size or n_channels
+        # configs/snake.gin:10-11 rebinds DilatedUnit.activation together with the encoder's
+        unit_activation = unit_activation or activation
+
+        net = [
+            normalization(cc.Conv1d(data_size * n_channels, capacity, kernel_size=kernel_size * 2 + 1,
+                                    padding=cc.get_padding(kernel_size * 2 + 1))),
+        ]
+        num_channels = capacity
+        for r, dils in zip(ratios, dilations_list):
+            for d in dils:
+                if adain is not None:
+                    net.append(adain(dim=num_channels))
+                net.append(Residual(DilatedUnit(dim=num_channels, kernel_size=kernel_size, dilation=d,
+                                                activation=unit_activation)))
+            net.append(activation(num_channels))
+            out_channels = num_channels * r if keep_dim else num_channels * 2
+            net.append(normalization(cc.Conv1d(num_channels, out_channels, kernel_size=2 * r, stride=r,
+                                               padding=cc.get_padding(2 * r, r))))
+            num_channels = out_channels
+
+        net.append(activation(num_channels))
+        net.append(normalization(cc.Conv1d(num_channels, latent_size * n_out, kernel_size=kernel_size,
+                                           padding=cc.get_padding(kernel_size))))
+        if recurrent_layer is not None:
+            net.append(recurrent_layer(latent_size * n_out))
+        self.net = cc.CachedSequential(*net)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.net(x)
+
+
+class GeneratorV2(nn.Module):
+
+    def __init__(self, capacity: int, ratios: Sequence[int], latent_size: int, kernel_size: int,
+                 dilations: Sequence[int], keep_dim: bool = False, data_size: Union[int, None] = None,
+                 recurrent_layer: Optional[Callable[[], nn.Module]] = None, n_channels: int = 1,
+                 amplitude_modulation: bool = False, noise_module=None,
+                 activation: Callable[[int], nn.Module] = _default_activation,
+                 adain: Optional[Callable[[int], nn.Module]] = None,
+                 unit_activation: Optional[Callable[[int], nn.Module]] = None) -> None:
+        super().__init__()
+        data_size = n_channels if data_size is None else data_size * n_channels
+        dilations_list = normalize_dilations(dilations, ratios)[::-1]
+        ratios = ratios[::-1]
+        unit_activation = unit_activation or activation
+        if keep_dim:
+            num_channels = int(np.prod(ratios)) * capacity
+        else:
+            num_channels = 2 ** len(ratios) * capacity
+
+        net = []
+        if recurrent_layer is not None:
+            net.append(recurrent_layer(latent_size))
+        net.append(normalization(cc.Conv1d(latent_size, num_channels, kernel_size=kernel_size,
+                                           padding=cc.get_padding(kernel_size))))
+        for r, dils in zip(ratios, dilations_list):
+            out_channels = num_channels // r if keep_dim else num_channels // 2
+            net.append(activation(num_channels))
+            net.append(normalization(cc.ConvTranspose1d(num_channels, out_channels, 2 * r, stride=r,
+                                                        padding=r // 2)))
+            num_channels = out_channels
+            for d in dils:
+                if adain is not None:
+                    net.append(adain(num_channels))
+                net.append(Residual(DilatedUnit(dim=num_channels, kernel_size=kernel_size, dilation=d,
+                                                activation=unit_activation)))
+        net.append(activation(num_channels))
+
+        waveform_module = normalization(
+            cc.Conv1d(num_channels, data_size * 2 if amplitude_modulation else data_size,
+                      kernel_size=kernel_size * 2 + 1, padding=cc.get_padding(kernel_size * 2 + 1)))
+
+        self.noise_module = None
+        self.waveform_module = None
+        if noise_module is not None:
+            self.waveform_module = waveform_module
+            self.noise_module = noise_module(out_channels, n_channels=n_channels)
+        else:
+            net.append(waveform_module)
+        self.net = cc.CachedSequential(*net)
+        self.amplitude_modulation = amplitude_modulation
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.net(x)
+        noise = 0.
+        if self.noise_module is not None:
+            noise = self.noise_module(x)
+            x = self.waveform_module(x)
+        if self.amplitude_modulation and self.noise_module is None:
+            return ops.am_tanh(x)                       # x*sigmoid(a) -> tanh, one kernel
+        if self.amplitude_modulation:
+            x, amplitude = x.split(x.shape[1] // 2, 1)
+            x = x * torch.sigmoid(amplitude)
+        x = x + noise
+        return torch.tanh(x)
+
+    def set_warmed_up(self, state: bool):
+        pass
+
+
+# ---------------------------------------------------------------------------------------------
+# latent heads (rave/blocks.py:717-745, 794-850)
+# ---------------------------------------------------------------------------------------------
+
+class VariationalEncoder(nn.Module):
+
+    def __init__(self, encoder, beta: float = 1.0, n_channels=1):
+        super().__init__()
+        self.encoder = encoder(n_channels=n_channels)
+        self.beta = beta
+        self.register_buffer("warmed_up", torch.tensor(0))
+
+    def reparametrize(self, z, eps: Optional[torch.Tensor] = None):
+        """`eps` lets a caller inject the noise (parity tests; the CPU and CUDA Philox streams
+        differ); default draws it like the reference (blocks.py:731)."""
+        mean, scale = z.chunk(2, 1)
+        std = nn.functional.softplus(scale) + 1e-4
+        var = std * std
+        logvar = torch.log(var)
+        if eps is None:
+            eps = torch.randn_like(mean)
+        z = eps * std + mean
+        kl = (mean * mean + var - logvar - 1).sum(1).mean()
+        return z, self.beta * kl
+
+    def set_warmed_up(self, state: bool):
+        state = torch.tensor(int(state), device=self.warmed_up.device)
+        self.warmed_up = state
+
+    def forward(self, x: torch.Tensor):
+        z = self.encoder(x)
+        if self.warmed_up:
+            z = z.detach()
+        return z
+
+
+class SphericalEncoder(nn.Module):
+
+    def __init__(self, encoder_cls, n_channels: int = 1) -> None:
+        super().__init__()
+        self.encoder = encoder_cls(n_channels=n_channels)
+
+    def reparametrize(self, z):
+        norm_z = z / torch.norm(z, p=2, dim=1, keepdim=True)
+        return norm_z, torch.zeros_like(z).mean()
+
+    def set_warmed_up(self, state: bool):
+        pass
+
+    def forward(self, x):
+        return self.encoder(x)
+
+
+class DiscreteEncoder(nn.Module):
+    """rave/blocks.py:794-830 (quirk D3: `enabled` is never switched on by the reference's own
+    training code, so RVQ is bypassed unless the caller sets it)."""
+
+    def __init__(self, encoder_cls, vq_cls, num_quantizers, noise_augmentation: int = 0,
+                 n_channels: int = 1):
+        super().__init__()
+        self.encoder = encoder_cls(n_channels=n_channels)
+        self.rvq = vq_cls()
+        self.num_quantizers = num_quantizers
+        self.register_buffer("warmed_up", torch.tensor(0))
+        self.register_buffer("enabled", torch.tensor(0))
+        self.noise_augmentation = noise_augmentation
+
+    def reparametrize(self, z):
+        if self.enabled:
+            z, diff, _ = self.rvq(z)
+        else:
+            diff = torch.zeros_like(z).mean()
+        if self.noise_augmentation:
+            noise = torch.randn(z.shape[0], self.noise_augmentation, z.shape[-1]).type_as(z)
+            z = torch.cat([z, noise], 1)
+        return z, diff
+
+    def set_warmed_up(self, state: bool):
+        state = torch.tensor(int(state), device=self.warmed_up.device)
+        self.warmed_up = state
+
+    def forward(self, x):
+        return self.encoder(x)

@@ -1,0 +1,130 @@
+"""Loss helpers -- the subset of rave/core.py the training step calls (SURVEY.md section 8f.1,
+a "next" row: cuFFT-backed `torch.stft` + elementwise reductions run on the device through
+PyTorch for now; the conv / PQMF hot path they consume is native).
+"""
+from typing import Callable, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+
+def mod_sigmoid(x):
+    return 2 * torch.sigmoid(x) ** 2.3 + 1e-7
+
+
+def get_augmented_latent_size(latent_size: int, noise_augmentation: int):
+    return latent_size + noise_augmentation
+
+
+def hinge_gan(score_real, score_fake):
+    """rave/core.py:151-155."""
+    loss_dis = (torch.relu(1 - score_real) + torch.relu(1 + score_fake)).mean()
+    loss_gen = -score_fake.mean()
+    return loss_dis, loss_gen
+
+
+def ls_gan(score_real, score_fake):
+    loss_dis = ((score_real - 1).pow(2) + score_fake.pow(2)).mean()
+    loss_gen = (score_fake - 1).pow(2).mean()
+    return loss_dis, loss_gen
+
+
+def nonsaturating_gan(score_real, score_fake):
+    score_real = torch.clamp(torch.sigmoid(score_real), 1e-7, 1 - 1e-7)
+    score_fake = torch.clamp(torch.sigmoid(score_fake), 1e-7, 1 - 1e-7)
+    loss_dis = -(torch.log(score_real) + torch.log(1 - score_fake)).mean()
+    loss_gen = -torch.log(score_fake).mean()
+    return loss_dis, loss_gen
+
+
+def valid_signal_crop(x, left_rf, right_rf):
+    """rave/core.py:220-225."""
+    dim = x.shape[1]
+    x = x[..., left_rf.item() // dim:]
+    if right_rf.item():
+        x = x[..., :-right_rf.item() // dim]
+    return x
+
+
+def mean_difference(target, value, norm: str = "L1", relative: bool = False):
+    """rave/core.py:236-252."""
+    diff = target - value
+    if norm == "L1":
+        diff = diff.abs().mean()
+        if relative:
+            diff = diff / target.abs().mean()
+        return diff
+    elif norm == "L2":
+        diff = (diff * diff).mean()
+        if relative:
+            diff = diff / (target * target).mean()
+        return diff
+    raise Exception(f"Norm must be either L1 or L2, got {norm}")
+
+
+class MultiScaleSTFT(nn.Module):
+    """rave/core.py:269-319 (magnitude spectrogram, hann window, hop = n_fft/4, centred)."""
+
+    def __init__(self, scales: Sequence[int], sample_rate: int, magnitude: bool = True,
+                 normalized: bool = False, num_mels: Optional[int] = None) -> None:
+        super().__init__()
+        if num_mels is not None:
+            raise NotImplementedError("mel scales need librosa, absent here; not used by v2/v3/discrete")
+        self.scales = scales
+        self.magnitude = magnitude
+        self.normalized = normalized
+        for s in scales:
+            self.register_buffer(f"window_{s}", torch.hann_window(s), persistent=False)
+
+    def forward(self, x):
+        x = x.reshape(-1, x.shape[-1])
+        out = []
+        for s in self.scales:
+            y = torch.stft(x, s, hop_length=s // 4, win_length=s, window=getattr(self, f"window_{s}"),
+                           center=True, pad_mode="reflect", normalized=self.normalized, onesided=True,
+                           return_complex=True)
+            out.append(y.abs() if self.magnitude else torch.stack([y.real, y.imag], -1))
+        return out
+
+
+class AudioDistanceV1(nn.Module):
+    """rave/core.py:322-344."""
+
+    def __init__(self, multiscale_stft: Callable[[], nn.Module], log_epsilon: float) -> None:
+        super().__init__()
+        self.multiscale_stft = multiscale_stft()
+        self.log_epsilon = log_epsilon
+
+    def forward(self, x, y):
+        stfts_x = self.multiscale_stft(x)
+        stfts_y = self.multiscale_stft(y)
+        distance = 0.
+        for sx, sy in zip(stfts_x, stfts_y):
+            logx = torch.log(sx + self.log_epsilon)
+            logy = torch.log(sy + self.log_epsilon)
+            distance = distance + mean_difference(sx, sy, norm="L2", relative=True) \
+                + mean_difference(logx, logy, norm="L1")
+        return {"spectral_distance": distance}
+
+
+@torch.enable_grad()
+def get_rave_receptive_field(model, n_channels=1):
+    """rave/core.py:180-217: autograd probe of the input gradient's support."""
+    N = 2 ** 15
+    model.eval()
+    device = next(iter(model.parameters())).device
+    while True:
+        x = torch.randn(1, model.n_channels, N, requires_grad=True, device=device)
+        z = model.encode(x)
+        z = model.encoder.reparametrize(z)[0]
+        y = model.decode(z)
+        y[0, 0, N // 2].backward()
+        grad = x.grad.data.reshape(-1)
+        left_grad, right_grad = grad.chunk(2, 0)
+        if (left_grad[0] == 0) and right_grad[-1] == 0:
+            break
+        N *= 2
+    left_rf = len(left_grad[left_grad != 0])
+    right_rf = len(right_grad[right_grad != 0])
+    model.zero_grad()
+    return left_rf, right_rf

@@ -1,0 +1,255 @@
+// Weight norm, stand-alone activations and the generator tail.
+//
+// Reference: torch.nn.utils.weight_norm via blocks.normalization (rave/blocks.py:15-22);
+// Snake (blocks.py:852-860); LeakyReLU(.2) (blocks.py:56,90,528,614); GeneratorV2 tail
+// x * sigmoid(a) -> tanh (blocks.py:704-711).
+#include "common.cuh"
+
+namespace rave {
+
+__device__ __forceinline__ float block_reduce_sum(float v, float *red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();  // protect `red` from a previous use
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+// one CTA per leading index c0
+__global__ void __launch_bounds__(256)
+weight_norm_fwd_kernel(const float *__restrict__ v, const float *__restrict__ g, float *__restrict__ w,
+                       float *__restrict__ norm_out, int R) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float *vr = v + (size_t)c * R;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    float x = vr[i];
+    s = fmaf(x, x, s);
+  }
+  const float n = sqrtf(block_reduce_sum(s, red));
+  const float scale = g[c] / n;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) w[(size_t)c * R + i] = vr[i] * scale;
+  if (threadIdx.x == 0 && norm_out) norm_out[c] = n;
+}
+
+__global__ void __launch_bounds__(256)
+weight_norm_bwd_kernel(const float *__restrict__ dw, const float *__restrict__ v,
+                       const float *__restrict__ g, const float *__restrict__ norm,
+                       float *__restrict__ dv, float *__restrict__ dg, int R) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float *vr = v + (size_t)c * R;
+  const float *dr = dw + (size_t)c * R;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) s = fmaf(dr[i], vr[i], s);
+  const float dot = block_reduce_sum(s, red);
+  const float n = norm[c];
+  const float gn = g[c] / n;
+  const float coef = dot / (n * n);
+  for (int i = threadIdx.x; i < R; i += blockDim.x) dv[(size_t)c * R + i] = gn * (dr[i] - vr[i] * coef);
+  if (threadIdx.x == 0) dg[c] = dot / n;
+}
+
+// grid: (ceil(L/1024), C, B)
+__global__ void __launch_bounds__(256)
+act_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int L, int act, float slope,
+               const float *__restrict__ alpha) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const float al = (act == RAVE_ACT_SNAKE) ? alpha[c] : 0.f;
+  const size_t base = ((size_t)b * C + c) * L;
+  for (int t = blockIdx.x * 1024 + threadIdx.x; t < min(L, (int)(blockIdx.x + 1) * 1024); t += 256)
+    y[base + t] = act_apply(x[base + t], act, slope, al);
+}
+
+// dx = dy * act'(x); Snake: dalpha[c] += sum dy * d/dalpha  (atomic over CTAs; dalpha pre-zeroed)
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dx,
+               float *__restrict__ dalpha, int C, int L, int act, float slope,
+               const float *__restrict__ alpha) {
+  __shared__ float red[32];
+  const int c = blockIdx.y, b = blockIdx.z;
+  const float al = (act == RAVE_ACT_SNAKE) ? alpha[c] : 0.f;
+  const size_t base = ((size_t)b * C + c) * L;
+  float s = 0.f;
+  for (int t = blockIdx.x * 1024 + threadIdx.x; t < min(L, (int)(blockIdx.x + 1) * 1024); t += 256) {
+    const float xv = x[base + t], g = dy[base + t];
+    dx[base + t] = g * act_grad(xv, act, slope, al);
+    if (act == RAVE_ACT_SNAKE) {
+      // d/dalpha [ sin^2(a x) / (a + eps) ] = x sin(2 a x)/(a+eps) - sin^2(a x)/(a+eps)^2
+      const float ae = al + 1e-9f;
+      const float sn = sinf(al * xv);
+      s += g * (xv * sinf(2.f * al * xv) / ae - sn * sn / (ae * ae));
+    }
+  }
+  if (act == RAVE_ACT_SNAKE && dalpha) {
+    const float tot = block_reduce_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(dalpha + c, tot);
+  }
+}
+
+// y[b][c][t] = tanh(x[b][c][t] * sigmoid(x[b][C+c][t]))
+__global__ void __launch_bounds__(256)
+am_tanh_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int L, long total) {
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const long bc = i / L;
+    const int t = (int)(i - bc * L);
+    const int b = (int)(bc / C), c = (int)(bc - (long)b * C);
+    const size_t xo = ((size_t)b * 2 * C + c) * L + t;
+    const float w = x[xo], a = x[xo + (size_t)C * L];
+    const float sg = 1.f / (1.f + expf(-a));
+    y[i] = tanhf(w * sg);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+am_tanh_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dx,
+                   int C, int L, long total) {
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const long bc = i / L;
+    const int t = (int)(i - bc * L);
+    const int b = (int)(bc / C), c = (int)(bc - (long)b * C);
+    const size_t xo = ((size_t)b * 2 * C + c) * L + t;
+    const float w = x[xo], a = x[xo + (size_t)C * L];
+    const float sg = 1.f / (1.f + expf(-a));
+    const float th = tanhf(w * sg);
+    const float g = dy[i] * (1.f - th * th);
+    dx[xo] = g * sg;
+    dx[xo + (size_t)C * L] = g * w * sg * (1.f - sg);
+  }
+}
+
+// y = bf16(act(x)); grid (ceil(L/2048), C, B), 2 elements per thread-iteration
+__global__ void __launch_bounds__(256)
+act_to_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, int C, int L, int act,
+                   float slope, const float *__restrict__ alpha) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const float al = (act == RAVE_ACT_SNAKE) ? alpha[c] : 0.f;
+  const size_t base = ((size_t)b * C + c) * L;
+  const int t_end = min(L, (int)(blockIdx.x + 1) * 2048);
+  for (int t = blockIdx.x * 2048 + threadIdx.x; t < t_end; t += 256)
+    y[base + t] = __float2bfloat16_rn(act_apply(x[base + t], act, slope, al));
+}
+
+// w[Cout][Cin][K] (transpose=0) or w[Cin][Cout][K] (transpose=1) -> wt[K][Cout][Cin] bf16;
+// flip=1 reverses the tap order (dgrad of a stride-1 conv is a conv with flipped taps).
+__global__ void __launch_bounds__(256)
+weight_tapmajor_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wt, int Cout, int Cin,
+                       int K, int transpose, int flip) {
+  const long total = (long)K * Cout * Cin;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int ci = (int)(i % Cin);
+    const long r = i / Cin;
+    const int co = (int)(r % Cout);
+    const int k = (int)(r / Cout);
+    const int ks = flip ? (K - 1 - k) : k;
+    const size_t src = transpose ? ((size_t)ci * Cout + co) * K + ks : ((size_t)co * Cin + ci) * K + ks;
+    wt[i] = __float2bfloat16_rn(w[src]);
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_weight_norm_fwd(const float *v, const float *g, float *w, float *norm_out, int C0,
+                                    int R, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(v && g && w, "weight_norm_fwd: null pointer");
+  RAVE_CHECK_ARG(C0 > 0 && R > 0, "weight_norm_fwd: bad shape");
+  weight_norm_fwd_kernel<<<C0, 256, 0, (cudaStream_t)stream>>>(v, g, w, norm_out, R);
+  RAVE_CHECK_LAUNCH("weight_norm_fwd");
+  return 0;
+}
+
+extern "C" int rave_weight_norm_bwd(const float *dw, const float *v, const float *g, const float *norm,
+                                    float *dv, float *dg, int C0, int R, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(dw && v && g && norm && dv && dg, "weight_norm_bwd: null pointer");
+  RAVE_CHECK_ARG(C0 > 0 && R > 0, "weight_norm_bwd: bad shape");
+  weight_norm_bwd_kernel<<<C0, 256, 0, (cudaStream_t)stream>>>(dw, v, g, norm, dv, dg, R);
+  RAVE_CHECK_LAUNCH("weight_norm_bwd");
+  return 0;
+}
+
+extern "C" int rave_act_fwd(const float *x, float *y, int B, int C, int L, int act, float slope,
+                            const float *alpha, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && y, "act_fwd: null pointer");
+  RAVE_CHECK_ARG(B > 0 && C > 0 && L > 0 && B <= 65535 && C <= 65535, "act_fwd: bad shape");
+  RAVE_CHECK_ARG(act != RAVE_ACT_SNAKE || alpha, "act_fwd: snake needs alpha");
+  dim3 grid(ceil_div(L, 1024), C, B);
+  act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, C, L, act, slope, alpha);
+  RAVE_CHECK_LAUNCH("act_fwd");
+  return 0;
+}
+
+extern "C" int rave_act_bwd(const float *dy, const float *x, float *dx, float *dalpha, int B, int C,
+                            int L, int act, float slope, const float *alpha, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(dy && x && dx, "act_bwd: null pointer");
+  RAVE_CHECK_ARG(B > 0 && C > 0 && L > 0 && B <= 65535 && C <= 65535, "act_bwd: bad shape");
+  RAVE_CHECK_ARG(act != RAVE_ACT_SNAKE || alpha, "act_bwd: snake needs alpha");
+  if (act == RAVE_ACT_SNAKE && dalpha) cudaMemsetAsync(dalpha, 0, sizeof(float) * C, (cudaStream_t)stream);
+  dim3 grid(ceil_div(L, 1024), C, B);
+  act_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, x, dx, dalpha, C, L, act, slope, alpha);
+  RAVE_CHECK_LAUNCH("act_bwd");
+  return 0;
+}
+
+extern "C" int rave_am_tanh_fwd(const float *x, float *y, int B, int C, int L, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && y && B > 0 && C > 0 && L > 0, "am_tanh_fwd: bad argument");
+  const long total = (long)B * C * L;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  am_tanh_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, C, L, total);
+  RAVE_CHECK_LAUNCH("am_tanh_fwd");
+  return 0;
+}
+
+extern "C" int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, int L,
+                                void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(dy && x && dx && B > 0 && C > 0 && L > 0, "am_tanh_bwd: bad argument");
+  const long total = (long)B * C * L;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  am_tanh_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, dx, C, L, total);
+  RAVE_CHECK_LAUNCH("am_tanh_bwd");
+  return 0;
+}
+
+extern "C" int rave_act_to_bf16(const float *x, void *y_bf16, int B, int C, int L, int act, float slope,
+                                const float *alpha, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && y_bf16, "act_to_bf16: null pointer");
+  RAVE_CHECK_ARG(B > 0 && C > 0 && L > 0 && B <= 65535 && C <= 65535, "act_to_bf16: bad shape");
+  RAVE_CHECK_ARG(act != RAVE_ACT_SNAKE || alpha, "act_to_bf16: snake needs alpha");
+  dim3 grid(ceil_div(L, 2048), C, B);
+  act_to_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)y_bf16, C, L, act, slope,
+                                                            alpha);
+  RAVE_CHECK_LAUNCH("act_to_bf16");
+  return 0;
+}
+
+extern "C" int rave_weight_to_tapmajor_bf16(const float *w, void *wt_bf16, int Cout, int Cin, int K,
+                                            int transpose, int flip, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(w && wt_bf16 && Cout > 0 && Cin > 0 && K > 0, "weight_to_tapmajor: bad argument");
+  const long total = (long)K * Cout * Cin;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  weight_tapmajor_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16 *)wt_bf16, Cout, Cin,
+                                                                  K, transpose, flip);
+  RAVE_CHECK_LAUNCH("weight_to_tapmajor");
+  return 0;
+}

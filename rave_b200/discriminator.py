@@ -1,0 +1,141 @@
+"""v1/v2 discriminators -- module surface of rave/discriminator.py:77-209 on librave_b200.so.
+
+`ConvNet` accepts the same `conv` argument the reference's gin files bind (`@torch.nn.Conv1d`,
+`@nn.Conv2d` with kernel (5,1): configs/v1.gin:84-86, configs/v2.gin:53-55) and maps it to a
+subclass with identical parameters / state_dict keys whose forward launches our kernels.  A
+(k,1) Conv2d over the folded signal [B,C,L/p,p] is a Conv1d along L/p with the period axis as
+extra batch: the fold is kept as a *view* of a [B,p,C,L/p] tensor, so the only
+copy is the 1-channel input.
+"""
+from typing import Callable, Optional, Sequence, Type
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import cc, ops
+from .blocks import normalization
+from ._lib import RaveB200Error
+
+
+class DiscConv1d(nn.Conv1d):
+    """nn.Conv1d (symmetric int padding, bias) on the library kernels; optional fused pre-activation."""
+
+    def forward(self, x, act=None):
+        code = cc._act_code(act)
+        p = self.padding[0]
+        return ops.conv1d(x, self.weight, self.bias, None, self.stride[0], self.dilation[0], (p, p),
+                          code[0], code[1], None)
+
+
+class DiscConv2dK1(nn.Conv2d):
+    """nn.Conv2d with kernel (k,1), stride (s,1), padding (p,0): conv1d along H, W folded into batch.
+    Input/outputs are [B,C,H,W] tensors (the output is a permuted view of a [B,W,C,H'] buffer)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.kernel_size[1] != 1 or self.stride[1] != 1 or self.padding[1] != 0 or self.groups != 1:
+            raise RaveB200Error("only (k,1) 2-D convolutions are on the hot path")
+
+    def forward(self, x, act=None):
+        code = cc._act_code(act)
+        B, C, H, W = x.shape
+        xw = x.permute(0, 3, 1, 2).reshape(B * W, C, H)   # free when x came from a previous layer
+        p = self.padding[0]
+        y = ops.conv1d(xw, self.weight.squeeze(-1), self.bias, None, self.stride[0], self.dilation[0],
+                       (p, p), code[0], code[1], None)
+        return y.view(B, W, y.shape[1], y.shape[2]).permute(0, 2, 3, 1)
+
+
+def _map_conv(conv):
+    if conv is nn.Conv1d or conv is DiscConv1d:
+        return DiscConv1d
+    if conv is nn.Conv2d or conv is DiscConv2dK1:
+        return DiscConv2dK1
+    raise RaveB200Error(f"unsupported conv class for the discriminator hot path: {conv}")
+
+
+class ConvNet(nn.Module):
+    """rave/discriminator.py:77-119.  Features = PRE-activation output of every conv."""
+
+    def __init__(self, in_size, out_size, capacity, n_layers, kernel_size, stride, conv) -> None:
+        super().__init__()
+        conv = _map_conv(conv)
+        channels = [in_size]
+        channels += list(capacity * 2 ** np.arange(n_layers))
+        if isinstance(stride, int):
+            stride = n_layers * [stride]
+        net = []
+        for i in range(n_layers):
+            if not isinstance(kernel_size, int):
+                pad = (cc.get_padding(kernel_size[0], stride[i], mode="centered")[0], 0)
+                s = (stride[i], 1)
+            else:
+                pad = cc.get_padding(kernel_size, stride[i], mode="centered")[0]
+                s = stride[i]
+            net.append(normalization(conv(int(channels[i]), int(channels[i + 1]), kernel_size, stride=s,
+                                          padding=pad)))
+            net.append(nn.LeakyReLU(.2))
+        net.append(conv(int(channels[-1]), out_size, 1))
+        self.net = nn.Sequential(*net)
+
+    def forward(self, x):
+        features = []
+        pending_act = None
+        for layer in self.net:
+            if isinstance(layer, nn.LeakyReLU):
+                pending_act = layer            # fused into the next conv's operand load
+                continue
+            x = layer(x, act=pending_act)
+            pending_act = None
+            features.append(x)
+        return features
+
+
+class MultiScaleDiscriminator(nn.Module):
+    """rave/discriminator.py:122-136."""
+
+    def __init__(self, n_discriminators, convnet, n_channels=1) -> None:
+        super().__init__()
+        self.layers = nn.ModuleList([convnet(in_size=n_channels) for _ in range(n_discriminators)])
+
+    def forward(self, x):
+        features = []
+        for layer in self.layers:
+            features.append(layer(x))
+            x = nn.functional.avg_pool1d(x, 2)
+        return features
+
+
+class MultiPeriodDiscriminator(nn.Module):
+    """rave/discriminator.py:174-195."""
+
+    def __init__(self, periods, convnet, n_channels=1) -> None:
+        super().__init__()
+        self.periods = periods
+        self.layers = nn.ModuleList([convnet(in_size=n_channels) for _ in periods])
+
+    def forward(self, x):
+        features = []
+        for layer, n in zip(self.layers, self.periods):
+            features.append(layer(self.fold(x, n)))
+        return features
+
+    def fold(self, x, n):
+        pad = (n - (x.shape[-1] % n)) % n
+        x = nn.functional.pad(x, (0, pad))
+        return x.reshape(*x.shape[:2], -1, n)
+
+
+class CombineDiscriminators(nn.Module):
+    """rave/discriminator.py:198-209."""
+
+    def __init__(self, discriminators: Sequence[Type[nn.Module]], n_channels=1) -> None:
+        super().__init__()
+        self.discriminators = nn.ModuleList(disc_cls(n_channels=n_channels) for disc_cls in discriminators)
+
+    def forward(self, x):
+        features = []
+        for disc in self.discriminators:
+            features.extend(disc(x))
+        return features

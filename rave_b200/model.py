@@ -1,0 +1,330 @@
+"""`RAVE` -- the caller of the hot path (rave/model.py:133-511), without pytorch-lightning.
+
+`__init__`, `encode`, `decode`, `forward`, `split_features`, `configure_optimizers` and
+`training_step` keep the reference's signatures and arithmetic (including quirk D1, the loss
+weights applied twice, rave/model.py:397,410-411).  Work whose result the reference discards is
+not computed: the D-step does not back-propagate into the generator,
+the G-step does not accumulate discriminator weight gradients, and `x_raw` gets no gradient --
+parameter updates are identical.  `reg.item()` (quirk D7, a host sync per step) is replaced by
+adding the (possibly zero) KL term unconditionally: same value, no sync.
+"""
+import math
+from typing import Callable, Dict, Iterable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import blocks, core
+
+_default_loss_weights = {
+    "audio_distance": 1.,
+    "multiband_audio_distance": 1.,
+    "adversarial": 1.,
+    "feature_matching": 20,
+}
+
+
+def _pqmf_encode(pqmf, x: torch.Tensor):
+    """rave/model.py:116-122."""
+    batch_size = x.shape[:-2]
+    x_multiband = x.reshape(-1, 1, x.shape[-1])
+    x_multiband = pqmf(x_multiband)
+    return x_multiband.reshape(*batch_size, -1, x_multiband.shape[-1])
+
+
+def _pqmf_decode(pqmf, x: torch.Tensor, batch_size: Iterable[int], n_channels: int):
+    """rave/model.py:125-130."""
+    x = x.reshape(x.shape[0] * n_channels, -1, x.shape[-1])
+    x = pqmf.inverse(x)
+    return x.reshape(*batch_size, n_channels, -1)
+
+
+class WarmupCallback:
+    """rave/model.py:45-61."""
+
+    def __init__(self) -> None:
+        self.state = {"training_steps": 0}
+
+    def on_train_batch_start(self, trainer, pl_module, batch, batch_idx) -> None:
+        if self.state["training_steps"] >= pl_module.warmup:
+            pl_module.warmed_up = True
+        self.state["training_steps"] += 1
+
+    def state_dict(self):
+        return self.state.copy()
+
+    def load_state_dict(self, state_dict):
+        self.state.update(state_dict)
+
+
+class BetaWarmupCallback:
+    """rave/model.py:78-113."""
+
+    def __init__(self, initial_value: float = .2, target_value: float = .2, warmup_len: int = 1,
+                 log: bool = True) -> None:
+        self.state = {"training_steps": 0}
+        self.warmup_len = warmup_len
+        self.initial_value = initial_value
+        self.target_value = target_value
+        self.log_warmup = log
+
+    def on_train_batch_start(self, trainer, pl_module, batch, batch_idx) -> None:
+        self.state["training_steps"] += 1
+        if self.state["training_steps"] >= self.warmup_len:
+            pl_module.beta_factor = self.target_value
+            return
+        warmup_ratio = self.state["training_steps"] / self.warmup_len
+        if self.log_warmup:
+            beta = math.log(self.initial_value) * (1 - warmup_ratio) + math.log(self.target_value) * warmup_ratio
+            pl_module.beta_factor = math.exp(beta)
+        else:
+            beta = warmup_ratio * (self.target_value - self.initial_value) + self.initial_value
+            pl_module.beta_factor = min(beta, self.target_value)
+
+    def state_dict(self):
+        return self.state.copy()
+
+    def load_state_dict(self, state_dict):
+        self.state.update(state_dict)
+
+
+class RAVE(nn.Module):
+
+    def __init__(self, latent_size, sampling_rate, encoder, decoder, discriminator, phase_1_duration,
+                 gan_loss, valid_signal_crop, feature_matching_fun, num_skipped_features,
+                 audio_distance: Callable[[], nn.Module],
+                 multiband_audio_distance: Callable[[], nn.Module], n_bands: int = 16, balancer=None,
+                 weights: Optional[Dict[str, float]] = None, warmup_quantize: Optional[int] = None,
+                 pqmf: Optional[Callable[[], nn.Module]] = None, spectrogram: Optional[Callable] = None,
+                 update_discriminator_every: int = 2, n_channels: int = 1, input_mode: str = "pqmf",
+                 output_mode: str = "pqmf", audio_monitor_epochs: int = 1,
+                 enable_pqmf_encode: Optional[bool] = None, enable_pqmf_decode: Optional[bool] = None,
+                 is_mel_input: Optional[bool] = None, loss_weights=None):
+        super().__init__()
+        self.pqmf = pqmf(n_channels=n_channels)
+        self.spectrogram = spectrogram
+        assert input_mode in ["pqmf", "mel", "raw"]
+        assert output_mode in ["raw", "pqmf"]
+        self.input_mode = input_mode
+        self.output_mode = output_mode
+        if (enable_pqmf_encode is not None) or (enable_pqmf_decode is not None):
+            self.input_mode = "pqmf" if enable_pqmf_encode else "raw"
+            self.output_mode = "pqmf" if enable_pqmf_decode else "raw"
+        if is_mel_input is not None:
+            self.input_mode = "mel"
+        if loss_weights is not None:
+            weights = loss_weights
+        assert weights is not None, "RAVE model requires either weights or loss_weights (depreciated) keyword"
+
+        self.encoder = encoder(n_channels=n_channels)
+        self.decoder = decoder(n_channels=n_channels)
+        self.discriminator = discriminator(n_channels=n_channels)
+        self.audio_distance = audio_distance()
+        self.multiband_audio_distance = multiband_audio_distance()
+        self.gan_loss = gan_loss
+
+        self.register_buffer("latent_pca", torch.eye(latent_size))
+        self.register_buffer("latent_mean", torch.zeros(latent_size))
+        self.register_buffer("fidelity", torch.zeros(latent_size))
+        self.latent_size = latent_size
+        self.automatic_optimization = False
+
+        self.warmup = phase_1_duration
+        self.warmup_quantize = warmup_quantize
+        # the reference aliases and mutates the module-global dict (quirk D1); a copy gives the
+        # same values without the cross-instance side effect
+        self.weights = dict(_default_loss_weights)
+        self.weights.update(weights)
+        self.warmed_up = False
+
+        self.sr = sampling_rate
+        self.valid_signal_crop = valid_signal_crop
+        self.n_channels = n_channels
+        self.feature_matching_fun = feature_matching_fun
+        self.num_skipped_features = num_skipped_features
+        self.update_discriminator_every = update_discriminator_every
+        self.eval_number = 0
+        self.beta_factor = 1.
+        self.integrator = None
+        self.register_buffer("receptive_field", torch.tensor([0, 0]).long())
+        self.audio_monitor_epochs = audio_monitor_epochs
+
+        self._optimizers = None
+        self._scheduler = None
+        self.logged: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ optimisers
+    def configure_optimizers(self):
+        """rave/model.py:226-236."""
+        gen_p = list(self.encoder.parameters()) + list(self.decoder.parameters())
+        dis_p = list(self.discriminator.parameters())
+        gen_opt = torch.optim.Adam(gen_p, 1e-3, (.5, .9))
+        dis_opt = torch.optim.Adam(dis_p, 1e-4, (.5, .9))
+        sched = torch.optim.lr_scheduler.LinearLR(gen_opt, start_factor=1.0, end_factor=0.1,
+                                                  total_iters=self.warmup)
+        return ({"optimizer": gen_opt, "lr_scheduler": {"scheduler": sched}}, {"optimizer": dis_opt})
+
+    def optimizers(self):
+        if self._optimizers is None:
+            g, d = self.configure_optimizers()
+            self._optimizers = (g["optimizer"], d["optimizer"])
+            self._scheduler = g["lr_scheduler"]["scheduler"]
+        return self._optimizers
+
+    def lr_schedulers(self):
+        self.optimizers()
+        return self._scheduler
+
+    def log(self, name, value):
+        self.logged[name] = value.detach() if torch.is_tensor(value) else value
+
+    def log_dict(self, d):
+        for k, v in d.items():
+            self.log(k, v)
+
+    # ------------------------------------------------------------------ inference path
+    def encode(self, x, return_mb: bool = False):
+        x_enc = x
+        if self.input_mode == "pqmf":
+            x_enc = _pqmf_encode(self.pqmf, x_enc)
+        elif self.input_mode == "mel":
+            raise NotImplementedError("mel input is not on the hot path")
+        z = self.encoder(x_enc)
+        if return_mb:
+            if self.input_mode == "pqmf":
+                return z, x_enc
+            return z, _pqmf_encode(self.pqmf, x_enc)
+        return z
+
+    def decode(self, z):
+        batch_size = z.shape[:-2]
+        y = self.decoder(z)
+        if self.output_mode == "pqmf":
+            y = _pqmf_decode(self.pqmf, y, batch_size=batch_size, n_channels=self.n_channels)
+        return y
+
+    def forward(self, x):
+        z = self.encode(x, return_mb=False)
+        z = self.encoder.reparametrize(z)[0]
+        return self.decode(z)
+
+    def on_train_batch_end(self, outputs=None, batch=None, batch_idx=None) -> None:
+        self.lr_schedulers().step()
+
+    def split_features(self, features):
+        feature_real, feature_fake = [], []
+        for scale in features:
+            true, fake = zip(*map(lambda x: torch.split(x, x.shape[0] // 2, 0), scale))
+            feature_real.append(true)
+            feature_fake.append(fake)
+        return feature_real, feature_fake
+
+    # ------------------------------------------------------------------ training step
+    def compute_losses(self, x_raw, is_dis_step: bool, eps: Optional[torch.Tensor] = None):
+        """Forward part of training_step (rave/model.py:292-399).  Returns (loss_gen dict, loss_dis,
+        aux)."""
+        batch_size = x_raw.shape[:-2]
+        self.encoder.set_warmed_up(self.warmed_up)
+        self.decoder.set_warmed_up(self.warmed_up)
+
+        z, x_multiband = self.encode(x_raw, return_mb=True)
+        if eps is not None:
+            z, reg = self.encoder.reparametrize(z, eps)[:2]
+        else:
+            z, reg = self.encoder.reparametrize(z)[:2]
+
+        y = self.decoder(z)
+        if self.output_mode == "pqmf":
+            y_multiband = y
+            y_raw = _pqmf_decode(self.pqmf, y, batch_size=batch_size, n_channels=self.n_channels)
+        else:
+            y_raw = y
+            y_multiband = _pqmf_encode(self.pqmf, y)
+        y_raw = y_raw[..., :x_raw.shape[-1]]
+        y_multiband = y_multiband[..., :x_multiband.shape[-1]]
+
+        if self.valid_signal_crop and self.receptive_field.sum():
+            x_multiband = core.valid_signal_crop(x_multiband, *self.receptive_field)
+            y_multiband = core.valid_signal_crop(y_multiband, *self.receptive_field)
+
+        distances = {}
+        for k, v in self.multiband_audio_distance(x_multiband, y_multiband).items():
+            distances[f"multiband_{k}"] = self.weights["multiband_audio_distance"] * v
+        for k, v in self.audio_distance(x_raw, y_raw).items():
+            distances[f"fullband_{k}"] = self.weights["audio_distance"] * v
+
+        feature_matching_distance = 0.
+        if self.warmed_up:
+            y_d = y_raw.detach() if is_dis_step else y_raw     # quirk D2: discarded gradients
+            xy = torch.cat([x_raw, y_d], 0)
+            features = self.discriminator(xy)
+            feature_real, feature_fake = self.split_features(features)
+            loss_dis = 0
+            loss_adv = 0
+            pred_real = 0
+            pred_fake = 0
+            for scale_real, scale_fake in zip(feature_real, feature_fake):
+                current = sum(map(self.feature_matching_fun, scale_real[self.num_skipped_features:],
+                                  scale_fake[self.num_skipped_features:])) / len(
+                                      scale_real[self.num_skipped_features:])
+                feature_matching_distance = feature_matching_distance + current
+                _dis, _adv = self.gan_loss(scale_real[-1], scale_fake[-1])
+                pred_real = pred_real + scale_real[-1].mean()
+                pred_fake = pred_fake + scale_fake[-1].mean()
+                loss_dis = loss_dis + _dis
+                loss_adv = loss_adv + _adv
+            feature_matching_distance = feature_matching_distance / len(feature_real)
+        else:
+            pred_real = torch.tensor(0.).to(x_raw)
+            pred_fake = torch.tensor(0.).to(x_raw)
+            loss_dis = torch.tensor(0.).to(x_raw)
+            loss_adv = torch.tensor(0.).to(x_raw)
+
+        loss_gen = {}
+        loss_gen.update(distances)
+        loss_gen["regularization"] = reg * self.beta_factor
+        if self.warmed_up:
+            loss_gen["feature_matching"] = self.weights["feature_matching"] * feature_matching_distance
+            loss_gen["adversarial"] = self.weights["adversarial"] * loss_adv
+        aux = dict(pred_real=pred_real, pred_fake=pred_fake, y_raw=y_raw, z=z)
+        return loss_gen, loss_dis, aux
+
+    def is_discriminator_step(self, batch_idx: int) -> bool:
+        return (not (batch_idx % self.update_discriminator_every)) and self.warmed_up
+
+    def training_step(self, batch, batch_idx, eps: Optional[torch.Tensor] = None, grad_hook=None):
+        """rave/model.py:288-424.  `grad_hook(params)` (optional) runs between backward and the
+        optimiser step: the data-parallel gradient all-reduce plugs in there (rave_b200/ddp.py)."""
+        gen_opt, dis_opt = self.optimizers()
+        x_raw = batch
+        is_dis = self.is_discriminator_step(batch_idx)
+
+        dis_params = [p for p in self.discriminator.parameters()]
+        for p in dis_params:                       # G-step: no discriminator wgrad (discarded work)
+            p.requires_grad_(is_dis)
+
+        loss_gen, loss_dis, aux = self.compute_losses(x_raw, is_dis, eps)
+
+        if is_dis:
+            dis_opt.zero_grad(set_to_none=True)
+            loss_dis.backward()
+            if grad_hook is not None:
+                grad_hook(dis_params)
+            dis_opt.step()
+        else:
+            gen_opt.zero_grad(set_to_none=True)
+            loss_gen_value = 0.
+            for k, v in loss_gen.items():
+                loss_gen_value = loss_gen_value + v * self.weights.get(k, 1.)
+            loss_gen_value.backward()
+            if grad_hook is not None:
+                grad_hook([p for g in gen_opt.param_groups for p in g["params"]])
+            gen_opt.step()
+
+        self.log("beta_factor", self.beta_factor)
+        if self.warmed_up:
+            self.log("loss_dis", loss_dis)
+            self.log("pred_real", aux["pred_real"].mean())
+            self.log("pred_fake", aux["pred_fake"].mean())
+        self.log_dict(loss_gen)
+        return self.logged

@@ -1,0 +1,350 @@
+"""torch.autograd.Function wrappers around the C ABI (include/rave_b200.h).
+
+PyTorch is plumbing here: it owns the device memory, the stream and the autograd tape; every
+arithmetic operation of the hot path is one of the library's sm_100a kernels.  There is no
+fallback implementation: host tensors or a missing library raise (`_lib.RaveB200Error`).
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+ACT_NONE, ACT_LEAKY, ACT_SNAKE = 0, 1, 2
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise _lib.RaveB200Error(f"expected float32 tensor, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def conv_out_len(Lin: int, K: int, stride: int, dil: int, pad_l: int, pad_r: int) -> int:
+    return (Lin + pad_l + pad_r - dil * (K - 1) - 1) // stride + 1
+
+
+# ----------------------------------------------------------------------------------------------
+# raw launches (no autograd)
+# ----------------------------------------------------------------------------------------------
+
+def _gather(src, w, bias, res, out, K, stride, dil, pad_l, ws_m, ws_c, act, slope, alpha,
+            post_act=0, post_slope=0.0, post_x=None, post_alpha=None):
+    B, Cs, Ls = src.shape
+    _, Cm, Lo = out.shape
+    call("rave_conv1d_gather_f32", ptr(src), ptr(w), ptr(bias), ptr(res), ptr(out), B, Cs, Ls, Cm, Lo,
+         K, stride, dil, pad_l, ws_m, ws_c, act, float(slope), ptr(alpha), post_act, float(post_slope),
+         ptr(post_x), ptr(post_alpha), stream_ptr())
+
+
+def _scatter(src, w, bias, res, out, K, stride, dil, pad_l, ws_m, ws_c, act, slope, alpha,
+             post_act=0, post_slope=0.0, post_x=None, post_alpha=None):
+    B, Cs, Ls = src.shape
+    _, Cm, Lo = out.shape
+    call("rave_conv1d_scatter_f32", ptr(src), ptr(w), ptr(bias), ptr(res), ptr(out), B, Cs, Ls, Cm, Lo,
+         K, stride, dil, pad_l, ws_m, ws_c, act, float(slope), ptr(alpha), post_act, float(post_slope),
+         ptr(post_x), ptr(post_alpha), stream_ptr())
+
+
+def _wgrad(P, Q, dw, K, stride, dil, pad_l, os_a, os_c, act_p, act_q, slope, alpha):
+    B, Ca, Lp = P.shape
+    _, Cc, Lq = Q.shape
+    lib = _lib.load()
+    nbytes = lib.rave_conv1d_wgrad_workspace_bytes(B, Ca, Cc, Lp, K)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=P.device)
+    call("rave_conv1d_wgrad_f32", ptr(P), ptr(Q), ptr(dw), B, Ca, Lp, Cc, Lq, K, stride, dil, pad_l,
+         os_a, os_c, act_p, act_q, float(slope), ptr(alpha), ptr(ws), stream_ptr())
+
+
+def _act_grad_input(g, x, act, slope, alpha):
+    """dx = g * act'(x) (+ dalpha for Snake)."""
+    dx = torch.empty_like(x)
+    dalpha = torch.empty_like(alpha) if act == ACT_SNAKE else None
+    B, C, L = x.shape
+    call("rave_act_bwd", ptr(g), ptr(x), ptr(dx), ptr(dalpha), B, C, L, act, float(slope), ptr(alpha),
+         stream_ptr())
+    return dx, dalpha
+
+
+# ----------------------------------------------------------------------------------------------
+# conv1d: y = bias + res + conv(act(x))      (cc.Conv1d.forward preceded by its activation)
+# ----------------------------------------------------------------------------------------------
+
+class Conv1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, res, alpha, stride, dil, pad_l, pad_r, act, slope):
+        x, w, bias, res, alpha = _f32c(x), _f32c(w), _f32c(bias), _f32c(res), _f32c(alpha)
+        B, Cin, Lin = x.shape
+        Cout, Cin_w, K = w.shape
+        if Cin_w != Cin:
+            raise _lib.RaveB200Error(f"conv1d: weight expects {Cin_w} input channels, got {Cin}")
+        Lout = conv_out_len(Lin, K, stride, dil, pad_l, pad_r)
+        if Lout <= 0:
+            raise _lib.RaveB200Error("conv1d: empty output")
+        y = torch.empty(B, Cout, Lout, dtype=torch.float32, device=x.device)
+        if res is not None and res.shape != y.shape:
+            raise _lib.RaveB200Error("conv1d: residual shape mismatch")
+        _gather(x, w, bias, res, y, K, stride, dil, pad_l, Cin * K, K, act, slope, alpha)
+        ctx.save_for_backward(x, w, alpha)
+        ctx.cfg = (stride, dil, pad_l, act, slope, bias is not None, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, alpha = ctx.saved_tensors
+        stride, dil, pad_l, act, slope, has_bias, has_res = ctx.cfg
+        dy = _f32c(dy)
+        B, Cin, Lin = x.shape
+        Cout, _, K = w.shape
+        dx = dw = dbias = dres = dalpha = None
+        if ctx.needs_input_grad[0] or (act == ACT_SNAKE and ctx.needs_input_grad[4]):
+            g = torch.empty_like(x)
+            if act == ACT_SNAKE:
+                _scatter(dy, w, None, None, g, K, stride, dil, pad_l, K, Cin * K, 0, 0.0, None)
+                dx, dalpha = _act_grad_input(g, x, act, slope, alpha)
+            else:
+                _scatter(dy, w, None, None, g, K, stride, dil, pad_l, K, Cin * K, 0, 0.0, None,
+                         post_act=act, post_slope=slope, post_x=x if act else None)
+                dx = g
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            _wgrad(dy, x, dw, K, stride, dil, pad_l, Cin * K, K, 0, act, slope, alpha)
+        if has_bias and ctx.needs_input_grad[2]:
+            dbias = dy.sum((0, 2))
+        if has_res and ctx.needs_input_grad[3]:
+            dres = dy
+        return dx, dw, dbias, dres, dalpha, None, None, None, None, None, None
+
+
+def conv1d(x, w, bias=None, res=None, stride=1, dilation=1, pad=(0, 0), act=ACT_NONE, slope=0.2,
+           alpha=None):
+    return Conv1dFn.apply(x, w, bias, res, alpha, stride, dilation, pad[0], pad[1], act, slope)
+
+
+# ----------------------------------------------------------------------------------------------
+# conv_transpose1d: y = bias + convT(act(x)),  w: [Cin, Cout, K]   (blocks.py:650-657)
+# ----------------------------------------------------------------------------------------------
+
+class ConvTranspose1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, alpha, stride, padding, act, slope):
+        x, w, bias, alpha = _f32c(x), _f32c(w), _f32c(bias), _f32c(alpha)
+        B, Cin, Lin = x.shape
+        Cin_w, Cout, K = w.shape
+        if Cin_w != Cin:
+            raise _lib.RaveB200Error(f"conv_transpose1d: weight expects {Cin_w} input channels, got {Cin}")
+        Lout = (Lin - 1) * stride - 2 * padding + K
+        y = torch.empty(B, Cout, Lout, dtype=torch.float32, device=x.device)
+        _scatter(x, w, bias, None, y, K, stride, 1, padding, K, Cout * K, act, slope, alpha)
+        ctx.save_for_backward(x, w, alpha)
+        ctx.cfg = (stride, padding, act, slope, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, alpha = ctx.saved_tensors
+        stride, padding, act, slope, has_bias = ctx.cfg
+        dy = _f32c(dy)
+        Cin, Cout, K = w.shape
+        dx = dw = dbias = dalpha = None
+        if ctx.needs_input_grad[0] or (act == ACT_SNAKE and ctx.needs_input_grad[3]):
+            g = torch.empty_like(x)
+            if act == ACT_SNAKE:
+                _gather(dy, w, None, None, g, K, stride, 1, padding, Cout * K, K, 0, 0.0, None)
+                dx, dalpha = _act_grad_input(g, x, act, slope, alpha)
+            else:
+                _gather(dy, w, None, None, g, K, stride, 1, padding, Cout * K, K, 0, 0.0, None,
+                        post_act=act, post_slope=slope, post_x=x if act else None)
+                dx = g
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            _wgrad(x, dy, dw, K, stride, 1, padding, Cout * K, K, act, 0, slope, alpha)
+        if has_bias and ctx.needs_input_grad[2]:
+            dbias = dy.sum((0, 2))
+        return dx, dw, dbias, dalpha, None, None, None, None
+
+
+def conv_transpose1d(x, w, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.2, alpha=None):
+    return ConvTranspose1dFn.apply(x, w, bias, alpha, stride, padding, act, slope)
+
+
+# ----------------------------------------------------------------------------------------------
+# weight norm (blocks.normalization -> torch.nn.utils.weight_norm, rave/blocks.py:15-22)
+# ----------------------------------------------------------------------------------------------
+
+class WeightNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, g):
+        v, g = _f32c(v), _f32c(g)
+        C0 = v.shape[0]
+        R = v.numel() // C0
+        w = torch.empty_like(v)
+        norm = torch.empty(C0, dtype=torch.float32, device=v.device)
+        call("rave_weight_norm_fwd", ptr(v), ptr(g), ptr(w), ptr(norm), C0, R, stream_ptr())
+        ctx.save_for_backward(v, g, norm)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g, norm = ctx.saved_tensors
+        dw = _f32c(dw)
+        C0 = v.shape[0]
+        R = v.numel() // C0
+        dv = torch.empty_like(v)
+        dg = torch.empty_like(g)
+        call("rave_weight_norm_bwd", ptr(dw), ptr(v), ptr(g), ptr(norm), ptr(dv), ptr(dg), C0, R,
+             stream_ptr())
+        return dv, dg
+
+
+def weight_norm(v, g):
+    return WeightNormFn.apply(v, g)
+
+
+# ----------------------------------------------------------------------------------------------
+# stand-alone activation (LeakyReLU / Snake) and generator tail
+# ----------------------------------------------------------------------------------------------
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, alpha, act, slope):
+        x, alpha = _f32c(x), _f32c(alpha)
+        B, C, L = x.shape
+        y = torch.empty_like(x)
+        call("rave_act_fwd", ptr(x), ptr(y), B, C, L, act, float(slope), ptr(alpha), stream_ptr())
+        ctx.save_for_backward(x, alpha)
+        ctx.cfg = (act, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, alpha = ctx.saved_tensors
+        act, slope = ctx.cfg
+        dx, dalpha = _act_grad_input(_f32c(dy), x, act, slope, alpha)
+        return dx, dalpha, None, None
+
+
+def activation(x, act, slope=0.2, alpha=None):
+    if act == ACT_NONE:
+        return x
+    shape = x.shape
+    if x.dim() != 3:
+        x = x.reshape(shape[0], shape[1], -1)
+    return ActFn.apply(x, alpha, act, slope).reshape(shape)
+
+
+class AmTanhFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        B, C2, L = x.shape
+        C = C2 // 2
+        y = torch.empty(B, C, L, dtype=torch.float32, device=x.device)
+        call("rave_am_tanh_fwd", ptr(x), ptr(y), B, C, L, stream_ptr())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, C2, L = x.shape
+        dx = torch.empty_like(x)
+        call("rave_am_tanh_bwd", ptr(_f32c(dy)), ptr(x), ptr(dx), B, C2 // 2, L, stream_ptr())
+        return dx
+
+
+def am_tanh(x):
+    """tanh(x[:, :C] * sigmoid(x[:, C:])) -- GeneratorV2 tail, rave/blocks.py:704-711."""
+    return AmTanhFn.apply(x)
+
+
+# ----------------------------------------------------------------------------------------------
+# PQMF
+# ----------------------------------------------------------------------------------------------
+
+def _pqmf_analysis_raw(x, taps, Lout, pad_l, flip):
+    B, T = x.shape
+    y = torch.empty(B, 16, Lout, dtype=torch.float32, device=x.device)
+    call("rave_pqmf_analysis_fwd", ptr(x), ptr(taps), ptr(y), B, T, Lout, taps.shape[1], pad_l,
+         int(flip), stream_ptr())
+    return y
+
+
+def _pqmf_synthesis_raw(x, w, pad_l, scale, flip):
+    B, M, L = x.shape
+    out = torch.empty(B, 16 * L, dtype=torch.float32, device=x.device)
+    call("rave_pqmf_synthesis_fwd", ptr(x), ptr(w), ptr(out), B, L, w.shape[2], pad_l, float(scale),
+         int(flip), stream_ptr())
+    return out
+
+
+class PqmfAnalysisFn(torch.autograd.Function):
+    """x[B,1,T] -> y[B,16,T/16]; `taps_bwd` = the same filter re-indexed as synthesis weights."""
+
+    @staticmethod
+    def forward(ctx, x, taps, taps_bwd, pad_l, pad_r, bwd_pad):
+        x = _f32c(x)
+        B, C, T = x.shape
+        if C != 1:
+            raise _lib.RaveB200Error("pqmf analysis expects [B,1,T]")
+        Lout = (T + pad_l + pad_r - taps.shape[1]) // 16 + 1
+        y = _pqmf_analysis_raw(x.view(B, T), taps, Lout, pad_l, True)
+        ctx.save_for_backward(taps_bwd)
+        ctx.cfg = (T, bwd_pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (taps_bwd,) = ctx.saved_tensors
+        T, bwd_pad = ctx.cfg
+        dy = _f32c(dy)
+        if dy.shape[2] * 16 != T:
+            raise _lib.RaveB200Error("pqmf analysis backward needs T == 16 * Lout")
+        dx = _pqmf_synthesis_raw(dy, taps_bwd, bwd_pad, 1.0, True)
+        return dx.view(dy.shape[0], 1, T), None, None, None, None, None
+
+
+class PqmfSynthesisFn(torch.autograd.Function):
+    """y[B,16,L] -> x[B,1,16 L]; `w_bwd` = the same filter re-indexed as analysis taps."""
+
+    @staticmethod
+    def forward(ctx, y, w, w_bwd, pad_l, bwd_pad):
+        y = _f32c(y)
+        B, M, L = y.shape
+        if M != 16:
+            raise _lib.RaveB200Error("pqmf synthesis expects 16 bands")
+        out = _pqmf_synthesis_raw(y, w, pad_l, 16.0, True)
+        ctx.save_for_backward(w_bwd)
+        ctx.cfg = (L, bwd_pad)
+        return out.view(B, 1, 16 * L)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (w_bwd,) = ctx.saved_tensors
+        L, bwd_pad = ctx.cfg
+        dout = _f32c(dout)
+        B = dout.shape[0]
+        dy = _pqmf_analysis_raw(dout.view(B, 16 * L), w_bwd, L, bwd_pad, True)
+        return dy, None, None, None, None
+
+
+def act_to_bf16(x, act=ACT_NONE, slope=0.2, alpha=None):
+    x = _f32c(x)
+    B, C, L = x.shape
+    y = torch.empty(B, C, L, dtype=torch.bfloat16, device=x.device)
+    call("rave_act_to_bf16", ptr(x), ptr(y), B, C, L, act, float(slope), ptr(alpha), stream_ptr())
+    return y
+
+
+def weight_to_tapmajor_bf16(w, transpose=False, flip=False):
+    w = _f32c(w)
+    if transpose:
+        Cin, Cout, K = w.shape
+    else:
+        Cout, Cin, K = w.shape
+    wt = torch.empty(K, Cout, Cin, dtype=torch.bfloat16, device=w.device)
+    call("rave_weight_to_tapmajor_bf16", ptr(w), ptr(wt), Cout, Cin, K, int(transpose), int(flip),
+         stream_ptr())
+    return wt

@@ -1,0 +1,345 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed
+golden fixtures generated from the unmodified reference.
+
+Tolerances (relative L2, fp32 parity mode): forward <= 2e-5, gradients <= 1e-4.  The oracle's own
+fp32 floor against an fp64 run of the same modules is ~1e-6.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import rave_oracle as O
+from tests.conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 2e-5
+BWD_TOL = 1e-4
+
+
+def load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def dev(t):
+    return t.cuda() if torch.is_tensor(t) else t
+
+
+# ------------------------------------------------------------------------------------ PQMF
+@pytest.mark.parametrize("mode", ["centered", "causal"])
+def test_pqmf_operators_golden(mode):
+    from rave_b200 import cc, pqmf
+    g = load("pqmf.pt")
+    with cc.configure(padding_mode=mode):
+        p = pqmf.CachedPQMF(attenuation=100, n_band=16).cuda()
+    x, y, xr = g[mode]["x"], g[mode]["y"], g[mode]["xr"]
+    y_gpu = p(x.cuda())
+    assert y_gpu.shape == y.shape
+    assert rel_l2(y_gpu, y) < 2e-6
+    xr_gpu = p.inverse(y.cuda())
+    assert xr_gpu.shape == xr.shape
+    assert rel_l2(xr_gpu, xr) < 2e-6
+
+
+def test_pqmf_backward_vs_oracle():
+    from rave_b200 import pqmf
+    p = pqmf.CachedPQMF(attenuation=100, n_band=16).cuda()
+    hk = p.hk.cpu()
+    x = torch.randn(3, 1, 4096)
+    xo = x.clone().requires_grad_(True)
+    yo = O.pqmf_analysis(xo, hk)
+    gy = torch.randn_like(yo)
+    (gx_o,) = torch.autograd.grad(yo, xo, gy)
+    xg = x.cuda().requires_grad_(True)
+    yg = p(xg)
+    (gx,) = torch.autograd.grad(yg, xg, gy.cuda())
+    assert rel_l2(gx, gx_o) < 1e-5
+    yb = torch.randn(3, 16, 256)
+    ybo = yb.clone().requires_grad_(True)
+    so = O.pqmf_synthesis(ybo, hk)
+    gs = torch.randn_like(so)
+    (gyb_o,) = torch.autograd.grad(so, ybo, gs)
+    ybg = yb.cuda().requires_grad_(True)
+    sg = p.inverse(ybg)
+    (gyb,) = torch.autograd.grad(sg, ybg, gs.cuda())
+    assert rel_l2(sg, so) < 2e-6
+    assert rel_l2(gyb, gyb_o) < 1e-5
+
+
+def test_pqmf_non_cached_variant_matches_polyphase_reference():
+    from rave_b200 import pqmf
+    g = load("pqmf.pt")
+    p = pqmf.PQMF(attenuation=100, n_band=16).cuda()
+    x, y = g["centered"]["x"], g["centered"]["y"]
+    assert rel_l2(p(x.cuda()), y) < 2e-6
+    assert rel_l2(p.inverse(y.cuda()), g["polyphase_inverse"]) < 2e-6
+
+
+def test_pqmf_full_size_properties():
+    """BASELINE size (32 x 65536): linearity, and the ~1e-3 near-perfect-reconstruction of
+    analysis -> synthesis with the 16-sample delay (size-independent properties)."""
+    from rave_b200 import pqmf
+    p = pqmf.CachedPQMF(attenuation=100, n_band=16).cuda()
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = (0.5 * torch.randn(32, 1, 65536, generator=g)).clamp(-1, 1).cuda()
+    x2 = torch.randn(32, 1, 65536, generator=g).cuda()
+    y = p(x)
+    assert y.shape == (32, 16, 4096)
+    lin = p(x + 0.25 * x2) - (y + 0.25 * p(x2))
+    assert lin.abs().max() < 5e-5
+    xr = p.inverse(y)
+    assert xr.shape == x.shape
+    r = rel_l2(xr[..., 16 + 1024:-1024], x[..., 1024:-1024 - 16])
+    assert 0.9e-3 < r < 1.1e-3
+    # one row against the CPU oracle
+    yo = O.pqmf_analysis(x[5:6].cpu(), p.hk.cpu())
+    assert rel_l2(y[5:6], yo) < 2e-6
+
+
+# ------------------------------------------------------------------------------ conv family
+CONV_CASES = [
+    # B, Cin, Cout, L, K, stride, dil, pad, act
+    (2, 16, 24, 200, 7, 1, 1, (3, 3), 0),
+    (2, 24, 24, 333, 3, 1, 9, (9, 9), 1),
+    (3, 24, 48, 256, 8, 4, 1, (3, 4), 1),
+    (2, 8, 16, 64, 4, 2, 1, (1, 2), 1),
+    (1, 130, 70, 97, 3, 1, 3, (6, 0), 1),     # causal padding, ragged sizes
+    (2, 1, 12, 1000, 15, 4, 1, (7, 7), 0),    # discriminator first layer (Cin = 1)
+    (2, 40, 1, 50, 1, 1, 1, (0, 0), 1),       # discriminator last layer (Cout = 1)
+    (2, 12, 12, 128, 3, 1, 1, (1, 1), 2),     # Snake prologue
+    (1, 3, 5, 9, 3, 1, 1, (1, 1), 0),         # tiny
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv1d_fwd_bwd_vs_oracle(case):
+    from rave_b200 import ops
+    B, Cin, Cout, L, K, stride, dil, pad, act = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, Cin, L, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    alpha = 0.5 + torch.rand(Cin, generator=g)
+    use_res = stride == 1 and Cin == Cout and pad[0] + pad[1] == dil * (K - 1)
+
+    def ref(x, w, b, alpha):
+        h = x
+        if act == 1:
+            h = O.leaky_relu(h, 0.2)
+        elif act == 2:
+            h = O.snake(h, alpha.view(-1, 1))
+        y = O.conv1d(h, w, b, stride, dil, pad)
+        return y + x if use_res else y
+
+    xo, wo, bo, ao = (t.clone().requires_grad_(True) for t in (x, w, b, alpha))
+    yo = ref(xo, wo, bo, ao)
+    gy = torch.randn(yo.shape, generator=g)
+    grads_o = torch.autograd.grad(yo, [xo, wo, bo] + ([ao] if act == 2 else []), gy)
+
+    xg, wg, bg, ag = (t.cuda().requires_grad_(True) for t in (x, w, b, alpha))
+    yg = ops.conv1d(xg, wg, bg, xg if use_res else None, stride, dil, pad, act, 0.2,
+                    ag if act == 2 else None)
+    assert yg.shape == yo.shape
+    assert rel_l2(yg, yo) < FWD_TOL
+    grads_g = torch.autograd.grad(yg, [xg, wg, bg] + ([ag] if act == 2 else []), gy.cuda())
+    for a, b_, name in zip(grads_g, grads_o, ["dx", "dw", "db", "dalpha"]):
+        assert rel_l2(a, b_) < BWD_TOL, name
+
+
+CONVT_CASES = [
+    (2, 32, 16, 40, 8, 4, 2, 1),
+    (2, 24, 12, 33, 4, 2, 1, 1),
+    (1, 130, 60, 17, 4, 2, 1, 0),
+    (2, 12, 6, 20, 8, 4, 2, 2),
+]
+
+
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transpose1d_fwd_bwd_vs_oracle(case):
+    from rave_b200 import ops
+    B, Cin, Cout, L, K, stride, padding, act = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, Cin, L, generator=g)
+    w = torch.randn(Cin, Cout, K, generator=g) / (Cin * K / stride) ** 0.5
+    alpha = 0.5 + torch.rand(Cin, generator=g)
+
+    def ref(x, w, alpha):
+        h = x
+        if act == 1:
+            h = O.leaky_relu(h, 0.2)
+        elif act == 2:
+            h = O.snake(h, alpha.view(-1, 1))
+        return O.conv_transpose1d(h, w, None, stride, padding)
+
+    xo, wo, ao = (t.clone().requires_grad_(True) for t in (x, w, alpha))
+    yo = ref(xo, wo, ao)
+    gy = torch.randn(yo.shape, generator=g)
+    grads_o = torch.autograd.grad(yo, [xo, wo] + ([ao] if act == 2 else []), gy)
+    xg, wg, ag = (t.cuda().requires_grad_(True) for t in (x, w, alpha))
+    yg = ops.conv_transpose1d(xg, wg, None, stride, padding, act, 0.2, ag if act == 2 else None)
+    assert yg.shape == yo.shape
+    assert rel_l2(yg, yo) < FWD_TOL
+    grads_g = torch.autograd.grad(yg, [xg, wg] + ([ag] if act == 2 else []), gy.cuda())
+    for a, b_, name in zip(grads_g, grads_o, ["dx", "dw", "dalpha"]):
+        assert rel_l2(a, b_) < BWD_TOL, name
+
+
+def test_weight_norm_fwd_bwd():
+    from rave_b200 import ops
+    for shape in [(24, 16, 7), (1536, 768, 4), (5, 3, 1), (32, 16, 5, 1)]:
+        v = torch.randn(*shape)
+        gshape = (shape[0],) + (1,) * (len(shape) - 1)
+        g = torch.rand(*gshape) + 0.5
+        vo, go = v.clone().requires_grad_(True), g.clone().requires_grad_(True)
+        wo = O.weight_norm(vo, go)
+        gw = torch.randn_like(wo)
+        dvo, dgo = torch.autograd.grad(wo, [vo, go], gw)
+        vg, gg = v.cuda().requires_grad_(True), g.cuda().requires_grad_(True)
+        wg = ops.weight_norm(vg, gg)
+        dvg, dgg = torch.autograd.grad(wg, [vg, gg], gw.cuda())
+        assert rel_l2(wg, wo) < 1e-6
+        assert rel_l2(dvg, dvo) < 1e-5 and rel_l2(dgg, dgo) < 1e-5
+
+
+def test_am_tanh_and_snake():
+    from rave_b200 import ops
+    x = torch.randn(2, 32, 100)
+    xo = x.clone().requires_grad_(True)
+    a, b = xo.split(16, 1)
+    yo = torch.tanh(a * torch.sigmoid(b))
+    gy = torch.randn_like(yo)
+    (gxo,) = torch.autograd.grad(yo, xo, gy)
+    xg = x.cuda().requires_grad_(True)
+    yg = ops.am_tanh(xg)
+    (gxg,) = torch.autograd.grad(yg, xg, gy.cuda())
+    assert rel_l2(yg, yo) < 1e-6 and rel_l2(gxg, gxo) < 1e-5
+    alpha = 0.5 + torch.rand(32)
+    xo = x.clone().requires_grad_(True)
+    ao = alpha.clone().requires_grad_(True)
+    so = O.snake(xo, ao.view(-1, 1))
+    gs = torch.randn_like(so)
+    gxo, gao = torch.autograd.grad(so, [xo, ao], gs)
+    xg = x.cuda().requires_grad_(True)
+    ag = alpha.cuda().requires_grad_(True)
+    sg = ops.activation(xg, ops.ACT_SNAKE, 0.0, ag)
+    gxg, gag = torch.autograd.grad(sg, [xg, ag], gs.cuda())
+    assert rel_l2(sg, so) < 1e-6 and rel_l2(gxg, gxo) < 1e-5 and rel_l2(gag, gao) < 1e-4
+
+
+# ---------------------------------------------------------------------------- model-level goldens
+def _build_autoencoder(name):
+    from rave_b200 import configs
+    g = load(f"autoencoder_{name}.pt")
+    kw = {"v2_tiny": {}, "v2_tiny_causal": dict(padding_mode="causal"), "v3_tiny": dict(name="v3"),
+          "v2_small_tiny": dict(ratios=[4, 2, 2, 2])}[name]
+    kw = dict(kw)
+    arch = kw.pop("name", "v2")
+    pq, enc, dec = configs.make_autoencoder(arch, capacity=8, latent_size=16, **kw)
+    holder = nn.Module()
+    holder.pqmf, holder.encoder, holder.decoder = pq, enc, dec
+    holder.load_state_dict(g["state_dict"], strict=True)
+    return g, holder.cuda().train()
+
+
+@pytest.mark.parametrize("name", ["v2_tiny", "v2_tiny_causal", "v3_tiny", "v2_small_tiny"])
+def test_autoencoder_golden_forward_backward(name):
+    """PQMF -> EncoderV2 -> reparametrize(eps) -> GeneratorV2 -> PQMF^-1 against tensors produced
+    by the unmodified reference (oracle/make_golden.py), forward and gradients."""
+    from rave_b200.model import _pqmf_decode, _pqmf_encode
+    g, m = _build_autoencoder(name)
+    x = g["x"].cuda().requires_grad_(True)
+    x_mb = _pqmf_encode(m.pqmf, x)
+    z = m.encoder(x_mb)
+    zs, kl = m.encoder.reparametrize(z, g["eps"].cuda())
+    y_mb = m.decoder(zs)
+    y = _pqmf_decode(m.pqmf, y_mb, batch_size=x.shape[:-2], n_channels=1)
+    assert y.shape == x.shape
+    assert rel_l2(x_mb, g["x_mb"]) < 2e-6
+    assert rel_l2(z, g["z"]) < FWD_TOL
+    assert rel_l2(kl, g["kl"]) < FWD_TOL
+    assert rel_l2(y_mb, g["y_mb"]) < FWD_TOL
+    assert rel_l2(y, g["y"]) < FWD_TOL
+    loss = (y * g["probe"].cuda()).sum()
+    params = dict(m.encoder.named_parameters(prefix="encoder"))
+    params.update(dict(m.decoder.named_parameters(prefix="decoder")))
+    names = sorted(g["grad_params"])
+    grads = torch.autograd.grad(loss, [x] + [params[n] for n in names])
+    assert rel_l2(grads[0], g["grad_x"]) < BWD_TOL
+    worst = max(rel_l2(a, g["grad_params"][n]) for a, n in zip(grads[1:], names))
+    assert worst < 5e-4, worst
+
+
+def test_discriminator_v2_golden_forward_backward():
+    from rave_b200 import configs
+    g = load("discriminator_v2.pt")
+    holder = nn.Module()
+    holder.discriminator = configs.make_discriminator_v2(capacity=g["capacity"])
+    holder.load_state_dict(g["state_dict"], strict=True)
+    disc = holder.discriminator.cuda()
+    x = g["x"].cuda().requires_grad_(True)
+    feats = disc(x)
+    assert len(feats) == 8
+    for fa, fb in zip(feats, g["features"]):
+        assert len(fa) == 5
+        for a, b in zip(fa, fb):
+            assert a.shape == b.shape
+            assert rel_l2(a, b) < FWD_TOL
+    fm, ld, la = O.gan_losses(feats, 1, True)      # pure torch arithmetic on device tensors
+    assert rel_l2(fm, g["fm"]) < FWD_TOL and rel_l2(ld, g["loss_dis"]) < FWD_TOL
+    tot = fm + ld + la
+    pp = dict(disc.named_parameters(prefix="discriminator"))
+    names = sorted(g["grad_params"])
+    grads = torch.autograd.grad(tot, [x] + [pp[n] for n in names])
+    assert rel_l2(grads[0], g["grad_x"]) < BWD_TOL
+    worst = max(rel_l2(a, g["grad_params"][n]) for a, n in zip(grads[1:], names))
+    assert worst < 5e-4, worst
+
+
+def test_v2_small_config2_vs_oracle():
+    """BASELINE config 2 at reduced batch: v2_small (CAPACITY 48, RATIOS [4,2,2,2]) PQMF+encoder+
+    generator forward in fp32 vs the CPU oracle, 1e-4 rel-L2 on z and y."""
+    from rave_b200 import configs
+    from rave_b200.model import _pqmf_decode, _pqmf_encode
+    torch.manual_seed(0)
+    pq, enc, dec = configs.make_autoencoder("v2_small")
+    holder = nn.Module()
+    holder.pqmf, holder.encoder, holder.decoder = pq, enc, dec
+    sd = {k: v.detach().clone() for k, v in holder.state_dict().items()}
+    gen = torch.Generator().manual_seed(1234)
+    x = (0.5 * torch.randn(2, 1, 65536, generator=gen)).clamp(-1, 1)
+    eps = torch.randn(2, 128, 128, generator=torch.Generator().manual_seed(4321))
+    taps = {}
+    y_o = O.rave_forward(x, sd, O.v2_small_config(), eps, taps)
+    holder.cuda()
+    x_mb = _pqmf_encode(pq, x.cuda())
+    z = enc(x_mb)
+    zs, _ = enc.reparametrize(z, eps.cuda())
+    y = _pqmf_decode(pq, dec(zs), batch_size=x.shape[:-2], n_channels=1)
+    assert rel_l2(z, taps["z"]) < 1e-4
+    assert rel_l2(y, y_o) < 1e-4
+
+
+def test_training_step_runs_and_updates():
+    """One phase-1 G step, one phase-2 D step, one phase-2 G step on a tiny model."""
+    from rave_b200 import configs
+    torch.manual_seed(0)
+    m = configs.build_rave("v2", capacity=8, latent_size=16, disc_capacity=4).cuda().train()
+    x = (0.5 * torch.randn(2, 1, 65536, device="cuda")).clamp(-1, 1)   # multiband STFT needs T/16 > 1024
+    w0 = m.decoder.net[0].weight_v.detach().clone()
+    d0 = m.discriminator.discriminators[1].layers[0].net[0].weight_v.detach().clone()
+    m.training_step(x, 1)
+    assert not torch.equal(w0, m.decoder.net[0].weight_v)
+    assert torch.equal(d0, m.discriminator.discriminators[1].layers[0].net[0].weight_v)
+    m.warmed_up = True
+    w1 = m.decoder.net[0].weight_v.detach().clone()
+    logs = m.training_step(x, 0)                      # D step
+    assert torch.equal(w1, m.decoder.net[0].weight_v)
+    assert not torch.equal(d0, m.discriminator.discriminators[1].layers[0].net[0].weight_v)
+    assert torch.isfinite(logs["loss_dis"])
+    logs = m.training_step(x, 1)                      # G step
+    assert not torch.equal(w1, m.decoder.net[0].weight_v)
+    for k in ("fullband_spectral_distance", "multiband_spectral_distance", "feature_matching",
+              "adversarial", "regularization"):
+        assert torch.isfinite(logs[k]), k
