@@ -125,16 +125,40 @@ int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, i
 
 /* ---------------------------------------------------------------------------------------------
  * tensor-core conv engine (tcgen05 + TMEM + TMA), implicit GEMM, time on the MMA M axis:
- *   D[l][co] = sum_k sum_ci A_k[l][ci] * W_k[co][ci],  A_k = shifted view of act-ed input.
- * See DESIGN.md section "tcgen05 conv engine".  Operands are bf16 (prec 1).  Input `xa` is the
- * ALREADY ACTIVATED operand tensor [B][Cin][Lin] in bf16 produced by the previous kernel's
- * epilogue; `wt` is the tap-major bf16 weight [K][Cout][Cin].  Epilogue: + bias, + res (fp32),
- * write `out_f32` (optional), write `out_act_bf16` = act(out) (optional).
+ *   D[(b,l)][co] = sum_k sum_ci A_k[(b,l)][ci] * W_k[co][ci],   A_k = row-shifted view of the input.
+ * See DESIGN.md section "tcgen05 conv engine".  Tensors on this path are CHANNEL-LAST:
+ *   xa      [B][Lin][Cin]  bf16 : the ALREADY ACTIVATED operand (written by the previous kernel's epilogue)
+ *   wt      [K][Cout][Cin] bf16 : tap-major effective weights (rave_weight_to_tapmajor_bf16)
+ *   res     [B][out_rows][Cout] fp32 or NULL (res_bf16: the same in bf16), bias [Cout] or NULL
+ *   dact_src[B][out_rows][Cout] bf16 or NULL : result *= LeakyReLU'(dact_src) before the residual add
+ *             (backward use: the activated operand saved by the forward pass carries the sign)
+ *   out_f32 [B][out_rows][Cout] fp32 or NULL : pre-activation stream (residual / features)
+ *   out_act [B][out_rows][Cout] bf16 or NULL : act(out), the next conv's operand
+ * Output row of (b,l) is l*out_row_stride + out_row_offset (phases of a transposed conv interleave);
+ * pass out_rows = 0, stride = 0, offset = 0 for a plain conv.  Requirements: Cin % 16 == 0,
+ * Cout % 16 == 0, Lin % stride == 0.
  * ------------------------------------------------------------------------------------------- */
 int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dil);
 int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bias, const float *res,
-                       float *out_f32, void *out_act_bf16, int B, int Cin, int Lin, int Cout, int Lout,
-                       int K, int stride, int dil, int pad_l, int act, float slope, void *stream);
+                       const void *res_bf16, const void *dact_src_bf16, float *out_f32, void *out_act_bf16,
+                       int B, int Cin, int Lin, int Cout, int Lout,
+                       int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
+                       int out_row_stride, int out_row_offset, void *stream);
+/* weight gradient on the same engine (split-K over rows, fp32 atomics into a zeroed buffer):
+ *   dwt[k][m][n] = sum_{b,l} P[b][l][m] * Q[b][l*stride + k*dil - pad_l][n]
+ * P [B][Lp][Cm] bf16 (conv: dy), Q [B][Lq][Cn] bf16 (conv: activated input); dwt [K][Cm][Cn] fp32.
+ * For ConvTranspose1d swap the roles (P = activated input, Q = dy).  Cm, Cn multiples of 8. */
+int rave_conv1d_tc_wgrad(const void *P_bf16, const void *Q_bf16, float *dwt, int B, int Cm, int Lp, int Cn,
+                         int Lq, int K, int stride, int dil, int pad_l, void *stream);
+/* dwt[K][Cm][Cn] -> dw[Cm][Cn][K] (transpose=0) or dw[Cn][Cm][K] (transpose=1), fp32 */
+int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int K, int transpose,
+                                void *stream);
+/* layout converters between the module-boundary layout [B][C][L] fp32 and the engine's channel-last:
+ *   to_cl:   y_bf16[b][l][c] = bf16(act(x[b][c][l])), optionally also y_f32[b][l][c] = x[b][c][l]
+ *   from_cl: y[b][c][l] = x_f32[b][l][c] */
+int rave_ncl_to_cl(const float *x, void *y_bf16, float *y_f32, int B, int C, int L, int act, float slope,
+                   const float *alpha, void *stream);
+int rave_cl_to_ncl(const float *x_cl, float *y, int B, int C, int L, void *stream);
 /* fp32 -> bf16 operand preparation: y = bf16(act(x)) */
 int rave_act_to_bf16(const float *x, void *y_bf16, int B, int C, int L, int act, float slope,
                      const float *alpha, void *stream);

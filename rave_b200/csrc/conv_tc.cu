@@ -1,8 +1,719 @@
-// placeholder until the tcgen05 engine lands
+// tcgen05 conv1d engine (sm_100a): im2col-free implicit GEMM with the TIME axis on the MMA M dimension.
+//
+//   D[m = (b,l)][n = co] = sum_{tap k} sum_{ci}  A_k[(b,l)][ci] * W_k[co][ci]
+//   A_k[(b,l)][ci] = xa[b][l*stride + k*dil - pad_l][ci]            (zero outside [0, Lin))
+//
+// Activations are CHANNEL-LAST bf16 (xa[b][l][c]): a tap shift / stride / dilation is then a pure ROW
+// offset of a K-major operand tile, which TMA expresses with a 4-D tensor map (c, phase, l/stride, b)
+// -- out-of-range rows (the conv padding) are zero-filled by the TMA unit, so there is no F.pad and no
+// im2col buffer.  Weights are tap-major bf16 wt[k][co][ci] (K-major B operand).  Both operand tiles use
+// the canonical K-major swizzled layout (row = one swizzle span = BLOCK_K*2 bytes), accumulators live
+// in TMEM (2 stages of BLOCK_N fp32 columns), and the epilogue (bias, residual, dual write of the
+// pre-activation fp32 stream and the bf16 activated operand of the NEXT conv) reads them back with
+// tcgen05.ld.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
+//
+// Replaces: cc.Conv1d.forward = F.pad + F.conv1d -> cuDNN (reference call sites rave/blocks.py:96-108,
+// 538-592, 637-692; rave/discriminator.py:99-111), the preceding activation module and the residual add.
 #include "common.cuh"
-extern "C" int rave_conv1d_tc_supported(int, int, int, int, int) { return 0; }
-extern "C" int rave_conv1d_tc_fwd(const void *, const void *, const float *, const float *, float *, void *,
-                                  int, int, int, int, int, int, int, int, int, int, float, void *) {
-  rave::set_error("conv1d_tc_fwd: not built");
-  return 3;
+#include "tc_common.cuh"
+
+namespace rave {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int ACC_STAGES = 2;
+
+struct TcParams {
+  int B, Cin, Lin, Cout, Lout, K, stride, dil, pad_l;
+  int BL, BB;              // rows of one M tile: BB batches x BL time steps (BL*BB == 128)
+  int n_lt, n_bg, n_nt;    // tile counts: time tiles, batch groups, N tiles
+  int num_kb;              // K blocks per tap = ceil(Cin / BLOCK_K)
+  int act;
+  float slope;
+  const float *bias;       // [Cout] or null
+  const float *res;        // channel-last fp32 [B][out_rows][Cout] or null
+  const __nv_bfloat16 *res_bf16;   // same, bf16 (gradient stream) or null
+  const __nv_bfloat16 *dact_src;   // channel-last bf16 [B][out_rows][Cout] or null: out *= leaky'(dact_src)
+  float *out_f32;          // channel-last fp32 or null
+  __nv_bfloat16 *out_act;  // channel-last bf16 = act(out) or null
+  int out_rows;            // rows per batch of the output tensors (>= Lout when phases interleave)
+  int out_row_stride;      // output row = l * out_row_stride + out_row_offset (transposed-conv phases)
+  int out_row_offset;
+};
+
+template <int BLOCK_N, int BLOCK_K>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
+  static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const TcParams p) {
+  using L = SmemLayout<BLOCK_N, BLOCK_K>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int SWZ = BLOCK_K * 2;
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
+                                 : (ACC_STAGES * BLOCK_N <= 128) ? 128 : (ACC_STAGES * BLOCK_N <= 256) ? 256 : 512;
+  static_assert(ACC_STAGES * BLOCK_N <= 512, "TMEM overflow");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tfull_bar = empty_bar + STAGES;
+  uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.n_lt * p.n_bg * p.n_nt;
+  const int kblocks = p.K * p.num_kb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_nt;
+        const int mt = tile / p.n_nt;
+        const int lt = mt % p.n_lt;
+        const int bg = mt / p.n_lt;
+        const int l0 = lt * p.BL;
+        const int b0 = bg * p.BB;
+        const int n0 = nt * BLOCK_N;
+        for (int k = 0; k < p.K; ++k) {
+          // input row = l*stride + k*dil - pad_l = (l + j)*stride + ph
+          const int off = k * p.dil - p.pad_l;
+          int j = off / p.stride;
+          int ph = off - j * p.stride;
+          if (ph < 0) { ph += p.stride; j -= 1; }
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t *sa = smem + stage * L::STAGE_BYTES;
+            uint8_t *sb = sa + L::A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t adesc = make_kmajor_desc(sa, SWZ);
+          const uint64_t bdesc = make_kmajor_desc(sb, SWZ);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+            // advance 16 bf16 = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+            umma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
+          if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // =========================== epilogue (4 warps) ===========================
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;    // row of the 128-row tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = tile % p.n_nt;
+      const int mt = tile / p.n_nt;
+      const int lt = mt % p.n_lt;
+      const int bg = mt / p.n_lt;
+      const int n0 = nt * BLOCK_N;
+      const int b = bg * p.BB + row / p.BL;
+      const int l = lt * p.BL + row % p.BL;
+      const bool valid = (b < p.B) && (l < p.Lout);
+      const size_t orow = (size_t)b * p.out_rows + (size_t)l * p.out_row_stride + p.out_row_offset;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        float v[16];
+        tmem_ld_32x16(taddr + c0, v);   // warp-collective: every lane participates, valid or not
+        if (valid) {
+          const int co = n0 + c0;
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co + i);
+          }
+          if (p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand
+            const uint4 *d4 = reinterpret_cast<const uint4 *>(p.dact_src + orow * p.Cout + co);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint4 d = __ldg(d4 + i);
+              const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // bf16 sign bits: element 2j in the low half, 2j+1 in the high half
+                if (w[j] & 0x00008000u) v[8 * i + 2 * j] *= p.slope;
+                if (w[j] & 0x80000000u) v[8 * i + 2 * j + 1] *= p.slope;
+              }
+            }
+          }
+          if (p.res_bf16) {
+            const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_bf16 + orow * p.Cout + co);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint4 d = __ldg(r4 + i);
+              const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
+                v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+              }
+            }
+          }
+          if (p.res) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(p.res + orow * p.Cout + co);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 r = __ldg(r4 + i);
+              v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+            }
+          }
+          if (p.out_f32) {
+            float4 *o4 = reinterpret_cast<float4 *>(p.out_f32 + orow * p.Cout + co);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (p.out_act) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a0 = v[2 * i], a1 = v[2 * i + 1];
+              if (p.act == RAVE_ACT_LEAKY) {
+                a0 = a0 > 0.f ? a0 : a0 * p.slope;
+                a1 = a1 > 0.f ? a1 : a1 * p.slope;
+              }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+              pk[i] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(p.out_act + orow * p.Cout + co);
+            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_enum(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+static int pick_block_k(int Cin) {
+  if (Cin % 64 == 0) return 64;
+  if (Cin % 32 == 0) return 32;
+  if (Cin % 16 == 0) return 16;
+  return 0;
+}
+
+static int pick_block_n(int Cout, long m_tiles) {
+  // largest tile that still gives every SM work; Cout must be a multiple of it
+  const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
+  int best = 0;
+  for (int c : cands) {
+    if (Cout % c) continue;
+    if (!best) best = c;
+    if (m_tiles * (Cout / c) >= 148) return c;
+  }
+  // not enough tiles even at the smallest N: take the smallest valid one >= 32 if any
+  for (int i = 7; i >= 0; --i)
+    if (Cout % cands[i] == 0 && cands[i] >= 32) return cands[i];
+  return best;
+}
+
+template <int BN, int BK>
+static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t stream) {
+  using L = SmemLayout<BN, BK>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("conv1d_tc: cudaFuncSetAttribute(%d bytes): %s", L::TOTAL, cudaGetErrorString(e));
+      return 2;
+    }
+    attr = true;
+  }
+  const int tiles = p.n_lt * p.n_bg * p.n_nt;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = tiles < sms ? tiles : sms;
+  conv_tc_kernel<BN, BK><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  RAVE_CHECK_LAUNCH("conv1d_tc");
+  return 0;
+}
+
+template <int BK>
+static int dispatch_n(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
+                      cudaStream_t s) {
+  switch (bn) {
+    case 256: return launch<256, BK>(ta, tb, p, s);
+    case 192: return launch<192, BK>(ta, tb, p, s);
+    case 128: return launch<128, BK>(ta, tb, p, s);
+    case 96: return launch<96, BK>(ta, tb, p, s);
+    case 64: return launch<64, BK>(ta, tb, p, s);
+    case 48: return launch<48, BK>(ta, tb, p, s);
+    case 32: return launch<32, BK>(ta, tb, p, s);
+    case 16: return launch<16, BK>(ta, tb, p, s);
+  }
+  set_error("conv1d_tc: no kernel for BLOCK_N=%d", bn);
+  return 1;
+}
+
+}  // namespace tc
+}  // namespace rave
+
+extern "C" int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dil) {
+  if (rave::tc::pick_block_k(Cin) == 0) return 0;
+  if (Cout % 16) return 0;
+  if (K < 1 || stride < 1 || dil < 1) return 0;
+  return 1;
+}
+
+extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *bias, const float *res,
+                                  const void *res_bf16, const void *dact_src, float *out_f32, void *out_act,
+                                  int B, int Cin, int Lin, int Cout, int Lout,
+                                  int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
+                                  int out_row_stride, int out_row_offset, void *stream) {
+  using namespace rave;
+  using namespace rave::tc;
+  RAVE_CHECK_ARG(xa && wt && (out_f32 || out_act), "conv1d_tc: null pointer");
+  RAVE_CHECK_ARG(rave_conv1d_tc_supported(Cin, Cout, K, stride, dil), "conv1d_tc: unsupported shape Cin=%d Cout=%d",
+                 Cin, Cout);
+  RAVE_CHECK_ARG(Lin % stride == 0, "conv1d_tc: Lin %d not a multiple of stride %d", Lin, stride);
+  RAVE_CHECK_ARG(act == RAVE_ACT_NONE || act == RAVE_ACT_LEAKY, "conv1d_tc: epilogue activation %d unsupported", act);
+  RAVE_CHECK_ARG(((uintptr_t)xa & 15) == 0 && ((uintptr_t)wt & 15) == 0, "conv1d_tc: operands must be 16B aligned");
+  EncodeTiledFn enc = get_encode_fn();
+  RAVE_CHECK_ARG(enc, "conv1d_tc: cuTensorMapEncodeTiled not available");
+
+  const int BK = pick_block_k(Cin);
+  TcParams p;
+  p.B = B; p.Cin = Cin; p.Lin = Lin; p.Cout = Cout; p.Lout = Lout; p.K = K; p.stride = stride; p.dil = dil;
+  p.pad_l = pad_l; p.act = act; p.slope = slope; p.bias = bias; p.res = res; p.out_f32 = out_f32;
+  p.res_bf16 = (const __nv_bfloat16 *)res_bf16; p.dact_src = (const __nv_bfloat16 *)dact_src;
+  p.out_act = (__nv_bfloat16 *)out_act;
+  p.out_rows = out_rows > 0 ? out_rows : Lout;
+  p.out_row_stride = out_row_stride > 0 ? out_row_stride : 1;
+  p.out_row_offset = out_row_offset;
+  int BL = 128;
+  while (BL > Lout && BL > 8) BL >>= 1;   // power of two <= max(Lout, 8)
+  p.BL = BL; p.BB = 128 / BL;
+  p.n_lt = ceil_div(Lout, BL);
+  p.n_bg = ceil_div(B, p.BB);
+  const int BN = pick_block_n(Cout, (long)p.n_lt * p.n_bg);
+  RAVE_CHECK_ARG(BN > 0, "conv1d_tc: no BLOCK_N for Cout=%d", Cout);
+  p.n_nt = Cout / BN;
+  p.num_kb = ceil_div(Cin, BK);
+
+  // A: channel-last activations viewed as (c, phase, l/stride, b)
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)stride, (cuuint64_t)(Lin / stride), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * stride, (cuuint64_t)Cin * 2 * Lin};
+    cuuint32_t box[4] = {(cuuint32_t)BK, 1, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(xa), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(BK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map A encode failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)K * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(wt), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(BK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map B encode failed (%d)", (int)r);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (BK) {
+    case 64: return dispatch_n<64>(BN, ta, tb, p, s);
+    case 32: return dispatch_n<32>(BN, ta, tb, p, s);
+    case 16: return dispatch_n<16>(BN, ta, tb, p, s);
+  }
+  set_error("conv1d_tc: no kernel for BLOCK_K=%d", BK);
+  return 1;
+}
+
+// =============================================================================================
+// wgrad on tcgen05:  dWt[k][m][n] += sum_{(b,l)} P[b][l][m] * Q[b][l*stride + k*dil - pad_l][n]
+//
+// P: channel-last bf16 [B][Lp][Cm] (conv: dy, M = Cout), Q: channel-last bf16 [B][Lq][Cn] (conv: the
+// activated operand xa, N = Cin).  The reduction runs over tensor ROWS, so both operands are MN-major
+// (the channel axis is contiguous): tiles are stored as 64-channel slabs [64 rows][64 ch] (128-byte
+// rows, SWIZZLE_128B), LBO = slab stride, SBO = 8 rows.  One CTA owns one (m-tile, n-tile, tap) and one
+// slice of the rows (split-K); partial tiles are combined with fp32 atomics into a pre-zeroed dWt.
+// Reference: autograd of F.conv1d / F.conv_transpose1d (weight gradient) at the call sites listed above.
+// =============================================================================================
+namespace rave {
+namespace tc {
+
+constexpr int WG_ROWS = 64;             // reduction rows per pipeline stage
+constexpr int WG_SLAB = WG_ROWS * 128;  // bytes of one [64 rows][64 ch] bf16 slab
+
+struct WgParams {
+  int B, Cm, Lp, Cn, Lq, K, stride, dil, pad_l;
+  int BL, BB, n_lt, n_bg;   // row chunk = BB batches x BL rows (BL*BB == 64)
+  int n_mt, n_nt, splits;
+  float *dwt;               // [K][Cm][Cn] fp32, pre-zeroed
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 64-channel slabs
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;        // stride between 8-row groups
+  d |= 1ull << 46;
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  return d;
+}
+
+template <int BLOCK_N>
+struct WgSmem {
+  static constexpr int NS = (BLOCK_N + 63) / 64;
+  static constexpr int STAGE_BYTES = (2 + NS) * WG_SLAB;
+  static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q,
+                const WgParams p) {
+  using L = WgSmem<BLOCK_N>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int NS = L::NS;
+  constexpr uint32_t TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tfull_bar = empty_bar + STAGES;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile / slice owned by this CTA
+  const int split = blockIdx.x % p.splits;
+  int t = blockIdx.x / p.splits;
+  const int nt = t % p.n_nt; t /= p.n_nt;
+  const int mt = t % p.n_mt; t /= p.n_mt;
+  const int k = t;
+  const int m0 = mt * 128, n0 = nt * BLOCK_N;
+  const int n_chunks = p.n_lt * p.n_bg;
+  const int per = (n_chunks + p.splits - 1) / p.splits;
+  const int ch_begin = split * per;
+  const int ch_end = min(n_chunks, ch_begin + per);
+  const int my_chunks = max(0, ch_end - ch_begin);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_p);
+    tma_prefetch_desc(&tmap_q);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (my_chunks > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const int off = k * p.dil - p.pad_l;
+        int j = off / p.stride;
+        int ph = off - j * p.stride;
+        if (ph < 0) { ph += p.stride; j -= 1; }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int lt = ch % p.n_lt, bg = ch / p.n_lt;
+          const int l0 = lt * p.BL, b0 = bg * p.BB;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t *sa = smem + stage * L::STAGE_BYTES;
+          uint8_t *sb = sa + 2 * WG_SLAB;
+          mbar_arrive_expect_tx(&full_bar[stage], (2 + NS) * WG_SLAB);
+          tma_load_4d(sa, &tmap_p, &full_bar[stage], m0, 0, l0, b0);
+          tma_load_4d(sa + WG_SLAB, &tmap_p, &full_bar[stage], m0 + 64, 0, l0, b0);
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            tma_load_4d(sb + s * WG_SLAB, &tmap_q, &full_bar[stage], n0 + 64 * s, ph, l0 + j, b0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      // bf16 x bf16 -> fp32, A and B both MN-major (bits 15 / 16)
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N) | (1u << 15) | (1u << 16);
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int c = 0; c < my_chunks; ++c) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + 2 * WG_SLAB;
+          const uint64_t adesc = make_mnmajor_desc(sa, WG_SLAB);
+          const uint64_t bdesc = make_mnmajor_desc(sb, WG_SLAB);
+#pragma unroll
+          for (int kk = 0; kk < WG_ROWS / 16; ++kk) {
+            // 16 reduction rows = 2048 bytes -> +128 in the (addr >> 4) field
+            umma_f16(tmem_base, adesc + 128 * kk, bdesc + 128 * kk, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (c == my_chunks - 1) umma_commit(tfull_bar);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+    } else {
+      const int quad = warp & 3;
+      const int m = m0 + quad * 32 + lane;
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+      float *dst = p.dwt + ((size_t)k * p.Cm + m) * p.Cn + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        float v[16];
+        tmem_ld_32x16(taddr + c0, v);
+        if (m < p.Cm) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + c0 + i < p.Cn) atomicAdd(dst + c0 + i, v[i]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// dwt[K][Cm][Cn] fp32 -> dw[Cm][Cn][K] (transpose=0) or dw[Cn][Cm][K] (transpose=1)
+__global__ void __launch_bounds__(256)
+tapmajor_to_weight_kernel(const float *__restrict__ dwt, float *__restrict__ dw, int Cm, int Cn, int K,
+                          int transpose) {
+  const long total = (long)K * Cm * Cn;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int k = (int)(i % K);
+    const long r = i / K;
+    int a, c;   // output index (a, c, k): dw[a][c][k]
+    a = (int)(r / (transpose ? Cm : Cn));
+    c = (int)(r % (transpose ? Cm : Cn));
+    const int m = transpose ? c : a, n = transpose ? a : c;
+    dw[i] = dwt[((size_t)k * Cm + m) * Cn + n];
+  }
+}
+
+template <int BN>
+static int launch_wg(const CUtensorMap &tp, const CUtensorMap &tq, const WgParams &p, cudaStream_t stream) {
+  using L = WgSmem<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc: cudaFuncSetAttribute(%d bytes): %s", L::TOTAL, cudaGetErrorString(e));
+      return 2;
+    }
+    attr = true;
+  }
+  const int grid = p.K * p.n_mt * p.n_nt * p.splits;
+  wgrad_tc_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tp, tq, p);
+  RAVE_CHECK_LAUNCH("wgrad_tc");
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace rave
+
+extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, int B, int Cm, int Lp, int Cn,
+                                    int Lq, int K, int stride, int dil, int pad_l, void *stream) {
+  using namespace rave;
+  using namespace rave::tc;
+  RAVE_CHECK_ARG(P && Q && dwt, "wgrad_tc: null pointer");
+  RAVE_CHECK_ARG(Cm % 8 == 0 && Cn % 8 == 0, "wgrad_tc: channel counts must be multiples of 8 (Cm=%d Cn=%d)", Cm, Cn);
+  RAVE_CHECK_ARG(Lq % stride == 0, "wgrad_tc: Lq %d not a multiple of stride %d", Lq, stride);
+  EncodeTiledFn enc = get_encode_fn();
+  RAVE_CHECK_ARG(enc, "wgrad_tc: cuTensorMapEncodeTiled not available");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(dwt, 0, sizeof(float) * (size_t)K * Cm * Cn, s);
+
+  WgParams p;
+  p.B = B; p.Cm = Cm; p.Lp = Lp; p.Cn = Cn; p.Lq = Lq; p.K = K; p.stride = stride; p.dil = dil; p.pad_l = pad_l;
+  p.dwt = dwt;
+  int BL = WG_ROWS;
+  while (BL > Lp && BL > 8) BL >>= 1;
+  p.BL = BL; p.BB = WG_ROWS / BL;
+  p.n_lt = ceil_div(Lp, BL);
+  p.n_bg = ceil_div(B, p.BB);
+  p.n_mt = ceil_div(Cm, 128);
+  int BN = 256;
+  if (Cn <= 256) BN = (Cn + 15) / 16 * 16;
+  else if (Cn % 256 == 0) BN = 256;
+  else if (Cn % 192 == 0) BN = 192;
+  else if (Cn % 128 == 0) BN = 128;
+  const int valid_bn[] = {16, 32, 48, 64, 96, 128, 192, 256};
+  int bn_ok = 0;
+  for (int v : valid_bn) if (v >= BN) { bn_ok = v; break; }
+  BN = bn_ok ? bn_ok : 256;
+  p.n_nt = ceil_div(Cn, BN);
+  const int tiles = p.K * p.n_mt * p.n_nt;
+  const int n_chunks = p.n_lt * p.n_bg;
+  int splits = ceil_div(2 * 148, tiles);
+  if (splits > n_chunks) splits = n_chunks;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+
+  CUtensorMap tp, tq;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cm, 1, (cuuint64_t)Lp, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cm * 2, (cuuint64_t)Cm * 2, (cuuint64_t)Cm * 2 * Lp};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(P), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RAVE_CHECK_ARG(r == CUDA_SUCCESS, "wgrad_tc: tensor map P encode failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cn, (cuuint64_t)stride, (cuuint64_t)(Lq / stride), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cn * 2, (cuuint64_t)Cn * 2 * stride, (cuuint64_t)Cn * 2 * Lq};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(Q), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RAVE_CHECK_ARG(r == CUDA_SUCCESS, "wgrad_tc: tensor map Q encode failed (%d)", (int)r);
+  }
+  switch (BN) {
+    case 16: return launch_wg<16>(tp, tq, p, s);
+    case 32: return launch_wg<32>(tp, tq, p, s);
+    case 48: return launch_wg<48>(tp, tq, p, s);
+    case 64: return launch_wg<64>(tp, tq, p, s);
+    case 96: return launch_wg<96>(tp, tq, p, s);
+    case 128: return launch_wg<128>(tp, tq, p, s);
+    case 192: return launch_wg<192>(tp, tq, p, s);
+    case 256: return launch_wg<256>(tp, tq, p, s);
+  }
+  set_error("wgrad_tc: no kernel for BLOCK_N=%d", BN);
+  return 1;
+}
+
+extern "C" int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int K, int transpose,
+                                           void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(dwt && dw && Cm > 0 && Cn > 0 && K > 0, "tapmajor_to_weight: bad argument");
+  const long total = (long)K * Cm * Cn;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tc::tapmajor_to_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwt, dw, Cm, Cn, K, transpose);
+  RAVE_CHECK_LAUNCH("tapmajor_to_weight");
+  return 0;
 }

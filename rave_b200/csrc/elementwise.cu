@@ -253,3 +253,77 @@ extern "C" int rave_weight_to_tapmajor_bf16(const float *w, void *wt_bf16, int C
   RAVE_CHECK_LAUNCH("weight_to_tapmajor");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// layout converters: module-boundary [B][C][L] fp32  <->  engine channel-last [B][L][C]
+// 32x32 tiles through shared memory so both sides are coalesced.
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+// grid: (ceil(L/32), ceil(C/32), B), block (32, 8)
+__global__ void __launch_bounds__(256)
+ncl_to_cl_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ yb, float *__restrict__ yf, int C,
+                 int L, int act, float slope, const float *__restrict__ alpha) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, l = l0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && l < L) ? x[((size_t)b * C + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = l0 + ty + 8 * i, c = c0 + tx;
+    if (l < L && c < C) {
+      const float v = tile[tx][ty + 8 * i];
+      const size_t o = ((size_t)b * L + l) * C + c;
+      if (yf) yf[o] = v;
+      if (yb) yb[o] = __float2bfloat16_rn(act_apply(v, act, slope, act == RAVE_ACT_SNAKE ? alpha[c] : 0.f));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cl_to_ncl_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int L) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = l0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && l < L) ? x[((size_t)b * L + l) * C + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, l = l0 + tx;
+    if (l < L && c < C) y[((size_t)b * C + c) * L + l] = tile[tx][ty + 8 * i];
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_ncl_to_cl(const float *x, void *y_bf16, float *y_f32, int B, int C, int L, int act,
+                              float slope, const float *alpha, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && (y_bf16 || y_f32) && B > 0 && C > 0 && L > 0 && B <= 65535, "ncl_to_cl: bad argument");
+  RAVE_CHECK_ARG(act != RAVE_ACT_SNAKE || alpha, "ncl_to_cl: snake needs alpha");
+  dim3 grid(ceil_div(L, 32), ceil_div(C, 32), B), block(32, 8);
+  ncl_to_cl_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)y_bf16, y_f32, C, L, act, slope,
+                                                            alpha);
+  RAVE_CHECK_LAUNCH("ncl_to_cl");
+  return 0;
+}
+
+extern "C" int rave_cl_to_ncl(const float *x_cl, float *y, int B, int C, int L, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x_cl && y && B > 0 && C > 0 && L > 0 && B <= 65535, "cl_to_ncl: bad argument");
+  dim3 grid(ceil_div(L, 32), ceil_div(C, 32), B), block(32, 8);
+  cl_to_ncl_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x_cl, y, C, L);
+  RAVE_CHECK_LAUNCH("cl_to_ncl");
+  return 0;
+}

@@ -348,3 +348,71 @@ def weight_to_tapmajor_bf16(w, transpose=False, flip=False):
     call("rave_weight_to_tapmajor_bf16", ptr(w), ptr(wt), Cout, Cin, K, int(transpose), int(flip),
          stream_ptr())
     return wt
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core engine (channel-last bf16 operands), raw launches
+# ----------------------------------------------------------------------------------------------
+
+def ncl_to_cl(x, act=ACT_NONE, slope=0.2, alpha=None, want_bf16=True, want_f32=False):
+    """[B,C,L] fp32 -> channel-last ([B,L,C] bf16 = act(x), and/or [B,L,C] fp32 = x)."""
+    x = _f32c(x)
+    B, C, L = x.shape
+    yb = torch.empty(B, L, C, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    yf = torch.empty(B, L, C, dtype=torch.float32, device=x.device) if want_f32 else None
+    call("rave_ncl_to_cl", ptr(x), ptr(yb), ptr(yf), B, C, L, act, float(slope), ptr(alpha), stream_ptr())
+    return yb, yf
+
+
+def cl_to_ncl(x_cl):
+    """[B,L,C] fp32 -> [B,C,L] fp32."""
+    x_cl = _f32c(x_cl)
+    B, L, C = x_cl.shape
+    y = torch.empty(B, C, L, dtype=torch.float32, device=x_cl.device)
+    call("rave_cl_to_ncl", ptr(x_cl), ptr(y), B, C, L, stream_ptr())
+    return y
+
+
+def conv1d_tc_supported(Cin, Cout, K=1, stride=1, dil=1):
+    return bool(_lib.load().rave_conv1d_tc_supported(Cin, Cout, K, stride, dil))
+
+
+def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=ACT_NONE, slope=0.2,
+              want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
+              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None):
+    """xa_cl [B,Lin,Cin] bf16 (activated operand), wt [K,Cout,Cin] bf16 -> (out_f32 [B,Lout,Cout] fp32,
+    out_act [B,Lout,Cout] bf16 = act(out)); either may be None."""
+    B, Lin, Cin = xa_cl.shape
+    K, Cout, Cin_w = wt.shape
+    if Cin_w != Cin or xa_cl.dtype != torch.bfloat16 or wt.dtype != torch.bfloat16:
+        raise _lib.RaveB200Error("conv1d_tc: operand mismatch")
+    if Lout is None:
+        Lout = conv_out_len(Lin, K, stride, dil, pad[0], pad[1])
+    rows = out_rows if out_rows else Lout
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(B, rows, Cout, dtype=torch.float32, device=xa_cl.device)
+    if want_act and out_act is None:
+        out_act = torch.empty(B, rows, Cout, dtype=torch.bfloat16, device=xa_cl.device)
+    call("rave_conv1d_tc_fwd", ptr(xa_cl), ptr(wt), ptr(bias), ptr(res_cl), ptr(res_bf16), ptr(dact_src),
+         ptr(out_f32), ptr(out_act), B, Cin, Lin, Cout, Lout, K, stride, dil, pad[0], act, float(slope),
+         out_rows, out_row_stride, out_row_offset, stream_ptr())
+    return out_f32, out_act
+
+
+def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0):
+    """dwt[k][m][n] = sum_{b,l} P[b,l,m] * Q[b, l*stride + k*dil - pad_l, n]  (bf16 operands, fp32 result)."""
+    B, Lp, Cm = P_cl.shape
+    _, Lq, Cn = Q_cl.shape
+    if P_cl.dtype != torch.bfloat16 or Q_cl.dtype != torch.bfloat16:
+        raise _lib.RaveB200Error("conv1d_tc_wgrad: operands must be bf16")
+    dwt = torch.empty(K, Cm, Cn, dtype=torch.float32, device=P_cl.device)
+    call("rave_conv1d_tc_wgrad", ptr(P_cl), ptr(Q_cl), ptr(dwt), B, Cm, Lp, Cn, Lq, K, stride, dil, pad_l,
+         stream_ptr())
+    return dwt
+
+
+def tapmajor_to_weight(dwt, transpose=False):
+    K, Cm, Cn = dwt.shape
+    dw = torch.empty((Cn, Cm, K) if transpose else (Cm, Cn, K), dtype=torch.float32, device=dwt.device)
+    call("rave_tapmajor_to_weight_f32", ptr(dwt), ptr(dw), Cm, Cn, K, int(transpose), stream_ptr())
+    return dw

@@ -1,0 +1,93 @@
+"""GPU: the tcgen05 conv engine against the CPU oracle evaluated on the SAME bf16-rounded operands
+(so the only difference is fp32 accumulation order: tolerance 2e-5), and against the un-rounded fp32
+oracle with the stated bf16-mode tolerance (1e-2 rel-L2 per conv)."""
+import pytest
+import torch
+
+from oracle import rave_oracle as O
+from tests.conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TC_CASES = [
+    # B, Cin, Cout, L, K, stride, dil, pad, bias, res
+    (2, 64, 64, 256, 3, 1, 1, (1, 1), False, False),
+    (2, 96, 96, 512, 3, 1, 3, (3, 3), False, True),
+    (3, 96, 96, 384, 1, 1, 1, (0, 0), False, True),
+    (2, 16, 96, 512, 7, 1, 1, (3, 3), False, False),
+    (2, 96, 192, 512, 8, 4, 1, (3, 4), False, False),
+    (4, 768, 1536, 64, 4, 2, 1, (1, 2), False, False),
+    (5, 1536, 256, 32, 3, 1, 1, (1, 1), False, False),
+    (2, 128, 1536, 32, 3, 1, 1, (1, 1), False, False),
+    (2, 192, 192, 1000, 3, 1, 9, (9, 9), True, True),       # ragged length (not a multiple of 128)
+    (2, 96, 32, 300, 7, 1, 1, (6, 0), True, False),          # causal padding
+    (1, 32, 48, 40, 15, 4, 1, (7, 7), True, False),          # discriminator-like
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv1d_tc_vs_oracle(case):
+    from rave_b200 import ops
+    B, Cin, Cout, L, K, stride, dil, pad, use_bias, use_res = case
+    assert ops.conv1d_tc_supported(Cin, Cout, K, stride, dil)
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, Cin, L, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / (Cin * K) ** 0.5
+    bias = torch.randn(Cout, generator=g) if use_bias else None
+    # oracle on bf16-rounded operands
+    xa = O.leaky_relu(x, 0.2).bfloat16().float()
+    wr = w.bfloat16().float()
+    y_exact = O.conv1d(xa, wr, bias, stride, dil, pad)
+    y_fp32 = O.conv1d(O.leaky_relu(x, 0.2), w, bias, stride, dil, pad)
+    res = torch.randn(y_exact.shape, generator=g) if use_res else None
+    if use_res:
+        y_exact = y_exact + res
+        y_fp32 = y_fp32 + res
+
+    xa_cl, _ = ops.ncl_to_cl(x.cuda(), ops.ACT_LEAKY, 0.2)
+    assert torch.equal(xa_cl.float().cpu(), xa.permute(0, 2, 1))
+    wt = ops.weight_to_tapmajor_bf16(w.cuda())
+    assert torch.equal(wt.float().cpu(), wr.permute(2, 0, 1))
+    res_cl = res.permute(0, 2, 1).contiguous().cuda() if use_res else None
+    out_f32, out_act = ops.conv1d_tc(xa_cl, wt, bias.cuda() if use_bias else None, res_cl, stride, dil, pad,
+                                     ops.ACT_LEAKY, 0.2, want_f32=True, want_act=True)
+    torch.cuda.synchronize()
+    y = ops.cl_to_ncl(out_f32)
+    assert y.shape == y_exact.shape
+    assert rel_l2(y, y_exact) < 2e-5
+    assert rel_l2(y, y_fp32) < 1e-2
+    act_ref = O.leaky_relu(y_exact, 0.2).bfloat16().float().permute(0, 2, 1)
+    assert rel_l2(out_act.float(), act_ref) < 5e-3
+
+
+WG_CASES = [
+    # B, Cm(=Cout), Cn(=Cin), L, K, stride, dil, pad_l, pad_r
+    (2, 64, 64, 256, 3, 1, 1, 1, 1),
+    (2, 96, 96, 512, 3, 1, 3, 3, 3),
+    (3, 96, 16, 384, 7, 1, 1, 3, 3),
+    (2, 192, 96, 512, 8, 4, 1, 3, 4),
+    (4, 1536, 768, 64, 4, 2, 1, 1, 2),
+    (5, 256, 1536, 32, 3, 1, 1, 1, 1),
+    (2, 192, 192, 1000, 3, 1, 9, 9, 9),
+    (2, 32, 96, 300, 7, 1, 1, 6, 0),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_conv1d_tc_wgrad_vs_oracle(case):
+    from rave_b200 import ops
+    B, Cm, Cn, L, K, stride, dil, pad_l, pad_r = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, Cn, L, generator=g).bfloat16().float()
+    Lout = (L + pad_l + pad_r - dil * (K - 1) - 1) // stride + 1
+    dy = torch.randn(B, Cm, Lout, generator=g).bfloat16().float()
+    w = torch.zeros(Cm, Cn, K, requires_grad=True)
+    y = O.conv1d(x, w, None, stride, dil, (pad_l, pad_r))
+    (dw_ref,) = torch.autograd.grad(y, w, dy)
+    P = dy.permute(0, 2, 1).contiguous().bfloat16().cuda()
+    Q = x.permute(0, 2, 1).contiguous().bfloat16().cuda()
+    dwt = ops.conv1d_tc_wgrad(P, Q, K, stride, dil, pad_l)
+    dw = ops.tapmajor_to_weight(dwt)
+    torch.cuda.synchronize()
+    assert dw.shape == dw_ref.shape
+    assert rel_l2(dw, dw_ref) < 2e-5
