@@ -195,10 +195,54 @@ def dominant_kernel_roofline(torch, pk):
                 peak_source=pk["source"] + " burst", note="fp32 CUDA-core parity kernel")
 
 
+def tc_kernel_roofline(torch, pk):
+    """Dominant kernel of the bf16 step: the tcgen05 implicit-GEMM conv, timed alone on the MSD
+    384->768 k15 s4 layer at the BASELINE batch (real+fake = 64 x 1024 rows in, 256 rows out).
+    4 rotating buffer sets (4 x 125 MB > 126 MB L2) so operands come from HBM."""
+    from rave_b200 import ops
+    B, Cin, Cout, Lin, K, stride, pad = 64, 384, 768, 1024, 15, 4, 7
+    Lout = (Lin + 2 * pad - K) // stride + 1
+    xs = [torch.randn(B, Lin, Cin, device="cuda").bfloat16() for _ in range(4)]
+    wt = (torch.randn(K, Cout, Cin, device="cuda") * 0.02).bfloat16()
+    of = [torch.empty(B, Lout, Cout, device="cuda") for _ in range(4)]
+    oa = [torch.empty(B, Lout, Cout, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
+
+    def run(i):
+        ops.conv1d_tc(xs[i % 4], wt, None, None, stride, 1, (pad, pad), 1, 0.2, want_f32=False, want_act=False,
+                      out_f32=of[i % 4], out_act=oa[i % 4], Lout=Lout)
+    for i in range(4):
+        run(i)
+    torch.cuda.synchronize()
+    n = 40
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * B * Lout * Cout * Cin * K
+    byts = 2.0 * B * Lin * Cin + B * Lout * Cout * (4 + 2) + 2.0 * K * Cout * Cin
+    t_hbm = byts / (pk["hbm_gbs"] * 1e9)
+    t_tensor = flops / (pk["bf16_tflops"] * 1e12)
+    bound = "hbm" if t_hbm >= t_tensor else "tensor"
+    if bound == "hbm":
+        ach, peak, unit = byts / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+    else:
+        ach, peak, unit = flops / (ms * 1e-3) / 1e12, pk["bf16_tflops"], "TFLOP/s"
+    return dict(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+                kernel="conv_tc_kernel<256,64> (MSD conv 384->768 k15 s4, B=64, Lin=1024)",
+                ms_per_launch=ms, algorithmic_bytes=byts, algorithmic_flops=flops,
+                peak_source=pk["source"] + " burst (cuBLAS bf16)")
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    import rave_b200
     from rave_b200 import _lib, configs, ddp
+    prec = "bf16" if args.precision in ("auto", "bf16") else "fp32"
+    rave_b200.set_precision(prec)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -275,7 +319,7 @@ def run_ours(args):
     value_e2e = audio_s * args.steps / (ms_e2e * 1e-3)
 
     if rank == 0:
-        roof = dominant_kernel_roofline(torch, pk)
+        roof = tc_kernel_roofline(torch, pk) if prec == "bf16" else dominant_kernel_roofline(torch, pk)
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_reference_run(args, 2, 1, args.cpu_seconds)
@@ -284,11 +328,12 @@ def run_ours(args):
             "metric": "audio-seconds/s (v2 train step fwd+bwd, 48 kHz)",
             "value": value, "unit": "audio-seconds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"{args.config} phase-2 training step (PQMF+enc+gen+MPD/MSD disc, fwd+bwd+Adam; "
                                    f"1 D-step per 4), per-GPU batch {B}x{T} @48kHz",
                        "global_batch": world * B, "samples": T, "parallelism": f"dp{world}",
-                       "precision": "fp32 parity kernels (CUDA-core FMA)",
+                       "precision": ("bf16 operands / fp32 accumulate (tcgen05 engine); PQMF + losses fp32"
+                                     if prec == "bf16" else "fp32 parity kernels (CUDA-core FMA)"),
                        "l2_policy": "working set per step (>10 GB of activations) exceeds the 126 MB L2; "
                                     "two alternating input batches"},
             "roofline": roof, "cpu_baseline": cpu,

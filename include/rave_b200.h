@@ -135,24 +135,36 @@ int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, i
  *   out_f32 [B][out_rows][Cout] fp32 or NULL : pre-activation stream (residual / features)
  *   out_act [B][out_rows][Cout] bf16 or NULL : act(out), the next conv's operand
  * Output row of (b,l) is l*out_row_stride + out_row_offset (phases of a transposed conv interleave);
- * pass out_rows = 0, stride = 0, offset = 0 for a plain conv.  Requirements: Cin % 16 == 0,
- * Cout % 16 == 0, Lin % stride == 0.
+ * pass out_rows = 0, stride = 0, offset = 0 for a plain conv.  `in_pitch` = allocated rows per batch
+ * of xa (0 = Lin); it must be >= Lin rounded up to `stride`, with rows [Lin, in_pitch) zero.
+ * Requirements: Cin % 16 == 0, Cout % 16 == 0.
  * ------------------------------------------------------------------------------------------- */
 int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dil);
 int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bias, const float *res,
                        const void *res_bf16, const void *dact_src_bf16, float *out_f32, void *out_act_bf16,
-                       int B, int Cin, int Lin, int Cout, int Lout,
+                       int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
                        int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
                        int out_row_stride, int out_row_offset, void *stream);
 /* weight gradient on the same engine (split-K over rows, fp32 atomics into a zeroed buffer):
  *   dwt[k][m][n] = sum_{b,l} P[b][l][m] * Q[b][l*stride + k*dil - pad_l][n]
  * P [B][Lp][Cm] bf16 (conv: dy), Q [B][Lq][Cn] bf16 (conv: activated input); dwt [K][Cm][Cn] fp32.
  * For ConvTranspose1d swap the roles (P = activated input, Q = dy).  Cm, Cn multiples of 8. */
-int rave_conv1d_tc_wgrad(const void *P_bf16, const void *Q_bf16, float *dwt, int B, int Cm, int Lp, int Cn,
-                         int Lq, int K, int stride, int dil, int pad_l, void *stream);
+int rave_conv1d_tc_wgrad(const void *P_bf16, const void *Q_bf16, float *dwt, int B, int Cm, int Lp, int p_pitch,
+                         int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l, void *stream);
 /* dwt[K][Cm][Cn] -> dw[Cm][Cn][K] (transpose=0) or dw[Cn][Cm][K] (transpose=1), fp32 */
 int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int K, int transpose,
                                 void *stream);
+/* fused weight preparation for the engine: v [C0][C1][K] fp32 (+ weight-norm g [C0]; norm [C0] is written)
+ *   outA[t][c0][c1] = bf16(w[c0][c1][tapsA[t]]), dims [nA][C0p][C1p]  (padded region zero)
+ *   outB[t][c1][c0] = bf16(w[c0][c1][tapsB[t]]), dims [nB][C1p][C0p]
+ * tapsA / tapsB are HOST int arrays (<= 32 entries); either output may be NULL.  w = g v / ||v|| (or v). */
+int rave_weight_prep_tc(const float *v, const float *g, float *norm, void *outA_bf16, const int *tapsA, int nA,
+                        void *outB_bf16, const int *tapsB, int nB, int C0, int C1, int K, int C0p, int C1p,
+                        void *stream);
+/* tap-major fp32 weight gradient dwt [K][C0p][C1p] -> dv [C0][C1][K] (+ dg [C0]) through the weight norm
+ * (g == NULL: plain re-layout). */
+int rave_weight_norm_bwd_tapmajor(const float *dwt, const float *v, const float *g, const float *norm, float *dv,
+                                  float *dg, int C0, int C1, int K, int C0p, int C1p, void *stream);
 /* layout converters between the module-boundary layout [B][C][L] fp32 and the engine's channel-last:
  *   to_cl:   y_bf16[b][l][c] = bf16(act(x[b][c][l])), optionally also y_f32[b][l][c] = x[b][c][l]
  *   from_cl: y[b][c][l] = x_f32[b][l][c] */

@@ -148,7 +148,28 @@ class CachedSequential(nn.Sequential):
                 break
         self.cumulative_delay = cumulative_delay * stride + last
 
+    def _tc_plan(self):
+        """Tensor-core plan of this sequence (None if a member is unsupported), cached per mode."""
+        from . import engine
+        key = self.training
+        cache = self.__dict__.setdefault("_tc_plan_cache", {})
+        if key not in cache:
+            specs = engine.plan_sequential(list(self))
+            if specs is not None and not engine.chain_supported(specs):
+                specs = None
+            cache[key] = specs
+        return cache[key]
+
     def forward(self, x, res=None):
+        from . import engine
+        if res is None and engine.precision() == "bf16" and x.is_cuda and x.dim() == 3:
+            specs = self._tc_plan()
+            if specs is not None and (specs[0].kind != "conv" or x.shape[-1] % specs[0].stride == 0):
+                (out,) = engine.run_chain(engine.to_channel_last(x), specs)
+                Lout = engine.chain_lengths(specs, x.shape[-1])[-1]
+                if out.shape[1] != Lout:
+                    out = out[:, :Lout].contiguous()
+                return engine.from_channel_last(out)
         mods = list(self)
         i = 0
         n = len(mods)

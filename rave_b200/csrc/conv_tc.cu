@@ -364,7 +364,7 @@ extern "C" int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, in
 
 extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *bias, const float *res,
                                   const void *res_bf16, const void *dact_src, float *out_f32, void *out_act,
-                                  int B, int Cin, int Lin, int Cout, int Lout,
+                                  int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
                                   int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
                                   int out_row_stride, int out_row_offset, void *stream) {
   using namespace rave;
@@ -372,7 +372,10 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   RAVE_CHECK_ARG(xa && wt && (out_f32 || out_act), "conv1d_tc: null pointer");
   RAVE_CHECK_ARG(rave_conv1d_tc_supported(Cin, Cout, K, stride, dil), "conv1d_tc: unsupported shape Cin=%d Cout=%d",
                  Cin, Cout);
-  RAVE_CHECK_ARG(Lin % stride == 0, "conv1d_tc: Lin %d not a multiple of stride %d", Lin, stride);
+  if (in_pitch <= 0) in_pitch = Lin;
+  RAVE_CHECK_ARG(in_pitch >= ceil_div(Lin, stride) * stride,
+                 "conv1d_tc: input pitch %d < Lin %d rounded up to the stride %d (slack rows must be zero)", in_pitch,
+                 Lin, stride);
   RAVE_CHECK_ARG(act == RAVE_ACT_NONE || act == RAVE_ACT_LEAKY, "conv1d_tc: epilogue activation %d unsupported", act);
   RAVE_CHECK_ARG(((uintptr_t)xa & 15) == 0 && ((uintptr_t)wt & 15) == 0, "conv1d_tc: operands must be 16B aligned");
   EncodeTiledFn enc = get_encode_fn();
@@ -400,8 +403,8 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   // A: channel-last activations viewed as (c, phase, l/stride, b)
   CUtensorMap ta, tb;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)stride, (cuuint64_t)(Lin / stride), (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * stride, (cuuint64_t)Cin * 2 * Lin};
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)stride, (cuuint64_t)ceil_div(Lin, stride), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * stride, (cuuint64_t)Cin * 2 * in_pitch};
     cuuint32_t box[4] = {(cuuint32_t)BK, 1, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(xa), dims, strides, box, estr,
@@ -633,13 +636,18 @@ static int launch_wg(const CUtensorMap &tp, const CUtensorMap &tq, const WgParam
 }  // namespace tc
 }  // namespace rave
 
-extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, int B, int Cm, int Lp, int Cn,
-                                    int Lq, int K, int stride, int dil, int pad_l, void *stream) {
+extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, int B, int Cm, int Lp, int p_pitch,
+                                    int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l,
+                                    void *stream) {
   using namespace rave;
   using namespace rave::tc;
   RAVE_CHECK_ARG(P && Q && dwt, "wgrad_tc: null pointer");
   RAVE_CHECK_ARG(Cm % 8 == 0 && Cn % 8 == 0, "wgrad_tc: channel counts must be multiples of 8 (Cm=%d Cn=%d)", Cm, Cn);
-  RAVE_CHECK_ARG(Lq % stride == 0, "wgrad_tc: Lq %d not a multiple of stride %d", Lq, stride);
+  if (p_pitch <= 0) p_pitch = Lp;
+  if (q_pitch <= 0) q_pitch = Lq;
+  RAVE_CHECK_ARG(q_pitch >= ceil_div(Lq, stride) * stride,
+                 "wgrad_tc: Q pitch %d < Lq %d rounded up to the stride %d (slack rows must be zero)", q_pitch, Lq,
+                 stride);
   EncodeTiledFn enc = get_encode_fn();
   RAVE_CHECK_ARG(enc, "wgrad_tc: cuTensorMapEncodeTiled not available");
   cudaStream_t s = (cudaStream_t)stream;
@@ -674,7 +682,7 @@ extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, in
   CUtensorMap tp, tq;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cm, 1, (cuuint64_t)Lp, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)Cm * 2, (cuuint64_t)Cm * 2, (cuuint64_t)Cm * 2 * Lp};
+    cuuint64_t strides[3] = {(cuuint64_t)Cm * 2, (cuuint64_t)Cm * 2, (cuuint64_t)Cm * 2 * p_pitch};
     cuuint32_t box[4] = {64, 1, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(P), dims, strides, box, estr,
@@ -683,8 +691,8 @@ extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, in
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "wgrad_tc: tensor map P encode failed (%d)", (int)r);
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Cn, (cuuint64_t)stride, (cuuint64_t)(Lq / stride), (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)Cn * 2, (cuuint64_t)Cn * 2 * stride, (cuuint64_t)Cn * 2 * Lq};
+    cuuint64_t dims[4] = {(cuuint64_t)Cn, (cuuint64_t)stride, (cuuint64_t)ceil_div(Lq, stride), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cn * 2, (cuuint64_t)Cn * 2 * stride, (cuuint64_t)Cn * 2 * q_pitch};
     cuuint32_t box[4] = {64, 1, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(Q), dims, strides, box, estr,

@@ -327,3 +327,145 @@ extern "C" int rave_cl_to_ncl(const float *x_cl, float *y, int B, int C, int L, 
   RAVE_CHECK_LAUNCH("cl_to_ncl");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// fused weight preparation for the tensor-core engine:
+//   row norms (weight norm)  ->  tap-major bf16 operand layouts for forward AND dgrad in one pass,
+// and the inverse on the way back (tap-major fp32 wgrad -> dv, dg).
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+struct TapList {
+  int n;
+  int tap[32];
+};
+
+__global__ void __launch_bounds__(256)
+weight_rownorm_kernel(const float *__restrict__ v, float *__restrict__ norm, int R) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float *vr = v + (size_t)c * R;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) s = fmaf(vr[i], vr[i], s);
+  const float n = sqrtf(block_reduce_sum(s, red));
+  if (threadIdx.x == 0) norm[c] = n;
+}
+
+// v [C0][C1][K] fp32 (+ g[C0], norm[C0] or null) ->
+//   outA[t][c0][c1] = bf16(w[c0][c1][tapsA[t]])   dims [nA][C0p][C1p]   (zero in the padded region)
+//   outB[t][c1][c0] = bf16(w[c0][c1][tapsB[t]])   dims [nB][C1p][C0p]
+// grid (C1p/32, C0p/32), block (32, 8); dynamic smem 32 * (32*K + 1) floats.
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(const float *__restrict__ v, const float *__restrict__ g, const float *__restrict__ norm,
+                   __nv_bfloat16 *__restrict__ outA, TapList tapsA, __nv_bfloat16 *__restrict__ outB,
+                   TapList tapsB, int C0, int C1, int K, int C0p, int C1p) {
+  extern __shared__ float sw[];   // [32 c0][32*K + 1]
+  __shared__ float scale[32];
+  const int pitch = 32 * K + 1;
+  const int c1t = blockIdx.x * 32, c0t = blockIdx.y * 32;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < 32) {
+    const int c0 = c0t + tid;
+    scale[tid] = (c0 < C0) ? (g ? g[c0] / norm[c0] : 1.f) : 0.f;
+  }
+  // load: for each of the 32 rows, the contiguous run of 32*K floats starting at (c0, c1t, 0)
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c0 = c0t + r;
+    for (int i = threadIdx.x; i < 32 * K; i += 32) {
+      const int c1 = c1t + i / K;
+      sw[r * pitch + i] = (c0 < C0 && c1 < C1) ? v[((size_t)c0 * C1 + c1t) * K + i] : 0.f;
+    }
+  }
+  __syncthreads();
+  if (outA) {
+    for (int t = 0; t < tapsA.n; ++t) {
+      const int k = tapsA.tap[t];
+      for (int r = threadIdx.y; r < 32; r += 8) {
+        const int c0 = c0t + r, c1 = c1t + threadIdx.x;
+        if (c0 < C0p && c1 < C1p)
+          outA[((size_t)t * C0p + c0) * C1p + c1] = __float2bfloat16_rn(sw[r * pitch + threadIdx.x * K + k] * scale[r]);
+      }
+    }
+  }
+  if (outB) {
+    for (int t = 0; t < tapsB.n; ++t) {
+      const int k = tapsB.tap[t];
+      for (int r = threadIdx.y; r < 32; r += 8) {      // r indexes c1 here, threadIdx.x indexes c0
+        const int c1 = c1t + r, c0 = c0t + threadIdx.x;
+        if (c0 < C0p && c1 < C1p)
+          outB[((size_t)t * C1p + c1) * C0p + c0] =
+              __float2bfloat16_rn(sw[threadIdx.x * pitch + r * K + k] * scale[threadIdx.x]);
+      }
+    }
+  }
+}
+
+// dwt [K][C0p][C1p] fp32 (tap-major wgrad) -> dv [C0][C1][K], dg [C0]   (g == null: dv = dw)
+__global__ void __launch_bounds__(256)
+weight_norm_bwd_tapmajor_kernel(const float *__restrict__ dwt, const float *__restrict__ v,
+                                const float *__restrict__ g, const float *__restrict__ norm,
+                                float *__restrict__ dv, float *__restrict__ dg, int C1, int K, int C0p, int C1p) {
+  __shared__ float red[32];
+  const int c0 = blockIdx.x;
+  const int R = C1 * K;
+  const float *vr = v + (size_t)c0 * R;
+  float s = 0.f;
+  if (g) {
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+      const int c1 = i / K, k = i - c1 * K;
+      s = fmaf(dwt[((size_t)k * C0p + c0) * C1p + c1], vr[i], s);
+    }
+  }
+  const float dot = g ? block_reduce_sum(s, red) : 0.f;
+  const float n = g ? norm[c0] : 1.f;
+  const float gn = g ? g[c0] / n : 1.f;
+  const float coef = g ? dot / (n * n) : 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    const int c1 = i / K, k = i - c1 * K;
+    dv[(size_t)c0 * R + i] = gn * (dwt[((size_t)k * C0p + c0) * C1p + c1] - vr[i] * coef);
+  }
+  if (g && threadIdx.x == 0) dg[c0] = dot / n;
+}
+
+}  // namespace rave
+
+extern "C" int rave_weight_prep_tc(const float *v, const float *g, float *norm, void *outA, const int *tapsA,
+                                   int nA, void *outB, const int *tapsB, int nB, int C0, int C1, int K, int C0p,
+                                   int C1p, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(v && (outA || outB) && C0 > 0 && C1 > 0 && K > 0 && K <= 32, "weight_prep: bad argument");
+  RAVE_CHECK_ARG(nA <= 32 && nB <= 32 && C0p >= C0 && C1p >= C1, "weight_prep: bad tap list / padding");
+  RAVE_CHECK_ARG(!g || norm, "weight_prep: weight norm needs a norm buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g) {
+    weight_rownorm_kernel<<<C0, 256, 0, s>>>(v, norm, C1 * K);
+    RAVE_CHECK_LAUNCH("weight_rownorm");
+  }
+  TapList ta, tb;
+  ta.n = outA ? nA : 0;
+  tb.n = outB ? nB : 0;
+  for (int i = 0; i < ta.n; ++i) ta.tap[i] = tapsA[i];
+  for (int i = 0; i < tb.n; ++i) tb.tap[i] = tapsB[i];
+  const int smem = 32 * (32 * K + 1) * sizeof(float);
+  static int attr_bytes = 0;
+  if (smem > 48 * 1024 && smem > attr_bytes) {
+    cudaFuncSetAttribute(weight_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (32 * 32 + 1) * 4);
+    attr_bytes = 32 * (32 * 32 + 1) * 4;
+  }
+  dim3 grid(ceil_div(C1p, 32), ceil_div(C0p, 32)), block(32, 8);
+  weight_prep_kernel<<<grid, block, smem, s>>>(v, g, norm, (__nv_bfloat16 *)outA, ta, (__nv_bfloat16 *)outB, tb,
+                                               C0, C1, K, C0p, C1p);
+  RAVE_CHECK_LAUNCH("weight_prep");
+  return 0;
+}
+
+extern "C" int rave_weight_norm_bwd_tapmajor(const float *dwt, const float *v, const float *g, const float *norm,
+                                             float *dv, float *dg, int C0, int C1, int K, int C0p, int C1p,
+                                             void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(dwt && v && dv && C0 > 0 && C1 > 0 && K > 0, "weight_norm_bwd_tapmajor: bad argument");
+  RAVE_CHECK_ARG(!g || (norm && dg), "weight_norm_bwd_tapmajor: weight norm needs norm and dg");
+  weight_norm_bwd_tapmajor_kernel<<<C0, 256, 0, (cudaStream_t)stream>>>(dwt, v, g, norm, dv, dg, C1, K, C0p, C1p);
+  RAVE_CHECK_LAUNCH("weight_norm_bwd_tapmajor");
+  return 0;
+}

@@ -79,7 +79,46 @@ class ConvNet(nn.Module):
         net.append(conv(int(channels[-1]), out_size, 1))
         self.net = nn.Sequential(*net)
 
+    def _tc_specs(self):
+        from . import engine
+        if "_tc_specs_cache" not in self.__dict__:
+            specs = engine.plan_convnet(self.net)
+            if specs is not None and not engine.chain_supported(specs):
+                specs = None
+            self.__dict__["_tc_specs_cache"] = specs
+        return self.__dict__["_tc_specs_cache"]
+
+    def _forward_tc(self, x, specs):
+        """bf16 tensor-core path: the whole ConvNet as one chain in channel-last layout; features come
+        back as permuted views with the reference's shapes."""
+        from . import engine
+        first = specs[0]
+        cpad = first.cin_pad
+        if x.dim() == 3:
+            B, C, L = x.shape
+            rows = x.transpose(1, 2)
+        else:
+            B, C, L, W = x.shape
+            rows = x.permute(0, 3, 2, 1).reshape(B * W, L, C)
+        rpad = (-L) % first.stride              # row pitch: a multiple of the first layer's stride
+        xa = nn.functional.pad(rows, (0, cpad, 0, rpad)).to(torch.bfloat16).contiguous()
+        outs = engine.run_chain(xa, specs, L)
+        lens = engine.chain_lengths(specs, L)
+        features = []
+        for s, o, Lo in zip(specs, outs, lens):
+            o = o[:, :Lo, :s.Cout]
+            if x.dim() == 3:
+                features.append(o.permute(0, 2, 1))
+            else:
+                features.append(o.reshape(B, W, Lo, s.Cout).permute(0, 3, 2, 1))
+        return features
+
     def forward(self, x):
+        from . import engine
+        if engine.precision() == "bf16" and x.is_cuda:
+            specs = self._tc_specs()
+            if specs is not None:
+                return self._forward_tc(x, specs)
         features = []
         pending_act = None
         for layer in self.net:

@@ -1,0 +1,472 @@
+"""Tensor-core execution engine: runs a whole conv chain (EncoderV2.net, GeneratorV2.net, a
+discriminator ConvNet) on the tcgen05 kernels in the engine's own layout and precision.
+
+Layout / precision ("bf16 mode", BASELINE config 3): every tensor between two convs is CHANNEL-LAST
+([B][L][C]); the operand of each conv is the bf16 tensor `a = act(h)` written by the PRODUCER's
+epilogue; the pre-activation stream `h` is written in fp32 only where a later layer needs it (residual
+skip) or the caller does (discriminator features, chain output).  The module-boundary layout of the
+reference ([B,C,L] fp32) is converted once on entry and once on exit of the chain.
+
+One `torch.autograd.Function` per chain: forward and backward are explicit kernel sequences, so
+autograd sees a single node and no intermediate is kept alive except the bf16 operands the backward
+needs (LeakyReLU'(h) is recovered from the sign of a = act(h)).
+
+Backward of layer i (operand a_in, output gradient g_i in h-space, bf16):
+    wgrad : dWt = sum_rows g_i (x) a_in                 (rave_conv1d_tc_wgrad)
+    dgrad : g_prev = (W^T g_i) * LeakyReLU'(a_in) + skip (rave_conv1d_tc_fwd with transposed taps,
+                                                         `dact_src` = a_in, `res_bf16` = skip/external grad)
+Strided convs' dgrad and ConvTranspose1d's forward are evaluated as `stride` interleaved phases,
+each a stride-1 conv over the taps of that phase (no zero-insertion, no wasted MACs).
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+_state = {"precision": "fp32"}
+
+
+def set_precision(mode: str) -> None:
+    """'fp32' : CUDA-core parity kernels ([B,C,L] fp32, per-layer autograd);
+    'bf16' : tcgen05 engine (bf16 operands, fp32 accumulate) for every chain it supports."""
+    if mode not in ("fp32", "bf16"):
+        raise ValueError(mode)
+    _state["precision"] = mode
+
+
+def precision() -> str:
+    return _state["precision"]
+
+
+@dataclass
+class LayerSpec:
+    kind: str                      # 'conv' | 'convT'
+    module: nn.Module              # owner of weight(_v/_g) / bias
+    Cin: int
+    Cout: int
+    K: int
+    stride: int = 1
+    dil: int = 1
+    pad: Tuple[int, int] = (0, 0)  # conv: (left, right); convT: (padding, padding)
+    pre_act: int = ops.ACT_NONE    # activation applied to this layer's INPUT (emitted by its producer)
+    pre_slope: float = 0.2
+    res_src: Optional[int] = None  # index of the layer whose fp32 stream is added (-1 = chain input)
+    want_f32: bool = False         # fp32 stream needed (residual source or external output)
+    is_output: bool = False        # returned to the caller (fp32, channel-last)
+    cin_pad: int = 0               # zero-padded input channels (Cin=1 layers run with Cin=16)
+    cout_pad: int = 0
+
+
+def chain_supported(specs: List[LayerSpec]) -> bool:
+    for s in specs:
+        if s.pre_act not in (ops.ACT_NONE, ops.ACT_LEAKY):
+            return False
+        cin = s.Cin + s.cin_pad
+        cout = s.Cout + s.cout_pad
+        if cin % 16 or cout % 16:
+            return False
+    return True
+
+
+# ----------------------------------------------------------------------------------------------
+# planning: walk a module list into LayerSpecs
+# ----------------------------------------------------------------------------------------------
+
+def _act_of(m):
+    from . import cc
+    code = cc._act_code(m)
+    return code
+
+
+def plan_sequential(mods: List[nn.Module]) -> Optional[List[LayerSpec]]:
+    """EncoderV2.net / GeneratorV2.net style sequences: activations, cc.Conv1d, cc.ConvTranspose1d,
+    Residual(DilatedUnit), AdaIN (identity in training).  Returns None if something is unsupported."""
+    from . import blocks, cc
+    specs: List[LayerSpec] = []
+    pending = (ops.ACT_NONE, 0.0)
+    last_idx = -1            # index of the layer producing the current stream (-1 = chain input)
+
+    def add_conv(conv, res_src=None):
+        nonlocal pending, last_idx
+        if isinstance(conv, cc.Conv1d):
+            Cout, Cin, K = conv.out_channels, conv.in_channels, conv.kernel_size[0]
+            spec = LayerSpec("conv", conv, Cin, Cout, K, conv.stride[0], conv.dilation[0], conv._pad,
+                             pending[0], pending[1], res_src)
+        else:
+            Cin, Cout, K = conv.in_channels, conv.out_channels, conv.kernel_size[0]
+            spec = LayerSpec("convT", conv, Cin, Cout, K, conv.stride[0], 1,
+                             (conv.padding[0], conv.padding[0]), pending[0], pending[1], None)
+        specs.append(spec)
+        pending = (ops.ACT_NONE, 0.0)
+        last_idx = len(specs) - 1
+
+    for m in mods:
+        if isinstance(m, blocks.AdaptiveInstanceNormalization):
+            if not m.training:
+                return None
+            continue
+        if isinstance(m, nn.LeakyReLU):
+            pending = (ops.ACT_LEAKY, float(m.negative_slope))
+            continue
+        if isinstance(m, blocks.Snake):
+            return None            # Snake epilogue not on the tensor-core path yet
+        if isinstance(m, (cc.Conv1d, cc.ConvTranspose1d)):
+            add_conv(m)
+            continue
+        if isinstance(m, blocks.Residual):
+            unit = m.aligned.branches[0]
+            if not isinstance(unit, blocks.DilatedUnit):
+                return None
+            if pending[0] != ops.ACT_NONE:
+                return None
+            src = last_idx
+            if src >= 0:
+                specs[src].want_f32 = True
+            a0, c3, a1, c1 = list(unit.net)
+            for a in (a0, a1):
+                if not isinstance(a, nn.LeakyReLU):
+                    return None
+            pending = (ops.ACT_LEAKY, float(a0.negative_slope))
+            add_conv(c3)
+            pending = (ops.ACT_LEAKY, float(a1.negative_slope))
+            add_conv(c1, res_src=src)
+            continue
+        return None
+    if pending[0] != ops.ACT_NONE or not specs:
+        return None
+    specs[-1].is_output = True
+    specs[-1].want_f32 = True
+    return specs
+
+
+def plan_convnet(net: nn.Sequential) -> Optional[List[LayerSpec]]:
+    """discriminator.ConvNet.net: [conv, LeakyReLU]*n + conv; every conv output is a feature.
+    Works for DiscConv1d and DiscConv2dK1 (the latter over the folded [B*p, H, C] view)."""
+    from . import discriminator as D
+    specs: List[LayerSpec] = []
+    pending = (ops.ACT_NONE, 0.0)
+    for m in net:
+        if isinstance(m, nn.LeakyReLU):
+            pending = (ops.ACT_LEAKY, float(m.negative_slope))
+            continue
+        if isinstance(m, (D.DiscConv1d, D.DiscConv2dK1)):
+            p = m.padding[0]
+            spec = LayerSpec("conv", m, m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0],
+                             m.dilation[0], (p, p), pending[0], pending[1], None, True, True)
+            if spec.Cin % 16:
+                spec.cin_pad = 16 - spec.Cin % 16
+            if spec.Cout % 16:
+                spec.cout_pad = 16 - spec.Cout % 16
+            specs.append(spec)
+            pending = (ops.ACT_NONE, 0.0)
+            continue
+        return None
+    return specs
+
+
+# ----------------------------------------------------------------------------------------------
+# weights
+# ----------------------------------------------------------------------------------------------
+
+def _layer_params(spec: LayerSpec):
+    m = spec.module
+    if hasattr(m, "weight_v"):
+        return m.weight_v, m.weight_g, m.bias
+    return m.weight, None, m.bias
+
+
+def _phase_taps(K: int, stride: int, pad: int, p: int):
+    """Taps of output phase p of a transposed map t = l*stride + k - pad: returns (k list in the
+    order of increasing source row, pad'') such that source row = q + i - pad'' for tap i."""
+    k0 = (p + pad) % stride
+    ks = list(range(k0, K, stride))          # k = k0 + stride*m, m = 0..n-1 ; source row = q + c0 - m
+    c0 = (p + pad - k0) // stride
+    n = len(ks)
+    # tap i (increasing source row) has m = n-1-i  ->  row = q + c0 - (n-1) + i
+    order = [ks[n - 1 - i] for i in range(n)]
+    return order, (n - 1) - c0
+
+
+class _PreparedWeights:
+    """Effective weight of one layer in every tap-major bf16 layout the kernels need, produced from
+    (v, g) by ONE fused launch pair (row norms + re-layout): rave_weight_prep_tc."""
+
+    def __init__(self, spec: LayerSpec, v: torch.Tensor, g: Optional[torch.Tensor], need_dgrad: bool):
+        import ctypes
+        self.spec = spec
+        K, s = spec.K, spec.stride
+        dev = v.device
+        C0, C1 = v.shape[0], v.shape[1]
+        if spec.kind == "conv":
+            C0p, C1p = spec.Cout + spec.cout_pad, spec.Cin + spec.cin_pad
+        else:
+            C0p, C1p = spec.Cin + spec.cin_pad, spec.Cout + spec.cout_pad
+        self.norm = torch.empty(C0, dtype=torch.float32, device=dev) if g is not None else None
+        self.fwd = None           # conv: [K][Cout][Cin]
+        self.fwd_phases = None    # convT: per output phase (wt [n][Cout][Cin], pad'')
+        self.dgrad = None         # stride-1 conv: flipped taps [K][Cin][Cout]; convT: [K][Cin][Cout]
+        self.dgrad_phases = None  # strided conv: per input phase (wt [n][Cin][Cout], pad'')
+        phases = None
+        if spec.kind == "conv":
+            tapsA = list(range(K))
+            if not need_dgrad:
+                tapsB = []
+            elif s == 1:
+                tapsB = list(range(K - 1, -1, -1))
+            else:
+                phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
+                tapsB = [k for order, _ in phases for k in order]
+        else:
+            phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
+            tapsB = [k for order, _ in phases for k in order]
+            tapsA = list(range(K)) if need_dgrad else []
+        outA = torch.empty(len(tapsA), C0p, C1p, dtype=torch.bfloat16, device=dev) if tapsA else None
+        outB = torch.empty(len(tapsB), C1p, C0p, dtype=torch.bfloat16, device=dev) if tapsB else None
+        arrA = (ctypes.c_int * max(1, len(tapsA)))(*tapsA)
+        arrB = (ctypes.c_int * max(1, len(tapsB)))(*tapsB)
+        _lib.call("rave_weight_prep_tc", _lib.ptr(v), _lib.ptr(g), _lib.ptr(self.norm), _lib.ptr(outA), arrA,
+                  len(tapsA), _lib.ptr(outB), arrB, len(tapsB), C0, C1, K, C0p, C1p, _lib.stream_ptr())
+
+        def split(buf):
+            out, off = [], 0
+            for order, padpp in phases:
+                n = len(order)
+                out.append((buf[off:off + n] if n else None, padpp))
+                off += n
+            return out
+
+        if spec.kind == "conv":
+            self.fwd = outA
+            if need_dgrad:
+                if s == 1:
+                    self.dgrad = outB
+                else:
+                    self.dgrad_phases = split(outB)
+        else:
+            self.fwd_phases = split(outB)
+            self.dgrad = outA
+
+
+# ----------------------------------------------------------------------------------------------
+# the chain Function
+# ----------------------------------------------------------------------------------------------
+
+def _out_len(spec: LayerSpec, Lin: int) -> int:
+    if spec.kind == "conv":
+        return ops.conv_out_len(Lin, spec.K, spec.stride, spec.dil, spec.pad[0], spec.pad[1])
+    return (Lin - 1) * spec.stride - 2 * spec.pad[0] + spec.K
+
+
+class TcChainFn(torch.autograd.Function):
+    """forward(x_cl_bf16 [B,L,Cin(+pad)], n_layers, specs, *flat_params) -> tuple of fp32 channel-last
+    outputs (one per spec with is_output)."""
+
+    @staticmethod
+    def forward(ctx, x_cl, specs, L0, *flat):
+        n = len(specs)
+        need_dgrad = x_cl.requires_grad or any(t is not None and t.requires_grad for t in flat)
+        B = x_cl.shape[0]
+        a = x_cl                                     # bf16 operand of the next layer (rows = pitch)
+        f32: Dict[int, torch.Tensor] = {}
+        acts: List[torch.Tensor] = []                 # operand consumed by layer i
+        prepared: List[_PreparedWeights] = []
+        norms: List[Optional[torch.Tensor]] = []
+        lens = [L0]
+        outputs = []
+        for i, s in enumerate(specs):
+            v, g, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
+            pw = _PreparedWeights(s, v.detach(), g.detach() if g is not None else None, need_dgrad)
+            prepared.append(pw)
+            norms.append(pw.norm)
+            Lin = lens[-1]
+            Lout = _out_len(s, Lin)
+            lens.append(Lout)
+            nxt = specs[i + 1] if i + 1 < n else None
+            want_act = nxt is not None
+            act_code = nxt.pre_act if nxt is not None else ops.ACT_NONE
+            act_slope = nxt.pre_slope if nxt is not None else 0.0
+            # rows allocated per batch: the consumer's 4-D tensor map needs a multiple of its stride
+            s_next = nxt.stride if (nxt is not None and nxt.kind == "conv") else 1
+            pitch = (Lout + s_next - 1) // s_next * s_next
+            cout_p = s.Cout + s.cout_pad
+            bias_p = bias
+            if bias is not None and s.cout_pad:
+                bias_p = nn.functional.pad(bias.detach(), (0, s.cout_pad))
+            res = f32[s.res_src] if s.res_src is not None else None
+            out_f32 = torch.empty(B, pitch, cout_p, dtype=torch.float32, device=a.device) if s.want_f32 else None
+            out_act = torch.empty(B, pitch, cout_p, dtype=torch.bfloat16, device=a.device) if want_act else None
+            if pitch > Lout:
+                for t in (out_f32, out_act):
+                    if t is not None:
+                        t[:, Lout:].zero_()
+            acts.append(a)
+            if s.kind == "conv":
+                ops.conv1d_tc(a, pw.fwd, bias_p, res, s.stride, s.dil, s.pad, act_code, act_slope,
+                              want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act, Lout=Lout,
+                              Lin=Lin, out_rows=pitch)
+            else:
+                for p, (wt, padpp) in enumerate(pw.fwd_phases):
+                    if wt is None:
+                        raise _lib.RaveB200Error("transposed conv with an empty phase is not supported")
+                    Lp = (Lout - p + s.stride - 1) // s.stride
+                    ops.conv1d_tc(a, wt, bias_p, None, 1, 1, (padpp, 0), act_code, act_slope, want_f32=False,
+                                  want_act=False, out_f32=out_f32, out_act=out_act, out_rows=pitch,
+                                  out_row_stride=s.stride, out_row_offset=p, Lout=Lp, Lin=Lin)
+            if s.want_f32:
+                f32[i] = out_f32
+            if s.is_output:
+                outputs.append(out_f32)
+            a = out_act
+        ctx.specs = specs
+        ctx.acts = acts
+        ctx.prepared = prepared
+        ctx.norms = norms
+        ctx.lens = lens
+        ctx.params = flat
+        ctx.x_requires_grad = x_cl.requires_grad
+        ctx.out_index = [i for i, s in enumerate(specs) if s.is_output]
+        return tuple(outputs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        specs = ctx.specs
+        n = len(specs)
+        flat = ctx.params
+        B = ctx.acts[0].shape[0]
+        # external gradients (fp32 channel-last, full pitched shape) -> bf16
+        ext: Dict[int, torch.Tensor] = {}
+        for i, g in zip(ctx.out_index, gouts):
+            if g is not None:
+                ext[i] = g.to(torch.bfloat16).contiguous()
+        skip: Dict[int, torch.Tensor] = {}     # residual pass-through gradient for layer idx (or -1)
+        g_cur: Optional[torch.Tensor] = None   # gradient (h-space, bf16) of layer i's output
+        grads = [None] * len(flat)
+        gx = None
+        for i in range(n - 1, -1, -1):
+            s = specs[i]
+            pw = ctx.prepared[i]
+            a_in = ctx.acts[i]
+            Lin, Lout = ctx.lens[i], ctx.lens[i + 1]
+            g = g_cur
+            if g is None:
+                g = ext.get(i)
+                if g is None:
+                    raise _lib.RaveB200Error("chain backward: no gradient reaches the last layer")
+            if s.res_src is not None:
+                skip[s.res_src] = g
+            cin_p, cout_p = s.Cin + s.cin_pad, s.Cout + s.cout_pad
+            v, gpar, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
+            # ---- weight gradient
+            if v.requires_grad:
+                if s.kind == "conv":
+                    dwt = ops.conv1d_tc_wgrad(g, a_in, s.K, s.stride, s.dil, s.pad[0], Lp=Lout, Lq=Lin)
+                else:
+                    dwt = ops.conv1d_tc_wgrad(a_in, g, s.K, s.stride, 1, s.pad[0], Lp=Lin, Lq=Lout)
+                # dwt is [K][C0p][C1p] in the parameter's own (C0, C1) order for both kinds
+                dv = torch.empty_like(v)
+                dg = torch.empty_like(gpar) if gpar is not None else None
+                _lib.call("rave_weight_norm_bwd_tapmajor", _lib.ptr(dwt), _lib.ptr(v), _lib.ptr(gpar),
+                          _lib.ptr(ctx.norms[i]), _lib.ptr(dv), _lib.ptr(dg), v.shape[0], v.shape[1], s.K,
+                          dwt.shape[1], dwt.shape[2], _lib.stream_ptr())
+                grads[3 * i], grads[3 * i + 1] = dv, dg
+            if bias is not None and bias.requires_grad:
+                grads[3 * i + 2] = g[:, :Lout, :s.Cout].float().sum((0, 1))
+            # ---- input gradient
+            need_prev = i > 0 or ctx.x_requires_grad
+            if not need_prev:
+                break
+            prev = i - 1
+            add = None
+            if prev in skip:
+                add = skip.pop(prev)
+            e = ext.get(prev) if prev >= 0 else None
+            if e is not None:
+                add = e if add is None else (add + e)
+            dact = a_in if s.pre_act == ops.ACT_LEAKY else None
+            in_pitch = a_in.shape[1]
+            gp = torch.empty(B, in_pitch, cin_p, dtype=torch.bfloat16, device=g.device)
+            if in_pitch > Lin:
+                gp[:, Lin:].zero_()
+            if s.kind == "conv":
+                if s.stride == 1:
+                    padp = (s.K - 1) * s.dil - s.pad[0]
+                    ops.conv1d_tc(g, pw.dgrad, None, None, 1, s.dil, (padp, 0), ops.ACT_NONE, s.pre_slope,
+                                  want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout,
+                                  out_rows=in_pitch, res_bf16=add, dact_src=dact)
+                else:
+                    for p, (wt, padpp) in enumerate(pw.dgrad_phases):
+                        Lp = (Lin - p + s.stride - 1) // s.stride
+                        if wt is None:
+                            raise _lib.RaveB200Error("strided conv with an empty dgrad phase is not supported")
+                        ops.conv1d_tc(g, wt, None, None, 1, 1, (padpp, 0), ops.ACT_NONE, s.pre_slope,
+                                      want_f32=False, want_act=False, out_act=gp, out_rows=in_pitch,
+                                      out_row_stride=s.stride, out_row_offset=p, Lout=Lp, Lin=Lout, res_bf16=add,
+                                      dact_src=dact)
+            else:
+                ops.conv1d_tc(g, pw.dgrad, None, None, s.stride, 1, (s.pad[0], 0), ops.ACT_NONE, s.pre_slope,
+                              want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout, out_rows=in_pitch,
+                              res_bf16=add, dact_src=dact)
+            g_cur = gp
+            if i == 0:
+                gx = gp
+        return (gx, None, None) + tuple(grads)
+
+
+def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None):
+    """x_cl_bf16: [B, pitch, Cin(+pad)] (rows beyond the true length L0 must be zero).  Returns one fp32
+    channel-last tensor [B, pitch_i, Cout_i(+pad)] per output layer (slice [:, :L_i, :Cout_i])."""
+    flat = []
+    for s in specs:
+        v, g, b = _layer_params(s)
+        flat += [v, g, b]
+    if L0 is None:
+        L0 = x_cl_bf16.shape[1]
+    return TcChainFn.apply(x_cl_bf16, specs, L0, *flat)
+
+
+def chain_lengths(specs: List[LayerSpec], L0: int) -> List[int]:
+    out, L = [], L0
+    for s in specs:
+        L = _out_len(s, L)
+        out.append(L)
+    return out
+
+
+class _ToChannelLast(torch.autograd.Function):
+    """[B,C,L] fp32 -> [B,L,C(+pad)] bf16; backward converts the bf16 channel-last gradient back."""
+
+    @staticmethod
+    def forward(ctx, x, cpad):
+        yb, _ = ops.ncl_to_cl(x)
+        ctx.C = x.shape[1]
+        if cpad:
+            yb = nn.functional.pad(yb, (0, cpad))
+        return yb
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[..., :ctx.C].float().permute(0, 2, 1).contiguous(), None
+
+
+class _FromChannelLast(torch.autograd.Function):
+    """[B,L,C] fp32 channel-last -> [B,C,L] fp32 (kernel transpose both ways)."""
+
+    @staticmethod
+    def forward(ctx, x_cl):
+        return ops.cl_to_ncl(x_cl)
+
+    @staticmethod
+    def backward(ctx, g):
+        _, gf = ops.ncl_to_cl(g.contiguous(), want_bf16=False, want_f32=True)
+        return gf
+
+
+def to_channel_last(x, cpad=0):
+    return _ToChannelLast.apply(x, cpad)
+
+
+def from_channel_last(x_cl):
+    return _FromChannelLast.apply(x_cl)

@@ -379,10 +379,12 @@ def conv1d_tc_supported(Cin, Cout, K=1, stride=1, dil=1):
 
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=ACT_NONE, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
-              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None):
+              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None):
     """xa_cl [B,Lin,Cin] bf16 (activated operand), wt [K,Cout,Cin] bf16 -> (out_f32 [B,Lout,Cout] fp32,
     out_act [B,Lout,Cout] bf16 = act(out)); either may be None."""
-    B, Lin, Cin = xa_cl.shape
+    B, in_pitch, Cin = xa_cl.shape          # allocated rows per batch; true length = Lin (slack rows zero)
+    if Lin is None:
+        Lin = in_pitch
     K, Cout, Cin_w = wt.shape
     if Cin_w != Cin or xa_cl.dtype != torch.bfloat16 or wt.dtype != torch.bfloat16:
         raise _lib.RaveB200Error("conv1d_tc: operand mismatch")
@@ -394,20 +396,23 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     if want_act and out_act is None:
         out_act = torch.empty(B, rows, Cout, dtype=torch.bfloat16, device=xa_cl.device)
     call("rave_conv1d_tc_fwd", ptr(xa_cl), ptr(wt), ptr(bias), ptr(res_cl), ptr(res_bf16), ptr(dact_src),
-         ptr(out_f32), ptr(out_act), B, Cin, Lin, Cout, Lout, K, stride, dil, pad[0], act, float(slope),
+         ptr(out_f32), ptr(out_act), B, Cin, Lin, in_pitch, Cout, Lout, K, stride, dil, pad[0], act, float(slope),
          out_rows, out_row_stride, out_row_offset, stream_ptr())
     return out_f32, out_act
 
 
-def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0):
-    """dwt[k][m][n] = sum_{b,l} P[b,l,m] * Q[b, l*stride + k*dil - pad_l, n]  (bf16 operands, fp32 result)."""
-    B, Lp, Cm = P_cl.shape
-    _, Lq, Cn = Q_cl.shape
+def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None):
+    """dwt[k][m][n] = sum_{b,l} P[b,l,m] * Q[b, l*stride + k*dil - pad_l, n]  (bf16 operands, fp32 result).
+    Tensors may be allocated with a row pitch larger than their true length (Lp / Lq)."""
+    B, p_pitch, Cm = P_cl.shape
+    _, q_pitch, Cn = Q_cl.shape
+    Lp = p_pitch if Lp is None else Lp
+    Lq = q_pitch if Lq is None else Lq
     if P_cl.dtype != torch.bfloat16 or Q_cl.dtype != torch.bfloat16:
         raise _lib.RaveB200Error("conv1d_tc_wgrad: operands must be bf16")
     dwt = torch.empty(K, Cm, Cn, dtype=torch.float32, device=P_cl.device)
-    call("rave_conv1d_tc_wgrad", ptr(P_cl), ptr(Q_cl), ptr(dwt), B, Cm, Lp, Cn, Lq, K, stride, dil, pad_l,
-         stream_ptr())
+    call("rave_conv1d_tc_wgrad", ptr(P_cl), ptr(Q_cl), ptr(dwt), B, Cm, Lp, p_pitch, Cn, Lq, q_pitch, K, stride,
+         dil, pad_l, stream_ptr())
     return dwt
 
 

@@ -1,0 +1,124 @@
+"""GPU: the channel-last tensor-core ENGINE (bf16 mode) end to end against the fp32 CPU oracle.
+
+Stated bf16-mode tolerances (operands rounded to bf16, fp32 accumulate; SURVEY 7.2 measures 8.7-9.6e-3
+for operand rounding alone through the v2 autoencoder): forward rel-L2 <= 3e-2, gradients rel-L2 <= 8e-2
+(and cosine similarity >= 0.995)."""
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import rave_oracle as O
+from tests.conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 3e-2
+BWD_TOL = 8e-2
+
+
+def cos(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+
+
+@pytest.fixture(autouse=True)
+def bf16_mode():
+    import rave_b200
+    rave_b200.set_precision("bf16")
+    yield
+    rave_b200.set_precision("fp32")
+
+
+@pytest.mark.parametrize("ratios", [[4, 4, 4, 2], [4, 2, 2, 2]])
+def test_autoencoder_bf16_vs_oracle(ratios):
+    from rave_b200 import configs
+    from rave_b200.model import _pqmf_decode, _pqmf_encode
+    torch.manual_seed(3)
+    pq, enc, dec = configs.make_autoencoder("v2", capacity=16, latent_size=16, ratios=ratios)
+    assert enc.encoder.net._tc_plan() is not None and dec.net._tc_plan() is not None
+    holder = nn.Module()
+    holder.pqmf, holder.encoder, holder.decoder = pq, enc, dec
+    sd = {k: v.detach().clone() for k, v in holder.state_dict().items()}
+    T = 16384
+    x = (0.5 * torch.randn(2, 1, T)).clamp(-1, 1)
+    cfg = O.ArchConfig(capacity=16, latent_size=16, ratios=ratios)
+    Lz = T // 16
+    for r in ratios:
+        Lz //= r
+    eps = torch.randn(2, 16, Lz)
+    probe = torch.randn(2, 1, T)
+    # oracle forward/backward (fp32 CPU)
+    params_o = {k: v.clone().requires_grad_(v.is_floating_point() and not k.startswith("pqmf")) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    taps = {}
+    y_o = O.rave_forward(xo, params_o, cfg, eps, taps)
+    names = sorted(k for k, v in params_o.items() if v.requires_grad)
+    grads_o = torch.autograd.grad((y_o * probe).sum(), [xo] + [params_o[k] for k in names])
+    # engine
+    holder.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    z = enc(_pqmf_encode(pq, xg))
+    zs, _ = enc.reparametrize(z, eps.cuda())
+    y = _pqmf_decode(pq, dec(zs), batch_size=xg.shape[:-2], n_channels=1)
+    assert y.shape == y_o.shape
+    assert rel_l2(z, taps["z"]) < FWD_TOL
+    assert rel_l2(y, y_o) < FWD_TOL
+    pg = dict(enc.named_parameters(prefix="encoder"))
+    pg.update(dict(dec.named_parameters(prefix="decoder")))
+    grads_g = torch.autograd.grad((y * probe.cuda()).sum(), [xg] + [pg[k] for k in names])
+    assert rel_l2(grads_g[0], grads_o[0]) < BWD_TOL and cos(grads_g[0], grads_o[0]) > 0.995
+    worst = 0.0
+    for k, a, b in zip(names, grads_g[1:], grads_o[1:]):
+        r = rel_l2(a, b)
+        worst = max(worst, r)
+        assert cos(a, b) > 0.99, (k, cos(a, b), r)
+    assert worst < 0.15, worst
+
+
+def test_discriminator_bf16_vs_oracle():
+    from rave_b200 import configs
+    torch.manual_seed(5)
+    holder = nn.Module()
+    holder.discriminator = configs.make_discriminator_v2(capacity=16)
+    sd = {k: v.detach().clone() for k, v in holder.state_dict().items()}
+    x = (0.5 * torch.randn(4, 1, 8192 + 3)).clamp(-1, 1)
+    params_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    feats_o = O.combine_discriminators_v2(xo, params_o)
+    fm_o, ld_o, la_o = O.gan_losses(feats_o, 1, True)
+    names = sorted(params_o)
+    grads_o = torch.autograd.grad(fm_o + ld_o + la_o, [xo] + [params_o[k] for k in names])
+    disc = holder.discriminator.cuda()
+    xg = x.cuda().requires_grad_(True)
+    feats = disc(xg)
+    assert len(feats) == 8
+    for fa, fb in zip(feats, feats_o):
+        assert len(fa) == 5
+        for a, b in zip(fa, fb):
+            assert a.shape == b.shape
+            assert rel_l2(a, b) < FWD_TOL
+    fm, ld, la = O.gan_losses(feats, 1, True)
+    assert rel_l2(fm, fm_o) < FWD_TOL and rel_l2(ld, ld_o) < FWD_TOL
+    pp = dict(disc.named_parameters(prefix="discriminator"))
+    grads = torch.autograd.grad(fm + ld + la, [xg] + [pp[k] for k in names])
+    assert cos(grads[0], grads_o[0]) > 0.99 and rel_l2(grads[0], grads_o[0]) < 0.15
+    for k, a, b in zip(names, grads[1:], grads_o[1:]):
+        assert cos(a, b) > 0.98, (k, cos(a, b), rel_l2(a, b))
+
+
+def test_training_step_bf16_runs():
+    import rave_b200
+    from rave_b200 import _lib, configs
+    torch.manual_seed(0)
+    m = configs.build_rave("v2", capacity=16, latent_size=16, disc_capacity=16).cuda().train()
+    x = (0.5 * torch.randn(2, 1, 65536, device="cuda")).clamp(-1, 1)
+    w0 = m.decoder.net[0].weight_v.detach().clone()
+    m.training_step(x, 1)
+    assert not torch.equal(w0, m.decoder.net[0].weight_v)
+    m.warmed_up = True
+    d0 = m.discriminator.discriminators[1].layers[0].net[0].weight_v.detach().clone()
+    logs = m.training_step(x, 0)
+    assert not torch.equal(d0, m.discriminator.discriminators[1].layers[0].net[0].weight_v)
+    logs = m.training_step(x, 1)
+    for k in ("fullband_spectral_distance", "feature_matching", "adversarial", "loss_dis"):
+        assert torch.isfinite(logs[k]), k
