@@ -105,14 +105,15 @@ def cpu_reference_run(args, steps, warmup, budget_s):
     import torch
     from oracle import rave_oracle as O
     from rave_b200 import configs
-    cores = os.cpu_count() or 1
+    # oneDNN convs of this size stop scaling (and regress) far below 128 threads: use one socket's worth
+    cores = min(os.cpu_count() or 1, int(os.environ.get("RAVE_CPU_THREADS", "32")))
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     m = configs.build_rave(args.config, sampling_rate=SR)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     del m
     cfg = O.ArchConfig() if args.config == "v2" else O.v2_small_config()
-    B_cpu = 1
+    B_cpu = 2
     x = synthetic_batch(B_cpu)
     eps = torch.randn(B_cpu, cfg.latent_size, T // (16 * int(__import__("numpy").prod(cfg.ratios))))
     times = []

@@ -181,6 +181,52 @@ class DilatedUnit(nn.Module):
         return self.net(x, res=res)
 
 
+class NoiseGeneratorV2(nn.Module):
+    """v2_small's filtered-noise branch (rave/blocks.py:243-292, configs/v2_small.gin:42-57): strided
+    convs (library kernels) -> band amplitudes -> FIR via irfft -> uniform noise -> FFT convolution
+    (torch/cuFFT: SURVEY 8f.4).  `forward(x, noise=None)`: a caller may inject the uniform noise
+    (parity tests: CPU and CUDA Philox streams differ)."""
+
+    def __init__(self, in_size: int, hidden_size: int, data_size: int, ratios, noise_bands: int,
+                 n_channels: int = 1, activation: Callable[[int], nn.Module] = _default_activation):
+        super().__init__()
+        from .core import amp_to_impulse_response, fft_convolve, mod_sigmoid  # noqa: F401
+        self.n_channels = n_channels
+        channels = [in_size]
+        channels.extend((len(ratios) - 1) * [hidden_size])
+        channels.append(data_size * noise_bands * n_channels)
+        net = []
+        for i, r in enumerate(ratios):
+            net.append(cc.Conv1d(channels[i], channels[i + 1], 2 * r, padding=(r, 0), stride=r))
+            if i != len(ratios) - 1:
+                net.append(activation(channels[i + 1]))
+        self.net = nn.Sequential(*net)
+        self.data_size = data_size
+        self.register_buffer("target_size", torch.tensor(int(np.prod(ratios))).long())
+
+    def forward(self, x, noise: Optional[torch.Tensor] = None):
+        from .core import amp_to_impulse_response, fft_convolve, mod_sigmoid
+        h = x
+        mods = list(self.net)
+        i = 0
+        while i < len(mods):               # conv, then `activation -> conv` pairs fused
+            m = mods[i]
+            if isinstance(m, cc.Conv1d):
+                h = m(h)
+                i += 1
+            else:
+                h = mods[i + 1](h, act=m)
+                i += 2
+        amp = mod_sigmoid(h - 5)
+        amp = amp.permute(0, 2, 1)
+        amp = amp.reshape(amp.shape[0], amp.shape[1], self.n_channels * self.data_size, -1)
+        ir = amp_to_impulse_response(amp, self.target_size)
+        if noise is None:
+            noise = torch.rand_like(ir) * 2 - 1
+        out = fft_convolve(noise, ir).permute(0, 2, 1, 3)
+        return out.reshape(out.shape[0], out.shape[1], -1)
+
+
 def normalize_dilations(dilations, ratios):
     if isinstance(dilations[0], int):
         dilations = [dilations for _ in ratios]

@@ -10,7 +10,7 @@ from functools import partial
 
 import torch.nn as nn
 
-from . import blocks, cc, core, discriminator, pqmf
+from . import blocks, cc, core, discriminator, pqmf, quantization
 from .model import RAVE
 
 V2_DILATIONS = [[1, 3, 9], [1, 3, 9], [1, 3, 9], [1, 3]]          # configs/v2.gin:13-18
@@ -23,6 +23,10 @@ ARCH = {
                      disc="v2", update_discriminator_every=2, phase_1_duration=1000000),
     "v3": dict(capacity=96, ratios=[4, 4, 4, 2], activation="snake", adain=True,       # v3.gin:3-13
                disc="descript", update_discriminator_every=4, phase_1_duration=1000000),
+    # discrete.gin:13-49 (EnCodec-style RVQ head; generator latent = 128 + 128 noise channels)
+    "discrete": dict(capacity=96, ratios=[4, 4, 2, 2], activation="leaky", adain=False, disc="v2",
+                     update_discriminator_every=4, phase_1_duration=200000, discrete=True,
+                     noise_augmentation=128, log_epsilon=1.0, num_skipped_features=0),
 }
 
 
@@ -33,7 +37,7 @@ def _activation_factory(kind):
 
 
 def make_autoencoder(name="v2", capacity=None, latent_size=128, n_band=16, n_channels=1,
-                     padding_mode="centered", ratios=None, activation=None, adain=None):
+                     padding_mode="centered", ratios=None, activation=None, adain=None, with_noise=False):
     """(pqmf, encoder, decoder) factories -> constructed modules for one architecture."""
     a = ARCH[name]
     capacity = capacity or a["capacity"]
@@ -48,10 +52,14 @@ def make_autoencoder(name="v2", capacity=None, latent_size=128, n_band=16, n_cha
                     latent_size=latent_size, n_out=2, kernel_size=3, dilations=V2_DILATIONS,
                     activation=act, adain=adain_f),
             n_channels=n_channels)
+        noise = None
+        if name == "v2_small" and with_noise:                                  # v2_small.gin:42-57
+            noise = partial(blocks.NoiseGeneratorV2, hidden_size=64, data_size=n_band, ratios=[2, 2, 2],
+                            noise_bands=32, activation=act)
         dec = blocks.GeneratorV2(data_size=n_band, capacity=capacity, ratios=ratios,  # v2.gin:43-50
                                  latent_size=latent_size, kernel_size=3, dilations=V2_DILATIONS,
                                  amplitude_modulation=True, activation=act, adain=adain_f,
-                                 n_channels=n_channels)
+                                 n_channels=n_channels, noise_module=noise)
     return pq, enc, dec
 
 
@@ -77,28 +85,44 @@ def build_rave(name="v2", sampling_rate=48000, capacity=None, latent_size=128, n
     rat = ratios or a["ratios"]
     stft = partial(core.MultiScaleSTFT, scales=[2048, 1024, 512, 256, 128],        # v1.gin:21-28
                    sample_rate=sampling_rate, magnitude=True)
-    distance = partial(core.AudioDistanceV1, multiscale_stft=stft, log_epsilon=1e-7)  # v2.gin:23
+    distance = partial(core.AudioDistanceV1, multiscale_stft=stft, log_epsilon=a.get("log_epsilon", 1e-7))
     if a["disc"] == "v2":
         disc = lambda n_channels=1: make_discriminator_v2(disc_capacity or cap, n_channels)
     else:
         from .descript_discriminator import DescriptDiscriminator
         disc = lambda n_channels=1: DescriptDiscriminator(n_channels=n_channels)
+    noise_aug = a.get("noise_augmentation", 0)
+    if a.get("discrete"):
+        encoder = partial(blocks.DiscreteEncoder,                                # discrete.gin:26-38
+                          encoder_cls=partial(blocks.EncoderV2, data_size=16, capacity=cap, ratios=rat,
+                                              latent_size=latent_size, n_out=1, kernel_size=3,
+                                              dilations=V2_DILATIONS, activation=act, adain=adain_f),
+                          vq_cls=partial(quantization.ResidualVectorQuantization, num_quantizers=16,
+                                         dim=latent_size, codebook_size=1024),
+                          num_quantizers=16, noise_augmentation=noise_aug)
+    else:
+        encoder = partial(blocks.VariationalEncoder,
+                          partial(blocks.EncoderV2, data_size=16, capacity=cap, ratios=rat,
+                                  latent_size=latent_size, n_out=2, kernel_size=3,
+                                  dilations=V2_DILATIONS, activation=act, adain=adain_f))
+    noise = None
+    if name == "v2_small":                                                       # v2_small.gin:42-57
+        noise = partial(blocks.NoiseGeneratorV2, hidden_size=64, data_size=16, ratios=[2, 2, 2],
+                        noise_bands=32, activation=act)
     with cc.configure(conv_bias=False, padding_mode=padding_mode):
         model = RAVE(
             latent_size=latent_size, sampling_rate=sampling_rate,
             pqmf=partial(pqmf.CachedPQMF, attenuation=100, n_band=16),
-            encoder=partial(blocks.VariationalEncoder,
-                            partial(blocks.EncoderV2, data_size=16, capacity=cap, ratios=rat,
-                                    latent_size=latent_size, n_out=2, kernel_size=3,
-                                    dilations=V2_DILATIONS, activation=act, adain=adain_f)),
+            encoder=encoder,
             decoder=partial(blocks.GeneratorV2, data_size=16, capacity=cap, ratios=rat,
-                            latent_size=latent_size, kernel_size=3, dilations=V2_DILATIONS,
-                            amplitude_modulation=True, activation=act, adain=adain_f),
+                            latent_size=core.get_augmented_latent_size(latent_size, noise_aug), kernel_size=3,
+                            dilations=V2_DILATIONS, amplitude_modulation=True, activation=act, adain=adain_f,
+                            noise_module=noise),
             discriminator=disc,
             phase_1_duration=phase_1_duration if phase_1_duration is not None else a["phase_1_duration"],
             gan_loss=core.hinge_gan, valid_signal_crop=True,                  # v2.gin:81-83
             feature_matching_fun=partial(core.mean_difference, norm="L1", relative=True),
-            num_skipped_features=1,
+            num_skipped_features=a.get("num_skipped_features", 1),
             audio_distance=distance, multiband_audio_distance=distance,
             weights={"feature_matching": 20},                                 # v2.gin:87-89
             update_discriminator_every=a["update_discriminator_every"], n_channels=n_channels)

@@ -128,3 +128,26 @@ def get_rave_receptive_field(model, n_channels=1):
     right_rf = len(right_grad[right_grad != 0])
     model.zero_grad()
     return left_rf, right_rf
+
+
+# ---------------------------------------------------------------------------------------------
+# FFT noise filtering helpers of NoiseGeneratorV2 (rave/core.py:48-81) -- cuFFT through torch,
+# SURVEY row 8f.4 ("next"); the strided convs that feed them are on the library kernels.
+# ---------------------------------------------------------------------------------------------
+
+def amp_to_impulse_response(amp, target_size):
+    """Zero-phase band amplitudes -> windowed, causal-shifted FIR of length `target_size`."""
+    spec = torch.complex(amp, torch.zeros_like(amp))
+    ir = torch.fft.irfft(spec)
+    n = ir.shape[-1]
+    ir = torch.roll(ir, n // 2, -1) * torch.hann_window(n, dtype=ir.dtype, device=ir.device)
+    ir = nn.functional.pad(ir, (0, int(target_size) - int(n)))
+    return torch.roll(ir, -n // 2, -1)
+
+
+def fft_convolve(signal, kernel):
+    """Linear convolution on the last axis via zero-padded rFFT, keeping the last half."""
+    signal = nn.functional.pad(signal, (0, signal.shape[-1]))
+    kernel = nn.functional.pad(kernel, (kernel.shape[-1], 0))
+    out = torch.fft.irfft(torch.fft.rfft(signal) * torch.fft.rfft(kernel))
+    return out[..., out.shape[-1] // 2:]

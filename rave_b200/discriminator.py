@@ -101,7 +101,7 @@ class ConvNet(nn.Module):
             B, C, L, W = x.shape
             rows = x.permute(0, 3, 2, 1).reshape(B * W, L, C)
         rpad = (-L) % first.stride              # row pitch: a multiple of the first layer's stride
-        xa = nn.functional.pad(rows, (0, cpad, 0, rpad)).to(torch.bfloat16).contiguous()
+        xa = nn.functional.pad(rows, (0, cpad, 0, rpad)).to(engine.ACT_DTYPE).contiguous()
         outs = engine.run_chain(xa, specs, L)
         lens = engine.chain_lengths(specs, L)
         features = []

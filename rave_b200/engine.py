@@ -27,6 +27,7 @@ import torch.nn as nn
 from . import _lib, ops
 
 _state = {"precision": "fp32"}
+ACT_DTYPE = torch.bfloat16   # storage type of operand / gradient streams (tests may widen it)
 
 
 def set_precision(mode: str) -> None:
@@ -195,7 +196,6 @@ class _PreparedWeights:
     (v, g) by ONE fused launch pair (row norms + re-layout): rave_weight_prep_tc."""
 
     def __init__(self, spec: LayerSpec, v: torch.Tensor, g: Optional[torch.Tensor], need_dgrad: bool):
-        import ctypes
         self.spec = spec
         K, s = spec.K, spec.stride
         dev = v.device
@@ -204,7 +204,6 @@ class _PreparedWeights:
             C0p, C1p = spec.Cout + spec.cout_pad, spec.Cin + spec.cin_pad
         else:
             C0p, C1p = spec.Cin + spec.cin_pad, spec.Cout + spec.cout_pad
-        self.norm = torch.empty(C0, dtype=torch.float32, device=dev) if g is not None else None
         self.fwd = None           # conv: [K][Cout][Cin]
         self.fwd_phases = None    # convT: per output phase (wt [n][Cout][Cin], pad'')
         self.dgrad = None         # stride-1 conv: flipped taps [K][Cin][Cout]; convT: [K][Cin][Cout]
@@ -223,12 +222,7 @@ class _PreparedWeights:
             phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
             tapsB = [k for order, _ in phases for k in order]
             tapsA = list(range(K)) if need_dgrad else []
-        outA = torch.empty(len(tapsA), C0p, C1p, dtype=torch.bfloat16, device=dev) if tapsA else None
-        outB = torch.empty(len(tapsB), C1p, C0p, dtype=torch.bfloat16, device=dev) if tapsB else None
-        arrA = (ctypes.c_int * max(1, len(tapsA)))(*tapsA)
-        arrB = (ctypes.c_int * max(1, len(tapsB)))(*tapsB)
-        _lib.call("rave_weight_prep_tc", _lib.ptr(v), _lib.ptr(g), _lib.ptr(self.norm), _lib.ptr(outA), arrA,
-                  len(tapsA), _lib.ptr(outB), arrB, len(tapsB), C0, C1, K, C0p, C1p, _lib.stream_ptr())
+        self.norm, outA, outB = ops.weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p)
 
         def split(buf):
             out, off = [], 0
@@ -297,7 +291,7 @@ class TcChainFn(torch.autograd.Function):
                 bias_p = nn.functional.pad(bias.detach(), (0, s.cout_pad))
             res = f32[s.res_src] if s.res_src is not None else None
             out_f32 = torch.empty(B, pitch, cout_p, dtype=torch.float32, device=a.device) if s.want_f32 else None
-            out_act = torch.empty(B, pitch, cout_p, dtype=torch.bfloat16, device=a.device) if want_act else None
+            out_act = torch.empty(B, pitch, cout_p, dtype=ACT_DTYPE, device=a.device) if want_act else None
             if pitch > Lout:
                 for t in (out_f32, out_act):
                     if t is not None:
@@ -312,6 +306,8 @@ class TcChainFn(torch.autograd.Function):
                     if wt is None:
                         raise _lib.RaveB200Error("transposed conv with an empty phase is not supported")
                     Lp = (Lout - p + s.stride - 1) // s.stride
+                    if Lp <= 0:
+                        continue
                     ops.conv1d_tc(a, wt, bias_p, None, 1, 1, (padpp, 0), act_code, act_slope, want_f32=False,
                                   want_act=False, out_f32=out_f32, out_act=out_act, out_rows=pitch,
                                   out_row_stride=s.stride, out_row_offset=p, Lout=Lp, Lin=Lin)
@@ -340,7 +336,7 @@ class TcChainFn(torch.autograd.Function):
         ext: Dict[int, torch.Tensor] = {}
         for i, g in zip(ctx.out_index, gouts):
             if g is not None:
-                ext[i] = g.to(torch.bfloat16).contiguous()
+                ext[i] = g.to(ACT_DTYPE).contiguous()
         skip: Dict[int, torch.Tensor] = {}     # residual pass-through gradient for layer idx (or -1)
         g_cur: Optional[torch.Tensor] = None   # gradient (h-space, bf16) of layer i's output
         grads = [None] * len(flat)
@@ -366,11 +362,7 @@ class TcChainFn(torch.autograd.Function):
                 else:
                     dwt = ops.conv1d_tc_wgrad(a_in, g, s.K, s.stride, 1, s.pad[0], Lp=Lin, Lq=Lout)
                 # dwt is [K][C0p][C1p] in the parameter's own (C0, C1) order for both kinds
-                dv = torch.empty_like(v)
-                dg = torch.empty_like(gpar) if gpar is not None else None
-                _lib.call("rave_weight_norm_bwd_tapmajor", _lib.ptr(dwt), _lib.ptr(v), _lib.ptr(gpar),
-                          _lib.ptr(ctx.norms[i]), _lib.ptr(dv), _lib.ptr(dg), v.shape[0], v.shape[1], s.K,
-                          dwt.shape[1], dwt.shape[2], _lib.stream_ptr())
+                dv, dg = ops.weight_norm_bwd_tapmajor(dwt, v, gpar, ctx.norms[i])
                 grads[3 * i], grads[3 * i + 1] = dv, dg
             if bias is not None and bias.requires_grad:
                 grads[3 * i + 2] = g[:, :Lout, :s.Cout].float().sum((0, 1))
@@ -387,7 +379,7 @@ class TcChainFn(torch.autograd.Function):
                 add = e if add is None else (add + e)
             dact = a_in if s.pre_act == ops.ACT_LEAKY else None
             in_pitch = a_in.shape[1]
-            gp = torch.empty(B, in_pitch, cin_p, dtype=torch.bfloat16, device=g.device)
+            gp = torch.empty(B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)
             if in_pitch > Lin:
                 gp[:, Lin:].zero_()
             if s.kind == "conv":
@@ -399,6 +391,8 @@ class TcChainFn(torch.autograd.Function):
                 else:
                     for p, (wt, padpp) in enumerate(pw.dgrad_phases):
                         Lp = (Lin - p + s.stride - 1) // s.stride
+                        if Lp <= 0:
+                            continue
                         if wt is None:
                             raise _lib.RaveB200Error("strided conv with an empty dgrad phase is not supported")
                         ops.conv1d_tc(g, wt, None, None, 1, 1, (padpp, 0), ops.ACT_NONE, s.pre_slope,

@@ -421,3 +421,34 @@ def tapmajor_to_weight(dwt, transpose=False):
     dw = torch.empty((Cn, Cm, K) if transpose else (Cm, Cn, K), dtype=torch.float32, device=dwt.device)
     call("rave_tapmajor_to_weight_f32", ptr(dwt), ptr(dw), Cm, Cn, K, int(transpose), stream_ptr())
     return dw
+
+
+def weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p):
+    """v [C0][C1][K(,1)] fp32 (+ weight-norm g) -> (norm [C0] | None, outA [nA][C0p][C1p] bf16 | None,
+    outB [nB][C1p][C0p] bf16 | None) with out?[t] = bf16(w[..][..][taps?[t]]), w = g v/||v|| (or v)."""
+    import ctypes
+    v = _f32c(v)
+    g = _f32c(g)
+    C0, C1 = v.shape[0], v.shape[1]
+    K = v.numel() // (C0 * C1)
+    dev = v.device
+    norm = torch.empty(C0, dtype=torch.float32, device=dev) if g is not None else None
+    outA = torch.empty(len(tapsA), C0p, C1p, dtype=torch.bfloat16, device=dev) if tapsA else None
+    outB = torch.empty(len(tapsB), C1p, C0p, dtype=torch.bfloat16, device=dev) if tapsB else None
+    arrA = (ctypes.c_int * max(1, len(tapsA)))(*tapsA)
+    arrB = (ctypes.c_int * max(1, len(tapsB)))(*tapsB)
+    call("rave_weight_prep_tc", ptr(v), ptr(g), ptr(norm), ptr(outA), arrA, len(tapsA), ptr(outB), arrB,
+         len(tapsB), C0, C1, K, C0p, C1p, stream_ptr())
+    return norm, outA, outB
+
+
+def weight_norm_bwd_tapmajor(dwt, v, g, norm):
+    """dwt [K][C0p][C1p] fp32 -> (dv like v, dg like g | None)."""
+    v = _f32c(v)
+    dv = torch.empty_like(v)
+    dg = torch.empty_like(g) if g is not None else None
+    C0, C1 = v.shape[0], v.shape[1]
+    K = v.numel() // (C0 * C1)
+    call("rave_weight_norm_bwd_tapmajor", ptr(dwt), ptr(v), ptr(g), ptr(norm), ptr(dv), ptr(dg), C0, C1, K,
+         dwt.shape[1], dwt.shape[2], stream_ptr())
+    return dv, dg

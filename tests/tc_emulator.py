@@ -1,0 +1,126 @@
+"""TEST DOUBLE: torch-CPU emulation of the tensor-core entry points' documented semantics
+(include/rave_b200.h), used ONLY by tests/test_engine_cpu.py to exercise the host-side engine logic
+(planning, phase decomposition, pitches, the explicit backward) without a GPU.  Not part of the product."""
+import torch
+import torch.nn.functional as F
+
+
+OPERAND_DTYPE = torch.bfloat16
+
+
+def _bf16(t):
+    return t.to(OPERAND_DTYPE)
+
+
+def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=0, slope=0.2,
+              want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
+              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None):
+    B, in_pitch, Cin = xa_cl.shape
+    Lin = in_pitch if Lin is None else Lin
+    K, Cout, _ = wt.shape
+    assert in_pitch >= -(-Lin // stride) * stride
+    if in_pitch > Lin:
+        assert float(xa_cl[:, Lin:].float().abs().max()) == 0.0, "slack rows must be zero"
+    x = xa_cl[:, :Lin].float().permute(0, 2, 1)                     # [B, Cin, Lin]
+    w = wt.float().permute(1, 2, 0)                                  # [Cout, Cin, K]
+    if Lout is None:
+        Lout = (Lin + pad[0] + pad[1] - dil * (K - 1) - 1) // stride + 1
+    # rows l*stride + k*dil - pad_l, zero outside [0, Lin)
+    need = (Lout - 1) * stride + (K - 1) * dil + 1
+    pl = pad[0]
+    if pl >= 0:
+        xp = F.pad(x, (pl, max(0, need - pl - Lin)))
+    else:
+        xp = F.pad(x[..., -pl:], (0, max(0, need - (Lin + pl))))
+    xp = xp[..., :max(need, 1)]
+    if xp.shape[-1] < need:
+        xp = F.pad(xp, (0, need - xp.shape[-1]))
+    y = F.conv1d(xp, w, None, stride, 0, dil)[..., :Lout]            # [B, Cout, Lout]
+    v = y.permute(0, 2, 1)                                           # [B, Lout, Cout]
+    if bias is not None:
+        v = v + bias
+    rows = out_rows if out_rows else Lout
+    ors = out_row_stride if out_row_stride else 1
+    idx = torch.arange(Lout) * ors + out_row_offset
+    if dact_src is not None:
+        sgn = torch.signbit(dact_src[:, idx].float())
+        v = torch.where(sgn, v * slope, v)
+    if res_bf16 is not None:
+        v = v + res_bf16[:, idx].float()
+    if res_cl is not None:
+        v = v + res_cl[:, idx]
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.zeros(B, rows, Cout)
+    if want_act and out_act is None:
+        out_act = torch.zeros(B, rows, Cout, dtype=OPERAND_DTYPE)
+    if out_f32 is not None:
+        out_f32[:, idx] = v
+    if out_act is not None:
+        a = F.leaky_relu(v, slope) if act == 1 else v
+        out_act[:, idx] = _bf16(a)
+    return out_f32, out_act
+
+
+def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None):
+    B, p_pitch, Cm = P_cl.shape
+    _, q_pitch, Cn = Q_cl.shape
+    Lp = p_pitch if Lp is None else Lp
+    Lq = q_pitch if Lq is None else Lq
+    P = P_cl[:, :Lp].float()
+    Q = Q_cl[:, :q_pitch].float()
+    if q_pitch > Lq:
+        assert float(Q[:, Lq:].abs().max()) == 0.0
+    dwt = torch.zeros(K, Cm, Cn)
+    l = torch.arange(Lp)
+    for k in range(K):
+        r = l * stride + k * dil - pad_l
+        ok = (r >= 0) & (r < Lq)
+        if ok.any():
+            dwt[k] = torch.einsum("blm,bln->mn", P[:, l[ok]], Q[:, r[ok]])
+    return dwt
+
+
+def weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p):
+    C0, C1 = v.shape[0], v.shape[1]
+    v3 = v.reshape(C0, C1, -1)
+    norm = None
+    w = v3
+    if g is not None:
+        norm = v3.reshape(C0, -1).norm(2, 1)
+        w = v3 * (g.reshape(C0, 1, 1) / norm.reshape(C0, 1, 1))
+    wp = F.pad(w, (0, 0, 0, C1p - C1, 0, C0p - C0))
+    outA = _bf16(wp[:, :, tapsA].permute(2, 0, 1).contiguous()) if tapsA else None
+    outB = _bf16(wp[:, :, tapsB].permute(2, 1, 0).contiguous()) if tapsB else None
+    return norm, outA, outB
+
+
+def weight_norm_bwd_tapmajor(dwt, v, g, norm):
+    C0, C1 = v.shape[0], v.shape[1]
+    dw = dwt[:, :C0, :C1].permute(1, 2, 0).reshape(v.shape)
+    if g is None:
+        return dw.contiguous(), None
+    v2 = v.reshape(C0, -1)
+    dw2 = dw.reshape(C0, -1)
+    dot = (dw2 * v2).sum(1)
+    n = norm
+    gg = g.reshape(C0)
+    dv = (gg / n).unsqueeze(1) * (dw2 - v2 * (dot / (n * n)).unsqueeze(1))
+    dg = (dot / n).reshape(g.shape)
+    return dv.reshape(v.shape), dg
+
+
+def ncl_to_cl(x, act=0, slope=0.2, alpha=None, want_bf16=True, want_f32=False):
+    xt = x.permute(0, 2, 1).contiguous()
+    a = F.leaky_relu(xt, slope) if act == 1 else xt
+    return (_bf16(a) if want_bf16 else None), (xt if want_f32 else None)
+
+
+def cl_to_ncl(x_cl):
+    return x_cl.permute(0, 2, 1).contiguous()
+
+
+def install(monkeypatch):
+    from rave_b200 import ops
+    for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
+                 "cl_to_ncl"):
+        monkeypatch.setattr(ops, name, globals()[name])

@@ -1,0 +1,131 @@
+"""CPU: host logic of the tensor-core engine (rave_b200/engine.py) -- layer planning, transposed-conv /
+strided-dgrad phase decomposition, row pitches, and the hand-written backward -- exercised against the
+fp32 oracle with the kernels replaced by a torch emulation of their documented semantics
+(tests/tc_emulator.py).  Tolerances are the bf16-mode ones (operands are rounded to bf16)."""
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import rave_oracle as O
+from tests import tc_emulator
+from tests.conftest import rel_l2
+
+
+def cos(a, b):
+    a, b = a.detach().double().reshape(-1), b.detach().double().reshape(-1)
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+
+
+@pytest.fixture(params=["exact_fp32", "bf16"])
+def emu(request, monkeypatch):
+    """exact_fp32: operands kept in fp32 -> the engine must reproduce the oracle to fp32 round-off (a pure
+    logic check); bf16: operands/gradients rounded like on the device (tolerances of the bf16 mode)."""
+    from rave_b200 import engine
+    tc_emulator.install(monkeypatch)
+    dt = torch.float32 if request.param == "exact_fp32" else torch.bfloat16
+    monkeypatch.setattr(tc_emulator, "OPERAND_DTYPE", dt)
+    monkeypatch.setattr(engine, "ACT_DTYPE", dt)
+    return request.param
+
+
+def tol(mode, exact, loose):
+    return exact if mode == "exact_fp32" else loose
+
+
+def test_phase_taps_cover_every_tap_once():
+    from rave_b200.engine import _phase_taps
+    for K, s, pad in [(8, 4, 3), (4, 2, 1), (8, 4, 2), (4, 2, 1), (15, 4, 7), (5, 4, 2), (5, 3, 2), (6, 2, 1)]:
+        seen = []
+        for p in range(s):
+            order, padpp = _phase_taps(K, s, pad, p)
+            for i, k in enumerate(order):
+                # source row of tap i for output q: q + i - padpp must equal (q*s + p + pad - k)/s
+                assert (p + pad - k) % s == 0
+                assert i - padpp == (p + pad - k) // s
+            seen += order
+        assert sorted(seen) == list(range(K))
+
+
+@pytest.mark.parametrize("ratios", [[4, 4, 4, 2], [4, 2, 2, 2]])
+def test_encoder_generator_chain_vs_oracle(emu, ratios):
+    from rave_b200 import configs, engine
+    torch.manual_seed(1)
+    _, enc, dec = configs.make_autoencoder("v2", capacity=16, latent_size=16, ratios=ratios)
+    sd = {"encoder." + k: v.detach().clone() for k, v in enc.state_dict().items()}
+    sd.update({"decoder." + k: v.detach().clone() for k, v in dec.state_dict().items()})
+    cfg = O.ArchConfig(capacity=16, latent_size=16, ratios=ratios)
+    B, L = 2, 512
+    x_mb = torch.randn(B, 16, L)
+    # ---------------- encoder
+    specs = enc.encoder.net._tc_plan()
+    assert specs is not None
+    po = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    xo = x_mb.clone().requires_grad_(True)
+    z_o = O.encoder_v2(xo, po, "encoder.encoder.", cfg)
+    xe = x_mb.clone().requires_grad_(True)
+    (out,) = engine.run_chain(engine.to_channel_last(xe), specs)
+    z = engine.from_channel_last(out[:, :engine.chain_lengths(specs, L)[-1]].contiguous())
+    assert z.shape == z_o.shape
+    assert rel_l2(z, z_o) < tol(emu, 1e-5, 3e-2)
+    probe = torch.randn_like(z_o)
+    names = sorted(k for k in po if k.startswith("encoder.") and po[k].requires_grad)
+    g_o = torch.autograd.grad((z_o * probe).sum(), [xo] + [po[k] for k in names])
+    pe = dict(enc.named_parameters(prefix="encoder"))
+    g_e = torch.autograd.grad((z * probe).sum(), [xe] + [pe[k] for k in names])
+    assert rel_l2(g_e[0], g_o[0]) < tol(emu, 1e-5, 0.15)
+    for k, a, b in zip(names, g_e[1:], g_o[1:]):
+        assert a.shape == b.shape and rel_l2(a, b) < tol(emu, 2e-5, 0.2), (k, rel_l2(a, b))
+    # ---------------- generator (up to the waveform conv, before x*sigmoid(a) -> tanh)
+    specs = dec.net._tc_plan()
+    zin = torch.randn(B, 16, z_o.shape[-1])
+    taps = {}
+    zo = zin.clone().requires_grad_(True)
+    O.generator_v2(zo, po, "decoder.", cfg, taps)
+    w_o = taps["wave"]
+    ze = zin.clone().requires_grad_(True)
+    (out,) = engine.run_chain(engine.to_channel_last(ze), specs)
+    w = engine.from_channel_last(out[:, :engine.chain_lengths(specs, zin.shape[-1])[-1]].contiguous())
+    assert w.shape == w_o.shape
+    assert rel_l2(w, w_o) < tol(emu, 1e-5, 3e-2)
+    probe = torch.randn_like(w_o)
+    names = sorted(k for k in po if k.startswith("decoder.") and po[k].requires_grad)
+    g_o = torch.autograd.grad((w_o * probe).sum(), [zo] + [po[k] for k in names])
+    pd = dict(dec.named_parameters(prefix="decoder"))
+    g_e = torch.autograd.grad((w * probe).sum(), [ze] + [pd[k] for k in names])
+    assert rel_l2(g_e[0], g_o[0]) < tol(emu, 1e-5, 0.15)
+    for k, a, b in zip(names, g_e[1:], g_o[1:]):
+        assert a.shape == b.shape and rel_l2(a, b) < tol(emu, 2e-5, 0.2), (k, rel_l2(a, b))
+
+
+def test_discriminator_chain_vs_oracle(emu):
+    """MPD (folded, ragged lengths -> row pitches) and MSD ConvNets through the engine."""
+    from rave_b200 import configs
+    torch.manual_seed(2)
+    disc = configs.make_discriminator_v2(capacity=16)
+    sd = {"discriminator." + k: v.detach().clone() for k, v in disc.state_dict().items()}
+    x = (0.5 * torch.randn(2, 1, 2048 + 3)).clamp(-1, 1)
+    po = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    feats_o = O.combine_discriminators_v2(xo, po)
+    xe = x.clone().requires_grad_(True)
+    mpd, msd = disc.discriminators
+    feats = []
+    for layer, n in zip(mpd.layers, mpd.periods):
+        feats.append(layer._forward_tc(mpd.fold(xe, n), layer._tc_specs()))
+    xs = xe
+    for layer in msd.layers:
+        feats.append(layer._forward_tc(xs, layer._tc_specs()))
+        xs = nn.functional.avg_pool1d(xs, 2)
+    for fa, fb in zip(feats, feats_o):
+        for a, b in zip(fa, fb):
+            assert a.shape == b.shape
+            assert rel_l2(a, b) < tol(emu, 1e-5, 3e-2), (a.shape, rel_l2(a, b))
+    fm_o, ld_o, la_o = O.gan_losses(feats_o, 1, True)
+    fm, ld, la = O.gan_losses(feats, 1, True)
+    names = sorted(po)
+    g_o = torch.autograd.grad(fm_o + ld_o + la_o, [xo] + [po[k] for k in names])
+    pp = dict(disc.named_parameters(prefix="discriminator"))
+    g_e = torch.autograd.grad(fm + ld + la, [xe] + [pp[k] for k in names])
+    assert rel_l2(g_e[0], g_o[0]) < tol(emu, 2e-5, 0.2)
+    for k, a, b in zip(names, g_e[1:], g_o[1:]):
+        assert a.shape == b.shape and rel_l2(a, b) < tol(emu, 5e-5, 0.25), (k, rel_l2(a, b))

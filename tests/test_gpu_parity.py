@@ -343,3 +343,23 @@ def test_training_step_runs_and_updates():
     for k in ("fullband_spectral_distance", "multiband_spectral_distance", "feature_matching",
               "adversarial", "regularization"):
         assert torch.isfinite(logs[k]), k
+
+
+def test_descript_mpd_vs_oracle():
+    """v3 discriminator, MPD branch (77 % of its FLOPs) on the library kernels vs the CPU oracle;
+    also the reference's key names (convs.i.0.*, conv_post.*)."""
+    from rave_b200.descript_discriminator import MPD, DescriptDiscriminator
+    torch.manual_seed(0)
+    mpd = MPD(5)
+    sd = {k: v.detach().clone() for k, v in mpd.state_dict().items()}
+    assert "convs.0.0.weight_g" in sd and "conv_post.weight_v" in sd and "convs.4.0.bias" in sd
+    x = torch.randn(2, 1, 2000)
+    want = O.descript_mpd(x, sd, "", 5)
+    got = mpd.cuda()(x.cuda())
+    assert len(got) == 6
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        assert rel_l2(a, b) < FWD_TOL
+    dd = DescriptDiscriminator()
+    y = torch.randn(2, 1, 300)
+    assert rel_l2(dd.preprocess(y.cuda()), O.descript_preprocess(y)) < 1e-6

@@ -93,3 +93,23 @@ def test_oracle_matches_live_reference():
     assert torch.equal(O.pqmf_analysis(x, p.hk), p(x))
     y = p(x)
     assert torch.equal(O.pqmf_synthesis(y, p.hk), p.inverse(y))
+
+
+@pytest.mark.reference
+def test_descript_mpd_oracle_matches_live_reference():
+    """Descript MPD (rave/descript_discriminator.py:30-66): too large for a committed fixture (1024-ch
+    layers), so the oracle restatement is pinned against the live reference in the build container."""
+    from oracle.ref_loader import load_reference
+    R = load_reference()
+    torch.manual_seed(0)
+    mpd = R.descript_discriminator.MPD(3)
+    x = torch.randn(2, 1, 999)
+    want = mpd(x)
+    sd = {k: v.detach() for k, v in mpd.state_dict().items()}
+    got = O.descript_mpd(x, sd, "", 3)
+    assert len(got) == len(want) == 6
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and rel_l2(a, b) < 1e-6
+    y = torch.randn(2, 1, 500)
+    dd = R.descript_discriminator.DescriptDiscriminator()
+    assert torch.equal(O.descript_preprocess(y), dd.preprocess(y))
