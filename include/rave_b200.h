@@ -145,14 +145,17 @@ int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bi
                        int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
                        int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
                        int out_row_stride, int out_row_offset, void *stream);
-/* weight gradient on the same engine (split-K over rows, fp32 atomics into a zeroed buffer):
- *   dwt[k][m][n] = sum_{b,l} P[b][l][m] * Q[b][l*stride + k*dil - pad_l][n]
- * P [B][Lp][Cm] bf16 (conv: dy), Q [B][Lq][Cn] bf16 (conv: activated input); dwt [K][Cm][Cn] fp32.
+/* weight gradient on the same engine (split-K over row slices; each slice writes its own partial):
+ *   sum_s dwt[s][k][m][n] = sum_{b,l} P[b][l][m] * Q[b][l*stride + k*dil - pad_l][n]
+ * P [B][Lp][Cm] bf16 (conv: dy), Q [B][Lq][Cn] bf16 (conv: activated input);
+ * dwt [splits][K][Cm][Cn] fp32 with splits = rave_conv1d_tc_wgrad_splits(...) (every element written once;
+ * the slices are summed, in order, by rave_weight_norm_bwd_tapmajor / rave_tapmajor_to_weight_f32).
  * For ConvTranspose1d swap the roles (P = activated input, Q = dy).  Cm, Cn multiples of 8. */
+int rave_conv1d_tc_wgrad_splits(int B, int Cm, int Lp, int Cn, int K);
 int rave_conv1d_tc_wgrad(const void *P_bf16, const void *Q_bf16, float *dwt, int B, int Cm, int Lp, int p_pitch,
                          int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l, void *stream);
-/* dwt[K][Cm][Cn] -> dw[Cm][Cn][K] (transpose=0) or dw[Cn][Cm][K] (transpose=1), fp32 */
-int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int K, int transpose,
+/* sum_s dwt[s][K][Cm][Cn] -> dw[Cm][Cn][K] (transpose=0) or dw[Cn][Cm][K] (transpose=1), fp32 */
+int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int K, int transpose, int splits,
                                 void *stream);
 /* fused weight preparation for the engine: v [C0][C1][K] fp32 (+ weight-norm g [C0]; norm [C0] is written)
  *   outA[t][c0][c1] = bf16(w[c0][c1][tapsA[t]]), dims [nA][C0p][C1p]  (padded region zero)
@@ -164,7 +167,7 @@ int rave_weight_prep_tc(const float *v, const float *g, float *norm, void *outA_
 /* tap-major fp32 weight gradient dwt [K][C0p][C1p] -> dv [C0][C1][K] (+ dg [C0]) through the weight norm
  * (g == NULL: plain re-layout). */
 int rave_weight_norm_bwd_tapmajor(const float *dwt, const float *v, const float *g, const float *norm, float *dv,
-                                  float *dg, int C0, int C1, int K, int C0p, int C1p, void *stream);
+                                  float *dg, int C0, int C1, int K, int C0p, int C1p, int splits, void *stream);
 /* layout converters between the module-boundary layout [B][C][L] fp32 and the engine's channel-last:
  *   to_cl:   y_bf16[b][l][c] = bf16(act(x[b][c][l])), optionally also y_f32[b][l][c] = x[b][c][l]
  *   from_cl: y[b][c][l] = x_f32[b][l][c] */

@@ -360,6 +360,7 @@ class VariationalEncoder(nn.Module):
         self.encoder = encoder(n_channels=n_channels)
         self.beta = beta
         self.register_buffer("warmed_up", torch.tensor(0))
+        self._warmed_up_host = None      # host mirror of the buffer: no device->host sync per step
 
     def reparametrize(self, z, eps: Optional[torch.Tensor] = None):
         """`eps` lets a caller inject the noise (parity tests; the CPU and CUDA Philox streams
@@ -375,12 +376,19 @@ class VariationalEncoder(nn.Module):
         return z, self.beta * kl
 
     def set_warmed_up(self, state: bool):
-        state = torch.tensor(int(state), device=self.warmed_up.device)
-        self.warmed_up = state
+        state = bool(state)
+        if self._warmed_up_host is None or self._warmed_up_host != state:
+            self.warmed_up = torch.tensor(int(state), device=self.warmed_up.device)
+            self._warmed_up_host = state
+
+    def _is_warmed_up(self) -> bool:
+        if self._warmed_up_host is None:          # e.g. right after load_state_dict: read the buffer once
+            self._warmed_up_host = bool(self.warmed_up)
+        return self._warmed_up_host
 
     def forward(self, x: torch.Tensor):
         z = self.encoder(x)
-        if self.warmed_up:
+        if self._is_warmed_up():
             z = z.detach()
         return z
 

@@ -452,7 +452,7 @@ struct WgParams {
   int B, Cm, Lp, Cn, Lq, K, stride, dil, pad_l;
   int BL, BB, n_lt, n_bg;   // row chunk = BB batches x BL rows (BL*BB == 64)
   int n_mt, n_nt, splits;
-  float *dwt;               // [K][Cm][Cn] fp32, pre-zeroed
+  float *dwt;               // [splits][K][Cm][Cn] fp32 partial sums (every element written exactly once)
 };
 
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -577,17 +577,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constan
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-      float *dst = p.dwt + ((size_t)k * p.Cm + m) * p.Cn + n0;
+      float *dst = p.dwt + (((size_t)split * p.K + k) * p.Cm + m) * p.Cn + n0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
         float v[16];
         tmem_ld_32x16(taddr + c0, v);
         if (m < p.Cm) {
+          if (n0 + c0 + 16 <= p.Cn && (p.Cn & 3) == 0) {
+            float4 *d4 = reinterpret_cast<float4 *>(dst + c0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (n0 + c0 + i < p.Cn) atomicAdd(dst + c0 + i, v[i]);
+            for (int i = 0; i < 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + c0 + i < p.Cn) dst[c0 + i] = v[i];
+          }
         }
       }
+    }
+  } else if (warp >= 2) {
+    // empty slice (more splits than row chunks): this CTA still owns its partial tile -> zeros
+    const int quad = warp & 3;
+    const int m = m0 + quad * 32 + lane;
+    if (m < p.Cm) {
+      float *dst = p.dwt + (((size_t)split * p.K + k) * p.Cm + m) * p.Cn + n0;
+      for (int c = 0; c < BLOCK_N; ++c)
+        if (n0 + c < p.Cn) dst[c] = 0.f;
     }
   }
 
@@ -602,7 +617,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constan
 // dwt[K][Cm][Cn] fp32 -> dw[Cm][Cn][K] (transpose=0) or dw[Cn][Cm][K] (transpose=1)
 __global__ void __launch_bounds__(256)
 tapmajor_to_weight_kernel(const float *__restrict__ dwt, float *__restrict__ dw, int Cm, int Cn, int K,
-                          int transpose) {
+                          int transpose, int splits) {
   const long total = (long)K * Cm * Cn;
   for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
     const int k = (int)(i % K);
@@ -611,7 +626,9 @@ tapmajor_to_weight_kernel(const float *__restrict__ dwt, float *__restrict__ dw,
     a = (int)(r / (transpose ? Cm : Cn));
     c = (int)(r % (transpose ? Cm : Cn));
     const int m = transpose ? c : a, n = transpose ? a : c;
-    dw[i] = dwt[((size_t)k * Cm + m) * Cn + n];
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp) acc += dwt[(size_t)sp * total + ((size_t)k * Cm + m) * Cn + n];
+    dw[i] = acc;
   }
 }
 
@@ -636,6 +653,45 @@ static int launch_wg(const CUtensorMap &tp, const CUtensorMap &tq, const WgParam
 }  // namespace tc
 }  // namespace rave
 
+namespace rave {
+namespace tc {
+static int wg_block_n(int Cn) {
+  int BN = 256;
+  if (Cn <= 256) BN = (Cn + 15) / 16 * 16;
+  else if (Cn % 256 == 0) BN = 256;
+  else if (Cn % 192 == 0) BN = 192;
+  else if (Cn % 128 == 0) BN = 128;
+  const int valid_bn[] = {16, 32, 48, 64, 96, 128, 192, 256};
+  for (int v : valid_bn)
+    if (v >= BN) return v;
+  return 256;
+}
+static void wg_geometry(int B, int Cm, int Lp, int Cn, int K, int *BL, int *n_lt, int *n_bg, int *n_mt, int *BN,
+                        int *n_nt, int *splits) {
+  int bl = WG_ROWS;
+  while (bl > Lp && bl > 8) bl >>= 1;
+  *BL = bl;
+  *n_lt = ceil_div(Lp, bl);
+  *n_bg = ceil_div(B, WG_ROWS / bl);
+  *n_mt = ceil_div(Cm, 128);
+  *BN = wg_block_n(Cn);
+  *n_nt = ceil_div(Cn, *BN);
+  const int tiles = K * (*n_mt) * (*n_nt);
+  const int n_chunks = (*n_lt) * (*n_bg);
+  int s = ceil_div(2 * 148, tiles);
+  if (s > n_chunks) s = n_chunks;
+  if (s < 1) s = 1;
+  *splits = s;
+}
+}  // namespace tc
+}  // namespace rave
+
+extern "C" int rave_conv1d_tc_wgrad_splits(int B, int Cm, int Lp, int Cn, int K) {
+  int BL, n_lt, n_bg, n_mt, BN, n_nt, splits;
+  rave::tc::wg_geometry(B, Cm, Lp, Cn, K, &BL, &n_lt, &n_bg, &n_mt, &BN, &n_nt, &splits);
+  return splits;
+}
+
 extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, int B, int Cm, int Lp, int p_pitch,
                                     int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l,
                                     void *stream) {
@@ -651,33 +707,13 @@ extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, in
   EncodeTiledFn enc = get_encode_fn();
   RAVE_CHECK_ARG(enc, "wgrad_tc: cuTensorMapEncodeTiled not available");
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(dwt, 0, sizeof(float) * (size_t)K * Cm * Cn, s);
 
   WgParams p;
   p.B = B; p.Cm = Cm; p.Lp = Lp; p.Cn = Cn; p.Lq = Lq; p.K = K; p.stride = stride; p.dil = dil; p.pad_l = pad_l;
   p.dwt = dwt;
-  int BL = WG_ROWS;
-  while (BL > Lp && BL > 8) BL >>= 1;
-  p.BL = BL; p.BB = WG_ROWS / BL;
-  p.n_lt = ceil_div(Lp, BL);
-  p.n_bg = ceil_div(B, p.BB);
-  p.n_mt = ceil_div(Cm, 128);
-  int BN = 256;
-  if (Cn <= 256) BN = (Cn + 15) / 16 * 16;
-  else if (Cn % 256 == 0) BN = 256;
-  else if (Cn % 192 == 0) BN = 192;
-  else if (Cn % 128 == 0) BN = 128;
-  const int valid_bn[] = {16, 32, 48, 64, 96, 128, 192, 256};
-  int bn_ok = 0;
-  for (int v : valid_bn) if (v >= BN) { bn_ok = v; break; }
-  BN = bn_ok ? bn_ok : 256;
-  p.n_nt = ceil_div(Cn, BN);
-  const int tiles = p.K * p.n_mt * p.n_nt;
-  const int n_chunks = p.n_lt * p.n_bg;
-  int splits = ceil_div(2 * 148, tiles);
-  if (splits > n_chunks) splits = n_chunks;
-  if (splits < 1) splits = 1;
-  p.splits = splits;
+  int BN;
+  wg_geometry(B, Cm, Lp, Cn, K, &p.BL, &p.n_lt, &p.n_bg, &p.n_mt, &BN, &p.n_nt, &p.splits);
+  p.BB = WG_ROWS / p.BL;
 
   CUtensorMap tp, tq;
   {
@@ -715,13 +751,14 @@ extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, in
 }
 
 extern "C" int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int K, int transpose,
-                                           void *stream) {
+                                           int splits, void *stream) {
   using namespace rave;
   RAVE_CHECK_ARG(dwt && dw && Cm > 0 && Cn > 0 && K > 0, "tapmajor_to_weight: bad argument");
   const long total = (long)K * Cm * Cn;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  tc::tapmajor_to_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwt, dw, Cm, Cn, K, transpose);
+  RAVE_CHECK_ARG(splits >= 1, "tapmajor_to_weight: splits must be >= 1");
+  tc::tapmajor_to_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwt, dw, Cm, Cn, K, transpose, splits);
   RAVE_CHECK_LAUNCH("tapmajor_to_weight");
   return 0;
 }

@@ -401,30 +401,35 @@ weight_prep_kernel(const float *__restrict__ v, const float *__restrict__ g, con
 }
 
 // dwt [K][C0p][C1p] fp32 (tap-major wgrad) -> dv [C0][C1][K], dg [C0]   (g == null: dv = dw)
+// dwt holds `splits` partial sums ([splits][K][C0p][C1p]); they are combined here in a fixed order
+// (deterministic), the combined dw row is staged in dv and then corrected in place.
 __global__ void __launch_bounds__(256)
 weight_norm_bwd_tapmajor_kernel(const float *__restrict__ dwt, const float *__restrict__ v,
                                 const float *__restrict__ g, const float *__restrict__ norm,
-                                float *__restrict__ dv, float *__restrict__ dg, int C1, int K, int C0p, int C1p) {
+                                float *__restrict__ dv, float *__restrict__ dg, int C1, int K, int C0p, int C1p,
+                                int splits) {
   __shared__ float red[32];
   const int c0 = blockIdx.x;
   const int R = C1 * K;
   const float *vr = v + (size_t)c0 * R;
+  float *dr = dv + (size_t)c0 * R;
+  const size_t split_stride = (size_t)K * C0p * C1p;
   float s = 0.f;
-  if (g) {
-    for (int i = threadIdx.x; i < R; i += blockDim.x) {
-      const int c1 = i / K, k = i - c1 * K;
-      s = fmaf(dwt[((size_t)k * C0p + c0) * C1p + c1], vr[i], s);
-    }
-  }
-  const float dot = g ? block_reduce_sum(s, red) : 0.f;
-  const float n = g ? norm[c0] : 1.f;
-  const float gn = g ? g[c0] / n : 1.f;
-  const float coef = g ? dot / (n * n) : 0.f;
   for (int i = threadIdx.x; i < R; i += blockDim.x) {
     const int c1 = i / K, k = i - c1 * K;
-    dv[(size_t)c0 * R + i] = gn * (dwt[((size_t)k * C0p + c0) * C1p + c1] - vr[i] * coef);
+    const float *src = dwt + ((size_t)k * C0p + c0) * C1p + c1;
+    float dw = 0.f;
+    for (int sp = 0; sp < splits; ++sp) dw += src[sp * split_stride];
+    dr[i] = dw;
+    s = fmaf(dw, vr[i], s);
   }
-  if (g && threadIdx.x == 0) dg[c0] = dot / n;
+  if (!g) return;
+  const float dot = block_reduce_sum(s, red);   // (also orders the dr writes before the re-reads below)
+  const float n = norm[c0];
+  const float gn = g[c0] / n;
+  const float coef = dot / (n * n);
+  for (int i = threadIdx.x; i < R; i += blockDim.x) dr[i] = gn * (dr[i] - vr[i] * coef);
+  if (threadIdx.x == 0) dg[c0] = dot / n;
 }
 
 }  // namespace rave
@@ -461,11 +466,13 @@ extern "C" int rave_weight_prep_tc(const float *v, const float *g, float *norm, 
 
 extern "C" int rave_weight_norm_bwd_tapmajor(const float *dwt, const float *v, const float *g, const float *norm,
                                              float *dv, float *dg, int C0, int C1, int K, int C0p, int C1p,
-                                             void *stream) {
+                                             int splits, void *stream) {
   using namespace rave;
   RAVE_CHECK_ARG(dwt && v && dv && C0 > 0 && C1 > 0 && K > 0, "weight_norm_bwd_tapmajor: bad argument");
   RAVE_CHECK_ARG(!g || (norm && dg), "weight_norm_bwd_tapmajor: weight norm needs norm and dg");
-  weight_norm_bwd_tapmajor_kernel<<<C0, 256, 0, (cudaStream_t)stream>>>(dwt, v, g, norm, dv, dg, C1, K, C0p, C1p);
+  RAVE_CHECK_ARG(splits >= 1, "weight_norm_bwd_tapmajor: splits must be >= 1");
+  weight_norm_bwd_tapmajor_kernel<<<C0, 256, 0, (cudaStream_t)stream>>>(dwt, v, g, norm, dv, dg, C1, K, C0p, C1p,
+                                                                       splits);
   RAVE_CHECK_LAUNCH("weight_norm_bwd_tapmajor");
   return 0;
 }

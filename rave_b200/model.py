@@ -153,6 +153,18 @@ class RAVE(nn.Module):
         self._scheduler = None
         self.logged: Dict[str, torch.Tensor] = {}
 
+    def _receptive_field_host(self):
+        """Host copy of the `receptive_field` buffer (read once: no device->host sync per step)."""
+        if getattr(self, "_rf_host", None) is None:
+            self._rf_host = tuple(int(v) for v in self.receptive_field.tolist())
+        return self._rf_host
+
+    def set_receptive_field(self, left: int, right: int):
+        """What validation_epoch_end does in the reference (rave/model.py:446-453)."""
+        self.receptive_field[0] = left
+        self.receptive_field[1] = right
+        self._rf_host = (int(left), int(right))
+
     # ------------------------------------------------------------------ optimisers
     def configure_optimizers(self):
         """rave/model.py:226-236."""
@@ -243,9 +255,15 @@ class RAVE(nn.Module):
         y_raw = y_raw[..., :x_raw.shape[-1]]
         y_multiband = y_multiband[..., :x_multiband.shape[-1]]
 
-        if self.valid_signal_crop and self.receptive_field.sum():
-            x_multiband = core.valid_signal_crop(x_multiband, *self.receptive_field)
-            y_multiband = core.valid_signal_crop(y_multiband, *self.receptive_field)
+        if self.valid_signal_crop:
+            left_rf, right_rf = self._receptive_field_host()
+            if left_rf + right_rf:
+                dim = x_multiband.shape[1]                      # core.valid_signal_crop, host-side ints
+                x_multiband = x_multiband[..., left_rf // dim:]
+                y_multiband = y_multiband[..., left_rf // dim:]
+                if right_rf:
+                    x_multiband = x_multiband[..., :-right_rf // dim]
+                    y_multiband = y_multiband[..., :-right_rf // dim]
 
         distances = {}
         for k, v in self.multiband_audio_distance(x_multiband, y_multiband).items():

@@ -410,16 +410,18 @@ def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None):
     Lq = q_pitch if Lq is None else Lq
     if P_cl.dtype != torch.bfloat16 or Q_cl.dtype != torch.bfloat16:
         raise _lib.RaveB200Error("conv1d_tc_wgrad: operands must be bf16")
-    dwt = torch.empty(K, Cm, Cn, dtype=torch.float32, device=P_cl.device)
+    splits = _lib.load().rave_conv1d_tc_wgrad_splits(B, Cm, Lp, Cn, K)
+    dwt = torch.empty(splits, K, Cm, Cn, dtype=torch.float32, device=P_cl.device)   # per-slice partial sums
     call("rave_conv1d_tc_wgrad", ptr(P_cl), ptr(Q_cl), ptr(dwt), B, Cm, Lp, p_pitch, Cn, Lq, q_pitch, K, stride,
          dil, pad_l, stream_ptr())
     return dwt
 
 
 def tapmajor_to_weight(dwt, transpose=False):
-    K, Cm, Cn = dwt.shape
+    """sum over the leading split axis of dwt [S][K][Cm][Cn] and re-layout to the parameter's [.,.,K]."""
+    S, K, Cm, Cn = dwt.shape
     dw = torch.empty((Cn, Cm, K) if transpose else (Cm, Cn, K), dtype=torch.float32, device=dwt.device)
-    call("rave_tapmajor_to_weight_f32", ptr(dwt), ptr(dw), Cm, Cn, K, int(transpose), stream_ptr())
+    call("rave_tapmajor_to_weight_f32", ptr(dwt), ptr(dw), Cm, Cn, K, int(transpose), S, stream_ptr())
     return dw
 
 
@@ -443,12 +445,12 @@ def weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p):
 
 
 def weight_norm_bwd_tapmajor(dwt, v, g, norm):
-    """dwt [K][C0p][C1p] fp32 -> (dv like v, dg like g | None)."""
+    """dwt [S][K][C0p][C1p] fp32 partial sums -> (dv like v, dg like g | None)."""
     v = _f32c(v)
     dv = torch.empty_like(v)
     dg = torch.empty_like(g) if g is not None else None
     C0, C1 = v.shape[0], v.shape[1]
     K = v.numel() // (C0 * C1)
     call("rave_weight_norm_bwd_tapmajor", ptr(dwt), ptr(v), ptr(g), ptr(norm), ptr(dv), ptr(dg), C0, C1, K,
-         dwt.shape[1], dwt.shape[2], stream_ptr())
+         dwt.shape[2], dwt.shape[3], dwt.shape[0], stream_ptr())
     return dv, dg

@@ -70,13 +70,17 @@ def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None):
     Q = Q_cl[:, :q_pitch].float()
     if q_pitch > Lq:
         assert float(Q[:, Lq:].abs().max()) == 0.0
-    dwt = torch.zeros(K, Cm, Cn)
+    S = 2                                  # two "row slices": the batch halves
+    dwt = torch.zeros(S, K, Cm, Cn)
     l = torch.arange(Lp)
+    half = (B + 1) // 2
     for k in range(K):
         r = l * stride + k * dil - pad_l
         ok = (r >= 0) & (r < Lq)
         if ok.any():
-            dwt[k] = torch.einsum("blm,bln->mn", P[:, l[ok]], Q[:, r[ok]])
+            dwt[0, k] = torch.einsum("blm,bln->mn", P[:half, l[ok]], Q[:half, r[ok]])
+            if B > half:
+                dwt[1, k] = torch.einsum("blm,bln->mn", P[half:, l[ok]], Q[half:, r[ok]])
     return dwt
 
 
@@ -96,7 +100,7 @@ def weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p):
 
 def weight_norm_bwd_tapmajor(dwt, v, g, norm):
     C0, C1 = v.shape[0], v.shape[1]
-    dw = dwt[:, :C0, :C1].permute(1, 2, 0).reshape(v.shape)
+    dw = dwt.sum(0)[:, :C0, :C1].permute(1, 2, 0).reshape(v.shape)
     if g is None:
         return dw.contiguous(), None
     v2 = v.reshape(C0, -1)
