@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--config", default="v2")
     ap.add_argument("--precision", default=os.environ.get("RAVE_B200_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="issue every launch from Python (no CUDA graphs)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     return ap.parse_args()
 
@@ -264,7 +265,22 @@ def run_ours(args):
     # second resident batch so consecutive steps do not hit identical cache lines
     x_dev2 = synthetic_batch(B, seed=4321 + rank).cuda()
 
+    trainer = None
+    graph_note = "eager launches"
+    if not args.no_graphs:
+        try:
+            from rave_b200.graphs import GraphedTrainer
+            trainer = GraphedTrainer(model, x_dev, grad_hook=reducer)
+            graph_note = "whole-step CUDA graphs (one for the G-step, one for the D-step)"
+        except Exception as e:          # report, and measure the eager path instead
+            graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            trainer = None
+            model._optimizers = None
+            torch.cuda.synchronize()
+
     def step(i, x):
+        if trainer is not None:
+            return trainer.step(x, i)
         return model.training_step(x, i, grad_hook=reducer)
 
     def barrier():
@@ -335,6 +351,7 @@ def run_ours(args):
                        "global_batch": world * B, "samples": T, "parallelism": f"dp{world}",
                        "precision": ("bf16 operands / fp32 accumulate (tcgen05 engine); PQMF + losses fp32"
                                      if prec == "bf16" else "fp32 parity kernels (CUDA-core FMA)"),
+                       "launch": graph_note,
                        "l2_policy": "working set per step (>10 GB of activations) exceeds the 126 MB L2; "
                                     "two alternating input batches"},
             "roofline": roof, "cpu_baseline": cpu,

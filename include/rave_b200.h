@@ -157,6 +157,28 @@ int rave_conv1d_tc_wgrad(const void *P_bf16, const void *Q_bf16, float *dwt, int
 /* sum_s dwt[s][K][Cm][Cn] -> dw[Cm][Cn][K] (transpose=0) or dw[Cn][Cm][K] (transpose=1), fp32 */
 int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int K, int transpose, int splits,
                                 void *stream);
+/* ---------------------------------------------------------------------------------------------
+ * small-channel kernels of the discriminators (csrc/conv_small.cu)
+ *   c1_fwd  : first conv of a ConvNet (Cin = 1; rave/discriminator.py:99-111 with in_size = 1):
+ *             out[r][l][co] = bias[co] + sum_k w[co][k] x[r][l*stride + k - pad_l];  x [R][x_pitch] fp32,
+ *             outputs channel-last [R][out_pitch][Cout] (fp32 stream and/or bf16 act(out)); Cout % 8 == 0.
+ *   c1_wgrad: dwt[s][k][co] partial sums over row slices, s < rave_conv1d_c1_wgrad_splits(R, Lout);
+ *             g bf16 channel-last [R][g_pitch][Cg] (first Cout channels), K <= 16, Cout <= 256.
+ *   fm_stats: feature-matching sums of rave/model.py:360-368 + core.mean_difference (rave/core.py:236-252)
+ *             on the bf16 operand stream a = LeakyReLU_slope(h), [2*Bh][pitch][C] (first Bh = real):
+ *             stats[0] += sum |h_r - h_f|, stats[1] += sum |h_r|  (l < L); stats must be pre-zeroed.
+ *   fm_grad : gradient of d0*S_diff + d1*S_abs w.r.t. h as a bf16 stream (slack rows zero). C % 8 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int rave_conv1d_c1_fwd(const float *x, const float *w, const float *bias, float *out_f32, void *out_act_bf16,
+                       int R, int x_pitch, int Lin, int Cout, int Lout, int out_pitch, int K, int stride,
+                       int pad_l, int act, float slope, void *stream);
+int rave_conv1d_c1_wgrad_splits(int R, int Lout);
+int rave_conv1d_c1_wgrad(const void *g_bf16, const float *x, float *dwt, int R, int x_pitch, int Lin, int Cout,
+                         int Cg, int Lout, int g_pitch, int K, int stride, int pad_l, void *stream);
+int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, int pitch, int C, float slope, void *stream);
+int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_bf16, int Bh, int L, int pitch, int C,
+                 float slope, void *stream);
+
 /* fused weight preparation for the engine: v [C0][C1][K] fp32 (+ weight-norm g [C0]; norm [C0] is written)
  *   outA[t][c0][c1] = bf16(w[c0][c1][tapsA[t]]), dims [nA][C0p][C1p]  (padded region zero)
  *   outB[t][c1][c0] = bf16(w[c0][c1][tapsB[t]]), dims [nB][C1p][C0p]

@@ -41,6 +41,11 @@ SIGNATURES = {
     "rave_conv1d_tc_wgrad_splits": (c_int, [_I, _I, _I, _I, _I]),
     "rave_weight_prep_tc": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rave_weight_norm_bwd_tapmajor": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "rave_conv1d_c1_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "rave_conv1d_c1_wgrad_splits": (c_int, [_I, _I]),
+    "rave_conv1d_c1_wgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rave_fm_stats": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P]),
+    "rave_fm_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "rave_ncl_to_cl": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "rave_cl_to_ncl": (c_int, [_P, _P, _I, _I, _I, _P]),
     "rave_act_to_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P]),

@@ -1,0 +1,293 @@
+// Small-channel kernels of the discriminators: layers that are NOT GEMM shaped and are bound by the
+// HBM traffic of their channel-last feature maps, written as direct CUDA-core kernels with coalesced
+// channel-contiguous access (north star: "warp shuffles for the small channel reductions, tensor
+// cores only where the contraction is genuinely dense").
+//
+//   * first conv of every ConvNet (Cin = 1): nn.Conv1d(1, C, 15, 4, 7) of the multi-scale and
+//     nn.Conv2d(1, C, (5,1), (4,1), (2,0)) of the multi-period discriminator, rave/discriminator.py:99-111
+//     (the folded period axis is extra batch) -- forward and weight gradient;
+//   * the feature-matching statistics of rave/model.py:360-368 (core.mean_difference, L1 / relative,
+//     rave/core.py:236-252) evaluated directly on the engine's bf16 operand stream a = LeakyReLU(h):
+//     S_diff = sum |h_real - h_fake|, S_abs = sum |h_real|, and the gradient of those two sums.
+#include "common.cuh"
+
+namespace rave {
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[r][l][co] = bias[co] + sum_k w[co][k] * x[r][l*stride + k - pad_l]      (x zero outside [0,Lin))
+// x: [R][x_pitch] fp32; outputs channel-last [R][out_pitch][Cout]: fp32 stream and/or bf16 act(out)
+// one thread = one output row position x 8 consecutive channels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_c1_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                   float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_act, int R, int x_pitch, int Lin,
+                   int Cout, int Lout, int out_pitch, int K, int stride, int pad_l, int act, float slope) {
+  extern __shared__ float sw[];   // [K][Cout] + bias[Cout]
+  float *sb = sw + K * Cout;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int k = i / Cout, co = i - k * Cout;
+    sw[i] = w[co * K + k];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int chunks = Cout >> 3;
+  const long total = (long)R * Lout * chunks;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % chunks) * 8;
+    const long rl = i / chunks;
+    const int l = (int)(rl % Lout);
+    const int r = (int)(rl / Lout);
+    const float *xr = x + (size_t)r * x_pitch;
+    const int base = l * stride - pad_l;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sb[c8 + j];
+    for (int k = 0; k < K; ++k) {
+      const int pos = base + k;
+      const float xv = (pos >= 0 && pos < Lin) ? __ldg(xr + pos) : 0.f;
+      const float4 w0 = *reinterpret_cast<const float4 *>(sw + k * Cout + c8);
+      const float4 w1 = *reinterpret_cast<const float4 *>(sw + k * Cout + c8 + 4);
+      acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+      acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+      acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+      acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+    }
+    const size_t o = ((size_t)r * out_pitch + l) * Cout + c8;
+    if (out_f32) {
+      float4 *o4 = reinterpret_cast<float4 *>(out_f32 + o);
+      o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (out_act) {
+      if (act == RAVE_ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * slope;
+      }
+      *reinterpret_cast<uint4 *>(out_act + o) = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                                                          pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dwt[cta][k][co] = sum_{(r,l) in the CTA's slice} g[r][l][co] * x[r][l*stride + k - pad_l]
+// g: bf16 channel-last [R][g_pitch][Cg] (only the first Cout channels are read).
+// block = Cout x NL threads (thread = one channel, NL row lanes); K <= 16 accumulators per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int C1_MAXK = 16;
+
+__global__ void __launch_bounds__(256)
+conv_c1_wgrad_kernel(const __nv_bfloat16 *__restrict__ g, const float *__restrict__ x, float *__restrict__ dwt,
+                     int R, int x_pitch, int Lin, int Cout, int Cg, int Lout, int g_pitch, int K, int stride,
+                     int pad_l, int NL) {
+  extern __shared__ float red[];   // [NL][K][Cout]
+  const int co = threadIdx.x % Cout;
+  const int lane = threadIdx.x / Cout;
+  float acc[C1_MAXK];
+#pragma unroll
+  for (int k = 0; k < C1_MAXK; ++k) acc[k] = 0.f;
+  const long total = (long)R * Lout;
+  const long per = (total + gridDim.x - 1) / gridDim.x;
+  const long begin = (long)blockIdx.x * per;
+  const long end = min(total, begin + per);
+  if (lane < NL) {
+    for (long i = begin + lane; i < end; i += NL) {
+      const int l = (int)(i % Lout);
+      const int r = (int)(i / Lout);
+      const float gv = __bfloat162float(g[((size_t)r * g_pitch + l) * Cg + co]);
+      const float *xr = x + (size_t)r * x_pitch;
+      const int base = l * stride - pad_l;
+#pragma unroll
+      for (int k = 0; k < C1_MAXK; ++k) {
+        if (k < K) {
+          const int pos = base + k;
+          const float xv = (pos >= 0 && pos < Lin) ? __ldg(xr + pos) : 0.f;
+          acc[k] = fmaf(gv, xv, acc[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < C1_MAXK; ++k)
+      if (k < K) red[((size_t)lane * K + k) * Cout + co] = acc[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    float s = 0.f;
+    for (int ln = 0; ln < NL; ++ln) s += red[(size_t)ln * K * Cout + i];
+    dwt[(size_t)blockIdx.x * K * Cout + i] = s;    // [cta][k][co]  (== [split][K][C0p=Cout][C1p=1])
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// feature-matching statistics on a = LeakyReLU(h) (bf16, channel-last [2*Bh][pitch][C]); the first Bh
+// batch entries are "real", the last Bh "fake" (rave/model.py:349-352 concatenates [x, y]).
+// stats[0] += sum |h_r - h_f|, stats[1] += sum |h_r|   over l < L, c < C.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float unleaky(float a, float inv_slope) { return a > 0.f ? a : a * inv_slope; }
+
+__global__ void __launch_bounds__(256)
+fm_stats_kernel(const __nv_bfloat16 *__restrict__ a, float *__restrict__ stats, int Bh, int L, int pitch, int C,
+                float inv_slope) {
+  __shared__ float red0[8], red1[8];
+  const int vecs = C >> 3;                       // 8 bf16 per 16-byte vector
+  const long total = (long)Bh * L * vecs;
+  const size_t half = (size_t)Bh * pitch * C;
+  float s0 = 0.f, s1 = 0.f;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int v = (int)(i % vecs);
+    const long bl = i / vecs;
+    const int l = (int)(bl % L);
+    const int b = (int)(bl / L);
+    const size_t o = ((size_t)b * pitch + l) * C + v * 8;
+    const uint4 r = *reinterpret_cast<const uint4 *>(a + o);
+    const uint4 f = *reinterpret_cast<const uint4 *>(a + o + half);
+    const uint32_t rw[4] = {r.x, r.y, r.z, r.w}, fw[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float hr0 = unleaky(bf16_lo(rw[j]), inv_slope), hr1 = unleaky(bf16_hi(rw[j]), inv_slope);
+      const float hf0 = unleaky(bf16_lo(fw[j]), inv_slope), hf1 = unleaky(bf16_hi(fw[j]), inv_slope);
+      s0 += fabsf(hr0 - hf0) + fabsf(hr1 - hf1);
+      s1 += fabsf(hr0) + fabsf(hr1);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red0[wid] = s0; red1[wid] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = 0; i < 8; ++i) { t0 += red0[i]; t1 += red1[i]; }
+    atomicAdd(stats, t0);
+    atomicAdd(stats + 1, t1);
+  }
+}
+
+// gradient of (d0 * S_diff + d1 * S_abs) with respect to h, written as the bf16 gradient stream:
+//   real rows: d0 sgn(h_r - h_f) + d1 sgn(h_r);  fake rows: -d0 sgn(h_r - h_f);  slack rows (l >= L): 0
+__global__ void __launch_bounds__(256)
+fm_grad_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ dstats,
+               __nv_bfloat16 *__restrict__ gout, int Bh, int L, int pitch, int C, float inv_slope) {
+  const float d0 = dstats[0], d1 = dstats[1];
+  const int vecs = C >> 3;
+  const long total = (long)Bh * pitch * vecs;
+  const size_t half = (size_t)Bh * pitch * C;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int v = (int)(i % vecs);
+    const long bl = i / vecs;
+    const int l = (int)(bl % pitch);
+    const int b = (int)(bl / pitch);
+    const size_t o = ((size_t)b * pitch + l) * C + v * 8;
+    uint32_t gr[4] = {0, 0, 0, 0}, gf[4] = {0, 0, 0, 0};
+    if (l < L) {
+      const uint4 r = *reinterpret_cast<const uint4 *>(a + o);
+      const uint4 f = *reinterpret_cast<const uint4 *>(a + o + half);
+      const uint32_t rw[4] = {r.x, r.y, r.z, r.w}, fw[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o_r[2], o_f[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float ar = h ? bf16_hi(rw[j]) : bf16_lo(rw[j]);
+          const float af = h ? bf16_hi(fw[j]) : bf16_lo(fw[j]);
+          const float hr = unleaky(ar, inv_slope), hf = unleaky(af, inv_slope);
+          const float sd = (hr > hf) ? 1.f : ((hr < hf) ? -1.f : 0.f);
+          const float sr = (hr > 0.f) ? 1.f : ((hr < 0.f) ? -1.f : 0.f);
+          o_r[h] = d0 * sd + d1 * sr;
+          o_f[h] = -d0 * sd;
+        }
+        gr[j] = pack_bf16(o_r[0], o_r[1]);
+        gf[j] = pack_bf16(o_f[0], o_f[1]);
+      }
+    }
+    *reinterpret_cast<uint4 *>(gout + o) = make_uint4(gr[0], gr[1], gr[2], gr[3]);
+    *reinterpret_cast<uint4 *>(gout + o + half) = make_uint4(gf[0], gf[1], gf[2], gf[3]);
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_conv1d_c1_fwd(const float *x, const float *w, const float *bias, float *out_f32,
+                                  void *out_act_bf16, int R, int x_pitch, int Lin, int Cout, int Lout,
+                                  int out_pitch, int K, int stride, int pad_l, int act, float slope, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && w && (out_f32 || out_act_bf16), "conv1d_c1_fwd: null pointer");
+  RAVE_CHECK_ARG(R > 0 && Lin > 0 && Lout > 0 && Cout > 0 && Cout % 8 == 0 && K > 0 && stride > 0,
+                 "conv1d_c1_fwd: bad shape (Cout must be a multiple of 8)");
+  RAVE_CHECK_ARG(act == RAVE_ACT_NONE || act == RAVE_ACT_LEAKY, "conv1d_c1_fwd: unsupported activation");
+  const long total = (long)R * Lout * (Cout / 8);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const size_t smem = (size_t)(K + 1) * Cout * sizeof(float);
+  conv_c1_fwd_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(
+      x, w, bias, out_f32, (__nv_bfloat16 *)out_act_bf16, R, x_pitch, Lin, Cout, Lout, out_pitch, K, stride, pad_l,
+      act, slope);
+  RAVE_CHECK_LAUNCH("conv1d_c1_fwd");
+  return 0;
+}
+
+extern "C" int rave_conv1d_c1_wgrad_splits(int R, int Lout) {
+  const long total = (long)R * Lout;
+  long s = total / 256;
+  if (s > 148 * 4) s = 148 * 4;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+extern "C" int rave_conv1d_c1_wgrad(const void *g_bf16, const float *x, float *dwt, int R, int x_pitch, int Lin,
+                                    int Cout, int Cg, int Lout, int g_pitch, int K, int stride, int pad_l,
+                                    void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(g_bf16 && x && dwt, "conv1d_c1_wgrad: null pointer");
+  RAVE_CHECK_ARG(K > 0 && K <= C1_MAXK && Cout > 0 && Cout <= 256 && Cg >= Cout, "conv1d_c1_wgrad: bad shape");
+  const int splits = rave_conv1d_c1_wgrad_splits(R, Lout);
+  int NL = 256 / Cout;
+  if (NL < 1) NL = 1;
+  const int threads = Cout * NL;
+  const size_t smem = (size_t)NL * K * Cout * sizeof(float);
+  RAVE_CHECK_ARG(smem <= 48 * 1024, "conv1d_c1_wgrad: reduction buffer too large");
+  conv_c1_wgrad_kernel<<<splits, threads, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16 *)g_bf16, x, dwt, R, x_pitch, Lin, Cout, Cg, Lout, g_pitch, K, stride, pad_l, NL);
+  RAVE_CHECK_LAUNCH("conv1d_c1_wgrad");
+  return 0;
+}
+
+extern "C" int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, int pitch, int C, float slope,
+                             void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(a_bf16 && stats && Bh > 0 && L > 0 && pitch >= L && C > 0 && C % 8 == 0 && slope > 0.f,
+                 "fm_stats: bad argument");
+  const long total = (long)Bh * L * (C / 8);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fm_stats_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a_bf16, stats, Bh, L, pitch,
+                                                                 C, 1.f / slope);
+  RAVE_CHECK_LAUNCH("fm_stats");
+  return 0;
+}
+
+extern "C" int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_bf16, int Bh, int L, int pitch,
+                            int C, float slope, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(a_bf16 && dstats && gout_bf16 && Bh > 0 && L > 0 && pitch >= L && C > 0 && C % 8 == 0 &&
+                     slope > 0.f,
+                 "fm_grad: bad argument");
+  const long total = (long)Bh * pitch * (C / 8);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fm_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a_bf16, dstats,
+                                                                (__nv_bfloat16 *)gout_bf16, Bh, L, pitch, C,
+                                                                1.f / slope);
+  RAVE_CHECK_LAUNCH("fm_grad");
+  return 0;
+}

@@ -88,20 +88,47 @@ class ConvNet(nn.Module):
             self.__dict__["_tc_specs_cache"] = specs
         return self.__dict__["_tc_specs_cache"]
 
-    def _forward_tc(self, x, specs):
-        """bf16 tensor-core path: the whole ConvNet as one chain in channel-last layout; features come
-        back as permuted views with the reference's shapes."""
+    def _chain_input(self, x, specs):
+        """Channel-last operand of the chain.  Cin = 1 (every shipped config): the raw fp32 rows
+        [B(*W), pitch] for the small-channel first-layer kernel; otherwise the zero-padded bf16 stream."""
         from . import engine
         first = specs[0]
-        cpad = first.cin_pad
         if x.dim() == 3:
             B, C, L = x.shape
+            W = 1
             rows = x.transpose(1, 2)
         else:
             B, C, L, W = x.shape
             rows = x.permute(0, 3, 2, 1).reshape(B * W, L, C)
         rpad = (-L) % first.stride              # row pitch: a multiple of the first layer's stride
-        xa = nn.functional.pad(rows, (0, cpad, 0, rpad)).to(engine.ACT_DTYPE).contiguous()
+        if C == 1 and first.dil == 1:
+            xa = nn.functional.pad(rows.reshape(B * W, L), (0, rpad)).contiguous()
+        else:
+            xa = nn.functional.pad(rows, (0, first.cin_pad, 0, rpad)).to(engine.ACT_DTYPE).contiguous()
+        return xa, B, W, L
+
+    def forward_fm(self, x):
+        """Fused feature-matching path (bf16 engine): x = cat([real, fake]) -> (stats [n-1, 2], counts,
+        score) with stats[i] = (sum|h_r - h_f|, sum|h_r|) of hidden feature i, counts[i] = its number of
+        elements per half, score = the last conv's output in the reference's shape."""
+        from . import engine
+        specs = self._tc_specs()
+        xa, B, W, L = self._chain_input(x, specs)
+        stats, last = engine.run_chain(xa, specs, L, fm=True)
+        lens = engine.chain_lengths(specs, L)
+        counts = [(B // 2) * W * Lo * s.Cout for s, Lo in zip(specs[:-1], lens[:-1])]
+        o = last[:, :lens[-1], :specs[-1].Cout]
+        if x.dim() == 3:
+            score = o.permute(0, 2, 1)
+        else:
+            score = o.reshape(B, W, lens[-1], specs[-1].Cout).permute(0, 3, 2, 1)
+        return stats, counts, score
+
+    def _forward_tc(self, x, specs):
+        """bf16 tensor-core path: the whole ConvNet as one chain in channel-last layout; features come
+        back as permuted views with the reference's shapes."""
+        from . import engine
+        xa, B, W, L = self._chain_input(x, specs)
         outs = engine.run_chain(xa, specs, L)
         lens = engine.chain_lengths(specs, L)
         features = []
@@ -138,6 +165,13 @@ class MultiScaleDiscriminator(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList([convnet(in_size=n_channels) for _ in range(n_discriminators)])
 
+    def forward_fm(self, x):
+        out = []
+        for layer in self.layers:
+            out.append(layer.forward_fm(x))
+            x = nn.functional.avg_pool1d(x, 2)
+        return out
+
     def forward(self, x):
         features = []
         for layer in self.layers:
@@ -160,6 +194,9 @@ class MultiPeriodDiscriminator(nn.Module):
             features.append(layer(self.fold(x, n)))
         return features
 
+    def forward_fm(self, x):
+        return [layer.forward_fm(self.fold(x, n)) for layer, n in zip(self.layers, self.periods)]
+
     def fold(self, x, n):
         pad = (n - (x.shape[-1] % n)) % n
         x = nn.functional.pad(x, (0, pad))
@@ -178,3 +215,22 @@ class CombineDiscriminators(nn.Module):
         for disc in self.discriminators:
             features.extend(disc(x))
         return features
+
+    def supports_fused_fm(self, x) -> bool:
+        """True when every sub-discriminator can run the fused feature-matching path on `x`."""
+        from . import engine
+        if engine.precision() != "bf16" or not x.is_cuda:
+            return False
+        for disc in self.discriminators:
+            if not hasattr(disc, "forward_fm"):
+                return False
+            for layer in disc.layers:
+                if not isinstance(layer, ConvNet) or layer._tc_specs() is None:
+                    return False
+        return True
+
+    def forward_fm(self, x):
+        out = []
+        for disc in self.discriminators:
+            out.extend(disc.forward_fm(x))
+        return out

@@ -195,7 +195,8 @@ class _PreparedWeights:
     """Effective weight of one layer in every tap-major bf16 layout the kernels need, produced from
     (v, g) by ONE fused launch pair (row norms + re-layout): rave_weight_prep_tc."""
 
-    def __init__(self, spec: LayerSpec, v: torch.Tensor, g: Optional[torch.Tensor], need_dgrad: bool):
+    def __init__(self, spec: LayerSpec, v: torch.Tensor, g: Optional[torch.Tensor], need_dgrad: bool,
+                 need_fwd: bool = True):
         self.spec = spec
         K, s = spec.K, spec.stride
         dev = v.device
@@ -210,7 +211,7 @@ class _PreparedWeights:
         self.dgrad_phases = None  # strided conv: per input phase (wt [n][Cin][Cout], pad'')
         phases = None
         if spec.kind == "conv":
-            tapsA = list(range(K))
+            tapsA = list(range(K)) if need_fwd else []
             if not need_dgrad:
                 tapsB = []
             elif s == 1:
@@ -222,7 +223,11 @@ class _PreparedWeights:
             phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
             tapsB = [k for order, _ in phases for k in order]
             tapsA = list(range(K)) if need_dgrad else []
-        self.norm, outA, outB = ops.weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p)
+        if tapsA or tapsB:
+            self.norm, outA, outB = ops.weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p)
+        else:
+            self.norm = ops.weight_norm_raw(v, g)[1] if g is not None else None
+            outA = outB = None
 
         def split(buf):
             out, off = [], 0
@@ -255,26 +260,39 @@ def _out_len(spec: LayerSpec, Lin: int) -> int:
 
 
 class TcChainFn(torch.autograd.Function):
-    """forward(x_cl_bf16 [B,L,Cin(+pad)], n_layers, specs, *flat_params) -> tuple of fp32 channel-last
-    outputs (one per spec with is_output)."""
+    """forward(x, specs, L0, fm, *flat_params).
+
+    x   : [B, pitch, Cin(+pad)] operand stream (ACT_DTYPE), or -- when the first layer has Cin == 1 --
+          the raw fp32 rows [B, pitch] (small-channel kernel, no padding to 16 channels, no bf16 rounding
+          of the audio).
+    fm  : False -> returns one fp32 channel-last tensor per `is_output` layer;
+          True  -> discriminator feature-matching mode: the batch is [real; fake]; returns
+                   (stats [n-1, 2] = per hidden layer (sum|h_r-h_f|, sum|h_r|), last layer fp32 output).
+                   Hidden features never reach HBM in fp32."""
 
     @staticmethod
-    def forward(ctx, x_cl, specs, L0, *flat):
+    def forward(ctx, x_in, specs, L0, fm, *flat):
         n = len(specs)
-        need_dgrad = x_cl.requires_grad or any(t is not None and t.requires_grad for t in flat)
-        B = x_cl.shape[0]
-        a = x_cl                                     # bf16 operand of the next layer (rows = pitch)
+        ctx.set_materialize_grads(False)
+        need_dgrad = x_in.requires_grad or any(t is not None and t.requires_grad for t in flat)
+        B = x_in.shape[0]
+        c1 = x_in.dim() == 2
+        if c1 and not (specs[0].kind == "conv" and specs[0].Cin == 1 and specs[0].dil == 1):
+            raise _lib.RaveB200Error("raw fp32 rows are only accepted by a Cin = 1 first conv")
+        dev = x_in.device
+        a = x_in
         f32: Dict[int, torch.Tensor] = {}
         acts: List[torch.Tensor] = []                 # operand consumed by layer i
         prepared: List[_PreparedWeights] = []
-        norms: List[Optional[torch.Tensor]] = []
         lens = [L0]
         outputs = []
+        stats = torch.zeros(max(n - 1, 1), 2, dtype=torch.float32, device=dev) if fm else None
         for i, s in enumerate(specs):
             v, g, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
-            pw = _PreparedWeights(s, v.detach(), g.detach() if g is not None else None, need_dgrad)
+            use_c1 = c1 and i == 0
+            pw = _PreparedWeights(s, v.detach(), g.detach() if g is not None else None, need_dgrad,
+                                  need_fwd=not use_c1)
             prepared.append(pw)
-            norms.append(pw.norm)
             Lin = lens[-1]
             Lout = _out_len(s, Lin)
             lens.append(Lout)
@@ -282,6 +300,7 @@ class TcChainFn(torch.autograd.Function):
             want_act = nxt is not None
             act_code = nxt.pre_act if nxt is not None else ops.ACT_NONE
             act_slope = nxt.pre_slope if nxt is not None else 0.0
+            want_f32 = s.want_f32 and not (fm and nxt is not None)
             # rows allocated per batch: the consumer's 4-D tensor map needs a multiple of its stride
             s_next = nxt.stride if (nxt is not None and nxt.kind == "conv") else 1
             pitch = (Lout + s_next - 1) // s_next * s_next
@@ -290,14 +309,18 @@ class TcChainFn(torch.autograd.Function):
             if bias is not None and s.cout_pad:
                 bias_p = nn.functional.pad(bias.detach(), (0, s.cout_pad))
             res = f32[s.res_src] if s.res_src is not None else None
-            out_f32 = torch.empty(B, pitch, cout_p, dtype=torch.float32, device=a.device) if s.want_f32 else None
-            out_act = torch.empty(B, pitch, cout_p, dtype=ACT_DTYPE, device=a.device) if want_act else None
+            out_f32 = torch.empty(B, pitch, cout_p, dtype=torch.float32, device=dev) if want_f32 else None
+            out_act = torch.empty(B, pitch, cout_p, dtype=ACT_DTYPE, device=dev) if want_act else None
             if pitch > Lout:
                 for t in (out_f32, out_act):
                     if t is not None:
                         t[:, Lout:].zero_()
             acts.append(a)
-            if s.kind == "conv":
+            if use_c1:
+                w_eff = ops.weight_norm_raw(v.detach(), g.detach())[0] if g is not None else v.detach()
+                ops.conv1d_c1(a, w_eff, bias, Lin, s.stride, s.pad, act_code, act_slope, out_f32=out_f32,
+                              out_act=out_act, Lout=Lout)
+            elif s.kind == "conv":
                 ops.conv1d_tc(a, pw.fwd, bias_p, res, s.stride, s.dil, s.pad, act_code, act_slope,
                               want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act, Lout=Lout,
                               Lin=Lin, out_rows=pitch)
@@ -311,19 +334,26 @@ class TcChainFn(torch.autograd.Function):
                     ops.conv1d_tc(a, wt, bias_p, None, 1, 1, (padpp, 0), act_code, act_slope, want_f32=False,
                                   want_act=False, out_f32=out_f32, out_act=out_act, out_rows=pitch,
                                   out_row_stride=s.stride, out_row_offset=p, Lout=Lp, Lin=Lin)
-            if s.want_f32:
+            if fm and nxt is not None:
+                if act_code != ops.ACT_LEAKY or s.cout_pad:
+                    raise _lib.RaveB200Error("feature-matching mode needs LeakyReLU between the layers")
+                ops.fm_stats(out_act, stats[i], Lout, act_slope)
+            if want_f32:
                 f32[i] = out_f32
-            if s.is_output:
+            if (s.is_output and not fm) or (fm and nxt is None):
                 outputs.append(out_f32)
             a = out_act
         ctx.specs = specs
         ctx.acts = acts
         ctx.prepared = prepared
-        ctx.norms = norms
         ctx.lens = lens
         ctx.params = flat
-        ctx.x_requires_grad = x_cl.requires_grad
+        ctx.fm = fm
+        ctx.c1 = c1
+        ctx.x_requires_grad = x_in.requires_grad
         ctx.out_index = [i for i, s in enumerate(specs) if s.is_output]
+        if fm:
+            return (stats,) + tuple(outputs)
         return tuple(outputs)
 
     @staticmethod
@@ -332,13 +362,20 @@ class TcChainFn(torch.autograd.Function):
         n = len(specs)
         flat = ctx.params
         B = ctx.acts[0].shape[0]
-        # external gradients (fp32 channel-last, full pitched shape) -> bf16
-        ext: Dict[int, torch.Tensor] = {}
-        for i, g in zip(ctx.out_index, gouts):
-            if g is not None:
-                ext[i] = g.to(ACT_DTYPE).contiguous()
+        ext: Dict[int, torch.Tensor] = {}      # external gradient of layer i's output (ACT_DTYPE, h-space)
+        dstats = None
+        if ctx.fm:
+            dstats = gouts[0]
+            if dstats is not None:
+                dstats = dstats.contiguous()
+            if gouts[1] is not None:
+                ext[n - 1] = gouts[1].to(ACT_DTYPE).contiguous()
+        else:
+            for i, g in zip(ctx.out_index, gouts):
+                if g is not None:
+                    ext[i] = g.to(ACT_DTYPE).contiguous()
         skip: Dict[int, torch.Tensor] = {}     # residual pass-through gradient for layer idx (or -1)
-        g_cur: Optional[torch.Tensor] = None   # gradient (h-space, bf16) of layer i's output
+        g_cur: Optional[torch.Tensor] = None   # gradient (h-space) of layer i's output
         grads = [None] * len(flat)
         gx = None
         for i in range(n - 1, -1, -1):
@@ -346,6 +383,7 @@ class TcChainFn(torch.autograd.Function):
             pw = ctx.prepared[i]
             a_in = ctx.acts[i]
             Lin, Lout = ctx.lens[i], ctx.lens[i + 1]
+            use_c1 = ctx.c1 and i == 0
             g = g_cur
             if g is None:
                 g = ext.get(i)
@@ -357,12 +395,14 @@ class TcChainFn(torch.autograd.Function):
             v, gpar, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
             # ---- weight gradient
             if v.requires_grad:
-                if s.kind == "conv":
+                if use_c1:
+                    dwt = ops.conv1d_c1_wgrad(g, a_in, s.Cout, s.K, Lin, Lout, s.stride, s.pad[0])
+                elif s.kind == "conv":
                     dwt = ops.conv1d_tc_wgrad(g, a_in, s.K, s.stride, s.dil, s.pad[0], Lp=Lout, Lq=Lin)
                 else:
                     dwt = ops.conv1d_tc_wgrad(a_in, g, s.K, s.stride, 1, s.pad[0], Lp=Lin, Lq=Lout)
-                # dwt is [K][C0p][C1p] in the parameter's own (C0, C1) order for both kinds
-                dv, dg = ops.weight_norm_bwd_tapmajor(dwt, v, gpar, ctx.norms[i])
+                # dwt is [S][K][C0p][C1p] in the parameter's own (C0, C1) order for both kinds
+                dv, dg = ops.weight_norm_bwd_tapmajor(dwt, v, gpar, pw.norm)
                 grads[3 * i], grads[3 * i + 1] = dv, dg
             if bias is not None and bias.requires_grad:
                 grads[3 * i + 2] = g[:, :Lout, :s.Cout].float().sum((0, 1))
@@ -375,6 +415,8 @@ class TcChainFn(torch.autograd.Function):
             if prev in skip:
                 add = skip.pop(prev)
             e = ext.get(prev) if prev >= 0 else None
+            if ctx.fm and prev >= 0 and dstats is not None:
+                e = ops.fm_grad(a_in, dstats[prev], Lin, s.pre_slope)
             if e is not None:
                 add = e if add is None else (add + e)
             dact = a_in if s.pre_act == ops.ACT_LEAKY else None
@@ -405,20 +447,21 @@ class TcChainFn(torch.autograd.Function):
                               res_bf16=add, dact_src=dact)
             g_cur = gp
             if i == 0:
-                gx = gp
-        return (gx, None, None) + tuple(grads)
+                gx = gp[..., 0].float() if ctx.c1 else gp
+        return (gx, None, None, None) + tuple(grads)
 
 
-def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None):
-    """x_cl_bf16: [B, pitch, Cin(+pad)] (rows beyond the true length L0 must be zero).  Returns one fp32
-    channel-last tensor [B, pitch_i, Cout_i(+pad)] per output layer (slice [:, :L_i, :Cout_i])."""
+def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None, fm: bool = False):
+    """x_cl_bf16: [B, pitch, Cin(+pad)] (rows beyond the true length L0 must be zero), or raw fp32 rows
+    [B, pitch] for a Cin = 1 first layer.  Returns one fp32 channel-last tensor [B, pitch_i, Cout_i(+pad)]
+    per output layer (slice [:, :L_i, :Cout_i]); with fm=True: (stats [n-1, 2], last layer output)."""
     flat = []
     for s in specs:
         v, g, b = _layer_params(s)
         flat += [v, g, b]
     if L0 is None:
         L0 = x_cl_bf16.shape[1]
-    return TcChainFn.apply(x_cl_bf16, specs, L0, *flat)
+    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, *flat)
 
 
 def chain_lengths(specs: List[LayerSpec], L0: int) -> List[int]:

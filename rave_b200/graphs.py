@@ -1,0 +1,54 @@
+"""Whole-step CUDA graphs: the phase-2 training step is ~1.3k kernel launches (ours + the loss
+arithmetic + Adam); issued from Python that is tens of milliseconds of host time, several times the
+GPU time of the bf16 step.  `GraphedTrainer` captures the generator step and the discriminator step of
+`RAVE.train_body` once (after eager warm-up) and replays them, so the step costs its GPU time.
+
+Replay-safe because train_body has no host-side decisions or syncs, the optimisers are `capturable`
+(lr and step counters live on the device; LinearLR updates the lr tensor in place between replays) and
+every buffer the library kernels see is allocated from the graph's private pool (tensor maps bake the
+addresses at capture).
+"""
+from typing import Dict, Optional
+
+import torch
+
+
+class GraphedTrainer:
+    def __init__(self, model, example_batch: torch.Tensor, grad_hook=None, warmup_steps: int = 3):
+        if not example_batch.is_cuda:
+            raise RuntimeError("GraphedTrainer needs a CUDA batch")
+        self.model = model
+        self.grad_hook = grad_hook
+        self.x_static = example_batch.clone()
+        model.optimizers(capturable=True)
+        if not model.warmed_up:
+            raise RuntimeError("capture phase-2 steps (model.warmed_up = True); phase 1 has no D-step")
+        self.graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
+        self.outputs: Dict[bool, Dict[str, torch.Tensor]] = {}
+        # eager warm-up on a side stream: lazy state (Adam moments, cuFFT plans, PQMF tables, kernel
+        # attributes, tensor-map entry point) must exist before capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(warmup_steps):
+                for is_dis in (True, False):
+                    model.train_body(self.x_static, is_dis, None, grad_hook)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pool = None
+        for is_dis in (True, False):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                logs = model.train_body(self.x_static, is_dis, None, grad_hook)
+                out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in logs.items()}
+            pool = g.pool()
+            self.graphs[is_dis] = g
+            self.outputs[is_dis] = out
+
+    def step(self, batch: torch.Tensor, batch_idx: int):
+        """Same contract as RAVE.training_step: returns the logged scalars (device tensors)."""
+        is_dis = self.model.is_discriminator_step(batch_idx)
+        self.x_static.copy_(batch, non_blocking=True)
+        self.graphs[is_dis].replay()
+        self.model.logged = self.outputs[is_dis]
+        return self.outputs[is_dis]

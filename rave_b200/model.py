@@ -166,19 +166,25 @@ class RAVE(nn.Module):
         self._rf_host = (int(left), int(right))
 
     # ------------------------------------------------------------------ optimisers
-    def configure_optimizers(self):
-        """rave/model.py:226-236."""
+    def configure_optimizers(self, capturable: bool = False):
+        """rave/model.py:226-236.  `capturable=True` keeps lr / step counters on the device so that the
+        whole step can be replayed from a CUDA graph (rave_b200/graphs.py); same Adam arithmetic."""
         gen_p = list(self.encoder.parameters()) + list(self.decoder.parameters())
         dis_p = list(self.discriminator.parameters())
-        gen_opt = torch.optim.Adam(gen_p, 1e-3, (.5, .9))
-        dis_opt = torch.optim.Adam(dis_p, 1e-4, (.5, .9))
+        if capturable:
+            dev = gen_p[0].device
+            gen_opt = torch.optim.Adam(gen_p, torch.tensor(1e-3, device=dev), (.5, .9), capturable=True)
+            dis_opt = torch.optim.Adam(dis_p, torch.tensor(1e-4, device=dev), (.5, .9), capturable=True)
+        else:
+            gen_opt = torch.optim.Adam(gen_p, 1e-3, (.5, .9))
+            dis_opt = torch.optim.Adam(dis_p, 1e-4, (.5, .9))
         sched = torch.optim.lr_scheduler.LinearLR(gen_opt, start_factor=1.0, end_factor=0.1,
                                                   total_iters=self.warmup)
         return ({"optimizer": gen_opt, "lr_scheduler": {"scheduler": sched}}, {"optimizer": dis_opt})
 
-    def optimizers(self):
+    def optimizers(self, capturable: bool = False):
         if self._optimizers is None:
-            g, d = self.configure_optimizers()
+            g, d = self.configure_optimizers(capturable)
             self._optimizers = (g["optimizer"], d["optimizer"])
             self._scheduler = g["lr_scheduler"]["scheduler"]
         return self._optimizers
@@ -272,9 +278,14 @@ class RAVE(nn.Module):
             distances[f"fullband_{k}"] = self.weights["audio_distance"] * v
 
         feature_matching_distance = 0.
+        fused = None
         if self.warmed_up:
             y_d = y_raw.detach() if is_dis_step else y_raw     # quirk D2: discarded gradients
             xy = torch.cat([x_raw, y_d], 0)
+            fused = self._fused_feature_matching(xy)
+        if fused is not None:
+            feature_matching_distance, loss_dis, loss_adv, pred_real, pred_fake = fused
+        elif self.warmed_up:
             features = self.discriminator(xy)
             feature_real, feature_fake = self.split_features(features)
             loss_dis = 0
@@ -307,16 +318,54 @@ class RAVE(nn.Module):
         aux = dict(pred_real=pred_real, pred_fake=pred_fake, y_raw=y_raw, z=z)
         return loss_gen, loss_dis, aux
 
+    def _fused_feature_matching(self, xy):
+        """The discrimination block (rave/model.py:348-379) without materialising the hidden features:
+        in bf16 mode every ConvNet returns, per hidden layer, (sum|h_r - h_f|, sum|h_r|) computed by the
+        engine from its own operand stream, plus the score tensor.  Same arithmetic as
+        core.mean_difference(norm='L1', relative=...) averaged like the reference."""
+        disc = self.discriminator
+        kw = getattr(self.feature_matching_fun, "keywords", None)
+        if kw is None or getattr(self.feature_matching_fun, "func", None) is not core.mean_difference:
+            return None
+        if kw.get("norm", "L1") != "L1" or not hasattr(disc, "supports_fused_fm") or not disc.supports_fused_fm(xy):
+            return None
+        relative = bool(kw.get("relative", False))
+        skip = self.num_skipped_features
+        fm_total, loss_dis, loss_adv, pred_real, pred_fake = 0., 0., 0., 0., 0.
+        nets = disc.forward_fm(xy)
+        for stats, counts, score in nets:
+            half = score.shape[0] // 2
+            s_real, s_fake = score[:half], score[half:]
+            terms = []
+            for i in range(skip, len(counts)):
+                if relative:
+                    terms.append(stats[i, 0] / stats[i, 1])
+                else:
+                    terms.append(stats[i, 0] / counts[i])
+            if skip <= len(counts):                       # the score itself is the last "feature"
+                terms.append(self.feature_matching_fun(s_real, s_fake))
+            fm_total = fm_total + sum(terms) / len(terms)
+            _dis, _adv = self.gan_loss(s_real, s_fake)
+            pred_real = pred_real + s_real.mean()
+            pred_fake = pred_fake + s_fake.mean()
+            loss_dis = loss_dis + _dis
+            loss_adv = loss_adv + _adv
+        return fm_total / len(nets), loss_dis, loss_adv, pred_real, pred_fake
+
     def is_discriminator_step(self, batch_idx: int) -> bool:
         return (not (batch_idx % self.update_discriminator_every)) and self.warmed_up
 
     def training_step(self, batch, batch_idx, eps: Optional[torch.Tensor] = None, grad_hook=None):
         """rave/model.py:288-424.  `grad_hook(params)` (optional) runs between backward and the
         optimiser step: the data-parallel gradient all-reduce plugs in there (rave_b200/ddp.py)."""
-        gen_opt, dis_opt = self.optimizers()
         x_raw = batch
         is_dis = self.is_discriminator_step(batch_idx)
+        return self.train_body(x_raw, is_dis, eps, grad_hook)
 
+    def train_body(self, x_raw, is_dis: bool, eps: Optional[torch.Tensor] = None, grad_hook=None):
+        """Everything `training_step` does for one batch once the step kind is known (no host-side
+        decisions, no device->host sync: capturable in a CUDA graph)."""
+        gen_opt, dis_opt = self.optimizers()
         dis_params = [p for p in self.discriminator.parameters()]
         for p in dis_params:                       # G-step: no discriminator wgrad (discarded work)
             p.requires_grad_(is_dis)

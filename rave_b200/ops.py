@@ -454,3 +454,56 @@ def weight_norm_bwd_tapmajor(dwt, v, g, norm):
     call("rave_weight_norm_bwd_tapmajor", ptr(dwt), ptr(v), ptr(g), ptr(norm), ptr(dv), ptr(dg), C0, C1, K,
          dwt.shape[2], dwt.shape[3], dwt.shape[0], stream_ptr())
     return dv, dg
+
+
+# ----------------------------------------------------------------------------------------------
+# small-channel discriminator kernels (csrc/conv_small.cu)
+# ----------------------------------------------------------------------------------------------
+
+def conv1d_c1(x_rows, w, bias, Lin, stride, pad, act, slope, out_f32=None, out_act=None, Lout=None):
+    """First conv of a ConvNet (Cin = 1): x_rows [R, x_pitch] fp32, w [Cout, 1, K(,1)] fp32 ->
+    channel-last outputs [R, out_pitch, Cout] written in place (fp32 stream and/or bf16 act(out))."""
+    x_rows = _f32c(x_rows)
+    w = _f32c(w)
+    R, x_pitch = x_rows.shape
+    Cout = w.shape[0]
+    K = w.numel() // Cout
+    ref = out_f32 if out_f32 is not None else out_act
+    call("rave_conv1d_c1_fwd", ptr(x_rows), ptr(w), ptr(bias), ptr(out_f32), ptr(out_act), R, x_pitch, Lin, Cout,
+         Lout, ref.shape[1], K, stride, pad[0], act, float(slope), stream_ptr())
+    return out_f32, out_act
+
+
+def conv1d_c1_wgrad(g_cl, x_rows, Cout, K, Lin, Lout, stride, pad_l):
+    """dwt [S, K, Cout, 1] fp32 partial sums: sum_rows g[r,l,co] * x[r, l*stride + k - pad_l]."""
+    R, g_pitch, Cg = g_cl.shape
+    x_rows = _f32c(x_rows)
+    splits = _lib.load().rave_conv1d_c1_wgrad_splits(R, Lout)
+    dwt = torch.empty(splits, K, Cout, 1, dtype=torch.float32, device=g_cl.device)
+    call("rave_conv1d_c1_wgrad", ptr(g_cl), ptr(x_rows), ptr(dwt), R, x_rows.shape[1], Lin, Cout, Cg, Lout, g_pitch,
+         K, stride, pad_l, stream_ptr())
+    return dwt
+
+
+def fm_stats(a_cl, stats_row, L, slope):
+    """stats_row[0:2] += (sum |h_r - h_f|, sum |h_r|) over the real/fake batch halves of a = leaky(h)."""
+    B2, pitch, C = a_cl.shape
+    call("rave_fm_stats", ptr(a_cl), stats_row.data_ptr(), B2 // 2, L, pitch, C, float(slope), stream_ptr())
+
+
+def fm_grad(a_cl, dstats_row, L, slope):
+    """bf16 gradient stream of dstats_row[0]*S_diff + dstats_row[1]*S_abs with respect to h."""
+    B2, pitch, C = a_cl.shape
+    g = torch.empty_like(a_cl)
+    call("rave_fm_grad", ptr(a_cl), dstats_row.data_ptr(), ptr(g), B2 // 2, L, pitch, C, float(slope), stream_ptr())
+    return g
+
+
+def weight_norm_raw(v, g):
+    """(w, norm) = (g v/||v||, ||v||) without autograd (engine-internal)."""
+    v, g = _f32c(v), _f32c(g)
+    C0 = v.shape[0]
+    w = torch.empty_like(v)
+    norm = torch.empty(C0, dtype=torch.float32, device=v.device)
+    call("rave_weight_norm_fwd", ptr(v), ptr(g), ptr(w), ptr(norm), C0, v.numel() // C0, stream_ptr())
+    return w, norm

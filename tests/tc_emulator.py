@@ -123,8 +123,69 @@ def cl_to_ncl(x_cl):
     return x_cl.permute(0, 2, 1).contiguous()
 
 
+def weight_norm_raw(v, g):
+    C0 = v.shape[0]
+    norm = v.reshape(C0, -1).norm(2, 1)
+    shape = (C0,) + (1,) * (v.dim() - 1)
+    return v * (g.reshape(shape) / norm.reshape(shape)), norm
+
+
+def conv1d_c1(x_rows, w, bias, Lin, stride, pad, act, slope, out_f32=None, out_act=None, Lout=None):
+    R, x_pitch = x_rows.shape
+    Cout = w.shape[0]
+    K = w.numel() // Cout
+    x = x_rows[:, :Lin].unsqueeze(1)
+    need = (Lout - 1) * stride + K
+    xp = F.pad(x, (pad[0], max(0, need - pad[0] - Lin)))
+    y = F.conv1d(xp, w.reshape(Cout, 1, K), bias, stride)[..., :Lout].permute(0, 2, 1)
+    if out_f32 is not None:
+        out_f32[:, :Lout] = y
+    if out_act is not None:
+        out_act[:, :Lout] = _bf16(F.leaky_relu(y, slope) if act == 1 else y)
+    return out_f32, out_act
+
+
+def conv1d_c1_wgrad(g_cl, x_rows, Cout, K, Lin, Lout, stride, pad_l):
+    R = g_cl.shape[0]
+    g = g_cl[:, :Lout, :Cout].float()
+    dwt = torch.zeros(3, K, Cout, 1)                       # 3 "slices": rows split arbitrarily
+    l = torch.arange(Lout)
+    for k in range(K):
+        pos = l * stride + k - pad_l
+        ok = (pos >= 0) & (pos < Lin)
+        if ok.any():
+            xv = x_rows[:, pos[ok]]                          # [R, n]
+            full = torch.einsum("rlc,rl->c", g[:, l[ok]], xv)
+            dwt[0, k, :, 0] = 0.25 * full
+            dwt[1, k, :, 0] = 0.5 * full
+            dwt[2, k, :, 0] = 0.25 * full
+    return dwt
+
+
+def _unleaky(a, slope):
+    return torch.where(a > 0, a, a / slope)
+
+
+def fm_stats(a_cl, stats_row, L, slope):
+    B2 = a_cl.shape[0]
+    h = _unleaky(a_cl[:, :L].float(), slope)
+    hr, hf = h[:B2 // 2], h[B2 // 2:]
+    stats_row[0] += (hr - hf).abs().sum()
+    stats_row[1] += hr.abs().sum()
+
+
+def fm_grad(a_cl, dstats_row, L, slope):
+    B2 = a_cl.shape[0]
+    h = _unleaky(a_cl.float(), slope)
+    hr, hf = h[:B2 // 2], h[B2 // 2:]
+    sd = torch.sign(hr - hf)
+    g = torch.cat([dstats_row[0] * sd + dstats_row[1] * torch.sign(hr), -dstats_row[0] * sd], 0)
+    g[:, L:] = 0
+    return _bf16(g)
+
+
 def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
-                 "cl_to_ncl"):
+                 "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -129,3 +129,38 @@ def test_discriminator_chain_vs_oracle(emu):
     assert rel_l2(g_e[0], g_o[0]) < tol(emu, 2e-5, 0.2)
     for k, a, b in zip(names, g_e[1:], g_o[1:]):
         assert a.shape == b.shape and rel_l2(a, b) < tol(emu, 5e-5, 0.25), (k, rel_l2(a, b))
+
+
+def test_fused_feature_matching_vs_oracle(emu):
+    """RAVE._fused_feature_matching (stats computed by the engine from its operand stream) reproduces
+    the reference's discrimination block (rave/model.py:348-379) and its gradients."""
+    from functools import partial
+    from rave_b200 import configs, core, engine
+    torch.manual_seed(4)
+    disc = configs.make_discriminator_v2(capacity=16)
+    sd = {"discriminator." + k: v.detach().clone() for k, v in disc.state_dict().items()}
+    x = (0.5 * torch.randn(4, 1, 2048 + 5)).clamp(-1, 1)
+    po = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    fm_o, ld_o, la_o = O.gan_losses(O.combine_discriminators_v2(xo, po), 1, True)
+
+    class Holder:            # the slice of RAVE that _fused_feature_matching touches
+        pass
+    from rave_b200.model import RAVE
+    h = Holder()
+    h.discriminator = disc
+    h.feature_matching_fun = partial(core.mean_difference, norm="L1", relative=True)
+    h.num_skipped_features = 1
+    h.gan_loss = core.hinge_gan
+    disc.supports_fused_fm = lambda xy: True            # (the real check also demands CUDA + bf16 mode)
+    xe = x.clone().requires_grad_(True)
+    fm, ld, la, pr, pf = RAVE._fused_feature_matching(h, xe)
+    t = tol(emu, 2e-5, 3e-2)
+    assert rel_l2(fm, fm_o) < t and rel_l2(ld, ld_o) < t and rel_l2(la, la_o) < t
+    names = sorted(po)
+    g_o = torch.autograd.grad(20 * fm_o + ld_o + la_o, [xo] + [po[k] for k in names])
+    pp = dict(disc.named_parameters(prefix="discriminator"))
+    g_e = torch.autograd.grad(20 * fm + ld + la, [xe] + [pp[k] for k in names])
+    assert rel_l2(g_e[0], g_o[0]) < tol(emu, 5e-5, 0.25)
+    for k, a, b in zip(names, g_e[1:], g_o[1:]):
+        assert a.shape == b.shape and rel_l2(a, b) < tol(emu, 1e-4, 0.3), (k, rel_l2(a, b))

@@ -123,3 +123,48 @@ def test_training_step_bf16_runs():
     logs = m.training_step(x, 1)
     for k in ("fullband_spectral_distance", "feature_matching", "adversarial", "loss_dis"):
         assert torch.isfinite(logs[k]), k
+
+
+def test_fused_feature_matching_bf16_vs_oracle():
+    """The fused discrimination block (no fp32 features in HBM) against the oracle's gan_losses."""
+    from rave_b200 import configs
+    torch.manual_seed(5)
+    m = configs.build_rave("v2", capacity=16, latent_size=16, disc_capacity=16).cuda().train()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items() if k.startswith("discriminator.")}
+    xy = (0.5 * torch.randn(4, 1, 8192)).clamp(-1, 1)
+    feats_o = O.combine_discriminators_v2(xy, sd)
+    fm_o, ld_o, la_o = O.gan_losses(feats_o, 1, True)
+    assert m.discriminator.supports_fused_fm(xy.cuda())
+    fm, ld, la, pr, pf = m._fused_feature_matching(xy.cuda())
+    assert rel_l2(fm, fm_o) < FWD_TOL and rel_l2(ld, ld_o) < FWD_TOL and rel_l2(la, la_o) < 5e-2
+
+
+def test_cuda_graph_training_matches_eager():
+    """GraphedTrainer replays == eager training_step on the same data (same kernels, same order)."""
+    import copy
+    from rave_b200 import configs
+    from rave_b200.graphs import GraphedTrainer
+    torch.manual_seed(0)
+    m1 = configs.build_rave("v2", capacity=16, latent_size=16, disc_capacity=16).cuda().train()
+    m1.warmed_up = True
+    m2 = copy.deepcopy(m1)
+    x = (0.5 * torch.randn(2, 1, 65536, device="cuda")).clamp(-1, 1)
+    # freeze the reparametrisation noise so both runs see the same numbers
+    for m in (m1, m2):
+        m.encoder.reparametrize = (lambda z, eps=None, enc=m.encoder: type(enc).reparametrize(enc, z, torch.zeros_like(z[:, :z.shape[1] // 2])))
+    tr = GraphedTrainer(m2, x, warmup_steps=2)
+    # eager twin performs the same updates as the trainer's warm-up: 2 rounds of (D, G); capture itself
+    # executes nothing
+    m1.optimizers(capturable=True)
+    for _ in range(2):
+        m1.train_body(x, True)
+        m1.train_body(x, False)
+    for i in range(4):
+        la = tr.step(x, i)
+        lb = m1.training_step(x, i)
+    torch.cuda.synchronize()
+    for k in ("fullband_spectral_distance", "feature_matching", "adversarial"):
+        assert rel_l2(la[k], lb[k]) < 2e-2, (k, float(la[k]), float(lb[k]))
+    w1 = m1.decoder.net[0].weight_v
+    w2 = m2.decoder.net[0].weight_v
+    assert rel_l2(w2, w1) < 1e-2

@@ -91,3 +91,38 @@ def test_conv1d_tc_wgrad_vs_oracle(case):
     torch.cuda.synchronize()
     assert dw.shape == dw_ref.shape
     assert rel_l2(dw, dw_ref) < 2e-5
+
+
+def test_small_channel_kernels_vs_emulator():
+    """conv_c1 fwd/wgrad and the feature-matching stats/grad kernels against the torch emulation of
+    their documented semantics (tests/tc_emulator.py), which test_engine_cpu.py ties to the oracle."""
+    from rave_b200 import ops
+    from tests import tc_emulator as E
+    torch.manual_seed(0)
+    for (R, L, Cout, K, stride, pad) in [(6, 1000, 96, 15, 4, 7), (10, 333, 48, 5, 4, 2), (3, 64, 32, 5, 3, 2)]:
+        x = torch.randn(R, L + 3)
+        w = torch.randn(Cout, 1, K) * 0.3
+        b = torch.randn(Cout)
+        Lout = (L + 2 * pad - K) // stride + 1
+        pitch = Lout + 2
+        of_e, oa_e = torch.zeros(R, pitch, Cout), torch.zeros(R, pitch, Cout, dtype=torch.bfloat16)
+        E.conv1d_c1(x, w, b, L, stride, (pad, pad), 1, 0.2, out_f32=of_e, out_act=oa_e, Lout=Lout)
+        of = torch.zeros(R, pitch, Cout, device="cuda")
+        oa = torch.zeros(R, pitch, Cout, device="cuda", dtype=torch.bfloat16)
+        ops.conv1d_c1(x.cuda(), w.cuda(), b.cuda(), L, stride, (pad, pad), 1, 0.2, out_f32=of, out_act=oa, Lout=Lout)
+        assert rel_l2(of, of_e) < 1e-5 and rel_l2(oa.float(), oa_e.float()) < 4e-3
+        g = torch.randn(R, pitch, Cout).bfloat16()
+        dw_e = E.conv1d_c1_wgrad(g, x, Cout, K, L, Lout, stride, pad).sum(0)
+        dw = ops.conv1d_c1_wgrad(g.cuda(), x.cuda(), Cout, K, L, Lout, stride, pad).sum(0)
+        assert dw.shape == dw_e.shape and rel_l2(dw, dw_e) < 1e-4
+    for (B2, L, pitch, C) in [(4, 100, 104, 96), (8, 17, 20, 192), (2, 5, 5, 16)]:
+        a = torch.randn(B2, pitch, C).bfloat16()
+        st_e = torch.zeros(2)
+        E.fm_stats(a, st_e, L, 0.2)
+        st = torch.zeros(2, device="cuda")
+        ops.fm_stats(a.cuda(), st, L, 0.2)
+        assert rel_l2(st, st_e) < 1e-4
+        d = torch.tensor([0.37, -1.2])
+        g_e = E.fm_grad(a, d, L, 0.2)
+        g = ops.fm_grad(a.cuda(), d.cuda(), L, 0.2)
+        assert torch.equal(g.float().cpu(), g_e.float())
