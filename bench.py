@@ -258,7 +258,7 @@ def run_ours(args):
     model = configs.build_rave(args.config, sampling_rate=SR).cuda().train()
     model.warmed_up = True          # phase 2: discriminator in the loop (BASELINE config 3)
     ddp.broadcast_module(model)
-    reducer = ddp.GradientAllReducer() if world > 1 else None
+    reducer = ddp.GradientAllReducer(async_op=args.no_graphs) if world > 1 else None
     B = args.batch
     x_host = synthetic_batch(B, seed=1234 + rank).pin_memory()
     x_dev = x_host.cuda()
@@ -308,6 +308,8 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
+    if trainer is not None:      # replayed launches do not pass through the library's counter
+        launches += sum(trainer.launches[model.is_discriminator_step(i)] for i in range(args.steps))
     clocks = sampler.stop() if sampler else None
 
     # ---- end to end: pinned host input -> H2D -> step -> D2H of the loss --------------------

@@ -162,8 +162,8 @@ int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int
  *   c1_fwd  : first conv of a ConvNet (Cin = 1; rave/discriminator.py:99-111 with in_size = 1):
  *             out[r][l][co] = bias[co] + sum_k w[co][k] x[r][l*stride + k - pad_l];  x [R][x_pitch] fp32,
  *             outputs channel-last [R][out_pitch][Cout] (fp32 stream and/or bf16 act(out)); Cout % 8 == 0.
- *   c1_wgrad: dwt[s][k][co] partial sums over row slices, s < rave_conv1d_c1_wgrad_splits(R, Lout);
- *             g bf16 channel-last [R][g_pitch][Cg] (first Cout channels), K <= 16, Cout <= 256.
+ *   c1_wgrad: dwt[s][k][co] with s < rave_conv1d_c1_wgrad_splits(R, Lout) (= 1: CTA partials are combined
+ *             with fp32 atomics); g bf16 channel-last [R][g_pitch][Cg] (first Cout channels), K <= 16.
  *   fm_stats: feature-matching sums of rave/model.py:360-368 + core.mean_difference (rave/core.py:236-252)
  *             on the bf16 operand stream a = LeakyReLU_slope(h), [2*Bh][pitch][C] (first Bh = real):
  *             stats[0] += sum |h_r - h_f|, stats[1] += sum |h_r|  (l < L); stats must be pre-zeroed.
@@ -175,6 +175,11 @@ int rave_conv1d_c1_fwd(const float *x, const float *w, const float *bias, float 
 int rave_conv1d_c1_wgrad_splits(int R, int Lout);
 int rave_conv1d_c1_wgrad(const void *g_bf16, const float *x, float *dwt, int R, int x_pitch, int Lin, int Cout,
                          int Cg, int Lout, int g_pitch, int K, int stride, int pad_l, void *stream);
+/* c1_dgrad: dx[r][t] = sum_k sum_co g[r][(t+pad-k)/stride][co] w[co][k]  (fp32 rows [R][x_pitch]);
+ * colsum : out[c] = sum_{r, l<L} g[r][l][c]  (bias gradient of a channel-last bf16 gradient stream). */
+int rave_conv1d_c1_dgrad(const void *g_bf16, const float *w, float *dx, int R, int x_pitch, int Lin, int Cout,
+                         int Cg, int Lout, int g_pitch, int K, int stride, int pad_l, void *stream);
+int rave_colsum_bf16(const void *g_bf16, float *out, int R, int L, int pitch, int Cg, int C, void *stream);
 int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, int pitch, int C, float slope, void *stream);
 int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_bf16, int Bh, int L, int pitch, int C,
                  float slope, void *stream);

@@ -38,13 +38,12 @@ conv_c1_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, con
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int chunks = Cout >> 3;
-  const long total = (long)R * Lout * chunks;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % chunks) * 8;
-    const long rl = i / chunks;
-    const int l = (int)(rl % Lout);
-    const int r = (int)(rl / Lout);
-    const float *xr = x + (size_t)r * x_pitch;
+  const int r = blockIdx.y;                         // one batch row per grid.y
+  const float *xr = x + (size_t)r * x_pitch;
+  const int per_row = Lout * chunks;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+    const int l = i / chunks;
+    const int c8 = (i - l * chunks) * 8;
     const int base = l * stride - pad_l;
     float acc[8];
 #pragma unroll
@@ -83,45 +82,155 @@ conv_c1_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, con
 // ---------------------------------------------------------------------------------------------
 constexpr int C1_MAXK = 16;
 
+// grid (slices_per_row, R): each CTA reduces a contiguous slice of positions of ONE batch row.
+// thread = 2 adjacent channels x one of NL position lanes, 4 positions in flight per thread.
 __global__ void __launch_bounds__(256)
 conv_c1_wgrad_kernel(const __nv_bfloat16 *__restrict__ g, const float *__restrict__ x, float *__restrict__ dwt,
                      int R, int x_pitch, int Lin, int Cout, int Cg, int Lout, int g_pitch, int K, int stride,
                      int pad_l, int NL) {
   extern __shared__ float red[];   // [NL][K][Cout]
-  const int co = threadIdx.x % Cout;
-  const int lane = threadIdx.x / Cout;
-  float acc[C1_MAXK];
+  const int half = Cout >> 1;
+  const int c2 = (threadIdx.x % half) * 2;
+  const int lane = threadIdx.x / half;
+  const int r = blockIdx.y;
+  float acc0[C1_MAXK], acc1[C1_MAXK];
 #pragma unroll
-  for (int k = 0; k < C1_MAXK; ++k) acc[k] = 0.f;
-  const long total = (long)R * Lout;
-  const long per = (total + gridDim.x - 1) / gridDim.x;
-  const long begin = (long)blockIdx.x * per;
-  const long end = min(total, begin + per);
+  for (int k = 0; k < C1_MAXK; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+  const int per = (Lout + gridDim.x - 1) / gridDim.x;
+  const int begin = blockIdx.x * per;
+  const int end = min(Lout, begin + per);
+  const float *xr = x + (size_t)r * x_pitch;
+  const __nv_bfloat16 *gr = g + (size_t)r * g_pitch * Cg + c2;
   if (lane < NL) {
-    for (long i = begin + lane; i < end; i += NL) {
-      const int l = (int)(i % Lout);
-      const int r = (int)(i / Lout);
-      const float gv = __bfloat162float(g[((size_t)r * g_pitch + l) * Cg + co]);
-      const float *xr = x + (size_t)r * x_pitch;
-      const int base = l * stride - pad_l;
+    for (int l0 = begin + lane; l0 < end; l0 += 4 * NL) {
+      uint32_t gw[4];
 #pragma unroll
-      for (int k = 0; k < C1_MAXK; ++k) {
-        if (k < K) {
-          const int pos = base + k;
-          const float xv = (pos >= 0 && pos < Lin) ? __ldg(xr + pos) : 0.f;
-          acc[k] = fmaf(gv, xv, acc[k]);
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + u * NL;
+        gw[u] = (l < end) ? *reinterpret_cast<const uint32_t *>(gr + (size_t)l * Cg) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + u * NL;
+        if (l >= end) break;
+        const float g0 = bf16_lo(gw[u]), g1 = bf16_hi(gw[u]);
+        const int base = l * stride - pad_l;
+#pragma unroll
+        for (int k = 0; k < C1_MAXK; ++k) {
+          if (k < K) {
+            const int pos = base + k;
+            const float xv = (pos >= 0 && pos < Lin) ? __ldg(xr + pos) : 0.f;
+            acc0[k] = fmaf(g0, xv, acc0[k]);
+            acc1[k] = fmaf(g1, xv, acc1[k]);
+          }
         }
       }
     }
 #pragma unroll
     for (int k = 0; k < C1_MAXK; ++k)
-      if (k < K) red[((size_t)lane * K + k) * Cout + co] = acc[k];
+      if (k < K) {
+        red[((size_t)lane * K + k) * Cout + c2] = acc0[k];
+        red[((size_t)lane * K + k) * Cout + c2 + 1] = acc1[k];
+      }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
     float s = 0.f;
     for (int ln = 0; ln < NL; ++ln) s += red[(size_t)ln * K * Cout + i];
-    dwt[(size_t)blockIdx.x * K * Cout + i] = s;    // [cta][k][co]  (== [split][K][C0p=Cout][C1p=1])
+    atomicAdd(dwt + i, s);                  // [k][co]  (== [1][K][C0p=Cout][C1p=1]), pre-zeroed
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// input gradient of the first conv:  dx[r][t] = sum_k sum_co g[r][(t + pad - k)/stride][co] w[co][k]
+// (terms with a non-integer / out-of-range row dropped).  One CTA = 256 consecutive samples of one
+// batch row: stage 1 computes P[l][k] = <g[r][l][:], w[:][k]> for the ~256/stride + K/stride rows that
+// touch the tile, stage 2 gathers.  g: bf16 channel-last [R][g_pitch][Cg].
+// ---------------------------------------------------------------------------------------------
+constexpr int C1_DG_TILE = 256;
+
+__global__ void __launch_bounds__(256)
+conv_c1_dgrad_kernel(const __nv_bfloat16 *__restrict__ g, const float *__restrict__ w, float *__restrict__ dx,
+                     int x_pitch, int Lin, int Cout, int Cg, int Lout, int g_pitch, int K, int stride, int pad_l) {
+  extern __shared__ float sm[];                 // w [K][Cout]  |  P [rows][K]
+  float *sw = sm;
+  float *P = sm + K * Cout;
+  const int r = blockIdx.y;
+  const int t0 = blockIdx.x * C1_DG_TILE;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int k = i / Cout, co = i - k * Cout;
+    sw[i] = w[co * K + k];
+  }
+  // rows l with l*stride + k - pad in [t0, t0 + TILE) for some k in [0, K)
+  int lmin = (t0 + pad_l - (K - 1) + stride - 1) / stride;
+  if (t0 + pad_l - (K - 1) < 0) lmin = 0;
+  int lmax = (t0 + C1_DG_TILE - 1 + pad_l) / stride;
+  if (lmax > Lout - 1) lmax = Lout - 1;
+  const int nrows = lmax - lmin + 1;
+  __syncthreads();
+  // stage 1: one warp per row, lanes over channel pairs, shuffle-reduce; K dot products per row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = warp; rr < nrows; rr += 8) {
+    const __nv_bfloat16 *gp = g + ((size_t)r * g_pitch + (lmin + rr)) * Cg;
+    float part[C1_MAXK];
+#pragma unroll
+    for (int k = 0; k < C1_MAXK; ++k) part[k] = 0.f;
+    for (int c2 = lane * 2; c2 < Cout; c2 += 64) {
+      const uint32_t gw = *reinterpret_cast<const uint32_t *>(gp + c2);
+      const float g0 = bf16_lo(gw), g1 = bf16_hi(gw);
+#pragma unroll
+      for (int k = 0; k < C1_MAXK; ++k)
+        if (k < K) part[k] = fmaf(g0, sw[k * Cout + c2], fmaf(g1, sw[k * Cout + c2 + 1], part[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < C1_MAXK; ++k) {
+      if (k < K) {
+        float v = part[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) P[rr * K + k] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // stage 2: gather
+  const int t = t0 + threadIdx.x;
+  if (t < Lin) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int q = t + pad_l - k;
+      if (q < 0) break;
+      const int l = q / stride;
+      if (l * stride == q && l >= lmin && l <= lmax) acc += P[(l - lmin) * K + k];
+    }
+    dx[(size_t)r * x_pitch + t] = acc;
+  }
+}
+
+// column sums of a bf16 channel-last tensor: out[c] = sum_{r, l < L} g[r][l][c]   (conv bias gradient)
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ g, float *__restrict__ out, int L, int pitch, int Cg, int C) {
+  // grid (slices, R); block 256 = 32 position lanes x 8 channel groups; each thread strides channels
+  __shared__ float red[8][33];
+  const int r = blockIdx.y;
+  const int per = (L + gridDim.x - 1) / gridDim.x;
+  const int begin = blockIdx.x * per, end = min(L, begin + per);
+  const int lane_l = threadIdx.x >> 5;      // 0..7 : position lane
+  const int lane_c = threadIdx.x & 31;      // channel lane
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane_c;
+    float s = 0.f;
+    if (c < C)
+      for (int l = begin + lane_l; l < end; l += 8) s += __bfloat162float(g[((size_t)r * pitch + l) * Cg + c]);
+    red[lane_l][lane_c] = s;
+    __syncthreads();
+    if (lane_l == 0 && c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][lane_c];
+      atomicAdd(out + c, t);
+    }
+    __syncthreads();
   }
 }
 
@@ -225,40 +334,81 @@ extern "C" int rave_conv1d_c1_fwd(const float *x, const float *w, const float *b
   RAVE_CHECK_ARG(R > 0 && Lin > 0 && Lout > 0 && Cout > 0 && Cout % 8 == 0 && K > 0 && stride > 0,
                  "conv1d_c1_fwd: bad shape (Cout must be a multiple of 8)");
   RAVE_CHECK_ARG(act == RAVE_ACT_NONE || act == RAVE_ACT_LEAKY, "conv1d_c1_fwd: unsupported activation");
-  const long total = (long)R * Lout * (Cout / 8);
-  long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  RAVE_CHECK_ARG(R <= 65535, "conv1d_c1_fwd: too many rows");
+  const int per_row = Lout * (Cout / 8);
+  int bx = (per_row + 255) / 256;
+  const int want = (148 * 16 + R - 1) / R;       // ~16 CTAs per SM in total
+  if (bx > want) bx = want;
+  if (bx < 1) bx = 1;
   const size_t smem = (size_t)(K + 1) * Cout * sizeof(float);
-  conv_c1_fwd_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(
+  conv_c1_fwd_kernel<<<dim3(bx, R), 256, smem, (cudaStream_t)stream>>>(
       x, w, bias, out_f32, (__nv_bfloat16 *)out_act_bf16, R, x_pitch, Lin, Cout, Lout, out_pitch, K, stride, pad_l,
       act, slope);
   RAVE_CHECK_LAUNCH("conv1d_c1_fwd");
   return 0;
 }
 
-extern "C" int rave_conv1d_c1_wgrad_splits(int R, int Lout) {
-  const long total = (long)R * Lout;
-  long s = total / 256;
-  if (s > 148 * 4) s = 148 * 4;
-  if (s < 1) s = 1;
-  return (int)s;
+static int c1_wgrad_slices(int R, int Lout) {
+  int sl = (148 * 8 + R - 1) / R;                 // ~8 CTAs per SM in total
+  const int max_sl = (Lout + 63) / 64;            // at least 64 positions per slice
+  if (sl > max_sl) sl = max_sl;
+  if (sl < 1) sl = 1;
+  return sl;
 }
+
+extern "C" int rave_conv1d_c1_wgrad_splits(int R, int Lout) { return 1; }
 
 extern "C" int rave_conv1d_c1_wgrad(const void *g_bf16, const float *x, float *dwt, int R, int x_pitch, int Lin,
                                     int Cout, int Cg, int Lout, int g_pitch, int K, int stride, int pad_l,
                                     void *stream) {
   using namespace rave;
   RAVE_CHECK_ARG(g_bf16 && x && dwt, "conv1d_c1_wgrad: null pointer");
-  RAVE_CHECK_ARG(K > 0 && K <= C1_MAXK && Cout > 0 && Cout <= 256 && Cg >= Cout, "conv1d_c1_wgrad: bad shape");
-  const int splits = rave_conv1d_c1_wgrad_splits(R, Lout);
-  int NL = 256 / Cout;
+  RAVE_CHECK_ARG(K > 0 && K <= C1_MAXK && Cout > 0 && Cout <= 512 && Cout % 2 == 0 && Cg >= Cout && Cg % 2 == 0,
+                 "conv1d_c1_wgrad: bad shape");
+  RAVE_CHECK_ARG(R <= 65535, "conv1d_c1_wgrad: too many rows");
+  const int slices = c1_wgrad_slices(R, Lout);
+  const int half = Cout / 2;
+  int NL = 256 / half;
   if (NL < 1) NL = 1;
-  const int threads = Cout * NL;
+  const int threads = half * NL;
   const size_t smem = (size_t)NL * K * Cout * sizeof(float);
   RAVE_CHECK_ARG(smem <= 48 * 1024, "conv1d_c1_wgrad: reduction buffer too large");
-  conv_c1_wgrad_kernel<<<splits, threads, smem, (cudaStream_t)stream>>>(
+  cudaMemsetAsync(dwt, 0, sizeof(float) * K * Cout, (cudaStream_t)stream);
+  conv_c1_wgrad_kernel<<<dim3(slices, R), threads, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16 *)g_bf16, x, dwt, R, x_pitch, Lin, Cout, Cg, Lout, g_pitch, K, stride, pad_l, NL);
   RAVE_CHECK_LAUNCH("conv1d_c1_wgrad");
+  return 0;
+}
+
+extern "C" int rave_conv1d_c1_dgrad(const void *g_bf16, const float *w, float *dx, int R, int x_pitch, int Lin,
+                                    int Cout, int Cg, int Lout, int g_pitch, int K, int stride, int pad_l,
+                                    void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(g_bf16 && w && dx, "conv1d_c1_dgrad: null pointer");
+  RAVE_CHECK_ARG(K > 0 && K <= C1_MAXK && Cout > 0 && Cout % 2 == 0 && Cg >= Cout && Cg % 2 == 0 && R <= 65535,
+                 "conv1d_c1_dgrad: bad shape");
+  const int max_rows = C1_DG_TILE / stride + (K - 1) / stride + 3;
+  const size_t smem = ((size_t)K * Cout + (size_t)max_rows * K) * sizeof(float);
+  RAVE_CHECK_ARG(smem <= 48 * 1024, "conv1d_c1_dgrad: shared memory");
+  dim3 grid(ceil_div(Lin, C1_DG_TILE), R);
+  conv_c1_dgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)g_bf16, w, dx, x_pitch, Lin,
+                                                                 Cout, Cg, Lout, g_pitch, K, stride, pad_l);
+  RAVE_CHECK_LAUNCH("conv1d_c1_dgrad");
+  return 0;
+}
+
+extern "C" int rave_colsum_bf16(const void *g_bf16, float *out, int R, int L, int pitch, int Cg, int C,
+                                void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(g_bf16 && out && R > 0 && R <= 65535 && L > 0 && pitch >= L && C > 0 && Cg >= C,
+                 "colsum_bf16: bad argument");
+  cudaMemsetAsync(out, 0, sizeof(float) * C, (cudaStream_t)stream);
+  int sl = (148 * 8 + R - 1) / R;
+  const int max_sl = (L + 63) / 64;
+  if (sl > max_sl) sl = max_sl;
+  if (sl < 1) sl = 1;
+  colsum_bf16_kernel<<<dim3(sl, R), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)g_bf16, out, L, pitch, Cg, C);
+  RAVE_CHECK_LAUNCH("colsum_bf16");
   return 0;
 }
 

@@ -415,8 +415,10 @@ weight_norm_bwd_tapmajor_kernel(const float *__restrict__ dwt, const float *__re
   float *dr = dv + (size_t)c0 * R;
   const size_t split_stride = (size_t)K * C0p * C1p;
   float s = 0.f;
-  for (int i = threadIdx.x; i < R; i += blockDim.x) {
-    const int c1 = i / K, k = i - c1 * K;
+  // iterate (k, c1) with c1 fastest: consecutive threads read consecutive addresses of every partial
+  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+    const int k = j / C1, c1 = j - k * C1;
+    const int i = c1 * K + k;                       // index inside the parameter row
     const float *src = dwt + ((size_t)k * C0p + c0) * C1p + c1;
     float dw = 0.f;
     for (int sp = 0; sp < splits; ++sp) dw += src[sp * split_stride];

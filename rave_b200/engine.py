@@ -290,8 +290,8 @@ class TcChainFn(torch.autograd.Function):
         for i, s in enumerate(specs):
             v, g, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
             use_c1 = c1 and i == 0
-            pw = _PreparedWeights(s, v.detach(), g.detach() if g is not None else None, need_dgrad,
-                                  need_fwd=not use_c1)
+            pw = _PreparedWeights(s, v.detach(), g.detach() if g is not None else None,
+                                  need_dgrad and not use_c1, need_fwd=not use_c1)
             prepared.append(pw)
             Lin = lens[-1]
             Lout = _out_len(s, Lin)
@@ -318,6 +318,7 @@ class TcChainFn(torch.autograd.Function):
             acts.append(a)
             if use_c1:
                 w_eff = ops.weight_norm_raw(v.detach(), g.detach())[0] if g is not None else v.detach()
+                ctx.w_eff0 = w_eff
                 ops.conv1d_c1(a, w_eff, bias, Lin, s.stride, s.pad, act_code, act_slope, out_f32=out_f32,
                               out_act=out_act, Lout=Lout)
             elif s.kind == "conv":
@@ -405,7 +406,7 @@ class TcChainFn(torch.autograd.Function):
                 dv, dg = ops.weight_norm_bwd_tapmajor(dwt, v, gpar, pw.norm)
                 grads[3 * i], grads[3 * i + 1] = dv, dg
             if bias is not None and bias.requires_grad:
-                grads[3 * i + 2] = g[:, :Lout, :s.Cout].float().sum((0, 1))
+                grads[3 * i + 2] = ops.colsum_bf16(g, Lout, s.Cout)
             # ---- input gradient
             need_prev = i > 0 or ctx.x_requires_grad
             if not need_prev:
@@ -421,6 +422,9 @@ class TcChainFn(torch.autograd.Function):
                 add = e if add is None else (add + e)
             dact = a_in if s.pre_act == ops.ACT_LEAKY else None
             in_pitch = a_in.shape[1]
+            if use_c1:                  # small-channel input gradient straight to the fp32 rows
+                gx = ops.conv1d_c1_dgrad(g, ctx.w_eff0, in_pitch, Lin, Lout, s.stride, s.pad[0])
+                break
             gp = torch.empty(B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)
             if in_pitch > Lin:
                 gp[:, Lin:].zero_()
@@ -447,7 +451,7 @@ class TcChainFn(torch.autograd.Function):
                               res_bf16=add, dact_src=dact)
             g_cur = gp
             if i == 0:
-                gx = gp[..., 0].float() if ctx.c1 else gp
+                gx = gp
         return (gx, None, None, None) + tuple(grads)
 
 

@@ -12,6 +12,8 @@ from typing import Dict, Optional
 
 import torch
 
+from . import _lib
+
 
 class GraphedTrainer:
     def __init__(self, model, example_batch: torch.Tensor, grad_hook=None, warmup_steps: int = 3):
@@ -25,6 +27,7 @@ class GraphedTrainer:
             raise RuntimeError("capture phase-2 steps (model.warmed_up = True); phase 1 has no D-step")
         self.graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self.outputs: Dict[bool, Dict[str, torch.Tensor]] = {}
+        self.launches: Dict[bool, int] = {}      # library kernel launches recorded in each graph
         # eager warm-up on a side stream: lazy state (Adam moments, cuFFT plans, PQMF tables, kernel
         # attributes, tensor-map entry point) must exist before capture
         side = torch.cuda.Stream()
@@ -38,10 +41,13 @@ class GraphedTrainer:
         pool = None
         for is_dis in (True, False):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            n0 = _lib.launch_count()
+            # thread_local: other threads (NCCL watchdog, samplers) may touch CUDA while we capture
+            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                 logs = model.train_body(self.x_static, is_dis, None, grad_hook)
                 out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in logs.items()}
             pool = g.pool()
+            self.launches[is_dis] = _lib.launch_count() - n0
             self.graphs[is_dis] = g
             self.outputs[is_dis] = out
 

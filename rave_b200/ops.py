@@ -507,3 +507,26 @@ def weight_norm_raw(v, g):
     norm = torch.empty(C0, dtype=torch.float32, device=v.device)
     call("rave_weight_norm_fwd", ptr(v), ptr(g), ptr(w), ptr(norm), C0, v.numel() // C0, stream_ptr())
     return w, norm
+
+
+def conv1d_c1_dgrad(g_cl, w, x_pitch, Lin, Lout, stride, pad_l):
+    """dx rows [R, x_pitch] fp32 of the Cin = 1 first conv (w: effective weight [Cout, 1, K(,1)])."""
+    R, g_pitch, Cg = g_cl.shape
+    w = _f32c(w)
+    Cout = w.shape[0]
+    K = w.numel() // Cout
+    dx = torch.zeros(R, x_pitch, dtype=torch.float32, device=g_cl.device) if x_pitch > Lin else \
+        torch.empty(R, x_pitch, dtype=torch.float32, device=g_cl.device)
+    call("rave_conv1d_c1_dgrad", ptr(g_cl), ptr(w), ptr(dx), R, x_pitch, Lin, Cout, Cg, Lout, g_pitch, K, stride,
+         pad_l, stream_ptr())
+    return dx
+
+
+def colsum_bf16(g_cl, L, C):
+    """sum over batch and the first L rows of a channel-last gradient stream -> [C] fp32 (bias gradient)."""
+    R, pitch, Cg = g_cl.shape
+    if g_cl.dtype != torch.bfloat16:
+        return g_cl[:, :L, :C].float().sum((0, 1))
+    out = torch.empty(C, dtype=torch.float32, device=g_cl.device)
+    call("rave_colsum_bf16", ptr(g_cl), ptr(out), R, L, pitch, Cg, C, stream_ptr())
+    return out

@@ -162,6 +162,22 @@ def conv1d_c1_wgrad(g_cl, x_rows, Cout, K, Lin, Lout, stride, pad_l):
     return dwt
 
 
+def conv1d_c1_dgrad(g_cl, w, x_pitch, Lin, Lout, stride, pad_l):
+    R = g_cl.shape[0]
+    Cout = w.shape[0]
+    K = w.numel() // Cout
+    g = g_cl[:, :Lout, :Cout].float().permute(0, 2, 1)               # [R, Cout, Lout]
+    full = F.conv_transpose1d(g, w.reshape(Cout, 1, K), None, stride)  # [R, 1, (Lout-1)*s + K]
+    dx = torch.zeros(R, x_pitch)
+    seg = full[:, 0, pad_l:pad_l + Lin]
+    dx[:, :seg.shape[1]] = seg
+    return dx
+
+
+def colsum_bf16(g_cl, L, C):
+    return g_cl[:, :L, :C].float().sum((0, 1))
+
+
 def _unleaky(a, slope):
     return torch.where(a > 0, a, a / slope)
 
@@ -187,5 +203,5 @@ def fm_grad(a_cl, dstats_row, L, slope):
 def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
-                 "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad"):
+                 "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -115,6 +115,12 @@ def test_small_channel_kernels_vs_emulator():
         dw_e = E.conv1d_c1_wgrad(g, x, Cout, K, L, Lout, stride, pad).sum(0)
         dw = ops.conv1d_c1_wgrad(g.cuda(), x.cuda(), Cout, K, L, Lout, stride, pad).sum(0)
         assert dw.shape == dw_e.shape and rel_l2(dw, dw_e) < 1e-4
+        we = torch.randn(Cout, 1, K) * 0.3
+        dx_e = E.conv1d_c1_dgrad(g, we, L + 3, L, Lout, stride, pad)
+        dx = ops.conv1d_c1_dgrad(g.cuda(), we.cuda(), L + 3, L, Lout, stride, pad)
+        assert dx.shape == dx_e.shape and rel_l2(dx, dx_e) < 1e-5
+        cs = ops.colsum_bf16(g.cuda(), Lout, Cout)
+        assert rel_l2(cs, E.colsum_bf16(g, Lout, Cout)) < 1e-5
     for (B2, L, pitch, C) in [(4, 100, 104, 96), (8, 17, 20, 192), (2, 5, 5, 16)]:
         a = torch.randn(B2, pitch, C).bfloat16()
         st_e = torch.zeros(2)
