@@ -180,6 +180,13 @@ int rave_conv1d_c1_wgrad(const void *g_bf16, const float *x, float *dwt, int R, 
 int rave_conv1d_c1_dgrad(const void *g_bf16, const float *w, float *dx, int R, int x_pitch, int Lin, int Cout,
                          int Cg, int Lout, int g_pitch, int K, int stride, int pad_l, void *stream);
 int rave_colsum_bf16(const void *g_bf16, float *out, int R, int L, int pitch, int Cg, int C, void *stream);
+/* Cin = 1 first layer on the tensor-core kernels: im2col of the K (<= 16) taps into 16 bf16 "channels"
+ *   X[r][l][k] = bf16(x[r][l*stride + k - pad_l])   (x fp32 rows [R][x_pitch]; X [R][out_pitch][16], zero elsewhere)
+ * and the scatter-free input gradient  dx[r][t] = sum_k P[r][(t+pad-k)/stride][k]  from P [R][p_pitch][16] fp32. */
+int rave_im2col_c1(const float *x, void *X_bf16, int R, int x_pitch, int Lin, int Lout, int out_pitch, int K,
+                   int stride, int pad_l, void *stream);
+int rave_gather_c1(const float *P, float *dx, int R, int x_pitch, int Lin, int Lout, int p_pitch, int K, int stride,
+                   int pad_l, void *stream);
 int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, int pitch, int C, float slope, void *stream);
 int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_bf16, int Bh, int L, int pitch, int C,
                  float slope, void *stream);

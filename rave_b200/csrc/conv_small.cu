@@ -441,3 +441,74 @@ extern "C" int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_
   RAVE_CHECK_LAUNCH("fm_grad");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Cin = 1 first layer on the tensor-core kernels: the K (<= 16) taps become 16 "channels" of a tiny
+// im2col, X[r][l][k] = bf16(x[r][l*stride + k - pad_l]) (33 MB for the 64 x 16384-row MSD input), so
+//   forward : conv_tc (Cin = 16, one tap)            out[r][l][co] = sum_k X[r][l][k] w[co][k]
+//   wgrad   : wgrad_tc (P = g, Q = X, one tap)       dw[co][k]     = sum_{r,l} g[r][l][co] X[r][l][k]
+//   dgrad   : conv_tc (Cin = Cout, Cout = 16) -> P[r][l][k] = <g[r][l][:], w[:][k]>, then the gather below
+//             dx[r][t] = sum_k P[r][(t + pad - k)/stride][k]
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+// grid (ceil(pitch/128), R), block 256: thread = (position, tap pair)
+__global__ void __launch_bounds__(256)
+im2col_c1_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ X, int x_pitch, int Lin, int Lout,
+                 int out_pitch, int K, int stride, int pad_l) {
+  const int r = blockIdx.y;
+  const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int k2 = (threadIdx.x & 7) * 2;
+  if (l >= out_pitch) return;
+  float v0 = 0.f, v1 = 0.f;
+  if (l < Lout) {
+    const float *xr = x + (size_t)r * x_pitch;
+    const int p0 = l * stride + k2 - pad_l, p1 = p0 + 1;
+    if (k2 < K && p0 >= 0 && p0 < Lin) v0 = __ldg(xr + p0);
+    if (k2 + 1 < K && p1 >= 0 && p1 < Lin) v1 = __ldg(xr + p1);
+  }
+  *reinterpret_cast<uint32_t *>(X + ((size_t)r * out_pitch + l) * 16 + k2) = pack_bf16(v0, v1);
+}
+
+// dx[r][t] = sum_k P[r][(t + pad - k)/stride][k]; P fp32 channel-last [R][p_pitch][16]
+__global__ void __launch_bounds__(256)
+gather_c1_kernel(const float *__restrict__ P, float *__restrict__ dx, int x_pitch, int Lin, int Lout, int p_pitch,
+                 int K, int stride, int pad_l) {
+  const int r = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= x_pitch) return;
+  float acc = 0.f;
+  if (t < Lin) {
+    const float *Pr = P + (size_t)r * p_pitch * 16;
+    for (int k = (t + pad_l) % stride; k < K; k += stride) {
+      const int q = t + pad_l - k;
+      if (q < 0) break;
+      const int l = q / stride;
+      if (l < Lout) acc += __ldg(Pr + (size_t)l * 16 + k);
+    }
+  }
+  dx[(size_t)r * x_pitch + t] = acc;
+}
+
+}  // namespace rave
+
+extern "C" int rave_im2col_c1(const float *x, void *X_bf16, int R, int x_pitch, int Lin, int Lout, int out_pitch,
+                              int K, int stride, int pad_l, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && X_bf16 && R > 0 && R <= 65535 && K > 0 && K <= 16 && out_pitch >= Lout, "im2col_c1: bad argument");
+  dim3 grid(ceil_div(out_pitch, 32), R);
+  im2col_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)X_bf16, x_pitch, Lin, Lout, out_pitch, K,
+                                                           stride, pad_l);
+  RAVE_CHECK_LAUNCH("im2col_c1");
+  return 0;
+}
+
+extern "C" int rave_gather_c1(const float *P, float *dx, int R, int x_pitch, int Lin, int Lout, int p_pitch, int K,
+                              int stride, int pad_l, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(P && dx && R > 0 && R <= 65535 && K > 0 && K <= 16 && p_pitch >= Lout, "gather_c1: bad argument");
+  dim3 grid(ceil_div(x_pitch, 256), R);
+  gather_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, dx, x_pitch, Lin, Lout, p_pitch, K, stride, pad_l);
+  RAVE_CHECK_LAUNCH("gather_c1");
+  return 0;
+}

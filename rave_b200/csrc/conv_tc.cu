@@ -14,6 +14,8 @@
 //
 // Replaces: cc.Conv1d.forward = F.pad + F.conv1d -> cuDNN (reference call sites rave/blocks.py:96-108,
 // 538-592, 637-692; rave/discriminator.py:99-111), the preceding activation module and the residual add.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -53,6 +55,79 @@ struct SmemLayout {
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
 };
+
+// Epilogue of one 128 x BLOCK_N accumulator tile: this thread owns TMEM lane `taddr.lane` = one output row.
+template <int BLOCK_N>
+__device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t taddr, int n0, bool valid, size_t orow) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        float v[16];
+        tmem_ld_32x16(taddr + c0, v);   // warp-collective: every lane participates, valid or not
+        if (valid) {
+          const int co = n0 + c0;
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co + i);
+          }
+          if (p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand
+            const uint4 *d4 = reinterpret_cast<const uint4 *>(p.dact_src + orow * p.Cout + co);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint4 d = __ldg(d4 + i);
+              const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // bf16 sign bits: element 2j in the low half, 2j+1 in the high half
+                if (w[j] & 0x00008000u) v[8 * i + 2 * j] *= p.slope;
+                if (w[j] & 0x80000000u) v[8 * i + 2 * j + 1] *= p.slope;
+              }
+            }
+          }
+          if (p.res_bf16) {
+            const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_bf16 + orow * p.Cout + co);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint4 d = __ldg(r4 + i);
+              const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
+                v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+              }
+            }
+          }
+          if (p.res) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(p.res + orow * p.Cout + co);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 r = __ldg(r4 + i);
+              v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+            }
+          }
+          if (p.out_f32) {
+            float4 *o4 = reinterpret_cast<float4 *>(p.out_f32 + orow * p.Cout + co);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (p.out_act) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a0 = v[2 * i], a1 = v[2 * i + 1];
+              if (p.act == RAVE_ACT_LEAKY) {
+                a0 = a0 > 0.f ? a0 : a0 * p.slope;
+                a1 = a1 > 0.f ? a1 : a1 * p.slope;
+              }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+              pk[i] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(p.out_act + orow * p.Cout + co);
+            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+}
 
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -183,74 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        float v[16];
-        tmem_ld_32x16(taddr + c0, v);   // warp-collective: every lane participates, valid or not
-        if (valid) {
-          const int co = n0 + c0;
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co + i);
-          }
-          if (p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand
-            const uint4 *d4 = reinterpret_cast<const uint4 *>(p.dact_src + orow * p.Cout + co);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint4 d = __ldg(d4 + i);
-              const uint32_t w[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // bf16 sign bits: element 2j in the low half, 2j+1 in the high half
-                if (w[j] & 0x00008000u) v[8 * i + 2 * j] *= p.slope;
-                if (w[j] & 0x80000000u) v[8 * i + 2 * j + 1] *= p.slope;
-              }
-            }
-          }
-          if (p.res_bf16) {
-            const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_bf16 + orow * p.Cout + co);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint4 d = __ldg(r4 + i);
-              const uint32_t w[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
-                v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-              }
-            }
-          }
-          if (p.res) {
-            const float4 *r4 = reinterpret_cast<const float4 *>(p.res + orow * p.Cout + co);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 r = __ldg(r4 + i);
-              v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-            }
-          }
-          if (p.out_f32) {
-            float4 *o4 = reinterpret_cast<float4 *>(p.out_f32 + orow * p.Cout + co);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          if (p.out_act) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a0 = v[2 * i], a1 = v[2 * i + 1];
-              if (p.act == RAVE_ACT_LEAKY) {
-                a0 = a0 > 0.f ? a0 : a0 * p.slope;
-                a1 = a1 > 0.f ? a1 : a1 * p.slope;
-              }
-              __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-              pk[i] = *reinterpret_cast<uint32_t *>(&h);
-            }
-            uint4 *o = reinterpret_cast<uint4 *>(p.out_act + orow * p.Cout + co);
-            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-        }
-      }
+      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -262,6 +270,180 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// =============================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): two SMs of one TPC compute a 256 x BLOCK_N tile.
+// Each CTA loads ITS 128 activation rows and HALF of the weight tile (BLOCK_N/2 rows) -- the pair's
+// tensor cores read both halves, so per-SM shared-memory fill drops from (16 + 32) KB to (16 + 16) KB
+// per k-block at BLOCK_N = 256, which is what lifts the single-CTA ~52 % tensor-pipe ceiling
+// (profiles/r1_ncu_conv_tc_msd384_768.md).  Leader CTA (cluster rank 0) issues every MMA and owns the
+// `full` and `tmem-empty` barriers; `empty` / `tmem-full` barriers are replicated and signalled with a
+// multicast tcgen05.commit.
+// =============================================================================================
+template <int BLOCK_N, int BLOCK_K>
+struct SmemLayout2 {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;          // this CTA's half of the weight tile
+  static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
+  static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const TcParams p) {
+  using L = SmemLayout2<BLOCK_N, BLOCK_K>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int SWZ = BLOCK_K * 2;
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
+                                 : (ACC_STAGES * BLOCK_N <= 128) ? 128 : (ACC_STAGES * BLOCK_N <= 256) ? 256 : 512;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "cta_group::2 needs N % 32 == 0 (16 rows of B per CTA granule)");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tfull_bar = empty_bar + STAGES;
+  uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int n_mt = p.n_lt * p.n_bg;
+  const int n_mp = (n_mt + 1) >> 1;                  // M tile pairs
+  const int num_tiles = n_mp * p.n_nt;
+  const int kblocks = p.K * p.num_kb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);        // leader's: its own arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);      // leader's: 4 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================== TMA producer (both CTAs) ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int nt = tile % p.n_nt;
+        const int mt = (tile / p.n_nt) * 2 + (int)rank;      // this CTA's M tile (may be >= n_mt: zero-filled)
+        const int lt = mt % p.n_lt;
+        const int bg = mt / p.n_lt;
+        const int l0 = lt * p.BL;
+        const int b0 = bg * p.BB;
+        const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int k = 0; k < p.K; ++k) {
+          const int off = k * p.dil - p.pad_l;
+          int j = off / p.stride;
+          int ph = off - j * p.stride;
+          if (ph < 0) { ph += p.stride; j -= 1; }
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t *sa = smem + stage * L::STAGE_BYTES;
+            uint8_t *sb = sa + L::A_BYTES;
+            tma_load_4d_2sm(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
+            tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (L::A_BYTES + L::B_BYTES));
+            else mbar_arrive_remote(&full_bar[stage], 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // =========================== MMA issuer (leader only) ===========================
+    constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t adesc = make_kmajor_desc(sa, SWZ);
+          const uint64_t bdesc = make_kmajor_desc(sb, SWZ);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / 16; ++kk)
+            umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (kb == kblocks - 1) umma_commit_2sm(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    // the peer's last arrivals must land before this CTA's barriers disappear
+    if (it > 0 && lane == 0) {
+      const int last = it - 1;
+      mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    // =========================== epilogue (4 warps in each CTA) ===========================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = tile % p.n_nt;
+      const int mt = (tile / p.n_nt) * 2 + (int)rank;
+      const int lt = mt % p.n_lt;
+      const int bg = mt / p.n_lt;
+      const int n0 = nt * BLOCK_N;
+      const int b = bg * p.BB + row / p.BL;
+      const int l = lt * p.BL + row % p.BL;
+      const bool valid = (mt < n_mt) && (b < p.B) && (l < p.Lout);
+      const size_t orow = (size_t)b * p.out_rows + (size_t)l * p.out_row_stride + p.out_row_offset;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
@@ -335,6 +517,44 @@ static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &
   return 0;
 }
 
+template <int BN, int BK>
+static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t stream) {
+  using L = SmemLayout2<BN, BK>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("conv1d_tc(2cta): cudaFuncSetAttribute(%d bytes): %s", L::TOTAL, cudaGetErrorString(e));
+      return 2;
+    }
+    attr = true;
+  }
+  const int n_mp = (p.n_lt * p.n_bg + 1) / 2;
+  const int tiles = n_mp * p.n_nt;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  conv_tc2_kernel<BN, BK><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  RAVE_CHECK_LAUNCH("conv1d_tc(2cta)");
+  return 0;
+}
+
+template <int BK>
+static int dispatch_n2(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t s) {
+  switch (bn) {
+    case 256: return launch2<256, BK>(ta, tb, p, s);
+    case 192: return launch2<192, BK>(ta, tb, p, s);
+    case 128: return launch2<128, BK>(ta, tb, p, s);
+    case 96: return launch2<96, BK>(ta, tb, p, s);
+    case 64: return launch2<64, BK>(ta, tb, p, s);
+  }
+  set_error("conv1d_tc(2cta): no kernel for BLOCK_N=%d", bn);
+  return 1;
+}
+
 template <int BK>
 static int dispatch_n(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
                       cudaStream_t s) {
@@ -399,6 +619,14 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   RAVE_CHECK_ARG(BN > 0, "conv1d_tc: no BLOCK_N for Cout=%d", Cout);
   p.n_nt = Cout / BN;
   p.num_kb = ceil_div(Cin, BK);
+  // CTA pairs (cta_group::2): opt-in via RAVE_TC_2CTA=1 until it replaces the single-CTA path; needs
+  // N % 32 == 0, a K-block of 64 (the tested configuration) and at least two M tiles
+  static int want2 = -1;
+  if (want2 < 0) {
+    const char *e = getenv("RAVE_TC_2CTA");
+    want2 = (e && e[0] == '1') ? 1 : 0;
+  }
+  const bool use2 = want2 && BK == 64 && (BN % 32 == 0) && BN >= 64 && (long)p.n_lt * p.n_bg >= 2;
 
   // A: channel-last activations viewed as (c, phase, l/stride, b)
   CUtensorMap ta, tb;
@@ -415,7 +643,7 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   {
     cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)K * Cout};
     cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(use2 ? BN / 2 : BN)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(wt), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(BK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -423,6 +651,7 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map B encode failed (%d)", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (use2) return dispatch_n2<64>(BN, ta, tb, p, s);
   switch (BK) {
     case 64: return dispatch_n<64>(BN, ta, tb, p, s);
     case 32: return dispatch_n<32>(BN, ta, tb, p, s);

@@ -317,10 +317,15 @@ class TcChainFn(torch.autograd.Function):
                         t[:, Lout:].zero_()
             acts.append(a)
             if use_c1:
+                # Cin = 1: the K taps become the 16 "channels" of a tiny im2col, then one tcgen05 launch
                 w_eff = ops.weight_norm_raw(v.detach(), g.detach())[0] if g is not None else v.detach()
-                ctx.w_eff0 = w_eff
-                ops.conv1d_c1(a, w_eff, bias, Lin, s.stride, s.pad, act_code, act_slope, out_f32=out_f32,
-                              out_act=out_act, Lout=Lout)
+                w_ck = nn.functional.pad(w_eff.reshape(s.Cout, s.K), (0, 16 - s.K, 0, s.cout_pad))   # [Cout_p, 16]
+                ctx.c1_wt_dgrad = w_ck.t().contiguous().to(ACT_DTYPE).unsqueeze(0)                  # [1][16][Cout_p]
+                X = ops.im2col_c1(a, Lin, Lout, Lout, s.K, s.stride, s.pad[0])
+                ctx.c1_X = X
+                ops.conv1d_tc(X, w_ck.to(ACT_DTYPE).unsqueeze(0).contiguous(), bias_p, None, 1, 1, (0, 0), act_code,
+                              act_slope, want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act,
+                              Lout=Lout, Lin=Lout, out_rows=pitch)
             elif s.kind == "conv":
                 ops.conv1d_tc(a, pw.fwd, bias_p, res, s.stride, s.dil, s.pad, act_code, act_slope,
                               want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act, Lout=Lout,
@@ -397,7 +402,9 @@ class TcChainFn(torch.autograd.Function):
             # ---- weight gradient
             if v.requires_grad:
                 if use_c1:
-                    dwt = ops.conv1d_c1_wgrad(g, a_in, s.Cout, s.K, Lin, Lout, s.stride, s.pad[0])
+                    d = ops.conv1d_tc_wgrad(g, ctx.c1_X, 1, 1, 1, 0, Lp=Lout, Lq=Lout)       # [S][1][Cout_p][16]
+                    dw_ck = d.sum(0)[0][:s.Cout, :s.K]                                         # [Cout][K]
+                    dwt = dw_ck.t().reshape(1, s.K, s.Cout, 1).contiguous()                    # [1][K][C0][C1=1]
                 elif s.kind == "conv":
                     dwt = ops.conv1d_tc_wgrad(g, a_in, s.K, s.stride, s.dil, s.pad[0], Lp=Lout, Lq=Lin)
                 else:
@@ -422,8 +429,10 @@ class TcChainFn(torch.autograd.Function):
                 add = e if add is None else (add + e)
             dact = a_in if s.pre_act == ops.ACT_LEAKY else None
             in_pitch = a_in.shape[1]
-            if use_c1:                  # small-channel input gradient straight to the fp32 rows
-                gx = ops.conv1d_c1_dgrad(g, ctx.w_eff0, in_pitch, Lin, Lout, s.stride, s.pad[0])
+            if use_c1:                  # P[r][l][k] = <g[r][l][:], w[:][k]> on the tensor cores, then a gather
+                P, _ = ops.conv1d_tc(g, ctx.c1_wt_dgrad, None, None, 1, 1, (0, 0), ops.ACT_NONE, 0.0, want_f32=True,
+                                     want_act=False, Lout=Lout, Lin=Lout)
+                gx = ops.gather_c1(P, in_pitch, Lin, Lout, s.K, s.stride, s.pad[0])
                 break
             gp = torch.empty(B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)
             if in_pitch > Lin:

@@ -530,3 +530,21 @@ def colsum_bf16(g_cl, L, C):
     out = torch.empty(C, dtype=torch.float32, device=g_cl.device)
     call("rave_colsum_bf16", ptr(g_cl), ptr(out), R, L, pitch, Cg, C, stream_ptr())
     return out
+
+
+def im2col_c1(x_rows, Lin, Lout, out_pitch, K, stride, pad_l):
+    """X [R, out_pitch, 16] bf16 with X[r,l,k] = x[r, l*stride + k - pad_l] (zero outside / beyond K, Lout)."""
+    x_rows = _f32c(x_rows)
+    R, x_pitch = x_rows.shape
+    X = torch.empty(R, out_pitch, 16, dtype=torch.bfloat16, device=x_rows.device)
+    call("rave_im2col_c1", ptr(x_rows), ptr(X), R, x_pitch, Lin, Lout, out_pitch, K, stride, pad_l, stream_ptr())
+    return X
+
+
+def gather_c1(P_cl, x_pitch, Lin, Lout, K, stride, pad_l):
+    """dx [R, x_pitch] fp32 = sum_k P[r, (t+pad-k)/stride, k] from P [R, p_pitch, 16] fp32."""
+    P_cl = _f32c(P_cl)
+    R, p_pitch, _ = P_cl.shape
+    dx = torch.empty(R, x_pitch, dtype=torch.float32, device=P_cl.device)
+    call("rave_gather_c1", ptr(P_cl), ptr(dx), R, x_pitch, Lin, Lout, p_pitch, K, stride, pad_l, stream_ptr())
+    return dx

@@ -178,6 +178,28 @@ def colsum_bf16(g_cl, L, C):
     return g_cl[:, :L, :C].float().sum((0, 1))
 
 
+def im2col_c1(x_rows, Lin, Lout, out_pitch, K, stride, pad_l):
+    R = x_rows.shape[0]
+    X = torch.zeros(R, out_pitch, 16)
+    l = torch.arange(Lout)
+    for k in range(K):
+        pos = l * stride + k - pad_l
+        ok = (pos >= 0) & (pos < Lin)
+        X[:, l[ok], k] = x_rows[:, pos[ok]]
+    return _bf16(X)
+
+
+def gather_c1(P_cl, x_pitch, Lin, Lout, K, stride, pad_l):
+    R = P_cl.shape[0]
+    dx = torch.zeros(R, x_pitch)
+    t = torch.arange(Lin)
+    for k in range(K):
+        q = t + pad_l - k
+        ok = (q >= 0) & (q % stride == 0) & (q // stride < Lout)
+        dx[:, t[ok]] += P_cl[:, (q[ok] // stride), k]
+    return dx
+
+
 def _unleaky(a, slope):
     return torch.where(a > 0, a, a / slope)
 
@@ -203,5 +225,5 @@ def fm_grad(a_cl, dstats_row, L, slope):
 def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
-                 "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16"):
+                 "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1"):
         monkeypatch.setattr(ops, name, globals()[name])

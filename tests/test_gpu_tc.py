@@ -119,6 +119,11 @@ def test_small_channel_kernels_vs_emulator():
         dx_e = E.conv1d_c1_dgrad(g, we, L + 3, L, Lout, stride, pad)
         dx = ops.conv1d_c1_dgrad(g.cuda(), we.cuda(), L + 3, L, Lout, stride, pad)
         assert dx.shape == dx_e.shape and rel_l2(dx, dx_e) < 1e-5
+        X_e = E.im2col_c1(x, L, Lout, pitch, K, stride, pad)
+        X = ops.im2col_c1(x.cuda(), L, Lout, pitch, K, stride, pad)
+        assert torch.equal(X.float().cpu(), X_e.float())
+        Pm = torch.randn(R, pitch, 16)
+        assert rel_l2(ops.gather_c1(Pm.cuda(), L + 3, L, Lout, K, stride, pad), E.gather_c1(Pm, L + 3, L, Lout, K, stride, pad)) < 1e-6
         cs = ops.colsum_bf16(g.cuda(), Lout, Cout)
         assert rel_l2(cs, E.colsum_bf16(g, Lout, Cout)) < 1e-5
     for (B2, L, pitch, C) in [(4, 100, 104, 96), (8, 17, 20, 192), (2, 5, 5, 16)]:
@@ -132,3 +137,14 @@ def test_small_channel_kernels_vs_emulator():
         g_e = E.fm_grad(a, d, L, 0.2)
         g = ops.fm_grad(a.cuda(), d.cuda(), L, 0.2)
         assert torch.equal(g.float().cpu(), g_e.float())
+
+
+def test_conv1d_tc_cta_pair_variant():
+    """cta_group::2 (CTA-pair) variant of the conv kernel, enabled by RAVE_TC_2CTA=1 (read once per
+    process, hence the subprocess)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RAVE_TC_2CTA="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_2cta.py")], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "2CTA OK" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
