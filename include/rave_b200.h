@@ -191,6 +191,16 @@ int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, int pitch, in
 int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_bf16, int Bh, int L, int pitch, int C,
                  float slope, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * fused spectral distance (replaces the elementwise tail of core.AudioDistanceV1, rave/core.py:322-344,
+ * and mean_difference, 236-252, for one STFT scale).  X, Y: complex64 spectrograms (interleaved re/im), n
+ * complex elements.  stats (pre-zeroed) += { sum(|X|-|Y|)^2, sum|X|^2, sum|log(|X|+eps)-log(|Y|+eps)| }.
+ * grad: dY = (coef[0]*-2(|X|-|Y|) - coef[1]*sgn(logX-logY)/(|Y|+eps)) * Y/|Y|, coef = 2 device floats.
+ * ------------------------------------------------------------------------------------------- */
+int rave_spectral_stats(const void *X_c64, const void *Y_c64, float *stats, long n, float eps, void *stream);
+int rave_spectral_grad(const void *X_c64, const void *Y_c64, void *dY_c64, const float *coef, long n, float eps,
+                       void *stream);
+
 /* fused weight preparation for the engine: v [C0][C1][K] fp32 (+ weight-norm g [C0]; norm [C0] is written)
  *   outA[t][c0][c1] = bf16(w[c0][c1][tapsA[t]]), dims [nA][C0p][C1p]  (padded region zero)
  *   outB[t][c1][c0] = bf16(w[c0][c1][tapsB[t]]), dims [nB][C1p][C0p]

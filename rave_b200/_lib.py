@@ -50,6 +50,8 @@ SIGNATURES = {
     "rave_gather_c1": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rave_fm_stats": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P]),
     "rave_fm_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "rave_spectral_stats": (c_int, [_P, _P, _P, _L, _F, _P]),
+    "rave_spectral_grad": (c_int, [_P, _P, _P, _P, _L, _F, _P]),
     "rave_ncl_to_cl": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "rave_cl_to_ncl": (c_int, [_P, _P, _I, _I, _I, _P]),
     "rave_act_to_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P]),

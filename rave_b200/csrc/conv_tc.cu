@@ -619,12 +619,12 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   RAVE_CHECK_ARG(BN > 0, "conv1d_tc: no BLOCK_N for Cout=%d", Cout);
   p.n_nt = Cout / BN;
   p.num_kb = ceil_div(Cin, BK);
-  // CTA pairs (cta_group::2): opt-in via RAVE_TC_2CTA=1 until it replaces the single-CTA path; needs
-  // N % 32 == 0, a K-block of 64 (the tested configuration) and at least two M tiles
+  // CTA pairs (cta_group::2, validated on B200: scripts/check_2cta.py): default on, RAVE_TC_2CTA=0 disables.
+  // Needs N % 32 == 0, a K-block of 64 (the tested configuration) and at least two M tiles.
   static int want2 = -1;
   if (want2 < 0) {
     const char *e = getenv("RAVE_TC_2CTA");
-    want2 = (e && e[0] == '1') ? 1 : 0;
+    want2 = (e && e[0] == '0') ? 0 : 1;
   }
   const bool use2 = want2 && BK == 64 && (BN % 32 == 0) && BN >= 64 && (long)p.n_lt * p.n_bg >= 2;
 

@@ -1,0 +1,82 @@
+// Fused multi-scale spectral distance: the elementwise / reduction tail of
+// core.AudioDistanceV1 (rave/core.py:322-344) + mean_difference (236-252) applied to the complex STFTs of
+// the input (X) and of the reconstruction (Y), one scale per launch:
+//     lin = mean((|X|-|Y|)^2) / mean(|X|^2)          log = mean(| log(|X|+eps) - log(|Y|+eps) |)
+// forward : stats[0] += sum (|X|-|Y|)^2, stats[1] += sum |X|^2, stats[2] += sum |log(|X|+eps) - log(|Y|+eps)|
+// backward: dY = ( c_lin * -2 (|X|-|Y|) + c_log * -sgn(logX - logY) / (|Y|+eps) ) * Y/|Y|
+//           (PyTorch's convention for the gradient of a real loss w.r.t. a complex tensor through abs()).
+// Replaces ~14 ATen elementwise/reduce kernels per scale forward and ~25 backward with one kernel each.
+#include "common.cuh"
+
+namespace rave {
+
+__global__ void __launch_bounds__(256)
+spectral_stats_kernel(const float2 *__restrict__ X, const float2 *__restrict__ Y, float *__restrict__ stats, long n,
+                      float eps) {
+  __shared__ float red[3][8];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const float2 x = X[i], y = Y[i];
+    const float ax = sqrtf(x.x * x.x + x.y * x.y);
+    const float ay = sqrtf(y.x * y.x + y.y * y.y);
+    const float d = ax - ay;
+    s0 = fmaf(d, d, s0);
+    s1 = fmaf(ax, ax, s1);
+    s2 += fabsf(logf(ax + eps) - logf(ay + eps));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = s0; red[1][wid] = s1; red[2][wid] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    atomicAdd(stats + threadIdx.x, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+spectral_grad_kernel(const float2 *__restrict__ X, const float2 *__restrict__ Y, float2 *__restrict__ dY,
+                     const float *__restrict__ coef, long n, float eps) {
+  const float c_lin = coef[0], c_log = coef[1];
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const float2 x = X[i], y = Y[i];
+    const float ax = sqrtf(x.x * x.x + x.y * x.y);
+    const float ay = sqrtf(y.x * y.x + y.y * y.y);
+    const float dl = logf(ax + eps) - logf(ay + eps);
+    const float sg = dl > 0.f ? 1.f : (dl < 0.f ? -1.f : 0.f);
+    const float dmag = c_lin * (-2.f) * (ax - ay) - c_log * sg / (ay + eps);
+    const float inv = ay > 0.f ? dmag / ay : 0.f;
+    dY[i] = make_float2(y.x * inv, y.y * inv);
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_spectral_stats(const void *X, const void *Y, float *stats, long n, float eps, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(X && Y && stats && n > 0, "spectral_stats: bad argument");
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  spectral_stats_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)X, (const float2 *)Y, stats, n,
+                                                                       eps);
+  RAVE_CHECK_LAUNCH("spectral_stats");
+  return 0;
+}
+
+extern "C" int rave_spectral_grad(const void *X, const void *Y, void *dY, const float *coef, long n, float eps,
+                                  void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(X && Y && dY && coef && n > 0, "spectral_grad: bad argument");
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  spectral_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)X, (const float2 *)Y,
+                                                                      (float2 *)dY, coef, n, eps);
+  RAVE_CHECK_LAUNCH("spectral_grad");
+  return 0;
+}

@@ -548,3 +548,39 @@ def gather_c1(P_cl, x_pitch, Lin, Lout, K, stride, pad_l):
     dx = torch.empty(R, x_pitch, dtype=torch.float32, device=P_cl.device)
     call("rave_gather_c1", ptr(P_cl), ptr(dx), R, x_pitch, Lin, Lout, p_pitch, K, stride, pad_l, stream_ptr())
     return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# fused spectral distance of one STFT scale (csrc/spectral.cu)
+# ----------------------------------------------------------------------------------------------
+
+class SpectralDistanceFn(torch.autograd.Function):
+    """lin + log distance between complex spectrograms X (target, no gradient) and Y (reconstruction)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, eps):
+        if X.dtype != torch.complex64 or Y.dtype != torch.complex64 or X.shape != Y.shape:
+            raise _lib.RaveB200Error("spectral distance expects two complex64 spectrograms of equal shape")
+        X = X.contiguous()
+        Y = Y.contiguous()
+        n = X.numel()
+        stats = torch.zeros(3, dtype=torch.float32, device=X.device)
+        call("rave_spectral_stats", ptr(torch.view_as_real(X)), ptr(torch.view_as_real(Y)), ptr(stats), n,
+             float(eps), stream_ptr())
+        ctx.save_for_backward(X, Y, stats)
+        ctx.eps = float(eps)
+        return stats[0] / stats[1] + stats[2] / n
+
+    @staticmethod
+    def backward(ctx, g):
+        X, Y, stats = ctx.saved_tensors
+        n = X.numel()
+        coef = torch.stack([g / stats[1], g / n]).to(torch.float32).contiguous()
+        dY = torch.empty_like(Y)
+        call("rave_spectral_grad", ptr(torch.view_as_real(X)), ptr(torch.view_as_real(Y)),
+             ptr(torch.view_as_real(dY)), ptr(coef), n, ctx.eps, stream_ptr())
+        return None, dY, None
+
+
+def spectral_distance(X, Y, eps):
+    return SpectralDistanceFn.apply(X, Y, eps)

@@ -6,7 +6,7 @@ import torch
 from oracle import rave_oracle as O
 from rave_b200 import ops
 
-assert os.environ.get("RAVE_TC_2CTA") == "1"
+assert os.environ.get("RAVE_TC_2CTA", "1") == "1"
 
 
 def rel(a, b):

@@ -363,3 +363,21 @@ def test_descript_mpd_vs_oracle():
     dd = DescriptDiscriminator()
     y = torch.randn(2, 1, 300)
     assert rel_l2(dd.preprocess(y.cuda()), O.descript_preprocess(y)) < 1e-6
+
+
+def test_fused_spectral_distance_vs_oracle():
+    """core.AudioDistanceV1 with the fused spectral kernels against the reference golden and
+    the oracle's autograd."""
+    from functools import partial
+    from rave_b200 import core
+    g = load("audio_distance.pt")
+    dist = core.AudioDistanceV1(partial(core.MultiScaleSTFT, scales=[2048, 1024, 512, 256, 128],
+                                        sample_rate=48000, magnitude=True), 1e-7).cuda()
+    d = dist(g["x"].cuda(), g["y"].cuda())["spectral_distance"]
+    assert rel_l2(d, g["distance"]) < 1e-5
+    x = g["x"]
+    yo = g["y"].clone().requires_grad_(True)
+    (go,) = torch.autograd.grad(O.audio_distance_v1(x, yo), yo)
+    yg = g["y"].cuda().requires_grad_(True)
+    (gg,) = torch.autograd.grad(dist(x.cuda(), yg)["spectral_distance"], yg)
+    assert rel_l2(gg, go) < 1e-4
