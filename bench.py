@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("RAVE_B200_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="issue every launch from Python (no CUDA graphs)")
+    ap.add_argument("--cudnn-baseline", action="store_true",
+                    help="also time the SAME step arithmetic through stock torch/cuDNN (TF32, as scripts/train.py:135-136 "
+                         "configures the reference) on this GPU and report it as `stock_cudnn_tf32`")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     return ap.parse_args()
 
@@ -238,6 +241,67 @@ def tc_kernel_roofline(torch, pk):
                 peak_source=pk["source"] + " burst (cuBLAS bf16)")
 
 
+def forward_roofline(torch, model, x_dev, pk, prec):
+    """North-star sub-metric: PQMF + encoder + generator FORWARD (v2, B=32x65536), against the block-fused
+    algorithmic work of SURVEY.md 8d (306.4 GFLOP, 1.690 GB per 32x65536 batch) and the measured peaks:
+    t_min = max(bytes / HBM, flops / tensor) as a single-kernel-equivalent bound."""
+    B = x_dev.shape[0]
+    flops = 306.4e9 * B / 32
+    byts = 1.690e9 * B / 32
+    with torch.no_grad():
+        for _ in range(3):
+            model(x_dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        e0.record()
+        for _ in range(n):
+            model(x_dev)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    t_hbm = byts / (pk["hbm_gbs"] * 1e9) * 1e3
+    t_tc = flops / (pk["bf16_tflops"] * 1e12) * 1e3
+    t_min = max(t_hbm, t_tc)
+    return dict(ms=ms, audio_seconds_per_s=B * T / SR / (ms * 1e-3), algorithmic_gflop=flops / 1e9,
+                algorithmic_gb=byts / 1e9, achieved_tflops=flops / (ms * 1e-3) / 1e12,
+                achieved_gbs=byts / (ms * 1e-3) / 1e9, t_min_ms=t_min, frac_of_roofline=t_min / ms,
+                note="eager launches, no CUDA graph; byte count is the fp32 block-fused formula of SURVEY 8d")
+
+
+def stock_cudnn_step(torch, args, B):
+    """The reference's own GPU execution path for this step: ATen -> cuDNN convolutions with TF32 enabled
+    (scripts/train.py:135-136), fp32 tensors, eager autograd.  Executed through the oracle restatement (the
+    reference modules need gin / cached_conv / pytorch_lightning); a reported baseline, never the product."""
+    from oracle import rave_oracle as O
+    from rave_b200 import configs
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.set_float32_matmul_precision("high")
+    torch.manual_seed(0)
+    m = configs.build_rave(args.config, sampling_rate=SR)
+    sd = {k: v.detach().clone().cuda() for k, v in m.state_dict().items()}
+    del m
+    cfg = O.ArchConfig() if args.config == "v2" else O.v2_small_config()
+    x = synthetic_batch(B).cuda()
+    import numpy as np
+    eps = torch.randn(B, cfg.latent_size, T // (16 * int(np.prod(cfg.ratios))), device="cuda")
+    for i in range(3):
+        O.train_step_cpu(x, sd, cfg, eps, dis_step=(i % 4 == 0))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 8
+    e0.record()
+    for i in range(n):
+        O.train_step_cpu(x, sd, cfg, eps, dis_step=(i % 4 == 0))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return dict(ms_per_step=ms, audio_seconds_per_s=B * T / SR / (ms * 1e-3),
+                note="oracle restatement on CUDA tensors: ATen/cuDNN TF32 convs, eager autograd, fwd+bwd without "
+                     "optimiser; same D-every-4th schedule")
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -339,6 +403,15 @@ def run_ours(args):
 
     if rank == 0:
         roof = tc_kernel_roofline(torch, pk) if prec == "bf16" else dominant_kernel_roofline(torch, pk)
+        fwd = forward_roofline(torch, model, x_dev, pk, prec)
+        stock = None
+        if args.cudnn_baseline and world == 1:
+            del model, trainer
+            torch.cuda.empty_cache()
+            try:
+                stock = stock_cudnn_step(torch, args, B)
+            except Exception as e:
+                stock = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_reference_run(args, 2, 1, args.cpu_seconds)
@@ -356,7 +429,7 @@ def run_ours(args):
                        "launch": graph_note,
                        "l2_policy": "working set per step (>10 GB of activations) exceeds the 126 MB L2; "
                                     "two alternating input batches"},
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "forward_pqmf_enc_gen": fwd, "stock_cudnn_tf32": stock, "cpu_baseline": cpu,
             "e2e": {"value": value_e2e, "unit": "audio-seconds/s", "h2d_bytes_per_step": B * T * 4,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,

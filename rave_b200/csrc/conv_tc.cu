@@ -57,76 +57,98 @@ struct SmemLayout {
 };
 
 // Epilogue of one 128 x BLOCK_N accumulator tile: this thread owns TMEM lane `taddr.lane` = one output row.
+// One chunk = CW (16 or 32) consecutive channels.  All global loads of the chunk (residual, gradient skip,
+// LeakyReLU' mask) are issued BEFORE the TMEM load so that their latency overlaps it: the HBM-bound layers
+// (C = 96 / 192 blocks) are limited by the bytes in flight per SM, not by arithmetic.
+template <int CW>
+__device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow) {
+  float v[CW];
+  float4 rf[CW / 4];
+  uint4 rb[CW / 8], dm[CW / 8];
+  const size_t off = orow * p.Cout + co;
+  if (valid) {
+    if (p.res) {
+      const float4 *r4 = reinterpret_cast<const float4 *>(p.res + off);
+#pragma unroll
+      for (int i = 0; i < CW / 4; ++i) rf[i] = __ldg(r4 + i);
+    }
+    if (p.res_bf16) {
+      const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_bf16 + off);
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) rb[i] = __ldg(r4 + i);
+    }
+    if (p.dact_src) {
+      const uint4 *d4 = reinterpret_cast<const uint4 *>(p.dact_src + off);
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) dm[i] = __ldg(d4 + i);
+    }
+  }
+  if (CW == 32) tmem_ld_32x32(taddr, v);
+  else tmem_ld_32x16(taddr, v);       // warp-collective: every lane participates, valid or not
+  if (!valid) return;
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] += __ldg(p.bias + co + i);
+  }
+  if (p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand (sign bits of bf16)
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+      const uint32_t w[4] = {dm[i].x, dm[i].y, dm[i].z, dm[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (w[j] & 0x00008000u) v[8 * i + 2 * j] *= p.slope;
+        if (w[j] & 0x80000000u) v[8 * i + 2 * j + 1] *= p.slope;
+      }
+    }
+  }
+  if (p.res_bf16) {
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+      const uint32_t w[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
+        v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    }
+  }
+  if (p.res) {
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+      v[4 * i + 0] += rf[i].x; v[4 * i + 1] += rf[i].y; v[4 * i + 2] += rf[i].z; v[4 * i + 3] += rf[i].w;
+    }
+  }
+  if (p.out_f32) {
+    float4 *o4 = reinterpret_cast<float4 *>(p.out_f32 + off);
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  if (p.out_act) {
+    uint4 *o = reinterpret_cast<uint4 *>(p.out_act + off);
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a0 = v[8 * i + 2 * j], a1 = v[8 * i + 2 * j + 1];
+        if (p.act == RAVE_ACT_LEAKY) {
+          a0 = a0 > 0.f ? a0 : a0 * p.slope;
+          a1 = a1 > 0.f ? a1 : a1 * p.slope;
+        }
+        __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+        pk[j] = *reinterpret_cast<uint32_t *>(&h);
+      }
+      o[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
 template <int BLOCK_N>
 __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t taddr, int n0, bool valid, size_t orow) {
+  constexpr int MAIN = BLOCK_N / 32 * 32;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        float v[16];
-        tmem_ld_32x16(taddr + c0, v);   // warp-collective: every lane participates, valid or not
-        if (valid) {
-          const int co = n0 + c0;
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co + i);
-          }
-          if (p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand
-            const uint4 *d4 = reinterpret_cast<const uint4 *>(p.dact_src + orow * p.Cout + co);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint4 d = __ldg(d4 + i);
-              const uint32_t w[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // bf16 sign bits: element 2j in the low half, 2j+1 in the high half
-                if (w[j] & 0x00008000u) v[8 * i + 2 * j] *= p.slope;
-                if (w[j] & 0x80000000u) v[8 * i + 2 * j + 1] *= p.slope;
-              }
-            }
-          }
-          if (p.res_bf16) {
-            const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_bf16 + orow * p.Cout + co);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint4 d = __ldg(r4 + i);
-              const uint32_t w[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
-                v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-              }
-            }
-          }
-          if (p.res) {
-            const float4 *r4 = reinterpret_cast<const float4 *>(p.res + orow * p.Cout + co);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 r = __ldg(r4 + i);
-              v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-            }
-          }
-          if (p.out_f32) {
-            float4 *o4 = reinterpret_cast<float4 *>(p.out_f32 + orow * p.Cout + co);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          if (p.out_act) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a0 = v[2 * i], a1 = v[2 * i + 1];
-              if (p.act == RAVE_ACT_LEAKY) {
-                a0 = a0 > 0.f ? a0 : a0 * p.slope;
-                a1 = a1 > 0.f ? a1 : a1 * p.slope;
-              }
-              __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-              pk[i] = *reinterpret_cast<uint32_t *>(&h);
-            }
-            uint4 *o = reinterpret_cast<uint4 *>(p.out_act + orow * p.Cout + co);
-            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-        }
-      }
+  for (int c0 = 0; c0 < MAIN; c0 += 32) tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow);
+  if (MAIN < BLOCK_N) tc_epi_chunk<16>(p, taddr + MAIN, n0 + MAIN, valid, orow);
 }
 
 template <int BLOCK_N, int BLOCK_K>

@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 
-_state = {"precision": "fp32"}
+_state = {"precision": "fp32", "prep_epoch": 0}
 ACT_DTYPE = torch.bfloat16   # storage type of operand / gradient streams (tests may widen it)
 
 
@@ -40,6 +40,29 @@ def set_precision(mode: str) -> None:
 
 def precision() -> str:
     return _state["precision"]
+
+
+def invalidate_prepared() -> None:
+    """Drop every cached tap-major weight: call after parameters were changed behind autograd's back
+    (CUDA-graph replays update them without bumping tensor versions)."""
+    _state["prep_epoch"] += 1
+
+
+def _prepared_for(spec, v, g, need_dgrad: bool, need_fwd: bool):
+    """Tap-major operand layouts of one layer, cached on the owning module and keyed on the parameter
+    versions: re-used while the weights do not change (inference; the discriminator during generator
+    steps).  Never cached while a CUDA graph is being captured (the graph must re-derive them on replay)."""
+    capturing = v.is_cuda and torch.cuda.is_current_stream_capturing()
+    key = (v._version, g._version if g is not None else -1, need_dgrad, need_fwd, str(ACT_DTYPE), str(v.device),
+           v.data_ptr(), _state["prep_epoch"])
+    if not capturing:
+        hit = spec.module.__dict__.get("_tc_prep")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+    pw = _PreparedWeights(spec, v, g, need_dgrad, need_fwd)
+    if not capturing:
+        spec.module.__dict__["_tc_prep"] = (key, pw)
+    return pw
 
 
 @dataclass
@@ -290,8 +313,8 @@ class TcChainFn(torch.autograd.Function):
         for i, s in enumerate(specs):
             v, g, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
             use_c1 = c1 and i == 0
-            pw = _PreparedWeights(s, v.detach(), g.detach() if g is not None else None,
-                                  need_dgrad and not use_c1, need_fwd=not use_c1)
+            pw = _prepared_for(s, v.detach(), g.detach() if g is not None else None,
+                               need_dgrad and not use_c1, not use_c1)
             prepared.append(pw)
             Lin = lens[-1]
             Lout = _out_len(s, Lin)

@@ -12,7 +12,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import _lib
+from . import _lib, engine
 
 
 class GraphedTrainer:
@@ -56,5 +56,6 @@ class GraphedTrainer:
         is_dis = self.model.is_discriminator_step(batch_idx)
         self.x_static.copy_(batch, non_blocking=True)
         self.graphs[is_dis].replay()
+        engine.invalidate_prepared()       # parameters changed without bumping their autograd versions
         self.model.logged = self.outputs[is_dis]
         return self.outputs[is_dis]

@@ -561,8 +561,14 @@ class SpectralDistanceFn(torch.autograd.Function):
     def forward(ctx, X, Y, eps):
         if X.dtype != torch.complex64 or Y.dtype != torch.complex64 or X.shape != Y.shape:
             raise _lib.RaveB200Error("spectral distance expects two complex64 spectrograms of equal shape")
-        X = X.contiguous()
-        Y = Y.contiguous()
+        # the kernels are elementwise: any COMMON dense layout will do (torch.stft returns a transposed
+        # view of a [N, frames, bins] buffer) -- avoid materialising contiguous copies
+        if X.stride() == Y.stride() and X.transpose(-1, -2).is_contiguous():
+            X, Y = X.transpose(-1, -2), Y.transpose(-1, -2)
+            ctx.transposed = True
+        else:
+            X, Y = X.contiguous(), Y.contiguous()
+            ctx.transposed = False
         n = X.numel()
         stats = torch.zeros(3, dtype=torch.float32, device=X.device)
         call("rave_spectral_stats", ptr(torch.view_as_real(X)), ptr(torch.view_as_real(Y)), ptr(stats), n,
@@ -576,10 +582,10 @@ class SpectralDistanceFn(torch.autograd.Function):
         X, Y, stats = ctx.saved_tensors
         n = X.numel()
         coef = torch.stack([g / stats[1], g / n]).to(torch.float32).contiguous()
-        dY = torch.empty_like(Y)
+        dY = torch.empty_like(Y, memory_format=torch.contiguous_format)
         call("rave_spectral_grad", ptr(torch.view_as_real(X)), ptr(torch.view_as_real(Y)),
              ptr(torch.view_as_real(dY)), ptr(coef), n, ctx.eps, stream_ptr())
-        return None, dY, None
+        return None, (dY.transpose(-1, -2) if ctx.transposed else dY), None
 
 
 def spectral_distance(X, Y, eps):
