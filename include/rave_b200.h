@@ -130,6 +130,8 @@ int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, i
  *   xa      [B][Lin][Cin]  bf16 : the ALREADY ACTIVATED operand (written by the previous kernel's epilogue)
  *   wt      [K][Cout][Cin] bf16 : tap-major effective weights (rave_weight_to_tapmajor_bf16)
  *   res     [B][out_rows][Cout] fp32 or NULL (res_bf16: the same in bf16), bias [Cout] or NULL
+ *   res_act [B][out_rows][Cout] bf16 or NULL : residual skip taken from an ACTIVATED operand tensor
+ *             a = LeakyReLU_{res_slope}(h): adds h = a > 0 ? a : a / res_slope (no separate fp32 stream)
  *   dact_src[B][out_rows][Cout] bf16 or NULL : result *= LeakyReLU'(dact_src) before the residual add
  *             (backward use: the activated operand saved by the forward pass carries the sign)
  *   out_f32 [B][out_rows][Cout] fp32 or NULL : pre-activation stream (residual / features)
@@ -141,7 +143,8 @@ int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, i
  * ------------------------------------------------------------------------------------------- */
 int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dil);
 int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bias, const float *res,
-                       const void *res_bf16, const void *dact_src_bf16, float *out_f32, void *out_act_bf16,
+                       const void *res_bf16, const void *dact_src_bf16, const void *res_act_bf16, float res_slope,
+                       float *out_f32, void *out_act_bf16,
                        int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
                        int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
                        int out_row_stride, int out_row_offset, void *stream);

@@ -487,7 +487,7 @@ def descript_preprocess(y: Tensor) -> Tensor:
 def stft_mag(x: Tensor, n_fft: int) -> Tensor:
     """torchaudio.transforms.Spectrogram(n_fft, win_length=n_fft, hop=n_fft//4, power=None)
     followed by abs (rave/core.py:269-319): hann (periodic) window, centred, reflect pad."""
-    win = torch.hann_window(n_fft, dtype=x.dtype)
+    win = torch.hann_window(n_fft, dtype=x.dtype, device=x.device)
     s = torch.stft(x, n_fft, hop_length=n_fft // 4, win_length=n_fft, window=win,
                    center=True, pad_mode="reflect", normalized=False, onesided=True,
                    return_complex=True)

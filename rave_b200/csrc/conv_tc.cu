@@ -37,6 +37,8 @@ struct TcParams {
   const float *res;        // channel-last fp32 [B][out_rows][Cout] or null
   const __nv_bfloat16 *res_bf16;   // same, bf16 (gradient stream) or null
   const __nv_bfloat16 *dact_src;   // channel-last bf16 [B][out_rows][Cout] or null: out *= leaky'(dact_src)
+  const __nv_bfloat16 *res_act;    // channel-last bf16 a = LeakyReLU(h) or null: out += h recovered from a
+  float res_inv_slope;             //   (residual skip without a separate fp32 stream: h = a > 0 ? a : a / slope)
   float *out_f32;          // channel-last fp32 or null
   __nv_bfloat16 *out_act;  // channel-last bf16 = act(out) or null
   int out_rows;            // rows per batch of the output tensors (>= Lout when phases interleave)
@@ -64,9 +66,14 @@ template <int CW>
 __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow) {
   float v[CW];
   float4 rf[CW / 4];
-  uint4 rb[CW / 8], dm[CW / 8];
+  uint4 rb[CW / 8], dm[CW / 8], ra[CW / 8];
   const size_t off = orow * p.Cout + co;
   if (valid) {
+    if (p.res_act) {
+      const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_act + off);
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) ra[i] = __ldg(r4 + i);
+    }
     if (p.res) {
       const float4 *r4 = reinterpret_cast<const float4 *>(p.res + off);
 #pragma unroll
@@ -109,6 +116,18 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
       for (int j = 0; j < 4; ++j) {
         v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
         v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    }
+  }
+  if (p.res_act) {     // residual skip from the unit's own bf16 operand: undo the LeakyReLU
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+      const uint32_t w[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a0 = __uint_as_float(w[j] << 16), a1 = __uint_as_float(w[j] & 0xFFFF0000u);
+        v[8 * i + 2 * j] += a0 > 0.f ? a0 : a0 * p.res_inv_slope;
+        v[8 * i + 2 * j + 1] += a1 > 0.f ? a1 : a1 * p.res_inv_slope;
       }
     }
   }
@@ -605,7 +624,8 @@ extern "C" int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, in
 }
 
 extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *bias, const float *res,
-                                  const void *res_bf16, const void *dact_src, float *out_f32, void *out_act,
+                                  const void *res_bf16, const void *dact_src, const void *res_act, float res_slope,
+                                  float *out_f32, void *out_act,
                                   int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
                                   int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
                                   int out_row_stride, int out_row_offset, void *stream) {
@@ -628,6 +648,8 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   p.B = B; p.Cin = Cin; p.Lin = Lin; p.Cout = Cout; p.Lout = Lout; p.K = K; p.stride = stride; p.dil = dil;
   p.pad_l = pad_l; p.act = act; p.slope = slope; p.bias = bias; p.res = res; p.out_f32 = out_f32;
   p.res_bf16 = (const __nv_bfloat16 *)res_bf16; p.dact_src = (const __nv_bfloat16 *)dact_src;
+  p.res_act = (const __nv_bfloat16 *)res_act;
+  p.res_inv_slope = (res_act && res_slope > 0.f) ? 1.f / res_slope : 1.f;
   p.out_act = (__nv_bfloat16 *)out_act;
   p.out_rows = out_rows > 0 ? out_rows : Lout;
   p.out_row_stride = out_row_stride > 0 ? out_row_stride : 1;

@@ -77,11 +77,13 @@ class LayerSpec:
     pad: Tuple[int, int] = (0, 0)  # conv: (left, right); convT: (padding, padding)
     pre_act: int = ops.ACT_NONE    # activation applied to this layer's INPUT (emitted by its producer)
     pre_slope: float = 0.2
-    res_src: Optional[int] = None  # index of the layer whose fp32 stream is added (-1 = chain input)
+    res_src: Optional[int] = None  # index of the layer whose output stream is added (residual skip)
     want_f32: bool = False         # fp32 stream needed (residual source or external output)
     is_output: bool = False        # returned to the caller (fp32, channel-last)
     cin_pad: int = 0               # zero-padded input channels (Cin=1 layers run with Cin=16)
     cout_pad: int = 0
+    res_opnd: Optional[int] = None # index of the layer whose INPUT operand a = LeakyReLU(h_src) carries the
+                                   # residual stream: the skip is recovered from it (no fp32 copy of h_src)
 
 
 def chain_supported(specs: List[LayerSpec]) -> bool:
@@ -147,16 +149,18 @@ def plan_sequential(mods: List[nn.Module]) -> Optional[List[LayerSpec]]:
             if pending[0] != ops.ACT_NONE:
                 return None
             src = last_idx
-            if src >= 0:
-                specs[src].want_f32 = True
+            if src < 0:
+                return None
             a0, c3, a1, c1 = list(unit.net)
             for a in (a0, a1):
                 if not isinstance(a, nn.LeakyReLU):
                     return None
             pending = (ops.ACT_LEAKY, float(a0.negative_slope))
             add_conv(c3)
+            c3_idx = last_idx
             pending = (ops.ACT_LEAKY, float(a1.negative_slope))
             add_conv(c1, res_src=src)
+            specs[-1].res_opnd = c3_idx       # h_src = unleaky(operand of conv3): no fp32 stream needed
             continue
         return None
     if pending[0] != ops.ACT_NONE or not specs:
@@ -331,7 +335,12 @@ class TcChainFn(torch.autograd.Function):
             bias_p = bias
             if bias is not None and s.cout_pad:
                 bias_p = nn.functional.pad(bias.detach(), (0, s.cout_pad))
-            res = f32[s.res_src] if s.res_src is not None else None
+            res = res_act = None
+            res_slope = 0.2
+            if s.res_opnd is not None:
+                res_act, res_slope = acts[s.res_opnd], specs[s.res_opnd].pre_slope
+            elif s.res_src is not None:
+                res = f32[s.res_src]
             out_f32 = torch.empty(B, pitch, cout_p, dtype=torch.float32, device=dev) if want_f32 else None
             out_act = torch.empty(B, pitch, cout_p, dtype=ACT_DTYPE, device=dev) if want_act else None
             if pitch > Lout:
@@ -352,7 +361,7 @@ class TcChainFn(torch.autograd.Function):
             elif s.kind == "conv":
                 ops.conv1d_tc(a, pw.fwd, bias_p, res, s.stride, s.dil, s.pad, act_code, act_slope,
                               want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act, Lout=Lout,
-                              Lin=Lin, out_rows=pitch)
+                              Lin=Lin, out_rows=pitch, res_act=res_act, res_slope=res_slope)
             else:
                 for p, (wt, padpp) in enumerate(pw.fwd_phases):
                     if wt is None:

@@ -379,7 +379,7 @@ def conv1d_tc_supported(Cin, Cout, K=1, stride=1, dil=1):
 
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=ACT_NONE, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
-              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None):
+              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2):
     """xa_cl [B,Lin,Cin] bf16 (activated operand), wt [K,Cout,Cin] bf16 -> (out_f32 [B,Lout,Cout] fp32,
     out_act [B,Lout,Cout] bf16 = act(out)); either may be None."""
     B, in_pitch, Cin = xa_cl.shape          # allocated rows per batch; true length = Lin (slack rows zero)
@@ -396,7 +396,7 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     if want_act and out_act is None:
         out_act = torch.empty(B, rows, Cout, dtype=torch.bfloat16, device=xa_cl.device)
     call("rave_conv1d_tc_fwd", ptr(xa_cl), ptr(wt), ptr(bias), ptr(res_cl), ptr(res_bf16), ptr(dact_src),
-         ptr(out_f32), ptr(out_act), B, Cin, Lin, in_pitch, Cout, Lout, K, stride, dil, pad[0], act, float(slope),
+         ptr(res_act), float(res_slope), ptr(out_f32), ptr(out_act), B, Cin, Lin, in_pitch, Cout, Lout, K, stride, dil, pad[0], act, float(slope),
          out_rows, out_row_stride, out_row_offset, stream_ptr())
     return out_f32, out_act
 

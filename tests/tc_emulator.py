@@ -14,7 +14,7 @@ def _bf16(t):
 
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=0, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
-              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None):
+              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2):
     B, in_pitch, Cin = xa_cl.shape
     Lin = in_pitch if Lin is None else Lin
     K, Cout, _ = wt.shape
@@ -47,6 +47,9 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
         v = torch.where(sgn, v * slope, v)
     if res_bf16 is not None:
         v = v + res_bf16[:, idx].float()
+    if res_act is not None:
+        ra = res_act[:, idx].float()
+        v = v + torch.where(ra > 0, ra, ra / res_slope)
     if res_cl is not None:
         v = v + res_cl[:, idx]
     if want_f32 and out_f32 is None:
