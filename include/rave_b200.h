@@ -215,6 +215,18 @@ int rave_weight_prep_tc(const float *v, const float *g, float *norm, void *outA_
  * (g == NULL: plain re-layout). */
 int rave_weight_norm_bwd_tapmajor(const float *dwt, const float *v, const float *g, const float *norm, float *dv,
                                   float *dg, int C0, int C1, int K, int C0p, int C1p, int splits, void *stream);
+/* multi-tensor forms of the two calls above: one launch pair for up to 64 layers (a whole chain). */
+typedef struct rave_wprep_layer {
+  const float *v, *g;          /* parameter [C0][C1][K] and its weight-norm gain (or NULL)            */
+  float *norm;                 /* [C0] row norms: written by prep, read by the backward                */
+  void *outA, *outB;           /* bf16 outputs as in rave_weight_prep_tc (either may be NULL)         */
+  const float *dwt;            /* backward: [splits][K][C0p][C1p] fp32 partial weight gradients       */
+  float *dv, *dg;              /* backward: gradients of v and g                                      */
+  int C0, C1, K, C0p, C1p, nA, nB, splits;
+  int tapsA[32], tapsB[32];
+} rave_wprep_layer;
+int rave_weight_prep_tc_multi(int n, const rave_wprep_layer *layers, void *stream);
+int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers, void *stream);
 /* layout converters between the module-boundary layout [B][C][L] fp32 and the engine's channel-last:
  *   to_cl:   y_bf16[b][l][c] = bf16(act(x[b][c][l])), optionally also y_f32[b][l][c] = x[b][c][l]
  *   from_cl: y[b][c][l] = x_f32[b][l][c] */

@@ -52,11 +52,23 @@ SIGNATURES = {
     "rave_fm_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "rave_spectral_stats": (c_int, [_P, _P, _P, _L, _F, _P]),
     "rave_spectral_grad": (c_int, [_P, _P, _P, _P, _L, _F, _P]),
+    "rave_weight_prep_tc_multi": (c_int, [_I, _P, _P]),
+    "rave_weight_norm_bwd_multi": (c_int, [_I, _P, _P]),
     "rave_ncl_to_cl": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "rave_cl_to_ncl": (c_int, [_P, _P, _I, _I, _I, _P]),
     "rave_act_to_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "rave_weight_to_tapmajor_bf16": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
 }
+
+
+
+class WPrepLayer(ctypes.Structure):
+    """struct rave_wprep_layer of include/rave_b200.h"""
+    _fields_ = [("v", c_void_p), ("g", c_void_p), ("norm", c_void_p), ("outA", c_void_p), ("outB", c_void_p),
+                ("dwt", c_void_p), ("dv", c_void_p), ("dg", c_void_p),
+                ("C0", c_int), ("C1", c_int), ("K", c_int), ("C0p", c_int), ("C1p", c_int), ("nA", c_int),
+                ("nB", c_int), ("splits", c_int), ("tapsA", c_int * 32), ("tapsB", c_int * 32)]
+
 
 _lib = None
 

@@ -478,3 +478,202 @@ extern "C" int rave_weight_norm_bwd_tapmajor(const float *dwt, const float *v, c
   RAVE_CHECK_LAUNCH("weight_norm_bwd_tapmajor");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// multi-tensor variants: ONE launch prepares (or back-propagates through the weight norm of) every
+// layer of a chain.  Per-layer launches of these tiny kernels were 11 % of the bf16 training step
+// (profiles/r1_launches_bf16_summary.md); the descriptor table travels by value in the kernel
+// parameters (<= 64 layers per launch).
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+constexpr int MT_MAX = 64;
+
+struct MtLayer {
+  const float *v, *g;
+  float *norm;
+  __nv_bfloat16 *outA, *outB;
+  const float *dwt;     // backward only
+  float *dv, *dg;       // backward only
+  int C0, C1, K, C0p, C1p, nA, nB, splits;
+  int row_begin;        // prefix sum of C0 (row-parallel kernels)
+  int tile_begin;       // prefix sum of tiles (prep kernel)
+  unsigned char tapsA[32], tapsB[32];
+};
+
+struct MtTable {
+  int n;
+  int total_rows, total_tiles, maxK;
+  MtLayer L[MT_MAX];
+};
+
+__device__ __forceinline__ int mt_find_row(const MtTable &t, int row) {
+  int i = 0;
+  while (i + 1 < t.n && t.L[i + 1].row_begin <= row) ++i;
+  return i;
+}
+__device__ __forceinline__ int mt_find_tile(const MtTable &t, int tile) {
+  int i = 0;
+  while (i + 1 < t.n && t.L[i + 1].tile_begin <= tile) ++i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256) mt_rownorm_kernel(const __grid_constant__ MtTable t) {
+  __shared__ float red[32];
+  const int li = mt_find_row(t, blockIdx.x);
+  const MtLayer &L = t.L[li];
+  if (!L.g) return;
+  const int c = blockIdx.x - L.row_begin;
+  const int R = L.C1 * L.K;
+  const float *vr = L.v + (size_t)c * R;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) s = fmaf(vr[i], vr[i], s);
+  const float n = sqrtf(block_reduce_sum(s, red));
+  if (threadIdx.x == 0) L.norm[c] = n;
+}
+
+__global__ void __launch_bounds__(256) mt_prep_kernel(const __grid_constant__ MtTable t) {
+  extern __shared__ float sw[];   // [32 c0][32*K + 1]
+  __shared__ float scale[32];
+  const int li = mt_find_tile(t, blockIdx.x);
+  const MtLayer &L = t.L[li];
+  const int K = L.K, C0 = L.C0, C1 = L.C1, C0p = L.C0p, C1p = L.C1p;
+  const int tiles_x = (C1p + 31) / 32;
+  const int tile = blockIdx.x - L.tile_begin;
+  const int c1t = (tile % tiles_x) * 32, c0t = (tile / tiles_x) * 32;
+  const int pitch = 32 * K + 1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (threadIdx.x < 32) {
+    const int c0 = c0t + threadIdx.x;
+    scale[threadIdx.x] = (c0 < C0) ? (L.g ? L.g[c0] / L.norm[c0] : 1.f) : 0.f;
+  }
+  for (int r = ty; r < 32; r += 8) {
+    const int c0 = c0t + r;
+    for (int i = tx; i < 32 * K; i += 32) {
+      const int c1 = c1t + i / K;
+      sw[r * pitch + i] = (c0 < C0 && c1 < C1) ? L.v[((size_t)c0 * C1 + c1t) * K + i] : 0.f;
+    }
+  }
+  __syncthreads();
+  if (L.outA) {
+    for (int a = 0; a < L.nA; ++a) {
+      const int k = L.tapsA[a];
+      for (int r = ty; r < 32; r += 8) {
+        const int c0 = c0t + r, c1 = c1t + tx;
+        if (c0 < C0p && c1 < C1p)
+          L.outA[((size_t)a * C0p + c0) * C1p + c1] = __float2bfloat16_rn(sw[r * pitch + tx * K + k] * scale[r]);
+      }
+    }
+  }
+  if (L.outB) {
+    for (int b = 0; b < L.nB; ++b) {
+      const int k = L.tapsB[b];
+      for (int r = ty; r < 32; r += 8) {
+        const int c1 = c1t + r, c0 = c0t + tx;
+        if (c0 < C0p && c1 < C1p)
+          L.outB[((size_t)b * C1p + c1) * C0p + c0] = __float2bfloat16_rn(sw[tx * pitch + r * K + k] * scale[tx]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) mt_wn_bwd_kernel(const __grid_constant__ MtTable t) {
+  __shared__ float red[32];
+  const int li = mt_find_row(t, blockIdx.x);
+  const MtLayer &L = t.L[li];
+  if (!L.dwt) return;
+  const int c0 = blockIdx.x - L.row_begin;
+  const int C1 = L.C1, K = L.K, C0p = L.C0p, C1p = L.C1p;
+  const int R = C1 * K;
+  const float *vr = L.v + (size_t)c0 * R;
+  float *dr = L.dv + (size_t)c0 * R;
+  const size_t split_stride = (size_t)K * C0p * C1p;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+    const int k = j / C1, c1 = j - k * C1;
+    const int i = c1 * K + k;
+    const float *src = L.dwt + ((size_t)k * C0p + c0) * C1p + c1;
+    float dw = 0.f;
+    for (int sp = 0; sp < L.splits; ++sp) dw += src[sp * split_stride];
+    dr[i] = dw;
+    s = fmaf(dw, vr[i], s);
+  }
+  if (!L.g) return;
+  const float dot = block_reduce_sum(s, red);
+  const float n = L.norm[c0];
+  const float gn = L.g[c0] / n;
+  const float coef = dot / (n * n);
+  for (int i = threadIdx.x; i < R; i += blockDim.x) dr[i] = gn * (dr[i] - vr[i] * coef);
+  if (threadIdx.x == 0) L.dg[c0] = dot / n;
+}
+
+}  // namespace rave
+
+// Host-side description of one layer (plain C struct of the ABI)
+extern "C" int rave_weight_prep_tc_multi(int n, const rave_wprep_layer *layers, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(n > 0 && n <= MT_MAX && layers, "weight_prep_multi: 1..%d layers per call", MT_MAX);
+  MtTable t;
+  memset(&t, 0, sizeof(t));
+  t.n = n;
+  int rows = 0, tiles = 0, maxK = 1;
+  bool any_g = false;
+  for (int i = 0; i < n; ++i) {
+    const rave_wprep_layer &h = layers[i];
+    RAVE_CHECK_ARG(h.v && h.C0 > 0 && h.C1 > 0 && h.K > 0 && h.K <= 32 && h.nA <= 32 && h.nB <= 32 &&
+                       h.C0p >= h.C0 && h.C1p >= h.C1 && (!h.g || h.norm),
+                   "weight_prep_multi: bad layer %d", i);
+    MtLayer &L = t.L[i];
+    L.v = h.v; L.g = h.g; L.norm = h.norm;
+    L.outA = (__nv_bfloat16 *)h.outA; L.outB = (__nv_bfloat16 *)h.outB;
+    L.C0 = h.C0; L.C1 = h.C1; L.K = h.K; L.C0p = h.C0p; L.C1p = h.C1p;
+    L.nA = h.outA ? h.nA : 0; L.nB = h.outB ? h.nB : 0;
+    for (int k = 0; k < L.nA; ++k) L.tapsA[k] = (unsigned char)h.tapsA[k];
+    for (int k = 0; k < L.nB; ++k) L.tapsB[k] = (unsigned char)h.tapsB[k];
+    L.row_begin = rows; L.tile_begin = tiles;
+    rows += h.C0;
+    tiles += (L.nA || L.nB) ? ceil_div(h.C0p, 32) * ceil_div(h.C1p, 32) : 0;
+    if (h.K > maxK) maxK = h.K;
+    any_g = any_g || h.g;
+  }
+  t.total_rows = rows; t.total_tiles = tiles; t.maxK = maxK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (any_g) {
+    mt_rownorm_kernel<<<rows, 256, 0, s>>>(t);
+    RAVE_CHECK_LAUNCH("mt_rownorm");
+  }
+  if (tiles > 0) {
+    const int smem = 32 * (32 * maxK + 1) * sizeof(float);
+    static int attr_bytes = 0;
+    if (smem > 48 * 1024 && smem > attr_bytes) {
+      cudaFuncSetAttribute(mt_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (32 * 32 + 1) * 4);
+      attr_bytes = 32 * (32 * 32 + 1) * 4;
+    }
+    mt_prep_kernel<<<tiles, 256, smem, s>>>(t);
+    RAVE_CHECK_LAUNCH("mt_prep");
+  }
+  return 0;
+}
+
+extern "C" int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(n > 0 && n <= MT_MAX && layers, "weight_norm_bwd_multi: 1..%d layers per call", MT_MAX);
+  MtTable t;
+  memset(&t, 0, sizeof(t));
+  t.n = n;
+  int rows = 0;
+  for (int i = 0; i < n; ++i) {
+    const rave_wprep_layer &h = layers[i];
+    RAVE_CHECK_ARG(h.v && h.dwt && h.dv && h.C0 > 0 && h.C1 > 0 && h.K > 0 && h.splits >= 1 && (!h.g || (h.norm && h.dg)),
+                   "weight_norm_bwd_multi: bad layer %d", i);
+    MtLayer &L = t.L[i];
+    L.v = h.v; L.g = h.g; L.norm = h.norm; L.dwt = h.dwt; L.dv = h.dv; L.dg = h.dg;
+    L.C0 = h.C0; L.C1 = h.C1; L.K = h.K; L.C0p = h.C0p; L.C1p = h.C1p; L.splits = h.splits;
+    L.row_begin = rows;
+    rows += h.C0;
+  }
+  t.total_rows = rows;
+  mt_wn_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(t);
+  RAVE_CHECK_LAUNCH("mt_wn_bwd");
+  return 0;
+}

@@ -48,23 +48,6 @@ def invalidate_prepared() -> None:
     _state["prep_epoch"] += 1
 
 
-def _prepared_for(spec, v, g, need_dgrad: bool, need_fwd: bool):
-    """Tap-major operand layouts of one layer, cached on the owning module and keyed on the parameter
-    versions: re-used while the weights do not change (inference; the discriminator during generator
-    steps).  Never cached while a CUDA graph is being captured (the graph must re-derive them on replay)."""
-    capturing = v.is_cuda and torch.cuda.is_current_stream_capturing()
-    key = (v._version, g._version if g is not None else -1, need_dgrad, need_fwd, str(ACT_DTYPE), str(v.device),
-           v.data_ptr(), _state["prep_epoch"])
-    if not capturing:
-        hit = spec.module.__dict__.get("_tc_prep")
-        if hit is not None and hit[0] == key:
-            return hit[1]
-    pw = _PreparedWeights(spec, v, g, need_dgrad, need_fwd)
-    if not capturing:
-        spec.module.__dict__["_tc_prep"] = (key, pw)
-    return pw
-
-
 @dataclass
 class LayerSpec:
     kind: str                      # 'conv' | 'convT'
@@ -219,46 +202,45 @@ def _phase_taps(K: int, stride: int, pad: int, p: int):
 
 
 class _PreparedWeights:
-    """Effective weight of one layer in every tap-major bf16 layout the kernels need, produced from
-    (v, g) by ONE fused launch pair (row norms + re-layout): rave_weight_prep_tc."""
+    """Effective weight of one layer in every tap-major bf16 layout the kernels need.  `plan()` decides
+    which layouts / tap orders are required; `prepare_layers()` produces them for a whole chain with ONE
+    multi-tensor launch pair (row norms + re-layout): rave_weight_prep_tc_multi."""
 
-    def __init__(self, spec: LayerSpec, v: torch.Tensor, g: Optional[torch.Tensor], need_dgrad: bool,
-                 need_fwd: bool = True):
+    def __init__(self, spec: LayerSpec, need_dgrad: bool, need_fwd: bool):
         self.spec = spec
         K, s = spec.K, spec.stride
-        dev = v.device
-        C0, C1 = v.shape[0], v.shape[1]
         if spec.kind == "conv":
-            C0p, C1p = spec.Cout + spec.cout_pad, spec.Cin + spec.cin_pad
+            self.C0p, self.C1p = spec.Cout + spec.cout_pad, spec.Cin + spec.cin_pad
         else:
-            C0p, C1p = spec.Cin + spec.cin_pad, spec.Cout + spec.cout_pad
+            self.C0p, self.C1p = spec.Cin + spec.cin_pad, spec.Cout + spec.cout_pad
+        self.norm = None
         self.fwd = None           # conv: [K][Cout][Cin]
         self.fwd_phases = None    # convT: per output phase (wt [n][Cout][Cin], pad'')
         self.dgrad = None         # stride-1 conv: flipped taps [K][Cin][Cout]; convT: [K][Cin][Cout]
         self.dgrad_phases = None  # strided conv: per input phase (wt [n][Cin][Cout], pad'')
-        phases = None
+        self.phases = None
+        self.need_dgrad = need_dgrad
         if spec.kind == "conv":
-            tapsA = list(range(K)) if need_fwd else []
+            self.tapsA = list(range(K)) if need_fwd else []
             if not need_dgrad:
-                tapsB = []
+                self.tapsB = []
             elif s == 1:
-                tapsB = list(range(K - 1, -1, -1))
+                self.tapsB = list(range(K - 1, -1, -1))
             else:
-                phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
-                tapsB = [k for order, _ in phases for k in order]
+                self.phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
+                self.tapsB = [k for order, _ in self.phases for k in order]
         else:
-            phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
-            tapsB = [k for order, _ in phases for k in order]
-            tapsA = list(range(K)) if need_dgrad else []
-        if tapsA or tapsB:
-            self.norm, outA, outB = ops.weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p)
-        else:
-            self.norm = ops.weight_norm_raw(v, g)[1] if g is not None else None
-            outA = outB = None
+            self.phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
+            self.tapsB = [k for order, _ in self.phases for k in order]
+            self.tapsA = list(range(K)) if need_dgrad else []
+
+    def finalize(self, norm, outA, outB):
+        spec = self.spec
+        self.norm = norm
 
         def split(buf):
             out, off = [], 0
-            for order, padpp in phases:
+            for order, padpp in self.phases:
                 n = len(order)
                 out.append((buf[off:off + n] if n else None, padpp))
                 off += n
@@ -266,14 +248,45 @@ class _PreparedWeights:
 
         if spec.kind == "conv":
             self.fwd = outA
-            if need_dgrad:
-                if s == 1:
+            if self.need_dgrad:
+                if spec.stride == 1:
                     self.dgrad = outB
                 else:
                     self.dgrad_phases = split(outB)
         else:
             self.fwd_phases = split(outB)
             self.dgrad = outA
+        return self
+
+
+def prepare_layers(jobs):
+    """jobs: list of (spec, v, g, need_dgrad, need_fwd).  Returns the list of _PreparedWeights, re-using the
+    per-module cache (keyed on parameter versions; bypassed while a CUDA graph is being captured) and
+    preparing all misses with one multi-tensor launch pair."""
+    out = [None] * len(jobs)
+    todo = []
+    for i, (spec, v, g, need_dgrad, need_fwd) in enumerate(jobs):
+        capturing = v.is_cuda and torch.cuda.is_current_stream_capturing()
+        key = (v._version, g._version if g is not None else -1, need_dgrad, need_fwd, str(ACT_DTYPE), str(v.device),
+               v.data_ptr(), _state["prep_epoch"])
+        if not capturing:
+            hit = spec.module.__dict__.get("_tc_prep")
+            if hit is not None and hit[0] == key:
+                out[i] = hit[1]
+                continue
+        todo.append((i, key, capturing, _PreparedWeights(spec, need_dgrad, need_fwd), v, g))
+    work = [(i, key, cap, pw, v, g) for (i, key, cap, pw, v, g) in todo if pw.tapsA or pw.tapsB]
+    if work:
+        res = ops.weight_prep_tc_multi([(v, g, pw.tapsA, pw.tapsB, pw.C0p, pw.C1p) for (_, _, _, pw, v, g) in work])
+        for (i, key, cap, pw, v, g), (norm, outA, outB) in zip(work, res):
+            out[i] = pw.finalize(norm, outA, outB)
+            if not cap:
+                pw.spec.module.__dict__["_tc_prep"] = (key, out[i])
+    for (i, key, cap, pw, v, g) in todo:
+        if out[i] is None:            # nothing to re-layout (a c1 layer without dgrad): only the norm
+            pw.norm = ops.weight_norm_raw(v, g)[1] if g is not None else None
+            out[i] = pw
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -314,12 +327,13 @@ class TcChainFn(torch.autograd.Function):
         lens = [L0]
         outputs = []
         stats = torch.zeros(max(n - 1, 1), 2, dtype=torch.float32, device=dev) if fm else None
+        prepared = prepare_layers([(s, flat[3 * i].detach(), flat[3 * i + 1].detach() if flat[3 * i + 1] is not None
+                                    else None, need_dgrad and not (c1 and i == 0), not (c1 and i == 0))
+                                   for i, s in enumerate(specs)])
         for i, s in enumerate(specs):
             v, g, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
             use_c1 = c1 and i == 0
-            pw = _prepared_for(s, v.detach(), g.detach() if g is not None else None,
-                               need_dgrad and not use_c1, not use_c1)
-            prepared.append(pw)
+            pw = prepared[i]
             Lin = lens[-1]
             Lout = _out_len(s, Lin)
             lens.append(Lout)
@@ -416,6 +430,7 @@ class TcChainFn(torch.autograd.Function):
         g_cur: Optional[torch.Tensor] = None   # gradient (h-space) of layer i's output
         grads = [None] * len(flat)
         gx = None
+        wn_jobs = []       # (layer, dwt partials, v, g, norm): one multi-tensor launch at the end
         for i in range(n - 1, -1, -1):
             s = specs[i]
             pw = ctx.prepared[i]
@@ -442,8 +457,7 @@ class TcChainFn(torch.autograd.Function):
                 else:
                     dwt = ops.conv1d_tc_wgrad(a_in, g, s.K, s.stride, 1, s.pad[0], Lp=Lin, Lq=Lout)
                 # dwt is [S][K][C0p][C1p] in the parameter's own (C0, C1) order for both kinds
-                dv, dg = ops.weight_norm_bwd_tapmajor(dwt, v, gpar, pw.norm)
-                grads[3 * i], grads[3 * i + 1] = dv, dg
+                wn_jobs.append((i, dwt, v, gpar, pw.norm))
             if bias is not None and bias.requires_grad:
                 grads[3 * i + 2] = ops.colsum_bf16(g, Lout, s.Cout)
             # ---- input gradient
@@ -493,6 +507,10 @@ class TcChainFn(torch.autograd.Function):
             g_cur = gp
             if i == 0:
                 gx = gp
+        if wn_jobs:
+            res = ops.weight_norm_bwd_multi([(dwt, v, gpar, norm) for (_, dwt, v, gpar, norm) in wn_jobs])
+            for (i, _, _, _, _), (dv, dg) in zip(wn_jobs, res):
+                grads[3 * i], grads[3 * i + 1] = dv, dg
         return (gx, None, None, None) + tuple(grads)
 
 

@@ -590,3 +590,59 @@ class SpectralDistanceFn(torch.autograd.Function):
 
 def spectral_distance(X, Y, eps):
     return SpectralDistanceFn.apply(X, Y, eps)
+
+
+# ----------------------------------------------------------------------------------------------
+# multi-tensor weight preparation / weight-norm backward (one launch pair per chain)
+# ----------------------------------------------------------------------------------------------
+
+def weight_prep_tc_multi(items):
+    """items: list of (v, g, tapsA, tapsB, C0p, C1p).  Returns a list of (norm, outA, outB) exactly like
+    weight_prep_tc, using ONE row-norm launch and ONE re-layout launch for (up to 64 of) the layers."""
+    outs = []
+    recs = []
+    for (v, g, tapsA, tapsB, C0p, C1p) in items:
+        v = _f32c(v)
+        g = _f32c(g)
+        C0, C1 = v.shape[0], v.shape[1]
+        K = v.numel() // (C0 * C1)
+        dev = v.device
+        norm = torch.empty(C0, dtype=torch.float32, device=dev) if g is not None else None
+        outA = torch.empty(len(tapsA), C0p, C1p, dtype=torch.bfloat16, device=dev) if tapsA else None
+        outB = torch.empty(len(tapsB), C1p, C0p, dtype=torch.bfloat16, device=dev) if tapsB else None
+        outs.append((norm, outA, outB))
+        recs.append((v, g, norm, outA, outB, tapsA, tapsB, C0, C1, K, C0p, C1p))
+    for i0 in range(0, len(recs), 64):
+        chunk = recs[i0:i0 + 64]
+        arr = (_lib.WPrepLayer * len(chunk))()
+        for L, (v, g, norm, outA, outB, tapsA, tapsB, C0, C1, K, C0p, C1p) in zip(arr, chunk):
+            L.v, L.g, L.norm, L.outA, L.outB = ptr(v), ptr(g), ptr(norm), ptr(outA), ptr(outB)
+            L.C0, L.C1, L.K, L.C0p, L.C1p, L.nA, L.nB, L.splits = C0, C1, K, C0p, C1p, len(tapsA), len(tapsB), 1
+            for j, t in enumerate(tapsA):
+                L.tapsA[j] = t
+            for j, t in enumerate(tapsB):
+                L.tapsB[j] = t
+        call("rave_weight_prep_tc_multi", len(chunk), arr, stream_ptr())
+    return outs
+
+
+def weight_norm_bwd_multi(items):
+    """items: list of (dwt [S][K][C0p][C1p], v, g | None, norm | None).  Returns a list of (dv, dg | None)."""
+    outs = []
+    recs = []
+    for (dwt, v, g, norm) in items:
+        v = _f32c(v)
+        dv = torch.empty_like(v)
+        dg = torch.empty_like(g) if g is not None else None
+        outs.append((dv, dg))
+        recs.append((dwt, v, g, norm, dv, dg))
+    for i0 in range(0, len(recs), 64):
+        chunk = recs[i0:i0 + 64]
+        arr = (_lib.WPrepLayer * len(chunk))()
+        for L, (dwt, v, g, norm, dv, dg) in zip(arr, chunk):
+            C0, C1 = v.shape[0], v.shape[1]
+            L.v, L.g, L.norm, L.dwt, L.dv, L.dg = ptr(v), ptr(g), ptr(norm), ptr(dwt), ptr(dv), ptr(dg)
+            L.C0, L.C1, L.K = C0, C1, v.numel() // (C0 * C1)
+            L.C0p, L.C1p, L.splits = dwt.shape[2], dwt.shape[3], dwt.shape[0]
+        call("rave_weight_norm_bwd_multi", len(chunk), arr, stream_ptr())
+    return outs

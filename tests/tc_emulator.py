@@ -225,8 +225,17 @@ def fm_grad(a_cl, dstats_row, L, slope):
     return _bf16(g)
 
 
+def weight_prep_tc_multi(items):
+    return [weight_prep_tc(*it) for it in items]
+
+
+def weight_norm_bwd_multi(items):
+    return [weight_norm_bwd_tapmajor(*it) for it in items]
+
+
 def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
-                 "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1"):
+                 "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1", "weight_prep_tc_multi",
+                 "weight_norm_bwd_multi"):
         monkeypatch.setattr(ops, name, globals()[name])

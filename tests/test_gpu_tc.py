@@ -148,3 +148,35 @@ def test_conv1d_tc_cta_pair_variant():
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_2cta.py")], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "2CTA OK" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_multi_tensor_weight_kernels_match_single():
+    from rave_b200 import ops
+    torch.manual_seed(1)
+    items, singles = [], []
+    for (C0, C1, K, wn, C0p, C1p) in [(96, 16, 7, True, 96, 16), (192, 96, 8, True, 192, 96), (96, 1, 15, True, 96, 16),
+                                      (1, 768, 1, False, 16, 768), (1536, 768, 4, True, 1536, 768), (48, 48, 3, True, 48, 48)]:
+        v = torch.randn(C0, C1, K, device="cuda")
+        g = (torch.rand(C0, 1, 1, device="cuda") + 0.5) if wn else None
+        tapsA = list(range(K))
+        tapsB = list(range(K - 1, -1, -1))
+        items.append((v, g, tapsA, tapsB, C0p, C1p))
+        singles.append(ops.weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p))
+    multi = ops.weight_prep_tc_multi(items)
+    for (n1, a1, b1), (n2, a2, b2) in zip(singles, multi):
+        assert (n1 is None) == (n2 is None)
+        if n1 is not None:
+            assert torch.equal(n1, n2)
+        assert torch.equal(a1, a2) and torch.equal(b1, b2)
+    jobs, ref = [], []
+    for (v, g, tapsA, tapsB, C0p, C1p), (norm, _, _) in zip(items, multi):
+        K = v.shape[2]
+        dwt = torch.randn(3, K, C0p, C1p, device="cuda")
+        jobs.append((dwt, v, g, norm))
+        ref.append(ops.weight_norm_bwd_tapmajor(dwt, v, g, norm))
+    out = ops.weight_norm_bwd_multi(jobs)
+    for (dv1, dg1), (dv2, dg2) in zip(ref, out):
+        assert torch.allclose(dv1, dv2, rtol=1e-5, atol=1e-6)
+        assert (dg1 is None) == (dg2 is None)
+        if dg1 is not None:
+            assert torch.allclose(dg1, dg2, rtol=1e-5, atol=1e-6)
