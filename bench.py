@@ -436,7 +436,15 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graphs hold NCCL kernels; tearing the communicator down under them can block
+        # (observed: both ranks stuck in destroy_process_group after the result line).  Synchronise, make sure
+        # every rank is done, flush, and leave without running the communicator's destructor.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -104,10 +104,27 @@ def launch_count() -> int:
     return int(load().rave_b200_launch_count())
 
 
+PROFILE = None      # set to a list: every call is timed alone (sync + CUDA events) and logged as
+                    # (entry point, integer arguments, milliseconds) -- scripts/profile_layers.py
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point; non-zero -> RuntimeError with the library's message."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        torch.cuda.synchronize()
+        ints = tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and abs(a) < (1 << 24))
+        ptrs = "".join("-" if a is None else "P" for a in args
+                       if a is None or (isinstance(a, int) and abs(a) >= (1 << 24)))
+        PROFILE.append((name, ints, ptrs, e0.elapsed_time(e1)))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RaveB200Error(f"{name} failed (rc={rc}): {last_error()}")
 
