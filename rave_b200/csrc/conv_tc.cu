@@ -44,6 +44,9 @@ struct TcParams {
   int out_rows;            // rows per batch of the output tensors (>= Lout when phases interleave)
   int out_row_stride;      // output row = l * out_row_stride + out_row_offset (transposed-conv phases)
   int out_row_offset;
+  int stages;              // pipeline depth actually used (<= the layout's STAGES); RAVE_TC_STAGES overrides
+  int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue stores, 2 = skip the
+                           // activation TMA loads, 4 = skip the weight TMA loads (results are garbage)
 };
 
 template <int BLOCK_N, int BLOCK_K>
@@ -215,57 +218,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_nt;
-        const int mt = tile / p.n_nt;
-        const int lt = mt % p.n_lt;
-        const int bg = mt / p.n_lt;
-        const int l0 = lt * p.BL;
-        const int b0 = bg * p.BB;
-        const int n0 = nt * BLOCK_N;
-        for (int k = 0; k < p.K; ++k) {
-          // input row = l*stride + k*dil - pad_l = (l + j)*stride + ph
-          const int off = k * p.dil - p.pad_l;
-          int j = off / p.stride;
-          int ph = off - j * p.stride;
-          if (ph < 0) { ph += p.stride; j -= 1; }
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t *sa = smem + stage * L::STAGE_BYTES;
-            uint8_t *sb = sa + L::A_BYTES;
+    // =========================== TMA producer (warp-uniform loop, elected lane issues) ===========================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_nt;
+      const int mt = tile / p.n_nt;
+      const int lt = mt % p.n_lt;
+      const int bg = mt / p.n_lt;
+      const int l0 = lt * p.BL;
+      const int b0 = bg * p.BB;
+      const int n0 = nt * BLOCK_N;
+      for (int k = 0; k < p.K; ++k) {
+        // input row = l*stride + k*dil - pad_l = (l + j)*stride + ph
+        const int off = k * p.dil - p.pad_l;
+        int j = off / p.stride;
+        int ph = off - j * p.stride;
+        if (ph < 0) { ph += p.stride; j -= 1; }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t *sa = smem + stage * L::STAGE_BYTES;
+          uint8_t *sb = sa + L::A_BYTES;
+          if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
             tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
+    // =========================== MMA issuer (warp-uniform loop, elected lane issues) ===========================
     constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      __syncwarp();
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      const uint32_t tmem_d = tmem_u + acc * BLOCK_N;
       for (int kb = 0; kb < kblocks; ++kb) {
-        if (lane == 0) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
-          const uint64_t adesc = make_kmajor_desc(sa, SWZ);
-          const uint64_t bdesc = make_kmajor_desc(sb, SWZ);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+        const uint64_t adesc = make_kmajor_desc(sa, SWZ);
+        const uint64_t bdesc = make_kmajor_desc(sa + L::A_BYTES, SWZ);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
             // advance 16 bf16 = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
@@ -386,57 +390,59 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // =========================== TMA producer (both CTAs) ===========================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int nt = tile % p.n_nt;
-        const int mt = (tile / p.n_nt) * 2 + (int)rank;      // this CTA's M tile (may be >= n_mt: zero-filled)
-        const int lt = mt % p.n_lt;
-        const int bg = mt / p.n_lt;
-        const int l0 = lt * p.BL;
-        const int b0 = bg * p.BB;
-        const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
-        for (int k = 0; k < p.K; ++k) {
-          const int off = k * p.dil - p.pad_l;
-          int j = off / p.stride;
-          int ph = off - j * p.stride;
-          if (ph < 0) { ph += p.stride; j -= 1; }
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t *sa = smem + stage * L::STAGE_BYTES;
-            uint8_t *sb = sa + L::A_BYTES;
-            tma_load_4d_2sm(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
-            tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (L::A_BYTES + L::B_BYTES));
+    // =========================== TMA producer (both CTAs; warp-uniform loop) ===========================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = 2 * (((p.dbg & 2) ? 0 : L::A_BYTES) + ((p.dbg & 4) ? 0 : L::B_BYTES));
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int nt = tile % p.n_nt;
+      const int mt = (tile / p.n_nt) * 2 + (int)rank;      // this CTA's M tile (may be >= n_mt: zero-filled)
+      const int lt = mt % p.n_lt;
+      const int bg = mt / p.n_lt;
+      const int l0 = lt * p.BL;
+      const int b0 = bg * p.BB;
+      const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+      for (int k = 0; k < p.K; ++k) {
+        const int off = k * p.dil - p.pad_l;
+        int j = off / p.stride;
+        int ph = off - j * p.stride;
+        if (ph < 0) { ph += p.stride; j -= 1; }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t *sa = smem + stage * L::STAGE_BYTES;
+          uint8_t *sb = sa + L::A_BYTES;
+          if (elect_one()) {
+            if (!(p.dbg & 2)) tma_load_4d_2sm(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
+            if (!(p.dbg & 4)) tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             else mbar_arrive_remote(&full_bar[stage], 0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1 && leader) {
     // =========================== MMA issuer (leader only) ===========================
     constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      __syncwarp();
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      const uint32_t tmem_d = tmem_u + acc * BLOCK_N;
       for (int kb = 0; kb < kblocks; ++kb) {
-        if (lane == 0) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
-          const uint64_t adesc = make_kmajor_desc(sa, SWZ);
-          const uint64_t bdesc = make_kmajor_desc(sb, SWZ);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+        const uint64_t adesc = make_kmajor_desc(sa, SWZ);
+        const uint64_t bdesc = make_kmajor_desc(sa + L::A_BYTES, SWZ);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / 16; ++kk)
             umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
@@ -444,11 +450,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (kb == kblocks - 1) umma_commit_2sm(&tfull_bar[acc]);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
     // the peer's last arrivals must land before this CTA's barriers disappear
-    if (it > 0 && lane == 0) {
+    if (it > 0) {
       const int last = it - 1;
       mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);
     }
@@ -468,215 +474,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int n0 = nt * BLOCK_N;
       const int b = bg * p.BB + row / p.BL;
       const int l = lt * p.BL + row % p.BL;
-      const bool valid = (mt < n_mt) && (b < p.B) && (l < p.Lout);
-      const size_t orow = (size_t)b * p.out_rows + (size_t)l * p.out_row_stride + p.out_row_offset;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
-  }
-}
-
-// =============================================================================================
-// "Halo" CTA-pair variant: one activation stage serves EVERY tap that reads the same input phase.
-//
-// The engine is bound by the L2 -> shared-memory fill rate (~43 B/clk/SM at the full-chip LTS cap), not by
-// the tensor pipe: conv_tc2 streams (16 + 16) KB per 512-clk MMA batch at BLOCK_N = 256.  Taps of one
-// phase group read the SAME rows shifted by a few positions (k*dil/stride), so this kernel loads one
-// (128 + halo)-row activation tile per (channel block, phase group) and points the A descriptor of each
-// tap at `tile + row_offset * span` -- the swizzle is a function of the absolute shared-memory address, so
-// a 128-byte-granular start offset inside a 1024-byte-aligned tile stays consistent with what TMA wrote.
-// A and W use separate rings: a K=15 stride-4 conv loads 4 activation stages and 15 weight stages per
-// channel block instead of 15 + 15.  Requires BB == 1 (one tile = 128 consecutive positions of one batch).
-// =============================================================================================
-constexpr int HALO_MAX_GROUPS = 8;
-constexpr int HALO_MAX_TAPS = 32;
-constexpr int HALO_MAX_STAGES = 8;
-
-struct HaloPlan {
-  int n_groups;            // distinct input phases
-  int rows;                // rows of one activation stage = 128 + max row offset
-  int a_stage_bytes;       // rows * span rounded up to 1024
-  int a_stages, w_stages;
-  int base_off_mode;       // experiment switch: also set the descriptor's matrix-base-offset field
-  int g_ph[HALO_MAX_GROUPS], g_j0[HALO_MAX_GROUPS], g_begin[HALO_MAX_GROUPS + 1];
-  int tap_k[HALO_MAX_TAPS], tap_roff[HALO_MAX_TAPS];
-};
-
-template <int BLOCK_N, int BLOCK_K>
-struct SmemLayout3 {
-  static constexpr int W_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
-  static constexpr int W_BYTES_PAD = (W_BYTES + 1023) / 1024 * 1024;
-  static constexpr int RING_BYTES = 200 * 1024;
-  static constexpr int BAR_BYTES = 512;
-  static constexpr int TOTAL = RING_BYTES + BAR_BYTES + 1024;
-};
-
-template <int BLOCK_N, int BLOCK_K>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-conv_tc3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const TcParams p, const __grid_constant__ HaloPlan hp) {
-  using L = SmemLayout3<BLOCK_N, BLOCK_K>;
-  constexpr int SWZ = BLOCK_K * 2;
-  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
-                                 : (ACC_STAGES * BLOCK_N <= 128) ? 128 : (ACC_STAGES * BLOCK_N <= 256) ? 256 : 512;
-  static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "cta_group::2 needs N % 32 == 0");
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *smem_a = smem;
-  uint8_t *smem_w = smem + hp.a_stages * hp.a_stage_bytes;
-  uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + L::RING_BYTES);
-  uint64_t *a_empty = a_full + HALO_MAX_STAGES;
-  uint64_t *w_full = a_empty + HALO_MAX_STAGES;
-  uint64_t *w_empty = w_full + HALO_MAX_STAGES;
-  uint64_t *tfull_bar = w_empty + HALO_MAX_STAGES;
-  uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tempty_bar + ACC_STAGES);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
-  const int n_mt = p.n_lt * p.n_bg;
-  const int n_mp = (n_mt + 1) >> 1;
-  const int num_tiles = n_mp * p.n_nt;
-  const uint32_t a_tx = (uint32_t)hp.rows * SWZ;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < HALO_MAX_STAGES; ++s) {
-      mbar_init(&a_full[s], 2);
-      mbar_init(&a_empty[s], 1);
-      mbar_init(&w_full[s], 2);
-      mbar_init(&w_empty[s], 1);
-    }
-    for (int s = 0; s < ACC_STAGES; ++s) {
-      mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
-    }
-    fence_barrier_init();
-  }
-  cluster_sync_all();
-  if (warp == 1) tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    // =========================== TMA producer (both CTAs) ===========================
-    if (lane == 0) {
-      int as = 0, ws = 0;
-      uint32_t aph = 0, wph = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int nt = tile % p.n_nt;
-        const int mt = (tile / p.n_nt) * 2 + (int)rank;
-        const int lt = mt % p.n_lt;
-        const int b0 = mt / p.n_lt;                  // BB == 1
-        const int l0 = lt * BLOCK_M;
-        const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
-        for (int g = 0; g < hp.n_groups; ++g) {
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(&a_empty[as], aph ^ 1);
-            tma_load_4d_2sm(smem_a + as * hp.a_stage_bytes, &tmap_a, &a_full[as], kb * BLOCK_K, hp.g_ph[g],
-                            l0 + hp.g_j0[g], b0);
-            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * a_tx);
-            else mbar_arrive_remote(&a_full[as], 0);
-            if (++as == hp.a_stages) { as = 0; aph ^= 1; }
-            for (int t = hp.g_begin[g]; t < hp.g_begin[g + 1]; ++t) {
-              mbar_wait(&w_empty[ws], wph ^ 1);
-              tma_load_2d_2sm(smem_w + ws * L::W_BYTES_PAD, &tmap_b, &w_full[ws], kb * BLOCK_K,
-                              hp.tap_k[t] * p.Cout + n0);
-              if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * L::W_BYTES);
-              else mbar_arrive_remote(&w_full[ws], 0);
-              if (++ws == hp.w_stages) { ws = 0; wph ^= 1; }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1 && leader) {
-    // =========================== MMA issuer (leader only) ===========================
-    constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
-    int as = 0, ws = 0;
-    uint32_t aph = 0, wph = 0;
-    int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      __syncwarp();
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-      uint32_t accum = 0;
-      for (int g = 0; g < hp.n_groups; ++g) {
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          if (lane == 0) {
-            mbar_wait(&a_full[as], aph);
-            const uint32_t sa = smem_u32(smem_a + as * hp.a_stage_bytes);
-            for (int t = hp.g_begin[g]; t < hp.g_begin[g + 1]; ++t) {
-              mbar_wait(&w_full[ws], wph);
-              tc_fence_after();
-              const uint32_t a_addr = sa + (uint32_t)hp.tap_roff[t] * SWZ;
-              uint64_t adesc = make_kmajor_desc(a_addr, SWZ);
-              if (hp.base_off_mode) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-              const uint64_t bdesc = make_kmajor_desc(smem_u32(smem_w + ws * L::W_BYTES_PAD), SWZ);
-#pragma unroll
-              for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-                umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, accum);
-                accum = 1;
-              }
-              umma_commit_2sm(&w_empty[ws]);
-              if (++ws == hp.w_stages) { ws = 0; wph ^= 1; }
-            }
-            umma_commit_2sm(&a_empty[as]);
-          } else {
-            // keep the ring counters of the idle lanes in step (they are only read by lane 0)
-            ws += hp.g_begin[g + 1] - hp.g_begin[g];
-            while (ws >= hp.w_stages) { ws -= hp.w_stages; wph ^= 1; }
-          }
-          if (++as == hp.a_stages) { as = 0; aph ^= 1; }
-          __syncwarp();
-        }
-      }
-      if (lane == 0) umma_commit_2sm(&tfull_bar[acc]);
-      __syncwarp();
-    }
-    if (it > 0 && lane == 0) {
-      const int last = it - 1;
-      mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);
-    }
-    __syncwarp();
-  } else if (warp >= 2) {
-    // =========================== epilogue (4 warps in each CTA) ===========================
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % p.n_nt;
-      const int mt = (tile / p.n_nt) * 2 + (int)rank;
-      const int lt = mt % p.n_lt;
-      const int b = mt / p.n_lt;
-      const int n0 = nt * BLOCK_N;
-      const int l = lt * BLOCK_M + row;
-      const bool valid = (mt < n_mt) && (b < p.B) && (l < p.Lout);
+      const bool valid = (mt < n_mt) && (b < p.B) && (l < p.Lout) && !(p.dbg & 1);
       const size_t orow = (size_t)b * p.out_rows + (size_t)l * p.out_row_stride + p.out_row_offset;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -786,101 +584,15 @@ static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
-  conv_tc2_kernel<BN, BK><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  TcParams q = p;
+  q.stages = L::STAGES;
+  {
+    const char *e = getenv("RAVE_TC_STAGES");
+    if (e && atoi(e) >= 2 && atoi(e) < L::STAGES) q.stages = atoi(e);
+  }
+  conv_tc2_kernel<BN, BK><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, q);
   RAVE_CHECK_LAUNCH("conv1d_tc(2cta)");
   return 0;
-}
-
-template <int BN, int BK>
-static int launch3(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, HaloPlan &hp, cudaStream_t stream) {
-  using L = SmemLayout3<BN, BK>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::TOTAL);
-    if (e != cudaSuccess) {
-      set_error("conv1d_tc(halo): cudaFuncSetAttribute(%d bytes): %s", L::TOTAL, cudaGetErrorString(e));
-      return 2;
-    }
-    attr = true;
-  }
-  // ring split: weights get up to 6 stages, activations the rest (each serves several taps)
-  hp.a_stage_bytes = (hp.rows * BK * 2 + 1023) / 1024 * 1024;
-  int ws = 6;
-  while (ws > 2 && L::RING_BYTES - ws * L::W_BYTES_PAD < 3 * hp.a_stage_bytes) --ws;
-  int as = (L::RING_BYTES - ws * L::W_BYTES_PAD) / hp.a_stage_bytes;
-  if (as > HALO_MAX_STAGES) as = HALO_MAX_STAGES;
-  if (as < 2) {
-    set_error("conv1d_tc(halo): activation stage of %d bytes does not fit", hp.a_stage_bytes);
-    return 1;
-  }
-  int wmax = (L::RING_BYTES - as * hp.a_stage_bytes) / L::W_BYTES_PAD;
-  if (wmax > HALO_MAX_STAGES) wmax = HALO_MAX_STAGES;
-  hp.a_stages = as;
-  hp.w_stages = wmax;
-  const int n_mp = (p.n_lt * p.n_bg + 1) / 2;
-  const int tiles = n_mp * p.n_nt;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int pairs = sms / 2;
-  if (pairs > tiles) pairs = tiles;
-  conv_tc3_kernel<BN, BK><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p, hp);
-  RAVE_CHECK_LAUNCH("conv1d_tc(halo)");
-  return 0;
-}
-
-template <int BK>
-static int dispatch_n3(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, HaloPlan &hp,
-                       cudaStream_t s) {
-  switch (bn) {
-    case 256: return launch3<256, BK>(ta, tb, p, hp, s);
-    case 192: return launch3<192, BK>(ta, tb, p, hp, s);
-    case 128: return launch3<128, BK>(ta, tb, p, hp, s);
-    case 96: return launch3<96, BK>(ta, tb, p, hp, s);
-    case 64: return launch3<64, BK>(ta, tb, p, hp, s);
-  }
-  set_error("conv1d_tc(halo): no kernel for BLOCK_N=%d", bn);
-  return 1;
-}
-
-// Phase groups of a conv: tap k reads input row (l + j_k) * stride + ph_k with k*dil - pad_l = j_k*stride + ph_k.
-// Returns false when the launch should use the per-tap kernels (no reuse, too many taps / groups, halo too tall).
-static bool build_halo_plan(const TcParams &p, HaloPlan &hp) {
-  if (p.K > HALO_MAX_TAPS || p.K < 2) return false;
-  int ph_of[HALO_MAX_TAPS], j_of[HALO_MAX_TAPS];
-  int groups = 0, gph[HALO_MAX_GROUPS], gj0[HALO_MAX_GROUPS], gcount[HALO_MAX_GROUPS];
-  for (int k = 0; k < p.K; ++k) {
-    const int off = k * p.dil - p.pad_l;
-    int j = off / p.stride, ph = off - j * p.stride;
-    if (ph < 0) { ph += p.stride; j -= 1; }
-    ph_of[k] = ph; j_of[k] = j;
-    int g = 0;
-    for (; g < groups; ++g) if (gph[g] == ph) break;
-    if (g == groups) {
-      if (groups == HALO_MAX_GROUPS) return false;
-      gph[g] = ph; gj0[g] = j; gcount[g] = 0; ++groups;
-    }
-    if (j < gj0[g]) gj0[g] = j;
-    ++gcount[g];
-  }
-  if (groups == p.K) return false;                 // every tap has its own phase: nothing to share
-  int halo = 0, n = 0;
-  hp.n_groups = groups;
-  for (int g = 0; g < groups; ++g) {
-    hp.g_ph[g] = gph[g]; hp.g_j0[g] = gj0[g]; hp.g_begin[g] = n;
-    for (int k = 0; k < p.K; ++k) {
-      if (ph_of[k] != gph[g]) continue;
-      hp.tap_k[n] = k;
-      hp.tap_roff[n] = j_of[k] - gj0[g];
-      if (hp.tap_roff[n] > halo) halo = hp.tap_roff[n];
-      ++n;
-    }
-  }
-  hp.g_begin[groups] = n;
-  if (halo > 64) return false;
-  hp.rows = BLOCK_M + halo;
-  return true;
 }
 
 template <int BK>
@@ -944,6 +656,12 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   RAVE_CHECK_ARG(enc, "conv1d_tc: cuTensorMapEncodeTiled not available");
 
   const int BK = pick_block_k(Cin);
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  {
+    const char *e = getenv("RAVE_TC_L2PROMO");
+    if (e) promo = atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : atoi(e) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                   : atoi(e) == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }
   TcParams p;
   p.B = B; p.Cin = Cin; p.Lin = Lin; p.Cout = Cout; p.Lout = Lout; p.K = K; p.stride = stride; p.dil = dil;
   p.pad_l = pad_l; p.act = act; p.slope = slope; p.bias = bias; p.res = res; p.out_f32 = out_f32;
@@ -954,6 +672,12 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   p.out_rows = out_rows > 0 ? out_rows : Lout;
   p.out_row_stride = out_row_stride > 0 ? out_row_stride : 1;
   p.out_row_offset = out_row_offset;
+  p.stages = 0;
+  p.dbg = 0;
+  {
+    const char *e = getenv("RAVE_TC_DBG");
+    if (e) p.dbg = atoi(e);
+  }
   int BL = 128;
   while (BL > Lout && BL > 8) BL >>= 1;   // power of two <= max(Lout, 8)
   p.BL = BL; p.BB = 128 / BL;
@@ -970,46 +694,32 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
     const char *e = getenv("RAVE_TC_2CTA");
     want2 = (e && e[0] == '0') ? 0 : 1;
   }
-  const bool use2 = want2 && BK == 64 && (BN % 32 == 0) && BN >= 64 && (long)p.n_lt * p.n_bg >= 2;
-  // halo variant (one activation stage per phase group): RAVE_TC_HALO=0 disables, =2 also sets the descriptor
-  // base-offset field (experiment); read on every call so tests can compare both paths in-process
-  HaloPlan hp;
-  bool use3 = false;
-  {
-    const char *e = getenv("RAVE_TC_HALO");
-    const int mode = e ? atoi(e) : 1;
-    if (mode && want2 && (BK == 64 || BK == 32) && (BN % 32 == 0) && BN >= 64 && p.BB == 1 &&
-        (long)p.n_lt * p.n_bg >= 2 && build_halo_plan(p, hp)) {
-      use3 = true;
-      hp.base_off_mode = mode == 2;
-    }
-  }
+  const bool use2 = want2 && (BK == 64 || BK == 32) && (BN % 32 == 0) && BN >= 64 && (long)p.n_lt * p.n_bg >= 2;
 
   // A: channel-last activations viewed as (c, phase, l/stride, b)
   CUtensorMap ta, tb;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)stride, (cuuint64_t)ceil_div(Lin, stride), (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * stride, (cuuint64_t)Cin * 2 * in_pitch};
-    cuuint32_t box[4] = {(cuuint32_t)BK, 1, (cuuint32_t)(use3 ? hp.rows : p.BL), (cuuint32_t)p.BB};
+    cuuint32_t box[4] = {(cuuint32_t)BK, 1, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(xa), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(BK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(BK * 2), promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map A encode failed (%d)", (int)r);
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)K * Cout};
     cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)((use2 || use3) ? BN / 2 : BN)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(use2 ? BN / 2 : BN)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(wt), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(BK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(BK * 2), promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map B encode failed (%d)", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (use3) return BK == 64 ? dispatch_n3<64>(BN, ta, tb, p, hp, s) : dispatch_n3<32>(BN, ta, tb, p, hp, s);
-  if (use2) return dispatch_n2<64>(BN, ta, tb, p, s);
+  if (use2) return BK == 64 ? dispatch_n2<64>(BN, ta, tb, p, s) : dispatch_n2<32>(BN, ta, tb, p, s);
   switch (BK) {
     case 64: return dispatch_n<64>(BN, ta, tb, p, s);
     case 32: return dispatch_n<32>(BN, ta, tb, p, s);
@@ -1112,52 +822,55 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constan
 
   if (my_chunks > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        const int off = k * p.dil - p.pad_l;
-        int j = off / p.stride;
-        int ph = off - j * p.stride;
-        if (ph < 0) { ph += p.stride; j -= 1; }
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int ch = ch_begin; ch < ch_end; ++ch) {
-          const int lt = ch % p.n_lt, bg = ch / p.n_lt;
-          const int l0 = lt * p.BL, b0 = bg * p.BB;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t *sa = smem + stage * L::STAGE_BYTES;
-          uint8_t *sb = sa + 2 * WG_SLAB;
+      // warp-uniform producer loop (see elect_one)
+      const int off = k * p.dil - p.pad_l;
+      int j = off / p.stride;
+      int ph = off - j * p.stride;
+      if (ph < 0) { ph += p.stride; j -= 1; }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int lt = ch % p.n_lt, bg = ch / p.n_lt;
+        const int l0 = lt * p.BL, b0 = bg * p.BB;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t *sa = smem + stage * L::STAGE_BYTES;
+        uint8_t *sb = sa + 2 * WG_SLAB;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], (2 + NS) * WG_SLAB);
           tma_load_4d(sa, &tmap_p, &full_bar[stage], m0, 0, l0, b0);
           tma_load_4d(sa + WG_SLAB, &tmap_p, &full_bar[stage], m0 + 64, 0, l0, b0);
 #pragma unroll
           for (int s = 0; s < NS; ++s)
             tma_load_4d(sb + s * WG_SLAB, &tmap_q, &full_bar[stage], n0 + 64 * s, ph, l0 + j, b0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
-      // bf16 x bf16 -> fp32, A and B both MN-major (bits 15 / 16)
+      // bf16 x bf16 -> fp32, A and B both MN-major (bits 15 / 16); warp-uniform issue loop
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N) | (1u << 15) | (1u << 16);
-      if (lane == 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int c = 0; c < my_chunks; ++c) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sb = sa + 2 * WG_SLAB;
-          const uint64_t adesc = make_mnmajor_desc(sa, WG_SLAB);
-          const uint64_t bdesc = make_mnmajor_desc(sb, WG_SLAB);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < my_chunks; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+        const uint64_t adesc = make_mnmajor_desc(sa, WG_SLAB);
+        const uint64_t bdesc = make_mnmajor_desc(sa + 2 * WG_SLAB, WG_SLAB);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < WG_ROWS / 16; ++kk) {
             // 16 reduction rows = 2048 bytes -> +128 in the (addr >> 4) field
-            umma_f16(tmem_base, adesc + 128 * kk, bdesc + 128 * kk, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+            umma_f16(tmem_u, adesc + 128 * kk, bdesc + 128 * kk, idesc, (c > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (c == my_chunks - 1) umma_commit(tfull_bar);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
     } else {
       const int quad = warp & 3;
       const int m = m0 + quad * 32 + lane;

@@ -55,6 +55,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp.  The producer / MMA-issue loops run WARP-UNIFORM (all 32 lanes execute the
+// loop, only the UTMALDG / UTCHMMA / UTCBAR instructions are predicated on the elected lane): stage indices, shared
+// memory addresses and descriptors then live in uniform registers.  Inside an `if (lane == 0)` region the compiler
+// treats them as per-thread values and wraps every UTC/UTMA instruction in an ELECT + R2UR.BROADCAST waterfall loop
+// (~25 instructions per MMA: the issue thread, not the tensor pipe, bounded the small-N / BLOCK_K=32 layers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
