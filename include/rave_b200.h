@@ -193,6 +193,14 @@ int rave_gather_c1(const float *P, float *dx, int R, int x_pitch, int Lin, int L
 int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, int pitch, int C, float slope, void *stream);
 int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_bf16, int Bh, int L, int pitch, int C,
                  float slope, void *stream);
+/* Discriminator score tail (replaces, per ConvNet, the scalar arithmetic of rave/model.py:348-379 with
+ * core.hinge_gan, rave/core.py:151-155, and core.mean_difference, 236-252, on the score map).
+ * score: channel-last fp32 [2*Bh][pitch][C], channel 0 = the score, real half first.
+ * stats (pre-zeroed) += { sum|s_r-s_f|, sum|s_r|, sum relu(1-s_r), sum relu(1+s_f), sum s_r, sum s_f }.
+ * rave_score_grad writes d(sum_i dstats[i]*stats[i])/ds as the bf16 gradient stream [2*Bh][pitch][C]. */
+int rave_score_stats(const float *score, float *stats, int Bh, int L, int pitch, int C, void *stream);
+int rave_score_grad(const float *score, const float *dstats, void *gout_bf16, int Bh, int L, int pitch, int C,
+                    void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * fused spectral distance (replaces the elementwise tail of core.AudioDistanceV1, rave/core.py:322-344,

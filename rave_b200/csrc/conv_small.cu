@@ -443,6 +443,106 @@ extern "C" int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Discriminator score tail (rave/model.py:348-379 with core.hinge_gan / core.mean_difference): every scalar the
+// training step derives from the score map s = last conv output (channel 0 of the channel-last fp32 tensor
+// [2*Bh][pitch][C], real half first) comes from six sums, produced by one launch instead of ~40 ATen launches
+// per ConvNet (and as many again in the backward):
+//   stats[0] = sum |s_r - s_f|    stats[1] = sum |s_r|          (score as the last feature-matching term)
+//   stats[2] = sum relu(1 - s_r)  stats[3] = sum relu(1 + s_f)  (hinge discriminator loss)
+//   stats[4] = sum s_r            stats[5] = sum s_f            (adversarial loss, pred_real / pred_fake)
+// score_grad_kernel is the gradient of sum_i d[i] * stats[i] with respect to s, written as the bf16 gradient
+// stream of the last conv (other channels and slack rows zero).
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+__global__ void __launch_bounds__(256)
+score_stats_kernel(const float *__restrict__ s, float *__restrict__ stats, int Bh, int L, int pitch, int C) {
+  __shared__ float red[6][8];
+  const long total = (long)Bh * L;
+  const size_t half = (size_t)Bh * pitch * C;
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int l = (int)(i % L);
+    const int b = (int)(i / L);
+    const size_t o = ((size_t)b * pitch + l) * C;
+    const float sr = s[o], sf = s[o + half];
+    a[0] += fabsf(sr - sf);
+    a[1] += fabsf(sr);
+    a[2] += fmaxf(1.f - sr, 0.f);
+    a[3] += fmaxf(1.f + sf, 0.f);
+    a[4] += sr;
+    a[5] += sf;
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+    if (lane == 0) red[j][wid] = a[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    atomicAdd(stats + threadIdx.x, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+score_grad_kernel(const float *__restrict__ s, const float *__restrict__ d, __nv_bfloat16 *__restrict__ gout,
+                  int Bh, int L, int pitch, int C) {
+  const float d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3], d4 = d[4], d5 = d[5];
+  const long total = (long)Bh * pitch;
+  const size_t half = (size_t)Bh * pitch * C;
+  const int vecs = C >> 3;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int l = (int)(i % pitch);
+    const size_t o = (size_t)i * C;
+    float gr = 0.f, gf = 0.f;
+    if (l < L) {
+      const float sr = s[o], sf = s[o + half];
+      const float sd = sr > sf ? 1.f : (sr < sf ? -1.f : 0.f);
+      const float sa = sr > 0.f ? 1.f : (sr < 0.f ? -1.f : 0.f);
+      gr = d0 * sd + d1 * sa - (sr < 1.f ? d2 : 0.f) + d4;
+      gf = -d0 * sd + (sf > -1.f ? d3 : 0.f) + d5;
+    }
+    uint4 *pr = reinterpret_cast<uint4 *>(gout + o);
+    uint4 *pf = reinterpret_cast<uint4 *>(gout + o + half);
+    pr[0] = make_uint4(pack_bf16(gr, 0.f), 0u, 0u, 0u);
+    pf[0] = make_uint4(pack_bf16(gf, 0.f), 0u, 0u, 0u);
+    for (int v = 1; v < vecs; ++v) {
+      pr[v] = make_uint4(0u, 0u, 0u, 0u);
+      pf[v] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_score_stats(const float *score, float *stats, int Bh, int L, int pitch, int C, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(score && stats && Bh > 0 && L > 0 && pitch >= L && C > 0, "score_stats: bad argument");
+  long blocks = ((long)Bh * L + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  score_stats_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(score, stats, Bh, L, pitch, C);
+  RAVE_CHECK_LAUNCH("score_stats");
+  return 0;
+}
+
+extern "C" int rave_score_grad(const float *score, const float *dstats, void *gout_bf16, int Bh, int L, int pitch,
+                               int C, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(score && dstats && gout_bf16 && Bh > 0 && L > 0 && pitch >= L && C > 0 && C % 8 == 0,
+                 "score_grad: bad argument");
+  long blocks = ((long)Bh * pitch + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  score_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(score, dstats, (__nv_bfloat16 *)gout_bf16, Bh, L,
+                                                                   pitch, C);
+  RAVE_CHECK_LAUNCH("score_grad");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cin = 1 first layer on the tensor-core kernels: the K (<= 16) taps become 16 "channels" of a tiny
 // im2col, X[r][l][k] = bf16(x[r][l*stride + k - pad_l]) (33 MB for the 64 x 16384-row MSD input), so
 //   forward : conv_tc (Cin = 16, one tap)            out[r][l][co] = sum_k X[r][l][k] w[co][k]

@@ -109,12 +109,13 @@ class ConvNet(nn.Module):
 
     def forward_fm(self, x):
         """Fused feature-matching path (bf16 engine): x = cat([real, fake]) -> (stats [n-1, 2], counts,
-        score) with stats[i] = (sum|h_r - h_f|, sum|h_r|) of hidden feature i, counts[i] = its number of
-        elements per half, score = the last conv's output in the reference's shape."""
+        score, score_stats [3, 2], n_score) with stats[i] = (sum|h_r - h_f|, sum|h_r|) of hidden feature i,
+        counts[i] = its number of elements per half, score = the last conv's output in the reference's shape,
+        score_stats = the six sums of the score tail (engine.TcChainFn), n_score = score elements per half."""
         from . import engine
         specs = self._tc_specs()
         xa, B, W, L = self._chain_input(x, specs)
-        stats, last = engine.run_chain(xa, specs, L, fm=True)
+        stats, score_stats, last = engine.run_chain(xa, specs, L, fm=True)
         lens = engine.chain_lengths(specs, L)
         counts = [(B // 2) * W * Lo * s.Cout for s, Lo in zip(specs[:-1], lens[:-1])]
         o = last[:, :lens[-1], :specs[-1].Cout]
@@ -122,7 +123,10 @@ class ConvNet(nn.Module):
             score = o.permute(0, 2, 1)
         else:
             score = o.reshape(B, W, lens[-1], specs[-1].Cout).permute(0, 3, 2, 1)
-        return stats, counts, score
+        # score_stats [3, 2] (engine.TcChainFn) is meaningful when the score has one channel; n_score = its
+        # number of elements per half
+        n_score = (B // 2) * W * lens[-1] if specs[-1].Cout == 1 else 0
+        return stats, counts, score, score_stats, n_score
 
     def _forward_tc(self, x, specs):
         """bf16 tensor-core path: the whole ConvNet as one chain in channel-last layout; features come

@@ -307,8 +307,13 @@ class TcChainFn(torch.autograd.Function):
           of the audio).
     fm  : False -> returns one fp32 channel-last tensor per `is_output` layer;
           True  -> discriminator feature-matching mode: the batch is [real; fake]; returns
-                   (stats [n-1, 2] = per hidden layer (sum|h_r-h_f|, sum|h_r|), last layer fp32 output).
-                   Hidden features never reach HBM in fp32."""
+                   (stats [n-1, 2] = per hidden layer (sum|h_r-h_f|, sum|h_r|),
+                    score_stats [3, 2] = ((sum|s_r-s_f|, sum|s_r|), (sum relu(1-s_r), sum relu(1+s_f)),
+                                          (sum s_r, sum s_f)) of channel 0 of the last layer -- zeros unless that
+                                          layer has one output channel,
+                    last layer fp32 output).
+                   Hidden features never reach HBM in fp32; the losses are assembled from the two small stats
+                   tensors (RAVE._fused_feature_matching), whose gradients drive fm_grad / score_grad here."""
 
     @staticmethod
     def forward(ctx, x_in, specs, L0, fm, *flat):
@@ -395,6 +400,13 @@ class TcChainFn(torch.autograd.Function):
             if (s.is_output and not fm) or (fm and nxt is None):
                 outputs.append(out_f32)
             a = out_act
+        score_stats = None
+        if fm:
+            score_stats = torch.zeros(3, 2, dtype=torch.float32, device=dev)
+            ctx.score_f32 = None
+            if specs[-1].Cout == 1:
+                ops.score_stats(outputs[-1], score_stats, lens[-1])
+                ctx.score_f32 = outputs[-1]
         ctx.specs = specs
         ctx.acts = acts
         ctx.prepared = prepared
@@ -405,7 +417,7 @@ class TcChainFn(torch.autograd.Function):
         ctx.x_requires_grad = x_in.requires_grad
         ctx.out_index = [i for i, s in enumerate(specs) if s.is_output]
         if fm:
-            return (stats,) + tuple(outputs)
+            return (stats, score_stats) + tuple(outputs)
         return tuple(outputs)
 
     @staticmethod
@@ -420,8 +432,11 @@ class TcChainFn(torch.autograd.Function):
             dstats = gouts[0]
             if dstats is not None:
                 dstats = dstats.contiguous()
-            if gouts[1] is not None:
-                ext[n - 1] = gouts[1].to(ACT_DTYPE).contiguous()
+            if gouts[2] is not None:
+                ext[n - 1] = gouts[2].to(ACT_DTYPE).contiguous()
+            if gouts[1] is not None and ctx.score_f32 is not None:
+                e = ops.score_grad(ctx.score_f32, gouts[1].to(torch.float32).contiguous(), ctx.lens[-1])
+                ext[n - 1] = e if (n - 1) not in ext else ext[n - 1] + e
         else:
             for i, g in zip(ctx.out_index, gouts):
                 if g is not None:
@@ -517,7 +532,8 @@ class TcChainFn(torch.autograd.Function):
 def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None, fm: bool = False):
     """x_cl_bf16: [B, pitch, Cin(+pad)] (rows beyond the true length L0 must be zero), or raw fp32 rows
     [B, pitch] for a Cin = 1 first layer.  Returns one fp32 channel-last tensor [B, pitch_i, Cout_i(+pad)]
-    per output layer (slice [:, :L_i, :Cout_i]); with fm=True: (stats [n-1, 2], last layer output)."""
+    per output layer (slice [:, :L_i, :Cout_i]); with fm=True: (stats [n-1, 2], score_stats [3, 2], last layer
+    output)."""
     flat = []
     for s in specs:
         v, g, b = _layer_params(s)

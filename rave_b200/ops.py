@@ -499,6 +499,21 @@ def fm_grad(a_cl, dstats_row, L, slope):
     return g
 
 
+def score_stats(score_cl, stats6, L):
+    """stats6[0:6] += the six sums of the discriminator score tail (channel 0 of the fp32 channel-last score
+    tensor [2*Bh, pitch, C], real half first): |s_r-s_f|, |s_r|, relu(1-s_r), relu(1+s_f), s_r, s_f."""
+    B2, pitch, C = score_cl.shape
+    call("rave_score_stats", ptr(score_cl), stats6.data_ptr(), B2 // 2, L, pitch, C, stream_ptr())
+
+
+def score_grad(score_cl, dstats6, L):
+    """bf16 gradient stream [2*Bh, pitch, C] of sum_i dstats6[i] * stats6[i] with respect to the score."""
+    B2, pitch, C = score_cl.shape
+    g = torch.empty(B2, pitch, C, dtype=torch.bfloat16, device=score_cl.device)
+    call("rave_score_grad", ptr(score_cl), dstats6.data_ptr(), ptr(g), B2 // 2, L, pitch, C, stream_ptr())
+    return g
+
+
 def weight_norm_raw(v, g):
     """(w, norm) = (g v/||v||, ||v||) without autograd (engine-internal)."""
     v, g = _f32c(v), _f32c(g)

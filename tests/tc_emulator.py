@@ -225,6 +225,29 @@ def fm_grad(a_cl, dstats_row, L, slope):
     return _bf16(g)
 
 
+def score_stats(score_cl, stats6, L):
+    B2 = score_cl.shape[0]
+    s = score_cl[:, :L, 0].float()
+    sr, sf = s[:B2 // 2], s[B2 // 2:]
+    stats6.view(-1).add_(torch.stack([(sr - sf).abs().sum(), sr.abs().sum(), torch.relu(1 - sr).sum(),
+                           torch.relu(1 + sf).sum(), sr.sum(), sf.sum()]))
+
+
+def score_grad(score_cl, dstats6, L):
+    B2, pitch, C = score_cl.shape
+    s = score_cl[:, :L, 0].float()
+    sr, sf = s[:B2 // 2], s[B2 // 2:]
+    d = dstats6.float().reshape(-1)
+    sd = torch.sign(sr - sf)
+    gr = d[0] * sd + d[1] * torch.sign(sr) - d[2] * (sr < 1).float() + d[4]
+    gf = -d[0] * sd + d[3] * (sf > -1).float() + d[5]
+    g = torch.zeros(B2, pitch, C, dtype=torch.float32)
+    g[:B2 // 2, :L, 0] = gr
+    g[B2 // 2:, :L, 0] = gf
+    from rave_b200 import engine
+    return g.to(engine.ACT_DTYPE)
+
+
 def weight_prep_tc_multi(items):
     return [weight_prep_tc(*it) for it in items]
 
@@ -237,5 +260,5 @@ def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
                  "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1", "weight_prep_tc_multi",
-                 "weight_norm_bwd_multi"):
+                 "weight_norm_bwd_multi", "score_stats", "score_grad"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -152,6 +152,7 @@ def test_fused_feature_matching_vs_oracle(emu):
     h.feature_matching_fun = partial(core.mean_difference, norm="L1", relative=True)
     h.num_skipped_features = 1
     h.gan_loss = core.hinge_gan
+    h._fused_tail = lambda nets, relative, skip: RAVE._fused_tail(h, nets, relative, skip)
     disc.supports_fused_fm = lambda xy: True            # (the real check also demands CUDA + bf16 mode)
     xe = x.clone().requires_grad_(True)
     fm, ld, la, pr, pf = RAVE._fused_feature_matching(h, xe)

@@ -184,3 +184,24 @@ def test_multi_tensor_weight_kernels_match_single():
         assert (dg1 is None) == (dg2 is None)
         if dg1 is not None:
             assert torch.allclose(dg1, dg2, rtol=1e-5, atol=1e-6)
+
+
+def test_score_tail_kernels_vs_emulator():
+    """rave_score_stats / rave_score_grad (discriminator score tail) against the torch emulation."""
+    from rave_b200 import ops
+    from tests import tc_emulator as E
+    g = torch.Generator().manual_seed(11)
+    for (B2, pitch, L, C) in [(8, 24, 24, 16), (64, 260, 257, 16), (6, 96, 94, 16)]:
+        s = torch.randn(B2, pitch, C, generator=g) * 1.5
+        st_ref = torch.zeros(3, 2)
+        E.score_stats(s, st_ref, L)
+        st = torch.zeros(3, 2, device="cuda")
+        ops.score_stats(s.cuda(), st, L)
+        torch.cuda.synchronize()
+        assert rel_l2(st, st_ref) < 1e-5
+        d = torch.randn(3, 2, generator=g)
+        g_ref = E.score_grad(s, d, L).float()
+        g_gpu = ops.score_grad(s.cuda(), d.cuda(), L)
+        torch.cuda.synchronize()
+        assert g_gpu.dtype == torch.bfloat16 and g_gpu.shape == (B2, pitch, C)
+        assert torch.equal(g_gpu.float().cpu(), g_ref.bfloat16().float())
