@@ -205,12 +205,14 @@ int rave_score_grad(const float *score, const float *dstats, void *gout_bf16, in
 /* ---------------------------------------------------------------------------------------------
  * fused spectral distance (replaces the elementwise tail of core.AudioDistanceV1, rave/core.py:322-344,
  * and mean_difference, 236-252, for one STFT scale).  X, Y: complex64 spectrograms (interleaved re/im), n
- * complex elements.  stats (pre-zeroed) += { sum(|X|-|Y|)^2, sum|X|^2, sum|log(|X|+eps)-log(|Y|+eps)| }.
- * grad: dY = (coef[0]*-2(|X|-|Y|) - coef[1]*sgn(logX-logY)/(|Y|+eps)) * Y/|Y|, coef = 2 device floats.
+ * complex elements.  stats: 5 pre-zeroed floats; [0..2] += { sum(|X|-|Y|)^2, sum|X|^2,
+ * sum|log(|X|+eps)-log(|Y|+eps)| }, [3] is a block ticket, [4] = the distance s0/s1 + s2/n (written by the last
+ * block).  grad: dY = (c_lin*-2(|X|-|Y|) - c_log*sgn(logX-logY)/(|Y|+eps)) * Y/|Y| with c_lin = g/stats[1],
+ * c_log = g/n and g = *gup the upstream gradient of the distance (device float).
  * ------------------------------------------------------------------------------------------- */
 int rave_spectral_stats(const void *X_c64, const void *Y_c64, float *stats, long n, float eps, void *stream);
-int rave_spectral_grad(const void *X_c64, const void *Y_c64, void *dY_c64, const float *coef, long n, float eps,
-                       void *stream);
+int rave_spectral_grad(const void *X_c64, const void *Y_c64, void *dY_c64, const float *stats, const float *gup,
+                       long n, float eps, void *stream);
 
 /* fused weight preparation for the engine: v [C0][C1][K] fp32 (+ weight-norm g [C0]; norm [C0] is written)
  *   outA[t][c0][c1] = bf16(w[c0][c1][tapsA[t]]), dims [nA][C0p][C1p]  (padded region zero)

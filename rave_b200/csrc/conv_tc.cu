@@ -329,8 +329,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // =============================================================================================
 template <int BLOCK_N, int BLOCK_K>
 struct SmemLayout2 {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;          // this CTA's half of the weight tile
+  // One pipeline stage always carries 64 reduction channels' worth of operands: UNITS = 64 / BLOCK_K
+  // (tap, channel-block) units, each with its own TMA box pair and BLOCK_K/16 MMAs, behind ONE barrier round
+  // trip -- a 32-channel block alone is only 2 MMAs (~190 clk at N = 192), less than the round trip costs.
+  static constexpr int UNITS = 64 / BLOCK_K;
+  static constexpr int A_UNIT = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_UNIT = (BLOCK_N / 2) * BLOCK_K * 2;           // this CTA's half of the weight tile
+  static constexpr int A_BYTES = UNITS * A_UNIT;
+  static constexpr int B_BYTES = UNITS * B_UNIT;
   static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
   static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
@@ -345,6 +351,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const TcParams p) {
   using L = SmemLayout2<BLOCK_N, BLOCK_K>;
   constexpr int STAGES = L::STAGES;
+  constexpr int UNITS = L::UNITS;
   constexpr int SWZ = BLOCK_K * 2;
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
                                  : (ACC_STAGES * BLOCK_N <= 128) ? 128 : (ACC_STAGES * BLOCK_N <= 256) ? 256 : 512;
@@ -393,7 +400,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // =========================== TMA producer (both CTAs; warp-uniform loop) ===========================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = 2 * (((p.dbg & 2) ? 0 : L::A_BYTES) + ((p.dbg & 4) ? 0 : L::B_BYTES));
+    const uint32_t unit_tx = 2 * (((p.dbg & 2) ? 0 : L::A_UNIT) + ((p.dbg & 4) ? 0 : L::B_UNIT));
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int nt = tile % p.n_nt;
       const int mt = (tile / p.n_nt) * 2 + (int)rank;      // this CTA's M tile (may be >= n_mt: zero-filled)
@@ -402,24 +409,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int l0 = lt * p.BL;
       const int b0 = bg * p.BB;
       const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
-      for (int k = 0; k < p.K; ++k) {
-        const int off = k * p.dil - p.pad_l;
-        int j = off / p.stride;
-        int ph = off - j * p.stride;
-        if (ph < 0) { ph += p.stride; j -= 1; }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t *sa = smem + stage * L::STAGE_BYTES;
-          uint8_t *sb = sa + L::A_BYTES;
-          if (elect_one()) {
-            if (!(p.dbg & 2)) tma_load_4d_2sm(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
-            if (!(p.dbg & 4)) tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            else mbar_arrive_remote(&full_bar[stage], 0);
+      for (int u0 = 0; u0 < kblocks; u0 += UNITS) {
+        const int nu = min(UNITS, kblocks - u0);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t *sa = smem + stage * L::STAGE_BYTES;
+        uint8_t *sb = sa + L::A_BYTES;
+        if (elect_one()) {
+#pragma unroll
+          for (int u = 0; u < UNITS; ++u) {
+            if (u < nu) {
+              const int k = (u0 + u) / p.num_kb, kb = (u0 + u) - k * p.num_kb;
+              // input row = l*stride + k*dil - pad_l = (l + j)*stride + ph
+              const int off = k * p.dil - p.pad_l;
+              int j = off / p.stride;
+              int ph = off - j * p.stride;
+              if (ph < 0) { ph += p.stride; j -= 1; }
+              if (!(p.dbg & 2))
+                tma_load_4d_2sm(sa + u * L::A_UNIT, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
+              if (!(p.dbg & 4))
+                tma_load_2d_2sm(sb + u * L::B_UNIT, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
+            }
           }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], unit_tx * nu);
+          else mbar_arrive_remote(&full_bar[stage], 0);
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && leader) {
@@ -436,18 +451,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + acc * BLOCK_N;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int u0 = 0; u0 < kblocks; u0 += UNITS) {
+        const int nu = min(UNITS, kblocks - u0);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-        const uint64_t adesc = make_kmajor_desc(sa, SWZ);
-        const uint64_t bdesc = make_kmajor_desc(sa + L::A_BYTES, SWZ);
+        const uint32_t sb = sa + L::A_BYTES;
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BLOCK_K / 16; ++kk)
-            umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          for (int u = 0; u < UNITS; ++u) {
+            if (u < nu) {
+              const uint64_t adesc = make_kmajor_desc(sa + u * L::A_UNIT, SWZ);
+              const uint64_t bdesc = make_kmajor_desc(sb + u * L::B_UNIT, SWZ);
+#pragma unroll
+              for (int kk = 0; kk < BLOCK_K / 16; ++kk)
+                umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (u0 > 0 || u > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
           umma_commit_2sm(&empty_bar[stage]);
-          if (kb == kblocks - 1) umma_commit_2sm(&tfull_bar[acc]);
+          if (u0 + UNITS >= kblocks) umma_commit_2sm(&tfull_bar[acc]);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -656,7 +678,9 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   RAVE_CHECK_ARG(enc, "conv1d_tc: cuTensorMapEncodeTiled not available");
 
   const int BK = pick_block_k(Cin);
-  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  // 256-byte L2 promotion over-fetches when a TMA row is a 64-byte (or shorter) span of a 192-byte channel row
+  // (measured on the Cin = 96 layers: 209.6 -> 184.7 us); neutral to slightly positive for 128-byte spans.
+  CUtensorMapL2promotion promo = BK == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
   {
     const char *e = getenv("RAVE_TC_L2PROMO");
     if (e) promo = atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : atoi(e) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
@@ -694,7 +718,7 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
     const char *e = getenv("RAVE_TC_2CTA");
     want2 = (e && e[0] == '0') ? 0 : 1;
   }
-  const bool use2 = want2 && (BK == 64 || BK == 32) && (BN % 32 == 0) && BN >= 64 && (long)p.n_lt * p.n_bg >= 2;
+  const bool use2 = want2 && (BN % 32 == 0) && BN >= 64 && (long)p.n_lt * p.n_bg >= 2;
 
   // A: channel-last activations viewed as (c, phase, l/stride, b)
   CUtensorMap ta, tb;
@@ -719,7 +743,9 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map B encode failed (%d)", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (use2) return BK == 64 ? dispatch_n2<64>(BN, ta, tb, p, s) : dispatch_n2<32>(BN, ta, tb, p, s);
+  if (use2)
+    return BK == 64 ? dispatch_n2<64>(BN, ta, tb, p, s) : BK == 32 ? dispatch_n2<32>(BN, ta, tb, p, s)
+                                                                   : dispatch_n2<16>(BN, ta, tb, p, s);
   switch (BK) {
     case 64: return dispatch_n<64>(BN, ta, tb, p, s);
     case 32: return dispatch_n<32>(BN, ta, tb, p, s);

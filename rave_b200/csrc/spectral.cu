@@ -2,8 +2,11 @@
 // core.AudioDistanceV1 (rave/core.py:322-344) + mean_difference (236-252) applied to the complex STFTs of
 // the input (X) and of the reconstruction (Y), one scale per launch:
 //     lin = mean((|X|-|Y|)^2) / mean(|X|^2)          log = mean(| log(|X|+eps) - log(|Y|+eps) |)
-// forward : stats[0] += sum (|X|-|Y|)^2, stats[1] += sum |X|^2, stats[2] += sum |log(|X|+eps) - log(|Y|+eps)|
-// backward: dY = ( c_lin * -2 (|X|-|Y|) + c_log * -sgn(logX - logY) / (|Y|+eps) ) * Y/|Y|
+// forward : stats[0] += sum (|X|-|Y|)^2, stats[1] += sum |X|^2, stats[2] += sum |log(|X|+eps) - log(|Y|+eps)|;
+//           the last block to finish (ticket in stats[3]) writes the distance stats[4] = s0/s1 + s2/n, so the
+//           scalar tail costs no extra launches
+// backward: dY = ( c_lin * -2 (|X|-|Y|) + c_log * -sgn(logX - logY) / (|Y|+eps) ) * Y/|Y|, c_lin = g/s1, c_log = g/n
+//           with the upstream gradient g read from device memory
 //           (PyTorch's convention for the gradient of a real loss w.r.t. a complex tensor through abs()).
 // Replaces ~14 ATen elementwise/reduce kernels per scale forward and ~25 backward with one kernel each.
 #include "common.cuh"
@@ -37,13 +40,24 @@ spectral_stats_kernel(const float2 *__restrict__ X, const float2 *__restrict__ Y
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
     atomicAdd(stats + threadIdx.x, t);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(stats + 3), 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      const float s0 = atomicAdd(stats, 0.f), s1 = atomicAdd(stats + 1, 0.f), s2 = atomicAdd(stats + 2, 0.f);
+      stats[4] = s0 / s1 + s2 / (float)n;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256)
 spectral_grad_kernel(const float2 *__restrict__ X, const float2 *__restrict__ Y, float2 *__restrict__ dY,
-                     const float *__restrict__ coef, long n, float eps) {
-  const float c_lin = coef[0], c_log = coef[1];
+                     const float *__restrict__ stats, const float *__restrict__ gup, long n, float eps) {
+  const float g = gup[0];
+  const float c_lin = g / stats[1], c_log = g / (float)n;
   for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
     const float2 x = X[i], y = Y[i];
     const float ax = sqrtf(x.x * x.x + x.y * x.y);
@@ -69,14 +83,14 @@ extern "C" int rave_spectral_stats(const void *X, const void *Y, float *stats, l
   return 0;
 }
 
-extern "C" int rave_spectral_grad(const void *X, const void *Y, void *dY, const float *coef, long n, float eps,
-                                  void *stream) {
+extern "C" int rave_spectral_grad(const void *X, const void *Y, void *dY, const float *stats, const float *gup, long n,
+                                  float eps, void *stream) {
   using namespace rave;
-  RAVE_CHECK_ARG(X && Y && dY && coef && n > 0, "spectral_grad: bad argument");
+  RAVE_CHECK_ARG(X && Y && dY && stats && gup && n > 0, "spectral_grad: bad argument");
   long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   spectral_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)X, (const float2 *)Y,
-                                                                      (float2 *)dY, coef, n, eps);
+                                                                      (float2 *)dY, stats, gup, n, eps);
   RAVE_CHECK_LAUNCH("spectral_grad");
   return 0;
 }

@@ -30,6 +30,9 @@ _state = {"precision": "fp32", "prep_epoch": 0}
 ACT_DTYPE = torch.bfloat16   # storage type of operand / gradient streams (tests may widen it)
 
 
+C1_GROUP = 4       # output positions per tensor-core row of a Cin = 1 first layer (see TcChainFn.forward)
+
+
 def set_precision(mode: str) -> None:
     """'fp32' : CUDA-core parity kernels ([B,C,L] fp32, per-layer autograd);
     'bf16' : tcgen05 engine (bf16 operands, fp32 accumulate) for every chain it supports."""
@@ -368,15 +371,33 @@ class TcChainFn(torch.autograd.Function):
                         t[:, Lout:].zero_()
             acts.append(a)
             if use_c1:
-                # Cin = 1: the K taps become the 16 "channels" of a tiny im2col, then one tcgen05 launch
+                # Cin = 1: the K taps become the 16 "channels" of a tiny im2col X[r][l][k].  Four consecutive
+                # positions are then read as ONE 64-channel row (X viewed as [R][L/4][64], 128-byte TMA rows
+                # instead of 32-byte ones) against the block-diagonal weight kron(I4, w): the output row holds
+                # the 4 x Cout results of those positions, i.e. the same bytes as out[r][4*l4 + p][co].
                 w_eff = ops.weight_norm_raw(v.detach(), g.detach())[0] if g is not None else v.detach()
                 w_ck = nn.functional.pad(w_eff.reshape(s.Cout, s.K), (0, 16 - s.K, 0, s.cout_pad))   # [Cout_p, 16]
-                ctx.c1_wt_dgrad = w_ck.t().contiguous().to(ACT_DTYPE).unsqueeze(0)                  # [1][16][Cout_p]
-                X = ops.im2col_c1(a, Lin, Lout, Lout, s.K, s.stride, s.pad[0])
+                G = C1_GROUP if (pitch % C1_GROUP == 0) else 1
+                Xp = (Lout + G - 1) // G * G
+                X = ops.im2col_c1(a, Lin, Lout, Xp, s.K, s.stride, s.pad[0])
                 ctx.c1_X = X
-                ops.conv1d_tc(X, w_ck.to(ACT_DTYPE).unsqueeze(0).contiguous(), bias_p, None, 1, 1, (0, 0), act_code,
-                              act_slope, want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act,
-                              Lout=Lout, Lin=Lout, out_rows=pitch)
+                ctx.c1_group = G
+                if G > 1:
+                    eye = torch.eye(G, dtype=w_ck.dtype, device=dev)
+                    w_blk = (eye[:, None, :, None] * w_ck[None, :, None, :]).reshape(G * cout_p, G * 16)
+                else:
+                    w_blk = w_ck
+                ctx.c1_wt_dgrad = w_blk.t().contiguous().to(ACT_DTYPE).unsqueeze(0)       # [1][G*16][G*Cout_p]
+                bias_g = bias_p.detach().repeat(G) if (bias_p is not None and G > 1) else bias_p
+                ops.conv1d_tc(X.view(B, Xp // G, G * 16), w_blk.to(ACT_DTYPE).unsqueeze(0).contiguous(), bias_g,
+                              None, 1, 1, (0, 0), act_code, act_slope, want_f32=False, want_act=False,
+                              out_f32=out_f32.view(B, pitch // G, G * cout_p) if out_f32 is not None else None,
+                              out_act=out_act.view(B, pitch // G, G * cout_p) if out_act is not None else None,
+                              Lout=Xp // G, Lin=Xp // G, out_rows=pitch // G)
+                if Xp > Lout:            # positions Lout .. Xp-1 of the last group saw zero taps but got the bias
+                    for t in (out_f32, out_act):
+                        if t is not None:
+                            t[:, Lout:Xp].zero_()
             elif s.kind == "conv":
                 ops.conv1d_tc(a, pw.fwd, bias_p, res, s.stride, s.dil, s.pad, act_code, act_slope,
                               want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act, Lout=Lout,
@@ -491,8 +512,18 @@ class TcChainFn(torch.autograd.Function):
             dact = a_in if s.pre_act == ops.ACT_LEAKY else None
             in_pitch = a_in.shape[1]
             if use_c1:                  # P[r][l][k] = <g[r][l][:], w[:][k]> on the tensor cores, then a gather
-                P, _ = ops.conv1d_tc(g, ctx.c1_wt_dgrad, None, None, 1, 1, (0, 0), ops.ACT_NONE, 0.0, want_f32=True,
-                                     want_act=False, Lout=Lout, Lin=Lout)
+                G = ctx.c1_group
+                gpitch = g.shape[1]
+                if G > 1 and gpitch % G == 0:
+                    # same 4-positions-per-row view as the forward (slack rows of g are zero)
+                    P, _ = ops.conv1d_tc(g.view(B, gpitch // G, G * cout_p), ctx.c1_wt_dgrad, None, None, 1, 1, (0, 0),
+                                         ops.ACT_NONE, 0.0, want_f32=True, want_act=False, Lout=gpitch // G,
+                                         Lin=gpitch // G)
+                    P = P.view(B, gpitch, 16)
+                else:
+                    wt_d = ctx.c1_wt_dgrad if G == 1 else ctx.c1_wt_dgrad[:, :16, :cout_p].contiguous()
+                    P, _ = ops.conv1d_tc(g, wt_d, None, None, 1, 1, (0, 0), ops.ACT_NONE, 0.0, want_f32=True,
+                                         want_act=False, Lout=Lout, Lin=Lout)
                 gx = ops.gather_c1(P, in_pitch, Lin, Lout, s.K, s.stride, s.pad[0])
                 break
             gp = torch.empty(B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)

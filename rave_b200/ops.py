@@ -585,21 +585,25 @@ class SpectralDistanceFn(torch.autograd.Function):
             X, Y = X.contiguous(), Y.contiguous()
             ctx.transposed = False
         n = X.numel()
-        stats = torch.zeros(3, dtype=torch.float32, device=X.device)
+        stats = torch.zeros(5, dtype=torch.float32, device=X.device)     # 3 sums, block ticket, distance
         call("rave_spectral_stats", ptr(torch.view_as_real(X)), ptr(torch.view_as_real(Y)), ptr(stats), n,
              float(eps), stream_ptr())
-        ctx.save_for_backward(X, Y, stats)
+        ctx.save_for_backward(X, Y)
+        ctx.stats = stats
         ctx.eps = float(eps)
-        return stats[0] / stats[1] + stats[2] / n
+        return stats[4]
 
     @staticmethod
     def backward(ctx, g):
-        X, Y, stats = ctx.saved_tensors
+        X, Y = ctx.saved_tensors
+        stats = ctx.stats
         n = X.numel()
-        coef = torch.stack([g / stats[1], g / n]).to(torch.float32).contiguous()
+        g = g.to(torch.float32)
+        if g.dim() != 0 or not g.is_cuda:
+            raise _lib.RaveB200Error("spectral distance: the upstream gradient must be a CUDA scalar")
         dY = torch.empty_like(Y, memory_format=torch.contiguous_format)
         call("rave_spectral_grad", ptr(torch.view_as_real(X)), ptr(torch.view_as_real(Y)),
-             ptr(torch.view_as_real(dY)), ptr(coef), n, ctx.eps, stream_ptr())
+             ptr(torch.view_as_real(dY)), stats.data_ptr(), g.data_ptr(), n, ctx.eps, stream_ptr())
         return None, (dY.transpose(-1, -2) if ctx.transposed else dY), None
 
 
