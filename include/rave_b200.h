@@ -213,6 +213,13 @@ int rave_score_grad(const float *score, const float *dstats, void *gout_bf16, in
 int rave_spectral_stats(const void *X_c64, const void *Y_c64, float *stats, long n, float eps, void *stream);
 int rave_spectral_grad(const void *X_c64, const void *Y_c64, void *dY_c64, const float *stats, const float *gup,
                        long n, float eps, void *stream);
+/* STFT framing of torch.stft(center=True, pad_mode="reflect", hop | n_fft) without the FFT (rave/core.py:286-306):
+ * frames[n][f][t] = window[t] * x[n][reflect(f*hop + t - n_fft/2)], F = 1 + T/hop frames; and its adjoint
+ * dx[n][j] (window, overlap-add, fold of the reflected borders). */
+int rave_stft_frames(const float *x, const float *window, float *frames, int N, int T, int n_fft, int hop,
+                     void *stream);
+int rave_stft_frames_bwd(const float *dframes, const float *window, float *dx, int N, int T, int n_fft, int hop,
+                         void *stream);
 
 /* fused weight preparation for the engine: v [C0][C1][K] fp32 (+ weight-norm g [C0]; norm [C0] is written)
  *   outA[t][c0][c1] = bf16(w[c0][c1][tapsA[t]]), dims [nA][C0p][C1p]  (padded region zero)

@@ -78,6 +78,13 @@ class MultiScaleSTFT(nn.Module):
 
     def complex_stfts(self, x):
         x = x.reshape(-1, x.shape[-1])
+        if x.is_cuda and x.dtype == torch.float32 and not self.normalized:
+            # library framing kernel (pad + frame + window; adjoint = window + overlap-add + fold) and cuFFT for
+            # the transform; like torch.stft the result is a [N, bins, frames] view of a [N, frames, bins] buffer
+            from . import ops
+            if all(x.shape[-1] > s // 2 for s in self.scales):
+                return [torch.fft.rfft(ops.stft_frames(x, getattr(self, f"window_{s}"), s, s // 4)).transpose(-1, -2)
+                        for s in self.scales]
         return [torch.stft(x, s, hop_length=s // 4, win_length=s, window=getattr(self, f"window_{s}"),
                            center=True, pad_mode="reflect", normalized=self.normalized, onesided=True,
                            return_complex=True) for s in self.scales]

@@ -409,8 +409,29 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int l0 = lt * p.BL;
       const int b0 = bg * p.BB;
       const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+      // running (tap, channel block) counters: all index arithmetic stays OUTSIDE the elected region (uniform
+      // registers, one division per tap) -- the producer has to turn a stage around in well under the ~400 clk
+      // the tensor pipe needs to consume it
+      int k = 0, kb = 0;
+      int j = (-p.pad_l) / p.stride, ph = (-p.pad_l) - j * p.stride;
+      if (ph < 0) { ph += p.stride; j -= 1; }
       for (int u0 = 0; u0 < kblocks; u0 += UNITS) {
         const int nu = min(UNITS, kblocks - u0);
+        int c_kb[UNITS], c_ph[UNITS], c_row[UNITS], c_w[UNITS];
+#pragma unroll
+        for (int u = 0; u < UNITS; ++u) {
+          c_kb[u] = kb * BLOCK_K; c_ph[u] = ph; c_row[u] = l0 + j; c_w[u] = k * p.Cout + n0;
+          if (u < nu) {
+            if (++kb == p.num_kb) {
+              kb = 0; ++k;
+              // input row = l*stride + k*dil - pad_l = (l + j)*stride + ph
+              const int off = k * p.dil - p.pad_l;
+              j = off / p.stride;
+              ph = off - j * p.stride;
+              if (ph < 0) { ph += p.stride; j -= 1; }
+            }
+          }
+        }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t *sa = smem + stage * L::STAGE_BYTES;
         uint8_t *sb = sa + L::A_BYTES;
@@ -418,16 +439,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int u = 0; u < UNITS; ++u) {
             if (u < nu) {
-              const int k = (u0 + u) / p.num_kb, kb = (u0 + u) - k * p.num_kb;
-              // input row = l*stride + k*dil - pad_l = (l + j)*stride + ph
-              const int off = k * p.dil - p.pad_l;
-              int j = off / p.stride;
-              int ph = off - j * p.stride;
-              if (ph < 0) { ph += p.stride; j -= 1; }
               if (!(p.dbg & 2))
-                tma_load_4d_2sm(sa + u * L::A_UNIT, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
+                tma_load_4d_2sm(sa + u * L::A_UNIT, &tmap_a, &full_bar[stage], c_kb[u], c_ph[u], c_row[u], b0);
               if (!(p.dbg & 4))
-                tma_load_2d_2sm(sb + u * L::B_UNIT, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
+                tma_load_2d_2sm(sb + u * L::B_UNIT, &tmap_b, &full_bar[stage], c_kb[u], c_w[u]);
             }
           }
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], unit_tx * nu);

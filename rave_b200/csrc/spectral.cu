@@ -70,7 +70,87 @@ spectral_grad_kernel(const float2 *__restrict__ X, const float2 *__restrict__ Y,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// STFT framing (torch.stft(center=True, pad_mode="reflect") minus the FFT itself, rave/core.py:286-306):
+//   frames[n][f][t] = w[t] * x[n][reflect(f*hop + t - n_fft/2)]          reflect(i) = -i (i<0), 2(T-1)-i (i>=T)
+// one kernel instead of reflection_pad1d + as_strided + mul, and one kernel for the adjoint (window, overlap-add,
+// fold of the reflected borders) instead of mul + index_add + reflection_pad1d_backward.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stft_frames_kernel(const float *__restrict__ x, const float *__restrict__ w, float *__restrict__ frames, long total,
+                   int T, int n_fft, int hop, int F) {
+  const int h = n_fft >> 1;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int t = (int)(i % n_fft);
+    const long nf = i / n_fft;
+    const int f = (int)(nf % F);
+    const long n = nf / F;
+    int j = f * hop + t - h;
+    if (j < 0) j = -j;
+    if (j >= T) j = 2 * (T - 1) - j;
+    frames[i] = __ldg(w + t) * __ldg(x + n * T + j);
+  }
+}
+
+__device__ __forceinline__ float stft_ola_at(const float *__restrict__ d, const float *__restrict__ w, int p, int n_fft,
+                                             int hop, int F) {
+  // sum over the frames that cover padded position p
+  float acc = 0.f;
+  int f_hi = p / hop;
+  if (f_hi > F - 1) f_hi = F - 1;
+  int f_lo = (p - n_fft + hop) / hop;          // ceil((p - n_fft + 1) / hop) for p - n_fft + 1 >= 0
+  if (p - n_fft + 1 <= 0) f_lo = 0;
+  for (int f = f_lo; f <= f_hi; ++f) {
+    const int t = p - f * hop;
+    acc = fmaf(__ldg(w + t), __ldg(d + (size_t)f * n_fft + t), acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256)
+stft_frames_bwd_kernel(const float *__restrict__ dframes, const float *__restrict__ w, float *__restrict__ dx, long total,
+                       int T, int n_fft, int hop, int F) {
+  const int h = n_fft >> 1;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int j = (int)(i % T);
+    const long n = i / T;
+    const float *d = dframes + (size_t)n * F * n_fft;
+    float acc = stft_ola_at(d, w, j + h, n_fft, hop, F);
+    if (j >= 1 && j <= h) acc += stft_ola_at(d, w, h - j, n_fft, hop, F);
+    if (j <= T - 2 && j >= T - 1 - h) acc += stft_ola_at(d, w, 2 * (T - 1) - j + h, n_fft, hop, F);
+    dx[i] = acc;
+  }
+}
+
 }  // namespace rave
+
+extern "C" int rave_stft_frames(const float *x, const float *window, float *frames, int N, int T, int n_fft, int hop,
+                                void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && window && frames && N > 0 && T > n_fft / 2 && n_fft >= 2 && hop > 0 && n_fft % hop == 0,
+                 "stft_frames: bad argument (reflect padding needs T > n_fft/2, hop | n_fft)");
+  const int F = 1 + T / hop;
+  const long total = (long)N * F * n_fft;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stft_frames_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, window, frames, total, T, n_fft, hop, F);
+  RAVE_CHECK_LAUNCH("stft_frames");
+  return 0;
+}
+
+extern "C" int rave_stft_frames_bwd(const float *dframes, const float *window, float *dx, int N, int T, int n_fft,
+                                    int hop, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(dframes && window && dx && N > 0 && T > n_fft / 2 && n_fft >= 2 && hop > 0 && n_fft % hop == 0,
+                 "stft_frames_bwd: bad argument");
+  const int F = 1 + T / hop;
+  const long total = (long)N * T;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stft_frames_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dframes, window, dx, total, T, n_fft, hop, F);
+  RAVE_CHECK_LAUNCH("stft_frames_bwd");
+  return 0;
+}
 
 extern "C" int rave_spectral_stats(const void *X, const void *Y, float *stats, long n, float eps, void *stream) {
   using namespace rave;

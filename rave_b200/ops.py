@@ -611,6 +611,34 @@ def spectral_distance(X, Y, eps):
     return SpectralDistanceFn.apply(X, Y, eps)
 
 
+class StftFramesFn(torch.autograd.Function):
+    """Windowed, reflect-padded frames [N, F, n_fft] of x [N, T] (torch.stft's framing, center=True)."""
+
+    @staticmethod
+    def forward(ctx, x, window, n_fft, hop):
+        x = _f32c(x)
+        N, T = x.shape
+        F = 1 + T // hop
+        frames = torch.empty(N, F, n_fft, dtype=torch.float32, device=x.device)
+        call("rave_stft_frames", ptr(x), ptr(window), ptr(frames), N, T, n_fft, hop, stream_ptr())
+        ctx.save_for_backward(window)
+        ctx.dims = (N, T, n_fft, hop)
+        return frames
+
+    @staticmethod
+    def backward(ctx, g):
+        (window,) = ctx.saved_tensors
+        N, T, n_fft, hop = ctx.dims
+        g = _f32c(g)
+        dx = torch.empty(N, T, dtype=torch.float32, device=g.device)
+        call("rave_stft_frames_bwd", ptr(g), ptr(window), ptr(dx), N, T, n_fft, hop, stream_ptr())
+        return dx, None, None, None
+
+
+def stft_frames(x, window, n_fft, hop):
+    return StftFramesFn.apply(x, window, n_fft, hop)
+
+
 # ----------------------------------------------------------------------------------------------
 # multi-tensor weight preparation / weight-norm backward (one launch pair per chain)
 # ----------------------------------------------------------------------------------------------

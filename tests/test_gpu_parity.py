@@ -381,3 +381,23 @@ def test_fused_spectral_distance_vs_oracle():
     yg = g["y"].cuda().requires_grad_(True)
     (gg,) = torch.autograd.grad(dist(x.cuda(), yg)["spectral_distance"], yg)
     assert rel_l2(gg, go) < 1e-4
+
+
+def test_stft_framing_kernels_vs_torch_stft():
+    """rave_stft_frames (+ cuFFT) against torch.stft(center=True, reflect) and its autograd, ragged lengths."""
+    from rave_b200 import core
+    torch.manual_seed(3)
+    for (N, T, scales) in [(3, 4096, [2048, 1024, 512, 256, 128]), (2, 1100, [512, 128]), (5, 65536, [2048, 128])]:
+        m = core.MultiScaleSTFT(scales, 48000, magnitude=True).cuda()
+        x = torch.randn(N, T, device="cuda", requires_grad=True)
+        got = m.complex_stfts(x)
+        for s, y in zip(scales, got):
+            xr = x.detach().clone().requires_grad_(True)
+            ref = torch.stft(xr, s, hop_length=s // 4, win_length=s, window=getattr(m, f"window_{s}"), center=True,
+                             pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+            assert y.shape == ref.shape
+            assert rel_l2(torch.view_as_real(y), torch.view_as_real(ref)) < 1e-5
+            wgt = torch.randn_like(torch.view_as_real(ref))
+            (g_ref,) = torch.autograd.grad((torch.view_as_real(ref) * wgt).sum(), xr)
+            (g_got,) = torch.autograd.grad((torch.view_as_real(y) * wgt).sum(), x, retain_graph=True)
+            assert rel_l2(g_got, g_ref) < 1e-5
