@@ -15,6 +15,7 @@
 // Replaces: cc.Conv1d.forward = F.pad + F.conv1d -> cuDNN (reference call sites rave/blocks.py:96-108,
 // 538-592, 637-692; rave/discriminator.py:99-111), the preceding activation module and the residual add.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -44,6 +45,8 @@ struct TcParams {
   int out_rows;            // rows per batch of the output tensors (>= Lout when phases interleave)
   int out_row_stride;      // output row = l * out_row_stride + out_row_offset (transposed-conv phases)
   int out_row_offset;
+  int tma_store;           // out_act goes through shared-memory staging + bulk tensor stores (CTA-pair kernel)
+  int st_rows, st_batches; // rows x batches of one epilogue warp's 32 tile rows (box of the store tensor map)
   int stages;              // pipeline depth actually used (<= the layout's STAGES); RAVE_TC_STAGES overrides
   int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue stores, 2 = skip the
                            // activation TMA loads, 4 = skip the weight TMA loads (results are garbage)
@@ -66,7 +69,8 @@ struct SmemLayout {
 // LeakyReLU' mask) are issued BEFORE the TMEM load so that their latency overlaps it: the HBM-bound layers
 // (C = 96 / 192 blocks) are limited by the bytes in flight per SM, not by arithmetic.
 template <int CW>
-__device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow) {
+__device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow,
+                                             uint8_t *stg = nullptr, int lane = 0) {
   float v[CW];
   float4 rf[CW / 4];
   uint4 rb[CW / 8], dm[CW / 8], ra[CW / 8];
@@ -95,7 +99,11 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
   }
   if (CW == 32) tmem_ld_32x32(taddr, v);
   else tmem_ld_32x16(taddr, v);       // warp-collective: every lane participates, valid or not
-  if (!valid) return;
+  if (!valid && !stg) return;
+  if (!valid) {                       // staged store: every row of the box is written (TMA clips the invalid ones)
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = 0.f;
+  }
   if (p.bias) {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] += __ldg(p.bias + co + i);
@@ -140,7 +148,7 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
       v[4 * i + 0] += rf[i].x; v[4 * i + 1] += rf[i].y; v[4 * i + 2] += rf[i].z; v[4 * i + 3] += rf[i].w;
     }
   }
-  if (p.out_f32) {
+  if (p.out_f32 && valid) {
     float4 *o4 = reinterpret_cast<float4 *>(p.out_f32 + off);
 #pragma unroll
     for (int i = 0; i < CW / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -149,6 +157,8 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
     uint4 *o = reinterpret_cast<uint4 *>(p.out_act + off);
 #pragma unroll
     for (int i = 0; i < CW / 8; ++i) {
+      // staged: row `lane` of a [32 rows][64 bytes] SWIZZLE_64B box, 16-byte chunk i at i ^ ((row >> 1) & 3)
+      uint4 *dst = stg ? reinterpret_cast<uint4 *>(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) : (o + i);
       uint32_t pk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -160,7 +170,7 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
         __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
         pk[j] = *reinterpret_cast<uint32_t *>(&h);
       }
-      o[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -171,6 +181,34 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t taddr, i
 #pragma unroll 1
   for (int c0 = 0; c0 < MAIN; c0 += 32) tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow);
   if (MAIN < BLOCK_N) tc_epi_chunk<16>(p, taddr + MAIN, n0 + MAIN, valid, orow);
+}
+
+// Tile epilogue with staged stores (CTA-pair kernel): each warp packs its 32 rows x 32 channels into a 2 KB
+// SWIZZLE_64B box in shared memory and ONE lane hands it to the TMA unit (bulk tensor store, clipped to the valid
+// rows / batches by the tensor map).  Per-thread row-wise 16-byte stores cost 32 partial-sector transactions per
+// instruction and kept the LSU busy for ~3000 clk per 128 x 192 tile -- as long as the MMAs of a K=5 layer.
+constexpr int STG_WARP_BYTES = 2 * 2048;      // two boxes per warp (double buffer)
+template <int BLOCK_N>
+__device__ __forceinline__ void tc_epilogue_staged(const TcParams &p, const CUtensorMap *tmap_o, uint32_t taddr,
+                                                   int n0, bool valid, size_t orow, uint8_t *stg_warp, int lane,
+                                                   int l_start, int b_start, bool any_valid, uint32_t &chunk_ctr) {
+  static_assert(BLOCK_N % 32 == 0, "staged epilogue works on 32-channel chunks");
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    uint8_t *stg = stg_warp + (chunk_ctr & 1u) * 2048;
+    if (chunk_ctr >= 2) {
+      if (lane == 0) tma_store_wait_read<1>();      // the store issued two chunks ago has read this buffer
+      __syncwarp();
+    }
+    tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow, stg, lane);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (any_valid) tma_store_3d(tmap_o, stg, n0 + c0, l_start, b_start);
+      tma_store_commit();
+    }
+    ++chunk_ctr;
+  }
 }
 
 template <int BLOCK_N, int BLOCK_K>
@@ -342,13 +380,14 @@ struct SmemLayout2 {
   static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+  static constexpr int STG_OFFSET = BAR_OFFSET + 1024;                 // epilogue staging: 4 warps x 2 boxes x 2 KB
+  static constexpr int TOTAL = STG_OFFSET + 4 * STG_WARP_BYTES + 1024;
 };
 
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const TcParams p) {
+                const __grid_constant__ CUtensorMap tmap_o, const TcParams p) {
   using L = SmemLayout2<BLOCK_N, BLOCK_K>;
   constexpr int STAGES = L::STAGES;
   constexpr int UNITS = L::UNITS;
@@ -500,6 +539,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // =========================== epilogue (4 warps in each CTA) ===========================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    uint8_t *stg_warp = smem + L::STG_OFFSET + quad * STG_WARP_BYTES;
+    uint32_t chunk_ctr = 0;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int acc = it & 1;
@@ -516,11 +557,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow);
+      if (p.tma_store) {
+        const int r0 = quad * 32;                   // first tile row of this warp
+        const int b_start = bg * p.BB + r0 / p.BL;
+        const int l_start = lt * p.BL + r0 % p.BL;
+        const bool any_valid = (mt < n_mt) && (b_start < p.B) && (l_start < p.Lout) && !(p.dbg & 1);
+        tc_epilogue_staged<BLOCK_N>(p, &tmap_o, taddr, n0, valid, orow, stg_warp, lane, l_start, b_start, any_valid,
+                                    chunk_ctr);
+      } else {
+        tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last bulk stores
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -602,7 +654,8 @@ static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &
 }
 
 template <int BN, int BK>
-static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t stream) {
+static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const TcParams &p,
+                   cudaStream_t stream) {
   using L = SmemLayout2<BN, BK>;
   static bool attr = false;
   if (!attr) {
@@ -627,19 +680,20 @@ static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams 
     const char *e = getenv("RAVE_TC_STAGES");
     if (e && atoi(e) >= 2 && atoi(e) < L::STAGES) q.stages = atoi(e);
   }
-  conv_tc2_kernel<BN, BK><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, q);
+  conv_tc2_kernel<BN, BK><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, to, q);
   RAVE_CHECK_LAUNCH("conv1d_tc(2cta)");
   return 0;
 }
 
 template <int BK>
-static int dispatch_n2(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t s) {
+static int dispatch_n2(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const TcParams &p,
+                       cudaStream_t s) {
   switch (bn) {
-    case 256: return launch2<256, BK>(ta, tb, p, s);
-    case 192: return launch2<192, BK>(ta, tb, p, s);
-    case 128: return launch2<128, BK>(ta, tb, p, s);
-    case 96: return launch2<96, BK>(ta, tb, p, s);
-    case 64: return launch2<64, BK>(ta, tb, p, s);
+    case 256: return launch2<256, BK>(ta, tb, to, p, s);
+    case 192: return launch2<192, BK>(ta, tb, to, p, s);
+    case 128: return launch2<128, BK>(ta, tb, to, p, s);
+    case 96: return launch2<96, BK>(ta, tb, to, p, s);
+    case 64: return launch2<64, BK>(ta, tb, to, p, s);
   }
   set_error("conv1d_tc(2cta): no kernel for BLOCK_N=%d", bn);
   return 1;
@@ -713,6 +767,7 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   p.out_row_offset = out_row_offset;
   p.stages = 0;
   p.dbg = 0;
+  p.tma_store = 0; p.st_rows = 0; p.st_batches = 0;
   {
     const char *e = getenv("RAVE_TC_DBG");
     if (e) p.dbg = atoi(e);
@@ -758,9 +813,30 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map B encode failed (%d)", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (use2)
-    return BK == 64 ? dispatch_n2<64>(BN, ta, tb, p, s) : BK == 32 ? dispatch_n2<32>(BN, ta, tb, p, s)
-                                                                   : dispatch_n2<16>(BN, ta, tb, p, s);
+  if (use2) {
+    // bf16 output through shared-memory staging + bulk tensor stores (RAVE_TC_TMASTORE=0: per-thread stores)
+    CUtensorMap to;
+    memset(&to, 0, sizeof(to));
+    p.tma_store = 0;
+    const char *e = getenv("RAVE_TC_TMASTORE");
+    if (out_act && !(e && e[0] == '0')) {
+      const int RB = p.BL < 32 ? p.BL : 32;
+      char *base = (char *)out_act + (size_t)p.out_row_offset * Cout * 2;
+      cuuint64_t dims[3] = {(cuuint64_t)Cout, (cuuint64_t)Lout, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)p.out_row_stride * Cout * 2, (cuuint64_t)p.out_rows * Cout * 2};
+      cuuint32_t box[3] = {32, (cuuint32_t)RB, (cuuint32_t)(32 / RB)};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = enc(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: output tensor map encode failed (%d)", (int)r);
+      p.tma_store = 1;
+      p.st_rows = RB;
+      p.st_batches = 32 / RB;
+    }
+    return BK == 64 ? dispatch_n2<64>(BN, ta, tb, to, p, s) : BK == 32 ? dispatch_n2<32>(BN, ta, tb, to, p, s)
+                                                                       : dispatch_n2<16>(BN, ta, tb, to, p, s);
+  }
   switch (BK) {
     case 64: return dispatch_n<64>(BN, ta, tb, p, s);
     case 32: return dispatch_n<32>(BN, ta, tb, p, s);

@@ -30,7 +30,9 @@ _state = {"precision": "fp32", "prep_epoch": 0}
 ACT_DTYPE = torch.bfloat16   # storage type of operand / gradient streams (tests may widen it)
 
 
-C1_GROUP = 4       # output positions per tensor-core row of a Cin = 1 first layer (see TcChainFn.forward)
+import os as _os
+# output positions per tensor-core row of a Cin = 1 first layer (see TcChainFn.forward); 1 = plain 16-channel rows
+C1_GROUP = int(_os.environ.get("RAVE_C1_GROUP", "4"))
 
 
 def set_precision(mode: str) -> None:

@@ -18,18 +18,19 @@ SHAPES = [
     ("msd_96_192_k15s4 (BK=32)", 64, 96, 192, 16384, 15, 4, 1, 7),
     ("mpd_96_192_k5s4 (BK=32)", 128, 96, 192, 8192, 5, 4, 1, 2),
     ("c1 im2col 16->96 k1", 64, 16, 96, 16384, 1, 1, 1, 0),
+    ("c1 as 64->384 k1 (4 positions per row)", 64, 64, 384, 4096, 1, 1, 1, 0),
     ("unit 96->96 k3 B32", 32, 96, 96, 4096, 3, 1, 1, 1),
 ]
 CONFIGS = [
     ("default", {}),
-    ("stages=3", {"RAVE_TC_STAGES": "3"}),
+    ("per-thread stores", {"RAVE_TC_TMASTORE": "0"}),
     ("no epilogue stores", {"RAVE_TC_DBG": "1"}),
     ("no loads at all", {"RAVE_TC_DBG": "6"}),
     ("no loads, no stores", {"RAVE_TC_DBG": "7"}),
     ("L2 promotion none", {"RAVE_TC_L2PROMO": "0"}),
     ("1-CTA kernel", {"RAVE_TC_2CTA": "0"}),
 ]
-KEYS = ["RAVE_TC_STAGES", "RAVE_TC_DBG", "RAVE_TC_L2PROMO"]
+KEYS = ["RAVE_TC_STAGES", "RAVE_TC_DBG", "RAVE_TC_L2PROMO", "RAVE_TC_TMASTORE"]
 
 for name, B, Cin, Cout, Lin, K, stride, dil, pad in SHAPES:
     x = torch.randn(B, Lin, Cin, device="cuda").bfloat16()

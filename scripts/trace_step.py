@@ -22,11 +22,13 @@ torch.cuda.synchronize()
 
 
 def short(n):
-    n = re.sub(r"\(.*", "", n)
-    if n.startswith("void at::") or "at::native" in n:
-        f = re.findall(r"(\w+(?:Functor|functor|_kernel_cuda|Ops|Op)\w*)", n)
-        return "at:" + re.sub(r"^void at::native::|^void at::", "", n)[:40] + " " + " ".join(f[:2])
-    return n[:70]
+    if n.startswith("void at::") or "at::native" in n or n.startswith("at::"):
+        m = re.sub(r"^void ", "", n)
+        m = m.replace("at::native::", "").replace("at::", "")
+        f = re.findall(r"(\w*(?:Functor|functor|_kernel_cuda|Ops|Op|index\w*|pad\w*|cat\w*|copy\w*)\w*)", m)
+        head = re.sub(r"<.*", "", m)[:36]
+        return "at:" + head + " " + " ".join(dict.fromkeys(f[:3]))
+    return re.sub(r"\(.*", "", n)[:70]
 
 
 for tag, idx in (("G-step", 1), ("D-step", 0)):
