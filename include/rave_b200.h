@@ -134,6 +134,10 @@ int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, i
  *             a = LeakyReLU_{res_slope}(h): adds h = a > 0 ? a : a / res_slope (no separate fp32 stream)
  *   dact_src[B][out_rows][Cout] bf16 or NULL : result *= LeakyReLU'(dact_src) before the residual add
  *             (backward use: the activated operand saved by the forward pass carries the sign)
+ *   fm_d    2 device floats (d0, d1) or NULL  : fused feature-matching gradient (needs dact_src): the batch is
+ *             [real; fake] with fm_bh rows per half; after the LeakyReLU' mask the epilogue adds, with
+ *             h = LeakyReLU^-1(dact_src), d0 sgn(h_r-h_f) + d1 sgn(h_r) to real rows and -d0 sgn(h_r-h_f) to fake
+ *             rows (rave/model.py:355-361 with core.mean_difference L1, rave/core.py:236-252)
  *   out_f32 [B][out_rows][Cout] fp32 or NULL : pre-activation stream (residual / features)
  *   out_act [B][out_rows][Cout] bf16 or NULL : act(out), the next conv's operand
  * Output row of (b,l) is l*out_row_stride + out_row_offset (phases of a transposed conv interleave);
@@ -147,16 +151,19 @@ int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bi
                        float *out_f32, void *out_act_bf16,
                        int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
                        int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
-                       int out_row_stride, int out_row_offset, void *stream);
+                       int out_row_stride, int out_row_offset, const float *fm_d, int fm_bh, void *stream);
 /* weight gradient on the same engine (split-K over row slices; each slice writes its own partial):
  *   sum_s dwt[s][k][m][n] = sum_{b,l} P[b][l][m] * Q[b][l*stride + k*dil - pad_l][n]
  * P [B][Lp][Cm] bf16 (conv: dy), Q [B][Lq][Cn] bf16 (conv: activated input);
  * dwt [splits][K][Cm][Cn] fp32 with splits = rave_conv1d_tc_wgrad_splits(...) (every element written once;
  * the slices are summed, in order, by rave_weight_norm_bwd_tapmajor / rave_tapmajor_to_weight_f32).
- * For ConvTranspose1d swap the roles (P = activated input, Q = dy).  Cm, Cn multiples of 8. */
+ * For ConvTranspose1d swap the roles (P = activated input, Q = dy).  Cm, Cn multiples of 8.
+ * dbias [Cm] fp32, pre-zeroed, or NULL: += sum_{b,l} P[b][l][m] (the conv bias gradient when P = dy), reduced by the
+ * tap-0 CTAs from the tiles they stream anyway (fp32 atomics across row slices). */
 int rave_conv1d_tc_wgrad_splits(int B, int Cm, int Lp, int Cn, int K);
-int rave_conv1d_tc_wgrad(const void *P_bf16, const void *Q_bf16, float *dwt, int B, int Cm, int Lp, int p_pitch,
-                         int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l, void *stream);
+int rave_conv1d_tc_wgrad(const void *P_bf16, const void *Q_bf16, float *dwt, float *dbias, int B, int Cm, int Lp,
+                         int p_pitch, int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l,
+                         void *stream);
 /* sum_s dwt[s][K][Cm][Cn] -> dw[Cm][Cn][K] (transpose=0) or dw[Cn][Cm][K] (transpose=1), fp32 */
 int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, int Cn, int K, int transpose, int splits,
                                 void *stream);

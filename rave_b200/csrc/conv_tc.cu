@@ -25,6 +25,8 @@ namespace tc {
 
 constexpr int BLOCK_M = 128;
 constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS2 = 320;      // CTA-pair kernel: producer, MMA issuer, 8 epilogue warps (2 per TMEM quadrant)
+constexpr int EPI_WARPS2 = 8;
 constexpr int ACC_STAGES = 2;
 
 struct TcParams {
@@ -45,6 +47,9 @@ struct TcParams {
   int out_rows;            // rows per batch of the output tensors (>= Lout when phases interleave)
   int out_row_stride;      // output row = l * out_row_stride + out_row_offset (transposed-conv phases)
   int out_row_offset;
+  const float *fm_d;       // feature-matching gradient fused into a dgrad epilogue (or null): dact_src is the bf16
+  long fm_half;            //   operand a = LeakyReLU(h) of [real; fake] rows, fm_half elements apart; adds
+  int fm_bh;               //   d0 sgn(h_r-h_f) + d1 sgn(h_r) to real rows (b < fm_bh), -d0 sgn(h_r-h_f) to fake rows
   int tma_store;           // out_act goes through shared-memory staging + bulk tensor stores (CTA-pair kernel)
   int st_rows, st_batches; // rows x batches of one epilogue warp's 32 tile rows (box of the store tensor map)
   int stages;              // pipeline depth actually used (<= the layout's STAGES); RAVE_TC_STAGES overrides
@@ -70,12 +75,17 @@ struct SmemLayout {
 // (C = 96 / 192 blocks) are limited by the bytes in flight per SM, not by arithmetic.
 template <int CW>
 __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow,
-                                             uint8_t *stg = nullptr, int lane = 0) {
+                                             uint8_t *stg = nullptr, int lane = 0, int fm_side = 0) {
   float v[CW];
   float4 rf[CW / 4];
-  uint4 rb[CW / 8], dm[CW / 8], ra[CW / 8];
+  uint4 rb[CW / 8], dm[CW / 8], ra[CW / 8], pm[CW / 8];
   const size_t off = orow * p.Cout + co;
   if (valid) {
+    if (fm_side) {     // partner row of the other batch half (same position, same channels)
+      const uint4 *q4 = reinterpret_cast<const uint4 *>(p.dact_src + (fm_side > 0 ? off + p.fm_half : off - p.fm_half));
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) pm[i] = __ldg(q4 + i);
+    }
     if (p.res_act) {
       const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_act + off);
 #pragma unroll
@@ -116,6 +126,29 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
       for (int j = 0; j < 4; ++j) {
         if (w[j] & 0x00008000u) v[8 * i + 2 * j] *= p.slope;
         if (w[j] & 0x80000000u) v[8 * i + 2 * j + 1] *= p.slope;
+      }
+    }
+  }
+  if (fm_side) {       // gradient of d0 * sum|h_r - h_f| + d1 * sum|h_r| with respect to h (this row's half)
+    const float d0 = __ldg(p.fm_d), d1 = __ldg(p.fm_d + 1);
+    const float inv = 1.f / p.slope;
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+      const uint32_t ws[4] = {dm[i].x, dm[i].y, dm[i].z, dm[i].w};
+      const uint32_t wp[4] = {pm[i].x, pm[i].y, pm[i].z, pm[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float as = h ? __uint_as_float(ws[j] & 0xFFFF0000u) : __uint_as_float(ws[j] << 16);
+          const float ap = h ? __uint_as_float(wp[j] & 0xFFFF0000u) : __uint_as_float(wp[j] << 16);
+          const float hs = as > 0.f ? as : as * inv, hp = ap > 0.f ? ap : ap * inv;
+          const float hr = fm_side > 0 ? hs : hp, hf = fm_side > 0 ? hp : hs;
+          const float sd = (hr > hf) ? 1.f : ((hr < hf) ? -1.f : 0.f);
+          float gfm = fm_side > 0 ? d0 * sd : -d0 * sd;
+          if (fm_side > 0) gfm += d1 * ((hr > 0.f) ? 1.f : ((hr < 0.f) ? -1.f : 0.f));
+          v[8 * i + 2 * j + h] += gfm;
+        }
       }
     }
   }
@@ -175,12 +208,16 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
   }
 }
 
+// `part` of `parts` warps share one TMEM lane quadrant and take alternate 32-column chunks (the epilogue is
+// latency-bound -- tcgen05.ld, convert, store with ONE warp per scheduler -- so the CTA-pair kernel runs two)
 template <int BLOCK_N>
-__device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t taddr, int n0, bool valid, size_t orow) {
+__device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t taddr, int n0, bool valid, size_t orow,
+                                            int fm_side, int part = 0, int parts = 1) {
   constexpr int MAIN = BLOCK_N / 32 * 32;
 #pragma unroll 1
-  for (int c0 = 0; c0 < MAIN; c0 += 32) tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow);
-  if (MAIN < BLOCK_N) tc_epi_chunk<16>(p, taddr + MAIN, n0 + MAIN, valid, orow);
+  for (int c0 = part * 32; c0 < MAIN; c0 += parts * 32)
+    tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow, nullptr, 0, fm_side);
+  if (MAIN < BLOCK_N && part == 0) tc_epi_chunk<16>(p, taddr + MAIN, n0 + MAIN, valid, orow, nullptr, 0, fm_side);
 }
 
 // Tile epilogue with staged stores (CTA-pair kernel): each warp packs its 32 rows x 32 channels into a 2 KB
@@ -191,16 +228,17 @@ constexpr int STG_WARP_BYTES = 2 * 2048;      // two boxes per warp (double buff
 template <int BLOCK_N>
 __device__ __forceinline__ void tc_epilogue_staged(const TcParams &p, const CUtensorMap *tmap_o, uint32_t taddr,
                                                    int n0, bool valid, size_t orow, uint8_t *stg_warp, int lane,
-                                                   int l_start, int b_start, bool any_valid, uint32_t &chunk_ctr) {
+                                                   int l_start, int b_start, bool any_valid, uint32_t &chunk_ctr,
+                                                   int fm_side, int part, int parts) {
   static_assert(BLOCK_N % 32 == 0, "staged epilogue works on 32-channel chunks");
 #pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+  for (int c0 = part * 32; c0 < BLOCK_N; c0 += parts * 32) {
     uint8_t *stg = stg_warp + (chunk_ctr & 1u) * 2048;
     if (chunk_ctr >= 2) {
       if (lane == 0) tma_store_wait_read<1>();      // the store issued two chunks ago has read this buffer
       __syncwarp();
     }
-    tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow, stg, lane);
+    tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow, stg, lane, fm_side);
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
@@ -341,7 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow);
+      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow, p.fm_d ? (b < p.fm_bh ? 1 : -1) : 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -380,12 +418,12 @@ struct SmemLayout2 {
   static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STG_OFFSET = BAR_OFFSET + 1024;                 // epilogue staging: 4 warps x 2 boxes x 2 KB
-  static constexpr int TOTAL = STG_OFFSET + 4 * STG_WARP_BYTES + 1024;
+  static constexpr int STG_OFFSET = BAR_OFFSET + 1024;                 // epilogue staging: 8 warps x 2 boxes x 2 KB
+  static constexpr int TOTAL = STG_OFFSET + EPI_WARPS2 * STG_WARP_BYTES + 1024;
 };
 
 template <int BLOCK_N, int BLOCK_K>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_o, const TcParams p) {
   using L = SmemLayout2<BLOCK_N, BLOCK_K>;
@@ -424,7 +462,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);      // leader's: 4 epilogue warps of each CTA
+      mbar_init(&tempty_bar[s], 2 * EPI_WARPS2);      // leader's: the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -537,9 +575,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     __syncwarp();
   } else if (warp >= 2) {
     // =========================== epilogue (4 warps in each CTA) ===========================
-    const int quad = warp & 3;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int part = (warp - 2) >> 2;          // which of the quadrant's two warps: alternate 32-column chunks
     const int row = quad * 32 + lane;
-    uint8_t *stg_warp = smem + L::STG_OFFSET + quad * STG_WARP_BYTES;
+    uint8_t *stg_warp = smem + L::STG_OFFSET + (warp - 2) * STG_WARP_BYTES;
     uint32_t chunk_ctr = 0;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -557,15 +596,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+      const int fm_side = p.fm_d ? (b < p.fm_bh ? 1 : -1) : 0;
       if (p.tma_store) {
         const int r0 = quad * 32;                   // first tile row of this warp
         const int b_start = bg * p.BB + r0 / p.BL;
         const int l_start = lt * p.BL + r0 % p.BL;
         const bool any_valid = (mt < n_mt) && (b_start < p.B) && (l_start < p.Lout) && !(p.dbg & 1);
         tc_epilogue_staged<BLOCK_N>(p, &tmap_o, taddr, n0, valid, orow, stg_warp, lane, l_start, b_start, any_valid,
-                                    chunk_ctr);
+                                    chunk_ctr, fm_side, part, EPI_WARPS2 / 4);
       } else {
-        tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow);
+        tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow, fm_side, part, EPI_WARPS2 / 4);
       }
       tc_fence_before();
       __syncwarp();
@@ -680,7 +720,7 @@ static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorM
     const char *e = getenv("RAVE_TC_STAGES");
     if (e && atoi(e) >= 2 && atoi(e) < L::STAGES) q.stages = atoi(e);
   }
-  conv_tc2_kernel<BN, BK><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, to, q);
+  conv_tc2_kernel<BN, BK><<<2 * pairs, NUM_THREADS2, L::TOTAL, stream>>>(ta, tb, to, q);
   RAVE_CHECK_LAUNCH("conv1d_tc(2cta)");
   return 0;
 }
@@ -731,7 +771,8 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
                                   float *out_f32, void *out_act,
                                   int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
                                   int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
-                                  int out_row_stride, int out_row_offset, void *stream) {
+                                  int out_row_stride, int out_row_offset, const float *fm_d, int fm_bh,
+                                  void *stream) {
   using namespace rave;
   using namespace rave::tc;
   RAVE_CHECK_ARG(xa && wt && (out_f32 || out_act), "conv1d_tc: null pointer");
@@ -765,6 +806,12 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   p.out_rows = out_rows > 0 ? out_rows : Lout;
   p.out_row_stride = out_row_stride > 0 ? out_row_stride : 1;
   p.out_row_offset = out_row_offset;
+  RAVE_CHECK_ARG(!fm_d || (dact_src && fm_bh > 0 && 2 * fm_bh == B && slope > 0.f),
+                 "conv1d_tc: the fused feature-matching gradient needs dact_src and a [real; fake] batch (B=%d, fm_bh=%d)",
+                 B, fm_bh);
+  p.fm_d = fm_d;
+  p.fm_bh = fm_bh;
+  p.fm_half = (long)fm_bh * p.out_rows * Cout;
   p.stages = 0;
   p.dbg = 0;
   p.tma_store = 0; p.st_rows = 0; p.st_batches = 0;
@@ -814,12 +861,12 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (use2) {
-    // bf16 output through shared-memory staging + bulk tensor stores (RAVE_TC_TMASTORE=0: per-thread stores)
+    // bf16 output through shared-memory staging + bulk tensor stores: RAVE_TC_TMASTORE=1
     CUtensorMap to;
     memset(&to, 0, sizeof(to));
     p.tma_store = 0;
     const char *e = getenv("RAVE_TC_TMASTORE");
-    if (out_act && !(e && e[0] == '0')) {
+    if (out_act && e && e[0] == '1') {       // measured slower than per-thread stores so far: opt-in
       const int RB = p.BL < 32 ? p.BL : 32;
       char *base = (char *)out_act + (size_t)p.out_row_offset * Cout * 2;
       cuuint64_t dims[3] = {(cuuint64_t)Cout, (cuuint64_t)Lout, (cuuint64_t)B};
@@ -867,6 +914,8 @@ struct WgParams {
   int BL, BB, n_lt, n_bg;   // row chunk = BB batches x BL rows (BL*BB == 64)
   int n_mt, n_nt, splits;
   float *dwt;               // [splits][K][Cm][Cn] fp32 partial sums (every element written exactly once)
+  float *dbias;             // [Cm] pre-zeroed or null: += column sums of P (the bias gradient of a conv layer), added
+                            // by the tap-0 / n-tile-0 CTAs from the P tiles they stream anyway
 };
 
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -886,7 +935,8 @@ struct WgSmem {
   static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+  static constexpr int CS_OFFSET = BAR_OFFSET + 256;                 // column-sum scratch [8][128] fp32
+  static constexpr int TOTAL = CS_OFFSET + 4096 + 1024;
 };
 
 template <int BLOCK_N>
@@ -920,13 +970,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constan
   const int ch_begin = split * per;
   const int ch_end = min(n_chunks, ch_begin + per);
   const int my_chunks = max(0, ch_end - ch_begin);
+  const bool do_cs = p.dbias != nullptr && k == 0 && nt == 0;      // this CTA also reduces its P tiles over rows
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_p);
     tma_prefetch_desc(&tmap_q);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], do_cs ? 5 : 1);     // MMA commit (+ the 4 column-sum warps)
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
@@ -989,6 +1040,41 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constan
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     } else {
+      if (do_cs) {
+        // bias gradient: column sums of the P tiles while the tensor core consumes them.  Thread = (8-channel group
+        // cg, row residue rg): rows rg, rg+8, ... of both 64-channel slabs, one 16-byte shared load per row.
+        const int te = (warp - 2) * 32 + lane;
+        const int cg = te & 15, rg = te >> 4;
+        const uint32_t col = (uint32_t)(cg >> 3) * WG_SLAB + (uint32_t)(((cg & 7) ^ rg) << 4);
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int c = 0; c < my_chunks; ++c) {
+          mbar_wait(&full_bar[stage], phase);
+          const uint8_t *sa = smem + stage * L::STAGE_BYTES + col;
+#pragma unroll
+          for (int i = 0; i < WG_ROWS / 8; ++i) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(sa + (rg + 8 * i) * 128);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              cs[2 * j] += __uint_as_float(w[j] << 16);
+              cs[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        float *scratch = reinterpret_cast<float *>(smem + L::CS_OFFSET);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) scratch[rg * 128 + cg * 8 + j] = cs[j];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += scratch[r * 128 + te];
+        if (m0 + te < p.Cm) atomicAdd(p.dbias + m0 + te, t);
+      }
       const int quad = warp & 3;
       const int m = m0 + quad * 32 + lane;
       mbar_wait(tfull_bar, 0);
@@ -1109,8 +1195,8 @@ extern "C" int rave_conv1d_tc_wgrad_splits(int B, int Cm, int Lp, int Cn, int K)
   return splits;
 }
 
-extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, int B, int Cm, int Lp, int p_pitch,
-                                    int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l,
+extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, float *dbias, int B, int Cm, int Lp,
+                                    int p_pitch, int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l,
                                     void *stream) {
   using namespace rave;
   using namespace rave::tc;
@@ -1128,6 +1214,7 @@ extern "C" int rave_conv1d_tc_wgrad(const void *P, const void *Q, float *dwt, in
   WgParams p;
   p.B = B; p.Cm = Cm; p.Lp = Lp; p.Cn = Cn; p.Lq = Lq; p.K = K; p.stride = stride; p.dil = dil; p.pad_l = pad_l;
   p.dwt = dwt;
+  p.dbias = dbias;
   int BN;
   wg_geometry(B, Cm, Lp, Cn, K, &p.BL, &p.n_lt, &p.n_bg, &p.n_mt, &BN, &p.n_nt, &p.splits);
   p.BB = WG_ROWS / p.BL;

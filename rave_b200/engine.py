@@ -484,20 +484,25 @@ class TcChainFn(torch.autograd.Function):
                 skip[s.res_src] = g
             cin_p, cout_p = s.Cin + s.cin_pad, s.Cout + s.cout_pad
             v, gpar, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
-            # ---- weight gradient
+            # ---- weight gradient (+ bias gradient: column sums of g, taken by the wgrad kernel from the tiles it
+            #      streams when g is its P operand, i.e. for conv layers)
+            want_db = bias is not None and bias.requires_grad
+            db = None
             if v.requires_grad:
+                if want_db and s.kind == "conv":
+                    db = torch.zeros(cout_p, dtype=torch.float32, device=g.device)
                 if use_c1:
-                    d = ops.conv1d_tc_wgrad(g, ctx.c1_X, 1, 1, 1, 0, Lp=Lout, Lq=Lout)       # [S][1][Cout_p][16]
+                    d = ops.conv1d_tc_wgrad(g, ctx.c1_X, 1, 1, 1, 0, Lp=Lout, Lq=Lout, dbias=db)  # [S][1][Cout_p][16]
                     dw_ck = d.sum(0)[0][:s.Cout, :s.K]                                         # [Cout][K]
                     dwt = dw_ck.t().reshape(1, s.K, s.Cout, 1).contiguous()                    # [1][K][C0][C1=1]
                 elif s.kind == "conv":
-                    dwt = ops.conv1d_tc_wgrad(g, a_in, s.K, s.stride, s.dil, s.pad[0], Lp=Lout, Lq=Lin)
+                    dwt = ops.conv1d_tc_wgrad(g, a_in, s.K, s.stride, s.dil, s.pad[0], Lp=Lout, Lq=Lin, dbias=db)
                 else:
                     dwt = ops.conv1d_tc_wgrad(a_in, g, s.K, s.stride, 1, s.pad[0], Lp=Lin, Lq=Lout)
                 # dwt is [S][K][C0p][C1p] in the parameter's own (C0, C1) order for both kinds
                 wn_jobs.append((i, dwt, v, gpar, pw.norm))
-            if bias is not None and bias.requires_grad:
-                grads[3 * i + 2] = ops.colsum_bf16(g, Lout, s.Cout)
+            if want_db:
+                grads[3 * i + 2] = db[:s.Cout] if db is not None else ops.colsum_bf16(g, Lout, s.Cout)
             # ---- input gradient
             need_prev = i > 0 or ctx.x_requires_grad
             if not need_prev:
@@ -507,8 +512,13 @@ class TcChainFn(torch.autograd.Function):
             if prev in skip:
                 add = skip.pop(prev)
             e = ext.get(prev) if prev >= 0 else None
+            fm_d = None
             if ctx.fm and prev >= 0 and dstats is not None:
-                e = ops.fm_grad(a_in, dstats[prev], Lin, s.pre_slope)
+                # feature-matching gradient of hidden feature `prev`: computed inside this layer's dgrad epilogue from
+                # the saved operand a_in (real and fake rows), no gradient tensor of its own
+                fm_d = dstats[prev]
+                if s.pre_act != ops.ACT_LEAKY or use_c1:
+                    raise _lib.RaveB200Error("fused feature-matching gradient needs a LeakyReLU operand")
             if e is not None:
                 add = e if add is None else (add + e)
             dact = a_in if s.pre_act == ops.ACT_LEAKY else None
@@ -536,7 +546,7 @@ class TcChainFn(torch.autograd.Function):
                     padp = (s.K - 1) * s.dil - s.pad[0]
                     ops.conv1d_tc(g, pw.dgrad, None, None, 1, s.dil, (padp, 0), ops.ACT_NONE, s.pre_slope,
                                   want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout,
-                                  out_rows=in_pitch, res_bf16=add, dact_src=dact)
+                                  out_rows=in_pitch, res_bf16=add, dact_src=dact, fm_d=fm_d)
                 else:
                     for p, (wt, padpp) in enumerate(pw.dgrad_phases):
                         Lp = (Lin - p + s.stride - 1) // s.stride
@@ -547,11 +557,11 @@ class TcChainFn(torch.autograd.Function):
                         ops.conv1d_tc(g, wt, None, None, 1, 1, (padpp, 0), ops.ACT_NONE, s.pre_slope,
                                       want_f32=False, want_act=False, out_act=gp, out_rows=in_pitch,
                                       out_row_stride=s.stride, out_row_offset=p, Lout=Lp, Lin=Lout, res_bf16=add,
-                                      dact_src=dact)
+                                      dact_src=dact, fm_d=fm_d)
             else:
                 ops.conv1d_tc(g, pw.dgrad, None, None, s.stride, 1, (s.pad[0], 0), ops.ACT_NONE, s.pre_slope,
                               want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout, out_rows=in_pitch,
-                              res_bf16=add, dact_src=dact)
+                              res_bf16=add, dact_src=dact, fm_d=fm_d)
             g_cur = gp
             if i == 0:
                 gx = gp

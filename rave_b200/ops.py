@@ -379,9 +379,11 @@ def conv1d_tc_supported(Cin, Cout, K=1, stride=1, dil=1):
 
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=ACT_NONE, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
-              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2):
+              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2,
+              fm_d=None):
     """xa_cl [B,Lin,Cin] bf16 (activated operand), wt [K,Cout,Cin] bf16 -> (out_f32 [B,Lout,Cout] fp32,
-    out_act [B,Lout,Cout] bf16 = act(out)); either may be None."""
+    out_act [B,Lout,Cout] bf16 = act(out)); either may be None.  fm_d (2 device floats): fused feature-matching
+    gradient of a [real; fake] batch, see include/rave_b200.h."""
     B, in_pitch, Cin = xa_cl.shape          # allocated rows per batch; true length = Lin (slack rows zero)
     if Lin is None:
         Lin = in_pitch
@@ -397,13 +399,15 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
         out_act = torch.empty(B, rows, Cout, dtype=torch.bfloat16, device=xa_cl.device)
     call("rave_conv1d_tc_fwd", ptr(xa_cl), ptr(wt), ptr(bias), ptr(res_cl), ptr(res_bf16), ptr(dact_src),
          ptr(res_act), float(res_slope), ptr(out_f32), ptr(out_act), B, Cin, Lin, in_pitch, Cout, Lout, K, stride, dil, pad[0], act, float(slope),
-         out_rows, out_row_stride, out_row_offset, stream_ptr())
+         out_rows, out_row_stride, out_row_offset, fm_d.data_ptr() if fm_d is not None else None,
+         B // 2 if fm_d is not None else 0, stream_ptr())
     return out_f32, out_act
 
 
-def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None):
+def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None, dbias=None):
     """dwt[k][m][n] = sum_{b,l} P[b,l,m] * Q[b, l*stride + k*dil - pad_l, n]  (bf16 operands, fp32 result).
-    Tensors may be allocated with a row pitch larger than their true length (Lp / Lq)."""
+    Tensors may be allocated with a row pitch larger than their true length (Lp / Lq).
+    dbias [Cm] fp32 (pre-zeroed): += column sums of P over its Lp valid rows (conv bias gradient)."""
     B, p_pitch, Cm = P_cl.shape
     _, q_pitch, Cn = Q_cl.shape
     Lp = p_pitch if Lp is None else Lp
@@ -412,8 +416,8 @@ def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None):
         raise _lib.RaveB200Error("conv1d_tc_wgrad: operands must be bf16")
     splits = _lib.load().rave_conv1d_tc_wgrad_splits(B, Cm, Lp, Cn, K)
     dwt = torch.empty(splits, K, Cm, Cn, dtype=torch.float32, device=P_cl.device)   # per-slice partial sums
-    call("rave_conv1d_tc_wgrad", ptr(P_cl), ptr(Q_cl), ptr(dwt), B, Cm, Lp, p_pitch, Cn, Lq, q_pitch, K, stride,
-         dil, pad_l, stream_ptr())
+    call("rave_conv1d_tc_wgrad", ptr(P_cl), ptr(Q_cl), ptr(dwt), dbias.data_ptr() if dbias is not None else None,
+         B, Cm, Lp, p_pitch, Cn, Lq, q_pitch, K, stride, dil, pad_l, stream_ptr())
     return dwt
 
 

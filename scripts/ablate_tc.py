@@ -23,7 +23,7 @@ SHAPES = [
 ]
 CONFIGS = [
     ("default", {}),
-    ("per-thread stores", {"RAVE_TC_TMASTORE": "0"}),
+    ("staged TMA stores", {"RAVE_TC_TMASTORE": "1"}),
     ("no epilogue stores", {"RAVE_TC_DBG": "1"}),
     ("no loads at all", {"RAVE_TC_DBG": "6"}),
     ("no loads, no stores", {"RAVE_TC_DBG": "7"}),

@@ -14,7 +14,8 @@ def _bf16(t):
 
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=0, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
-              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2):
+              out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2,
+              fm_d=None):
     B, in_pitch, Cin = xa_cl.shape
     Lin = in_pitch if Lin is None else Lin
     K, Cout, _ = wt.shape
@@ -45,6 +46,12 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     if dact_src is not None:
         sgn = torch.signbit(dact_src[:, idx].float())
         v = torch.where(sgn, v * slope, v)
+    if fm_d is not None:
+        a = dact_src[:, idx].float()
+        h = torch.where(a > 0, a, a / slope)
+        hr, hf = h[:B // 2], h[B // 2:]
+        sd = torch.sign(hr - hf)
+        v = v + torch.cat([fm_d[0] * sd + fm_d[1] * torch.sign(hr), -fm_d[0] * sd], 0)
     if res_bf16 is not None:
         v = v + res_bf16[:, idx].float()
     if res_act is not None:
@@ -64,12 +71,14 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     return out_f32, out_act
 
 
-def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None):
+def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None, dbias=None):
     B, p_pitch, Cm = P_cl.shape
     _, q_pitch, Cn = Q_cl.shape
     Lp = p_pitch if Lp is None else Lp
     Lq = q_pitch if Lq is None else Lq
     P = P_cl[:, :Lp].float()
+    if dbias is not None:
+        dbias += P.sum((0, 1))
     Q = Q_cl[:, :q_pitch].float()
     if q_pitch > Lq:
         assert float(Q[:, Lq:].abs().max()) == 0.0

@@ -90,11 +90,13 @@ def test_conv1d_tc_wgrad_vs_oracle(case):
     (dw_ref,) = torch.autograd.grad(y, w, dy)
     P = dy.permute(0, 2, 1).contiguous().bfloat16().cuda()
     Q = x.permute(0, 2, 1).contiguous().bfloat16().cuda()
-    dwt = ops.conv1d_tc_wgrad(P, Q, K, stride, dil, pad_l)
+    db = torch.zeros(Cm, device="cuda")
+    dwt = ops.conv1d_tc_wgrad(P, Q, K, stride, dil, pad_l, dbias=db)
     dw = ops.tapmajor_to_weight(dwt)
     torch.cuda.synchronize()
     assert dw.shape == dw_ref.shape
     assert rel_l2(dw, dw_ref) < 2e-5
+    assert rel_l2(db, dy.sum((0, 2))) < 1e-5          # fused bias gradient (column sums of P)
 
 
 def test_small_channel_kernels_vs_emulator():
@@ -205,3 +207,30 @@ def test_score_tail_kernels_vs_emulator():
         torch.cuda.synchronize()
         assert g_gpu.dtype == torch.bfloat16 and g_gpu.shape == (B2, pitch, C)
         assert torch.equal(g_gpu.float().cpu(), g_ref.bfloat16().float())
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 96, 300, 3, 1), (6, 192, 96, 515, 2, 4)])
+def test_conv1d_tc_fused_fm_gradient_vs_emulator(shape):
+    """dgrad-style launch with the feature-matching gradient fused into the epilogue (LeakyReLU' mask from the saved
+    operand, then + d0 sgn(h_r - h_f) + d1 sgn(h_r) / - d0 sgn(h_r - h_f)), plain and phase-interleaved rows."""
+    from rave_b200 import ops
+    from tests import tc_emulator as E
+    B, Cin, Cout, L, K, rs = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, L, Cin, generator=g).bfloat16()
+    wt = (torch.randn(K, Cout, Cin, generator=g) / (Cin * K) ** 0.5).bfloat16()
+    rows = L * rs + 3
+    a = torch.nn.functional.leaky_relu(torch.randn(B, rows, Cout, generator=g), 0.2).bfloat16()
+    d = torch.tensor([0.37, -0.21])
+    kw = dict(stride=1, dil=1, pad=(K - 1, 0), act=0, slope=0.2, want_f32=False, want_act=False, Lout=L, Lin=L,
+              out_rows=rows, out_row_stride=rs, out_row_offset=rs - 1)
+    ref = torch.zeros(B, rows, Cout, dtype=torch.bfloat16)
+    E.conv1d_tc(x, wt, None, None, out_act=ref, dact_src=a, fm_d=d, **kw)
+    out = torch.zeros(B, rows, Cout, dtype=torch.bfloat16, device="cuda")
+    ops.conv1d_tc(x.cuda(), wt.cuda(), None, None, out_act=out, dact_src=a.cuda(), fm_d=d.cuda(), **kw)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), ref.float()) < 4e-3          # bf16 rounding of the stored gradient
+    idx = torch.arange(L) * rs + rs - 1
+    mask = torch.ones(rows, dtype=torch.bool)
+    mask[idx] = False
+    assert float(out[:, mask].float().abs().max()) == 0.0   # rows of other phases untouched
