@@ -33,6 +33,7 @@ def summarize(tag, log):
     for (name, ints, ptrs), (c, ms) in agg.items():
         fam[name] += ms
         extra = ""
+        t = 0.0
         if name == "rave_conv1d_tc_fwd":
             Bc, Cin, Lin, pitch, Cout, Lout, K, stride, dil, pad = ints[:10]
             fl = 2.0 * Bc * Lout * Cout * Cin * K
@@ -52,11 +53,18 @@ def summarize(tag, log):
             by = 2.0 * Bc * (Lp * Cm + Lq * Cn)
             t = max(fl / PEAK_F, by / PEAK_B) * 1e3
             extra = f" GF={fl/1e9:7.1f} MB={by/1e6:7.1f} roof={t*1e3:7.1f}us frac={t*c/ms:5.2f} TF={fl*c/ms/1e9:6.0f}"
-        rows.append((ms, c, name, ints, ptrs, extra))
+        rows.append((ms, c, name, ints, ptrs, extra, t * c))
     for n, ms in sorted(fam.items(), key=lambda kv: -kv[1]):
         print(f"  {ms:8.3f} ms  {ms/tot*100:5.1f}%  {n}")
+    tot_roof = sum(r[6] for r in rows)
+    tot_tc = sum(r[0] for r in rows if r[6] > 0)
+    print(f"  tcgen05 launches: {tot_tc:.3f} ms measured vs {tot_roof:.3f} ms roofline "
+          f"(max(flops/{PEAK_F/1e12:.0f} TF, bytes/{PEAK_B/1e12:.1f} TB/s) per launch)")
+    print("  -- per shape, sorted by time above the roofline")
+    for ms, c, name, ints, ptrs, extra, roof in sorted(rows, key=lambda r: -(r[0] - r[6]))[:25]:
+        print(f"  +{(ms-roof)*1e3:7.1f}us  {ms*1e3:8.1f}us x{c:3d} {name[5:]:20s} {ints} {ptrs}{extra}")
     print("  -- per shape (sorted by total time)")
-    for ms, c, name, ints, ptrs, extra in sorted(rows, key=lambda r: -r[0])[:70]:
+    for ms, c, name, ints, ptrs, extra, roof in sorted(rows, key=lambda r: -r[0])[:70]:
         print(f"  {ms*1e3:8.1f}us x{c:3d} avg {ms/c*1e3:7.1f}us {name[5:]:24s} {ints} {ptrs}{extra}")
 
 
