@@ -247,7 +247,7 @@ typedef struct rave_wprep_layer {
   const float *dwt;            /* backward: [splits][K][C0p][C1p] fp32 partial weight gradients       */
   float *dv, *dg;              /* backward: gradients of v and g                                      */
   int C0, C1, K, C0p, C1p, nA, nB, splits;
-  int tapsA[32], tapsB[32];
+  int tapsA[32], tapsB[32];    /* tap index, or -1 for an all-zero slab (phase-fused layouts)          */
 } rave_wprep_layer;
 int rave_weight_prep_tc_multi(int n, const rave_wprep_layer *layers, void *stream);
 int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers, void *stream);

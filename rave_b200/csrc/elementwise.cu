@@ -561,7 +561,8 @@ __global__ void __launch_bounds__(256) mt_prep_kernel(const __grid_constant__ Mt
       for (int r = ty; r < 32; r += 8) {
         const int c0 = c0t + r, c1 = c1t + tx;
         if (c0 < C0p && c1 < C1p)
-          L.outA[((size_t)a * C0p + c0) * C1p + c1] = __float2bfloat16_rn(sw[r * pitch + tx * K + k] * scale[r]);
+          L.outA[((size_t)a * C0p + c0) * C1p + c1] =
+              __float2bfloat16_rn(k == 255 ? 0.f : sw[r * pitch + tx * K + k] * scale[r]);     // tap -1: zero slab
       }
     }
   }
@@ -571,7 +572,8 @@ __global__ void __launch_bounds__(256) mt_prep_kernel(const __grid_constant__ Mt
       for (int r = ty; r < 32; r += 8) {
         const int c1 = c1t + r, c0 = c0t + tx;
         if (c0 < C0p && c1 < C1p)
-          L.outB[((size_t)b * C1p + c1) * C0p + c0] = __float2bfloat16_rn(sw[tx * pitch + r * K + k] * scale[tx]);
+          L.outB[((size_t)b * C1p + c1) * C0p + c0] =
+              __float2bfloat16_rn(k == 255 ? 0.f : sw[tx * pitch + r * K + k] * scale[tx]);
       }
     }
   }

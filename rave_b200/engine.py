@@ -206,6 +206,24 @@ def _phase_taps(K: int, stride: int, pad: int, p: int):
     return order, (n - 1) - c0
 
 
+def _fused_phase_taps(K: int, stride: int, pad: int):
+    """All `stride` output phases of a transposed map as ONE stride-1 conv whose output row q holds the `stride`
+    positions q*stride + p side by side: returns (taps, J, pad_l) with taps[j*stride + p] = the parameter tap that
+    phase p applies to source row q + j - pad_l (or -1: no tap, zero slab).  The weight [J][stride*C][C'] built from
+    this list turns stride launches with strided output rows into one launch with stride-times wider rows
+    (same bytes in memory), and the shared source rows are fetched once instead of once per phase."""
+    phases = [_phase_taps(K, stride, pad, p) for p in range(stride)]
+    omin = min(-padpp for _, padpp in phases)
+    omax = max(len(order) - 1 - padpp for order, padpp in phases)
+    J = omax - omin + 1
+    taps = []
+    for j in range(J):
+        for order, padpp in phases:
+            i = omin + j + padpp
+            taps.append(order[i] if 0 <= i < len(order) else -1)
+    return taps, J, -omin
+
+
 class _PreparedWeights:
     """Effective weight of one layer in every tap-major bf16 layout the kernels need.  `plan()` decides
     which layouts / tap orders are required; `prepare_layers()` produces them for a whole chain with ONE
@@ -220,10 +238,10 @@ class _PreparedWeights:
             self.C0p, self.C1p = spec.Cin + spec.cin_pad, spec.Cout + spec.cout_pad
         self.norm = None
         self.fwd = None           # conv: [K][Cout][Cin]
-        self.fwd_phases = None    # convT: per output phase (wt [n][Cout][Cin], pad'')
-        self.dgrad = None         # stride-1 conv: flipped taps [K][Cin][Cout]; convT: [K][Cin][Cout]
-        self.dgrad_phases = None  # strided conv: per input phase (wt [n][Cin][Cout], pad'')
-        self.phases = None
+        self.fwd_fused = None     # convT: all output phases as one conv, wt [J][stride*Cout][Cin] (see
+        self.dgrad = None         #   _fused_phase_taps); stride-1 conv: flipped taps [K][Cin][Cout]; convT: [K][Cin][Cout]
+        self.dgrad_fused = None   # strided conv: all input phases as one conv, wt [J][stride*Cin][Cout]
+        self.fused_J = self.fused_pad = 0
         self.need_dgrad = need_dgrad
         if spec.kind == "conv":
             self.tapsA = list(range(K)) if need_fwd else []
@@ -232,34 +250,25 @@ class _PreparedWeights:
             elif s == 1:
                 self.tapsB = list(range(K - 1, -1, -1))
             else:
-                self.phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
-                self.tapsB = [k for order, _ in self.phases for k in order]
+                self.tapsB, self.fused_J, self.fused_pad = _fused_phase_taps(K, s, spec.pad[0])
         else:
-            self.phases = [_phase_taps(K, s, spec.pad[0], p) for p in range(s)]
-            self.tapsB = [k for order, _ in self.phases for k in order]
+            self.tapsB, self.fused_J, self.fused_pad = _fused_phase_taps(K, s, spec.pad[0])
             self.tapsA = list(range(K)) if need_dgrad else []
+        if len(self.tapsB) > 32:
+            raise _lib.RaveB200Error(f"phase-fused layout of K={K}, stride={s} needs {len(self.tapsB)} > 32 slabs")
 
     def finalize(self, norm, outA, outB):
         spec = self.spec
         self.norm = norm
-
-        def split(buf):
-            out, off = [], 0
-            for order, padpp in self.phases:
-                n = len(order)
-                out.append((buf[off:off + n] if n else None, padpp))
-                off += n
-            return out
-
         if spec.kind == "conv":
             self.fwd = outA
             if self.need_dgrad:
                 if spec.stride == 1:
                     self.dgrad = outB
-                else:
-                    self.dgrad_phases = split(outB)
-        else:
-            self.fwd_phases = split(outB)
+                else:       # [J*stride][Cin_p][Cout_p] -> [J][stride*Cin_p][Cout_p]
+                    self.dgrad_fused = outB.view(self.fused_J, spec.stride * self.C1p, self.C0p)
+        else:               # [J*stride][Cout_p][Cin_p] -> [J][stride*Cout_p][Cin_p]
+            self.fwd_fused = outB.view(self.fused_J, spec.stride * self.C1p, self.C0p)
             self.dgrad = outA
         return self
 
@@ -405,15 +414,22 @@ class TcChainFn(torch.autograd.Function):
                               want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act, Lout=Lout,
                               Lin=Lin, out_rows=pitch, res_act=res_act, res_slope=res_slope)
             else:
-                for p, (wt, padpp) in enumerate(pw.fwd_phases):
-                    if wt is None:
-                        raise _lib.RaveB200Error("transposed conv with an empty phase is not supported")
-                    Lp = (Lout - p + s.stride - 1) // s.stride
-                    if Lp <= 0:
-                        continue
-                    ops.conv1d_tc(a, wt, bias_p, None, 1, 1, (padpp, 0), act_code, act_slope, want_f32=False,
-                                  want_act=False, out_f32=out_f32, out_act=out_act, out_rows=pitch,
-                                  out_row_stride=s.stride, out_row_offset=p, Lout=Lp, Lin=Lin)
+                # transposed conv: the `stride` output phases side by side in one stride-1 conv (output row q =
+                # positions q*stride .. q*stride + stride-1: the same bytes as the [B][pitch][Cout] tensor)
+                st = s.stride
+                if pitch % st:
+                    raise _lib.RaveB200Error("transposed conv: the output pitch must be a multiple of the stride")
+                rows_q = pitch // st
+                bias_f = bias_p.detach().repeat(st) if bias_p is not None else None
+                ops.conv1d_tc(a, pw.fwd_fused, bias_f, None, 1, 1, (pw.fused_pad, 0), act_code, act_slope,
+                              want_f32=False, want_act=False,
+                              out_f32=out_f32.view(B, rows_q, st * cout_p) if out_f32 is not None else None,
+                              out_act=out_act.view(B, rows_q, st * cout_p) if out_act is not None else None,
+                              out_rows=rows_q, Lout=rows_q, Lin=Lin)
+                if pitch > Lout:         # positions beyond the true length were computed too: back to zero
+                    for t in (out_f32, out_act):
+                        if t is not None:
+                            t[:, Lout:].zero_()
             if fm and nxt is not None:
                 if act_code != ops.ACT_LEAKY or s.cout_pad:
                     raise _lib.RaveB200Error("feature-matching mode needs LeakyReLU between the layers")
@@ -548,16 +564,21 @@ class TcChainFn(torch.autograd.Function):
                                   want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout,
                                   out_rows=in_pitch, res_bf16=add, dact_src=dact, fm_d=fm_d)
                 else:
-                    for p, (wt, padpp) in enumerate(pw.dgrad_phases):
-                        Lp = (Lin - p + s.stride - 1) // s.stride
-                        if Lp <= 0:
-                            continue
-                        if wt is None:
-                            raise _lib.RaveB200Error("strided conv with an empty dgrad phase is not supported")
-                        ops.conv1d_tc(g, wt, None, None, 1, 1, (padpp, 0), ops.ACT_NONE, s.pre_slope,
-                                      want_f32=False, want_act=False, out_act=gp, out_rows=in_pitch,
-                                      out_row_stride=s.stride, out_row_offset=p, Lout=Lp, Lin=Lout, res_bf16=add,
-                                      dact_src=dact, fm_d=fm_d)
+                    # strided conv: the `stride` input phases side by side in one stride-1 conv over g (row q of the
+                    # result = input positions q*stride .. +stride-1); g rows are fetched once, not once per phase
+                    st = s.stride
+                    if in_pitch % st:
+                        raise _lib.RaveB200Error("strided conv dgrad: the operand pitch must be a multiple of the stride")
+                    rows_q = in_pitch // st
+                    wide = st * cin_p
+
+                    def v4(t):
+                        return t.view(B, rows_q, wide) if t is not None else None
+                    ops.conv1d_tc(g, pw.dgrad_fused, None, None, 1, 1, (pw.fused_pad, 0), ops.ACT_NONE, s.pre_slope,
+                                  want_f32=False, want_act=False, out_act=v4(gp), out_rows=rows_q, Lout=rows_q,
+                                  Lin=Lout, res_bf16=v4(add), dact_src=v4(dact), fm_d=fm_d)
+                    if in_pitch > Lin:
+                        gp[:, Lin:].zero_()
             else:
                 ops.conv1d_tc(g, pw.dgrad, None, None, s.stride, 1, (s.pad[0], 0), ops.ACT_NONE, s.pre_slope,
                               want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout, out_rows=in_pitch,

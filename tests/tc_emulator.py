@@ -104,7 +104,7 @@ def weight_prep_tc(v, g, tapsA, tapsB, C0p, C1p):
     if g is not None:
         norm = v3.reshape(C0, -1).norm(2, 1)
         w = v3 * (g.reshape(C0, 1, 1) / norm.reshape(C0, 1, 1))
-    wp = F.pad(w, (0, 0, 0, C1p - C1, 0, C0p - C0))
+    wp = F.pad(w, (0, 1, 0, C1p - C1, 0, C0p - C0))          # extra all-zero tap: index -1
     outA = _bf16(wp[:, :, tapsA].permute(2, 0, 1).contiguous()) if tapsA else None
     outB = _bf16(wp[:, :, tapsB].permute(2, 1, 0).contiguous()) if tapsB else None
     return norm, outA, outB
