@@ -25,8 +25,7 @@ namespace tc {
 
 constexpr int BLOCK_M = 128;
 constexpr int NUM_THREADS = 192;
-constexpr int NUM_THREADS2 = 320;      // CTA-pair kernel: producer, MMA issuer, 8 epilogue warps (2 per TMEM quadrant)
-constexpr int EPI_WARPS2 = 8;
+constexpr int NUM_THREADS2 = 320;      // CTA-pair kernel: producer, MMA issuer, up to 8 epilogue warps (2 per TMEM quadrant)
 constexpr int ACC_STAGES = 2;
 
 struct TcParams {
@@ -50,8 +49,6 @@ struct TcParams {
   const float *fm_d;       // feature-matching gradient fused into a dgrad epilogue (or null): dact_src is the bf16
   long fm_half;            //   operand a = LeakyReLU(h) of [real; fake] rows, fm_half elements apart; adds
   int fm_bh;               //   d0 sgn(h_r-h_f) + d1 sgn(h_r) to real rows (b < fm_bh), -d0 sgn(h_r-h_f) to fake rows
-  int tma_store;           // out_act goes through shared-memory staging + bulk tensor stores (CTA-pair kernel)
-  int st_rows, st_batches; // rows x batches of one epilogue warp's 32 tile rows (box of the store tensor map)
   int stages;              // pipeline depth actually used (<= the layout's STAGES); RAVE_TC_STAGES overrides
   int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue stores, 2 = skip the
                            // activation TMA loads, 4 = skip the weight TMA loads (results are garbage)
@@ -75,7 +72,7 @@ struct SmemLayout {
 // (C = 96 / 192 blocks) are limited by the bytes in flight per SM, not by arithmetic.
 template <int CW>
 __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow,
-                                             uint8_t *stg = nullptr, int lane = 0, int fm_side = 0) {
+                                             int fm_side = 0) {
   float v[CW];
   float4 rf[CW / 4];
   uint4 rb[CW / 8], dm[CW / 8], ra[CW / 8], pm[CW / 8];
@@ -109,11 +106,7 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
   }
   if (CW == 32) tmem_ld_32x32(taddr, v);
   else tmem_ld_32x16(taddr, v);       // warp-collective: every lane participates, valid or not
-  if (!valid && !stg) return;
-  if (!valid) {                       // staged store: every row of the box is written (TMA clips the invalid ones)
-#pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = 0.f;
-  }
+  if (!valid) return;
   if (p.bias) {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] += __ldg(p.bias + co + i);
@@ -181,7 +174,7 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
       v[4 * i + 0] += rf[i].x; v[4 * i + 1] += rf[i].y; v[4 * i + 2] += rf[i].z; v[4 * i + 3] += rf[i].w;
     }
   }
-  if (p.out_f32 && valid) {
+  if (p.out_f32) {
     float4 *o4 = reinterpret_cast<float4 *>(p.out_f32 + off);
 #pragma unroll
     for (int i = 0; i < CW / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -190,8 +183,7 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
     uint4 *o = reinterpret_cast<uint4 *>(p.out_act + off);
 #pragma unroll
     for (int i = 0; i < CW / 8; ++i) {
-      // staged: row `lane` of a [32 rows][64 bytes] SWIZZLE_64B box, 16-byte chunk i at i ^ ((row >> 1) & 3)
-      uint4 *dst = stg ? reinterpret_cast<uint4 *>(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) : (o + i);
+      uint4 *dst = o + i;
       uint32_t pk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -216,37 +208,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t taddr, i
   constexpr int MAIN = BLOCK_N / 32 * 32;
 #pragma unroll 1
   for (int c0 = part * 32; c0 < MAIN; c0 += parts * 32)
-    tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow, nullptr, 0, fm_side);
-  if (MAIN < BLOCK_N && part == 0) tc_epi_chunk<16>(p, taddr + MAIN, n0 + MAIN, valid, orow, nullptr, 0, fm_side);
-}
-
-// Tile epilogue with staged stores (CTA-pair kernel): each warp packs its 32 rows x 32 channels into a 2 KB
-// SWIZZLE_64B box in shared memory and ONE lane hands it to the TMA unit (bulk tensor store, clipped to the valid
-// rows / batches by the tensor map).  Per-thread row-wise 16-byte stores cost 32 partial-sector transactions per
-// instruction and kept the LSU busy for ~3000 clk per 128 x 192 tile -- as long as the MMAs of a K=5 layer.
-constexpr int STG_WARP_BYTES = 2 * 2048;      // two boxes per warp (double buffer)
-template <int BLOCK_N>
-__device__ __forceinline__ void tc_epilogue_staged(const TcParams &p, const CUtensorMap *tmap_o, uint32_t taddr,
-                                                   int n0, bool valid, size_t orow, uint8_t *stg_warp, int lane,
-                                                   int l_start, int b_start, bool any_valid, uint32_t &chunk_ctr,
-                                                   int fm_side, int part, int parts) {
-  static_assert(BLOCK_N % 32 == 0, "staged epilogue works on 32-channel chunks");
-#pragma unroll 1
-  for (int c0 = part * 32; c0 < BLOCK_N; c0 += parts * 32) {
-    uint8_t *stg = stg_warp + (chunk_ctr & 1u) * 2048;
-    if (chunk_ctr >= 2) {
-      if (lane == 0) tma_store_wait_read<1>();      // the store issued two chunks ago has read this buffer
-      __syncwarp();
-    }
-    tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow, stg, lane, fm_side);
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      if (any_valid) tma_store_3d(tmap_o, stg, n0 + c0, l_start, b_start);
-      tma_store_commit();
-    }
-    ++chunk_ctr;
-  }
+    tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow, fm_side);
+  if (MAIN < BLOCK_N && part == 0) tc_epi_chunk<16>(p, taddr + MAIN, n0 + MAIN, valid, orow, fm_side);
 }
 
 template <int BLOCK_N, int BLOCK_K>
@@ -418,14 +381,13 @@ struct SmemLayout2 {
   static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STG_OFFSET = BAR_OFFSET + 1024;                 // epilogue staging: 8 warps x 2 boxes x 2 KB
-  static constexpr int TOTAL = STG_OFFSET + EPI_WARPS2 * STG_WARP_BYTES + 1024;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const __grid_constant__ CUtensorMap tmap_o, const TcParams p) {
+                const TcParams p) {
   using L = SmemLayout2<BLOCK_N, BLOCK_K>;
   constexpr int STAGES = L::STAGES;
   constexpr int UNITS = L::UNITS;
@@ -452,6 +414,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int n_mp = (n_mt + 1) >> 1;                  // M tile pairs
   const int num_tiles = n_mp * p.n_nt;
   const int kblocks = p.K * p.num_kb;
+  const int epi_warps = (int)(blockDim.x >> 5) - 2;      // 4 or 8 (launch configuration)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -462,7 +425,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 2 * EPI_WARPS2);      // leader's: the epilogue warps of both CTAs
+      mbar_init(&tempty_bar[s], 2 * epi_warps);       // leader's: the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -576,10 +539,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp >= 2) {
     // =========================== epilogue (4 warps in each CTA) ===========================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int part = (warp - 2) >> 2;          // which of the quadrant's two warps: alternate 32-column chunks
+    const int part = (warp - 2) >> 2;          // which of the quadrant's warps: alternate 32-column chunks
+    const int parts = epi_warps >> 2;
     const int row = quad * 32 + lane;
-    uint8_t *stg_warp = smem + L::STG_OFFSET + (warp - 2) * STG_WARP_BYTES;
-    uint32_t chunk_ctr = 0;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int acc = it & 1;
@@ -597,22 +559,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
       const int fm_side = p.fm_d ? (b < p.fm_bh ? 1 : -1) : 0;
-      if (p.tma_store) {
-        const int r0 = quad * 32;                   // first tile row of this warp
-        const int b_start = bg * p.BB + r0 / p.BL;
-        const int l_start = lt * p.BL + r0 % p.BL;
-        const bool any_valid = (mt < n_mt) && (b_start < p.B) && (l_start < p.Lout) && !(p.dbg & 1);
-        tc_epilogue_staged<BLOCK_N>(p, &tmap_o, taddr, n0, valid, orow, stg_warp, lane, l_start, b_start, any_valid,
-                                    chunk_ctr, fm_side, part, EPI_WARPS2 / 4);
-      } else {
-        tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow, fm_side, part, EPI_WARPS2 / 4);
-      }
+      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow, fm_side, part, parts);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
     }
-    if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last bulk stores
-    __syncwarp();
   }
 
   tc_fence_before();
@@ -670,6 +621,27 @@ static int pick_block_n(int Cout, long m_tiles) {
   return best;
 }
 
+// CTA-pair kernel: pick the N tile by a small cost model instead of "largest tile that fills the machine".
+//   waves(BN) = ceil(pair-tiles / 74),  stage clocks = max(MMA = 2*BN (4 MMAs of a 256 x BN x 16 atom at BN/2 clk),
+//   fill = (16 KB activations + BN*64 B weights per CTA) / ~60 B/clk);  cost = waves * stage clocks.
+// The decoder / encoder blocks with few rows and many channels (768 x 768 at 2048 rows) were given BN = 64 to reach
+// 148 tiles: two waves of fill-bound tiles; BN = 128 does the same work in one wave of better-balanced tiles.
+static int pick_block_n2(int Cout, long m_tiles) {
+  const int cands[] = {256, 192, 128, 96, 64};
+  const long n_mp = (m_tiles + 1) / 2;
+  int best = 0;
+  double best_cost = 0;
+  for (int c : cands) {
+    if (Cout % c) continue;
+    const long tiles = n_mp * (Cout / c);
+    const long waves = (tiles + 73) / 74;
+    const double mma = 2.0 * c, fill = (16384.0 + 64.0 * c) / 60.0;
+    const double cost = (double)waves * (mma > fill ? mma : fill);
+    if (!best || cost < best_cost) { best = c; best_cost = cost; }
+  }
+  return best;
+}
+
 template <int BN, int BK>
 static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t stream) {
   using L = SmemLayout<BN, BK>;
@@ -694,8 +666,7 @@ static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &
 }
 
 template <int BN, int BK>
-static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const TcParams &p,
-                   cudaStream_t stream) {
+static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t stream) {
   using L = SmemLayout2<BN, BK>;
   static bool attr = false;
   if (!attr) {
@@ -720,20 +691,27 @@ static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorM
     const char *e = getenv("RAVE_TC_STAGES");
     if (e && atoi(e) >= 2 && atoi(e) < L::STAGES) q.stages = atoi(e);
   }
-  conv_tc2_kernel<BN, BK><<<2 * pairs, NUM_THREADS2, L::TOTAL, stream>>>(ta, tb, to, q);
+  // epilogue warps: 8 (two per TMEM quadrant) when a tile has little MMA work per output column -- those layers are
+  // bound by the latency of the TMEM-load / convert / store chain -- else 4 (the extra warps only take issue slots
+  // from the tensor-bound loops); RAVE_TC_EPIWARPS overrides
+  int epi = (long)p.K * p.Cin <= 1024 ? 8 : 4;
+  {
+    const char *e = getenv("RAVE_TC_EPIWARPS");
+    if (e && (atoi(e) == 4 || atoi(e) == 8)) epi = atoi(e);
+  }
+  conv_tc2_kernel<BN, BK><<<2 * pairs, 64 + 32 * epi, L::TOTAL, stream>>>(ta, tb, q);
   RAVE_CHECK_LAUNCH("conv1d_tc(2cta)");
   return 0;
 }
 
 template <int BK>
-static int dispatch_n2(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const TcParams &p,
-                       cudaStream_t s) {
+static int dispatch_n2(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t s) {
   switch (bn) {
-    case 256: return launch2<256, BK>(ta, tb, to, p, s);
-    case 192: return launch2<192, BK>(ta, tb, to, p, s);
-    case 128: return launch2<128, BK>(ta, tb, to, p, s);
-    case 96: return launch2<96, BK>(ta, tb, to, p, s);
-    case 64: return launch2<64, BK>(ta, tb, to, p, s);
+    case 256: return launch2<256, BK>(ta, tb, p, s);
+    case 192: return launch2<192, BK>(ta, tb, p, s);
+    case 128: return launch2<128, BK>(ta, tb, p, s);
+    case 96: return launch2<96, BK>(ta, tb, p, s);
+    case 64: return launch2<64, BK>(ta, tb, p, s);
   }
   set_error("conv1d_tc(2cta): no kernel for BLOCK_N=%d", bn);
   return 1;
@@ -814,7 +792,6 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   p.fm_half = (long)fm_bh * p.out_rows * Cout;
   p.stages = 0;
   p.dbg = 0;
-  p.tma_store = 0; p.st_rows = 0; p.st_batches = 0;
   {
     const char *e = getenv("RAVE_TC_DBG");
     if (e) p.dbg = atoi(e);
@@ -824,17 +801,19 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   p.BL = BL; p.BB = 128 / BL;
   p.n_lt = ceil_div(Lout, BL);
   p.n_bg = ceil_div(B, p.BB);
-  const int BN = pick_block_n(Cout, (long)p.n_lt * p.n_bg);
-  RAVE_CHECK_ARG(BN > 0, "conv1d_tc: no BLOCK_N for Cout=%d", Cout);
-  p.n_nt = Cout / BN;
-  p.num_kb = ceil_div(Cin, BK);
-  // CTA pairs (cta_group::2, validated on B200: scripts/check_2cta.py): default on, RAVE_TC_2CTA=0 disables.
-  // Needs N % 32 == 0, a K-block of 64 (the tested configuration) and at least two M tiles.
   static int want2 = -1;
   if (want2 < 0) {
     const char *e = getenv("RAVE_TC_2CTA");
     want2 = (e && e[0] == '0') ? 0 : 1;
   }
+  int BN = 0;
+  if (want2 && (long)p.n_lt * p.n_bg >= 2) BN = pick_block_n2(Cout, (long)p.n_lt * p.n_bg);
+  if (!BN) BN = pick_block_n(Cout, (long)p.n_lt * p.n_bg);
+  RAVE_CHECK_ARG(BN > 0, "conv1d_tc: no BLOCK_N for Cout=%d", Cout);
+  p.n_nt = Cout / BN;
+  p.num_kb = ceil_div(Cin, BK);
+  // CTA pairs (cta_group::2, validated on B200: scripts/check_2cta.py): default on, RAVE_TC_2CTA=0 disables.
+  // Needs N % 32 == 0, a K-block of 64 (the tested configuration) and at least two M tiles.
   const bool use2 = want2 && (BN % 32 == 0) && BN >= 64 && (long)p.n_lt * p.n_bg >= 2;
 
   // A: channel-last activations viewed as (c, phase, l/stride, b)
@@ -860,30 +839,9 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map B encode failed (%d)", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (use2) {
-    // bf16 output through shared-memory staging + bulk tensor stores: RAVE_TC_TMASTORE=1
-    CUtensorMap to;
-    memset(&to, 0, sizeof(to));
-    p.tma_store = 0;
-    const char *e = getenv("RAVE_TC_TMASTORE");
-    if (out_act && e && e[0] == '1') {       // measured slower than per-thread stores so far: opt-in
-      const int RB = p.BL < 32 ? p.BL : 32;
-      char *base = (char *)out_act + (size_t)p.out_row_offset * Cout * 2;
-      cuuint64_t dims[3] = {(cuuint64_t)Cout, (cuuint64_t)Lout, (cuuint64_t)B};
-      cuuint64_t strides[2] = {(cuuint64_t)p.out_row_stride * Cout * 2, (cuuint64_t)p.out_rows * Cout * 2};
-      cuuint32_t box[3] = {32, (cuuint32_t)RB, (cuuint32_t)(32 / RB)};
-      cuuint32_t estr[3] = {1, 1, 1};
-      CUresult r = enc(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: output tensor map encode failed (%d)", (int)r);
-      p.tma_store = 1;
-      p.st_rows = RB;
-      p.st_batches = 32 / RB;
-    }
-    return BK == 64 ? dispatch_n2<64>(BN, ta, tb, to, p, s) : BK == 32 ? dispatch_n2<32>(BN, ta, tb, to, p, s)
-                                                                       : dispatch_n2<16>(BN, ta, tb, to, p, s);
-  }
+  if (use2)
+    return BK == 64 ? dispatch_n2<64>(BN, ta, tb, p, s) : BK == 32 ? dispatch_n2<32>(BN, ta, tb, p, s)
+                                                                   : dispatch_n2<16>(BN, ta, tb, p, s);
   switch (BK) {
     case 64: return dispatch_n<64>(BN, ta, tb, p, s);
     case 32: return dispatch_n<32>(BN, ta, tb, p, s);

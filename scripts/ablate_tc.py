@@ -20,17 +20,20 @@ SHAPES = [
     ("c1 im2col 16->96 k1", 64, 16, 96, 16384, 1, 1, 1, 0),
     ("c1 as 64->384 k1 (4 positions per row)", 64, 64, 384, 4096, 1, 1, 1, 0),
     ("unit 96->96 k3 B32", 32, 96, 96, 4096, 3, 1, 1, 1),
+    ("fused dgrad 192->4x96 (J=4)", 64, 192, 384, 4096, 4, 1, 1, 2),
+    ("unit 768->768 k3 L=64", 32, 768, 768, 64, 3, 1, 1, 1),
 ]
 CONFIGS = [
     ("default", {}),
-    ("staged TMA stores", {"RAVE_TC_TMASTORE": "1"}),
+    ("4 epilogue warps", {"RAVE_TC_EPIWARPS": "4"}),
+    ("8 epilogue warps", {"RAVE_TC_EPIWARPS": "8"}),
     ("no epilogue stores", {"RAVE_TC_DBG": "1"}),
     ("no loads at all", {"RAVE_TC_DBG": "6"}),
     ("no loads, no stores", {"RAVE_TC_DBG": "7"}),
     ("L2 promotion none", {"RAVE_TC_L2PROMO": "0"}),
     ("1-CTA kernel", {"RAVE_TC_2CTA": "0"}),
 ]
-KEYS = ["RAVE_TC_STAGES", "RAVE_TC_DBG", "RAVE_TC_L2PROMO", "RAVE_TC_TMASTORE"]
+KEYS = ["RAVE_TC_STAGES", "RAVE_TC_DBG", "RAVE_TC_L2PROMO", "RAVE_TC_EPIWARPS"]
 
 for name, B, Cin, Cout, Lin, K, stride, dil, pad in SHAPES:
     x = torch.randn(B, Lin, Cin, device="cuda").bfloat16()
