@@ -191,12 +191,17 @@ int rave_conv1d_c1_dgrad(const void *g_bf16, const float *w, float *dx, int R, i
                          int Cg, int Lout, int g_pitch, int K, int stride, int pad_l, void *stream);
 int rave_colsum_bf16(const void *g_bf16, float *out, int R, int L, int pitch, int Cg, int C, void *stream);
 /* Cin = 1 first layer on the tensor-core kernels: im2col of the K (<= 16) taps into 16 bf16 "channels"
- *   X[r][l][k] = bf16(x[r][l*stride + k - pad_l])   (x fp32 rows [R][x_pitch]; X [R][out_pitch][16], zero elsewhere)
- * and the scatter-free input gradient  dx[r][t] = sum_k P[r][(t+pad-k)/stride][k]  from P [R][p_pitch][16] fp32. */
-int rave_im2col_c1(const float *x, void *X_bf16, int R, int x_pitch, int Lin, int Lout, int out_pitch, int K,
-                   int stride, int pad_l, void *stream);
-int rave_gather_c1(const float *P, float *dx, int R, int x_pitch, int Lin, int Lout, int p_pitch, int K, int stride,
-                   int pad_l, void *stream);
+ *   X[r][l][k] = bf16(row_r[l*stride + k - pad_l])        (X [R][out_pitch][16], zero elsewhere)
+ * where the R rows are read straight from a signal tensor src [Bs][src_pitch] (src_len valid samples):
+ *   row r = b*period + w, position i -> (1/pool) * sum_{j<pool} src[b][(i*pool + j)*period + w]
+ * (period > 1 = MultiPeriodDiscriminator.fold, rave/discriminator.py:187-195; pool = 2^scale = the avg_pool1d
+ * chain of MultiScaleDiscriminator, rave/discriminator.py:150-171; period = pool = 1: src already holds the rows),
+ * and the adjoint: dsrc (pre-zeroed or accumulating) += scatter-free gather of P [R][p_pitch][16] fp32 back through
+ * the taps, the pooling and the fold. */
+int rave_im2col_c1(const float *src, void *X_bf16, int R, int src_pitch, int src_len, int Lin, int Lout,
+                   int out_pitch, int K, int stride, int pad_l, int period, int pool, void *stream);
+int rave_gather_c1(const float *P, float *dsrc, int R, int src_pitch, int src_len, int Lin, int Lout, int p_pitch,
+                   int K, int stride, int pad_l, int period, int pool, void *stream);
 int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, int pitch, int C, float slope, void *stream);
 int rave_fm_grad(const void *a_bf16, const float *dstats, void *gout_bf16, int Bh, int L, int pitch, int C,
                  float slope, void *stream);

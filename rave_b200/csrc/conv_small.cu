@@ -552,63 +552,88 @@ extern "C" int rave_score_grad(const float *score, const float *dstats, void *go
 // ---------------------------------------------------------------------------------------------
 namespace rave {
 
-// grid (ceil(pitch/128), R), block 256: thread = (position, tap pair)
+// Source addressing shared by the im2col and its adjoint: the R chain rows are derived from a signal tensor
+// src[Bs][src_pitch] (src_len valid samples) WITHOUT materialising them:
+//   row r = b*period + w,  position i  ->  (1/pool) * sum_{j<pool} src[b][(i*pool + j)*period + w]
+// period > 1: MultiPeriodDiscriminator.fold (zero padding to a multiple of the period, rave/discriminator.py:187-195);
+// pool > 1: the avg_pool1d(2) chain of MultiScaleDiscriminator (rave/discriminator.py:150-171, pool = 2^scale).
+__device__ __forceinline__ float c1_src_value(const float *__restrict__ xb, int i, int w, int period, int pool,
+                                              int src_len) {
+  float v = 0.f;
+  for (int j = 0; j < pool; ++j) {
+    const long e = ((long)i * pool + j) * period + w;
+    if (e < src_len) v += __ldg(xb + e);
+  }
+  return pool > 1 ? v / (float)pool : v;
+}
+
+// grid (ceil(pitch/32), R), block 256: thread = (position, tap pair)
 __global__ void __launch_bounds__(256)
-im2col_c1_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ X, int x_pitch, int Lin, int Lout,
-                 int out_pitch, int K, int stride, int pad_l) {
+im2col_c1_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ X, int src_pitch, int src_len, int Lin,
+                 int Lout, int out_pitch, int K, int stride, int pad_l, int period, int pool) {
   const int r = blockIdx.y;
   const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
   const int k2 = (threadIdx.x & 7) * 2;
   if (l >= out_pitch) return;
   float v0 = 0.f, v1 = 0.f;
   if (l < Lout) {
-    const float *xr = x + (size_t)r * x_pitch;
+    const int b = r / period, w = r - b * period;
+    const float *xb = x + (size_t)b * src_pitch;
     const int p0 = l * stride + k2 - pad_l, p1 = p0 + 1;
-    if (k2 < K && p0 >= 0 && p0 < Lin) v0 = __ldg(xr + p0);
-    if (k2 + 1 < K && p1 >= 0 && p1 < Lin) v1 = __ldg(xr + p1);
+    if (k2 < K && p0 >= 0 && p0 < Lin) v0 = c1_src_value(xb, p0, w, period, pool, src_len);
+    if (k2 + 1 < K && p1 >= 0 && p1 < Lin) v1 = c1_src_value(xb, p1, w, period, pool, src_len);
   }
   *reinterpret_cast<uint32_t *>(X + ((size_t)r * out_pitch + l) * 16 + k2) = pack_bf16(v0, v1);
 }
 
-// dx[r][t] = sum_k P[r][(t + pad - k)/stride][k]; P fp32 channel-last [R][p_pitch][16]
+// dsrc[b][(t*pool + j)*period + w] += (1/pool) * sum_k P[r][(t + pad - k)/stride][k]; P fp32 channel-last [R][p_pitch][16].
+// Every source element is touched by at most one (r, t, j): plain read-modify-write, launches are stream-ordered.
 __global__ void __launch_bounds__(256)
-gather_c1_kernel(const float *__restrict__ P, float *__restrict__ dx, int x_pitch, int Lin, int Lout, int p_pitch,
-                 int K, int stride, int pad_l) {
+gather_c1_kernel(const float *__restrict__ P, float *__restrict__ dx, int src_pitch, int src_len, int Lin, int Lout,
+                 int p_pitch, int K, int stride, int pad_l, int period, int pool) {
   const int r = blockIdx.y;
   const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= x_pitch) return;
+  if (t >= Lin) return;
   float acc = 0.f;
-  if (t < Lin) {
-    const float *Pr = P + (size_t)r * p_pitch * 16;
-    for (int k = (t + pad_l) % stride; k < K; k += stride) {
-      const int q = t + pad_l - k;
-      if (q < 0) break;
-      const int l = q / stride;
-      if (l < Lout) acc += __ldg(Pr + (size_t)l * 16 + k);
-    }
+  const float *Pr = P + (size_t)r * p_pitch * 16;
+  for (int k = (t + pad_l) % stride; k < K; k += stride) {
+    const int q = t + pad_l - k;
+    if (q < 0) break;
+    const int l = q / stride;
+    if (l < Lout) acc += __ldg(Pr + (size_t)l * 16 + k);
   }
-  dx[(size_t)r * x_pitch + t] = acc;
+  const int b = r / period, w = r - b * period;
+  float *db = dx + (size_t)b * src_pitch;
+  if (pool > 1) acc /= (float)pool;
+  for (int j = 0; j < pool; ++j) {
+    const long e = ((long)t * pool + j) * period + w;
+    if (e < src_len) db[e] += acc;
+  }
 }
 
 }  // namespace rave
 
-extern "C" int rave_im2col_c1(const float *x, void *X_bf16, int R, int x_pitch, int Lin, int Lout, int out_pitch,
-                              int K, int stride, int pad_l, void *stream) {
+extern "C" int rave_im2col_c1(const float *x, void *X_bf16, int R, int src_pitch, int src_len, int Lin, int Lout,
+                              int out_pitch, int K, int stride, int pad_l, int period, int pool, void *stream) {
   using namespace rave;
-  RAVE_CHECK_ARG(x && X_bf16 && R > 0 && R <= 65535 && K > 0 && K <= 16 && out_pitch >= Lout, "im2col_c1: bad argument");
+  RAVE_CHECK_ARG(x && X_bf16 && R > 0 && R <= 65535 && K > 0 && K <= 16 && out_pitch >= Lout && period >= 1 &&
+                     pool >= 1 && (period == 1 || pool == 1) && R % period == 0,
+                 "im2col_c1: bad argument");
   dim3 grid(ceil_div(out_pitch, 32), R);
-  im2col_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)X_bf16, x_pitch, Lin, Lout, out_pitch, K,
-                                                           stride, pad_l);
+  im2col_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)X_bf16, src_pitch, src_len, Lin, Lout,
+                                                           out_pitch, K, stride, pad_l, period, pool);
   RAVE_CHECK_LAUNCH("im2col_c1");
   return 0;
 }
-
-extern "C" int rave_gather_c1(const float *P, float *dx, int R, int x_pitch, int Lin, int Lout, int p_pitch, int K,
-                              int stride, int pad_l, void *stream) {
+extern "C" int rave_gather_c1(const float *P, float *dsrc, int R, int src_pitch, int src_len, int Lin, int Lout,
+                              int p_pitch, int K, int stride, int pad_l, int period, int pool, void *stream) {
   using namespace rave;
-  RAVE_CHECK_ARG(P && dx && R > 0 && R <= 65535 && K > 0 && K <= 16 && p_pitch >= Lout, "gather_c1: bad argument");
-  dim3 grid(ceil_div(x_pitch, 256), R);
-  gather_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, dx, x_pitch, Lin, Lout, p_pitch, K, stride, pad_l);
+  RAVE_CHECK_ARG(P && dsrc && R > 0 && R <= 65535 && K > 0 && K <= 16 && p_pitch >= Lout && period >= 1 && pool >= 1 &&
+                     (period == 1 || pool == 1) && R % period == 0,
+                 "gather_c1: bad argument");
+  dim3 grid(ceil_div(Lin, 256), R);
+  gather_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, dsrc, src_pitch, src_len, Lin, Lout, p_pitch, K, stride,
+                                                           pad_l, period, pool);
   RAVE_CHECK_LAUNCH("gather_c1");
   return 0;
 }

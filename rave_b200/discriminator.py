@@ -107,19 +107,26 @@ class ConvNet(nn.Module):
             xa = nn.functional.pad(rows, (0, first.cin_pad, 0, rpad)).to(engine.ACT_DTYPE).contiguous()
         return xa, B, W, L
 
-    def forward_fm(self, x):
-        """Fused feature-matching path (bf16 engine): x = cat([real, fake]) -> (stats [n-1, 2], counts,
-        score, score_stats [3, 2], n_score) with stats[i] = (sum|h_r - h_f|, sum|h_r|) of hidden feature i,
+    def forward_fm(self, x, period: int = 1, pool: int = 1):
+        """Fused feature-matching path (bf16 engine): x = cat([real, fake]) RAW signal [B, 1, T] -> (stats [n-1, 2],
+        counts, score, score_stats [3, 2], n_score) with stats[i] = (sum|h_r - h_f|, sum|h_r|) of hidden feature i,
         counts[i] = its number of elements per half, score = the last conv's output in the reference's shape,
-        score_stats = the six sums of the score tail (engine.TcChainFn), n_score = score elements per half."""
+        score_stats = the six sums of the score tail (engine.TcChainFn), n_score = score elements per half.
+        `period` > 1: this ConvNet sees MultiPeriodDiscriminator.fold(x, period); `pool` > 1: it sees x average-
+        pooled by `pool` (MultiScaleDiscriminator) -- in both cases the first layer reads x in place."""
         from . import engine
         specs = self._tc_specs()
-        xa, B, W, L = self._chain_input(x, specs)
-        stats, score_stats, last = engine.run_chain(xa, specs, L, fm=True)
+        first = specs[0]
+        if x.dim() != 3 or x.shape[1] != 1 or first.Cin != 1 or first.dil != 1:
+            raise RuntimeError("forward_fm expects a mono signal [B, 1, T] and a Cin = 1 first layer")
+        B, _, T = x.shape
+        W = period
+        L = (T + period - 1) // period if period > 1 else T // pool
+        stats, score_stats, last = engine.run_chain(x.reshape(B, T), specs, L, fm=True, src=(period, pool))
         lens = engine.chain_lengths(specs, L)
         counts = [(B // 2) * W * Lo * s.Cout for s, Lo in zip(specs[:-1], lens[:-1])]
         o = last[:, :lens[-1], :specs[-1].Cout]
-        if x.dim() == 3:
+        if period == 1:
             score = o.permute(0, 2, 1)
         else:
             score = o.reshape(B, W, lens[-1], specs[-1].Cout).permute(0, 3, 2, 1)
@@ -170,11 +177,8 @@ class MultiScaleDiscriminator(nn.Module):
         self.layers = nn.ModuleList([convnet(in_size=n_channels) for _ in range(n_discriminators)])
 
     def forward_fm(self, x):
-        out = []
-        for layer in self.layers:
-            out.append(layer.forward_fm(x))
-            x = nn.functional.avg_pool1d(x, 2)
-        return out
+        # scale i sees avg_pool1d(., 2) applied i times = the mean over 2^i consecutive samples (floor lengths agree)
+        return [layer.forward_fm(x, pool=2 ** i) for i, layer in enumerate(self.layers)]
 
     def forward(self, x):
         features = []
@@ -199,7 +203,7 @@ class MultiPeriodDiscriminator(nn.Module):
         return features
 
     def forward_fm(self, x):
-        return [layer.forward_fm(self.fold(x, n)) for layer, n in zip(self.layers, self.periods)]
+        return [layer.forward_fm(x, period=n) for layer, n in zip(self.layers, self.periods)]
 
     def fold(self, x, n):
         pad = (n - (x.shape[-1] % n)) % n
@@ -223,13 +227,16 @@ class CombineDiscriminators(nn.Module):
     def supports_fused_fm(self, x) -> bool:
         """True when every sub-discriminator can run the fused feature-matching path on `x`."""
         from . import engine
-        if engine.precision() != "bf16" or not x.is_cuda:
+        if engine.precision() != "bf16" or not x.is_cuda or x.dim() != 3 or x.shape[1] != 1:
             return False
         for disc in self.discriminators:
             if not hasattr(disc, "forward_fm"):
                 return False
             for layer in disc.layers:
                 if not isinstance(layer, ConvNet) or layer._tc_specs() is None:
+                    return False
+                first = layer._tc_specs()[0]
+                if first.Cin != 1 or first.dil != 1:
                     return False
         return True
 

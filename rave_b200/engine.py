@@ -317,8 +317,9 @@ class TcChainFn(torch.autograd.Function):
     """forward(x, specs, L0, fm, *flat_params).
 
     x   : [B, pitch, Cin(+pad)] operand stream (ACT_DTYPE), or -- when the first layer has Cin == 1 --
-          the raw fp32 rows [B, pitch] (small-channel kernel, no padding to 16 channels, no bf16 rounding
-          of the audio).
+          a raw fp32 signal tensor [Bs, T] from which the chain rows are read in place: `src = (period, pool)`
+          (L0 = positions per row; B = Bs*period rows; MPD fold / MSD pooling, ops.im2col_c1); no padding to 16
+          channels, no bf16 rounding of the audio, no folded / pooled copy.
     fm  : False -> returns one fp32 channel-last tensor per `is_output` layer;
           True  -> discriminator feature-matching mode: the batch is [real; fake]; returns
                    (stats [n-1, 2] = per hidden layer (sum|h_r-h_f|, sum|h_r|),
@@ -330,12 +331,15 @@ class TcChainFn(torch.autograd.Function):
                    tensors (RAVE._fused_feature_matching), whose gradients drive fm_grad / score_grad here."""
 
     @staticmethod
-    def forward(ctx, x_in, specs, L0, fm, *flat):
+    def forward(ctx, x_in, specs, L0, fm, src, *flat):
         n = len(specs)
         ctx.set_materialize_grads(False)
         need_dgrad = x_in.requires_grad or any(t is not None and t.requires_grad for t in flat)
-        B = x_in.shape[0]
         c1 = x_in.dim() == 2
+        period, pool = src if (c1 and src is not None) else (1, 1)
+        B = x_in.shape[0] * period
+        ctx.c1_src = (period, pool, tuple(x_in.shape))
+        ctx.B = B
         if c1 and not (specs[0].kind == "conv" and specs[0].Cin == 1 and specs[0].dil == 1):
             raise _lib.RaveB200Error("raw fp32 rows are only accepted by a Cin = 1 first conv")
         dev = x_in.device
@@ -390,7 +394,7 @@ class TcChainFn(torch.autograd.Function):
                 w_ck = nn.functional.pad(w_eff.reshape(s.Cout, s.K), (0, 16 - s.K, 0, s.cout_pad))   # [Cout_p, 16]
                 G = C1_GROUP if (pitch % C1_GROUP == 0) else 1
                 Xp = (Lout + G - 1) // G * G
-                X = ops.im2col_c1(a, Lin, Lout, Xp, s.K, s.stride, s.pad[0])
+                X = ops.im2col_c1(a, Lin, Lout, Xp, s.K, s.stride, s.pad[0], period, pool)
                 ctx.c1_X = X
                 ctx.c1_group = G
                 if G > 1:
@@ -464,7 +468,7 @@ class TcChainFn(torch.autograd.Function):
         specs = ctx.specs
         n = len(specs)
         flat = ctx.params
-        B = ctx.acts[0].shape[0]
+        B = ctx.B
         ext: Dict[int, torch.Tensor] = {}      # external gradient of layer i's output (ACT_DTYPE, h-space)
         dstats = None
         if ctx.fm:
@@ -552,7 +556,8 @@ class TcChainFn(torch.autograd.Function):
                     wt_d = ctx.c1_wt_dgrad if G == 1 else ctx.c1_wt_dgrad[:, :16, :cout_p].contiguous()
                     P, _ = ops.conv1d_tc(g, wt_d, None, None, 1, 1, (0, 0), ops.ACT_NONE, 0.0, want_f32=True,
                                          want_act=False, Lout=Lout, Lin=Lout)
-                gx = ops.gather_c1(P, in_pitch, Lin, Lout, s.K, s.stride, s.pad[0])
+                period, pool, src_shape = ctx.c1_src
+                gx = ops.gather_c1(P, src_shape, Lin, Lout, s.K, s.stride, s.pad[0], period, pool)
                 break
             gp = torch.empty(B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)
             if in_pitch > Lin:
@@ -590,10 +595,11 @@ class TcChainFn(torch.autograd.Function):
             res = ops.weight_norm_bwd_multi([(dwt, v, gpar, norm) for (_, dwt, v, gpar, norm) in wn_jobs])
             for (i, _, _, _, _), (dv, dg) in zip(wn_jobs, res):
                 grads[3 * i], grads[3 * i + 1] = dv, dg
-        return (gx, None, None, None) + tuple(grads)
+        return (gx, None, None, None, None) + tuple(grads)
 
 
-def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None, fm: bool = False):
+def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None, fm: bool = False,
+              src: Optional[Tuple[int, int]] = None):
     """x_cl_bf16: [B, pitch, Cin(+pad)] (rows beyond the true length L0 must be zero), or raw fp32 rows
     [B, pitch] for a Cin = 1 first layer.  Returns one fp32 channel-last tensor [B, pitch_i, Cout_i(+pad)]
     per output layer (slice [:, :L_i, :Cout_i]); with fm=True: (stats [n-1, 2], score_stats [3, 2], last layer
@@ -604,7 +610,7 @@ def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int]
         flat += [v, g, b]
     if L0 is None:
         L0 = x_cl_bf16.shape[1]
-    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, *flat)
+    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, src, *flat)
 
 
 def chain_lengths(specs: List[LayerSpec], L0: int) -> List[int]:

@@ -551,22 +551,28 @@ def colsum_bf16(g_cl, L, C):
     return out
 
 
-def im2col_c1(x_rows, Lin, Lout, out_pitch, K, stride, pad_l):
-    """X [R, out_pitch, 16] bf16 with X[r,l,k] = x[r, l*stride + k - pad_l] (zero outside / beyond K, Lout)."""
-    x_rows = _f32c(x_rows)
-    R, x_pitch = x_rows.shape
-    X = torch.empty(R, out_pitch, 16, dtype=torch.bfloat16, device=x_rows.device)
-    call("rave_im2col_c1", ptr(x_rows), ptr(X), R, x_pitch, Lin, Lout, out_pitch, K, stride, pad_l, stream_ptr())
+def im2col_c1(src, Lin, Lout, out_pitch, K, stride, pad_l, period=1, pool=1):
+    """X [R, out_pitch, 16] bf16 with X[r,l,k] = row_r[l*stride + k - pad_l] (zero outside / beyond K, Lout), the
+    R = Bs*period rows read straight from src [Bs, T]: row b*period + w, position i ->
+    mean_j src[b, (i*pool + j)*period + w] (MPD fold / MSD average pooling, see include/rave_b200.h)."""
+    src = _f32c(src)
+    Bs, T = src.shape
+    R = Bs * period
+    X = torch.empty(R, out_pitch, 16, dtype=torch.bfloat16, device=src.device)
+    call("rave_im2col_c1", ptr(src), ptr(X), R, T, T, Lin, Lout, out_pitch, K, stride, pad_l, period, pool,
+         stream_ptr())
     return X
 
 
-def gather_c1(P_cl, x_pitch, Lin, Lout, K, stride, pad_l):
-    """dx [R, x_pitch] fp32 = sum_k P[r, (t+pad-k)/stride, k] from P [R, p_pitch, 16] fp32."""
+def gather_c1(P_cl, src_shape, Lin, Lout, K, stride, pad_l, period=1, pool=1):
+    """dsrc [Bs, T] fp32: the adjoint of im2col_c1 applied to P [R, p_pitch, 16] fp32 (taps, pooling, fold)."""
     P_cl = _f32c(P_cl)
     R, p_pitch, _ = P_cl.shape
-    dx = torch.empty(R, x_pitch, dtype=torch.float32, device=P_cl.device)
-    call("rave_gather_c1", ptr(P_cl), ptr(dx), R, x_pitch, Lin, Lout, p_pitch, K, stride, pad_l, stream_ptr())
-    return dx
+    Bs, T = src_shape
+    dsrc = torch.zeros(Bs, T, dtype=torch.float32, device=P_cl.device)
+    call("rave_gather_c1", ptr(P_cl), ptr(dsrc), R, T, T, Lin, Lout, p_pitch, K, stride, pad_l, period, pool,
+         stream_ptr())
+    return dsrc
 
 
 # ----------------------------------------------------------------------------------------------

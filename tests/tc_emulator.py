@@ -190,7 +190,20 @@ def colsum_bf16(g_cl, L, C):
     return g_cl[:, :L, :C].float().sum((0, 1))
 
 
-def im2col_c1(x_rows, Lin, Lout, out_pitch, K, stride, pad_l):
+def _c1_rows(src, Lin, period, pool):
+    """rows [Bs*period, Lin] derived from src [Bs, T] exactly like the reference: fold (zero pad to a multiple of the
+    period) or repeated average pooling."""
+    Bs, T = src.shape
+    if period > 1:
+        xp = F.pad(src, (0, Lin * period - T))
+        return xp.reshape(Bs, Lin, period).permute(0, 2, 1).reshape(Bs * period, Lin)
+    if pool > 1:
+        return src[:, :Lin * pool].reshape(Bs, Lin, pool).mean(-1)
+    return src[:, :Lin]
+
+
+def im2col_c1(src, Lin, Lout, out_pitch, K, stride, pad_l, period=1, pool=1):
+    x_rows = _c1_rows(src.float(), Lin, period, pool)
     R = x_rows.shape[0]
     X = torch.zeros(R, out_pitch, 16)
     l = torch.arange(Lout)
@@ -201,15 +214,21 @@ def im2col_c1(x_rows, Lin, Lout, out_pitch, K, stride, pad_l):
     return _bf16(X)
 
 
-def gather_c1(P_cl, x_pitch, Lin, Lout, K, stride, pad_l):
+def gather_c1(P_cl, src_shape, Lin, Lout, K, stride, pad_l, period=1, pool=1):
     R = P_cl.shape[0]
-    dx = torch.zeros(R, x_pitch)
+    Bs, T = src_shape
+    dx = torch.zeros(R, Lin)
     t = torch.arange(Lin)
     for k in range(K):
         q = t + pad_l - k
         ok = (q >= 0) & (q % stride == 0) & (q // stride < Lout)
         dx[:, t[ok]] += P_cl[:, (q[ok] // stride), k]
-    return dx
+    # adjoint of _c1_rows
+    with torch.enable_grad():
+        src = torch.zeros(Bs, T, requires_grad=True)
+        rows = _c1_rows(src, Lin, period, pool)
+        (g,) = torch.autograd.grad(rows, src, dx)
+    return g.detach()
 
 
 def _unleaky(a, slope):

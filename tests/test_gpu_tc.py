@@ -125,11 +125,26 @@ def test_small_channel_kernels_vs_emulator():
         dx_e = E.conv1d_c1_dgrad(g, we, L + 3, L, Lout, stride, pad)
         dx = ops.conv1d_c1_dgrad(g.cuda(), we.cuda(), L + 3, L, Lout, stride, pad)
         assert dx.shape == dx_e.shape and rel_l2(dx, dx_e) < 1e-5
-        X_e = E.im2col_c1(x, L, Lout, pitch, K, stride, pad)
-        X = ops.im2col_c1(x.cuda(), L, Lout, pitch, K, stride, pad)
+        xz = x.clone()
+        xz[:, L:] = 0                         # rows handed over as a padded tensor: slack beyond L is zero
+        X_e = E.im2col_c1(xz, L, Lout, pitch, K, stride, pad)
+        X = ops.im2col_c1(xz.cuda(), L, Lout, pitch, K, stride, pad)
         assert torch.equal(X.float().cpu(), X_e.float())
         Pm = torch.randn(R, pitch, 16)
-        assert rel_l2(ops.gather_c1(Pm.cuda(), L + 3, L, Lout, K, stride, pad), E.gather_c1(Pm, L + 3, L, Lout, K, stride, pad)) < 1e-6
+        assert rel_l2(ops.gather_c1(Pm.cuda(), (R, L + 3), L, Lout, K, stride, pad),
+                      E.gather_c1(Pm, (R, L + 3), L, Lout, K, stride, pad)) < 1e-6
+        # the same rows read in place from a signal tensor: fold by a period / average pooling
+        for (period, pool) in [(3, 1), (7, 1), (1, 2), (1, 4)]:
+            Bs, T = 4, L * period * pool - (2 if period > 1 else 0) + (1 if pool > 1 else 0)
+            src = torch.randn(Bs, T)
+            Ls = (T + period - 1) // period if period > 1 else T // pool
+            Lo = (Ls + 2 * pad - K) // stride + 1
+            Xs_e = E.im2col_c1(src, Ls, Lo, Lo + 1, K, stride, pad, period, pool)
+            Xs = ops.im2col_c1(src.cuda(), Ls, Lo, Lo + 1, K, stride, pad, period, pool)
+            assert rel_l2(Xs.float(), Xs_e.float()) < 4e-3          # bf16 rounding of pooled means may differ by 1 ulp
+            Ps = torch.randn(Bs * period, Lo + 1, 16)
+            assert rel_l2(ops.gather_c1(Ps.cuda(), (Bs, T), Ls, Lo, K, stride, pad, period, pool),
+                          E.gather_c1(Ps, (Bs, T), Ls, Lo, K, stride, pad, period, pool)) < 1e-6
         cs = ops.colsum_bf16(g.cuda(), Lout, Cout)
         assert rel_l2(cs, E.colsum_bf16(g, Lout, Cout)) < 1e-5
     for (B2, L, pitch, C) in [(4, 100, 104, 96), (8, 17, 20, 192), (2, 5, 5, 16)]:
