@@ -68,41 +68,39 @@ struct SmemLayout {
 
 // Epilogue of one 128 x BLOCK_N accumulator tile: this thread owns TMEM lane `taddr.lane` = one output row.
 // One chunk = CW (16 or 32) consecutive channels.  All global loads of the chunk (residual, gradient skip,
-// LeakyReLU' mask) are issued BEFORE the TMEM load so that their latency overlaps it: the HBM-bound layers
-// (C = 96 / 192 blocks) are limited by the bytes in flight per SM, not by arithmetic.
+// LeakyReLU' mask, feature-matching partner row) are issued BEFORE the TMEM load so that their latency overlaps it.
+// Row segments move as 256-bit vectors (LDG/STG.E.ENL2.256, sm_100): one full 32-byte sector per lane and
+// instruction -- with 128-bit accesses every store was a HALF-sector L2 transaction and the HBM-bound layers ran
+// at ~2.4 TB/s of store traffic (profiles/r1_ablation_conv_tc2.txt: "no epilogue stores").
+template <int NWORDS>
+__device__ __forceinline__ void ld_words(const void *ptr, uint32_t *w) {
+  static_assert(NWORDS % 8 == 0, "256-bit granules");
+#pragma unroll
+  for (int i = 0; i < NWORDS / 8; ++i) ldg256(reinterpret_cast<const uint8_t *>(ptr) + 32 * i, w + 8 * i);
+}
+template <int NWORDS>
+__device__ __forceinline__ void st_words(void *ptr, const uint32_t *w) {
+  static_assert(NWORDS % 8 == 0, "256-bit granules");
+#pragma unroll
+  for (int i = 0; i < NWORDS / 8; ++i) stg256(reinterpret_cast<uint8_t *>(ptr) + 32 * i, w + 8 * i);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
 template <int CW>
 __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow,
                                              int fm_side = 0) {
+  constexpr int NW = CW / 2;      // 32-bit words of a bf16 row segment
   float v[CW];
-  float4 rf[CW / 4];
-  uint4 rb[CW / 8], dm[CW / 8], ra[CW / 8], pm[CW / 8];
+  uint32_t rf[CW], rb[NW], dm[NW], ra[NW], pm[NW];
   const size_t off = orow * p.Cout + co;
   if (valid) {
-    if (fm_side) {     // partner row of the other batch half (same position, same channels)
-      const uint4 *q4 = reinterpret_cast<const uint4 *>(p.dact_src + (fm_side > 0 ? off + p.fm_half : off - p.fm_half));
-#pragma unroll
-      for (int i = 0; i < CW / 8; ++i) pm[i] = __ldg(q4 + i);
-    }
-    if (p.res_act) {
-      const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_act + off);
-#pragma unroll
-      for (int i = 0; i < CW / 8; ++i) ra[i] = __ldg(r4 + i);
-    }
-    if (p.res) {
-      const float4 *r4 = reinterpret_cast<const float4 *>(p.res + off);
-#pragma unroll
-      for (int i = 0; i < CW / 4; ++i) rf[i] = __ldg(r4 + i);
-    }
-    if (p.res_bf16) {
-      const uint4 *r4 = reinterpret_cast<const uint4 *>(p.res_bf16 + off);
-#pragma unroll
-      for (int i = 0; i < CW / 8; ++i) rb[i] = __ldg(r4 + i);
-    }
-    if (p.dact_src) {
-      const uint4 *d4 = reinterpret_cast<const uint4 *>(p.dact_src + off);
-#pragma unroll
-      for (int i = 0; i < CW / 8; ++i) dm[i] = __ldg(d4 + i);
-    }
+    if (fm_side)       // partner row of the other batch half (same position, same channels)
+      ld_words<NW>(p.dact_src + (fm_side > 0 ? off + p.fm_half : off - p.fm_half), pm);
+    if (p.res_act) ld_words<NW>(p.res_act + off, ra);
+    if (p.res) ld_words<CW>(p.res + off, rf);
+    if (p.res_bf16) ld_words<NW>(p.res_bf16 + off, rb);
+    if (p.dact_src) ld_words<NW>(p.dact_src + off, dm);
   }
   if (CW == 32) tmem_ld_32x32(taddr, v);
   else tmem_ld_32x16(taddr, v);       // warp-collective: every lane participates, valid or not
@@ -113,90 +111,67 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
   }
   if (p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand (sign bits of bf16)
 #pragma unroll
-    for (int i = 0; i < CW / 8; ++i) {
-      const uint32_t w[4] = {dm[i].x, dm[i].y, dm[i].z, dm[i].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (w[j] & 0x00008000u) v[8 * i + 2 * j] *= p.slope;
-        if (w[j] & 0x80000000u) v[8 * i + 2 * j + 1] *= p.slope;
-      }
+    for (int w = 0; w < NW; ++w) {
+      if (dm[w] & 0x00008000u) v[2 * w] *= p.slope;
+      if (dm[w] & 0x80000000u) v[2 * w + 1] *= p.slope;
     }
   }
   if (fm_side) {       // gradient of d0 * sum|h_r - h_f| + d1 * sum|h_r| with respect to h (this row's half)
     const float d0 = __ldg(p.fm_d), d1 = __ldg(p.fm_d + 1);
     const float inv = 1.f / p.slope;
 #pragma unroll
-    for (int i = 0; i < CW / 8; ++i) {
-      const uint32_t ws[4] = {dm[i].x, dm[i].y, dm[i].z, dm[i].w};
-      const uint32_t wp[4] = {pm[i].x, pm[i].y, pm[i].z, pm[i].w};
+    for (int w = 0; w < NW; ++w) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float as = h ? __uint_as_float(ws[j] & 0xFFFF0000u) : __uint_as_float(ws[j] << 16);
-          const float ap = h ? __uint_as_float(wp[j] & 0xFFFF0000u) : __uint_as_float(wp[j] << 16);
-          const float hs = as > 0.f ? as : as * inv, hp = ap > 0.f ? ap : ap * inv;
-          const float hr = fm_side > 0 ? hs : hp, hf = fm_side > 0 ? hp : hs;
-          const float sd = (hr > hf) ? 1.f : ((hr < hf) ? -1.f : 0.f);
-          float gfm = fm_side > 0 ? d0 * sd : -d0 * sd;
-          if (fm_side > 0) gfm += d1 * ((hr > 0.f) ? 1.f : ((hr < 0.f) ? -1.f : 0.f));
-          v[8 * i + 2 * j + h] += gfm;
-        }
+      for (int h = 0; h < 2; ++h) {
+        const float as = h ? bf_hi(dm[w]) : bf_lo(dm[w]);
+        const float ap = h ? bf_hi(pm[w]) : bf_lo(pm[w]);
+        const float hs = as > 0.f ? as : as * inv, hp = ap > 0.f ? ap : ap * inv;
+        const float hr = fm_side > 0 ? hs : hp, hf = fm_side > 0 ? hp : hs;
+        const float sd = (hr > hf) ? 1.f : ((hr < hf) ? -1.f : 0.f);
+        float gfm = fm_side > 0 ? d0 * sd : -d0 * sd;
+        if (fm_side > 0) gfm += d1 * ((hr > 0.f) ? 1.f : ((hr < 0.f) ? -1.f : 0.f));
+        v[2 * w + h] += gfm;
       }
     }
   }
   if (p.res_bf16) {
 #pragma unroll
-    for (int i = 0; i < CW / 8; ++i) {
-      const uint32_t w[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
-        v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-      }
+    for (int w = 0; w < NW; ++w) {
+      v[2 * w] += bf_lo(rb[w]);
+      v[2 * w + 1] += bf_hi(rb[w]);
     }
   }
   if (p.res_act) {     // residual skip from the unit's own bf16 operand: undo the LeakyReLU
 #pragma unroll
-    for (int i = 0; i < CW / 8; ++i) {
-      const uint32_t w[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a0 = __uint_as_float(w[j] << 16), a1 = __uint_as_float(w[j] & 0xFFFF0000u);
-        v[8 * i + 2 * j] += a0 > 0.f ? a0 : a0 * p.res_inv_slope;
-        v[8 * i + 2 * j + 1] += a1 > 0.f ? a1 : a1 * p.res_inv_slope;
-      }
+    for (int w = 0; w < NW; ++w) {
+      const float a0 = bf_lo(ra[w]), a1 = bf_hi(ra[w]);
+      v[2 * w] += a0 > 0.f ? a0 : a0 * p.res_inv_slope;
+      v[2 * w + 1] += a1 > 0.f ? a1 : a1 * p.res_inv_slope;
     }
   }
   if (p.res) {
 #pragma unroll
-    for (int i = 0; i < CW / 4; ++i) {
-      v[4 * i + 0] += rf[i].x; v[4 * i + 1] += rf[i].y; v[4 * i + 2] += rf[i].z; v[4 * i + 3] += rf[i].w;
-    }
+    for (int i = 0; i < CW; ++i) v[i] += __uint_as_float(rf[i]);
   }
   if (p.out_f32) {
-    float4 *o4 = reinterpret_cast<float4 *>(p.out_f32 + off);
+    uint32_t o[CW];
 #pragma unroll
-    for (int i = 0; i < CW / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int i = 0; i < CW; ++i) o[i] = __float_as_uint(v[i]);
+    st_words<CW>(p.out_f32 + off, o);
   }
   if (p.out_act) {
-    uint4 *o = reinterpret_cast<uint4 *>(p.out_act + off);
+    uint32_t pk[NW];
 #pragma unroll
-    for (int i = 0; i < CW / 8; ++i) {
-      uint4 *dst = o + i;
-      uint32_t pk[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a0 = v[8 * i + 2 * j], a1 = v[8 * i + 2 * j + 1];
-        if (p.act == RAVE_ACT_LEAKY) {
-          a0 = a0 > 0.f ? a0 : a0 * p.slope;
-          a1 = a1 > 0.f ? a1 : a1 * p.slope;
-        }
-        __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-        pk[j] = *reinterpret_cast<uint32_t *>(&h);
+    for (int w = 0; w < NW; ++w) {
+      float a0 = v[2 * w], a1 = v[2 * w + 1];
+      if (p.act == RAVE_ACT_LEAKY) {
+        a0 = a0 > 0.f ? a0 : a0 * p.slope;
+        a1 = a1 > 0.f ? a1 : a1 * p.slope;
       }
-      *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+      pk[w] = *reinterpret_cast<uint32_t *>(&h);
     }
+    st_words<NW>(p.out_act + off, pk);
   }
 }
 
@@ -762,6 +737,9 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
                  Lin, stride);
   RAVE_CHECK_ARG(act == RAVE_ACT_NONE || act == RAVE_ACT_LEAKY, "conv1d_tc: epilogue activation %d unsupported", act);
   RAVE_CHECK_ARG(((uintptr_t)xa & 15) == 0 && ((uintptr_t)wt & 15) == 0, "conv1d_tc: operands must be 16B aligned");
+  RAVE_CHECK_ARG((((uintptr_t)out_f32 | (uintptr_t)out_act | (uintptr_t)res | (uintptr_t)res_bf16 | (uintptr_t)dact_src |
+                   (uintptr_t)res_act) & 31) == 0,
+                 "conv1d_tc: epilogue tensors must be 32-byte aligned (256-bit row segments)");
   EncodeTiledFn enc = get_encode_fn();
   RAVE_CHECK_ARG(enc, "conv1d_tc: cuTensorMapEncodeTiled not available");
 

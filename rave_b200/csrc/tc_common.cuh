@@ -55,6 +55,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane; 32-byte aligned addresses
+__device__ __forceinline__ void ldg256(const void *p, uint32_t *r) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void *p, const uint32_t *r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // One lane of a fully converged warp.  The producer / MMA-issue loops run WARP-UNIFORM (all 32 lanes execute the
 // loop, only the UTMALDG / UTCHMMA / UTCBAR instructions are predicated on the elected lane): stage indices, shared
 // memory addresses and descriptors then live in uniform registers.  Inside an `if (lane == 0)` region the compiler
