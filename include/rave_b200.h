@@ -270,6 +270,15 @@ int rave_act_to_bf16(const float *x, void *y_bf16, int B, int C, int L, int act,
 int rave_weight_to_tapmajor_bf16(const float *w, void *wt_bf16, int Cout, int Cin, int K, int transpose,
                                  int flip, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-tensor Adam, torch.optim.Adam arithmetic without weight decay / amsgrad (rave/model.py:226-236):
+ *   step += 1;  m = lerp(m, g, 1-b1);  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ * n fp32 tensors given by host arrays of device pointers; lr and step are single device floats (graph-replayable).
+ * ------------------------------------------------------------------------------------------- */
+int rave_adam_multi(int n, float *const *params, const float *const *grads, float *const *exp_avg,
+                    float *const *exp_avg_sq, const long *numel, const float *lr, float *step, float beta1, float beta2,
+                    float eps, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

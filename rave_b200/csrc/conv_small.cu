@@ -567,23 +567,31 @@ __device__ __forceinline__ float c1_src_value(const float *__restrict__ xb, int 
   return pool > 1 ? v / (float)pool : v;
 }
 
-// grid (ceil(pitch/32), R), block 256: thread = (position, tap pair)
+// grid (ceil(pitch/256), R), block 256: one thread = one position = one 32-byte row of X (a single 256-bit store);
+// the K source positions of neighbouring threads overlap (K > stride), so the strided reads hit in L1
 __global__ void __launch_bounds__(256)
 im2col_c1_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ X, int src_pitch, int src_len, int Lin,
                  int Lout, int out_pitch, int K, int stride, int pad_l, int period, int pool) {
   const int r = blockIdx.y;
-  const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
-  const int k2 = (threadIdx.x & 7) * 2;
+  const int l = blockIdx.x * 256 + threadIdx.x;
   if (l >= out_pitch) return;
-  float v0 = 0.f, v1 = 0.f;
+  uint32_t wds[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   if (l < Lout) {
     const int b = r / period, w = r - b * period;
     const float *xb = x + (size_t)b * src_pitch;
-    const int p0 = l * stride + k2 - pad_l, p1 = p0 + 1;
-    if (k2 < K && p0 >= 0 && p0 < Lin) v0 = c1_src_value(xb, p0, w, period, pool, src_len);
-    if (k2 + 1 < K && p1 >= 0 && p1 < Lin) v1 = c1_src_value(xb, p1, w, period, pool, src_len);
+    const int p0 = l * stride - pad_l;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      float v0 = 0.f, v1 = 0.f;
+      const int pa = p0 + 2 * k2, pb = pa + 1;
+      if (2 * k2 < K && pa >= 0 && pa < Lin) v0 = c1_src_value(xb, pa, w, period, pool, src_len);
+      if (2 * k2 + 1 < K && pb >= 0 && pb < Lin) v1 = c1_src_value(xb, pb, w, period, pool, src_len);
+      wds[k2] = pack_bf16(v0, v1);
+    }
   }
-  *reinterpret_cast<uint32_t *>(X + ((size_t)r * out_pitch + l) * 16 + k2) = pack_bf16(v0, v1);
+  uint4 *dst = reinterpret_cast<uint4 *>(X + ((size_t)r * out_pitch + l) * 16);
+  dst[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+  dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
 }
 
 // dsrc[b][(t*pool + j)*period + w] += (1/pool) * sum_k P[r][(t + pad - k)/stride][k]; P fp32 channel-last [R][p_pitch][16].
@@ -619,7 +627,7 @@ extern "C" int rave_im2col_c1(const float *x, void *X_bf16, int R, int src_pitch
   RAVE_CHECK_ARG(x && X_bf16 && R > 0 && R <= 65535 && K > 0 && K <= 16 && out_pitch >= Lout && period >= 1 &&
                      pool >= 1 && (period == 1 || pool == 1) && R % period == 0,
                  "im2col_c1: bad argument");
-  dim3 grid(ceil_div(out_pitch, 32), R);
+  dim3 grid(ceil_div(out_pitch, 256), R);
   im2col_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)X_bf16, src_pitch, src_len, Lin, Lout,
                                                            out_pitch, K, stride, pad_l, period, pool);
   RAVE_CHECK_LAUNCH("im2col_c1");

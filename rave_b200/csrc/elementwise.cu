@@ -679,3 +679,80 @@ extern "C" int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers,
   RAVE_CHECK_LAUNCH("mt_wn_bwd");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Multi-tensor Adam (torch.optim.Adam semantics without weight decay / amsgrad, rave/model.py:226-236): ONE launch per
+// <= ADAM_MAX parameter tensors.  lr and the step counter live in device memory (graph-replayable; the LinearLR
+// schedule writes lr in place).  PyTorch's capturable foreach path spends ~25 multi-tensor launches plus one scalar
+// division per parameter tensor (120-210 launches per step here).
+//   m = lerp(m, g, 1-b1);  v = b2 v + (1-b2) g^2;  p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+constexpr int ADAM_MAX = 96;
+constexpr int ADAM_CHUNK = 256 * 4 * 8;      // elements per block
+
+struct AdamTable {
+  int n, total_blocks;
+  float *p[ADAM_MAX];
+  const float *g[ADAM_MAX];
+  float *m[ADAM_MAX], *v[ADAM_MAX];
+  int numel[ADAM_MAX], block_begin[ADAM_MAX];
+};
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamTable t, const float *__restrict__ lr, const float *__restrict__ step,
+                  float b1, float b2, float eps) {
+  int i = 0;
+  while (i + 1 < t.n && t.block_begin[i + 1] <= (int)blockIdx.x) ++i;
+  const int base = ((int)blockIdx.x - t.block_begin[i]) * ADAM_CHUNK;
+  const int n = t.numel[i];
+  const float st = step[0];
+  const float bc1 = 1.f - powf(b1, st), bc2s = sqrtf(1.f - powf(b2, st));
+  const float step_size = lr[0] / bc1;
+  float *__restrict__ p = t.p[i];
+  const float *__restrict__ g = t.g[i];
+  float *__restrict__ m = t.m[i];
+  float *__restrict__ v = t.v[i];
+  for (int j = base + threadIdx.x; j < min(n, base + ADAM_CHUNK); j += 256) {
+    const float gj = g[j];
+    const float mj = m[j] + (1.f - b1) * (gj - m[j]);
+    const float vj = b2 * v[j] + (1.f - b2) * gj * gj;
+    m[j] = mj;
+    v[j] = vj;
+    p[j] -= step_size * mj / (sqrtf(vj) / bc2s + eps);
+  }
+}
+
+__global__ void adam_step_inc_kernel(float *step) { step[0] += 1.f; }
+
+}  // namespace rave
+
+extern "C" int rave_adam_multi(int n, float *const *params, const float *const *grads, float *const *exp_avg,
+                               float *const *exp_avg_sq, const long *numel, const float *lr, float *step, float beta1,
+                               float beta2, float eps, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(n > 0 && params && grads && exp_avg && exp_avg_sq && numel && lr && step, "adam_multi: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_step_inc_kernel<<<1, 1, 0, s>>>(step);         // t <- t + 1 first, as torch.optim.Adam does
+  RAVE_CHECK_LAUNCH("adam_step");
+  for (int i0 = 0; i0 < n; i0 += ADAM_MAX) {
+    AdamTable t;
+    memset(&t, 0, sizeof(t));
+    t.n = (n - i0 < ADAM_MAX) ? n - i0 : ADAM_MAX;
+    int blocks = 0;
+    for (int i = 0; i < t.n; ++i) {
+      RAVE_CHECK_ARG(params[i0 + i] && grads[i0 + i] && exp_avg[i0 + i] && exp_avg_sq[i0 + i] && numel[i0 + i] > 0 &&
+                         numel[i0 + i] < (1L << 31),
+                     "adam_multi: bad tensor %d", i0 + i);
+      t.p[i] = params[i0 + i]; t.g[i] = grads[i0 + i]; t.m[i] = exp_avg[i0 + i]; t.v[i] = exp_avg_sq[i0 + i];
+      t.numel[i] = (int)numel[i0 + i];
+      t.block_begin[i] = blocks;
+      blocks += (int)((numel[i0 + i] + ADAM_CHUNK - 1) / ADAM_CHUNK);
+    }
+    t.total_blocks = blocks;
+    adam_multi_kernel<<<blocks, 256, 0, s>>>(t, lr, step, beta1, beta2, eps);
+    RAVE_CHECK_LAUNCH("adam_multi");
+  }
+  return 0;
+}

@@ -171,7 +171,12 @@ class RAVE(nn.Module):
         whole step can be replayed from a CUDA graph (rave_b200/graphs.py); same Adam arithmetic."""
         gen_p = list(self.encoder.parameters()) + list(self.decoder.parameters())
         dis_p = list(self.discriminator.parameters())
-        if capturable:
+        if gen_p[0].is_cuda:
+            # multi-tensor Adam kernel, lr / step counter on the device: graph-replayable either way
+            from .optim import FusedAdam
+            gen_opt = FusedAdam(gen_p, 1e-3, (.5, .9))
+            dis_opt = FusedAdam(dis_p, 1e-4, (.5, .9))
+        elif capturable:
             dev = gen_p[0].device
             gen_opt = torch.optim.Adam(gen_p, torch.tensor(1e-3, device=dev), (.5, .9), capturable=True)
             dis_opt = torch.optim.Adam(dis_p, torch.tensor(1e-4, device=dev), (.5, .9), capturable=True)

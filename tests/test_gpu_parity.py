@@ -401,3 +401,28 @@ def test_stft_framing_kernels_vs_torch_stft():
             (g_ref,) = torch.autograd.grad((torch.view_as_real(ref) * wgt).sum(), xr)
             (g_got,) = torch.autograd.grad((torch.view_as_real(y) * wgt).sum(), x, retain_graph=True)
             assert rel_l2(g_got, g_ref) < 1e-5
+
+
+def test_fused_adam_matches_torch_adam():
+    """rave_adam_multi (one launch per <= 96 tensors, device-side lr / step) against torch.optim.Adam."""
+    from rave_b200.optim import FusedAdam
+    torch.manual_seed(5)
+    shapes = [(7,), (96, 1, 15), (192, 96, 5), (300, 300), (1,)] + [(33, 3)] * 120      # > 96 tensors, > one chunk
+    ref_p = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    our_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    ref = torch.optim.Adam(ref_p, 1e-3, (.5, .9))
+    ours = FusedAdam(our_p, 1e-3, (.5, .9))
+    for it in range(4):
+        for a, b in zip(ref_p, our_p):
+            g = torch.randn_like(a)
+            a.grad = g.clone()
+            b.grad = g.clone()
+        if it == 2:                                   # the schedule writes the lr in place
+            ref.param_groups[0]["lr"] = 5e-4
+            ours.param_groups[0]["lr"].fill_(5e-4)
+        ref.step()
+        ours.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ref_p, our_p):
+        assert rel_l2(b, a) < 2e-6
+    assert float(ours.param_groups[0]["step"]) == 4.0
