@@ -50,7 +50,7 @@ struct TcParams {
   long fm_half;            //   operand a = LeakyReLU(h) of [real; fake] rows, fm_half elements apart; adds
   int fm_bh;               //   d0 sgn(h_r-h_f) + d1 sgn(h_r) to real rows (b < fm_bh), -d0 sgn(h_r-h_f) to fake rows
   int stages;              // pipeline depth actually used (<= the layout's STAGES); RAVE_TC_STAGES overrides
-  int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue stores, 2 = skip the
+  int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue stores, 8 = no L2 prefetch, 2 = skip the
                            // activation TMA loads, 4 = skip the weight TMA loads (results are garbage)
 };
 
@@ -530,6 +530,29 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int l = lt * p.BL + row % p.BL;
       const bool valid = (mt < n_mt) && (b < p.B) && (l < p.Lout) && !(p.dbg & 1);
       const size_t orow = (size_t)b * p.out_rows + (size_t)l * p.out_row_stride + p.out_row_offset;
+      // The epilogue is a chain of dependent (load -> TMEM read -> math -> store) steps per 32-column chunk with one
+      // or two warps per scheduler: its global loads were served from HBM at full latency (the backward launches,
+      // which read the saved operand rows, ran at ~1.7 TB/s).  Pull the NEXT tile's row segments of every epilogue
+      // operand into L2 now -- a whole tile ahead -- so the loads issued later hit L2.
+      if (part == 0 && !(p.dbg & 8)) {
+        const int tile2 = tile + num_pairs;
+        if (tile2 < num_tiles) {
+          const int mt2 = (tile2 / p.n_nt) * 2 + (int)rank;
+          const int b2 = (mt2 / p.n_lt) * p.BB + row / p.BL;
+          const int l2 = (mt2 % p.n_lt) * p.BL + row % p.BL;
+          if (mt2 < n_mt && b2 < p.B && l2 < p.Lout) {
+            const size_t off2 = ((size_t)b2 * p.out_rows + (size_t)l2 * p.out_row_stride + p.out_row_offset) * p.Cout +
+                                (size_t)(tile2 % p.n_nt) * BLOCK_N;
+#pragma unroll
+            for (int c = 0; c < BLOCK_N; c += 64) {       // 128-byte lines of a bf16 row segment
+              if (p.dact_src) prefetch_l2(p.dact_src + off2 + c);
+              if (p.fm_d) prefetch_l2(p.dact_src + (b2 < p.fm_bh ? off2 + p.fm_half : off2 - p.fm_half) + c);
+              if (p.res_bf16) prefetch_l2(p.res_bf16 + off2 + c);
+              if (p.res_act) prefetch_l2(p.res_act + off2 + c);
+            }
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;

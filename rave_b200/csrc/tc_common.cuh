@@ -67,6 +67,8 @@ __device__ __forceinline__ void stg256(void *p, const uint32_t *r) {
                : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // One lane of a fully converged warp.  The producer / MMA-issue loops run WARP-UNIFORM (all 32 lanes execute the
 // loop, only the UTMALDG / UTCHMMA / UTCBAR instructions are predicated on the elected lane): stage indices, shared
 // memory addresses and descriptors then live in uniform registers.  Inside an `if (lane == 0)` region the compiler

@@ -22,6 +22,9 @@ SHAPES = [
     ("unit 96->96 k3 B32", 32, 96, 96, 4096, 3, 1, 1, 1),
     ("fused dgrad 192->4x96 (J=4)", 64, 192, 384, 4096, 4, 1, 1, 2),
     ("unit 768->768 k3 L=64", 32, 768, 768, 64, 3, 1, 1, 1),
+    ("BWD fused dgrad 192->4x96 (J=2, mask + fm partner)", 320, 192, 384, 820, 2, 1, 1, 1),
+    ("BWD fused dgrad 192->4x96 (J=4, mask + fm partner)", 64, 192, 384, 4096, 4, 1, 1, 2),
+    ("BWD fused dgrad 384->4x192 (J=4, mask + fm partner)", 64, 384, 768, 1024, 4, 1, 1, 2),
 ]
 CONFIGS = [
     ("default", {}),
@@ -30,6 +33,7 @@ CONFIGS = [
     ("no epilogue stores", {"RAVE_TC_DBG": "1"}),
     ("no loads at all", {"RAVE_TC_DBG": "6"}),
     ("no loads, no stores", {"RAVE_TC_DBG": "7"}),
+    ("no L2 prefetch of epilogue operands", {"RAVE_TC_DBG": "8"}),
     ("L2 promotion none", {"RAVE_TC_L2PROMO": "0"}),
     ("1-CTA kernel", {"RAVE_TC_2CTA": "0"}),
 ]
@@ -40,6 +44,9 @@ for name, B, Cin, Cout, Lin, K, stride, dil, pad in SHAPES:
     wt = (torch.randn(K, Cout, Cin, device="cuda") * 0.05).bfloat16()
     Lout = (Lin + 2 * pad - dil * (K - 1) - 1) // stride + 1
     oa = torch.empty(B, Lout, Cout, device="cuda", dtype=torch.bfloat16)
+    bwd = name.startswith("BWD")
+    dact = torch.randn(B, Lout, Cout, device="cuda").bfloat16() if bwd else None
+    fmd = torch.tensor([0.3, -0.2], device="cuda") if bwd else None
     fl = 2.0 * B * Lout * Cout * Cin * K
     print(f"== {name}: {fl/1e9:.1f} GFLOP, rows {B*Lout}", flush=True)
     for cname, env in CONFIGS:
@@ -50,8 +57,8 @@ for name, B, Cin, Cout, Lin, K, stride, dil, pad in SHAPES:
         os.environ.update(env)
 
         def run():
-            ops.conv1d_tc(x, wt, None, None, stride, dil, (pad, pad), 1, 0.2, want_f32=False, want_act=False,
-                          out_f32=None, out_act=oa, Lout=Lout)
+            ops.conv1d_tc(x, wt, None, None, stride, dil, (pad, pad), 0 if bwd else 1, 0.2, want_f32=False,
+                          want_act=False, out_f32=None, out_act=oa, Lout=Lout, dact_src=dact, fm_d=fmd)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
