@@ -249,7 +249,9 @@ typedef struct rave_wprep_layer {
   const float *v, *g;          /* parameter [C0][C1][K] and its weight-norm gain (or NULL)            */
   float *norm;                 /* [C0] row norms: written by prep, read by the backward                */
   void *outA, *outB;           /* bf16 outputs as in rave_weight_prep_tc (either may be NULL)         */
-  const float *dwt;            /* backward: [splits][K][C0p][C1p] fp32 partial weight gradients       */
+  const float *dwt;            /* backward: [splits][K][C0p][C1p] fp32 partial weight gradients; or, when nA > 1,
+                                  the phase-wide form [splits][nB][C0p][nA*C1p] (strided layers: the wgrad ran on
+                                  the operand viewed with nA positions per row) with tap k in slot tapsA[k] = j*nA+p */
   float *dv, *dg;              /* backward: gradients of v and g                                      */
   int C0, C1, K, C0p, C1p, nA, nB, splits;
   int tapsA[32], tapsB[32];    /* tap index, or -1 for an all-zero slab (phase-fused layouts)          */

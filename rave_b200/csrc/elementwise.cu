@@ -496,6 +496,8 @@ struct MtLayer {
   const float *dwt;     // backward only
   float *dv, *dg;       // backward only
   int C0, C1, K, C0p, C1p, nA, nB, splits;
+  int wide, J;          // backward with a phase-wide gradient buffer [S][J][C0p][wide*C1p]: tap k lives in slot
+                        // tapsA[k] = j*wide + p (0 / 0: plain [S][K][C0p][C1p])
   int row_begin;        // prefix sum of C0 (row-parallel kernels)
   int tile_begin;       // prefix sum of tiles (prep kernel)
   unsigned char tapsA[32], tapsB[32];
@@ -589,12 +591,14 @@ __global__ void __launch_bounds__(256) mt_wn_bwd_kernel(const __grid_constant__ 
   const int R = C1 * K;
   const float *vr = L.v + (size_t)c0 * R;
   float *dr = L.dv + (size_t)c0 * R;
-  const size_t split_stride = (size_t)K * C0p * C1p;
+  const int wide = L.wide > 1 ? L.wide : 1;
+  const size_t split_stride = (size_t)(L.wide > 1 ? L.J : K) * C0p * C1p * wide;
   float s = 0.f;
   for (int j = threadIdx.x; j < R; j += blockDim.x) {
     const int k = j / C1, c1 = j - k * C1;
     const int i = c1 * K + k;
-    const float *src = L.dwt + ((size_t)k * C0p + c0) * C1p + c1;
+    const int slot = L.wide > 1 ? (int)L.tapsA[k] : k;
+    const float *src = L.dwt + ((size_t)(slot / wide) * C0p + c0) * ((size_t)C1p * wide) + (size_t)(slot % wide) * C1p + c1;
     float dw = 0.f;
     for (int sp = 0; sp < L.splits; ++sp) dw += src[sp * split_stride];
     dr[i] = dw;
@@ -671,6 +675,15 @@ extern "C" int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers,
     MtLayer &L = t.L[i];
     L.v = h.v; L.g = h.g; L.norm = h.norm; L.dwt = h.dwt; L.dv = h.dv; L.dg = h.dg;
     L.C0 = h.C0; L.C1 = h.C1; L.K = h.K; L.C0p = h.C0p; L.C1p = h.C1p; L.splits = h.splits;
+    L.wide = h.nA > 1 ? h.nA : 0;
+    L.J = h.nB;
+    if (L.wide) {
+      RAVE_CHECK_ARG(h.K <= 32 && h.nB >= 1, "weight_norm_bwd_multi: bad phase-wide layer %d", i);
+      for (int k = 0; k < h.K; ++k) {
+        RAVE_CHECK_ARG(h.tapsA[k] >= 0 && h.tapsA[k] < h.nA * h.nB, "weight_norm_bwd_multi: bad tap slot (layer %d)", i);
+        L.tapsA[k] = (unsigned char)h.tapsA[k];
+      }
+    }
     L.row_begin = rows;
     rows += h.C0;
   }

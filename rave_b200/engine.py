@@ -224,6 +224,17 @@ def _fused_phase_taps(K: int, stride: int, pad: int):
     return taps, J, -omin
 
 
+def _wide_wgrad_taps(K: int, stride: int, pad: int):
+    """Weight gradient of a strided layer on the operand viewed with `stride` positions per row: tap k reads source
+    row l*stride + k - pad = (l + j)*stride + p, i.e. row l + j / channel block p of the view.  Returns (J, pad_l,
+    slots) with slots[k] = (j - jmin)*stride + p: a J-tap stride-1 wgrad over stride-times wider rows (128-byte-plus
+    contiguous TMA rows, the P tiles fetched J times instead of K times)."""
+    js = [(k - pad) // stride for k in range(K)]
+    jmin = min(js)
+    slots = [(j - jmin) * stride + ((k - pad) - j * stride) for k, j in enumerate(js)]
+    return max(js) - jmin + 1, -jmin, slots
+
+
 class _PreparedWeights:
     """Effective weight of one layer in every tap-major bf16 layout the kernels need.  `plan()` decides
     which layouts / tap orders are required; `prepare_layers()` produces them for a whole chain with ONE
@@ -508,6 +519,7 @@ class TcChainFn(torch.autograd.Function):
             #      streams when g is its P operand, i.e. for conv layers)
             want_db = bias is not None and bias.requires_grad
             db = None
+            remap = None
             if v.requires_grad:
                 if want_db and s.kind == "conv":
                     db = torch.zeros(cout_p, dtype=torch.float32, device=g.device)
@@ -515,12 +527,22 @@ class TcChainFn(torch.autograd.Function):
                     d = ops.conv1d_tc_wgrad(g, ctx.c1_X, 1, 1, 1, 0, Lp=Lout, Lq=Lout, dbias=db)  # [S][1][Cout_p][16]
                     dw_ck = d.sum(0)[0][:s.Cout, :s.K]                                         # [Cout][K]
                     dwt = dw_ck.t().reshape(1, s.K, s.Cout, 1).contiguous()                    # [1][K][C0][C1=1]
-                elif s.kind == "conv":
-                    dwt = ops.conv1d_tc_wgrad(g, a_in, s.K, s.stride, s.dil, s.pad[0], Lp=Lout, Lq=Lin, dbias=db)
                 else:
-                    dwt = ops.conv1d_tc_wgrad(a_in, g, s.K, s.stride, 1, s.pad[0], Lp=Lin, Lq=Lout)
-                # dwt is [S][K][C0p][C1p] in the parameter's own (C0, C1) order for both kinds
-                wn_jobs.append((i, dwt, v, gpar, pw.norm))
+                    P_op, Q_op = (g, a_in) if s.kind == "conv" else (a_in, g)
+                    Lp_, Lq_ = (Lout, Lin) if s.kind == "conv" else (Lin, Lout)
+                    st = s.stride
+                    if st > 1 and s.dil == 1 and Q_op.shape[1] % st == 0 and s.K <= 32:
+                        # strided layer: wgrad on the Q operand viewed with `stride` positions per row
+                        J, padw, slots = _wide_wgrad_taps(s.K, st, s.pad[0])
+                        Bq, qp, cq = Q_op.shape
+                        dwt = ops.conv1d_tc_wgrad(P_op, Q_op.view(Bq, qp // st, st * cq), J, 1, 1, padw, Lp=Lp_,
+                                                  Lq=(Lq_ + st - 1) // st, dbias=db)
+                        remap = (st, slots)
+                    else:
+                        dwt = ops.conv1d_tc_wgrad(P_op, Q_op, s.K, st, s.dil if s.kind == "conv" else 1, s.pad[0],
+                                                  Lp=Lp_, Lq=Lq_, dbias=db)
+                # dwt is [S][K][C0p][C1p] (or the phase-wide form + remap) in the parameter's own (C0, C1) order
+                wn_jobs.append((i, dwt, v, gpar, pw.norm, remap))
             if want_db:
                 grads[3 * i + 2] = db[:s.Cout] if db is not None else ops.colsum_bf16(g, Lout, s.Cout)
             # ---- input gradient
@@ -592,8 +614,9 @@ class TcChainFn(torch.autograd.Function):
             if i == 0:
                 gx = gp
         if wn_jobs:
-            res = ops.weight_norm_bwd_multi([(dwt, v, gpar, norm) for (_, dwt, v, gpar, norm) in wn_jobs])
-            for (i, _, _, _, _), (dv, dg) in zip(wn_jobs, res):
+            res = ops.weight_norm_bwd_multi([job[1:] for job in wn_jobs])
+            for job, (dv, dg) in zip(wn_jobs, res):
+                i = job[0]
                 grads[3 * i], grads[3 * i + 1] = dv, dg
         return (gx, None, None, None, None) + tuple(grads)
 

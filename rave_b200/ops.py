@@ -684,22 +684,32 @@ def weight_prep_tc_multi(items):
 
 
 def weight_norm_bwd_multi(items):
-    """items: list of (dwt [S][K][C0p][C1p], v, g | None, norm | None).  Returns a list of (dv, dg | None)."""
+    """items: list of (dwt [S][K][C0p][C1p], v, g | None, norm | None[, remap]).  remap = (wide, slots): the
+    gradient buffer is phase-wide, [S][J][C0p][wide*C1p], with parameter tap k in slot slots[k] = j*wide + p.
+    Returns a list of (dv, dg | None)."""
     outs = []
     recs = []
-    for (dwt, v, g, norm) in items:
+    for item in items:
+        dwt, v, g, norm = item[:4]
+        remap = item[4] if len(item) > 4 else None
         v = _f32c(v)
         dv = torch.empty_like(v)
         dg = torch.empty_like(g) if g is not None else None
         outs.append((dv, dg))
-        recs.append((dwt, v, g, norm, dv, dg))
+        recs.append((dwt, v, g, norm, dv, dg, remap))
     for i0 in range(0, len(recs), 64):
         chunk = recs[i0:i0 + 64]
         arr = (_lib.WPrepLayer * len(chunk))()
-        for L, (dwt, v, g, norm, dv, dg) in zip(arr, chunk):
+        for L, (dwt, v, g, norm, dv, dg, remap) in zip(arr, chunk):
             C0, C1 = v.shape[0], v.shape[1]
             L.v, L.g, L.norm, L.dwt, L.dv, L.dg = ptr(v), ptr(g), ptr(norm), ptr(dwt), ptr(dv), ptr(dg)
             L.C0, L.C1, L.K = C0, C1, v.numel() // (C0 * C1)
             L.C0p, L.C1p, L.splits = dwt.shape[2], dwt.shape[3], dwt.shape[0]
+            if remap is not None:
+                wide, slots = remap
+                L.C1p = dwt.shape[3] // wide
+                L.nA, L.nB = wide, dwt.shape[1]
+                for k, sl in enumerate(slots):
+                    L.tapsA[k] = sl
         call("rave_weight_norm_bwd_multi", len(chunk), arr, stream_ptr())
     return outs

@@ -281,7 +281,17 @@ def weight_prep_tc_multi(items):
 
 
 def weight_norm_bwd_multi(items):
-    return [weight_norm_bwd_tapmajor(*it) for it in items]
+    out = []
+    for it in items:
+        dwt, v, g, norm = it[:4]
+        if len(it) > 4 and it[4] is not None:          # phase-wide buffer [S][J][C0p][wide*C1p] -> [S][K][C0p][C1p]
+            wide, slots = it[4]
+            S, J, C0p, W = dwt.shape
+            C1p = W // wide
+            d5 = dwt.reshape(S, J, C0p, wide, C1p)
+            dwt = torch.stack([d5[:, sl // wide, :, sl % wide, :] for sl in slots], 1)
+        out.append(weight_norm_bwd_tapmajor(dwt, v, g, norm))
+    return out
 
 
 def install(monkeypatch):
