@@ -39,7 +39,10 @@ CONFIGS = [
 ]
 KEYS = ["RAVE_TC_STAGES", "RAVE_TC_DBG", "RAVE_TC_L2PROMO", "RAVE_TC_EPIWARPS"]
 
+FILTER = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, B, Cin, Cout, Lin, K, stride, dil, pad in SHAPES:
+    if FILTER and FILTER not in name:
+        continue
     x = torch.randn(B, Lin, Cin, device="cuda").bfloat16()
     wt = (torch.randn(K, Cout, Cin, device="cuda") * 0.05).bfloat16()
     Lout = (Lin + 2 * pad - dil * (K - 1) - 1) // stride + 1
