@@ -106,8 +106,12 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
   else tmem_ld_32x16(taddr, v);       // warp-collective: every lane participates, valid or not
   if (!valid) return;
   if (p.bias) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + co);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] += __ldg(p.bias + co + i);
+    for (int i = 0; i < CW / 4; ++i) {
+      const float4 bb = __ldg(b4 + i);
+      v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+    }
   }
   if (p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand (sign bits of bf16)
 #pragma unroll
@@ -146,8 +150,8 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       const float a0 = bf_lo(ra[w]), a1 = bf_hi(ra[w]);
-      v[2 * w] += a0 > 0.f ? a0 : a0 * p.res_inv_slope;
-      v[2 * w + 1] += a1 > 0.f ? a1 : a1 * p.res_inv_slope;
+      v[2 * w] += fminf(a0, a0 * p.res_inv_slope);          // inverse LeakyReLU (1/slope >= 1): two instructions
+      v[2 * w + 1] += fminf(a1, a1 * p.res_inv_slope);
     }
   }
   if (p.res) {
@@ -165,9 +169,9 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       float a0 = v[2 * w], a1 = v[2 * w + 1];
-      if (p.act == RAVE_ACT_LEAKY) {
-        a0 = a0 > 0.f ? a0 : a0 * p.slope;
-        a1 = a1 > 0.f ? a1 : a1 * p.slope;
+      if (p.act == RAVE_ACT_LEAKY) {       // 0 <= slope <= 1 (checked on the host): max(x, slope x)
+        a0 = fmaxf(a0, a0 * p.slope);
+        a1 = fmaxf(a1, a1 * p.slope);
       }
       __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
       pk[w] = *reinterpret_cast<uint32_t *>(&h);
@@ -760,6 +764,11 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
                  "conv1d_tc: input pitch %d < Lin %d rounded up to the stride %d (slack rows must be zero)", in_pitch,
                  Lin, stride);
   RAVE_CHECK_ARG(act == RAVE_ACT_NONE || act == RAVE_ACT_LEAKY, "conv1d_tc: epilogue activation %d unsupported", act);
+  RAVE_CHECK_ARG(act != RAVE_ACT_LEAKY || (slope >= 0.f && slope <= 1.f), "conv1d_tc: LeakyReLU slope %g outside [0, 1]",
+                 (double)slope);
+  RAVE_CHECK_ARG(!res_act || (res_slope > 0.f && res_slope <= 1.f), "conv1d_tc: res_slope %g outside (0, 1]",
+                 (double)res_slope);
+  RAVE_CHECK_ARG(((uintptr_t)bias & 15) == 0, "conv1d_tc: bias must be 16-byte aligned");
   RAVE_CHECK_ARG(((uintptr_t)xa & 15) == 0 && ((uintptr_t)wt & 15) == 0, "conv1d_tc: operands must be 16B aligned");
   RAVE_CHECK_ARG((((uintptr_t)out_f32 | (uintptr_t)out_act | (uintptr_t)res | (uintptr_t)res_bf16 | (uintptr_t)dact_src |
                    (uintptr_t)res_act) & 31) == 0,

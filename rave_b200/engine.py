@@ -531,9 +531,10 @@ class TcChainFn(torch.autograd.Function):
                     P_op, Q_op = (g, a_in) if s.kind == "conv" else (a_in, g)
                     Lp_, Lq_ = (Lout, Lin) if s.kind == "conv" else (Lin, Lout)
                     st = s.stride
-                    if st > 1 and s.dil == 1 and Q_op.shape[1] % st == 0 and s.K <= 32:
-                        # strided layer: wgrad on the Q operand viewed with `stride` positions per row
-                        J, padw, slots = _wide_wgrad_taps(s.K, st, s.pad[0])
+                    J, padw, slots = _wide_wgrad_taps(s.K, st, s.pad[0]) if st > 1 else (0, 0, None)
+                    if st > 1 and s.dil == 1 and Q_op.shape[1] % st == 0 and s.K <= 32 and 4 * J * st <= 5 * s.K:
+                        # strided layer with many taps (K = 15, stride 4: 16 slots for 15 taps): wgrad on the Q operand
+                        # viewed with `stride` positions per row.  Short kernels (K = 5: 8 slots) would waste the MMAs.
                         Bq, qp, cq = Q_op.shape
                         dwt = ops.conv1d_tc_wgrad(P_op, Q_op.view(Bq, qp // st, st * cq), J, 1, 1, padw, Lp=Lp_,
                                                   Lq=(Lq_ + st - 1) // st, dbias=db)
