@@ -77,18 +77,35 @@ spectral_grad_kernel(const float2 *__restrict__ X, const float2 *__restrict__ Y,
 // fold of the reflected borders) instead of mul + index_add + reflection_pad1d_backward.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-stft_frames_kernel(const float *__restrict__ x, const float *__restrict__ w, float *__restrict__ frames, long total,
-                   int T, int n_fft, int hop, int F) {
+stft_frames_kernel(const float *__restrict__ x, const float *__restrict__ w, float *__restrict__ frames, long total4,
+                   int T, int n_fft, int hop, int F, int vec_ok) {
+  // one thread = 4 consecutive samples of one frame (n_fft is a power of two >= 16: shifts, one division by F)
   const int h = n_fft >> 1;
-  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-    const int t = (int)(i % n_fft);
-    const long nf = i / n_fft;
+  const int q = n_fft >> 2;                   // float4 per frame
+  const int qs = 31 - __clz(q);
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += (long)gridDim.x * 256) {
+    const int t = (int)(i & (q - 1)) << 2;
+    const long nf = i >> qs;
     const int f = (int)(nf % F);
     const long n = nf / F;
-    int j = f * hop + t - h;
-    if (j < 0) j = -j;
-    if (j >= T) j = 2 * (T - 1) - j;
-    frames[i] = __ldg(w + t) * __ldg(x + n * T + j);
+    const int j0 = f * hop + t - h;
+    const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + t));
+    const float *xn = x + n * T;
+    float4 xv;
+    if (vec_ok && j0 >= 0 && j0 + 3 < T) {
+      xv = __ldg(reinterpret_cast<const float4 *>(xn + j0));
+    } else {
+      float e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int j = j0 + u;
+        if (j < 0) j = -j;
+        if (j >= T) j = 2 * (T - 1) - j;
+        e[u] = __ldg(xn + j);
+      }
+      xv = make_float4(e[0], e[1], e[2], e[3]);
+    }
+    reinterpret_cast<float4 *>(frames)[i] = make_float4(ww.x * xv.x, ww.y * xv.y, ww.z * xv.z, ww.w * xv.w);
   }
 }
 
@@ -127,13 +144,15 @@ stft_frames_bwd_kernel(const float *__restrict__ dframes, const float *__restric
 extern "C" int rave_stft_frames(const float *x, const float *window, float *frames, int N, int T, int n_fft, int hop,
                                 void *stream) {
   using namespace rave;
-  RAVE_CHECK_ARG(x && window && frames && N > 0 && T > n_fft / 2 && n_fft >= 2 && hop > 0 && n_fft % hop == 0,
-                 "stft_frames: bad argument (reflect padding needs T > n_fft/2, hop | n_fft)");
+  RAVE_CHECK_ARG(x && window && frames && N > 0 && T > n_fft / 2 && n_fft >= 16 && (n_fft & (n_fft - 1)) == 0 &&
+                     hop > 0 && n_fft % hop == 0 && hop % 4 == 0,
+                 "stft_frames: bad argument (reflect padding needs T > n_fft/2; n_fft a power of two >= 16, 4 | hop | n_fft)");
   const int F = 1 + T / hop;
-  const long total = (long)N * F * n_fft;
-  long blocks = (total + 255) / 256;
+  const long total4 = (long)N * F * (n_fft / 4);
+  long blocks = (total4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  stft_frames_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, window, frames, total, T, n_fft, hop, F);
+  const int vec_ok = (T % 4 == 0) && (((uintptr_t)x & 15) == 0);
+  stft_frames_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, window, frames, total4, T, n_fft, hop, F, vec_ok);
   RAVE_CHECK_LAUNCH("stft_frames");
   return 0;
 }

@@ -500,6 +500,14 @@ class TcChainFn(torch.autograd.Function):
         grads = [None] * len(flat)
         gx = None
         wn_jobs = []       # (layer, dwt partials, v, g, norm): one multi-tensor launch at the end
+        # bias gradients accumulated by the wgrad kernels: ONE zero-filled buffer for the whole chain
+        db_off, db_total = {}, 0
+        for i, s in enumerate(specs):
+            bias_i, v_i = flat[3 * i + 2], flat[3 * i]
+            if s.kind == "conv" and bias_i is not None and bias_i.requires_grad and v_i.requires_grad:
+                db_off[i] = db_total
+                db_total += (s.Cout + s.cout_pad + 7) // 8 * 8
+        db_all = torch.zeros(db_total, dtype=torch.float32, device=ctx.acts[-1].device) if db_total else None
         for i in range(n - 1, -1, -1):
             s = specs[i]
             pw = ctx.prepared[i]
@@ -521,8 +529,8 @@ class TcChainFn(torch.autograd.Function):
             db = None
             remap = None
             if v.requires_grad:
-                if want_db and s.kind == "conv":
-                    db = torch.zeros(cout_p, dtype=torch.float32, device=g.device)
+                if i in db_off:
+                    db = db_all[db_off[i]:db_off[i] + cout_p]
                 if use_c1:
                     d = ops.conv1d_tc_wgrad(g, ctx.c1_X, 1, 1, 1, 0, Lp=Lout, Lq=Lout, dbias=db)  # [S][1][Cout_p][16]
                     dw_ck = d.sum(0)[0][:s.Cout, :s.K]                                         # [Cout][K]

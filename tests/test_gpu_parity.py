@@ -387,7 +387,7 @@ def test_stft_framing_kernels_vs_torch_stft():
     """rave_stft_frames (+ cuFFT) against torch.stft(center=True, reflect) and its autograd, ragged lengths."""
     from rave_b200 import core
     torch.manual_seed(3)
-    for (N, T, scales) in [(3, 4096, [2048, 1024, 512, 256, 128]), (2, 1100, [512, 128]), (5, 65536, [2048, 128])]:
+    for (N, T, scales) in [(3, 4096, [2048, 1024, 512, 256, 128]), (2, 1100, [512, 128]), (2, 1101, [256]), (5, 65536, [2048, 128])]:
         m = core.MultiScaleSTFT(scales, 48000, magnitude=True).cuda()
         x = torch.randn(N, T, device="cuda", requires_grad=True)
         got = m.complex_stfts(x)
