@@ -1151,6 +1151,7 @@ static void wg_geometry(int B, int Cm, int Lp, int Cn, int K, int *BL, int *n_lt
   const int tiles = K * (*n_mt) * (*n_nt);
   const int n_chunks = (*n_lt) * (*n_bg);
   int s = ceil_div(2 * 148, tiles);
+  if (s > 32) s = 32;      // every slice writes a full partial tile that the weight-norm backward re-reads
   if (s > n_chunks) s = n_chunks;
   if (s < 1) s = 1;
   *splits = s;

@@ -599,8 +599,15 @@ __global__ void __launch_bounds__(256) mt_wn_bwd_kernel(const __grid_constant__ 
     const int i = c1 * K + k;
     const int slot = L.wide > 1 ? (int)L.tapsA[k] : k;
     const float *src = L.dwt + ((size_t)(slot / wide) * C0p + c0) * ((size_t)C1p * wide) + (size_t)(slot % wide) * C1p + c1;
-    float dw = 0.f;
-    for (int sp = 0; sp < L.splits; ++sp) dw += src[sp * split_stride];
+    // split-K partials: 8 independent loads in flight per thread (the sum was a chain of dependent L2 round trips)
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int sp = 0;
+    for (; sp + 8 <= L.splits; sp += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += __ldg(src + (size_t)(sp + u) * split_stride);
+    }
+    for (; sp < L.splits; ++sp) acc[sp & 7] += __ldg(src + (size_t)sp * split_stride);
+    const float dw = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     dr[i] = dw;
     s = fmaf(dw, vr[i], s);
   }
