@@ -137,7 +137,9 @@ int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, i
  *   fm_d    2 device floats (d0, d1) or NULL  : fused feature-matching gradient (needs dact_src): the batch is
  *             [real; fake] with fm_bh rows per half; after the LeakyReLU' mask the epilogue adds, with
  *             h = LeakyReLU^-1(dact_src), d0 sgn(h_r-h_f) + d1 sgn(h_r) to real rows and -d0 sgn(h_r-h_f) to fake
- *             rows (rave/model.py:355-361 with core.mean_difference L1, rave/core.py:236-252)
+ *             rows (rave/model.py:355-361 with core.mean_difference L1, rave/core.py:236-252).  fm_bh < 0: the
+ *             launch covers ONLY the fake half (B = -fm_bh rows; generator step: the real half's input gradient is
+ *             never used), the real partner rows lie |fm_bh| batches before dact_src in the same allocation
  *   out_f32 [B][out_rows][Cout] fp32 or NULL : pre-activation stream (residual / features)
  *   out_act [B][out_rows][Cout] bf16 or NULL : act(out), the next conv's operand
  * Output row of (b,l) is l*out_row_stride + out_row_offset (phases of a transposed conv interleave);

@@ -795,12 +795,12 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   p.out_rows = out_rows > 0 ? out_rows : Lout;
   p.out_row_stride = out_row_stride > 0 ? out_row_stride : 1;
   p.out_row_offset = out_row_offset;
-  RAVE_CHECK_ARG(!fm_d || (dact_src && fm_bh > 0 && 2 * fm_bh == B && slope > 0.f),
+  RAVE_CHECK_ARG(!fm_d || (dact_src && slope > 0.f && ((fm_bh > 0 && 2 * fm_bh == B) || (fm_bh < 0 && -fm_bh == B))),
                  "conv1d_tc: the fused feature-matching gradient needs dact_src and a [real; fake] batch (B=%d, fm_bh=%d)",
                  B, fm_bh);
   p.fm_d = fm_d;
-  p.fm_bh = fm_bh;
-  p.fm_half = (long)fm_bh * p.out_rows * Cout;
+  p.fm_bh = fm_bh > 0 ? fm_bh : 0;                 // fm_bh < 0: every row is a fake row (partner |fm_bh| batches before)
+  p.fm_half = (long)(fm_bh > 0 ? fm_bh : -fm_bh) * p.out_rows * Cout;
   p.stages = 0;
   p.dbg = 0;
   {

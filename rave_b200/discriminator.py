@@ -107,7 +107,7 @@ class ConvNet(nn.Module):
             xa = nn.functional.pad(rows, (0, first.cin_pad, 0, rpad)).to(engine.ACT_DTYPE).contiguous()
         return xa, B, W, L
 
-    def forward_fm(self, x, period: int = 1, pool: int = 1):
+    def forward_fm(self, x, period: int = 1, pool: int = 1, fake_grad_only: bool = False):
         """Fused feature-matching path (bf16 engine): x = cat([real, fake]) RAW signal [B, 1, T] -> (stats [n-1, 2],
         counts, score, score_stats [3, 2], n_score) with stats[i] = (sum|h_r - h_f|, sum|h_r|) of hidden feature i,
         counts[i] = its number of elements per half, score = the last conv's output in the reference's shape,
@@ -122,7 +122,8 @@ class ConvNet(nn.Module):
         B, _, T = x.shape
         W = period
         L = (T + period - 1) // period if period > 1 else T // pool
-        stats, score_stats, last = engine.run_chain(x.reshape(B, T), specs, L, fm=True, src=(period, pool))
+        stats, score_stats, last = engine.run_chain(x.reshape(B, T), specs, L, fm=True, src=(period, pool),
+                                                    fake_grad_only=fake_grad_only)
         lens = engine.chain_lengths(specs, L)
         counts = [(B // 2) * W * Lo * s.Cout for s, Lo in zip(specs[:-1], lens[:-1])]
         o = last[:, :lens[-1], :specs[-1].Cout]
@@ -176,9 +177,9 @@ class MultiScaleDiscriminator(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList([convnet(in_size=n_channels) for _ in range(n_discriminators)])
 
-    def forward_fm(self, x):
+    def forward_fm(self, x, fake_grad_only: bool = False):
         # scale i sees avg_pool1d(., 2) applied i times = the mean over 2^i consecutive samples (floor lengths agree)
-        return [layer.forward_fm(x, pool=2 ** i) for i, layer in enumerate(self.layers)]
+        return [layer.forward_fm(x, pool=2 ** i, fake_grad_only=fake_grad_only) for i, layer in enumerate(self.layers)]
 
     def forward(self, x):
         features = []
@@ -202,8 +203,9 @@ class MultiPeriodDiscriminator(nn.Module):
             features.append(layer(self.fold(x, n)))
         return features
 
-    def forward_fm(self, x):
-        return [layer.forward_fm(x, period=n) for layer, n in zip(self.layers, self.periods)]
+    def forward_fm(self, x, fake_grad_only: bool = False):
+        return [layer.forward_fm(x, period=n, fake_grad_only=fake_grad_only)
+                for layer, n in zip(self.layers, self.periods)]
 
     def fold(self, x, n):
         pad = (n - (x.shape[-1] % n)) % n
@@ -240,8 +242,10 @@ class CombineDiscriminators(nn.Module):
                     return False
         return True
 
-    def forward_fm(self, x):
+    def forward_fm(self, x, fake_grad_only: bool = False):
+        """fake_grad_only: the caller will only use the gradient with respect to the FAKE half of x (generator step,
+        frozen discriminator): the backward then runs on that half alone (engine.TcChainFn.backward)."""
         out = []
         for disc in self.discriminators:
-            out.extend(disc.forward_fm(x))
+            out.extend(disc.forward_fm(x, fake_grad_only=fake_grad_only))
         return out

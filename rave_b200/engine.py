@@ -342,7 +342,7 @@ class TcChainFn(torch.autograd.Function):
                    tensors (RAVE._fused_feature_matching), whose gradients drive fm_grad / score_grad here."""
 
     @staticmethod
-    def forward(ctx, x_in, specs, L0, fm, src, *flat):
+    def forward(ctx, x_in, specs, L0, fm, src, fake_grad_only, *flat):
         n = len(specs)
         ctx.set_materialize_grads(False)
         need_dgrad = x_in.requires_grad or any(t is not None and t.requires_grad for t in flat)
@@ -351,6 +351,7 @@ class TcChainFn(torch.autograd.Function):
         B = x_in.shape[0] * period
         ctx.c1_src = (period, pool, tuple(x_in.shape))
         ctx.B = B
+        ctx.fake_grad_only = bool(fake_grad_only) and fm
         if c1 and not (specs[0].kind == "conv" and specs[0].Cin == 1 and specs[0].dil == 1):
             raise _lib.RaveB200Error("raw fp32 rows are only accepted by a Cin = 1 first conv")
         dev = x_in.device
@@ -480,6 +481,17 @@ class TcChainFn(torch.autograd.Function):
         n = len(specs)
         flat = ctx.params
         B = ctx.B
+        # Generator step through a discriminator chain ([real; fake] batch, frozen parameters): the gradient of the real
+        # rows only ever reaches the real INPUT, which nobody asks for -- conv layers do not mix batch rows, the
+        # feature-matching term of the fake rows needs the real activations only as constants.  Run the whole backward
+        # on the fake half (half the dgrad FLOPs and bytes).
+        fo = ctx.fake_grad_only and not any(t is not None and t.requires_grad for t in flat)
+        Bh = B // 2
+        if fo:
+            B = Bh
+
+        def half(t):
+            return t[Bh:] if (fo and t is not None) else t
         ext: Dict[int, torch.Tensor] = {}      # external gradient of layer i's output (ACT_DTYPE, h-space)
         dstats = None
         if ctx.fm:
@@ -487,9 +499,9 @@ class TcChainFn(torch.autograd.Function):
             if dstats is not None:
                 dstats = dstats.contiguous()
             if gouts[2] is not None:
-                ext[n - 1] = gouts[2].to(ACT_DTYPE).contiguous()
+                ext[n - 1] = half(gouts[2].to(ACT_DTYPE).contiguous())
             if gouts[1] is not None and ctx.score_f32 is not None:
-                e = ops.score_grad(ctx.score_f32, gouts[1].to(torch.float32).contiguous(), ctx.lens[-1])
+                e = half(ops.score_grad(ctx.score_f32, gouts[1].to(torch.float32).contiguous(), ctx.lens[-1]))
                 ext[n - 1] = e if (n - 1) not in ext else ext[n - 1] + e
         else:
             for i, g in zip(ctx.out_index, gouts):
@@ -511,9 +523,10 @@ class TcChainFn(torch.autograd.Function):
         for i in range(n - 1, -1, -1):
             s = specs[i]
             pw = ctx.prepared[i]
-            a_in = ctx.acts[i]
-            Lin, Lout = ctx.lens[i], ctx.lens[i + 1]
             use_c1 = ctx.c1 and i == 0
+            a_full = ctx.acts[i]
+            a_in = a_full if use_c1 else half(a_full)
+            Lin, Lout = ctx.lens[i], ctx.lens[i + 1]
             g = g_cur
             if g is None:
                 g = ext.get(i)
@@ -573,6 +586,7 @@ class TcChainFn(torch.autograd.Function):
             if e is not None:
                 add = e if add is None else (add + e)
             dact = a_in if s.pre_act == ops.ACT_LEAKY else None
+            fm_partner = a_full[:Bh] if (fo and fm_d is not None) else None
             in_pitch = a_in.shape[1]
             if use_c1:                  # P[r][l][k] = <g[r][l][:], w[:][k]> on the tensor cores, then a gather
                 G = ctx.c1_group
@@ -588,7 +602,8 @@ class TcChainFn(torch.autograd.Function):
                     P, _ = ops.conv1d_tc(g, wt_d, None, None, 1, 1, (0, 0), ops.ACT_NONE, 0.0, want_f32=True,
                                          want_act=False, Lout=Lout, Lin=Lout)
                 period, pool, src_shape = ctx.c1_src
-                gx = ops.gather_c1(P, src_shape, Lin, Lout, s.K, s.stride, s.pad[0], period, pool)
+                gx = ops.gather_c1(P, src_shape, Lin, Lout, s.K, s.stride, s.pad[0], period, pool,
+                                   batch0=src_shape[0] // 2 if fo else 0)
                 break
             gp = torch.empty(B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)
             if in_pitch > Lin:
@@ -598,7 +613,8 @@ class TcChainFn(torch.autograd.Function):
                     padp = (s.K - 1) * s.dil - s.pad[0]
                     ops.conv1d_tc(g, pw.dgrad, None, None, 1, s.dil, (padp, 0), ops.ACT_NONE, s.pre_slope,
                                   want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout,
-                                  out_rows=in_pitch, res_bf16=add, dact_src=dact, fm_d=fm_d)
+                                  out_rows=in_pitch, res_bf16=add, dact_src=dact, fm_d=fm_d,
+                                  fm_partner=fm_partner)
                 else:
                     # strided conv: the `stride` input phases side by side in one stride-1 conv over g (row q of the
                     # result = input positions q*stride .. +stride-1); g rows are fetched once, not once per phase
@@ -612,13 +628,14 @@ class TcChainFn(torch.autograd.Function):
                         return t.view(B, rows_q, wide) if t is not None else None
                     ops.conv1d_tc(g, pw.dgrad_fused, None, None, 1, 1, (pw.fused_pad, 0), ops.ACT_NONE, s.pre_slope,
                                   want_f32=False, want_act=False, out_act=v4(gp), out_rows=rows_q, Lout=rows_q,
-                                  Lin=Lout, res_bf16=v4(add), dact_src=v4(dact), fm_d=fm_d)
+                                  Lin=Lout, res_bf16=v4(add), dact_src=v4(dact), fm_d=fm_d,
+                                  fm_partner=v4(fm_partner))
                     if in_pitch > Lin:
                         gp[:, Lin:].zero_()
             else:
                 ops.conv1d_tc(g, pw.dgrad, None, None, s.stride, 1, (s.pad[0], 0), ops.ACT_NONE, s.pre_slope,
                               want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout, out_rows=in_pitch,
-                              res_bf16=add, dact_src=dact, fm_d=fm_d)
+                              res_bf16=add, dact_src=dact, fm_d=fm_d, fm_partner=fm_partner)
             g_cur = gp
             if i == 0:
                 gx = gp
@@ -627,11 +644,11 @@ class TcChainFn(torch.autograd.Function):
             for job, (dv, dg) in zip(wn_jobs, res):
                 i = job[0]
                 grads[3 * i], grads[3 * i + 1] = dv, dg
-        return (gx, None, None, None, None) + tuple(grads)
+        return (gx, None, None, None, None, None) + tuple(grads)
 
 
 def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None, fm: bool = False,
-              src: Optional[Tuple[int, int]] = None):
+              src: Optional[Tuple[int, int]] = None, fake_grad_only: bool = False):
     """x_cl_bf16: [B, pitch, Cin(+pad)] (rows beyond the true length L0 must be zero), or raw fp32 rows
     [B, pitch] for a Cin = 1 first layer.  Returns one fp32 channel-last tensor [B, pitch_i, Cout_i(+pad)]
     per output layer (slice [:, :L_i, :Cout_i]); with fm=True: (stats [n-1, 2], score_stats [3, 2], last layer
@@ -642,7 +659,7 @@ def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int]
         flat += [v, g, b]
     if L0 is None:
         L0 = x_cl_bf16.shape[1]
-    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, src, *flat)
+    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, src, fake_grad_only, *flat)
 
 
 def chain_lengths(specs: List[LayerSpec], L0: int) -> List[int]:

@@ -287,7 +287,7 @@ class RAVE(nn.Module):
         if self.warmed_up:
             y_d = y_raw.detach() if is_dis_step else y_raw     # quirk D2: discarded gradients
             xy = torch.cat([x_raw, y_d], 0)
-            fused = self._fused_feature_matching(xy)
+            fused = self._fused_feature_matching(xy, fake_grad_only=not is_dis_step)
         if fused is not None:
             feature_matching_distance, loss_dis, loss_adv, pred_real, pred_fake = fused
         elif self.warmed_up:
@@ -323,7 +323,7 @@ class RAVE(nn.Module):
         aux = dict(pred_real=pred_real, pred_fake=pred_fake, y_raw=y_raw, z=z)
         return loss_gen, loss_dis, aux
 
-    def _fused_feature_matching(self, xy):
+    def _fused_feature_matching(self, xy, fake_grad_only: bool = False):
         """The discrimination block (rave/model.py:348-379) without materialising the hidden features:
         in bf16 mode every ConvNet returns, per hidden layer, (sum|h_r - h_f|, sum|h_r|) computed by the
         engine from its own operand stream, plus the score tensor.  Same arithmetic as
@@ -337,7 +337,7 @@ class RAVE(nn.Module):
         relative = bool(kw.get("relative", False))
         skip = self.num_skipped_features
         fm_total, loss_dis, loss_adv, pred_real, pred_fake = 0., 0., 0., 0., 0.
-        nets = disc.forward_fm(xy)
+        nets = disc.forward_fm(xy, fake_grad_only=fake_grad_only)
         tail = self._fused_tail(nets, relative, skip)
         if tail is not None:
             return tail

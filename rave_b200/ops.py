@@ -380,10 +380,11 @@ def conv1d_tc_supported(Cin, Cout, K=1, stride=1, dil=1):
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=ACT_NONE, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
               out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2,
-              fm_d=None):
+              fm_d=None, fm_partner=None):
     """xa_cl [B,Lin,Cin] bf16 (activated operand), wt [K,Cout,Cin] bf16 -> (out_f32 [B,Lout,Cout] fp32,
     out_act [B,Lout,Cout] bf16 = act(out)); either may be None.  fm_d (2 device floats): fused feature-matching
-    gradient of a [real; fake] batch, see include/rave_b200.h."""
+    gradient of a [real; fake] batch, see include/rave_b200.h; with fm_partner (the real rows, stored right before
+    dact_src in the same allocation) the launch covers the fake half only."""
     B, in_pitch, Cin = xa_cl.shape          # allocated rows per batch; true length = Lin (slack rows zero)
     if Lin is None:
         Lin = in_pitch
@@ -397,10 +398,18 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
         out_f32 = torch.empty(B, rows, Cout, dtype=torch.float32, device=xa_cl.device)
     if want_act and out_act is None:
         out_act = torch.empty(B, rows, Cout, dtype=torch.bfloat16, device=xa_cl.device)
+    fm_bh = 0
+    if fm_d is not None:
+        fm_bh = B // 2
+        if fm_partner is not None:
+            if (fm_partner.shape != dact_src.shape or not fm_partner.is_contiguous()
+                    or fm_partner.data_ptr() + fm_partner.numel() * fm_partner.element_size() != dact_src.data_ptr()):
+                raise _lib.RaveB200Error("conv1d_tc: fm_partner must be the half stored right before dact_src")
+            fm_bh = -B
     call("rave_conv1d_tc_fwd", ptr(xa_cl), ptr(wt), ptr(bias), ptr(res_cl), ptr(res_bf16), ptr(dact_src),
          ptr(res_act), float(res_slope), ptr(out_f32), ptr(out_act), B, Cin, Lin, in_pitch, Cout, Lout, K, stride, dil, pad[0], act, float(slope),
          out_rows, out_row_stride, out_row_offset, fm_d.data_ptr() if fm_d is not None else None,
-         B // 2 if fm_d is not None else 0, stream_ptr())
+         fm_bh, stream_ptr())
     return out_f32, out_act
 
 
@@ -564,14 +573,17 @@ def im2col_c1(src, Lin, Lout, out_pitch, K, stride, pad_l, period=1, pool=1):
     return X
 
 
-def gather_c1(P_cl, src_shape, Lin, Lout, K, stride, pad_l, period=1, pool=1):
-    """dsrc [Bs, T] fp32: the adjoint of im2col_c1 applied to P [R, p_pitch, 16] fp32 (taps, pooling, fold)."""
+def gather_c1(P_cl, src_shape, Lin, Lout, K, stride, pad_l, period=1, pool=1, batch0=0):
+    """dsrc [Bs, T] fp32: the adjoint of im2col_c1 applied to P [R, p_pitch, 16] fp32 (taps, pooling, fold).  With
+    batch0 > 0, P holds only the rows of source batches batch0 .. Bs-1 (the other gradients stay zero)."""
     P_cl = _f32c(P_cl)
     R, p_pitch, _ = P_cl.shape
     Bs, T = src_shape
     dsrc = torch.zeros(Bs, T, dtype=torch.float32, device=P_cl.device)
-    call("rave_gather_c1", ptr(P_cl), ptr(dsrc), R, T, T, Lin, Lout, p_pitch, K, stride, pad_l, period, pool,
-         stream_ptr())
+    if R != (Bs - batch0) * period:
+        raise _lib.RaveB200Error("gather_c1: row count does not match the source batches")
+    call("rave_gather_c1", ptr(P_cl), dsrc.data_ptr() + batch0 * T * 4, R, T, T, Lin, Lout, p_pitch, K, stride, pad_l,
+         period, pool, stream_ptr())
     return dsrc
 
 

@@ -15,7 +15,7 @@ def _bf16(t):
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=0, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
               out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2,
-              fm_d=None):
+              fm_d=None, fm_partner=None):
     B, in_pitch, Cin = xa_cl.shape
     Lin = in_pitch if Lin is None else Lin
     K, Cout, _ = wt.shape
@@ -46,7 +46,12 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     if dact_src is not None:
         sgn = torch.signbit(dact_src[:, idx].float())
         v = torch.where(sgn, v * slope, v)
-    if fm_d is not None:
+    if fm_d is not None and fm_partner is not None:      # fake half only: partner = the real rows
+        a = dact_src[:, idx].float()
+        ar = fm_partner[:, idx].float()
+        hf, hr = torch.where(a > 0, a, a / slope), torch.where(ar > 0, ar, ar / slope)
+        v = v - fm_d[0] * torch.sign(hr - hf)
+    elif fm_d is not None:
         a = dact_src[:, idx].float()
         h = torch.where(a > 0, a, a / slope)
         hr, hf = h[:B // 2], h[B // 2:]
@@ -214,7 +219,10 @@ def im2col_c1(src, Lin, Lout, out_pitch, K, stride, pad_l, period=1, pool=1):
     return _bf16(X)
 
 
-def gather_c1(P_cl, src_shape, Lin, Lout, K, stride, pad_l, period=1, pool=1):
+def gather_c1(P_cl, src_shape, Lin, Lout, K, stride, pad_l, period=1, pool=1, batch0=0):
+    if batch0:
+        part = gather_c1(P_cl, (src_shape[0] - batch0, src_shape[1]), Lin, Lout, K, stride, pad_l, period, pool)
+        return torch.cat([torch.zeros(batch0, src_shape[1]), part], 0)
     R = P_cl.shape[0]
     Bs, T = src_shape
     dx = torch.zeros(R, Lin)

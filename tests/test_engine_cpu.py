@@ -159,9 +159,21 @@ def test_fused_feature_matching_vs_oracle(emu):
     t = tol(emu, 2e-5, 3e-2)
     assert rel_l2(fm, fm_o) < t and rel_l2(ld, ld_o) < t and rel_l2(la, la_o) < t
     names = sorted(po)
-    g_o = torch.autograd.grad(20 * fm_o + ld_o + la_o, [xo] + [po[k] for k in names])
+    g_o = torch.autograd.grad(20 * fm_o + ld_o + la_o, [xo] + [po[k] for k in names], retain_graph=True)
     pp = dict(disc.named_parameters(prefix="discriminator"))
     g_e = torch.autograd.grad(20 * fm + ld + la, [xe] + [pp[k] for k in names])
     assert rel_l2(g_e[0], g_o[0]) < tol(emu, 5e-5, 0.25)
     for k, a, b in zip(names, g_e[1:], g_o[1:]):
         assert a.shape == b.shape and rel_l2(a, b) < tol(emu, 1e-4, 0.3), (k, rel_l2(a, b))
+    # generator step: frozen discriminator, only the FAKE half's input gradient is wanted -> the backward runs on
+    # that half alone; it must reproduce the oracle's gradient there (and leave the real half at zero)
+    for p_ in disc.parameters():
+        p_.requires_grad_(False)
+    xf = x.clone().requires_grad_(True)
+    fm2, ld2, la2, _, _ = RAVE._fused_feature_matching(h, xf, fake_grad_only=True)
+    assert rel_l2(fm2, fm_o) < t and rel_l2(la2, la_o) < t
+    (gf,) = torch.autograd.grad(20 * fm2 + la2, xf)
+    (go,) = torch.autograd.grad(20 * fm_o + la_o, xo)
+    half = x.shape[0] // 2
+    assert float(gf[:half].abs().max()) == 0.0
+    assert rel_l2(gf[half:], go[half:]) < tol(emu, 5e-5, 0.25)
