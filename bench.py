@@ -57,7 +57,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md): NVML, else nvidia-smi."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
@@ -67,7 +67,29 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
         self._stop_evt = threading.Event()
 
+    def _run_nvml(self):
+        """NVML samples every ~5 ms (a timed region of 8 steps is ~100 ms: nvidia-smi is too slow for that)."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self._stop_evt.is_set():
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for b, n in bits.items():
+                if r & b:
+                    self.reasons.add(n)
+            self._stop_evt.wait(0.005)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -235,8 +257,11 @@ def tc_kernel_roofline(torch, pk):
         ach, peak, unit = byts / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
     else:
         ach, peak, unit = flops / (ms * 1e-3) / 1e12, pk["bf16_tflops"], "TFLOP/s"
-    return dict(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
-                kernel="conv_tc_kernel<256,64> (MSD conv 384->768 k15 s4, B=64, Lin=1024)",
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
+    # (profiles/r1_ncu_conv_tc2_msd384_768.md): 64.7 MB + 35.0 MB, below the algorithmic bytes (outputs partly in L2)
+    return dict(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=99.7e6,
+                traffic_source="profiles/r1_ncu_conv_tc2_msd384_768.md (ncu --set full, one launch)",
+                kernel="conv_tc2_kernel<256,64> (MSD conv 384->768 k15 s4, B=64, Lin=1024)",
                 ms_per_launch=ms, algorithmic_bytes=byts, algorithmic_flops=flops,
                 peak_source=pk["source"] + " burst (cuBLAS bf16)")
 
