@@ -75,6 +75,10 @@ class MultiScaleSTFT(nn.Module):
         self.normalized = normalized
         for s in scales:
             self.register_buffer(f"window_{s}", torch.hann_window(s), persistent=False)
+            bw = torch.full((s // 2 + 1,), 0.5 * s)       # rfft backward as one c2r transform (ops.RfftFn)
+            bw[0] = s
+            bw[-1] = s
+            self.register_buffer(f"rfft_bw_{s}", bw, persistent=False)
 
     def complex_stfts(self, x):
         x = x.reshape(-1, x.shape[-1])
@@ -83,8 +87,8 @@ class MultiScaleSTFT(nn.Module):
             # the transform; like torch.stft the result is a [N, bins, frames] view of a [N, frames, bins] buffer
             from . import ops
             if all(x.shape[-1] > s // 2 for s in self.scales):
-                return [torch.fft.rfft(ops.stft_frames(x, getattr(self, f"window_{s}"), s, s // 4)).transpose(-1, -2)
-                        for s in self.scales]
+                return [ops.rfft(ops.stft_frames(x, getattr(self, f"window_{s}"), s, s // 4),
+                                 getattr(self, f"rfft_bw_{s}")).transpose(-1, -2) for s in self.scales]
         return [torch.stft(x, s, hop_length=s // 4, win_length=s, window=getattr(self, f"window_{s}"),
                            center=True, pad_mode="reflect", normalized=self.normalized, onesided=True,
                            return_complex=True) for s in self.scales]
