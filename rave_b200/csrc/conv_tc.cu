@@ -1152,6 +1152,9 @@ static void wg_geometry(int B, int Cm, int Lp, int Cn, int K, int *BL, int *n_lt
   const int n_chunks = (*n_lt) * (*n_bg);
   int s = ceil_div(2 * 148, tiles);
   if (s > 32) s = 32;      // every slice writes a full partial tile that the weight-norm backward re-reads
+  // ... and a slice of only a few 64-row chunks is all prologue + partial-tile write (the encoder / decoder blocks:
+  // 2.4 GFLOP in 40 us): at least 8 chunks per slice
+  if (s > n_chunks / 8) s = n_chunks / 8;
   if (s > n_chunks) s = n_chunks;
   if (s < 1) s = 1;
   *splits = s;
