@@ -234,6 +234,11 @@ int rave_stft_frames(const float *x, const float *window, float *frames, int N, 
                      void *stream);
 int rave_stft_frames_bwd(const float *dframes, const float *window, float *dx, int N, int T, int n_fft, int hop,
                          void *stream);
+/* gradient of rfft (last axis, n = 2*(bins-1)) prepared for ONE c2r transform: Z[k] = G[k]*n*(1 | 1/2 | ... | 1/2 | 1)
+ * with the imaginary parts of the DC / Nyquist bins dropped; dx = irfft(Z, n).  G [N][F][bins] complex64 with element
+ * strides (sN, sF, sB); Z contiguous. */
+int rave_rfft_bwd_scale(const void *G_c64, void *Z_c64, long N, int F, int bins, long sN, long sF, long sB,
+                        void *stream);
 
 /* fused weight preparation for the engine: v [C0][C1][K] fp32 (+ weight-norm g [C0]; norm [C0] is written)
  *   outA[t][c0][c1] = bf16(w[c0][c1][tapsA[t]]), dims [nA][C0p][C1p]  (padded region zero)

@@ -139,7 +139,38 @@ stft_frames_bwd_kernel(const float *__restrict__ dframes, const float *__restric
   }
 }
 
+// Gradient of y = rfft(x) (last axis, length n) as the input of ONE c2r transform: Z[k] = G[k] * n * (k == 0 || k == n/2
+// ? 1 : 1/2), imaginary parts of the DC and Nyquist bins dropped (cuFFT's C2R result is unspecified for a non-Hermitian
+// input; those parts carry no gradient).  dx = irfft(Z, n).  G: [N][F][bins] complex64 with arbitrary strides.
+__global__ void __launch_bounds__(256)
+rfft_bwd_scale_kernel(const float2 *__restrict__ G, float2 *__restrict__ Z, long total, int F, int bins, long sN, long sF,
+                      long sB, float n) {
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int k = (int)(i % bins);
+    const long nf = i / bins;
+    const int f = (int)(nf % F);
+    const long b = nf / F;
+    const float2 g = G[b * sN + f * sF + k * sB];
+    const bool edge = (k == 0) || (k == bins - 1);
+    const float sc = edge ? n : 0.5f * n;
+    Z[i] = make_float2(g.x * sc, edge ? 0.f : g.y * sc);
+  }
+}
+
 }  // namespace rave
+
+extern "C" int rave_rfft_bwd_scale(const void *G_c64, void *Z_c64, long N, int F, int bins, long sN, long sF, long sB,
+                                   void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(G_c64 && Z_c64 && N > 0 && F > 0 && bins > 1, "rfft_bwd_scale: bad argument");
+  const long total = N * F * bins;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  rfft_bwd_scale_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)G_c64, (float2 *)Z_c64, total, F,
+                                                                       bins, sN, sF, sB, (float)(2 * (bins - 1)));
+  RAVE_CHECK_LAUNCH("rfft_bwd_scale");
+  return 0;
+}
 
 extern "C" int rave_stft_frames(const float *x, const float *window, float *frames, int N, int T, int n_fft, int hop,
                                 void *stream) {

@@ -662,10 +662,11 @@ def stft_frames(x, window, n_fft, hop):
 
 
 class RfftFn(torch.autograd.Function):
-    """torch.fft.rfft on the last axis with the backward written as ONE c2r transform: for y = rfft(x) and a gradient G
-    of y, dx = irfft(G * w, n) with w = n * (1, 1/2, ..., 1/2, 1) (checked against autograd in float64).  PyTorch's own
-    backward zero-pads G to full length, runs a complex-to-complex transform of twice the size and copies the real part
-    (4-5 launches on 33 MB tensors per STFT scale)."""
+    """torch.fft.rfft on the last axis of a [N, F, n] tensor with the backward written as ONE c2r transform: for
+    y = rfft(x) and a gradient G of y, dx = irfft(Z, n) with Z = G * n * (1, 1/2, ..., 1/2, 1) and the imaginary parts of
+    the DC / Nyquist bins dropped (checked against autograd in float64).  PyTorch's own backward zero-pads G to full
+    length, runs a complex-to-complex transform of twice the size and copies the real part (4-5 launches on 33 MB
+    tensors per STFT scale)."""
 
     @staticmethod
     def forward(ctx, x, w):
@@ -676,7 +677,18 @@ class RfftFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (w,) = ctx.saved_tensors
-        return torch.fft.irfft(g * w, n=ctx.n), None
+        if g.is_cuda and g.dim() == 3 and g.dtype == torch.complex64:
+            g = g.resolve_conj()
+            N, F, bins = g.shape
+            z = torch.empty(N, F, bins, dtype=torch.complex64, device=g.device)
+            sN, sF, sB = g.stride()
+            call("rave_rfft_bwd_scale", torch.view_as_real(g).data_ptr(), ptr(torch.view_as_real(z)), N, F, bins, sN,
+                 sF, sB, stream_ptr())
+        else:
+            z = g * w
+            z = torch.complex(z.real, torch.cat([torch.zeros_like(z.imag[..., :1]), z.imag[..., 1:-1],
+                                                 torch.zeros_like(z.imag[..., :1])], -1))
+        return torch.fft.irfft(z, n=ctx.n), None
 
 
 def rfft_weights(n, device):
