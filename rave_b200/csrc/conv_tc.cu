@@ -1150,7 +1150,7 @@ static void wg_geometry(int B, int Cm, int Lp, int Cn, int K, int *BL, int *n_lt
   *n_nt = ceil_div(Cn, *BN);
   const int tiles = K * (*n_mt) * (*n_nt);
   const int n_chunks = (*n_lt) * (*n_bg);
-  int s = ceil_div(2 * 148, tiles);
+  int s = ceil_div(tiles >= 74 ? 148 : 2 * 148, tiles);     // many tiles already: one wave-and-a-bit is enough
   if (s > 32) s = 32;      // every slice writes a full partial tile that the weight-norm backward re-reads
   // ... and a slice of only a few 64-row chunks is all prologue + partial-tile write (the encoder / decoder blocks:
   // 2.4 GFLOP in 40 us): at least 8 chunks per slice

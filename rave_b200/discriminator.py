@@ -10,6 +10,8 @@ copy is the 1-channel input.
 from typing import Callable, Optional, Sequence, Type
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -177,9 +179,12 @@ class MultiScaleDiscriminator(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList([convnet(in_size=n_channels) for _ in range(n_discriminators)])
 
-    def forward_fm(self, x, fake_grad_only: bool = False):
+    def fm_jobs(self):
         # scale i sees avg_pool1d(., 2) applied i times = the mean over 2^i consecutive samples (floor lengths agree)
-        return [layer.forward_fm(x, pool=2 ** i, fake_grad_only=fake_grad_only) for i, layer in enumerate(self.layers)]
+        return [(layer, {"pool": 2 ** i}) for i, layer in enumerate(self.layers)]
+
+    def forward_fm(self, x, fake_grad_only: bool = False):
+        return [layer.forward_fm(x, fake_grad_only=fake_grad_only, **kw) for layer, kw in self.fm_jobs()]
 
     def forward(self, x):
         features = []
@@ -203,9 +208,11 @@ class MultiPeriodDiscriminator(nn.Module):
             features.append(layer(self.fold(x, n)))
         return features
 
+    def fm_jobs(self):
+        return [(layer, {"period": n}) for layer, n in zip(self.layers, self.periods)]
+
     def forward_fm(self, x, fake_grad_only: bool = False):
-        return [layer.forward_fm(x, period=n, fake_grad_only=fake_grad_only)
-                for layer, n in zip(self.layers, self.periods)]
+        return [layer.forward_fm(x, fake_grad_only=fake_grad_only, **kw) for layer, kw in self.fm_jobs()]
 
     def fold(self, x, n):
         pad = (n - (x.shape[-1] % n)) % n
@@ -245,7 +252,29 @@ class CombineDiscriminators(nn.Module):
     def forward_fm(self, x, fake_grad_only: bool = False):
         """fake_grad_only: the caller will only use the gradient with respect to the FAKE half of x (generator step,
         frozen discriminator): the backward then runs on that half alone (engine.TcChainFn.backward)."""
-        out = []
+        jobs = []
         for disc in self.discriminators:
-            out.extend(disc.forward_fm(x, fake_grad_only=fake_grad_only))
+            jobs.extend(disc.fm_jobs())
+        ns = int(os.environ.get("RAVE_DISC_STREAMS", "1"))
+        if ns <= 1 or not x.is_cuda:
+            return [layer.forward_fm(x, fake_grad_only=fake_grad_only, **kw) for layer, kw in jobs]
+        # The nets are independent chains of persistent kernels: issued on a few streams, the tail of one kernel (CTAs
+        # finishing at different times) and the prologue of the next overlap with another net's work instead of leaving
+        # SMs idle; autograd replays every chain's backward on the stream its forward ran on.
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_fm_streams", None) is None or len(self._fm_streams) != ns:
+            self._fm_streams = [torch.cuda.Stream() for _ in range(ns)]
+        out = [None] * len(jobs)
+        for j, (layer, kw) in enumerate(jobs):
+            st = self._fm_streams[j % ns]
+            st.wait_stream(cur)
+            x.record_stream(st)
+            with torch.cuda.stream(st):
+                out[j] = layer.forward_fm(x, fake_grad_only=fake_grad_only, **kw)
+        for st in self._fm_streams:
+            cur.wait_stream(st)
+        for res in out:
+            for t in res:
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
         return out

@@ -545,8 +545,21 @@ class TcChainFn(torch.autograd.Function):
                 if i in db_off:
                     db = db_all[db_off[i]:db_off[i] + cout_p]
                 if use_c1:
-                    d = ops.conv1d_tc_wgrad(g, ctx.c1_X, 1, 1, 1, 0, Lp=Lout, Lq=Lout, dbias=db)  # [S][1][Cout_p][16]
-                    dw_ck = d.sum(0)[0][:s.Cout, :s.K]                                         # [Cout][K]
+                    G = ctx.c1_group
+                    X = ctx.c1_X
+                    if G > 1 and g.shape[1] % G == 0 and X.shape[1] % G == 0:
+                        # same G-positions-per-row view as the forward: 64-channel rows for the TMA loads; the wanted
+                        # [Cout][16] gradient is the sum of the G diagonal blocks of the [G*Cout][G*16] result
+                        dbw = torch.zeros(G * cout_p, dtype=torch.float32, device=g.device) if db is not None else None
+                        d = ops.conv1d_tc_wgrad(g.view(B, g.shape[1] // G, G * cout_p), X.view(B, X.shape[1] // G, G * 16),
+                                                1, 1, 1, 0, Lp=(Lout + G - 1) // G, Lq=(Lout + G - 1) // G, dbias=dbw)
+                        blk = d.sum(0)[0].view(G, cout_p, G, 16)
+                        dw_full = torch.diagonal(blk, dim1=0, dim2=2).sum(-1)                  # [Cout_p][16]
+                        if db is not None:
+                            db.copy_(dbw.view(G, cout_p).sum(0))
+                    else:
+                        dw_full = ops.conv1d_tc_wgrad(g, X, 1, 1, 1, 0, Lp=Lout, Lq=Lout, dbias=db).sum(0)[0]
+                    dw_ck = dw_full[:s.Cout, :s.K]                                             # [Cout][K]
                     dwt = dw_ck.t().reshape(1, s.K, s.Cout, 1).contiguous()                    # [1][K][C0][C1=1]
                 else:
                     P_op, Q_op = (g, a_in) if s.kind == "conv" else (a_in, g)
