@@ -1,0 +1,7 @@
+#!/bin/bash
+# In-situ profiles of the graphed step (CUPTI timeline), per-launch roofline table, roofline-by-ablation of the conv kernel.
+# Usage: gpurun --timeout 1500 -- 'bash scripts/gpu_profile.sh'; copy what matters from gpurun_out/ to profiles/.
+mkdir -p gpurun_out
+echo "== trace"; timeout 600 python scripts/trace_step.py > gpurun_out/trace_step.txt 2> gpurun_out/trace_step.err; echo "exit $?"; grep "====" gpurun_out/trace_step.txt
+echo "== layers"; timeout 600 python scripts/profile_layers.py > gpurun_out/layers.txt 2> gpurun_out/layers.err; echo "exit $?"; head -4 gpurun_out/layers.txt | cut -c1-200
+echo "== ablate"; timeout 600 python scripts/ablate_tc.py > gpurun_out/ablate.log 2>&1; echo "exit $?"; grep -E "^==|default" gpurun_out/ablate.log | cut -c1-100
