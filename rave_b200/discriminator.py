@@ -255,7 +255,7 @@ class CombineDiscriminators(nn.Module):
         jobs = []
         for disc in self.discriminators:
             jobs.extend(disc.fm_jobs())
-        ns = int(os.environ.get("RAVE_DISC_STREAMS", "1"))
+        ns = int(os.environ.get("RAVE_DISC_STREAMS", "8"))
         if ns <= 1 or not x.is_cuda:
             return [layer.forward_fm(x, fake_grad_only=fake_grad_only, **kw) for layer, kw in jobs]
         # The nets are independent chains of persistent kernels: issued on a few streams, the tail of one kernel (CTAs

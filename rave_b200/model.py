@@ -11,6 +11,9 @@ adding the (possibly zero) KL term unconditionally: same value, no sync.
 import math
 from typing import Callable, Dict, Iterable, Optional
 
+import contextlib
+import os
+
 import torch
 import torch.nn as nn
 
@@ -276,11 +279,24 @@ class RAVE(nn.Module):
                     x_multiband = x_multiband[..., :-right_rf // dim]
                     y_multiband = y_multiband[..., :-right_rf // dim]
 
+        # The spectral losses (20 STFTs + their small kernels) and the discriminator chains only share their inputs:
+        # the former go to a side stream so that they fill the holes between the discriminator's persistent kernels
+        # (autograd replays each part's backward on its own stream).
+        side = None
+        if y_raw.is_cuda and self.warmed_up and int(os.environ.get("RAVE_DISC_STREAMS", "8")) > 1:
+            if getattr(self, "_loss_stream", None) is None:
+                self._loss_stream = torch.cuda.Stream()
+            side = self._loss_stream
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
+            for t in (x_multiband, y_multiband, x_raw, y_raw):
+                t.record_stream(side)
         distances = {}
-        for k, v in self.multiband_audio_distance(x_multiband, y_multiband).items():
-            distances[f"multiband_{k}"] = self.weights["multiband_audio_distance"] * v
-        for k, v in self.audio_distance(x_raw, y_raw).items():
-            distances[f"fullband_{k}"] = self.weights["audio_distance"] * v
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            for k, v in self.multiband_audio_distance(x_multiband, y_multiband).items():
+                distances[f"multiband_{k}"] = self.weights["multiband_audio_distance"] * v
+            for k, v in self.audio_distance(x_raw, y_raw).items():
+                distances[f"fullband_{k}"] = self.weights["audio_distance"] * v
 
         feature_matching_distance = 0.
         fused = None
@@ -314,6 +330,10 @@ class RAVE(nn.Module):
             loss_dis = torch.tensor(0.).to(x_raw)
             loss_adv = torch.tensor(0.).to(x_raw)
 
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            for v in distances.values():
+                v.record_stream(torch.cuda.current_stream())
         loss_gen = {}
         loss_gen.update(distances)
         loss_gen["regularization"] = reg * self.beta_factor

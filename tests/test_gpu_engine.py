@@ -139,9 +139,12 @@ def test_fused_feature_matching_bf16_vs_oracle():
     assert rel_l2(fm, fm_o) < FWD_TOL and rel_l2(ld, ld_o) < FWD_TOL and rel_l2(la, la_o) < 5e-2
 
 
-def test_cuda_graph_training_matches_eager():
-    """GraphedTrainer replays == eager training_step on the same data (same kernels, same order)."""
+@pytest.mark.parametrize("streams", ["1", "8"])
+def test_cuda_graph_training_matches_eager(streams, monkeypatch):
+    """GraphedTrainer replays == eager training_step on the same data (same kernels, same order); with the
+    discriminator nets captured on 8 side streams against a single-stream eager twin."""
     import copy
+    monkeypatch.setenv("RAVE_DISC_STREAMS", streams)
     from rave_b200 import configs
     from rave_b200.graphs import GraphedTrainer
     torch.manual_seed(0)
@@ -155,6 +158,7 @@ def test_cuda_graph_training_matches_eager():
     tr = GraphedTrainer(m2, x, warmup_steps=2)
     # eager twin performs the same updates as the trainer's warm-up: 2 rounds of (D, G); capture itself
     # executes nothing
+    monkeypatch.setenv("RAVE_DISC_STREAMS", "1")
     m1.optimizers(capturable=True)
     for _ in range(2):
         m1.train_body(x, True)
