@@ -21,8 +21,6 @@ each a stride-1 conv over the taps of that phase (no zero-insertion, no wasted M
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
-import os
-
 import torch
 import torch.nn as nn
 
@@ -514,15 +512,6 @@ class TcChainFn(torch.autograd.Function):
         grads = [None] * len(flat)
         gx = None
         wn_jobs = []       # (layer, dwt partials, v, g, norm): one multi-tensor launch at the end
-        # The weight gradients hang off the dgrad chain like leaves (wgrad_i needs g_i, nothing needs wgrad_i until the
-        # weight-norm backward at the end): they go to a side stream, so the prologue / tail / partial-tile writes of
-        # these mostly small launches overlap with the dgrad kernels instead of sitting between them.
-        main = wside = None
-        any_w = any(t is not None and t.requires_grad for t in flat)
-        if any_w and ctx.acts[-1].is_cuda and int(os.environ.get("RAVE_WGRAD_STREAM", "1")):
-            main = torch.cuda.current_stream()
-            wside = _wgrad_stream(main)
-            wside.wait_stream(main)
         # bias gradients accumulated by the wgrad kernels: ONE zero-filled buffer for the whole chain
         db_off, db_total = {}, 0
         for i, s in enumerate(specs):
@@ -552,13 +541,6 @@ class TcChainFn(torch.autograd.Function):
             want_db = bias is not None and bias.requires_grad
             db = None
             remap = None
-            on_side = v.requires_grad and wside is not None
-            if on_side:
-                wside.wait_stream(main)               # g (and the operand) were produced on the main stream
-                for t in (g, a_in):
-                    if torch.is_tensor(t):
-                        t.record_stream(wside)
-                torch.cuda.set_stream(wside)
             if v.requires_grad:
                 if i in db_off:
                     db = db_all[db_off[i]:db_off[i] + cout_p]
@@ -596,8 +578,6 @@ class TcChainFn(torch.autograd.Function):
                                                   Lp=Lp_, Lq=Lq_, dbias=db)
                 # dwt is [S][K][C0p][C1p] (or the phase-wide form + remap) in the parameter's own (C0, C1) order
                 wn_jobs.append((i, dwt, v, gpar, pw.norm, remap))
-            if on_side:
-                torch.cuda.set_stream(main)
             if want_db:
                 grads[3 * i + 2] = db[:s.Cout] if db is not None else ops.colsum_bf16(g, Lout, s.Cout)
             # ---- input gradient
@@ -672,29 +652,12 @@ class TcChainFn(torch.autograd.Function):
             g_cur = gp
             if i == 0:
                 gx = gp
-        if wside is not None:
-            main.wait_stream(wside)
-            for job in wn_jobs:
-                job[1].record_stream(main)
         if wn_jobs:
             res = ops.weight_norm_bwd_multi([job[1:] for job in wn_jobs])
             for job, (dv, dg) in zip(wn_jobs, res):
                 i = job[0]
                 grads[3 * i], grads[3 * i + 1] = dv, dg
         return (gx, None, None, None, None, None) + tuple(grads)
-
-
-_WGRAD_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
-
-
-def _wgrad_stream(main) -> "torch.cuda.Stream":
-    """One side stream per (device, main stream): concurrent chains (discriminator nets on their own streams) must not
-    funnel their weight gradients through a shared one."""
-    key = (main.device_index, main.cuda_stream)
-    st = _WGRAD_STREAMS.get(key)
-    if st is None:
-        st = _WGRAD_STREAMS[key] = torch.cuda.Stream(device=main.device)
-    return st
 
 
 def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None, fm: bool = False,
