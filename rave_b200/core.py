@@ -105,26 +105,15 @@ class AudioDistanceV1(nn.Module):
         self.multiscale_stft = multiscale_stft()
         self.log_epsilon = log_epsilon
 
-    def fused_path(self, x) -> bool:
+    def forward(self, x, y):
         mstft = self.multiscale_stft
-        return (x.is_cuda and not x.requires_grad and isinstance(mstft, MultiScaleSTFT) and mstft.magnitude
-                and x.dtype == torch.float32)
-
-    def target_stfts(self, x):
-        """Complex STFTs of the target signal for the fused path: they do not depend on the reconstruction, so the
-        training step computes them early (side stream, under the encoder / generator forward) and hands them back
-        through `forward(..., target=...)`."""
-        with torch.no_grad():
-            return self.multiscale_stft.complex_stfts(x)
-
-    def forward(self, x, y, target=None):
-        mstft = self.multiscale_stft
-        if self.fused_path(x):
+        if (x.is_cuda and not x.requires_grad and isinstance(mstft, MultiScaleSTFT) and mstft.magnitude
+                and x.dtype == torch.float32):
             # fused path: one kernel per scale for the whole |.|, log, L2-relative + L1 tail (and one for its
             # gradient) instead of ~40 ATen launches; cuFFT still does the transforms
             from . import ops
             distance = 0.
-            for sx, sy in zip(target if target is not None else mstft.complex_stfts(x), mstft.complex_stfts(y)):
+            for sx, sy in zip(mstft.complex_stfts(x), mstft.complex_stfts(y)):
                 distance = distance + ops.spectral_distance(sx, sy, self.log_epsilon)
             return {"spectral_distance": distance}
         stfts_x = self.multiscale_stft(x)

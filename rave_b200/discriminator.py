@@ -249,40 +249,12 @@ class CombineDiscriminators(nn.Module):
                     return False
         return True
 
-    def _fm_jobs(self):
-        jobs = []
-        for disc in self.discriminators:
-            jobs.extend(disc.fm_jobs())
-        return jobs
-
-    def _streams(self, ns):
-        if getattr(self, "_fm_streams", None) is None or len(self._fm_streams) != ns:
-            self._fm_streams = [torch.cuda.Stream() for _ in range(ns)]
-        return self._fm_streams
-
-    def prefetch_weights(self) -> None:
-        """Prepare every net's weights (weight norm, tap-major bf16 layouts) NOW, each on the stream its chain will run
-        on: they do not depend on the generator output, so this work hides under the encoder / generator forward.
-        Needs an open engine step cache (engine.begin_step); no-op in single-stream mode."""
-        from . import engine
-        ns = int(os.environ.get("RAVE_DISC_STREAMS", "8"))
-        if ns <= 1 or not next(self.parameters()).is_cuda or engine.precision() != "bf16":
-            return
-        cur = torch.cuda.current_stream()
-        streams = self._streams(ns)
-        for j, (layer, _) in enumerate(self._fm_jobs()):
-            specs = layer._tc_specs()
-            if specs is None:
-                return
-            st = streams[j % ns]
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                engine.prefetch_chain_weights(specs, c1=specs[0].Cin == 1 and specs[0].dil == 1)
-
     def forward_fm(self, x, fake_grad_only: bool = False):
         """fake_grad_only: the caller will only use the gradient with respect to the FAKE half of x (generator step,
         frozen discriminator): the backward then runs on that half alone (engine.TcChainFn.backward)."""
-        jobs = self._fm_jobs()
+        jobs = []
+        for disc in self.discriminators:
+            jobs.extend(disc.fm_jobs())
         ns = int(os.environ.get("RAVE_DISC_STREAMS", "8"))
         if ns <= 1 or not x.is_cuda:
             return [layer.forward_fm(x, fake_grad_only=fake_grad_only, **kw) for layer, kw in jobs]
@@ -290,7 +262,8 @@ class CombineDiscriminators(nn.Module):
         # finishing at different times) and the prologue of the next overlap with another net's work instead of leaving
         # SMs idle; autograd replays every chain's backward on the stream its forward ran on.
         cur = torch.cuda.current_stream()
-        self._streams(ns)
+        if getattr(self, "_fm_streams", None) is None or len(self._fm_streams) != ns:
+            self._fm_streams = [torch.cuda.Stream() for _ in range(ns)]
         out = [None] * len(jobs)
         for j, (layer, kw) in enumerate(jobs):
             st = self._fm_streams[j % ns]

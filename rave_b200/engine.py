@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 
-_state = {"precision": "fp32", "prep_epoch": 0, "step_cache": None}
+_state = {"precision": "fp32", "prep_epoch": 0}
 ACT_DTYPE = torch.bfloat16   # storage type of operand / gradient streams (tests may widen it)
 
 
@@ -45,18 +45,6 @@ def set_precision(mode: str) -> None:
 
 def precision() -> str:
     return _state["precision"]
-
-
-def begin_step() -> None:
-    """Open a per-step cache of prepared weights: within ONE training step (eager or being captured into a CUDA graph)
-    the parameters do not change between the early `prefetch` of a chain's weights and their use, so what was
-    prepared early -- on a side stream, under the low-occupancy encoder / generator forward -- is picked up by the
-    chain.  `end_step` closes it (the optimiser is about to change the parameters)."""
-    _state["step_cache"] = {}
-
-
-def end_step() -> None:
-    _state["step_cache"] = None
 
 
 def invalidate_prepared() -> None:
@@ -302,13 +290,7 @@ def prepare_layers(jobs):
     preparing all misses with one multi-tensor launch pair."""
     out = [None] * len(jobs)
     todo = []
-    sc = _state.get("step_cache")
     for i, (spec, v, g, need_dgrad, need_fwd) in enumerate(jobs):
-        if sc is not None:
-            hit = sc.get((id(spec.module), need_dgrad, need_fwd))
-            if hit is not None:
-                out[i] = hit
-                continue
         capturing = v.is_cuda and torch.cuda.is_current_stream_capturing()
         key = (v._version, g._version if g is not None else -1, need_dgrad, need_fwd, str(ACT_DTYPE), str(v.device),
                v.data_ptr(), _state["prep_epoch"])
@@ -329,54 +311,6 @@ def prepare_layers(jobs):
         if out[i] is None:            # nothing to re-layout (a c1 layer without dgrad): only the norm
             pw.norm = ops.weight_norm_raw(v, g)[1] if g is not None else None
             out[i] = pw
-    if sc is not None:
-        for i, (spec, v, g, need_dgrad, need_fwd) in enumerate(jobs):
-            sc[(id(spec.module), need_dgrad, need_fwd)] = out[i]
-    return out
-
-
-def prefetch_chain_weights(specs: List[LayerSpec], c1: bool) -> None:
-    """Prepare a chain's weights now (into the step cache, on the current stream) exactly as TcChainFn.forward will ask
-    for them during training (dgrad layouts included).  No-op without an open step cache."""
-    if _state.get("step_cache") is None:
-        return
-    jobs = []
-    for i, s in enumerate(specs):
-        v, g, _ = _layer_params(s)
-        first_c1 = c1 and i == 0
-        jobs.append((s, v.detach(), g.detach() if g is not None else None, not first_c1, not first_c1))
-    prepare_layers(jobs)
-    if c1:
-        _c1_weights(specs[0], *_layer_params(specs[0]))
-
-
-def _c1_weights(spec: LayerSpec, v, g, bias):
-    """Effective weight of a Cin = 1 first layer in the forms its tensor-core path needs: the block-diagonal
-    kron(I_G, w) [G*Cout_p][G*16] (bf16, forward), its transpose (dgrad) and the bias repeated G times."""
-    sc = _state.get("step_cache")
-    key = (id(spec.module), "c1")
-    if sc is not None and key in sc:
-        return sc[key]
-    cout_p = spec.Cout + spec.cout_pad
-    G = C1_GROUP
-    w_eff = ops.weight_norm_raw(v.detach(), g.detach())[0] if g is not None else v.detach()
-    w_ck = nn.functional.pad(w_eff.reshape(spec.Cout, spec.K), (0, 16 - spec.K, 0, spec.cout_pad))   # [Cout_p, 16]
-    if G > 1:
-        eye = torch.eye(G, dtype=w_ck.dtype, device=w_ck.device)
-        w_blk = (eye[:, None, :, None] * w_ck[None, :, None, :]).reshape(G * cout_p, G * 16)
-    else:
-        w_blk = w_ck
-    bias_p = bias
-    if bias is not None and spec.cout_pad:
-        bias_p = nn.functional.pad(bias.detach(), (0, spec.cout_pad))
-    out = dict(G=G, w_ck=w_ck,
-               fwd=w_blk.to(ACT_DTYPE).unsqueeze(0).contiguous(),                  # [1][G*Cout_p][G*16]
-               dgrad=w_blk.t().contiguous().to(ACT_DTYPE).unsqueeze(0),            # [1][G*16][G*Cout_p]
-               bias_g=(bias_p.detach().repeat(G) if (bias_p is not None and G > 1) else bias_p),
-               fwd1=w_ck.to(ACT_DTYPE).unsqueeze(0).contiguous(),
-               dgrad1=w_ck.t().contiguous().to(ACT_DTYPE).unsqueeze(0))
-    if sc is not None:
-        sc[key] = out
     return out
 
 
@@ -468,16 +402,22 @@ class TcChainFn(torch.autograd.Function):
                 # positions are then read as ONE 64-channel row (X viewed as [R][L/4][64], 128-byte TMA rows
                 # instead of 32-byte ones) against the block-diagonal weight kron(I4, w): the output row holds
                 # the 4 x Cout results of those positions, i.e. the same bytes as out[r][4*l4 + p][co].
-                cw = _c1_weights(s, v, g, bias)
-                G = cw["G"] if (pitch % cw["G"] == 0) else 1
+                w_eff = ops.weight_norm_raw(v.detach(), g.detach())[0] if g is not None else v.detach()
+                w_ck = nn.functional.pad(w_eff.reshape(s.Cout, s.K), (0, 16 - s.K, 0, s.cout_pad))   # [Cout_p, 16]
+                G = C1_GROUP if (pitch % C1_GROUP == 0) else 1
                 Xp = (Lout + G - 1) // G * G
                 X = ops.im2col_c1(a, Lin, Lout, Xp, s.K, s.stride, s.pad[0], period, pool)
                 ctx.c1_X = X
                 ctx.c1_group = G
-                ctx.c1_wt_dgrad = cw["dgrad"] if G > 1 else cw["dgrad1"]
-                ops.conv1d_tc(X.view(B, Xp // G, G * 16), cw["fwd"] if G > 1 else cw["fwd1"],
-                              cw["bias_g"] if G > 1 else bias_p, None, 1, 1, (0, 0), act_code, act_slope,
-                              want_f32=False, want_act=False,
+                if G > 1:
+                    eye = torch.eye(G, dtype=w_ck.dtype, device=dev)
+                    w_blk = (eye[:, None, :, None] * w_ck[None, :, None, :]).reshape(G * cout_p, G * 16)
+                else:
+                    w_blk = w_ck
+                ctx.c1_wt_dgrad = w_blk.t().contiguous().to(ACT_DTYPE).unsqueeze(0)       # [1][G*16][G*Cout_p]
+                bias_g = bias_p.detach().repeat(G) if (bias_p is not None and G > 1) else bias_p
+                ops.conv1d_tc(X.view(B, Xp // G, G * 16), w_blk.to(ACT_DTYPE).unsqueeze(0).contiguous(), bias_g,
+                              None, 1, 1, (0, 0), act_code, act_slope, want_f32=False, want_act=False,
                               out_f32=out_f32.view(B, pitch // G, G * cout_p) if out_f32 is not None else None,
                               out_act=out_act.view(B, pitch // G, G * cout_p) if out_act is not None else None,
                               Lout=Xp // G, Lin=Xp // G, out_rows=pitch // G)

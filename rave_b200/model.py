@@ -253,40 +253,7 @@ class RAVE(nn.Module):
         self.encoder.set_warmed_up(self.warmed_up)
         self.decoder.set_warmed_up(self.warmed_up)
 
-        # Work that does not depend on the reconstruction is issued FIRST, on side streams, so that it runs under the
-        # low-occupancy encoder / generator forward: the discriminators' weight preparation and the target's STFTs.
-        multi = (x_raw.is_cuda and self.warmed_up and int(os.environ.get("RAVE_DISC_STREAMS", "8")) > 1)
-        side = None
-        early = None
-        if multi:
-            from . import engine
-            if hasattr(self.discriminator, "prefetch_weights") and engine.precision() == "bf16":
-                self.discriminator.prefetch_weights()
-            if getattr(self, "_loss_stream", None) is None:
-                self._loss_stream = torch.cuda.Stream()
-            side = self._loss_stream
-
-        if self.input_mode == "pqmf":
-            x_multiband = _pqmf_encode(self.pqmf, x_raw)
-            crop = None
-            if self.valid_signal_crop:
-                left_rf, right_rf = self._receptive_field_host()
-                if left_rf + right_rf:
-                    dim = x_multiband.shape[1]
-                    crop = (left_rf // dim, (-right_rf // dim) if right_rf else None)
-            if (side is not None and isinstance(self.multiband_audio_distance, core.AudioDistanceV1)
-                    and isinstance(self.audio_distance, core.AudioDistanceV1)
-                    and self.audio_distance.fused_path(x_raw) and self.multiband_audio_distance.fused_path(x_multiband)):
-                cur = torch.cuda.current_stream()
-                side.wait_stream(cur)
-                x_multiband.record_stream(side)
-                x_raw.record_stream(side)
-                with torch.cuda.stream(side):
-                    xm = x_multiband if crop is None else x_multiband[..., crop[0]:crop[1]]
-                    early = (self.multiband_audio_distance.target_stfts(xm), self.audio_distance.target_stfts(x_raw))
-            z = self.encoder(x_multiband)
-        else:
-            z, x_multiband = self.encode(x_raw, return_mb=True)
+        z, x_multiband = self.encode(x_raw, return_mb=True)
         if eps is not None:
             z, reg = self.encoder.reparametrize(z, eps)[:2]
         else:
@@ -315,18 +282,20 @@ class RAVE(nn.Module):
         # The spectral losses (20 STFTs + their small kernels) and the discriminator chains only share their inputs:
         # the former go to a side stream so that they fill the holes between the discriminator's persistent kernels
         # (autograd replays each part's backward on its own stream).
-        if side is not None:
+        side = None
+        if y_raw.is_cuda and self.warmed_up and int(os.environ.get("RAVE_DISC_STREAMS", "8")) > 1:
+            if getattr(self, "_loss_stream", None) is None:
+                self._loss_stream = torch.cuda.Stream()
+            side = self._loss_stream
             cur = torch.cuda.current_stream()
             side.wait_stream(cur)
             for t in (x_multiband, y_multiband, x_raw, y_raw):
                 t.record_stream(side)
         distances = {}
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-            kw_mb = {"target": early[0]} if early is not None else {}
-            kw_fb = {"target": early[1]} if early is not None else {}
-            for k, v in self.multiband_audio_distance(x_multiband, y_multiband, **kw_mb).items():
+            for k, v in self.multiband_audio_distance(x_multiband, y_multiband).items():
                 distances[f"multiband_{k}"] = self.weights["multiband_audio_distance"] * v
-            for k, v in self.audio_distance(x_raw, y_raw, **kw_fb).items():
+            for k, v in self.audio_distance(x_raw, y_raw).items():
                 distances[f"fullband_{k}"] = self.weights["audio_distance"] * v
 
         feature_matching_distance = 0.
@@ -467,12 +436,7 @@ class RAVE(nn.Module):
         for p in dis_params:                       # G-step: no discriminator wgrad (discarded work)
             p.requires_grad_(is_dis)
 
-        from . import engine
-        engine.begin_step()          # weights prepared early in this step are picked up by the chains (engine.begin_step)
-        try:
-            loss_gen, loss_dis, aux = self.compute_losses(x_raw, is_dis, eps)
-        finally:
-            engine.end_step()
+        loss_gen, loss_dis, aux = self.compute_losses(x_raw, is_dis, eps)
 
         if is_dis:
             dis_opt.zero_grad(set_to_none=True)
