@@ -42,89 +42,12 @@ class GradientAllReducer:
             out.append(cur)
         return out
 
-    # ---------------------------------------------------------------------------------------------------
-    # early reduction: groups of parameters whose gradients become complete together (decoder, then encoder; each
-    # discriminator net) are reduced as soon as their last gradient has been accumulated, on a communication stream,
-    # while the rest of the backward keeps running.  `arm(groups)` before backward; the usual call after it reduces
-    # whatever is left and joins the stream.
-    # ---------------------------------------------------------------------------------------------------
-    def arm(self, groups: List[List[torch.nn.Parameter]]) -> None:
-        if self.world_size(self.group) == 1:
-            return
-        if not hasattr(self, "_hooked"):
-            self._hooked = set()
-            self._owner = {}
-        self._groups = [[p for p in g if p.requires_grad] for g in groups]
-        self._owner = {}
-        for gi, g in enumerate(self._groups):
-            for p in g:
-                self._owner[id(p)] = gi
-                if id(p) not in self._hooked:
-                    p.register_post_accumulate_grad_hook(self._on_grad)
-                    self._hooked.add(id(p))
-        self._pending = [len(g) for g in self._groups]
-        self._reduced = set()
-        self._armed = True
-        self._comm = None
-
-    def _on_grad(self, p: torch.nn.Parameter) -> None:
-        if not getattr(self, "_armed", False):
-            return
-        gi = self._owner.get(id(p))
-        if gi is None:
-            return
-        self._pending[gi] -= 1
-        if self._pending[gi] == 0:
-            group = self._groups[gi]
-            if group and group[0].is_cuda:
-                cur = torch.cuda.current_stream()
-                if self._comm is None:
-                    if not hasattr(self, "_comm_stream"):
-                        self._comm_stream = torch.cuda.Stream()
-                    self._comm = self._comm_stream
-                self._comm.wait_stream(cur)
-                for q in group:
-                    q.grad.record_stream(self._comm)
-                with torch.cuda.stream(self._comm):
-                    self._reduce(group, async_op=False)
-            else:
-                self._reduce(group, async_op=False)
-            self._reduced.update(id(q) for q in group)
-
-    def _reduce(self, params: List[torch.nn.Parameter], async_op: bool) -> None:
-        ws = self.world_size(self.group)
-        work = []
-        for bucket in self.buckets(params):
-            flat = torch.cat([p.grad.reshape(-1) for p in bucket])
-            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
-            work.append((h, flat, bucket))
-            self.bytes_reduced += flat.numel() * 4
-            self.n_collectives += 1
-        for h, flat, bucket in work:
-            if h is not None and async_op:
-                h.wait()
-            flat.div_(ws)
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
-
     def __call__(self, params: Iterable[torch.nn.Parameter]) -> None:
         ws = self.world_size(self.group)
         if ws == 1:
             return
-        params = list(params)
-        if getattr(self, "_armed", False):
-            self._armed = False
-            if self._comm is not None:
-                torch.cuda.current_stream().wait_stream(self._comm)
-                self._comm = None
-            params = [p for p in params if id(p) not in self._reduced]
-            if not params:
-                return
         work = []
-        for bucket in self.buckets(params):
+        for bucket in self.buckets(list(params)):
             flat = torch.cat([p.grad.reshape(-1) for p in bucket])
             h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=self.async_op)
             work.append((h, flat, bucket))

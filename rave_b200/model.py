@@ -438,13 +438,6 @@ class RAVE(nn.Module):
 
         loss_gen, loss_dis, aux = self.compute_losses(x_raw, is_dis, eps)
 
-        if grad_hook is not None and hasattr(grad_hook, "arm"):
-            # data parallel: reduce each group as soon as its gradients are complete (rave_b200/ddp.py)
-            if is_dis:
-                nets = [m for m in self.discriminator.modules() if type(m).__name__ == "ConvNet"]
-                grad_hook.arm([list(n.parameters()) for n in nets] if nets else [dis_params])
-            else:
-                grad_hook.arm([list(self.decoder.parameters()), list(self.encoder.parameters())])
         if is_dis:
             dis_opt.zero_grad(set_to_none=True)
             loss_dis.backward()

@@ -45,30 +45,6 @@ def _worker(rank, world, port, bucket_bytes, ret):
         n_with_grad = sum(p.numel() for i, p in enumerate(model.parameters()) if i != 2)
         assert red.bytes_reduced == 4 * n_with_grad
         ret[rank] = red.n_collectives
-        # early reduction: groups are reduced from the post-accumulate hooks while backward is still running; the
-        # call after backward only handles what is left.  Same result as reducing everything afterwards.
-        x = torch.full((2, 7), float(rank + 1))
-        for p in model.parameters():
-            p.grad = None
-        model(x).sum().backward()
-        ddp.GradientAllReducer(bucket_bytes=bucket_bytes)(list(model.parameters()))
-        ref = [p.grad.clone() for p in model.parameters()]
-        for p in model.parameters():
-            p.grad = None
-        red2 = ddp.GradientAllReducer(bucket_bytes=bucket_bytes)
-        groups = [list(model[2].parameters()), list(model[1].parameters())]      # model[0] is "the rest"
-        red2.arm(groups)
-        model(x).sum().backward()
-        assert len(red2._reduced) == sum(len(g) for g in groups), "hooks did not fire for every group"
-        red2(list(model.parameters()))
-        for p, r in zip(model.parameters(), ref):
-            assert torch.allclose(p.grad, r, rtol=1e-6, atol=1e-7)
-        # disarmed: a later backward must not trigger collectives from the hooks
-        n_before = red2.n_collectives
-        for p in model.parameters():
-            p.grad = None
-        model(x).sum().backward()
-        assert red2.n_collectives == n_before
     finally:
         dist.destroy_process_group()
 
