@@ -240,12 +240,18 @@ colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ g, float *__restrict__ out,
 // stats[0] += sum |h_r - h_f|, stats[1] += sum |h_r|   over l < L, c < C.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float unleaky(float a, float inv_slope) { return a > 0.f ? a : a * inv_slope; }
+__device__ __forceinline__ void ldg256_nc(const void *p, uint32_t *r) {     // 32-byte aligned, read-only
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
 
 __global__ void __launch_bounds__(256)
 fm_stats_kernel(const __nv_bfloat16 *__restrict__ a, float *__restrict__ stats, int Bh, int L, int pitch, int C,
                 float inv_slope) {
+  // one thread = 16 channels (one 256-bit load per batch half); C % 16 == 0
   __shared__ float red0[8], red1[8];
-  const int vecs = C >> 3;                       // 8 bf16 per 16-byte vector
+  const int vecs = C >> 4;
   const long total = (long)Bh * L * vecs;
   const size_t half = (size_t)Bh * pitch * C;
   float s0 = 0.f, s1 = 0.f;
@@ -254,12 +260,12 @@ fm_stats_kernel(const __nv_bfloat16 *__restrict__ a, float *__restrict__ stats, 
     const long bl = i / vecs;
     const int l = (int)(bl % L);
     const int b = (int)(bl / L);
-    const size_t o = ((size_t)b * pitch + l) * C + v * 8;
-    const uint4 r = *reinterpret_cast<const uint4 *>(a + o);
-    const uint4 f = *reinterpret_cast<const uint4 *>(a + o + half);
-    const uint32_t rw[4] = {r.x, r.y, r.z, r.w}, fw[4] = {f.x, f.y, f.z, f.w};
+    const size_t o = ((size_t)b * pitch + l) * C + v * 16;
+    uint32_t rw[8], fw[8];
+    ldg256_nc(a + o, rw);
+    ldg256_nc(a + o + half, fw);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const float hr0 = unleaky(bf16_lo(rw[j]), inv_slope), hr1 = unleaky(bf16_hi(rw[j]), inv_slope);
       const float hf0 = unleaky(bf16_lo(fw[j]), inv_slope), hf1 = unleaky(bf16_hi(fw[j]), inv_slope);
       s0 += fabsf(hr0 - hf0) + fabsf(hr1 - hf1);
@@ -415,9 +421,10 @@ extern "C" int rave_colsum_bf16(const void *g_bf16, float *out, int R, int L, in
 extern "C" int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, int pitch, int C, float slope,
                              void *stream) {
   using namespace rave;
-  RAVE_CHECK_ARG(a_bf16 && stats && Bh > 0 && L > 0 && pitch >= L && C > 0 && C % 8 == 0 && slope > 0.f,
-                 "fm_stats: bad argument");
-  const long total = (long)Bh * L * (C / 8);
+  RAVE_CHECK_ARG(a_bf16 && stats && Bh > 0 && L > 0 && pitch >= L && C > 0 && C % 16 == 0 && slope > 0.f &&
+                     ((uintptr_t)a_bf16 & 31) == 0,
+                 "fm_stats: bad argument (C %% 16 == 0, 32-byte aligned operand)");
+  const long total = (long)Bh * L * (C / 16);
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   fm_stats_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a_bf16, stats, Bh, L, pitch,
