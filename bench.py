@@ -435,6 +435,11 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, ms_e2e = times.tolist()
+    if world > 1 and rank != 0:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     audio_s = world * B * T / SR
     value = audio_s * args.steps / (ms * 1e-3)
     value_e2e = audio_s * args.steps / (ms_e2e * 1e-3)
@@ -475,10 +480,9 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         # The captured graphs hold NCCL kernels; tearing the communicator down under them can block
-        # (observed: both ranks stuck in destroy_process_group after the result line).  Synchronise, make sure
-        # every rank is done, flush, and leave without running the communicator's destructor.
-        torch.cuda.synchronize()
-        dist.barrier()
+        # (observed: both ranks stuck in destroy_process_group after the result line).  Synchronise, flush, and
+        # leave without running the communicator's destructor.  No collective after the timing reduction: ranks
+        # other than 0 are done there and leave on their own (see below), rank 0 finishes its single-GPU extras alone.
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
