@@ -177,3 +177,48 @@ def test_fused_feature_matching_vs_oracle(emu):
     half = x.shape[0] // 2
     assert float(gf[:half].abs().max()) == 0.0
     assert rel_l2(gf[half:], go[half:]) < tol(emu, 5e-5, 0.25)
+
+
+@pytest.mark.parametrize("K,stride,pad", [(15, 4, 7), (5, 4, 2), (8, 4, 2), (4, 2, 1), (16, 8, 4), (7, 3, 3)])
+def test_phase_fused_taps_reproduce_transposed_map(K, stride, pad):
+    """engine._fused_phase_taps: the J-tap stride-1 conv over rows of `stride` positions equals the transposed map
+    t = l*stride + k - pad (dgrad of a strided conv / forward of a transposed conv), checked on scalar 'channels'."""
+    from rave_b200 import engine
+    taps, J, pad_l = engine._fused_phase_taps(K, stride, pad)
+    assert len(taps) == J * stride
+    g = torch.Generator().manual_seed(K * 100 + stride)
+    Lsrc = 23
+    src = torch.randn(Lsrc, generator=g, dtype=torch.float64)
+    w = torch.randn(K, generator=g, dtype=torch.float64)
+    Lout = (Lsrc - 1) * stride - 2 * pad + K
+    ref = torch.zeros(Lout + 4 * stride, dtype=torch.float64)
+    for l in range(Lsrc):
+        for k in range(K):
+            t = l * stride + k - pad
+            if 0 <= t < Lout:
+                ref[t] += src[l] * w[k]
+    got = torch.zeros_like(ref)
+    rows = (Lout + stride - 1) // stride
+    for q in range(rows):
+        for j in range(J):
+            l = q + j - pad_l
+            if not (0 <= l < Lsrc):
+                continue
+            for p in range(stride):
+                k = taps[j * stride + p]
+                if k >= 0 and q * stride + p < Lout:
+                    got[q * stride + p] += src[l] * w[k]
+    assert torch.allclose(got, ref, atol=1e-12)
+
+
+@pytest.mark.parametrize("K,stride,pad", [(15, 4, 7), (5, 4, 2), (8, 4, 3), (4, 2, 1)])
+def test_wide_wgrad_slots_cover_every_tap_once(K, stride, pad):
+    """engine._wide_wgrad_taps: tap k of a strided layer reads row l + j(k) / channel block p(k) of the operand viewed
+    with `stride` positions per row; the slots are distinct and decode back to l*stride + k - pad."""
+    from rave_b200 import engine
+    J, pad_l, slots = engine._wide_wgrad_taps(K, stride, pad)
+    assert len(set(slots)) == K and max(slots) < J * stride
+    for k, sl in enumerate(slots):
+        j, p = sl // stride - pad_l, sl % stride
+        for l in range(5):
+            assert (l + j) * stride + p == l * stride + k - pad
