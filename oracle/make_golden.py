@@ -224,6 +224,119 @@ def golden_discriminator_v2(R, capacity=4, B=2, T=8192):
     torch.save(fx, os.path.join(GOLDEN, "discriminator_v2.pt"))
 
 
+def build_ref_rave(R, cfg: O.ArchConfig, disc_capacity=4, update_discriminator_every=2, phase_1_duration=1000,
+                   kind="v2"):
+    """The reference's `rave.RAVE` bound the way configs/{v2,v3,discrete}.gin bind it (v2.gin:53-89, v1.gin:95-112,
+    snake.gin, adain.gin, descript_discriminator.gin, discrete.gin:13-49), at the capacities given."""
+    D = R.discriminator
+    blocks, core = R.blocks, R.core
+    norm = blocks.normalization
+    D.normalization = lambda m, mode="weight_norm": norm(m, mode)
+    snake = kind == "v3"
+    act = (lambda dim: blocks.Snake(dim)) if snake else (lambda dim: nn.LeakyReLU(.2))
+    adain = (lambda dim: blocks.AdaptiveInstanceNormalization(dim)) if kind == "v3" else None
+    if kind == "v3":
+        disc = R.descript_discriminator.DescriptDiscriminator
+    else:
+        periods_net = partial(D.ConvNet, out_size=1, capacity=disc_capacity, n_layers=4, stride=4,
+                              conv=nn.Conv2d, kernel_size=(5, 1))
+        scales_net = partial(D.ConvNet, out_size=1, capacity=disc_capacity, n_layers=4, stride=4,
+                             conv=nn.Conv1d, kernel_size=15)
+        disc = partial(D.CombineDiscriminators, [
+            partial(D.MultiPeriodDiscriminator, periods=[2, 3, 5, 7, 11], convnet=periods_net),
+            partial(D.MultiScaleDiscriminator, n_discriminators=3, convnet=scales_net)])
+    enc_v2 = partial(blocks.EncoderV2, data_size=cfg.n_band, capacity=cfg.capacity, ratios=cfg.ratios,
+                     latent_size=cfg.latent_size, n_out=1 if kind == "discrete" else 2,
+                     kernel_size=cfg.kernel_size, dilations=cfg.dilations, activation=act, adain=adain)
+    noise_aug = 0
+    if kind == "discrete":
+        noise_aug = cfg.latent_size
+        enc = partial(blocks.DiscreteEncoder, encoder_cls=enc_v2,
+                      vq_cls=partial(R.quantization.ResidualVectorQuantization, num_quantizers=16,
+                                     dim=cfg.latent_size, codebook_size=1024),
+                      num_quantizers=16, noise_augmentation=noise_aug)
+    else:
+        enc = partial(blocks.VariationalEncoder, enc_v2)
+    dec = partial(blocks.GeneratorV2, data_size=cfg.n_band, capacity=cfg.capacity, ratios=cfg.ratios,
+                  latent_size=core.get_augmented_latent_size(cfg.latent_size, noise_aug),
+                  kernel_size=cfg.kernel_size, dilations=cfg.dilations,
+                  amplitude_modulation=True, activation=act, adain=adain)
+    stft = partial(core.MultiScaleSTFT, scales=[2048, 1024, 512, 256, 128], sample_rate=48000, magnitude=True)
+    dist = partial(core.AudioDistanceV1, multiscale_stft=stft, log_epsilon=1.0 if kind == "discrete" else 1e-7)
+    orig_du = blocks.DilatedUnit
+    blocks.DilatedUnit = partial(orig_du, activation=act)        # snake.gin:10-11
+    try:
+        m = R.model.RAVE(latent_size=cfg.latent_size, sampling_rate=48000, encoder=enc, decoder=dec,
+                         discriminator=disc, phase_1_duration=phase_1_duration, gan_loss=core.hinge_gan,
+                         valid_signal_crop=True,
+                         feature_matching_fun=partial(core.mean_difference, norm="L1", relative=True),
+                         num_skipped_features=0 if kind == "discrete" else 1, audio_distance=dist,
+                         multiband_audio_distance=dist, weights={"feature_matching": 20},
+                         pqmf=partial(R.pqmf.CachedPQMF, attenuation=100, n_band=cfg.n_band),
+                         update_discriminator_every=update_discriminator_every, n_channels=1)
+    finally:
+        blocks.DilatedUnit = orig_du
+        D.normalization = norm
+    return m
+
+
+def golden_training_step(R, B=2, T=32768):
+    """The reference's OWN `RAVE.training_step` (rave/model.py:288-424) executed under the stubs: a phase-1
+    generator step, a phase-2 discriminator step and a phase-2 generator step on the same model, in that order.
+    Commits, per step: the batch, the reparametrisation noise the reference drew (global RNG re-seeded right before
+    the call; `randn_like` is the first draw), every logged scalar and the full post-step state_dict."""
+    print("RAVE.training_step (phase-1 G, phase-2 D, phase-2 G)")
+    set_padding_mode("centered")
+    cfg = O.ArchConfig(capacity=8, latent_size=16)
+    torch.manual_seed(0)
+    m = build_ref_rave(R, cfg)
+    m.train()
+    m.receptive_field[0], m.receptive_field[1] = 1024, 512       # what validation_epoch_end would have measured
+    opts = m.configure_optimizers()
+    gen_opt, dis_opt = opts[0]["optimizer"], opts[1]["optimizer"]
+    logs = {}
+    m.optimizers = lambda: (gen_opt, dis_opt)
+    m.log = lambda k, v: logs.__setitem__(k, v.detach().clone() if torch.is_tensor(v) else torch.tensor(float(v)))
+    m.log_dict = lambda d: [m.log(k, v) for k, v in d.items()]
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    Lz = T // cfg.n_band
+    for r in cfg.ratios:
+        Lz //= r
+    steps = []
+    for name, warmed, batch_idx, seed in (("phase1_gen", False, 0, 100), ("phase2_dis", True, 0, 101),
+                                          ("phase2_gen", True, 1, 102)):
+        m.warmed_up = warmed
+        x = make_input(B, 1, T, seed=500 + seed)
+        torch.manual_seed(seed)
+        eps = torch.randn(B, cfg.latent_size, Lz)
+        torch.manual_seed(seed)
+        logs.clear()
+        m.training_step(x.clone(), batch_idx)
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        # gradients the step's optimiser consumed (zero_grad runs BEFORE backward in the reference, so they are still
+        # there): discriminator.* after a D-step, encoder.* / decoder.* after a G-step
+        dis_step = warmed and batch_idx % m.update_discriminator_every == 0
+        grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()
+                 if p.grad is not None and (k.startswith("discriminator.") == dis_step)
+                 and not (warmed and k.startswith("encoder.")) and not k.startswith("pqmf.")}
+        steps.append(dict(name=name, warmed_up=warmed, batch_idx=batch_idx, x=x, eps=eps,
+                          logs={k: v.clone() for k, v in logs.items()}, state_dict=sd, grads=grads))
+        print("  ", name, {k: round(float(v), 6) for k, v in logs.items()})
+    # pin the restatement: losses of each step from the state the step started in
+    prev = sd0
+    for st in steps:
+        sdp = {k: v for k, v in prev.items()}
+        tot, ldis, parts = O.train_step_losses(st["x"], sdp, cfg, st["eps"], warmed_up=st["warmed_up"], beta=1.0,
+                                               receptive_field=(1024, 512), return_parts=True)
+        for k, v in parts.items():
+            check(f"{st['name']} {k}", v, st["logs"][k], 2e-6)
+        if st["warmed_up"]:
+            check(f"{st['name']} loss_dis", ldis, st["logs"]["loss_dis"], 2e-6)
+        prev = st["state_dict"]
+    torch.save(dict(cfg=vars(cfg), disc_capacity=4, update_discriminator_every=2, receptive_field=(1024, 512),
+                    state_dict=sd0, steps=steps), os.path.join(GOLDEN, "training_step_v2_tiny.pt"))
+
+
 def golden_losses(R):
     print("spectral distance (core.AudioDistanceV1)")
     core = R.core
@@ -251,6 +364,15 @@ def golden_state_dict_keys(R):
         keys.update({"decoder." + k: tuple(v.shape) for k, v in dec.state_dict().items()})
         out[name] = keys
         print(f"  {name}: {len(keys)} keys")
+    # the whole `rave.RAVE` module tree (pqmf.*, encoder.*, decoder.*, discriminator.*, buffers) at full size
+    for name, cfg, kind in (("rave_v2", O.ArchConfig(), "v2"),
+                            ("rave_v3", O.ArchConfig(activation="snake", adain=True), "v3"),
+                            ("rave_discrete", O.ArchConfig(ratios=(4, 4, 2, 2), n_out=1), "discrete")):
+        torch.manual_seed(0)
+        m = build_ref_rave(R, cfg, disc_capacity=cfg.capacity, kind=kind)
+        out[name] = {k: (tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()}
+        print(f"  {name}: {len(out[name])} keys, {sum(v.numel() for v in m.state_dict().values()) / 1e6:.2f} M values")
+        del m
     torch.save(out, os.path.join(GOLDEN, "state_dict_keys.pt"))
 
 
@@ -267,6 +389,7 @@ def main():
     golden_autoencoder(R, "v2_small_tiny", O.ArchConfig(capacity=8, latent_size=16, ratios=(4, 2, 2, 2)), B=1, T=4096)
     golden_discriminator_v2(R)
     golden_losses(R)
+    golden_training_step(R)
     golden_state_dict_keys(R)
     print("golden fixtures written to", GOLDEN)
 

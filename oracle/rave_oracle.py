@@ -563,10 +563,23 @@ def v2_small_config(**kw) -> ArchConfig:
 # ----------------------------------------------------------------------------------
 
 
+def valid_signal_crop(x: Tensor, left_rf: int, right_rf: int) -> Tensor:
+    """rave/core.py:220-225 (the `-right_rf // dim` floor division of a negative number included)."""
+    dim = x.shape[1]
+    x = x[..., left_rf // dim:]
+    if right_rf:
+        x = x[..., :-right_rf // dim]
+    return x
+
+
 def train_step_losses(x: Tensor, sd, cfg: ArchConfig, eps: Tensor, warmed_up: bool = True,
-                      beta: float = 1.0, fm_weight: float = 20.0):
+                      beta: float = 1.0, fm_weight: float = 20.0, receptive_field=(0, 0),
+                      return_parts: bool = False):
     """Forward arithmetic of RAVE.training_step (rave/model.py:292-399) for the v2 family,
-    returning (loss_gen_total, loss_dis).  Quirk D1 (weights applied twice) included."""
+    returning (loss_gen_total, loss_dis[, the logged loss_gen terms]).  Quirk D1 (weights applied
+    twice, rave/model.py:397,410-411) included; `receptive_field` = the buffer valid_signal_crop reads
+    (rave/model.py:322-330).  Pinned against the reference's own training_step by
+    oracle/make_golden.py::golden_training_step (tests/golden/training_step_v2_tiny.pt)."""
     hk = sd["pqmf.hk"]
     x_mb = pqmf_encode(x, hk, cfg.pad_mode)
     z = encoder_v2(x_mb, sd, "encoder.encoder.", cfg)
@@ -575,8 +588,14 @@ def train_step_losses(x: Tensor, sd, cfg: ArchConfig, eps: Tensor, warmed_up: bo
     zs, reg = reparametrize(z, eps)
     y_mb = generator_v2(zs, sd, "decoder.", cfg)
     y = pqmf_decode(y_mb, hk, cfg.n_channels, cfg.pad_mode)
+    y = y[..., :x.shape[-1]]
+    y_mb = y_mb[..., :x_mb.shape[-1]]
+    x_mb_c, y_mb_c = x_mb, y_mb
+    if receptive_field[0] + receptive_field[1]:
+        x_mb_c = valid_signal_crop(x_mb, *receptive_field)
+        y_mb_c = valid_signal_crop(y_mb, *receptive_field)
     losses = {
-        "multiband_spectral_distance": audio_distance_v1(x_mb, y_mb),
+        "multiband_spectral_distance": audio_distance_v1(x_mb_c, y_mb_c),
         "fullband_spectral_distance": audio_distance_v1(x, y),
         "regularization": reg * beta,
     }
@@ -588,19 +607,38 @@ def train_step_losses(x: Tensor, sd, cfg: ArchConfig, eps: Tensor, warmed_up: bo
         losses["adversarial"] = loss_adv
     weights = {"feature_matching": fm_weight}
     total = sum(v * weights.get(k, 1.0) for k, v in losses.items())
+    if return_parts:
+        return total, loss_dis, losses
     return total, loss_dis
 
 
-def train_step_cpu(x: Tensor, sd, cfg: ArchConfig, eps: Tensor, dis_step: bool):
-    """One forward+backward of the reference's phase-2 step on CPU via autograd (no optimiser
-    state: the timing baseline counts the same fwd+bwd work the GPU arm does)."""
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, betas=(0.5, 0.9),
+              eps: float = 1e-8):
+    """torch.optim.Adam (no weight decay / amsgrad) as rave/model.py:226-236 configures it; returns the
+    new (p, m, v).  `step` is the 1-based count after this update."""
+    b1, b2 = betas
+    m = m * b1 + g * (1 - b1)
+    v = v * b2 + g * g * (1 - b2)
+    denom = (v.sqrt() / math.sqrt(1 - b2 ** step)) + eps
+    return p - (lr / (1 - b1 ** step)) * m / denom, m, v
+
+
+def train_step_cpu(x: Tensor, sd, cfg: ArchConfig, eps: Tensor, dis_step: bool, warmed_up: bool = True,
+                   receptive_field=(0, 0), return_named: bool = False):
+    """One forward+backward of the reference's training step on CPU via autograd (no optimiser
+    state: the timing baseline counts the same fwd+bwd work the GPU arm does).  Gradients go to the group
+    the reference steps: discriminator (D-step), encoder+decoder (G-step; the encoder's are None in phase 2)."""
     params = {k: v.clone().requires_grad_(v.is_floating_point() and not k.startswith("pqmf."))
               for k, v in sd.items()}
-    total, loss_dis = train_step_losses(x, params, cfg, eps, True)
+    total, loss_dis = train_step_losses(x, params, cfg, eps, warmed_up, receptive_field=receptive_field)
     if dis_step:
-        ps = [v for k, v in params.items() if k.startswith("discriminator.") and v.requires_grad]
-        grads = torch.autograd.grad(loss_dis, ps, allow_unused=True)
+        names = [k for k, v in params.items() if k.startswith("discriminator.") and v.requires_grad]
+        grads = torch.autograd.grad(loss_dis, [params[k] for k in names], allow_unused=True)
     else:
-        ps = [v for k, v in params.items() if k.startswith("decoder.") and v.requires_grad]
-        grads = torch.autograd.grad(total, ps, allow_unused=True)
+        names = [k for k, v in params.items() if (k.startswith("decoder.") or (k.startswith("encoder.")
+                                                                               and not warmed_up))
+                 and v.requires_grad]
+        grads = torch.autograd.grad(total, [params[k] for k in names], allow_unused=True)
+    if return_named:
+        return total.detach(), loss_dis.detach(), dict(zip(names, grads))
     return total.detach(), loss_dis.detach(), grads

@@ -153,6 +153,10 @@ def plan_sequential(mods: List[nn.Module]) -> Optional[List[LayerSpec]]:
         return None
     if pending[0] != ops.ACT_NONE or not specs:
         return None
+    if specs[0].pre_act != ops.ACT_NONE:
+        # a chain's operands are activated by their PRODUCER's epilogue; the chain input has no producer, so a
+        # sequence that starts with an activation (DilatedUnit.net on its own) is not run here
+        return None
     specs[-1].is_output = True
     specs[-1].want_f32 = True
     return specs

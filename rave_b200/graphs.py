@@ -6,8 +6,15 @@ GPU time of the bf16 step.  `GraphedTrainer` captures the generator step and the
 Replay-safe because train_body has no host-side decisions or syncs, the optimisers are `capturable`
 (lr and step counters live on the device; LinearLR updates the lr tensor in place between replays) and
 every buffer the library kernels see is allocated from the graph's private pool (tensor maps bake the
-addresses at capture).
+addresses at capture).  Host-side scalars that a schedule may move are read from device memory:
+`beta_factor` (BetaWarmupCallback) lives in `model._beta_dev`, refreshed before every replay; the loss
+weights (`model.weights`) are constants of the captured graph -- changing them needs a new GraphedTrainer.
+
+The eager warm-up the capture needs (lazy state, cuFFT plans, kernel attributes) performs real optimiser
+updates; parameters, buffers and optimiser state are snapshotted before it and restored afterwards, so
+constructing a GraphedTrainer does not move the model.
 """
+import copy
 from typing import Dict, Optional
 
 import torch
@@ -25,6 +32,11 @@ class GraphedTrainer:
         model.optimizers(capturable=True)
         if not model.warmed_up:
             raise RuntimeError("capture phase-2 steps (model.warmed_up = True); phase 1 has no D-step")
+        self._weights_at_capture = dict(model.weights)
+        model._beta_dev = torch.tensor(float(model.beta_factor), dtype=torch.float32, device=example_batch.device)
+        gen_opt, dis_opt = model.optimizers()
+        snap_tensors = [(t, t.detach().clone()) for t in list(model.parameters()) + list(model.buffers())]
+        snap_opt = [(o, copy.deepcopy(o.state_dict())) for o in (gen_opt, dis_opt)]
         self.graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self.outputs: Dict[bool, Dict[str, torch.Tensor]] = {}
         self.launches: Dict[bool, int] = {}      # library kernel launches recorded in each graph
@@ -50,12 +62,36 @@ class GraphedTrainer:
             self.launches[is_dis] = _lib.launch_count() - n0
             self.graphs[is_dis] = g
             self.outputs[is_dis] = out
+        # undo the warm-up updates: parameters / buffers back to their values, optimiser state back to what it was
+        # (moments the warm-up created lazily are zeroed IN PLACE: the graphs hold their addresses)
+        with torch.no_grad():
+            for t, v in snap_tensors:
+                t.copy_(v)
+            for opt, sd in snap_opt:
+                old = {}
+                for g_new, g_old in zip(opt.param_groups, sd["param_groups"]):
+                    for p, idx in zip(g_new["params"], g_old["params"]):
+                        old[p] = sd["state"].get(idx)
+                    st_old = g_old.get("step")
+                    if torch.is_tensor(g_new.get("step")):
+                        g_new["step"].copy_(st_old) if torch.is_tensor(st_old) else g_new["step"].zero_()
+                for p, st in opt.state.items():
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            o = old.get(p)
+                            v.copy_(o[k]) if (o is not None and k in o) else v.zero_()
+        engine.invalidate_prepared()
 
     def step(self, batch: torch.Tensor, batch_idx: int):
         """Same contract as RAVE.training_step: returns the logged scalars (device tensors)."""
         is_dis = self.model.is_discriminator_step(batch_idx)
+        if self.model.weights != self._weights_at_capture:
+            raise RuntimeError("GraphedTrainer: model.weights changed after capture (the loss weights are constants of "
+                               "the captured graphs); build a new GraphedTrainer")
+        self.model._beta_dev.fill_(float(self.model.beta_factor))
         self.x_static.copy_(batch, non_blocking=True)
         self.graphs[is_dis].replay()
         engine.invalidate_prepared()       # parameters changed without bumping their autograd versions
+        self.outputs[is_dis]["beta_factor"] = self.model.beta_factor
         self.model.logged = self.outputs[is_dis]
         return self.outputs[is_dis]

@@ -158,15 +158,17 @@ class RAVE(nn.Module):
 
     def _receptive_field_host(self):
         """Host copy of the `receptive_field` buffer (read once: no device->host sync per step)."""
-        if getattr(self, "_rf_host", None) is None:
-            self._rf_host = tuple(int(v) for v in self.receptive_field.tolist())
-        return self._rf_host
+        ver = self.receptive_field._version          # bumped by load_state_dict / any in-place write to the buffer
+        hit = getattr(self, "_rf_host", None)
+        if hit is None or hit[0] != ver or hit[1] is not self.receptive_field:
+            hit = self._rf_host = (ver, self.receptive_field, tuple(int(v) for v in self.receptive_field.tolist()))
+        return hit[2]
 
     def set_receptive_field(self, left: int, right: int):
         """What validation_epoch_end does in the reference (rave/model.py:446-453)."""
         self.receptive_field[0] = left
         self.receptive_field[1] = right
-        self._rf_host = (int(left), int(right))
+        self._rf_host = (self.receptive_field._version, self.receptive_field, (int(left), int(right)))
 
     # ------------------------------------------------------------------ optimisers
     def configure_optimizers(self, capturable: bool = False):
@@ -336,7 +338,12 @@ class RAVE(nn.Module):
                 v.record_stream(torch.cuda.current_stream())
         loss_gen = {}
         loss_gen.update(distances)
-        loss_gen["regularization"] = reg * self.beta_factor
+        # schedule-driven scalar: a captured graph reads it from device memory (GraphedTrainer refreshes the tensor
+        # before every replay), eager steps use the Python float as the reference does
+        beta_dev = getattr(self, "_beta_dev", None)
+        if beta_dev is not None and not (reg.is_cuda and torch.cuda.is_current_stream_capturing()):
+            beta_dev = None
+        loss_gen["regularization"] = reg * (beta_dev if beta_dev is not None else self.beta_factor)
         if self.warmed_up:
             loss_gen["feature_matching"] = self.weights["feature_matching"] * feature_matching_distance
             loss_gen["adversarial"] = self.weights["adversarial"] * loss_adv

@@ -57,4 +57,9 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             _lib.call("rave_adam_multi", n, pa, ga, ma, va, na, lr.data_ptr(), group["step"].data_ptr(), float(b1),
                       float(b2), float(group["eps"]), _lib.stream_ptr())
+        # The kernel writes the parameters through raw pointers: autograd's version counters do not move, so the
+        # engine's per-module cache of prepared (weight-normalised, tap-major bf16) weights would keep serving the
+        # pre-update values.  Drop it (a host-side epoch counter; captured graphs never use the cache).
+        from . import engine
+        engine.invalidate_prepared()
         return loss

@@ -114,6 +114,17 @@ def test_state_dict_contract_full_size(name):
     assert sd == ks
 
 
+@pytest.mark.parametrize("name", ["v2", "v3", "discrete"])
+def test_full_rave_state_dict_contract(name):
+    """The whole `rave.RAVE` module tree (pqmf.*, encoder.*, decoder.*, discriminator.*, buffers; dumped from the
+    reference built with the gin bindings of configs/{v2,v3,discrete}.gin): same keys, shapes and dtypes."""
+    ks = torch.load(os.path.join(GOLDEN, "state_dict_keys.pt"), weights_only=False)["rave_" + name]
+    m = configs.build_rave(name)
+    sd = {k: (tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()}
+    assert set(sd) == set(ks), sorted(set(sd) ^ set(ks))[:20]
+    assert sd == ks, [k for k in sd if sd[k] != ks[k]][:20]
+
+
 def test_tiny_golden_state_dicts_load_strictly():
     for name, kw in (("v2_tiny", {}), ("v2_tiny_causal", dict(padding_mode="causal")),
                      ("v3_tiny", dict(name="v3")), ("v2_small_tiny", dict(ratios=[4, 2, 2, 2]))):

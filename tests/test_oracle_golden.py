@@ -113,3 +113,75 @@ def test_descript_mpd_oracle_matches_live_reference():
     y = torch.randn(2, 1, 500)
     dd = R.descript_discriminator.DescriptDiscriminator()
     assert torch.equal(O.descript_preprocess(y), dd.preprocess(y))
+
+
+# fp32 conditioning of the training-step gradients, (all tensors, worst tensor) rel-L2: see the comments in the test
+GRAD_TOL = {"phase1_gen": (3e-3, 1e-2), "phase2_dis": (2e-5, 1e-3), "phase2_gen": (5e-2, 1e-1)}
+# fraction of parameter elements whose Adam update may differ by more than 5 % of lr (same conditioning)
+UPD_FRAC = {"phase1_gen": 2e-3, "phase2_dis": 2e-3, "phase2_gen": 6e-2}
+
+
+def test_training_step_restatement_reproduces_reference_steps():
+    """tests/golden/training_step_v2_tiny.pt holds three steps of the reference's OWN RAVE.training_step
+    (rave/model.py:288-424; phase-1 G, phase-2 D, phase-2 G).  The restatement (O.train_step_losses / train_step_cpu,
+    the CPU arm of bench.py) must give the same logged losses, and its gradients pushed through O.adam_step must land
+    on the reference's post-step parameters."""
+    g = load("training_step_v2_tiny.pt")
+    cfg = O.ArchConfig(**g["cfg"])
+    rf = tuple(g["receptive_field"])
+    prev = g["state_dict"]
+    moments = {}
+    steps_taken = {"gen": 0, "dis": 0}
+    for st in g["steps"]:
+        dis_step = st["warmed_up"] and st["batch_idx"] % g["update_discriminator_every"] == 0
+        total, loss_dis, parts = O.train_step_losses(st["x"], prev, cfg, st["eps"], warmed_up=st["warmed_up"],
+                                                     receptive_field=rf, return_parts=True)
+        for k, v in parts.items():
+            assert rel_l2(v, st["logs"][k]) < 2e-6, (st["name"], k)
+        if st["warmed_up"]:
+            assert rel_l2(loss_dis, st["logs"]["loss_dis"]) < 2e-6
+        _, _, grads = O.train_step_cpu(st["x"], prev, cfg, st["eps"], dis_step, warmed_up=st["warmed_up"],
+                                       receptive_field=rf, return_named=True)
+        group = "dis" if dis_step else "gen"
+        steps_taken[group] += 1
+        lr = 1e-4 if dis_step else 1e-3
+        new = dict(prev)
+        n_upd = 0
+        assert {k for k, gr in grads.items() if gr is not None} == set(st["grads"]), st["name"]
+        for k, gr in grads.items():
+            if gr is None:
+                continue
+            # The gradient of the log-magnitude spectral distance is ill-conditioned in fp32: the reference's OWN fp32
+            # gradients sit 5e-4 (rel-L2, all tensors) from an fp64 evaluation of the same step, this restatement's 8e-4
+            # (measured in the build container); the losses themselves agree to the last bit.
+            # The phase-2 generator step adds the L1 feature-matching term, whose gradient is sign(h_r - h_f): elements
+            # at rounding level flip, and the reference's fp32 gradients are 1.1e-2 from fp64 (this restatement's 0.9e-2).
+            # The discriminator step (hinge on the scores) is well conditioned: 5e-7.
+            if st["grads"][k].abs().max() > 0:
+                assert rel_l2(gr, st["grads"][k]) < GRAD_TOL[st["name"]][1], (st["name"], k, rel_l2(gr, st["grads"][k]))
+            m, v = moments.get(k, (torch.zeros_like(gr), torch.zeros_like(gr)))
+            # per-parameter step count: the encoder is frozen in phase 2 (z.detach()), its Adam state stays behind
+            cnt = moments.get(("n", k), 0) + 1
+            new[k], m, v = O.adam_step(prev[k], gr, m, v, cnt, lr)
+            moments[k], moments[("n", k)] = (m, v), cnt
+            n_upd += 1
+        assert n_upd > 0
+        cat = lambda d: torch.cat([d[k].reshape(-1) for k in sorted(st["grads"])])
+        assert rel_l2(cat(grads), cat(st["grads"])) < GRAD_TOL[st["name"]][0], (st["name"],
+                                                                                rel_l2(cat(grads), cat(st["grads"])))
+        n_bad = n_all = 0
+        for k in prev:
+            want = st["state_dict"][k]
+            if not want.is_floating_point():      # integer buffers (warmed_up flags, receptive_field): module state
+                continue
+            upd_ref = (want - prev[k]).double()
+            upd = (new[k] - prev[k]).double()
+            if upd_ref.abs().max() == 0:
+                assert upd.abs().max() == 0, (st["name"], k)
+            else:
+                # a first Adam step is lr * sign(g): an element whose gradient sits at rounding level may flip, so
+                # count elements that moved differently instead of taking a norm
+                n_bad += int(((upd - upd_ref).abs() > 0.05 * lr).sum())
+                n_all += upd.numel()
+        assert n_bad <= UPD_FRAC[st["name"]] * n_all, (st["name"], n_bad, n_all)
+        prev = st["state_dict"]
