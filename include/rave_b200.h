@@ -57,6 +57,16 @@ int rave_pqmf_analysis_fwd(const float *x, const float *taps, float *y, int B, i
                            int ntaps, int pad_l, int flip_sign, void *stream);
 int rave_pqmf_synthesis_fwd(const float *x, const float *w, float *out, int B, int L, int K,
                             int pad_l, float scale, int flip_sign, void *stream);
+/* The same two operators for a COSINE-MODULATED bank (rave/pqmf.py:32-52 builds nothing else): every table is rank
+ * one per tap residue mod 32, T[k][32 i + r] = C[k][r] * Q[r][i], so the FIR splits into a polyphase prototype
+ * filter (Qt: [17][32], Qt[i][r] = Q[r][i]) and a 16 x 32 (de)modulation (analysis: Ct [32 r][16 k]; synthesis:
+ * Cc [16 c][32 r]) -- 66 instead of 512 / 528 multiply-adds per sample.  Same index conventions as above with
+ * taps[k][j] = Ct[j%32][k] Qt[j/32][j%32] and w[m][c][j] = Cc[c][(16j+m)%32] Qt[(16j+m)/32][(16j+m)%32].
+ * Results agree with the dense form to fp32 rounding (different summation order). */
+int rave_pqmf_analysis_fast(const float *x, const float *Ct, const float *Qt, float *y, int B, int T, int Lout,
+                            int pad_l, int flip_sign, void *stream);
+int rave_pqmf_synthesis_fast(const float *x, const float *Cc, const float *Qt, float *out, int B, int L,
+                             int pad_l, float scale, int flip_sign, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * conv1d family, fp32 CUDA-core path (replaces cc.Conv1d.forward = F.pad + F.conv1d,

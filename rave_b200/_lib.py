@@ -20,6 +20,8 @@ SIGNATURES = {
     "rave_b200_launch_count": (c_ulonglong, []),
     "rave_pqmf_analysis_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rave_pqmf_synthesis_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "rave_pqmf_analysis_fast": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rave_pqmf_synthesis_fast": (c_int, [_P, _P, _P, _P, _I, _I, _I, _F, _I, _P]),
     "rave_conv1d_gather_f32": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L,
                                        _I, _F, _P, _I, _F, _P, _P, _P]),
     "rave_conv1d_scatter_f32": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L,

@@ -62,6 +62,15 @@ def mean_difference(target, value, norm: str = "L1", relative: bool = False):
     raise Exception(f"Norm must be either L1 or L2, got {norm}")
 
 
+class _StftWindow(nn.Module):
+    """Holder of one scale's hann window (`stfts.<i>.window`, the key torchaudio.transforms.Spectrogram contributes)."""
+
+    def __init__(self, n_fft: int) -> None:
+        super().__init__()
+        self.n_fft = n_fft
+        self.register_buffer("window", torch.hann_window(n_fft))
+
+
 class MultiScaleSTFT(nn.Module):
     """rave/core.py:269-319 (magnitude spectrogram, hann window, hop = n_fft/4, centred)."""
 
@@ -73,12 +82,20 @@ class MultiScaleSTFT(nn.Module):
         self.scales = scales
         self.magnitude = magnitude
         self.normalized = normalized
+        # the reference keeps one torchaudio Spectrogram per scale in `self.stfts` (rave/core.py:283-296), whose hann
+        # `window` buffers are part of RAVE.state_dict(): same names here
+        self.stfts = nn.ModuleList([_StftWindow(s) for s in scales])
         for s in scales:
-            self.register_buffer(f"window_{s}", torch.hann_window(s), persistent=False)
             bw = torch.full((s // 2 + 1,), 0.5 * s)       # rfft backward as one c2r transform (ops.RfftFn)
             bw[0] = s
             bw[-1] = s
             self.register_buffer(f"rfft_bw_{s}", bw, persistent=False)
+
+    def __getattr__(self, name):
+        if name.startswith("window_"):                  # window_<n_fft>: the persistent buffer stfts[i].window
+            s = int(name[7:])
+            return self.stfts[list(self.scales).index(s)].window
+        return super().__getattr__(name)
 
     def complex_stfts(self, x):
         x = x.reshape(-1, x.shape[-1])

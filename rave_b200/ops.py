@@ -265,16 +265,26 @@ def am_tanh(x):
 # ----------------------------------------------------------------------------------------------
 
 def _pqmf_analysis_raw(x, taps, Lout, pad_l, flip):
+    """taps: dense table [16][ntaps], or the factorised form (Ct [32][16], Qt [17][32]) of pqmf._factorise."""
     B, T = x.shape
     y = torch.empty(B, 16, Lout, dtype=torch.float32, device=x.device)
+    if isinstance(taps, tuple):
+        call("rave_pqmf_analysis_fast", ptr(x), ptr(taps[0]), ptr(taps[1]), ptr(y), B, T, Lout, pad_l, int(flip),
+             stream_ptr())
+        return y
     call("rave_pqmf_analysis_fwd", ptr(x), ptr(taps), ptr(y), B, T, Lout, taps.shape[1], pad_l,
          int(flip), stream_ptr())
     return y
 
 
 def _pqmf_synthesis_raw(x, w, pad_l, scale, flip):
+    """w: dense weights [16][16][K], or the factorised form (Cc [16][32], Qt [17][32])."""
     B, M, L = x.shape
     out = torch.empty(B, 16 * L, dtype=torch.float32, device=x.device)
+    if isinstance(w, tuple):
+        call("rave_pqmf_synthesis_fast", ptr(x), ptr(w[0]), ptr(w[1]), ptr(out), B, L, pad_l, float(scale), int(flip),
+             stream_ptr())
+        return out
     call("rave_pqmf_synthesis_fwd", ptr(x), ptr(w), ptr(out), B, L, w.shape[2], pad_l, float(scale),
          int(flip), stream_ptr())
     return out
@@ -289,15 +299,16 @@ class PqmfAnalysisFn(torch.autograd.Function):
         B, C, T = x.shape
         if C != 1:
             raise _lib.RaveB200Error("pqmf analysis expects [B,1,T]")
-        Lout = (T + pad_l + pad_r - taps.shape[1]) // 16 + 1
+        ntaps = taps.shape[1] if torch.is_tensor(taps) else taps[2]
+        Lout = (T + pad_l + pad_r - ntaps) // 16 + 1
         y = _pqmf_analysis_raw(x.view(B, T), taps, Lout, pad_l, True)
-        ctx.save_for_backward(taps_bwd)
+        ctx.taps_bwd = taps_bwd          # constant filter tables (never differentiated)
         ctx.cfg = (T, bwd_pad)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (taps_bwd,) = ctx.saved_tensors
+        taps_bwd = ctx.taps_bwd
         T, bwd_pad = ctx.cfg
         dy = _f32c(dy)
         if dy.shape[2] * 16 != T:
@@ -316,13 +327,13 @@ class PqmfSynthesisFn(torch.autograd.Function):
         if M != 16:
             raise _lib.RaveB200Error("pqmf synthesis expects 16 bands")
         out = _pqmf_synthesis_raw(y, w, pad_l, 16.0, True)
-        ctx.save_for_backward(w_bwd)
+        ctx.w_bwd = w_bwd
         ctx.cfg = (L, bwd_pad)
         return out.view(B, 1, 16 * L)
 
     @staticmethod
     def backward(ctx, dout):
-        (w_bwd,) = ctx.saved_tensors
+        w_bwd = ctx.w_bwd
         L, bwd_pad = ctx.cfg
         dout = _f32c(dout)
         B = dout.shape[0]

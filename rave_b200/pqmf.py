@@ -135,9 +135,35 @@ class PQMF(nn.Module):
         return ops.PqmfSynthesisFn.apply(x, t["w"], t["w_bwd"], t["w_pad"], t["w_bwd_pad"])
 
 
+import os as _os
+USE_FAST = _os.environ.get("RAVE_PQMF_DENSE", "0") != "1"      # factorised kernels when the bank is cosine-modulated (always, for rave/pqmf.py designs)
+
+
 def _require_16(n_band):
     if n_band != 16:
         raise RaveB200Error(f"only the 16-band PQMF (every shipped config) has a device kernel, got {n_band}")
+
+
+def _factorise(H, tol=5e-6):
+    """H [16 bands][n] (n <= 544): rank-one-per-residue factorisation H[k][32 i + r] = C[k][r] Q[r][i] of a
+    cosine-modulated bank (the modulating cosine of rave/pqmf.py:43-52 flips sign every 2M = 32 taps).  Computed in
+    float64 on the host from the table itself -- whatever was loaded from a checkpoint is what gets factorised --
+    and verified: returns None (-> dense kernels) if the table is not rank one to `tol` (relative Frobenius).
+    Returns (C [16][32], Qt [17][32]) as float32 CPU tensors."""
+    M, n = H.shape
+    if M != 16 or n > 32 * 17:
+        return None
+    Hp = torch.zeros(16, 32 * 17, dtype=torch.float64)
+    Hp[:, :n] = H.detach().to("cpu", torch.float64)
+    A = Hp.view(16, 17, 32).permute(2, 0, 1)                    # [r][k][i]
+    U, S, Vh = torch.linalg.svd(A, full_matrices=False)
+    root = S[:, 0].clamp_min(0).sqrt()
+    C = (U[:, :, 0] * root[:, None]).t().contiguous()            # [k][r]
+    Q = (Vh[:, 0, :] * root[:, None])                            # [r][i]
+    resid = (A - torch.einsum("kr,ri->rki", C, Q)).norm() / A.norm().clamp_min(1e-300)
+    if not bool(resid <= tol):
+        return None
+    return C.float().contiguous(), Q.t().float().contiguous()
 
 
 def _build_tables(taps, pad_l, pad_r, w, w_pad):
@@ -168,9 +194,23 @@ def _build_tables(taps, pad_l, pad_r, w, w_pad):
     mm = 15 - (i % 16)
     jj = K - 1 - (i // 16)
     w_bwd = 16.0 * w[mm, :, jj].transpose(0, 1).contiguous()       # [c][i]
-    return dict(taps=taps.contiguous(), pad_l=pad_l, pad_r=pad_r, taps_bwd=taps_bwd.contiguous(),
-                taps_bwd_pad=P, w=w.contiguous(), w_pad=w_pad, w_bwd=w_bwd,
-                w_bwd_pad=16 * (K - 1 - w_pad))
+    out = dict(taps=taps.contiguous(), pad_l=pad_l, pad_r=pad_r, taps_bwd=taps_bwd.contiguous(),
+               taps_bwd_pad=P, w=w.contiguous(), w_pad=w_pad, w_bwd=w_bwd,
+               w_bwd_pad=16 * (K - 1 - w_pad), dense=dict(taps=taps.contiguous(), taps_bwd=taps_bwd.contiguous(),
+                                                          w=w.contiguous(), w_bwd=w_bwd))
+    if USE_FAST and K <= 33:
+        # factorised tables for the fast kernels (csrc/pqmf.cu): analysis-form tables are [16][n], synthesis-form
+        # weights w[m][c][j] are the band filters H[c][16 j + m]
+        def syn_as_bank(wt):
+            return wt.permute(1, 2, 0).reshape(16, -1)
+        fa, fs = _factorise(taps), _factorise(syn_as_bank(w))
+        fab, fsb = _factorise(syn_as_bank(taps_bwd)), _factorise(w_bwd)
+        if all(f is not None for f in (fa, fs, fab, fsb)):
+            out["taps"] = (fa[0].t().contiguous().to(dev), fa[1].to(dev), ntaps)          # Ct [32][16], Qt
+            out["w"] = (fs[0].to(dev), fs[1].to(dev))                                        # Cc [16][32], Qt
+            out["taps_bwd"] = (fab[0].to(dev), fab[1].to(dev))
+            out["w_bwd"] = (fsb[0].t().contiguous().to(dev), fsb[1].to(dev), w_bwd.shape[1])
+    return out
 
 
 class CachedPQMF(PQMF):

@@ -86,7 +86,7 @@ def test_pqmf_adjoint_tables_are_exact_adjoints():
     gy = torch.randn_like(y)
     (gx,) = torch.autograd.grad(y, x, gy)
     # adjoint as a synthesis:  out[16t+15-m] = sum_c sum_j w'[m][c][j] s(c,tau) gy[c][tau], tau=t+j-P
-    wb = t["taps_bwd"].double()
+    wb = t["dense"]["taps_bwd"].double()
     P = t["taps_bwd_pad"]
     s = O.reverse_half(gy)
     conv = torch.nn.functional.conv1d(torch.nn.functional.pad(s, (P, 32 - P)), wb)
@@ -97,7 +97,7 @@ def test_pqmf_adjoint_tables_are_exact_adjoints():
     xo = O.pqmf_synthesis(yb, hk)
     go = torch.randn_like(xo)
     (gyb,) = torch.autograd.grad(xo, yb, go)
-    tb = t["w_bwd"].double()
+    tb = t["dense"]["w_bwd"].double()
     pad = t["w_bwd_pad"]
     an = torch.nn.functional.conv1d(torch.nn.functional.pad(go, (pad, tb.shape[1])), tb.unsqueeze(1), stride=16)
     an = O.reverse_half(an[..., :64])
