@@ -164,6 +164,16 @@ int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bi
                        int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
                        int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
                        int out_row_stride, int out_row_offset, const float *fm_d, int fm_bh, void *stream);
+/* Split-operand ("bf16x3") forward: the accurate fast mode (<= 1e-4 rel-L2 end to end; reference arithmetic is fp32,
+ * scripts/train.py:135-136 allow TF32).  xa [B][in_pitch][2*Cin] bf16 rows [hi | lo] (x = hi + lo), wt [2][K][Cout][Cin]
+ * (rave_weight_prep_tc_multi_x3); the tensor cores accumulate hi*hi + lo*hi + hi*lo in fp32.  out_act / res_act are
+ * [hi | lo] rows of 2*Cout; bias / res / out_f32 as in rave_conv1d_tc_fwd.  act_cs (0 = Cout): channels per POSITION
+ * when an output row holds several positions side by side (phase-fused transposed conv) -- each position is its own
+ * [hi | lo] pair of 2*act_cs channels.  No gradient epilogues (forward path). */
+int rave_conv1d_tc_fwd_x3(const void *xa_bf16, const void *wt_bf16, const float *bias, const float *res,
+                          const void *res_act, float res_slope, float *out_f32, void *out_act, int B, int Cin, int Lin,
+                          int in_pitch, int Cout, int Lout, int K, int stride, int dil, int pad_l, int act, float slope,
+                          int out_rows, int out_row_stride, int out_row_offset, int act_cs, void *stream);
 /* weight gradient on the same engine (split-K over row slices; each slice writes its own partial):
  *   sum_s dwt[s][k][m][n] = sum_{b,l} P[b][l][m] * Q[b][l*stride + k*dil - pad_l][n]
  * P [B][Lp][Cm] bf16 (conv: dy), Q [B][Lq][Cn] bf16 (conv: activated input);
@@ -274,6 +284,9 @@ typedef struct rave_wprep_layer {
   int tapsA[32], tapsB[32];    /* tap index, or -1 for an all-zero slab (phase-fused layouts)          */
 } rave_wprep_layer;
 int rave_weight_prep_tc_multi(int n, const rave_wprep_layer *layers, void *stream);
+/* split-operand ("bf16x3") layouts: outA [2][nA][C0p][C1p], outB [2][nB][C1p][C0p] with part 0 = bf16(w) and
+ * part 1 = bf16(w - part 0) (operands of rave_conv1d_tc_fwd_x3) */
+int rave_weight_prep_tc_multi_x3(int n, const rave_wprep_layer *layers, void *stream);
 int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers, void *stream);
 /* layout converters between the module-boundary layout [B][C][L] fp32 and the engine's channel-last:
  *   to_cl:   y_bf16[b][l][c] = bf16(act(x[b][c][l])), optionally also y_f32[b][l][c] = x[b][c][l]
@@ -281,6 +294,8 @@ int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers, void *stre
 int rave_ncl_to_cl(const float *x, void *y_bf16, float *y_f32, int B, int C, int L, int act, float slope,
                    const float *alpha, void *stream);
 int rave_cl_to_ncl(const float *x_cl, float *y, int B, int C, int L, void *stream);
+/* split-operand entry: y[b][l][0..C) = hi = bf16(x[b][c][l]), y[b][l][C..2C) = bf16(x - hi) */
+int rave_ncl_to_cl_x3(const float *x, void *y_bf16, int B, int C, int L, void *stream);
 /* fp32 -> bf16 operand preparation: y = bf16(act(x)) */
 int rave_act_to_bf16(const float *x, void *y_bf16, int B, int C, int L, int act, float slope,
                      const float *alpha, void *stream);

@@ -38,6 +38,10 @@ SIGNATURES = {
     "rave_conv1d_tc_supported": (c_int, [_I, _I, _I, _I, _I]),
     "rave_conv1d_tc_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I,
                                    _F, _I, _I, _I, _P, _I, _P]),
+    "rave_conv1d_tc_fwd_x3": (c_int, [_P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I,
+                                      _I, _I, _I, _P]),
+    "rave_weight_prep_tc_multi_x3": (c_int, [_I, _P, _P]),
+    "rave_ncl_to_cl_x3": (c_int, [_P, _P, _I, _I, _I, _P]),
     "rave_conv1d_tc_wgrad": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rave_tapmajor_to_weight_f32": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "rave_conv1d_tc_wgrad_splits": (c_int, [_I, _I, _I, _I, _I]),

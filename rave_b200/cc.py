@@ -162,10 +162,14 @@ class CachedSequential(nn.Sequential):
 
     def forward(self, x, res=None):
         from . import engine
-        if res is None and engine.precision() == "bf16" and x.is_cuda and x.dim() == 3:
+        mode = engine.precision()
+        x3 = mode == "bf16x3"
+        if x3 and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            mode = "fp32"          # the split-operand mode is a forward path: gradients run on the fp32 kernels
+        if res is None and mode in ("bf16", "bf16x3") and x.is_cuda and x.dim() == 3:
             specs = self._tc_plan()
             if specs is not None and (specs[0].kind != "conv" or x.shape[-1] % specs[0].stride == 0):
-                (out,) = engine.run_chain(engine.to_channel_last(x), specs)
+                (out,) = engine.run_chain(engine.to_channel_last(x, x3=x3), specs, x3=x3)
                 Lout = engine.chain_lengths(specs, x.shape[-1])[-1]
                 if out.shape[1] != Lout:
                     out = out[:, :Lout].contiguous()

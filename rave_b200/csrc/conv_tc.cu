@@ -49,16 +49,24 @@ struct TcParams {
   const float *fm_d;       // feature-matching gradient fused into a dgrad epilogue (or null): dact_src is the bf16
   long fm_half;            //   operand a = LeakyReLU(h) of [real; fake] rows, fm_half elements apart; adds
   int fm_bh;               //   d0 sgn(h_r-h_f) + d1 sgn(h_r) to real rows (b < fm_bh), -d0 sgn(h_r-h_f) to fake rows
+  int x3;                  // split-operand mode ("bf16x3"): activations [.., 2*Cin] = [hi | lo], weights [2][K][Cout][Cin]
+  int act_ld;              // row length (elements) of the bf16 operand tensors the epilogue touches (out_act, res_act):
+                           // Cout, or 2*Cout in x3 mode
+  int act_cs;              // x3: channels per POSITION of an output row (Cout; Cout/stride when the row holds the phases
+                           // of a transposed conv side by side): column n = q*cs + c lives at q*2cs + c (hi), +cs (lo)
   int stages;              // pipeline depth actually used (<= the layout's STAGES); RAVE_TC_STAGES overrides
   int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue, 8 = no L2 prefetch, 2 = skip the
                            // activation TMA loads, 4 = skip the weight TMA loads (results are garbage)
 };
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool X3 = false>
 struct SmemLayout {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int PARTS = X3 ? 2 : 1;                    // x3: hi and lo operand tiles side by side
+  static constexpr int A_PART = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_PART = (BLOCK_N * BLOCK_K * 2 + 1023) / 1024 * 1024;
+  static constexpr int A_BYTES = PARTS * A_PART;
+  static constexpr int B_BYTES = PARTS * BLOCK_N * BLOCK_K * 2;          // bytes the TMA unit delivers
+  static constexpr int B_BYTES_PAD = PARTS * B_PART;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
   static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
@@ -87,20 +95,26 @@ __device__ __forceinline__ void st_words(void *ptr, const uint32_t *w) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-template <int CW>
+template <int CW, bool X3>
 __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow,
                                              int fm_side = 0) {
   constexpr int NW = CW / 2;      // 32-bit words of a bf16 row segment
   float v[CW];
-  uint32_t rf[CW], rb[NW], dm[NW], ra[NW], pm[NW];
+  uint32_t rf[CW], rb[NW], dm[NW], ra[NW], ra2[X3 ? NW : 1], pm[NW];
   const size_t off = orow * p.Cout + co;
+  // bf16 operand tensors: in x3 mode every position is [hi | lo] (2 * act_cs channels)
+  const int cs = X3 ? p.act_cs : 0;
+  const size_t offa = X3 ? orow * (size_t)p.act_ld + (size_t)(co / cs) * (2 * cs) + (co % cs) : off;
   if (valid) {
-    if (fm_side)       // partner row of the other batch half (same position, same channels)
+    if (!X3 && fm_side)       // partner row of the other batch half (same position, same channels)
       ld_words<NW>(p.dact_src + (fm_side > 0 ? off + p.fm_half : off - p.fm_half), pm);
-    if (p.res_act) ld_words<NW>(p.res_act + off, ra);
+    if (p.res_act) {
+      ld_words<NW>(p.res_act + offa, ra);
+      if (X3) ld_words<NW>(p.res_act + offa + cs, ra2);
+    }
     if (p.res) ld_words<CW>(p.res + off, rf);
-    if (p.res_bf16) ld_words<NW>(p.res_bf16 + off, rb);
-    if (p.dact_src) ld_words<NW>(p.dact_src + off, dm);
+    if (!X3 && p.res_bf16) ld_words<NW>(p.res_bf16 + off, rb);
+    if (!X3 && p.dact_src) ld_words<NW>(p.dact_src + off, dm);
   }
   if (CW == 32) tmem_ld_32x32(taddr, v);
   else tmem_ld_32x16(taddr, v);       // warp-collective: every lane participates, valid or not
@@ -113,14 +127,14 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
       v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
     }
   }
-  if (p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand (sign bits of bf16)
+  if (!X3 && p.dact_src) {   // chain rule through the LeakyReLU that produced this conv's operand (sign bits of bf16)
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       if (dm[w] & 0x00008000u) v[2 * w] *= p.slope;
       if (dm[w] & 0x80000000u) v[2 * w + 1] *= p.slope;
     }
   }
-  if (fm_side) {
+  if (!X3 && fm_side) {
     // Gradient of d0 * sum|h_r - h_f| + d1 * sum|h_r| with respect to h.  LeakyReLU is strictly increasing, so
     // sgn(h_r - h_f) = sgn(a_r - a_f) and sgn(h_r) = sgn(a_r): the saved operands are compared as they are.  With
     // t = sgn(a_self - a_partner) both halves get d0 * t (real: d0 sgn(h_r-h_f); fake: -d0 sgn(h_r-h_f) = d0 t), real
@@ -139,7 +153,7 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
       }
     }
   }
-  if (p.res_bf16) {
+  if (!X3 && p.res_bf16) {
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       v[2 * w] += bf_lo(rb[w]);
@@ -149,7 +163,11 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
   if (p.res_act) {     // residual skip from the unit's own bf16 operand: undo the LeakyReLU
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-      const float a0 = bf_lo(ra[w]), a1 = bf_hi(ra[w]);
+      float a0 = bf_lo(ra[w]), a1 = bf_hi(ra[w]);
+      if (X3) {          // operand = hi + lo (exact in fp32: two 8-bit significands)
+        a0 += bf_lo(ra2[w]);
+        a1 += bf_hi(ra2[w]);
+      }
       v[2 * w] += fminf(a0, a0 * p.res_inv_slope);          // inverse LeakyReLU (1/slope >= 1): two instructions
       v[2 * w + 1] += fminf(a1, a1 * p.res_inv_slope);
     }
@@ -165,7 +183,7 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
     st_words<CW>(p.out_f32 + off, o);
   }
   if (p.out_act) {
-    uint32_t pk[NW];
+    uint32_t pk[NW], pl[X3 ? NW : 1];
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       float a0 = v[2 * w], a1 = v[2 * w + 1];
@@ -175,28 +193,33 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
       }
       __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
       pk[w] = *reinterpret_cast<uint32_t *>(&h);
+      if (X3) {        // lo = bf16(a - hi): the operand is carried with a 16-bit significand
+        __nv_bfloat162 l = __floats2bfloat162_rn(a0 - bf_lo(pk[w]), a1 - bf_hi(pk[w]));
+        pl[w] = *reinterpret_cast<uint32_t *>(&l);
+      }
     }
-    st_words<NW>(p.out_act + off, pk);
+    st_words<NW>(p.out_act + offa, pk);
+    if (X3) st_words<NW>(p.out_act + offa + cs, pl);
   }
 }
 
 // `part` of `parts` warps share one TMEM lane quadrant and take alternate 32-column chunks (the epilogue is
 // latency-bound -- tcgen05.ld, convert, store with ONE warp per scheduler -- so the CTA-pair kernel runs two)
-template <int BLOCK_N>
+template <int BLOCK_N, bool X3>
 __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t taddr, int n0, bool valid, size_t orow,
                                             int fm_side, int part = 0, int parts = 1) {
   constexpr int MAIN = BLOCK_N / 32 * 32;
 #pragma unroll 1
   for (int c0 = part * 32; c0 < MAIN; c0 += parts * 32)
-    tc_epi_chunk<32>(p, taddr + c0, n0 + c0, valid, orow, fm_side);
-  if (MAIN < BLOCK_N && part == 0) tc_epi_chunk<16>(p, taddr + MAIN, n0 + MAIN, valid, orow, fm_side);
+    tc_epi_chunk<32, X3>(p, taddr + c0, n0 + c0, valid, orow, fm_side);
+  if (MAIN < BLOCK_N && part == 0) tc_epi_chunk<16, X3>(p, taddr + MAIN, n0 + MAIN, valid, orow, fm_side);
 }
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const TcParams p) {
-  using L = SmemLayout<BLOCK_N, BLOCK_K>;
+  using L = SmemLayout<BLOCK_N, BLOCK_K, X3>;
   constexpr int STAGES = L::STAGES;
   constexpr int SWZ = BLOCK_K * 2;
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
@@ -262,6 +285,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_arrive_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
             tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, ph, l0 + j, b0);
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, k * p.Cout + n0);
+            if (X3) {      // lo halves: channels Cin.. of the activation rows, weight slabs K.. (wt is [2][K][Cout][Cin])
+              tma_load_4d(sa + L::A_PART, &tmap_a, &full_bar[stage], p.Cin + kb * BLOCK_K, ph, l0 + j, b0);
+              tma_load_2d(sb + L::B_PART, &tmap_b, &full_bar[stage], kb * BLOCK_K, (p.K + k) * p.Cout + n0);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -294,6 +321,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // advance 16 bf16 = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
             umma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
           }
+          if (X3) {        // a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (the lo*lo term is below fp32 accumulation noise)
+            const uint64_t adesc_lo = make_kmajor_desc(sa + L::A_PART, SWZ);
+            const uint64_t bdesc_lo = make_kmajor_desc(sa + L::A_BYTES + L::B_PART, SWZ);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / 16; ++kk) umma_f16(tmem_d, adesc_lo + 2 * kk, bdesc + 2 * kk, idesc, 1u);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / 16; ++kk) umma_f16(tmem_d, adesc + 2 * kk, bdesc_lo + 2 * kk, idesc, 1u);
+          }
           umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
           if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
         }
@@ -322,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow, p.fm_d ? (b < p.fm_bh ? 1 : -1) : 0);
+      tc_epilogue<BLOCK_N, X3>(p, taddr, n0, valid, orow, p.fm_d ? (b < p.fm_bh ? 1 : -1) : 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -346,16 +381,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // `full` and `tmem-empty` barriers; `empty` / `tmem-full` barriers are replicated and signalled with a
 // multicast tcgen05.commit.
 // =============================================================================================
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool X3 = false>
 struct SmemLayout2 {
   // One pipeline stage always carries 64 reduction channels' worth of operands: UNITS = 64 / BLOCK_K
   // (tap, channel-block) units, each with its own TMA box pair and BLOCK_K/16 MMAs, behind ONE barrier round
   // trip -- a 32-channel block alone is only 2 MMAs (~190 clk at N = 192), less than the round trip costs.
   static constexpr int UNITS = 64 / BLOCK_K;
+  static constexpr int PARTS = X3 ? 2 : 1;                              // x3: [hi units][lo units] of each operand
   static constexpr int A_UNIT = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_UNIT = (BLOCK_N / 2) * BLOCK_K * 2;           // this CTA's half of the weight tile
-  static constexpr int A_BYTES = UNITS * A_UNIT;
-  static constexpr int B_BYTES = UNITS * B_UNIT;
+  static constexpr int A_BYTES = PARTS * UNITS * A_UNIT;
+  static constexpr int B_BYTES = PARTS * UNITS * B_UNIT;
   static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
   static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
@@ -364,11 +400,11 @@ struct SmemLayout2 {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool X3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const TcParams p) {
-  using L = SmemLayout2<BLOCK_N, BLOCK_K>;
+  using L = SmemLayout2<BLOCK_N, BLOCK_K, X3>;
   constexpr int STAGES = L::STAGES;
   constexpr int UNITS = L::UNITS;
   constexpr int SWZ = BLOCK_K * 2;
@@ -420,7 +456,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // =========================== TMA producer (both CTAs; warp-uniform loop) ===========================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t unit_tx = 2 * (((p.dbg & 2) ? 0 : L::A_UNIT) + ((p.dbg & 4) ? 0 : L::B_UNIT));
+    const uint32_t unit_tx = 2 * L::PARTS * (((p.dbg & 2) ? 0 : L::A_UNIT) + ((p.dbg & 4) ? 0 : L::B_UNIT));
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int nt = tile % p.n_nt;
       const int mt = (tile / p.n_nt) * 2 + (int)rank;      // this CTA's M tile (may be >= n_mt: zero-filled)
@@ -463,6 +499,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 tma_load_4d_2sm(sa + u * L::A_UNIT, &tmap_a, &full_bar[stage], c_kb[u], c_ph[u], c_row[u], b0);
               if (!(p.dbg & 4))
                 tma_load_2d_2sm(sb + u * L::B_UNIT, &tmap_b, &full_bar[stage], c_kb[u], c_w[u]);
+              if (X3) {    // lo halves: channels Cin.. of the activation rows, weight slabs K.. (wt is [2][K][Cout][Cin])
+                tma_load_4d_2sm(sa + (UNITS + u) * L::A_UNIT, &tmap_a, &full_bar[stage], p.Cin + c_kb[u], c_ph[u],
+                                c_row[u], b0);
+                tma_load_2d_2sm(sb + (UNITS + u) * L::B_UNIT, &tmap_b, &full_bar[stage], c_kb[u], c_w[u] + p.K * p.Cout);
+              }
             }
           }
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], unit_tx * nu);
@@ -501,6 +542,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
               for (int kk = 0; kk < BLOCK_K / 16; ++kk)
                 umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (u0 > 0 || u > 0 || kk > 0) ? 1u : 0u);
+              if (X3) {    // + a_lo * w_hi + a_hi * w_lo
+                const uint64_t adesc_lo = make_kmajor_desc(sa + (UNITS + u) * L::A_UNIT, SWZ);
+                const uint64_t bdesc_lo = make_kmajor_desc(sb + (UNITS + u) * L::B_UNIT, SWZ);
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_K / 16; ++kk)
+                  umma_f16_2sm(tmem_d, adesc_lo + 2 * kk, bdesc + 2 * kk, idesc, 1u);
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_K / 16; ++kk)
+                  umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc_lo + 2 * kk, idesc, 1u);
+              }
             }
           }
           umma_commit_2sm(&empty_bar[stage]);
@@ -546,14 +597,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const int b2 = (mt2 / p.n_lt) * p.BB + row / p.BL;
           const int l2 = (mt2 % p.n_lt) * p.BL + row % p.BL;
           if (mt2 < n_mt && b2 < p.B && l2 < p.Lout) {
-            const size_t off2 = ((size_t)b2 * p.out_rows + (size_t)l2 * p.out_row_stride + p.out_row_offset) * p.Cout +
-                                (size_t)(tile2 % p.n_nt) * BLOCK_N;
+            const size_t off2 = ((size_t)b2 * p.out_rows + (size_t)l2 * p.out_row_stride + p.out_row_offset) *
+                                    (X3 ? p.act_ld : p.Cout) + (size_t)(tile2 % p.n_nt) * BLOCK_N;
 #pragma unroll
             for (int c = 0; c < BLOCK_N; c += 64) {       // 128-byte lines of a bf16 row segment
-              if (p.dact_src) prefetch_l2(p.dact_src + off2 + c);
-              if (p.fm_d) prefetch_l2(p.dact_src + (b2 < p.fm_bh ? off2 + p.fm_half : off2 - p.fm_half) + c);
-              if (p.res_bf16) prefetch_l2(p.res_bf16 + off2 + c);
+              if (!X3 && p.dact_src) prefetch_l2(p.dact_src + off2 + c);
+              if (!X3 && p.fm_d) prefetch_l2(p.dact_src + (b2 < p.fm_bh ? off2 + p.fm_half : off2 - p.fm_half) + c);
+              if (!X3 && p.res_bf16) prefetch_l2(p.res_bf16 + off2 + c);
               if (p.res_act) prefetch_l2(p.res_act + off2 + c);
+              if (X3 && p.res_act) prefetch_l2(p.res_act + off2 + p.act_cs + c);
             }
           }
         }
@@ -562,7 +614,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
       const int fm_side = p.fm_d ? (b < p.fm_bh ? 1 : -1) : 0;
-      tc_epilogue<BLOCK_N>(p, taddr, n0, valid, orow, fm_side, part, parts);
+      tc_epilogue<BLOCK_N, X3>(p, taddr, n0, valid, orow, fm_side, part, parts);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
@@ -645,12 +697,12 @@ static int pick_block_n2(int Cout, long m_tiles) {
   return best;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool X3>
 static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t stream) {
-  using L = SmemLayout<BN, BK>;
+  using L = SmemLayout<BN, BK, X3>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL);
     if (e != cudaSuccess) {
       set_error("conv1d_tc: cudaFuncSetAttribute(%d bytes): %s", L::TOTAL, cudaGetErrorString(e));
@@ -663,17 +715,17 @@ static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = tiles < sms ? tiles : sms;
-  conv_tc_kernel<BN, BK><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  conv_tc_kernel<BN, BK, X3><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
   RAVE_CHECK_LAUNCH("conv1d_tc");
   return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool X3>
 static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t stream) {
-  using L = SmemLayout2<BN, BK>;
+  using L = SmemLayout2<BN, BK, X3>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL);
     if (e != cudaSuccess) {
       set_error("conv1d_tc(2cta): cudaFuncSetAttribute(%d bytes): %s", L::TOTAL, cudaGetErrorString(e));
@@ -702,44 +754,71 @@ static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams 
     const char *e = getenv("RAVE_TC_EPIWARPS");
     if (e && (atoi(e) == 4 || atoi(e) == 8)) epi = atoi(e);
   }
-  conv_tc2_kernel<BN, BK><<<2 * pairs, 64 + 32 * epi, L::TOTAL, stream>>>(ta, tb, q);
+  conv_tc2_kernel<BN, BK, X3><<<2 * pairs, 64 + 32 * epi, L::TOTAL, stream>>>(ta, tb, q);
   RAVE_CHECK_LAUNCH("conv1d_tc(2cta)");
   return 0;
 }
 
-template <int BK>
+template <int BK, bool X3>
 static int dispatch_n2(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t s) {
   switch (bn) {
-    case 256: return launch2<256, BK>(ta, tb, p, s);
-    case 192: return launch2<192, BK>(ta, tb, p, s);
-    case 128: return launch2<128, BK>(ta, tb, p, s);
-    case 96: return launch2<96, BK>(ta, tb, p, s);
-    case 64: return launch2<64, BK>(ta, tb, p, s);
+    case 256: return launch2<256, BK, X3>(ta, tb, p, s);
+    case 192: return launch2<192, BK, X3>(ta, tb, p, s);
+    case 128: return launch2<128, BK, X3>(ta, tb, p, s);
+    case 96: return launch2<96, BK, X3>(ta, tb, p, s);
+    case 64: return launch2<64, BK, X3>(ta, tb, p, s);
   }
   set_error("conv1d_tc(2cta): no kernel for BLOCK_N=%d", bn);
   return 1;
 }
 
-template <int BK>
+template <int BK, bool X3>
 static int dispatch_n(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
                       cudaStream_t s) {
   switch (bn) {
-    case 256: return launch<256, BK>(ta, tb, p, s);
-    case 192: return launch<192, BK>(ta, tb, p, s);
-    case 128: return launch<128, BK>(ta, tb, p, s);
-    case 96: return launch<96, BK>(ta, tb, p, s);
-    case 64: return launch<64, BK>(ta, tb, p, s);
-    case 48: return launch<48, BK>(ta, tb, p, s);
-    case 32: return launch<32, BK>(ta, tb, p, s);
-    case 16: return launch<16, BK>(ta, tb, p, s);
+    case 256: return launch<256, BK, X3>(ta, tb, p, s);
+    case 192: return launch<192, BK, X3>(ta, tb, p, s);
+    case 128: return launch<128, BK, X3>(ta, tb, p, s);
+    case 96: return launch<96, BK, X3>(ta, tb, p, s);
+    case 64: return launch<64, BK, X3>(ta, tb, p, s);
+    case 48: return launch<48, BK, X3>(ta, tb, p, s);
+    case 32: return launch<32, BK, X3>(ta, tb, p, s);
+    case 16: return launch<16, BK, X3>(ta, tb, p, s);
   }
   set_error("conv1d_tc: no kernel for BLOCK_N=%d", bn);
   return 1;
 }
 
+template <bool X3>
+static int dispatch_all(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
+                        cudaStream_t s) {
+  if (use2)
+    return BK == 64 ? dispatch_n2<64, X3>(BN, ta, tb, p, s) : BK == 32 ? dispatch_n2<32, X3>(BN, ta, tb, p, s)
+                                                                       : dispatch_n2<16, X3>(BN, ta, tb, p, s);
+  switch (BK) {
+    case 64: return dispatch_n<64, X3>(BN, ta, tb, p, s);
+    case 32: return dispatch_n<32, X3>(BN, ta, tb, p, s);
+    case 16: return dispatch_n<16, X3>(BN, ta, tb, p, s);
+  }
+  set_error("conv1d_tc: no kernel for BLOCK_K=%d", BK);
+  return 1;
+}
+
+// The split-operand (x3) instantiations live in their own translation unit (conv_tc_x3.cu includes this file with
+// RAVE_TC_X3_UNIT defined) so that the two sets of ~40 kernels compile in parallel.
+int conv_tc_dispatch_x3(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
+                        cudaStream_t s);
+#ifdef RAVE_TC_X3_UNIT
+int conv_tc_dispatch_x3(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
+                        cudaStream_t s) {
+  return dispatch_all<true>(use2, BK, BN, ta, tb, p, s);
+}
+#endif
+
 }  // namespace tc
 }  // namespace rave
 
+#ifndef RAVE_TC_X3_UNIT
 extern "C" int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dil) {
   if (rave::tc::pick_block_k(Cin) == 0) return 0;
   if (Cout % 16) return 0;
@@ -747,15 +826,17 @@ extern "C" int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, in
   return 1;
 }
 
-extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *bias, const float *res,
-                                  const void *res_bf16, const void *dact_src, const void *res_act, float res_slope,
-                                  float *out_f32, void *out_act,
-                                  int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
-                                  int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
-                                  int out_row_stride, int out_row_offset, const float *fm_d, int fm_bh,
-                                  void *stream) {
+static int conv1d_tc_fwd_impl(const void *xa, const void *wt, const float *bias, const float *res,
+                              const void *res_bf16, const void *dact_src, const void *res_act, float res_slope,
+                              float *out_f32, void *out_act,
+                              int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
+                              int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
+                              int out_row_stride, int out_row_offset, const float *fm_d, int fm_bh,
+                              void *stream, int x3, int act_cs = 0) {
   using namespace rave;
   using namespace rave::tc;
+  RAVE_CHECK_ARG(!x3 || (!res_bf16 && !dact_src && !fm_d),
+                 "conv1d_tc(x3): the split-operand mode has no gradient epilogues (forward path only)");
   RAVE_CHECK_ARG(xa && wt && (out_f32 || out_act), "conv1d_tc: null pointer");
   RAVE_CHECK_ARG(rave_conv1d_tc_supported(Cin, Cout, K, stride, dil), "conv1d_tc: unsupported shape Cin=%d Cout=%d",
                  Cin, Cout);
@@ -802,6 +883,13 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   p.fm_bh = fm_bh > 0 ? fm_bh : 0;                 // fm_bh < 0: every row is a fake row (partner |fm_bh| batches before)
   p.fm_half = (long)(fm_bh > 0 ? fm_bh : -fm_bh) * p.out_rows * Cout;
   p.stages = 0;
+  p.x3 = x3 ? 1 : 0;
+  p.act_ld = x3 ? 2 * Cout : Cout;
+  p.act_cs = act_cs > 0 ? act_cs : Cout;
+  RAVE_CHECK_ARG(!x3 || (Cout % p.act_cs == 0 && p.act_cs % 16 == 0 && (p.act_cs % 32 == 0 || p.act_cs == Cout)),
+                 "conv1d_tc(x3): %d channels per position do not tile the %d-column rows in 32-column chunks", p.act_cs,
+                 Cout);
+  RAVE_CHECK_ARG(!x3 || !res_act || p.act_cs == Cout, "conv1d_tc(x3): res_act needs one position per row");
   p.dbg = 0;
   {
     const char *e = getenv("RAVE_TC_DBG");
@@ -830,8 +918,9 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
   // A: channel-last activations viewed as (c, phase, l/stride, b)
   CUtensorMap ta, tb;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)stride, (cuuint64_t)ceil_div(Lin, stride), (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * stride, (cuuint64_t)Cin * 2 * in_pitch};
+    const cuuint64_t ca = (cuuint64_t)Cin * (x3 ? 2 : 1);       // channels per activation row ([hi | lo] in x3 mode)
+    cuuint64_t dims[4] = {ca, (cuuint64_t)stride, (cuuint64_t)ceil_div(Lin, stride), (cuuint64_t)B};
+    cuuint64_t strides[3] = {ca * 2, ca * 2 * stride, ca * 2 * in_pitch};
     cuuint32_t box[4] = {(cuuint32_t)BK, 1, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(xa), dims, strides, box, estr,
@@ -840,7 +929,7 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map A encode failed (%d)", (int)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)K * Cout};
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)K * Cout * (x3 ? 2 : 1)};
     cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(use2 ? BN / 2 : BN)};
     cuuint32_t estr[2] = {1, 1};
@@ -850,16 +939,36 @@ extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *b
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map B encode failed (%d)", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (use2)
-    return BK == 64 ? dispatch_n2<64>(BN, ta, tb, p, s) : BK == 32 ? dispatch_n2<32>(BN, ta, tb, p, s)
-                                                                   : dispatch_n2<16>(BN, ta, tb, p, s);
-  switch (BK) {
-    case 64: return dispatch_n<64>(BN, ta, tb, p, s);
-    case 32: return dispatch_n<32>(BN, ta, tb, p, s);
-    case 16: return dispatch_n<16>(BN, ta, tb, p, s);
-  }
-  set_error("conv1d_tc: no kernel for BLOCK_K=%d", BK);
-  return 1;
+  if (x3) return conv_tc_dispatch_x3(use2, BK, BN, ta, tb, p, s);
+  return dispatch_all<false>(use2, BK, BN, ta, tb, p, s);
+}
+
+extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *bias, const float *res,
+                                  const void *res_bf16, const void *dact_src, const void *res_act, float res_slope,
+                                  float *out_f32, void *out_act,
+                                  int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
+                                  int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
+                                  int out_row_stride, int out_row_offset, const float *fm_d, int fm_bh,
+                                  void *stream) {
+  return conv1d_tc_fwd_impl(xa, wt, bias, res, res_bf16, dact_src, res_act, res_slope, out_f32, out_act, B, Cin, Lin,
+                            in_pitch, Cout, Lout, K, stride, dil, pad_l, act, slope, out_rows, out_row_stride,
+                            out_row_offset, fm_d, fm_bh, stream, 0);
+}
+
+// Split-operand ("bf16x3") variant: the accurate fast mode.  xa: [B][in_pitch][2*Cin] bf16 rows [hi | lo] with
+// x = hi + lo (16-bit significand), wt: [2][K][Cout][Cin] (all hi slabs, then all lo slabs); the tensor cores accumulate
+// hi*hi + lo*hi + hi*lo in fp32 (relative error ~2^-17 per product instead of 2^-9).  out_act / res_act are [hi | lo]
+// rows of 2*Cout; fp32 tensors as in rave_conv1d_tc_fwd.  act_cs (0 = Cout): channels per position when an output row
+// holds several positions side by side (phase-fused transposed conv): each position is its own [hi | lo] pair.
+// Forward only (no gradient epilogues).
+extern "C" int rave_conv1d_tc_fwd_x3(const void *xa, const void *wt, const float *bias, const float *res,
+                                     const void *res_act, float res_slope, float *out_f32, void *out_act,
+                                     int B, int Cin, int Lin, int in_pitch, int Cout, int Lout,
+                                     int K, int stride, int dil, int pad_l, int act, float slope, int out_rows,
+                                     int out_row_stride, int out_row_offset, int act_cs, void *stream) {
+  return conv1d_tc_fwd_impl(xa, wt, bias, res, nullptr, nullptr, res_act, res_slope, out_f32, out_act, B, Cin, Lin,
+                            in_pitch, Cout, Lout, K, stride, dil, pad_l, act, slope, out_rows, out_row_stride,
+                            out_row_offset, nullptr, 0, stream, 1, act_cs);
 }
 
 // =============================================================================================
@@ -1239,3 +1348,4 @@ extern "C" int rave_tapmajor_to_weight_f32(const float *dwt, float *dw, int Cm, 
   RAVE_CHECK_LAUNCH("tapmajor_to_weight");
   return 0;
 }
+#endif  // RAVE_TC_X3_UNIT

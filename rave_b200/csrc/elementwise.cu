@@ -286,6 +286,32 @@ ncl_to_cl_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ yb, fl
   }
 }
 
+// x3 operand entry: y[b][l][0..C) = bf16(x), y[b][l][C..2C) = bf16(x - hi)
+__global__ void __launch_bounds__(256)
+ncl_to_cl_x3_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, int C, int L) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, l = l0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && l < L) ? x[((size_t)b * C + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = l0 + ty + 8 * i, c = c0 + tx;
+    if (l < L && c < C) {
+      const float v = tile[tx][ty + 8 * i];
+      const size_t o = ((size_t)b * L + l) * (2 * C) + c;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      y[o] = hi;
+      y[o + C] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cl_to_ncl_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int L) {
   __shared__ float tile[32][33];
@@ -316,6 +342,15 @@ extern "C" int rave_ncl_to_cl(const float *x, void *y_bf16, float *y_f32, int B,
   ncl_to_cl_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)y_bf16, y_f32, C, L, act, slope,
                                                             alpha);
   RAVE_CHECK_LAUNCH("ncl_to_cl");
+  return 0;
+}
+
+extern "C" int rave_ncl_to_cl_x3(const float *x, void *y_bf16, int B, int C, int L, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && y_bf16 && B > 0 && C > 0 && L > 0 && B <= 65535, "ncl_to_cl_x3: bad argument");
+  dim3 grid(ceil_div(L, 32), ceil_div(C, 32), B), block(32, 8);
+  ncl_to_cl_x3_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)y_bf16, C, L);
+  RAVE_CHECK_LAUNCH("ncl_to_cl_x3");
   return 0;
 }
 
@@ -506,6 +541,7 @@ struct MtLayer {
 struct MtTable {
   int n;
   int total_rows, total_tiles, maxK;
+  int x3;               // split-operand layouts: out[2][taps][..][..] -- all hi slabs, then all lo slabs
   MtLayer L[MT_MAX];
 };
 
@@ -562,9 +598,16 @@ __global__ void __launch_bounds__(256) mt_prep_kernel(const __grid_constant__ Mt
       const int k = L.tapsA[a];
       for (int r = ty; r < 32; r += 8) {
         const int c0 = c0t + r, c1 = c1t + tx;
-        if (c0 < C0p && c1 < C1p)
-          L.outA[((size_t)a * C0p + c0) * C1p + c1] =
-              __float2bfloat16_rn(k == 255 ? 0.f : sw[r * pitch + tx * K + k] * scale[r]);     // tap -1: zero slab
+        if (c0 < C0p && c1 < C1p) {
+          const float w = k == 255 ? 0.f : sw[r * pitch + tx * K + k] * scale[r];             // tap -1: zero slab
+          const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+          if (t.x3) {
+            L.outA[((size_t)a * C0p + c0) * C1p + c1] = hi;
+            L.outA[((size_t)(L.nA + a) * C0p + c0) * C1p + c1] = __float2bfloat16_rn(w - __bfloat162float(hi));
+          } else {
+            L.outA[((size_t)a * C0p + c0) * C1p + c1] = hi;
+          }
+        }
       }
     }
   }
@@ -573,9 +616,16 @@ __global__ void __launch_bounds__(256) mt_prep_kernel(const __grid_constant__ Mt
       const int k = L.tapsB[b];
       for (int r = ty; r < 32; r += 8) {
         const int c1 = c1t + r, c0 = c0t + tx;
-        if (c0 < C0p && c1 < C1p)
-          L.outB[((size_t)b * C1p + c1) * C0p + c0] =
-              __float2bfloat16_rn(k == 255 ? 0.f : sw[tx * pitch + r * K + k] * scale[tx]);
+        if (c0 < C0p && c1 < C1p) {
+          const float w = k == 255 ? 0.f : sw[tx * pitch + r * K + k] * scale[tx];
+          const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+          if (t.x3) {
+            L.outB[((size_t)b * C1p + c1) * C0p + c0] = hi;
+            L.outB[((size_t)(L.nB + b) * C1p + c1) * C0p + c0] = __float2bfloat16_rn(w - __bfloat162float(hi));
+          } else {
+            L.outB[((size_t)b * C1p + c1) * C0p + c0] = hi;
+          }
+        }
       }
     }
   }
@@ -623,7 +673,7 @@ __global__ void __launch_bounds__(256) mt_wn_bwd_kernel(const __grid_constant__ 
 }  // namespace rave
 
 // Host-side description of one layer (plain C struct of the ABI)
-extern "C" int rave_weight_prep_tc_multi(int n, const rave_wprep_layer *layers, void *stream) {
+static int weight_prep_tc_multi_impl(int n, const rave_wprep_layer *layers, void *stream, int x3) {
   using namespace rave;
   RAVE_CHECK_ARG(n > 0 && n <= MT_MAX && layers, "weight_prep_multi: 1..%d layers per call", MT_MAX);
   MtTable t;
@@ -650,6 +700,7 @@ extern "C" int rave_weight_prep_tc_multi(int n, const rave_wprep_layer *layers, 
     any_g = any_g || h.g;
   }
   t.total_rows = rows; t.total_tiles = tiles; t.maxK = maxK;
+  t.x3 = x3;
   cudaStream_t s = (cudaStream_t)stream;
   if (any_g) {
     mt_rownorm_kernel<<<rows, 256, 0, s>>>(t);
@@ -666,6 +717,15 @@ extern "C" int rave_weight_prep_tc_multi(int n, const rave_wprep_layer *layers, 
     RAVE_CHECK_LAUNCH("mt_prep");
   }
   return 0;
+}
+
+extern "C" int rave_weight_prep_tc_multi(int n, const rave_wprep_layer *layers, void *stream) {
+  return weight_prep_tc_multi_impl(n, layers, stream, 0);
+}
+// split-operand layouts for rave_conv1d_tc_fwd_x3: outA [2][nA][C0p][C1p], outB [2][nB][C1p][C0p] with part 0 = bf16(w),
+// part 1 = bf16(w - part 0)
+extern "C" int rave_weight_prep_tc_multi_x3(int n, const rave_wprep_layer *layers, void *stream) {
+  return weight_prep_tc_multi_impl(n, layers, stream, 1);
 }
 
 extern "C" int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers, void *stream) {

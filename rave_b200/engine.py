@@ -36,9 +36,13 @@ C1_GROUP = int(_os.environ.get("RAVE_C1_GROUP", "4"))
 
 
 def set_precision(mode: str) -> None:
-    """'fp32' : CUDA-core parity kernels ([B,C,L] fp32, per-layer autograd);
-    'bf16' : tcgen05 engine (bf16 operands, fp32 accumulate) for every chain it supports."""
-    if mode not in ("fp32", "bf16"):
+    """'fp32'   : CUDA-core parity kernels ([B,C,L] fp32, per-layer autograd);
+    'bf16'   : tcgen05 engine (bf16 operands, fp32 accumulate) for every chain it supports (~1e-2 rel-L2 end to end);
+    'bf16x3' : the accurate fast mode -- the same tcgen05 kernels on split operands (x = hi + lo, three MMAs per
+               product: hi*hi + lo*hi + hi*lo, fp32 accumulate), <= 1e-4 rel-L2 end to end like the fp32 path, for the
+               FORWARD of the encoder / generator chains (no autograd graph: inference, validation, export warm-up);
+               anything that needs gradients runs on the fp32 kernels in this mode."""
+    if mode not in ("fp32", "bf16", "bf16x3"):
         raise ValueError(mode)
     _state["precision"] = mode
 
@@ -272,7 +276,8 @@ class _PreparedWeights:
         if len(self.tapsB) > 32:
             raise _lib.RaveB200Error(f"phase-fused layout of K={K}, stride={s} needs {len(self.tapsB)} > 32 slabs")
 
-    def finalize(self, norm, outA, outB):
+    def finalize(self, norm, outA, outB, parts: int = 1):
+        """parts = 2: split-operand layouts, [all hi slabs | all lo slabs] along the leading axis."""
         spec = self.spec
         self.norm = norm
         if spec.kind == "conv":
@@ -281,36 +286,38 @@ class _PreparedWeights:
                 if spec.stride == 1:
                     self.dgrad = outB
                 else:       # [J*stride][Cin_p][Cout_p] -> [J][stride*Cin_p][Cout_p]
-                    self.dgrad_fused = outB.view(self.fused_J, spec.stride * self.C1p, self.C0p)
+                    self.dgrad_fused = outB.view(parts * self.fused_J, spec.stride * self.C1p, self.C0p)
         else:               # [J*stride][Cout_p][Cin_p] -> [J][stride*Cout_p][Cin_p]
-            self.fwd_fused = outB.view(self.fused_J, spec.stride * self.C1p, self.C0p)
+            self.fwd_fused = outB.view(parts * self.fused_J, spec.stride * self.C1p, self.C0p)
             self.dgrad = outA
         return self
 
 
-def prepare_layers(jobs):
+def prepare_layers(jobs, x3: bool = False):
     """jobs: list of (spec, v, g, need_dgrad, need_fwd).  Returns the list of _PreparedWeights, re-using the
     per-module cache (keyed on parameter versions; bypassed while a CUDA graph is being captured) and
-    preparing all misses with one multi-tensor launch pair."""
+    preparing all misses with one multi-tensor launch pair.  x3: split-operand ([hi slabs | lo slabs]) layouts."""
     out = [None] * len(jobs)
     todo = []
     for i, (spec, v, g, need_dgrad, need_fwd) in enumerate(jobs):
         capturing = v.is_cuda and torch.cuda.is_current_stream_capturing()
         key = (v._version, g._version if g is not None else -1, need_dgrad, need_fwd, str(ACT_DTYPE), str(v.device),
-               v.data_ptr(), _state["prep_epoch"])
+               v.data_ptr(), _state["prep_epoch"], x3)
+        slot = "_tc_prep_x3" if x3 else "_tc_prep"
         if not capturing:
-            hit = spec.module.__dict__.get("_tc_prep")
+            hit = spec.module.__dict__.get(slot)
             if hit is not None and hit[0] == key:
                 out[i] = hit[1]
                 continue
         todo.append((i, key, capturing, _PreparedWeights(spec, need_dgrad, need_fwd), v, g))
     work = [(i, key, cap, pw, v, g) for (i, key, cap, pw, v, g) in todo if pw.tapsA or pw.tapsB]
     if work:
-        res = ops.weight_prep_tc_multi([(v, g, pw.tapsA, pw.tapsB, pw.C0p, pw.C1p) for (_, _, _, pw, v, g) in work])
+        res = ops.weight_prep_tc_multi([(v, g, pw.tapsA, pw.tapsB, pw.C0p, pw.C1p) for (_, _, _, pw, v, g) in work],
+                                       x3=x3)
         for (i, key, cap, pw, v, g), (norm, outA, outB) in zip(work, res):
-            out[i] = pw.finalize(norm, outA, outB)
+            out[i] = pw.finalize(norm, outA, outB, 2 if x3 else 1)
             if not cap:
-                pw.spec.module.__dict__["_tc_prep"] = (key, out[i])
+                pw.spec.module.__dict__["_tc_prep_x3" if x3 else "_tc_prep"] = (key, out[i])
     for (i, key, cap, pw, v, g) in todo:
         if out[i] is None:            # nothing to re-layout (a c1 layer without dgrad): only the norm
             pw.norm = ops.weight_norm_raw(v, g)[1] if g is not None else None
@@ -346,10 +353,16 @@ class TcChainFn(torch.autograd.Function):
                    tensors (RAVE._fused_feature_matching), whose gradients drive fm_grad / score_grad here."""
 
     @staticmethod
-    def forward(ctx, x_in, specs, L0, fm, src, fake_grad_only, *flat):
+    def forward(ctx, x_in, specs, L0, fm, src, fake_grad_only, x3, *flat):
         n = len(specs)
         ctx.set_materialize_grads(False)
         need_dgrad = x_in.requires_grad or any(t is not None and t.requires_grad for t in flat)
+        if x3:
+            # split-operand mode: forward chains only (x_in rows are [hi | lo]); the caller keeps autograd away
+            if fm or x_in.dim() == 2:
+                raise _lib.RaveB200Error("bf16x3: discriminator chains are not run in the split-operand mode")
+            need_dgrad = False
+        AW = 2 if x3 else 1                    # operand row width multiplier
         c1 = x_in.dim() == 2
         period, pool = src if (c1 and src is not None) else (1, 1)
         B = x_in.shape[0] * period
@@ -368,7 +381,7 @@ class TcChainFn(torch.autograd.Function):
         stats = torch.zeros(max(n - 1, 1), 2, dtype=torch.float32, device=dev) if fm else None
         prepared = prepare_layers([(s, flat[3 * i].detach(), flat[3 * i + 1].detach() if flat[3 * i + 1] is not None
                                     else None, need_dgrad and not (c1 and i == 0), not (c1 and i == 0))
-                                   for i, s in enumerate(specs)])
+                                   for i, s in enumerate(specs)], x3=x3)
         for i, s in enumerate(specs):
             v, g, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
             use_c1 = c1 and i == 0
@@ -395,7 +408,7 @@ class TcChainFn(torch.autograd.Function):
             elif s.res_src is not None:
                 res = f32[s.res_src]
             out_f32 = torch.empty(B, pitch, cout_p, dtype=torch.float32, device=dev) if want_f32 else None
-            out_act = torch.empty(B, pitch, cout_p, dtype=ACT_DTYPE, device=dev) if want_act else None
+            out_act = torch.empty(B, pitch, AW * cout_p, dtype=ACT_DTYPE, device=dev) if want_act else None
             if pitch > Lout:
                 for t in (out_f32, out_act):
                     if t is not None:
@@ -432,7 +445,7 @@ class TcChainFn(torch.autograd.Function):
             elif s.kind == "conv":
                 ops.conv1d_tc(a, pw.fwd, bias_p, res, s.stride, s.dil, s.pad, act_code, act_slope,
                               want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act, Lout=Lout,
-                              Lin=Lin, out_rows=pitch, res_act=res_act, res_slope=res_slope)
+                              Lin=Lin, out_rows=pitch, res_act=res_act, res_slope=res_slope, x3=x3)
             else:
                 # transposed conv: the `stride` output phases side by side in one stride-1 conv (output row q =
                 # positions q*stride .. q*stride + stride-1: the same bytes as the [B][pitch][Cout] tensor)
@@ -444,8 +457,8 @@ class TcChainFn(torch.autograd.Function):
                 ops.conv1d_tc(a, pw.fwd_fused, bias_f, None, 1, 1, (pw.fused_pad, 0), act_code, act_slope,
                               want_f32=False, want_act=False,
                               out_f32=out_f32.view(B, rows_q, st * cout_p) if out_f32 is not None else None,
-                              out_act=out_act.view(B, rows_q, st * cout_p) if out_act is not None else None,
-                              out_rows=rows_q, Lout=rows_q, Lin=Lin)
+                              out_act=out_act.view(B, rows_q, st * AW * cout_p) if out_act is not None else None,
+                              out_rows=rows_q, Lout=rows_q, Lin=Lin, x3=x3, act_cs=cout_p if x3 else 0)
                 if pitch > Lout:         # positions beyond the true length were computed too: back to zero
                     for t in (out_f32, out_act):
                         if t is not None:
@@ -661,11 +674,11 @@ class TcChainFn(torch.autograd.Function):
             for job, (dv, dg) in zip(wn_jobs, res):
                 i = job[0]
                 grads[3 * i], grads[3 * i + 1] = dv, dg
-        return (gx, None, None, None, None, None) + tuple(grads)
+        return (gx, None, None, None, None, None, None) + tuple(grads)
 
 
 def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None, fm: bool = False,
-              src: Optional[Tuple[int, int]] = None, fake_grad_only: bool = False):
+              src: Optional[Tuple[int, int]] = None, fake_grad_only: bool = False, x3: bool = False):
     """x_cl_bf16: [B, pitch, Cin(+pad)] (rows beyond the true length L0 must be zero), or raw fp32 rows
     [B, pitch] for a Cin = 1 first layer.  Returns one fp32 channel-last tensor [B, pitch_i, Cout_i(+pad)]
     per output layer (slice [:, :L_i, :Cout_i]); with fm=True: (stats [n-1, 2], score_stats [3, 2], last layer
@@ -676,7 +689,7 @@ def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int]
         flat += [v, g, b]
     if L0 is None:
         L0 = x_cl_bf16.shape[1]
-    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, src, fake_grad_only, *flat)
+    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, src, fake_grad_only, x3, *flat)
 
 
 def chain_lengths(specs: List[LayerSpec], L0: int) -> List[int]:
@@ -716,7 +729,13 @@ class _FromChannelLast(torch.autograd.Function):
         return gf
 
 
-def to_channel_last(x, cpad=0):
+def to_channel_last(x, cpad=0, x3=False):
+    if x3:                       # split operand rows [hi | lo]; forward-only path, no autograd node
+        y = ops.ncl_to_cl_x3(x.detach())
+        if cpad:
+            B, L, C2 = y.shape
+            y = nn.functional.pad(y.view(B, L, 2, C2 // 2), (0, cpad)).reshape(B, L, C2 + 2 * cpad)
+        return y
     return _ToChannelLast.apply(x, cpad)
 
 

@@ -375,6 +375,15 @@ def ncl_to_cl(x, act=ACT_NONE, slope=0.2, alpha=None, want_bf16=True, want_f32=F
     return yb, yf
 
 
+def ncl_to_cl_x3(x):
+    """[B,C,L] fp32 -> channel-last split operand [B,L,2C] bf16: [hi = bf16(x) | lo = bf16(x - hi)]."""
+    x = _f32c(x)
+    B, C, L = x.shape
+    y = torch.empty(B, L, 2 * C, dtype=torch.bfloat16, device=x.device)
+    call("rave_ncl_to_cl_x3", ptr(x), ptr(y), B, C, L, stream_ptr())
+    return y
+
+
 def cl_to_ncl(x_cl):
     """[B,L,C] fp32 -> [B,C,L] fp32."""
     x_cl = _f32c(x_cl)
@@ -391,7 +400,7 @@ def conv1d_tc_supported(Cin, Cout, K=1, stride=1, dil=1):
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=ACT_NONE, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
               out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2,
-              fm_d=None, fm_partner=None):
+              fm_d=None, fm_partner=None, x3=False, act_cs=0):
     """xa_cl [B,Lin,Cin] bf16 (activated operand), wt [K,Cout,Cin] bf16 -> (out_f32 [B,Lout,Cout] fp32,
     out_act [B,Lout,Cout] bf16 = act(out)); either may be None.  fm_d (2 device floats): fused feature-matching
     gradient of a [real; fake] batch, see include/rave_b200.h; with fm_partner (the real rows, stored right before
@@ -400,6 +409,11 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     if Lin is None:
         Lin = in_pitch
     K, Cout, Cin_w = wt.shape
+    if x3:                                   # split operands: rows [hi | lo] of 2*Cin, weights [2][K][Cout][Cin]
+        if Cin % 2 or K % 2:
+            raise _lib.RaveB200Error("conv1d_tc(x3): operands must be [hi | lo] pairs")
+        Cin //= 2
+        K //= 2
     if Cin_w != Cin or xa_cl.dtype != torch.bfloat16 or wt.dtype != torch.bfloat16:
         raise _lib.RaveB200Error("conv1d_tc: operand mismatch")
     if Lout is None:
@@ -408,7 +422,14 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty(B, rows, Cout, dtype=torch.float32, device=xa_cl.device)
     if want_act and out_act is None:
-        out_act = torch.empty(B, rows, Cout, dtype=torch.bfloat16, device=xa_cl.device)
+        out_act = torch.empty(B, rows, Cout * (2 if x3 else 1), dtype=torch.bfloat16, device=xa_cl.device)
+    if x3:
+        if res_bf16 is not None or dact_src is not None or fm_d is not None:
+            raise _lib.RaveB200Error("conv1d_tc(x3): forward path only")
+        call("rave_conv1d_tc_fwd_x3", ptr(xa_cl), ptr(wt), ptr(bias), ptr(res_cl), ptr(res_act), float(res_slope),
+             ptr(out_f32), ptr(out_act), B, Cin, Lin, in_pitch, Cout, Lout, K, stride, dil, pad[0], act, float(slope),
+             out_rows, out_row_stride, out_row_offset, act_cs, stream_ptr())
+        return out_f32, out_act
     fm_bh = 0
     if fm_d is not None:
         fm_bh = B // 2
@@ -717,9 +738,11 @@ def rfft(x, w):
 # multi-tensor weight preparation / weight-norm backward (one launch pair per chain)
 # ----------------------------------------------------------------------------------------------
 
-def weight_prep_tc_multi(items):
+def weight_prep_tc_multi(items, x3=False):
     """items: list of (v, g, tapsA, tapsB, C0p, C1p).  Returns a list of (norm, outA, outB) exactly like
-    weight_prep_tc, using ONE row-norm launch and ONE re-layout launch for (up to 64 of) the layers."""
+    weight_prep_tc, using ONE row-norm launch and ONE re-layout launch for (up to 64 of) the layers.
+    x3: split-operand layouts, outA [2 * nA][C0p][C1p] / outB [2 * nB][C1p][C0p] = all hi slabs, then all lo slabs."""
+    P = 2 if x3 else 1
     outs = []
     recs = []
     for (v, g, tapsA, tapsB, C0p, C1p) in items:
@@ -729,8 +752,8 @@ def weight_prep_tc_multi(items):
         K = v.numel() // (C0 * C1)
         dev = v.device
         norm = torch.empty(C0, dtype=torch.float32, device=dev) if g is not None else None
-        outA = torch.empty(len(tapsA), C0p, C1p, dtype=torch.bfloat16, device=dev) if tapsA else None
-        outB = torch.empty(len(tapsB), C1p, C0p, dtype=torch.bfloat16, device=dev) if tapsB else None
+        outA = torch.empty(P * len(tapsA), C0p, C1p, dtype=torch.bfloat16, device=dev) if tapsA else None
+        outB = torch.empty(P * len(tapsB), C1p, C0p, dtype=torch.bfloat16, device=dev) if tapsB else None
         outs.append((norm, outA, outB))
         recs.append((v, g, norm, outA, outB, tapsA, tapsB, C0, C1, K, C0p, C1p))
     for i0 in range(0, len(recs), 64):
@@ -743,7 +766,7 @@ def weight_prep_tc_multi(items):
                 L.tapsA[j] = t
             for j, t in enumerate(tapsB):
                 L.tapsB[j] = t
-        call("rave_weight_prep_tc_multi", len(chunk), arr, stream_ptr())
+        call("rave_weight_prep_tc_multi_x3" if x3 else "rave_weight_prep_tc_multi", len(chunk), arr, stream_ptr())
     return outs
 
 

@@ -15,7 +15,10 @@ def _bf16(t):
 def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), act=0, slope=0.2,
               want_f32=True, want_act=False, out_f32=None, out_act=None, out_rows=0, out_row_stride=0,
               out_row_offset=0, Lout=None, res_bf16=None, dact_src=None, Lin=None, res_act=None, res_slope=0.2,
-              fm_d=None, fm_partner=None):
+              fm_d=None, fm_partner=None, x3=False, act_cs=0):
+    if x3:
+        return _conv1d_tc_x3(xa_cl, wt, bias, res_cl, stride, dil, pad, act, slope, out_f32, out_act, out_rows, Lout,
+                             Lin, res_act, res_slope, act_cs)
     B, in_pitch, Cin = xa_cl.shape
     Lin = in_pitch if Lin is None else Lin
     K, Cout, _ = wt.shape
@@ -74,6 +77,58 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
         a = F.leaky_relu(v, slope) if act == 1 else v
         out_act[:, idx] = _bf16(a)
     return out_f32, out_act
+
+
+def _split(v):
+    hi = v.to(torch.bfloat16)
+    lo = (v - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def _conv1d_tc_x3(xa_cl, wt, bias, res_cl, stride, dil, pad, act, slope, out_f32, out_act, out_rows, Lout, Lin, res_act,
+                  res_slope, act_cs):
+    """Split-operand semantics of rave_conv1d_tc_fwd_x3 (include/rave_b200.h): rows [hi | lo], weights [2][K][Cout][Cin],
+    hi*hi + lo*hi + hi*lo accumulated in fp32; out_act positions are [hi | lo] pairs of act_cs channels."""
+    B, in_pitch, C2 = xa_cl.shape
+    Cin = C2 // 2
+    K = wt.shape[0] // 2
+    Cout = wt.shape[1]
+    a_hi, a_lo = xa_cl[..., :Cin].float(), xa_cl[..., Cin:].float()
+    w_hi, w_lo = wt[:K].float(), wt[K:].float()
+    saved = OPERAND_DTYPE
+
+    def run(a, w):
+        o, _ = conv1d_tc(a.to(torch.bfloat16), w.to(torch.bfloat16), None, None, stride, dil, pad, 0, slope,
+                         want_f32=True, want_act=False, out_rows=out_rows, Lout=Lout, Lin=Lin)
+        return o
+    v = run(a_hi, w_hi) + run(a_lo, w_hi) + run(a_hi, w_lo)
+    rows = v.shape[1]
+    LoutE = Lout if Lout is not None else rows
+    if bias is not None:
+        v[:, :LoutE] += bias
+    if res_act is not None:
+        ra = res_act[..., :Cout].float() + res_act[..., Cout:].float()
+        v[:, :LoutE] += torch.where(ra > 0, ra, ra / res_slope)[:, :LoutE]
+    if res_cl is not None:
+        v[:, :LoutE] += res_cl[:, :LoutE]
+    if out_f32 is not None:
+        out_f32[:, :LoutE] = v[:, :LoutE]
+    else:
+        out_f32 = None
+    if out_act is not None:
+        a = F.leaky_relu(v, slope) if act == 1 else v
+        cs = act_cs if act_cs else Cout
+        hi, lo = _split(a)
+        q = Cout // cs
+        pair = torch.stack([hi.reshape(B, rows, q, cs), lo.reshape(B, rows, q, cs)], 3)      # [B, rows, q, 2, cs]
+        out_act[:, :LoutE] = pair.reshape(B, rows, 2 * Cout)[:, :LoutE]
+    return out_f32, out_act
+
+
+def ncl_to_cl_x3(x):
+    xt = x.permute(0, 2, 1).contiguous()
+    hi, lo = _split(xt)
+    return torch.cat([hi, lo], -1)
 
 
 def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None, dbias=None):
@@ -284,8 +339,20 @@ def score_grad(score_cl, dstats6, L):
     return g.to(engine.ACT_DTYPE)
 
 
-def weight_prep_tc_multi(items):
-    return [weight_prep_tc(*it) for it in items]
+def weight_prep_tc_multi(items, x3=False):
+    if not x3:
+        return [weight_prep_tc(*it) for it in items]
+    out = []
+    saved = globals()["OPERAND_DTYPE"]
+    globals()["OPERAND_DTYPE"] = torch.float32            # keep fp32, then split into [hi slabs | lo slabs]
+    try:
+        for it in items:
+            norm, A, Bm = weight_prep_tc(*it)
+            cat = lambda t: None if t is None else torch.cat(_split(t.float()), 0)
+            out.append((norm, cat(A), cat(Bm)))
+    finally:
+        globals()["OPERAND_DTYPE"] = saved
+    return out
 
 
 def weight_norm_bwd_multi(items):
@@ -306,5 +373,5 @@ def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
                  "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1", "weight_prep_tc_multi",
-                 "weight_norm_bwd_multi", "score_stats", "score_grad"):
+                 "weight_norm_bwd_multi", "score_stats", "score_grad", "ncl_to_cl_x3"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -222,3 +222,35 @@ def test_wide_wgrad_slots_cover_every_tap_once(K, stride, pad):
         j, p = sl // stride - pad_l, sl % stride
         for l in range(5):
             assert (l + j) * stride + p == l * stride + k - pad
+
+
+def test_split_operand_chain_reaches_fp32_accuracy(monkeypatch):
+    """bf16x3 (x = hi + lo, hi*hi + lo*hi + hi*lo in fp32): the encoder and generator chains through the engine with
+    the kernels emulated must sit within 1e-4 rel-L2 of the fp32 oracle (the north-star tolerance; single-pass bf16
+    gives ~1e-2) -- checks the planning / layouts of the split mode (weights [hi slabs | lo slabs], [hi | lo] rows,
+    per-position pairs after a phase-fused transposed conv, residual recovered from hi + lo)."""
+    from rave_b200 import configs, engine
+    tc_emulator.install(monkeypatch)
+    torch.manual_seed(1)
+    _, enc, dec = configs.make_autoencoder("v2", capacity=16, latent_size=16)
+    sd = {"encoder." + k: v.detach().clone() for k, v in enc.state_dict().items()}
+    sd.update({"decoder." + k: v.detach().clone() for k, v in dec.state_dict().items()})
+    cfg = O.ArchConfig(capacity=16, latent_size=16)
+    B, L = 2, 512
+    x_mb = torch.randn(B, 16, L)
+    with torch.no_grad():
+        specs = enc.encoder.net._tc_plan()
+        z_o = O.encoder_v2(x_mb, sd, "encoder.encoder.", cfg)
+        (out,) = engine.run_chain(engine.to_channel_last(x_mb, x3=True), specs, x3=True)
+        z = engine.from_channel_last(out[:, :engine.chain_lengths(specs, L)[-1]].contiguous())
+        assert z.shape == z_o.shape
+        print("bf16x3 encoder rel-L2", rel_l2(z, z_o))
+        assert rel_l2(z, z_o) < 5e-5
+        specs = dec.net._tc_plan()
+        zin = torch.randn(B, 16, z_o.shape[-1])
+        taps = {}
+        O.generator_v2(zin, sd, "decoder.", cfg, taps)
+        (out,) = engine.run_chain(engine.to_channel_last(zin, x3=True), specs, x3=True)
+        w = engine.from_channel_last(out[:, :engine.chain_lengths(specs, zin.shape[-1])[-1]].contiguous())
+        print("bf16x3 generator rel-L2", rel_l2(w, taps["wave"]))
+        assert rel_l2(w, taps["wave"]) < 5e-5
