@@ -158,6 +158,9 @@ int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, i
  * Requirements: Cin % 16 == 0, Cout % 16 == 0.
  * ------------------------------------------------------------------------------------------- */
 int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dil);
+/* kernel instance rave_conv1d_tc_fwd selects for a shape: BLOCK_N | BLOCK_K << 12 | (CTA pair ? 1 << 24 : 0), 0 = none
+ * (bench.py names the dominant kernel with it) */
+int rave_conv1d_tc_plan(int B, int Cin, int Cout, int Lout);
 int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bias, const float *res,
                        const void *res_bf16, const void *dact_src_bf16, const void *res_act_bf16, float res_slope,
                        float *out_f32, void *out_act_bf16,

@@ -424,8 +424,17 @@ class DiscreteEncoder(nn.Module):
         self.register_buffer("enabled", torch.tensor(0))
         self.noise_augmentation = noise_augmentation
 
+    def _enabled_host(self) -> bool:
+        """Host copy of the `enabled` buffer (re-read only when the buffer was written: no device sync per step, and a
+        captured CUDA graph never touches it)."""
+        t = self.enabled
+        hit = self.__dict__.get("_enabled_cache")
+        if hit is None or hit[0] is not t or hit[1] != t._version:
+            hit = self.__dict__["_enabled_cache"] = (t, t._version, bool(t.item()))
+        return hit[2]
+
     def reparametrize(self, z):
-        if self.enabled:
+        if self._enabled_host():
             z, diff, _ = self.rvq(z)
         else:
             diff = torch.zeros_like(z).mean()

@@ -826,6 +826,25 @@ extern "C" int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, in
   return 1;
 }
 
+// Which kernel instance rave_conv1d_tc_fwd runs for a shape: BLOCK_N | BLOCK_K << 12 | (CTA pair ? 1 << 24 : 0); 0 = none.
+extern "C" int rave_conv1d_tc_plan(int B, int Cin, int Cout, int Lout) {
+  using namespace rave;
+  using namespace rave::tc;
+  const int BK = pick_block_k(Cin);
+  if (!BK || Cout % 16) return 0;
+  int BL = 128;
+  while (BL > Lout && BL > 8) BL >>= 1;
+  const long m_tiles = (long)ceil_div(Lout, BL) * ceil_div(B, 128 / BL);
+  const char *e = getenv("RAVE_TC_2CTA");
+  const bool want2 = !(e && e[0] == '0');
+  int BN = 0;
+  if (want2 && m_tiles >= 2) BN = pick_block_n2(Cout, m_tiles);
+  if (!BN) BN = pick_block_n(Cout, m_tiles);
+  if (!BN) return 0;
+  const bool use2 = want2 && (BN % 32 == 0) && BN >= 64 && m_tiles >= 2;
+  return BN | (BK << 12) | (use2 ? 1 << 24 : 0);
+}
+
 static int conv1d_tc_fwd_impl(const void *xa, const void *wt, const float *bias, const float *res,
                               const void *res_bf16, const void *dact_src, const void *res_act, float res_slope,
                               float *out_f32, void *out_act,

@@ -155,14 +155,13 @@ def test_cuda_graph_training_matches_eager(streams, monkeypatch):
     # freeze the reparametrisation noise so both runs see the same numbers
     for m in (m1, m2):
         m.encoder.reparametrize = (lambda z, eps=None, enc=m.encoder: type(enc).reparametrize(enc, z, torch.zeros_like(z[:, :z.shape[1] // 2])))
+    w_before = m2.decoder.net[0].weight_v.detach().clone()
     tr = GraphedTrainer(m2, x, warmup_steps=2)
-    # eager twin performs the same updates as the trainer's warm-up: 2 rounds of (D, G); capture itself
-    # executes nothing
+    # the trainer's eager warm-up is undone (parameters, buffers, optimiser state restored) and capture itself executes
+    # nothing: the twin starts from the same state without any catching up
+    assert torch.equal(w_before, m2.decoder.net[0].weight_v)
     monkeypatch.setenv("RAVE_DISC_STREAMS", "1")
     m1.optimizers(capturable=True)
-    for _ in range(2):
-        m1.train_body(x, True)
-        m1.train_body(x, False)
     for i in range(4):
         la = tr.step(x, i)
         lb = m1.training_step(x, i)
@@ -172,3 +171,77 @@ def test_cuda_graph_training_matches_eager(streams, monkeypatch):
     w1 = m1.decoder.net[0].weight_v
     w2 = m2.decoder.net[0].weight_v
     assert rel_l2(w2, w1) < 1e-2
+
+
+# ------------------------------------------------------------------------------------ the benched configuration
+def test_autoencoder_capacity96_bf16_vs_oracle():
+    """BASELINE config 3's encoder / generator at FULL width (capacity 96: the 96/192/384/768-channel stages, 1536-channel
+    up/down convs) and full length (T = 65536), bf16 engine against the fp32 CPU oracle, forward and every gradient.
+    Also bounds the drift of the bf16 residual stream (the skip is recovered from the unit's bf16 operand) over the 11
+    residual blocks of each stack.  Per-tensor numbers are printed (pytest -s)."""
+    from rave_b200 import configs
+    from rave_b200.model import _pqmf_decode, _pqmf_encode
+    torch.manual_seed(0)
+    pq, enc, dec = configs.make_autoencoder("v2")
+    holder = nn.Module()
+    holder.pqmf, holder.encoder, holder.decoder = pq, enc, dec
+    sd = {k: v.detach().clone() for k, v in holder.state_dict().items()}
+    B, T = 2, 65536
+    x = (0.5 * torch.randn(B, 1, T, generator=torch.Generator().manual_seed(1234))).clamp(-1, 1)
+    cfg = O.ArchConfig()
+    eps = torch.randn(B, 128, 32, generator=torch.Generator().manual_seed(4321))
+    probe = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(7))
+    params_o = {k: v.clone().requires_grad_(v.is_floating_point() and not k.startswith("pqmf")) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    taps = {}
+    y_o = O.rave_forward(xo, params_o, cfg, eps, taps)
+    names = sorted(k for k, v in params_o.items() if v.requires_grad)
+    grads_o = torch.autograd.grad((y_o * probe).sum(), [xo] + [params_o[k] for k in names])
+    holder.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    z = enc(_pqmf_encode(pq, xg))
+    zs, _ = enc.reparametrize(z, eps.cuda())
+    y = _pqmf_decode(pq, dec(zs), batch_size=xg.shape[:-2], n_channels=1)
+    rz, ry = rel_l2(z, taps["z"]), rel_l2(y, y_o)
+    print(f"capacity 96 bf16: z rel-L2 {rz:.3e}  y rel-L2 {ry:.3e}")
+    assert rz < FWD_TOL and ry < FWD_TOL
+    pg = dict(enc.named_parameters(prefix="encoder"))
+    pg.update(dict(dec.named_parameters(prefix="decoder")))
+    grads_g = torch.autograd.grad((y * probe.cuda()).sum(), [xg] + [pg[k] for k in names])
+    print(f"  grad_x rel-L2 {rel_l2(grads_g[0], grads_o[0]):.3e} cos {cos(grads_g[0], grads_o[0]):.4f}")
+    assert rel_l2(grads_g[0], grads_o[0]) < BWD_TOL and cos(grads_g[0], grads_o[0]) > 0.98
+    ga = torch.cat([a.detach().cpu().reshape(-1) for a in grads_g[1:]])
+    gb = torch.cat([b.reshape(-1) for b in grads_o[1:]])
+    print(f"  all parameter gradients: rel-L2 {rel_l2(ga, gb):.3e} cos {cos(ga, gb):.4f}")
+    assert cos(ga, gb) > 0.99 and rel_l2(ga, gb) < 0.15
+    worst = min((cos(a, b), k) for k, a, b in zip(names, grads_g[1:], grads_o[1:]))
+    print(f"  worst tensor: cos {worst[0]:.4f} ({worst[1]})")
+    for k, a, b in zip(names, grads_g[1:], grads_o[1:]):
+        assert cos(a, b) > 0.93, (k, cos(a, b), rel_l2(a, b))
+
+
+def test_discriminator_capacity96_bf16_vs_oracle():
+    """BASELINE config 3's MPD + MSD at capacity 96 (the 96/192/384/768-channel k15 / (5,1) layers), [real; fake] batch
+    of 2 + 2 x 65536, fused feature-matching path of the bf16 engine against the oracle's losses and input gradient."""
+    from rave_b200 import configs
+    torch.manual_seed(5)
+    m = configs.build_rave("v2").cuda().train()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items() if k.startswith("discriminator.")}
+    xy = (0.5 * torch.randn(4, 1, 65536, generator=torch.Generator().manual_seed(11))).clamp(-1, 1)
+    xo = xy.clone().requires_grad_(True)
+    feats_o = O.combine_discriminators_v2(xo, sd)
+    fm_o, ld_o, la_o = O.gan_losses(feats_o, 1, True)
+    (gx_o,) = torch.autograd.grad(20 * fm_o + la_o, xo)
+    for p in m.discriminator.parameters():
+        p.requires_grad_(False)                      # generator step: frozen discriminator
+    xg = xy.cuda().requires_grad_(True)
+    assert m.discriminator.supports_fused_fm(xg)
+    fm, ld, la, pr, pf = m._fused_feature_matching(xg, fake_grad_only=True)
+    print(f"capacity 96 disc bf16: fm {float(fm):.5f} vs {float(fm_o):.5f}; loss_dis {float(ld):.5f} vs {float(ld_o):.5f}; "
+          f"adv {float(la):.5f} vs {float(la_o):.5f}")
+    assert rel_l2(fm, fm_o) < FWD_TOL and rel_l2(ld, ld_o) < FWD_TOL and abs(float(la) - float(la_o)) < 5e-2 * max(1.0, abs(float(la_o)))
+    (gx,) = torch.autograd.grad(20 * fm + la, xg)
+    half = xy.shape[0] // 2
+    c, r = cos(gx[half:], gx_o[half:]), rel_l2(gx[half:], gx_o[half:])
+    print(f"  fake-half input gradient: cos {c:.4f} rel-L2 {r:.3e}")
+    assert c > 0.9
