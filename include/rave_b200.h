@@ -308,6 +308,18 @@ int rave_weight_to_tapmajor_bf16(const float *w, void *wt_bf16, int Cout, int Ci
                                  int flip, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * NoiseGeneratorV2 tail (rave/blocks.py:284-292 + mod_sigmoid / amp_to_impulse_response / fft_convolve,
+ * rave/core.py:20-21,48-81) as ONE kernel:  amp = 2 sigmoid(h - 5)^2.3 + 1e-7;  ir = M amp (M [TS][NB]: the linear
+ * irfft -> roll -> hann -> crop/pad -> roll pipeline applied to the identity, built by the host);
+ * out[b][c][t*TS + i] = sum_{j<=i} noise[b][t][c][j] ir[i-j].  h [B][C*NB][T], noise [B][T][C][TS], out [B][C][T*TS].
+ * TS <= 16, NB <= 64.  bwd: gradient with respect to h (noise is a constant).
+ * ------------------------------------------------------------------------------------------- */
+int rave_noise_fir_fwd(const float *h, const float *M, const float *noise, float *out, int B, int C, int NB, int T,
+                       int TS, void *stream);
+int rave_noise_fir_bwd(const float *h, const float *M, const float *noise, const float *dout, float *dh, int B, int C,
+                       int NB, int T, int TS, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-tensor Adam, torch.optim.Adam arithmetic without weight decay / amsgrad (rave/model.py:226-236):
  *   step += 1;  m = lerp(m, g, 1-b1);  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
  * n fp32 tensors given by host arrays of device pointers; lr and step are single device floats (graph-replayable).

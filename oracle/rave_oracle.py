@@ -642,3 +642,56 @@ def train_step_cpu(x: Tensor, sd, cfg: ArchConfig, eps: Tensor, dis_step: bool, 
     if return_named:
         return total.detach(), loss_dis.detach(), dict(zip(names, grads))
     return total.detach(), loss_dis.detach(), grads
+
+
+# ----------------------------------------------------------------------------------
+# NoiseGeneratorV2 (rave/blocks.py:243-292; helpers rave/core.py:20-21, 48-81) ------
+# ----------------------------------------------------------------------------------
+
+
+def mod_sigmoid(x: Tensor) -> Tensor:
+    """rave/core.py:20-21."""
+    return 2 * torch.sigmoid(x) ** 2.3 + 1e-7
+
+
+def amp_to_impulse_response(amp: Tensor, target_size: int) -> Tensor:
+    """rave/core.py:48-69: zero-phase amplitudes -> irfft -> centre -> hann -> pad / crop -> un-centre."""
+    amp = torch.view_as_complex(torch.stack([amp, torch.zeros_like(amp)], -1))
+    amp = torch.fft.irfft(amp)
+    filter_size = amp.shape[-1]
+    amp = torch.roll(amp, filter_size // 2, -1)
+    amp = amp * torch.hann_window(filter_size, dtype=amp.dtype, device=amp.device)
+    amp = F.pad(amp, (0, int(target_size) - int(filter_size)))
+    return torch.roll(amp, -filter_size // 2, -1)
+
+
+def fft_convolve(signal: Tensor, kernel: Tensor) -> Tensor:
+    """rave/core.py:71-81."""
+    signal = F.pad(signal, (0, signal.shape[-1]))
+    kernel = F.pad(kernel, (kernel.shape[-1], 0))
+    output = torch.fft.irfft(torch.fft.rfft(signal) * torch.fft.rfft(kernel))
+    return output[..., output.shape[-1] // 2:]
+
+
+def noise_generator_v2(x: Tensor, sd, prefix: str, ratios=(2, 2, 2), data_size: int = 16, n_channels: int = 1,
+                       noise: Optional[Tensor] = None, slope: float = 0.2) -> Tensor:
+    """rave/blocks.py:243-292 with the uniform noise injected (`noise` [B, T', C, target] in [-1, 1); the reference
+    draws it with torch.rand_like).  Convs: cc.Conv1d(k = 2r, stride r, padding (r, 0)), LeakyReLU(.2) between them
+    (configs/v2_small.gin:42-57), plain weights + bias (`normalization` is not applied to this branch)."""
+    h = x
+    for i, r in enumerate(ratios):
+        idx = 2 * i                       # nn.Sequential: conv, act, conv, act, conv
+        if i:
+            h = leaky_relu(h, slope)
+        h = conv1d(h, sd[f"{prefix}net.{idx}.weight"], sd.get(f"{prefix}net.{idx}.bias"), r, 1, (r, 0))
+    amp = mod_sigmoid(h - 5)
+    amp = amp.permute(0, 2, 1)
+    amp = amp.reshape(amp.shape[0], amp.shape[1], n_channels * data_size, -1)
+    target = 1
+    for r in ratios:
+        target *= r
+    ir = amp_to_impulse_response(amp, target)
+    if noise is None:
+        noise = torch.rand_like(ir) * 2 - 1
+    out = fft_convolve(noise, ir).permute(0, 2, 1, 3)
+    return out.reshape(out.shape[0], out.shape[1], -1)

@@ -64,6 +64,8 @@ SIGNATURES = {
     "rave_stft_frames": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "rave_stft_frames_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "rave_rfft_bwd_scale": (c_int, [_P, _P, _L, _I, _I, _L, _L, _L, _P]),
+    "rave_noise_fir_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rave_noise_fir_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rave_adam_multi": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P]),
     "rave_weight_prep_tc_multi": (c_int, [_I, _P, _P]),
     "rave_weight_norm_bwd_multi": (c_int, [_I, _P, _P]),

@@ -202,7 +202,13 @@ class NoiseGeneratorV2(nn.Module):
                 net.append(activation(channels[i + 1]))
         self.net = nn.Sequential(*net)
         self.data_size = data_size
-        self.register_buffer("target_size", torch.tensor(int(np.prod(ratios))).long())
+        self.noise_bands = noise_bands
+        self._target = int(np.prod(ratios))            # host copy of `target_size` (no device sync per forward)
+        self.register_buffer("target_size", torch.tensor(self._target).long())
+        # every step of amp_to_impulse_response is linear in the amplitudes: its matrix, from the identity
+        from .core import amp_to_impulse_response
+        self.register_buffer("_ir_matrix", amp_to_impulse_response(torch.eye(noise_bands), self._target).t().contiguous(),
+                             persistent=False)          # [target, bands]
 
     def forward(self, x, noise: Optional[torch.Tensor] = None):
         from .core import amp_to_impulse_response, fft_convolve, mod_sigmoid
@@ -217,10 +223,16 @@ class NoiseGeneratorV2(nn.Module):
             else:
                 h = mods[i + 1](h, act=m)
                 i += 2
+        C = self.n_channels * self.data_size
+        if h.is_cuda and self._target <= 16 and self.noise_bands <= 64:
+            # one library kernel for mod_sigmoid -> impulse response -> causal convolution with the noise block
+            if noise is None:
+                noise = torch.rand(h.shape[0], h.shape[2], C, self._target, device=h.device) * 2 - 1
+            return ops.noise_fir(h, self._ir_matrix, noise, C)
         amp = mod_sigmoid(h - 5)
         amp = amp.permute(0, 2, 1)
-        amp = amp.reshape(amp.shape[0], amp.shape[1], self.n_channels * self.data_size, -1)
-        ir = amp_to_impulse_response(amp, self.target_size)
+        amp = amp.reshape(amp.shape[0], amp.shape[1], C, -1)
+        ir = amp_to_impulse_response(amp, self._target)
         if noise is None:
             noise = torch.rand_like(ir) * 2 - 1
         out = fft_convolve(noise, ir).permute(0, 2, 1, 3)

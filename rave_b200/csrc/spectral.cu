@@ -224,3 +224,125 @@ extern "C" int rave_spectral_grad(const void *X, const void *Y, void *dY, const 
   RAVE_CHECK_LAUNCH("spectral_grad");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// NoiseGeneratorV2 tail (rave/blocks.py:284-292, rave/core.py:20-21,48-81): band amplitudes -> FIR -> filtered
+// uniform noise, in ONE kernel.  The reference goes mod_sigmoid -> irfft -> roll -> hann -> pad/crop -> roll
+// (amp_to_impulse_response) and then a zero-padded rfft * rfft -> irfft (fft_convolve): 4 FFT launches and ~15
+// elementwise kernels for what is, per (batch, frame, channel) group, a [target x bands] LINEAR map of the amplitudes
+// (every step of amp_to_impulse_response is linear) followed by a causal convolution of `target` samples:
+//     amp[k]   = 2 sigmoid(h[b][c*NB + k][t] - 5)^2.3 + 1e-7
+//     ir[n]    = sum_k M[n][k] amp[k]                       (M: the reference pipeline applied to the identity, host)
+//     out[b][c][t*TS + i] = sum_{j <= i} noise[b][t][c][j] * ir[i - j]
+// h: [B][C*NB][T] conv output (NCL), noise: [B][T][C][TS], out: [B][C][T*TS].  One thread per (b, c, t).
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+constexpr int NF_MAX_TS = 16;     // target_size (prod of the noise ratios; 8 in configs/v2_small.gin:42-57)
+constexpr int NF_MAX_NB = 64;     // noise bands (32)
+
+__device__ __forceinline__ float mod_sigmoid_f(float x) {
+  const float s = 1.f / (1.f + __expf(-x));
+  return 2.f * powf(s, 2.3f) + 1e-7f;
+}
+
+__global__ void __launch_bounds__(128)
+noise_fir_fwd_kernel(const float *__restrict__ h, const float *__restrict__ M, const float *__restrict__ noise,
+                     float *__restrict__ out, int C, int NB, int T, int TS) {
+  extern __shared__ float Ms[];            // [TS][NB]
+  for (int i = threadIdx.x; i < TS * NB; i += blockDim.x) Ms[i] = M[i];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  float ir[NF_MAX_TS];
+#pragma unroll
+  for (int n = 0; n < NF_MAX_TS; ++n) ir[n] = 0.f;
+  const float *hp = h + ((size_t)b * C * NB + (size_t)c * NB) * T + t;
+  for (int k = 0; k < NB; ++k) {
+    const float a = mod_sigmoid_f(hp[(size_t)k * T] - 5.f);
+#pragma unroll
+    for (int n = 0; n < NF_MAX_TS; ++n)
+      if (n < TS) ir[n] = fmaf(Ms[n * NB + k], a, ir[n]);
+  }
+  const float *np_ = noise + (((size_t)b * T + t) * C + c) * TS;
+  float nz[NF_MAX_TS];
+#pragma unroll
+  for (int j = 0; j < NF_MAX_TS; ++j) nz[j] = j < TS ? np_[j] : 0.f;
+  float *op = out + ((size_t)b * C + c) * T * TS + (size_t)t * TS;
+#pragma unroll
+  for (int i = 0; i < NF_MAX_TS; ++i) {
+    if (i >= TS) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NF_MAX_TS; ++j)
+      if (j <= i) acc = fmaf(nz[j], ir[i - j], acc);
+    op[i] = acc;
+  }
+}
+
+// dh[b][c*NB + k][t] = mod_sigmoid'(h - 5) * sum_n M[n][k] * dir[n],   dir[n] = sum_{i >= n} dout[i] noise[i - n]
+__global__ void __launch_bounds__(128)
+noise_fir_bwd_kernel(const float *__restrict__ h, const float *__restrict__ M, const float *__restrict__ noise,
+                     const float *__restrict__ dout, float *__restrict__ dh, int C, int NB, int T, int TS) {
+  extern __shared__ float Ms[];
+  for (int i = threadIdx.x; i < TS * NB; i += blockDim.x) Ms[i] = M[i];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const float *np_ = noise + (((size_t)b * T + t) * C + c) * TS;
+  const float *gp = dout + ((size_t)b * C + c) * T * TS + (size_t)t * TS;
+  float nz[NF_MAX_TS], go[NF_MAX_TS], dir[NF_MAX_TS];
+#pragma unroll
+  for (int j = 0; j < NF_MAX_TS; ++j) {
+    nz[j] = j < TS ? np_[j] : 0.f;
+    go[j] = j < TS ? gp[j] : 0.f;
+  }
+#pragma unroll
+  for (int n = 0; n < NF_MAX_TS; ++n) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < NF_MAX_TS; ++i)
+      if (i >= n && i < TS) acc = fmaf(go[i], nz[i - n], acc);
+    dir[n] = acc;
+  }
+  const size_t base = ((size_t)b * C * NB + (size_t)c * NB) * T + t;
+  for (int k = 0; k < NB; ++k) {
+    float da = 0.f;
+#pragma unroll
+    for (int n = 0; n < NF_MAX_TS; ++n)
+      if (n < TS) da = fmaf(Ms[n * NB + k], dir[n], da);
+    // d/dx [2 s^2.3] = 4.6 s^2.3 (1 - s),  s = sigmoid(x)
+    const float x = h[base + (size_t)k * T] - 5.f;
+    const float s = 1.f / (1.f + __expf(-x));
+    dh[base + (size_t)k * T] = da * 4.6f * powf(s, 2.3f) * (1.f - s);
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_noise_fir_fwd(const float *h, const float *M, const float *noise, float *out, int B, int C, int NB,
+                                  int T, int TS, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(h && M && noise && out && B > 0 && C > 0 && T > 0, "noise_fir: bad argument");
+  RAVE_CHECK_ARG(TS >= 1 && TS <= NF_MAX_TS && NB >= 1 && NB <= NF_MAX_NB && B <= 65535 && C <= 65535,
+                 "noise_fir: target_size %d (<= %d) / bands %d (<= %d) outside the kernel's range", TS, NF_MAX_TS, NB,
+                 NF_MAX_NB);
+  dim3 grid(ceil_div(T, 128), C, B);
+  noise_fir_fwd_kernel<<<grid, 128, TS * NB * sizeof(float), (cudaStream_t)stream>>>(h, M, noise, out, C, NB, T, TS);
+  RAVE_CHECK_LAUNCH("noise_fir_fwd");
+  return 0;
+}
+
+extern "C" int rave_noise_fir_bwd(const float *h, const float *M, const float *noise, const float *dout, float *dh,
+                                  int B, int C, int NB, int T, int TS, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(h && M && noise && dout && dh && B > 0 && C > 0 && T > 0, "noise_fir_bwd: bad argument");
+  RAVE_CHECK_ARG(TS >= 1 && TS <= NF_MAX_TS && NB >= 1 && NB <= NF_MAX_NB && B <= 65535 && C <= 65535,
+                 "noise_fir_bwd: shape outside the kernel's range");
+  dim3 grid(ceil_div(T, 128), C, B);
+  noise_fir_bwd_kernel<<<grid, 128, TS * NB * sizeof(float), (cudaStream_t)stream>>>(h, M, noise, dout, dh, C, NB, T, TS);
+  RAVE_CHECK_LAUNCH("noise_fir_bwd");
+  return 0;
+}

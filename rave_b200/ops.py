@@ -734,6 +734,37 @@ def rfft(x, w):
     return RfftFn.apply(x, w)
 
 
+class NoiseFirFn(torch.autograd.Function):
+    """h [B, C*NB, T] (conv output), M [TS, NB], noise [B, T, C, TS] -> filtered noise [B, C, T*TS]
+    (rave_noise_fir_fwd / _bwd: the whole tail of NoiseGeneratorV2.forward)."""
+
+    @staticmethod
+    def forward(ctx, h, M, noise, C):
+        h = _f32c(h)
+        noise = _f32c(noise)
+        B, CN, T = h.shape
+        NB = CN // C
+        TS = M.shape[0]
+        out = torch.empty(B, C, T * TS, dtype=torch.float32, device=h.device)
+        call("rave_noise_fir_fwd", ptr(h), ptr(M), ptr(noise), ptr(out), B, C, NB, T, TS, stream_ptr())
+        ctx.save_for_backward(h, M, noise)
+        ctx.dims = (B, C, NB, T, TS)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, M, noise = ctx.saved_tensors
+        B, C, NB, T, TS = ctx.dims
+        dh = torch.empty_like(h)
+        call("rave_noise_fir_bwd", ptr(h), ptr(M), ptr(noise), ptr(_f32c(dout)), ptr(dh), B, C, NB, T, TS,
+             stream_ptr())
+        return dh, None, None, None
+
+
+def noise_fir(h, M, noise, C):
+    return NoiseFirFn.apply(h, M, noise, C)
+
+
 # ----------------------------------------------------------------------------------------------
 # multi-tensor weight preparation / weight-norm backward (one launch pair per chain)
 # ----------------------------------------------------------------------------------------------

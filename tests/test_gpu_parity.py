@@ -533,3 +533,32 @@ def test_eager_bf16_training_uses_updated_weights():
         assert torch.equal(y_hot, y_cold)
     finally:
         rave_b200.set_precision("fp32")
+
+
+def test_noise_generator_v2_vs_oracle():
+    """a13 / SURVEY 8f.4: NoiseGeneratorV2 (v2_small's filtered-noise branch) -- strided convs on the library kernels and
+    the whole mod_sigmoid -> impulse response -> FFT-convolution tail as ONE library kernel (rave_noise_fir_*) -- against
+    the oracle restatement of the reference (4 FFTs), forward and gradients, with the uniform noise injected."""
+    from rave_b200 import blocks, cc
+    torch.manual_seed(0)
+    with cc.configure(conv_bias=False):
+        ng = blocks.NoiseGeneratorV2(in_size=48, hidden_size=64, data_size=16, ratios=[2, 2, 2], noise_bands=32)
+    sd = {"n." + k: v.detach().clone() for k, v in ng.state_dict().items()}
+    B, T = 3, 520
+    x = torch.randn(B, 48, T)
+    noise = torch.rand(B, T // 8, 16, 8) * 2 - 1
+    po = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    y_o = O.noise_generator_v2(xo, po, "n.", (2, 2, 2), 16, 1, noise)
+    probe = torch.randn_like(y_o)
+    names = sorted(k for k, v in po.items() if v.requires_grad)
+    g_o = torch.autograd.grad((y_o * probe).sum(), [xo] + [po[k] for k in names])
+    ng.cuda()
+    xg = x.cuda().requires_grad_(True)
+    y = ng(xg, noise.cuda())
+    assert y.shape == y_o.shape
+    assert rel_l2(y, y_o) < FWD_TOL
+    pg = dict(ng.named_parameters(prefix="n"))
+    g = torch.autograd.grad((y * probe.cuda()).sum(), [xg] + [pg[k] for k in names])
+    for k, a, b in zip(["x"] + names, g, g_o):
+        assert rel_l2(a, b) < 5e-4, (k, rel_l2(a, b))

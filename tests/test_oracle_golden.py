@@ -185,3 +185,22 @@ def test_training_step_restatement_reproduces_reference_steps():
                 n_all += upd.numel()
         assert n_bad <= UPD_FRAC[st["name"]] * n_all, (st["name"], n_bad, n_all)
         prev = st["state_dict"]
+
+
+@pytest.mark.reference
+def test_noise_generator_oracle_matches_live_reference():
+    """a13: the restatement of NoiseGeneratorV2 (+ mod_sigmoid / amp_to_impulse_response / fft_convolve) against the
+    unmodified reference module; the reference's torch.rand_like draw is reproduced by re-seeding."""
+    from oracle.ref_loader import load_reference
+    R = load_reference()
+    torch.manual_seed(0)
+    ng = R.blocks.NoiseGeneratorV2(in_size=48, hidden_size=64, data_size=16, ratios=[2, 2, 2], noise_bands=32)
+    sd = {"n." + k: v.detach().clone() for k, v in ng.state_dict().items()}
+    x = torch.randn(2, 48, 256)
+    torch.manual_seed(77)
+    y_ref = ng(x)
+    torch.manual_seed(77)
+    noise = torch.rand(2, 32, 16, 8) * 2 - 1          # rand_like(ir): ir is [B, T/8, 16, 8]
+    y = O.noise_generator_v2(x, sd, "n.", (2, 2, 2), 16, 1, noise)
+    assert y.shape == y_ref.shape == (2, 16, 256)
+    assert rel_l2(y, y_ref) < 1e-6
