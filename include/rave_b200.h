@@ -158,6 +158,18 @@ int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, i
  * Requirements: Cin % 16 == 0, Cout % 16 == 0.
  * ------------------------------------------------------------------------------------------- */
 int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dil);
+/* Fused Residual(DilatedUnit) forward (rave/blocks.py:31-45, 83-112):  out = x + Conv1x1(LeakyReLU(Conv3_dil(LeakyReLU(x))))
+ * in one tcgen05 kernel; the intermediate operand stays in shared memory as the A operand of the second GEMM.
+ *   xa      [B][pitch][C] bf16 : a = LeakyReLU_{slope_in}(x), the unit's input operand (the skip x is recovered from it)
+ *   w3t     [3][C][C] bf16, w1t [1][C][C] bf16 : tap-major effective weights (rave_weight_prep_tc_multi)
+ *   a1_out  [B][pitch][C] bf16 or NULL : LeakyReLU_{slope_mid}(conv3) kept for the backward (training)
+ *   out_f32 / out_act [B][pitch][C] or NULL : the unit's output, fp32 and / or act_out(out) as bf16 operand
+ * conv3 reads rows l + k*dil - pad_l (zero outside [0, L)).  C in {96, 192, 384} (the v2 / v3 / discrete widths below
+ * the 768-channel stage, whose [128 x 768] intermediate does not fit on one SM).  Backward: the per-layer kernels. */
+int rave_dilated_unit_tc_supported(int C, int L);
+int rave_dilated_unit_tc_fwd(const void *xa_bf16, const void *w3t_bf16, const void *w1t_bf16, void *a1_out,
+                             float *out_f32, void *out_act, int B, int C, int L, int pitch, int dil, int pad_l,
+                             float slope_in, float slope_mid, int act_out, float slope_out, void *stream);
 /* kernel instance rave_conv1d_tc_fwd selects for a shape: BLOCK_N | BLOCK_K << 12 | (CTA pair ? 1 << 24 : 0), 0 = none
  * (bench.py names the dominant kernel with it) */
 int rave_conv1d_tc_plan(int B, int Cin, int Cout, int Lout);

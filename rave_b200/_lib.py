@@ -36,6 +36,8 @@ SIGNATURES = {
     "rave_am_tanh_fwd": (c_int, [_P, _P, _I, _I, _I, _P]),
     "rave_am_tanh_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "rave_conv1d_tc_supported": (c_int, [_I, _I, _I, _I, _I]),
+    "rave_dilated_unit_tc_supported": (c_int, [_I, _I]),
+    "rave_dilated_unit_tc_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _I, _F, _P]),
     "rave_conv1d_tc_plan": (c_int, [_I, _I, _I, _I]),
     "rave_conv1d_tc_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I,
                                    _F, _I, _I, _I, _P, _I, _P]),

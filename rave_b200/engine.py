@@ -33,6 +33,8 @@ ACT_DTYPE = torch.bfloat16   # storage type of operand / gradient streams (tests
 import os as _os
 # output positions per tensor-core row of a Cin = 1 first layer (see TcChainFn.forward); 1 = plain 16-channel rows
 C1_GROUP = int(_os.environ.get("RAVE_C1_GROUP", "4"))
+# Residual(DilatedUnit) blocks as ONE launch (csrc/unit_tc.cu) where the width allows it; 0 = two launches per unit
+FUSE_UNITS = _os.environ.get("RAVE_FUSE_UNITS", "1") != "0"
 
 
 def set_precision(mode: str) -> None:
@@ -382,12 +384,52 @@ class TcChainFn(torch.autograd.Function):
         prepared = prepare_layers([(s, flat[3 * i].detach(), flat[3 * i + 1].detach() if flat[3 * i + 1] is not None
                                     else None, need_dgrad and not (c1 and i == 0), not (c1 and i == 0))
                                    for i, s in enumerate(specs)], x3=x3)
+        fused_second = False
         for i, s in enumerate(specs):
+            if fused_second:           # the 1x1 conv of a unit the previous iteration ran as one fused launch
+                fused_second = False
+                continue
             v, g, bias = flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]
             use_c1 = c1 and i == 0
             pw = prepared[i]
             Lin = lens[-1]
             Lout = _out_len(s, Lin)
+            s1 = specs[i + 1] if i + 1 < n else None
+            if (FUSE_UNITS and not x3 and not fm and not use_c1 and s1 is not None and ACT_DTYPE == torch.bfloat16
+                    and s.kind == "conv" and s1.kind == "conv" and s.K == 3 and s1.K == 1 and s.stride == 1
+                    and s1.stride == 1 and s.pre_act == ops.ACT_LEAKY and s1.pre_act == ops.ACT_LEAKY
+                    and s1.res_opnd == i and s.res_src is None and s.res_opnd is None and bias is None
+                    and flat[3 * i + 5] is None and s.Cin == s.Cout == s1.Cin == s1.Cout
+                    and not (s.cin_pad or s.cout_pad or s1.cin_pad or s1.cout_pad) and Lout == Lin
+                    and ops.dilated_unit_tc_supported(s.Cin, Lin)):
+                # Residual(DilatedUnit) = act -> conv3(dil) -> act -> conv1x1 -> + x in ONE kernel: the intermediate
+                # operand stays in shared memory (written to HBM only when a backward will need it)
+                s2 = specs[i + 2] if i + 2 < n else None
+                s_next = s2.stride if (s2 is not None and s2.kind == "conv") else 1
+                pitch = (Lout + s_next - 1) // s_next * s_next
+                if pitch == a.shape[1]:
+                    want_f32 = s1.want_f32
+                    out_f32 = torch.empty(B, pitch, s.Cout, dtype=torch.float32, device=dev) if want_f32 else None
+                    out_act = torch.empty(B, pitch, s.Cout, dtype=ACT_DTYPE, device=dev) if s2 is not None else None
+                    if pitch > Lout:
+                        for t in (out_f32, out_act):
+                            if t is not None:
+                                t[:, Lout:].zero_()
+                    a1, _, _ = ops.dilated_unit_tc(a, pw.fwd, prepared[i + 1].fwd, s.dil, s.pad[0], s.pre_slope,
+                                                   s1.pre_slope, s2.pre_act if s2 is not None else ops.ACT_NONE,
+                                                   s2.pre_slope if s2 is not None else 0.0, L=Lout, want_a1=need_dgrad,
+                                                   out_f32=out_f32, out_act=out_act)
+                    acts.append(a)
+                    acts.append(a1)
+                    lens.append(Lout)
+                    lens.append(Lout)
+                    if want_f32:
+                        f32[i + 1] = out_f32
+                    if s1.is_output:
+                        outputs.append(out_f32)
+                    a = out_act
+                    fused_second = True
+                    continue
             lens.append(Lout)
             nxt = specs[i + 1] if i + 1 < n else None
             want_act = nxt is not None

@@ -445,6 +445,26 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     return out_f32, out_act
 
 
+def dilated_unit_tc_supported(C, L):
+    return bool(_lib.load().rave_dilated_unit_tc_supported(C, L))
+
+
+def dilated_unit_tc(xa_cl, w3t, w1t, dil, pad_l, slope_in, slope_mid, act_out, slope_out, L=None, want_a1=False,
+                    out_f32=None, out_act=None):
+    """Fused Residual(DilatedUnit) forward (rave_dilated_unit_tc_fwd): xa_cl [B, pitch, C] bf16 = LeakyReLU(x),
+    w3t [3, C, C], w1t [1, C, C] bf16 -> (a1 [B, pitch, C] bf16 | None, out_f32, out_act)."""
+    B, pitch, C = xa_cl.shape
+    L = pitch if L is None else L
+    if w3t.shape != (3, C, C) or w1t.shape != (1, C, C):
+        raise _lib.RaveB200Error("dilated_unit_tc: weight shapes")
+    a1 = torch.empty(B, pitch, C, dtype=torch.bfloat16, device=xa_cl.device) if want_a1 else None
+    if a1 is not None and pitch > L:
+        a1[:, L:].zero_()
+    call("rave_dilated_unit_tc_fwd", ptr(xa_cl), ptr(w3t), ptr(w1t), ptr(a1), ptr(out_f32), ptr(out_act), B, C, L,
+         pitch, dil, pad_l, float(slope_in), float(slope_mid), act_out, float(slope_out), stream_ptr())
+    return a1, out_f32, out_act
+
+
 def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None, dbias=None):
     """dwt[k][m][n] = sum_{b,l} P[b,l,m] * Q[b, l*stride + k*dil - pad_l, n]  (bf16 operands, fp32 result).
     Tensors may be allocated with a row pitch larger than their true length (Lp / Lq).

@@ -125,6 +125,25 @@ def _conv1d_tc_x3(xa_cl, wt, bias, res_cl, stride, dil, pad, act, slope, out_f32
     return out_f32, out_act
 
 
+def dilated_unit_tc_supported(C, L):
+    return C in (96, 192, 384) and L >= 8
+
+
+def dilated_unit_tc(xa_cl, w3t, w1t, dil, pad_l, slope_in, slope_mid, act_out, slope_out, L=None, want_a1=False,
+                    out_f32=None, out_act=None):
+    """Semantics of rave_dilated_unit_tc_fwd: the two per-layer launches back to back, the intermediate rounded to the
+    operand type exactly as the kernel rounds it before the second GEMM."""
+    B, pitch, C = xa_cl.shape
+    L = pitch if L is None else L
+    _, a1 = conv1d_tc(xa_cl, w3t, None, None, 1, dil, (pad_l, 2 * dil - pad_l), 1, slope_mid, want_f32=False,
+                      want_act=True, out_rows=pitch, Lout=L, Lin=L)
+    if pitch > L:
+        a1[:, L:] = 0
+    conv1d_tc(a1, w1t, None, None, 1, 1, (0, 0), act_out, slope_out, want_f32=False, want_act=False, out_f32=out_f32,
+              out_act=out_act, out_rows=pitch, Lout=L, Lin=L, res_act=xa_cl, res_slope=slope_in)
+    return (a1 if want_a1 else None), out_f32, out_act
+
+
 def ncl_to_cl_x3(x):
     xt = x.permute(0, 2, 1).contiguous()
     hi, lo = _split(xt)
@@ -373,5 +392,6 @@ def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
                  "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1", "weight_prep_tc_multi",
-                 "weight_norm_bwd_multi", "score_stats", "score_grad", "ncl_to_cl_x3"):
+                 "weight_norm_bwd_multi", "score_stats", "score_grad", "ncl_to_cl_x3", "dilated_unit_tc",
+                 "dilated_unit_tc_supported"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -254,3 +254,41 @@ def test_split_operand_chain_reaches_fp32_accuracy(monkeypatch):
         w = engine.from_channel_last(out[:, :engine.chain_lengths(specs, zin.shape[-1])[-1]].contiguous())
         print("bf16x3 generator rel-L2", rel_l2(w, taps["wave"]))
         assert rel_l2(w, taps["wave"]) < 5e-5
+
+
+def test_fused_units_are_planned_and_match_the_two_launch_form(emu, monkeypatch):
+    """The engine runs Residual(DilatedUnit) blocks of width 96 / 192 / 384 through ops.dilated_unit_tc (one launch);
+    with the kernel's semantics emulated, forward and every gradient must equal the unfused chain (same arithmetic)."""
+    from rave_b200 import configs, engine
+    calls = []
+    real = tc_emulator.dilated_unit_tc
+
+    def spy(*a, **k):
+        calls.append(a[0].shape)
+        return real(*a, **k)
+    from rave_b200 import ops
+    monkeypatch.setattr(ops, "dilated_unit_tc", spy)
+    torch.manual_seed(4)
+    _, enc, dec = configs.make_autoencoder("v2", capacity=96, latent_size=16, ratios=[4, 2])
+    x_mb = torch.randn(1, 16, 256)
+    outs = {}
+    for fuse in (True, False):
+        monkeypatch.setattr(engine, "FUSE_UNITS", fuse)
+        if emu == "bf16":
+            monkeypatch.setattr(engine, "ACT_DTYPE", torch.bfloat16)
+        specs = enc.encoder.net._tc_plan()
+        xe = x_mb.clone().requires_grad_(True)
+        n0 = len(calls)
+        (out,) = engine.run_chain(engine.to_channel_last(xe), specs)
+        z = engine.from_channel_last(out[:, :engine.chain_lengths(specs, 256)[-1]].contiguous())
+        pe = dict(enc.named_parameters())
+        names = sorted(pe)
+        g = torch.autograd.grad((z * torch.ones_like(z)).sum(), [xe] + [pe[k] for k in names])
+        outs[fuse] = (z.detach(), [t.detach() for t in g], len(calls) - n0)
+    if emu == "bf16":
+        assert outs[True][2] == 6 and outs[False][2] == 0          # 3 units at C = 96, 3 at C = 192
+        assert torch.equal(outs[True][0], outs[False][0])
+        for a, b in zip(outs[True][1], outs[False][1]):
+            assert torch.equal(a, b)
+    else:
+        assert outs[True][2] == 0               # fp32 operand emulation: the fused kernel is a bf16 kernel

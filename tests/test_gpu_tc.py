@@ -249,3 +249,52 @@ def test_conv1d_tc_fused_fm_gradient_vs_emulator(shape):
     mask = torch.ones(rows, dtype=torch.bool)
     mask[idx] = False
     assert float(out[:, mask].float().abs().max()) == 0.0   # rows of other phases untouched
+
+
+UNIT_CASES = [
+    # B, C, L, dil, pad_l (centered = dil, causal = 2 * dil), training (keep a1), fp32 output
+    (2, 96, 512, 1, 1, True, False),
+    (3, 96, 1000, 3, 3, False, True),        # ragged length
+    (2, 96, 4096, 9, 9, True, False),
+    (2, 192, 1024, 3, 3, True, True),
+    (5, 192, 256, 9, 18, False, False),      # causal padding
+    (2, 384, 256, 1, 1, True, False),        # two N chunks of 192
+    (9, 384, 64, 9, 9, False, True),         # several batches per tile
+    (32, 96, 4096, 3, 3, True, False),       # BASELINE config 3 shape: 1024 tiles over 148 persistent CTAs
+]
+
+
+@pytest.mark.parametrize("case", UNIT_CASES)
+def test_fused_dilated_unit_vs_two_launches_and_oracle(case):
+    """rave_dilated_unit_tc_fwd (one kernel, intermediate in shared memory) against the per-layer tcgen05 launches it
+    replaces (same operands, same accumulation order: <= 1e-6) and against the fp32 oracle of Residual(DilatedUnit)
+    (rave/blocks.py:31-45, 83-112) at the bf16-mode tolerance."""
+    from rave_b200 import ops
+    B, C, L, dil, pad_l, keep_a1, want_f32 = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, C, L, generator=g)
+    w3 = torch.randn(C, C, 3, generator=g) / (3 * C) ** 0.5
+    w1 = torch.randn(C, C, 1, generator=g) / C ** 0.5
+    pad = (pad_l, 2 * dil - pad_l)
+    y_ref = x + O.conv1d(O.leaky_relu(O.conv1d(O.leaky_relu(x, 0.2), w3, None, 1, dil, pad), 0.2), w1, None, 1, 1, (0, 0))
+    xa, _ = ops.ncl_to_cl(x.cuda(), ops.ACT_LEAKY, 0.2)
+    w3t = ops.weight_to_tapmajor_bf16(w3.cuda())
+    w1t = ops.weight_to_tapmajor_bf16(w1.cuda())
+    # two launches
+    _, a1_ref = ops.conv1d_tc(xa, w3t, None, None, 1, dil, pad, ops.ACT_LEAKY, 0.2, want_f32=False, want_act=True)
+    o_ref, oa_ref = ops.conv1d_tc(a1_ref, w1t, None, None, 1, 1, (0, 0), ops.ACT_LEAKY, 0.2, want_f32=True, want_act=True,
+                                  res_act=xa, res_slope=0.2)
+    # fused
+    out_f32 = torch.full((B, L, C), float("nan"), device="cuda") if want_f32 else None
+    out_act = torch.empty(B, L, C, device="cuda", dtype=torch.bfloat16)
+    a1, _, _ = ops.dilated_unit_tc(xa, w3t, w1t, dil, pad_l, 0.2, 0.2, ops.ACT_LEAKY, 0.2, want_a1=keep_a1,
+                                   out_f32=out_f32, out_act=out_act)
+    torch.cuda.synchronize()
+    if keep_a1:
+        assert rel_l2(a1.float(), a1_ref.float()) < 1e-6
+    assert rel_l2(out_act.float(), oa_ref.float()) < 1e-6
+    if want_f32:
+        assert rel_l2(out_f32, o_ref) < 1e-6
+        assert rel_l2(ops.cl_to_ncl(out_f32), y_ref) < 1.5e-2
+    y_act = O.leaky_relu(y_ref, 0.2).permute(0, 2, 1)
+    assert rel_l2(out_act.float(), y_act) < 1.5e-2
