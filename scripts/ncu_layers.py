@@ -1,5 +1,5 @@
 """Representative launches of the step in isolation, one of each after a warm-up, for
-`ncu --set full --clock-control none -k regex:'conv_tc|wgrad_tc|pqmf' ...` (scripts/gpu_ncu.sh) and, without ncu, a table
+`ncu --set full --clock-control none -k regex:'conv_tc|wgrad_tc|pqmf|dilated_unit' ...` (scripts/gpu_ncu.sh) and, without ncu, a table
 of their times (CUDA events, rotating buffers > L2).  Shapes are the ones of BASELINE config 3 (v2, B = 32 x 65536):
   mpd0_fwd     : MPD period-2 first layer (Cin = 1 read as 4 positions x 16 taps), 235 MB, HBM-bound
   mpd1_dgrad   : fused dgrad of the MPD period-2 second layer (phase-fused, fm gradient + LeakyReLU' in the epilogue)
@@ -91,6 +91,22 @@ timed("unit768_k3", lambda i: ops.conv1d_tc(xd[i], wd3, None, None, 1, 1, (1, 1)
 timed("unit768_k1", lambda i: ops.conv1d_tc(xd[i], wd1, None, None, 1, 1, (0, 0), 1, 0.2, want_f32=False, want_act=False,
                                              out_act=od[i], Lout=L, res_act=xd[(i + 1) % NB], res_slope=0.2),
       6.0 * B * L * C + 2.0 * C * C, 2.0 * B * L * C * C, NB)
+# ---- fused Residual(DilatedUnit) kernels (csrc/unit_tc.cu) at the three widths, inference form (no a1 write) and training
+for (Bu, Cu, Lu, du) in ((32, 96, 4096, 3), (32, 192, 1024, 3), (32, 384, 256, 3)):
+    xu = [bf(Bu, Lu, Cu) for _ in range(NB)]
+    w3u, w1u = bf(3, Cu, Cu, scale=0.05), bf(1, Cu, Cu, scale=0.05)
+    ouu = [torch.empty(Bu, Lu, Cu, device=dev, dtype=torch.bfloat16) for _ in range(NB)]
+    for keep in (False, True):
+        timed(f"fused{Cu}{'_a1' if keep else ''}",
+              lambda i: ops.dilated_unit_tc(xu[i], w3u, w1u, du, du, 0.2, 0.2, 1, 0.2, want_a1=keep, out_act=ouu[i]),
+              (6.0 if keep else 4.0) * Bu * Lu * Cu + 8.0 * Cu * Cu, 2.0 * Bu * Lu * Cu * Cu * 4, NB)
+# ---- split-operand (bf16x3) conv: DilatedUnit k3 at C = 192
+x3a = [torch.cat([bf(32, 1024, 192), bf(32, 1024, 192, scale=0.004)], -1).contiguous() for _ in range(NB)]
+w3x = torch.cat([bf(3, 192, 192, scale=0.05), bf(3, 192, 192, scale=0.0002)], 0).contiguous()
+o3x = [torch.empty(32, 1024, 384, device=dev, dtype=torch.bfloat16) for _ in range(NB)]
+timed("x3_unit192_k3", lambda i: ops.conv1d_tc(x3a[i], w3x, None, None, 1, 3, (3, 3), 1, 0.2, want_f32=False,
+                                                want_act=False, out_act=o3x[i], Lout=1024, x3=True),
+      8.0 * 32 * 1024 * 192, 6.0 * 32 * 1024 * 192 * 192 * 3, NB)
 # ---- wgrad of the MSD 96 -> 192 layer (per-tap form)
 gw = bf(64, Lout, 192)
 timed("wgrad_msd0_l1", lambda i: ops.conv1d_tc_wgrad(gw, x1[i], K, st, 1, pad), 2.0 * 64 * (Lout * 192 + Lin * 96),
