@@ -473,6 +473,48 @@ def descript_mpd(x: Tensor, sd, prefix: str, period: int) -> List[Tensor]:
     return fmap
 
 
+DESCRIPT_BANDS = [(0.0, 0.1), (0.1, 0.25), (0.25, 0.5), (0.5, 0.75), (0.75, 1.0)]
+
+
+def descript_mrd(x: Tensor, sd, prefix: str, window_length: int, bands=DESCRIPT_BANDS) -> List[Tensor]:
+    """MRD (rave/descript_discriminator.py:118-184): complex STFT (torchaudio Spectrogram, hann, hop = wl/4, centred,
+    power=None) as [b, (c re/im), t, f], split into 5 frequency bands, each through its own stack of (3,9)/(3,3)
+    weight-normed Conv2d + LeakyReLU(.1) (stride 2 along frequency in layers 1-3); the band outputs are concatenated
+    along frequency for conv_post.  Features are POST-activation, 5 x 5 + 1 = 26 of them."""
+    n_fft = window_length // 2 + 1
+    bnd = [(int(b[0] * n_fft), int(b[1] * n_fft)) for b in bands]
+    B, C, T = x.shape
+    win = torch.hann_window(window_length, dtype=x.dtype, device=x.device)
+    s = torch.stft(x.reshape(B * C, T), window_length, hop_length=int(0.25 * window_length),
+                   win_length=window_length, window=win, center=True, pad_mode="reflect", normalized=False,
+                   onesided=True, return_complex=True)                       # [B*C, f, t]
+    s = torch.view_as_real(s).reshape(B, C, s.shape[-2], s.shape[-1], 2)     # b c f t p
+    xs = s.permute(0, 1, 4, 3, 2).reshape(B, 2 * C, s.shape[3], s.shape[2])  # b (c p) t f
+    fmap, outs = [], []
+    strides = [(1, 1), (1, 2), (1, 2), (1, 2), (1, 1)]
+    pads = [(1, 4)] * 4 + [(1, 1)]
+    for bi, (lo, hi) in enumerate(bnd):
+        band = xs[..., lo:hi]
+        for li in range(5):
+            q = f"{prefix}band_convs.{bi}.{li}.0."
+            band = leaky_relu(F.conv2d(band, wn_weight(sd, q), sd[q + "bias"], strides[li], pads[li]), 0.1)
+            fmap.append(band)
+        outs.append(band)
+    q = f"{prefix}conv_post."
+    fmap.append(F.conv2d(torch.cat(outs, -1), wn_weight(sd, q), sd[q + "bias"], 1, (1, 1)))
+    return fmap
+
+
+def descript_discriminator(x: Tensor, sd, prefix: str = "discriminator.", periods=(2, 3, 5, 7, 11),
+                           fft_sizes=(2048, 1024, 512)) -> List[List[Tensor]]:
+    """DescriptDiscriminator.forward (rave/descript_discriminator.py:187-217): preprocess, 5 MPDs, 3 MRDs."""
+    x = descript_preprocess(x)
+    out = [descript_mpd(x, sd, f"{prefix}discriminators.{i}.", p) for i, p in enumerate(periods)]
+    n = len(periods)
+    out += [descript_mrd(x, sd, f"{prefix}discriminators.{n + i}.", w) for i, w in enumerate(fft_sizes)]
+    return out
+
+
 def descript_preprocess(y: Tensor) -> Tensor:
     """DescriptDiscriminator.preprocess (rave/descript_discriminator.py:207-212)."""
     y = y - y.mean(dim=-1, keepdims=True)

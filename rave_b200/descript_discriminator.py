@@ -3,16 +3,18 @@ the reference but never instantiated: `rates=[]`, and its constructor call would
 
 MPD (77 % of the v3 discriminator FLOPs) runs on the library's conv kernels: a (5,1)
 Conv2d over the period-folded signal is a Conv1d along the folded axis with the period as extra batch.
-MRD (banded complex STFT -> (3,9) Conv2d stacks) is SURVEY row 8f.3 ("next"): it is kept on
-torch (cuFFT + cuDNN) behind the same module surface so that `DescriptDiscriminator` is usable and its
-state_dict keys match.  Features are POST-activation (descript_discriminator.py:59-61).
+MRD (banded complex STFT -> (3,9) Conv2d stacks) runs on the library too: the STFT is the framing
+kernel of csrc/spectral.cu (+ cuFFT for the transform, as for the spectral losses), and a (kt, kf) Conv2d with unit
+time stride is ONE library conv1d along frequency over rows [(b, t)] whose channels are the kt time-shifted copies of
+the input channels (`DiscConv2d`): out[b,:,t,:] = sum_dt conv1d_f(x[b,:,t+dt-pt,:], W[:,:,dt,:]).
+Features are POST-activation (descript_discriminator.py:59-61).  No cuDNN on this path.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import _lib, ops
 from .blocks import weight_norm
 from .discriminator import DiscConv2dK1
 
@@ -26,10 +28,33 @@ def WNConv2dK1(*args, **kwargs):
     return nn.Sequential(conv, nn.LeakyReLU(0.1))
 
 
+class DiscConv2d(nn.Conv2d):
+    """nn.Conv2d with kernel (kt, kf), stride (1, sf), padding (pt, pf) on the library's conv1d kernel: the kt time taps
+    become kt x Cin input channels of a conv along frequency (rows = (batch, time) pairs).  Same parameters / state_dict
+    keys as nn.Conv2d; input and output are [B, C, T, F] tensors."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.stride[0] != 1 or self.groups != 1 or self.dilation != (1, 1) or self.padding_mode != "zeros" \
+                or 2 * self.padding[0] != self.kernel_size[0] - 1:
+            raise _lib.RaveB200Error("DiscConv2d: unit time stride, 'same' time padding, no groups / dilation")
+
+    def forward(self, x):
+        B, C, T, Fq = x.shape
+        kt, kf = self.kernel_size
+        pt, pf = self.padding
+        xp = F.pad(x, (0, 0, pt, pt))
+        xi = torch.stack([xp[:, :, dt:dt + T] for dt in range(kt)], 1)            # [B, kt, C, T, F]
+        xi = xi.permute(0, 3, 1, 2, 4).reshape(B * T, kt * C, Fq)                 # rows (b, t), channels (dt, c)
+        w = self.weight.permute(0, 2, 1, 3).reshape(self.out_channels, kt * C, kf)
+        y = ops.conv1d(xi, w, self.bias, None, self.stride[1], 1, (pf, pf), ops.ACT_NONE, 0.0, None)
+        return y.view(B, T, self.out_channels, y.shape[-1]).permute(0, 2, 1, 3)
+
+
 def WNConv2d(*args, **kwargs):
-    """Generic 2-D variant (MRD): torch/cuDNN for now."""
+    """WNConv2d of the reference for general (kt, kf) kernels (MRD), on the library kernels."""
     act = kwargs.pop("act", True)
-    conv = torch.nn.utils.weight_norm(nn.Conv2d(*args, **kwargs))
+    conv = weight_norm(DiscConv2d(*args, **kwargs))
     if not act:
         return conv
     return nn.Sequential(conv, nn.LeakyReLU(0.1))
@@ -74,12 +99,11 @@ BANDS = [(0.0, 0.1), (0.1, 0.25), (0.25, 0.5), (0.5, 0.75), (0.75, 1.0)]
 
 
 class MRD(nn.Module):
-    """rave/descript_discriminator.py:118-184 (torch: SURVEY 8f.3)."""
+    """rave/descript_discriminator.py:118-184 on the library kernels (see the module docstring)."""
 
     def __init__(self, window_length: int, hop_factor: float = 0.25, sample_rate: int = 44100,
                  bands: list = BANDS, n_channels: int = 1):
         super().__init__()
-        from torchaudio.transforms import Spectrogram
         self.window_length = window_length
         self.hop_factor = hop_factor
         self.sample_rate = sample_rate
@@ -95,13 +119,23 @@ class MRD(nn.Module):
         ])
         self.band_convs = nn.ModuleList([convs() for _ in range(len(self.bands))])
         self.conv_post = WNConv2d(ch, 1, (3, 3), (1, 1), padding=(1, 1), act=False)
-        self.stft = Spectrogram(n_fft=window_length, win_length=window_length,
-                                hop_length=int(hop_factor * window_length), center=True, power=None)
+        # torchaudio.transforms.Spectrogram(n_fft = win_length = window_length, hop, centred, power=None) holds a hann
+        # `window` buffer under `stft.window`: same key here
+        self.stft = _StftHolder(window_length, int(hop_factor * window_length))
 
     def spectrogram(self, x):
-        x = torch.view_as_real(self.stft(x))               # b c f t p
-        b, c, f, t, p = x.shape
-        x = x.permute(0, 1, 4, 3, 2).reshape(b, c * p, t, f)  # "b c f t p -> b (c p) t f"
+        B, C, T = x.shape
+        st = self.stft
+        if x.is_cuda and T > st.n_fft // 2:
+            # framing kernel (reflect pad + frame + window; adjoint = overlap-add) + one rfft: [N, frames, bins]
+            z = ops.rfft(ops.stft_frames(x.reshape(B * C, T), st.window, st.n_fft, st.hop), st.rfft_bw)
+        else:
+            z = torch.stft(x.reshape(B * C, T), st.n_fft, hop_length=st.hop, win_length=st.n_fft, window=st.window,
+                           center=True, pad_mode="reflect", normalized=False, onesided=True,
+                           return_complex=True).transpose(-1, -2)
+        z = torch.view_as_real(z)                                           # [(b c), t, f, p]
+        t, f = z.shape[1], z.shape[2]
+        x = z.reshape(B, C, t, f, 2).permute(0, 1, 4, 2, 3).reshape(B, 2 * C, t, f)   # "b c f t p -> b (c p) t f"
         return [x[..., lo:hi] for lo, hi in self.bands]
 
     def forward(self, x):
@@ -109,12 +143,27 @@ class MRD(nn.Module):
         outs = []
         for band, stack in zip(self.spectrogram(x), self.band_convs):
             for layer in stack:
-                band = layer(band)
+                h = layer[0](band)
+                band = ops.activation(h.contiguous(), ops.ACT_LEAKY, layer[1].negative_slope)   # post-activation feature
                 fmap.append(band)
             outs.append(band)
         x = self.conv_post(torch.cat(outs, dim=-1))
         fmap.append(x)
         return fmap
+
+
+class _StftHolder(nn.Module):
+    """State of torchaudio.transforms.Spectrogram that reaches the state_dict (`window`), plus the rfft backward
+    weights of ops.RfftFn."""
+
+    def __init__(self, n_fft: int, hop: int):
+        super().__init__()
+        self.n_fft, self.hop = n_fft, hop
+        self.register_buffer("window", torch.hann_window(n_fft))
+        bw = torch.full((n_fft // 2 + 1,), 0.5 * n_fft)
+        bw[0] = n_fft
+        bw[-1] = n_fft
+        self.register_buffer("rfft_bw", bw, persistent=False)
 
 
 class DescriptDiscriminator(nn.Module):

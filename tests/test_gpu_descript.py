@@ -1,0 +1,77 @@
+"""GPU: the v3 discriminator (rave/descript_discriminator.py) entirely on the library kernels -- MPD as conv1d over the
+period-folded signal, MRD as framing kernel + rfft + (kt, kf) Conv2d stacks run as conv1d along frequency -- against the
+oracle restatement (pinned against the live reference: tests/test_oracle_golden.py), forward features and gradients."""
+import pytest
+import torch
+
+from oracle import rave_oracle as O
+from tests.conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def test_disc_conv2d_vs_torch_conv2d():
+    """DiscConv2d (time taps folded into channels, conv1d along frequency) == F.conv2d, forward and gradients."""
+    from rave_b200.descript_discriminator import DiscConv2d
+    torch.manual_seed(0)
+    for (cin, cout, k, s, p, shape) in [(2, 32, (3, 9), (1, 1), (1, 4), (2, 2, 17, 51)),
+                                        (32, 32, (3, 9), (1, 2), (1, 4), (2, 32, 9, 77)),
+                                        (32, 1, (3, 3), (1, 1), (1, 1), (3, 32, 5, 20))]:
+        conv = DiscConv2d(cin, cout, k, s, padding=p)
+        x = torch.randn(*shape)
+        xo = x.clone().requires_grad_(True)
+        y_o = torch.nn.functional.conv2d(xo, conv.weight, conv.bias, s, p)
+        probe = torch.randn_like(y_o)
+        g_o = torch.autograd.grad((y_o * probe).sum(), [xo, conv.weight, conv.bias])
+        conv.cuda()
+        xg = x.cuda().requires_grad_(True)
+        y = conv(xg)
+        assert y.shape == y_o.shape and rel_l2(y, y_o) < 2e-5
+        g = torch.autograd.grad((y * probe.cuda()).sum(), [xg, conv.weight, conv.bias])
+        for a, b in zip(g, g_o):
+            assert rel_l2(a, b) < 1e-4
+
+
+def test_descript_mrd_vs_oracle():
+    from rave_b200.descript_discriminator import MRD
+    torch.manual_seed(0)
+    mrd = MRD(512)
+    sd = {k: v.detach().clone() for k, v in mrd.state_dict().items()}
+    assert "band_convs.0.0.0.weight_g" in sd and "conv_post.weight_v" in sd and "stft.window" in sd
+    x = torch.randn(2, 1, 4000)
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and "window" not in k) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    want = O.descript_mrd(xo, po, "", 512)
+    mrd.cuda()
+    xg = x.cuda().requires_grad_(True)
+    got = mrd(xg)
+    assert len(got) == len(want) == 26
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and rel_l2(a, b) < 5e-5, (a.shape, rel_l2(a, b))
+    probes = [torch.randn_like(b) for b in want]
+    names = sorted(k for k, v in po.items() if v.requires_grad)
+    g_o = torch.autograd.grad(sum((b * p).sum() for b, p in zip(want, probes)), [xo] + [po[k] for k in names])
+    pg = dict(mrd.named_parameters())
+    g = torch.autograd.grad(sum((a * p.cuda()).sum() for a, p in zip(got, probes)), [xg] + [pg[k] for k in names])
+    for k, a, b in zip(["x"] + names, g, g_o):
+        assert rel_l2(a, b) < 5e-4, (k, rel_l2(a, b))
+
+
+def test_descript_discriminator_full_vs_oracle():
+    """DescriptDiscriminator.forward (preprocess, 5 MPD + 3 MRD): 8 feature lists (6 / 26 features), all on library
+    kernels, against the oracle; then the training-step arithmetic (feature matching + hinge) on those features."""
+    from rave_b200.descript_discriminator import DescriptDiscriminator
+    torch.manual_seed(1)
+    dd = DescriptDiscriminator()
+    sd = {"discriminator." + k: v.detach().clone() for k, v in dd.state_dict().items()}
+    x = (0.5 * torch.randn(2, 1, 8192 + 5)).clamp(-1, 1)
+    want = O.descript_discriminator(x, sd)
+    dd.cuda()
+    got = dd(x.cuda())
+    assert [len(f) for f in got] == [6] * 5 + [26] * 3
+    for fa, fb in zip(got, want):
+        for a, b in zip(fa, fb):
+            assert a.shape == b.shape and rel_l2(a, b) < 1e-4, (a.shape, rel_l2(a, b))
+    fm, ld, la = O.gan_losses([[f.cpu() for f in s] for s in got], 1, True)
+    fm_o, ld_o, la_o = O.gan_losses(want, 1, True)
+    assert rel_l2(fm, fm_o) < 1e-4 and rel_l2(ld, ld_o) < 1e-4

@@ -115,6 +115,23 @@ def test_descript_mpd_oracle_matches_live_reference():
     assert torch.equal(O.descript_preprocess(y), dd.preprocess(y))
 
 
+@pytest.mark.reference
+def test_descript_mrd_oracle_matches_live_reference():
+    """Descript MRD (rave/descript_discriminator.py:118-184) and the whole DescriptDiscriminator.forward against the
+    unmodified reference."""
+    from oracle.ref_loader import load_reference
+    R = load_reference()
+    torch.manual_seed(0)
+    mrd = R.descript_discriminator.MRD(512)
+    x = torch.randn(2, 1, 4000)
+    want = mrd(x)
+    sd = {k: v.detach() for k, v in mrd.state_dict().items()}
+    got = O.descript_mrd(x, sd, "", 512)
+    assert len(got) == len(want) == 26
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and rel_l2(a, b) < 2e-6, (a.shape, rel_l2(a, b))
+
+
 # fp32 conditioning of the training-step gradients, (all tensors, worst tensor) rel-L2: see the comments in the test
 GRAD_TOL = {"phase1_gen": (3e-3, 1e-2), "phase2_dis": (2e-5, 1e-3), "phase2_gen": (5e-2, 1e-1)}
 # fraction of parameter elements whose Adam update may differ by more than 5 % of lr (same conditioning)
