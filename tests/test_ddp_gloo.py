@@ -42,6 +42,10 @@ def _worker(rank, world, port, bucket_bytes, ret):
                 assert p.grad is None
             else:
                 assert torch.allclose(p.grad, torch.full_like(p, 1.5)), (i, p.grad)
+        # buffers that moved on each rank (the RVQ's EMA state) follow rank 0
+        model.buf.fill_(float(10 + rank))
+        assert ddp.broadcast_buffers(model) == 4
+        assert torch.equal(model.buf, torch.full((4,), 10.0))
         n_with_grad = sum(p.numel() for i, p in enumerate(model.parameters()) if i != 2)
         assert red.bytes_reduced == 4 * n_with_grad
         ret[rank] = red.n_collectives
