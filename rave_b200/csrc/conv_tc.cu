@@ -25,7 +25,7 @@ namespace tc {
 
 constexpr int BLOCK_M = 128;
 constexpr int NUM_THREADS = 192;
-constexpr int NUM_THREADS2 = 320;      // CTA-pair kernel: producer, MMA issuer, up to 8 epilogue warps (2 per TMEM quadrant)
+constexpr int NUM_THREADS2 = 352;      // CTA-pair kernel: producer, MMA issuer, up to 8 epilogue warps (2 per TMEM quadrant), chunk loader
 constexpr int ACC_STAGES = 2;
 
 struct TcParams {
@@ -55,6 +55,15 @@ struct TcParams {
   int act_cs;              // x3: channels per POSITION of an output row (Cout; Cout/stride when the row holds the phases
                            // of a transposed conv side by side): column n = q*cs + c lives at q*2cs + c (hi), +cs (lo)
   int stages;              // pipeline depth actually used (<= the layout's STAGES); RAVE_TC_STAGES overrides
+  // TMA-staged epilogue (CTA-pair kernel): the bf16 row segments the epilogue reads (LeakyReLU' mask, feature-matching
+  // partner, gradient skip, operand skip) and writes (out_act) move as [128 rows x 64 channels] chunks between HBM and
+  // shared memory by cp.async.bulk.tensor -- per-thread row accesses touch 32 different 128-byte lines per
+  // instruction and the L1 wavefront rate, not HBM, bounded the backward launches
+  int etma;                // 0 = per-thread global loads / stores
+  int in0_kind;            // chunk operand slot A: 0 none, 1 dact_src, 2 res_act
+  int in1_kind;            // chunk operand slot B: 0 none, 1 feature-matching partner rows, 2 res_bf16
+  int e_stages;            // chunk buffers in flight (1 or 2)
+  int epi_off, bar_off;    // byte offsets of the chunk buffers / the barriers in (1024-aligned) shared memory
   int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue, 8 = no L2 prefetch, 2 = skip the
                            // activation TMA loads, 4 = skip the weight TMA loads (results are garbage)
 };
@@ -203,12 +212,107 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
   }
 }
 
+// TMA-staged variant of tc_epi_chunk (32 rows x 32 channels per warp): the bf16 operands come from the chunk buffers
+// the loader warp filled ([128 rows][128 bytes], SWIZZLE_128B: 16-byte unit u of row r sits at r*128 + ((u ^ (r & 7)) << 4),
+// so the 8 lanes of a shared-memory phase hit 8 different bank groups), the activated output is returned packed in
+// `pk` for the caller to stage.  fp32 streams (bias, res, out_f32) are rare and small: per-thread accesses as before.
+constexpr int ECH_BYTES = 128 * 128;      // one [128 x 64] bf16 chunk
+__device__ __forceinline__ void tc_epi_chunk_tma(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow,
+                                                 int fm_side, const uint8_t *in0, const uint8_t *in1, uint32_t rowoff,
+                                                 uint32_t rx, int half, uint32_t *pk) {
+  float v[32];
+  uint32_t a0w[16], a1w[16], rf[32];
+  const size_t off = orow * p.Cout + co;
+  if (p.in0_kind) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lds128(in0 + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), a0w + 4 * q);
+  }
+  if (p.in1_kind) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lds128(in1 + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), a1w + 4 * q);
+  }
+  if (p.res && valid) ld_words<32>(p.res + off, rf);
+  tmem_ld_32x32(taddr, v);
+  if (p.bias) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + co);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 bb = __ldg(b4 + i);
+      v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+    }
+  }
+  if (p.in0_kind == 1) {       // LeakyReLU' from the sign bits of the saved operand
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      if (a0w[w] & 0x00008000u) v[2 * w] *= p.slope;
+      if (a0w[w] & 0x80000000u) v[2 * w + 1] *= p.slope;
+    }
+  }
+  if (p.in1_kind == 1) {       // feature-matching gradient (see tc_epi_chunk)
+    const float d0 = __ldg(p.fm_d), d1 = fm_side > 0 ? __ldg(p.fm_d + 1) : 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float as = h ? bf_hi(a0w[w]) : bf_lo(a0w[w]);
+        const float ap = h ? bf_hi(a1w[w]) : bf_lo(a1w[w]);
+        const float t = (as > ap ? 1.f : 0.f) - (as < ap ? 1.f : 0.f);
+        const float sr = (as > 0.f ? 1.f : 0.f) - (as < 0.f ? 1.f : 0.f);
+        v[2 * w + h] = fmaf(d1, sr, fmaf(d0, t, v[2 * w + h]));
+      }
+    }
+  }
+  if (p.in1_kind == 2) {
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      v[2 * w] += bf_lo(a1w[w]);
+      v[2 * w + 1] += bf_hi(a1w[w]);
+    }
+  }
+  if (p.in0_kind == 2) {       // residual skip from the unit's own bf16 operand: undo the LeakyReLU
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      const float a0 = bf_lo(a0w[w]), a1 = bf_hi(a0w[w]);
+      v[2 * w] += fminf(a0, a0 * p.res_inv_slope);
+      v[2 * w + 1] += fminf(a1, a1 * p.res_inv_slope);
+    }
+  }
+  if (p.res && valid) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(rf[i]);
+  }
+  if (p.out_f32 && valid) {
+    uint32_t o[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(v[i]);
+    st_words<32>(p.out_f32 + off, o);
+  }
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    float a0 = v[2 * w], a1 = v[2 * w + 1];
+    if (p.act == RAVE_ACT_LEAKY) {
+      a0 = fmaxf(a0, a0 * p.slope);
+      a1 = fmaxf(a1, a1 * p.slope);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+    pk[w] = *reinterpret_cast<uint32_t *>(&h);
+  }
+}
+
 // `part` of `parts` warps share one TMEM lane quadrant and take alternate 32-column chunks (the epilogue is
 // latency-bound -- tcgen05.ld, convert, store with ONE warp per scheduler -- so the CTA-pair kernel runs two)
 template <int BLOCK_N, bool X3>
 __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t taddr, int n0, bool valid, size_t orow,
                                             int fm_side, int part = 0, int parts = 1) {
   constexpr int MAIN = BLOCK_N / 32 * 32;
+  if (X3 && (p.act_cs & 31)) {
+    // split-operand rows whose positions are 16 (mod 32) channels wide (capacity-48 transposed convs: 48 channels per
+    // position): a 32-column chunk would straddle a [hi | lo] boundary -> 16-column chunks
+#pragma unroll 1
+    for (int c0 = part * 16; c0 < BLOCK_N; c0 += parts * 16)
+      tc_epi_chunk<16, X3>(p, taddr + c0, n0 + c0, valid, orow, fm_side);
+    return;
+  }
 #pragma unroll 1
   for (int c0 = part * 32; c0 < MAIN; c0 += parts * 32)
     tc_epi_chunk<32, X3>(p, taddr + c0, n0 + c0, valid, orow, fm_side);
@@ -403,7 +507,8 @@ struct SmemLayout2 {
 template <int BLOCK_N, int BLOCK_K, bool X3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const TcParams p) {
+                const __grid_constant__ CUtensorMap tmap_e0, const __grid_constant__ CUtensorMap tmap_e1,
+                const __grid_constant__ CUtensorMap tmap_eo, const TcParams p) {
   using L = SmemLayout2<BLOCK_N, BLOCK_K, X3>;
   constexpr int STAGES = L::STAGES;
   constexpr int UNITS = L::UNITS;
@@ -414,11 +519,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + p.bar_off);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *tfull_bar = empty_bar + STAGES;
   uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tempty_bar + ACC_STAGES);
+  uint64_t *efull_bar = tempty_bar + ACC_STAGES;       // chunk operands landed (loader warp -> epilogue)
+  uint64_t *eempty_bar = efull_bar + 2;                // chunk operands consumed (epilogue -> loader warp)
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(eempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -430,11 +537,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int n_mp = (n_mt + 1) >> 1;                  // M tile pairs
   const int num_tiles = n_mp * p.n_nt;
   const int kblocks = p.K * p.num_kb;
-  const int epi_warps = (int)(blockDim.x >> 5) - 2;      // 4 or 8 (launch configuration)
+  // 4 or 8 epilogue warps (launch configuration); the TMA-staged epilogue adds a chunk-loader warp after them
+  const int epi_warps = (int)(blockDim.x >> 5) - 2 - (p.etma ? 1 : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.etma) {
+      tma_prefetch_desc(&tmap_eo);
+      if (p.in0_kind) tma_prefetch_desc(&tmap_e0);
+      if (p.in1_kind) tma_prefetch_desc(&tmap_e1);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 2);        // leader's: its own arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[s], 1);
@@ -442,6 +555,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * epi_warps);       // leader's: the epilogue warps of both CTAs
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&efull_bar[s], 1);
+      mbar_init(&eempty_bar[s], epi_warps);
     }
     fence_barrier_init();
   }
@@ -567,6 +684,110 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);
     }
     __syncwarp();
+  } else if (p.etma && warp == 2 + epi_warps) {
+    // =========================== chunk loader (TMA-staged epilogue operands) ===========================
+    // Runs up to e_stages chunks ahead of the epilogue -- across tile boundaries, i.e. the next tile's operand rows
+    // arrive while its MMAs are still running.  Rows / batches beyond the tensor are zero-filled by the TMA unit.
+    const int n_in = (p.in0_kind ? 1 : 0) + (p.in1_kind ? 1 : 0);
+    if (n_in > 0) {
+      constexpr int NCHUNK = (BLOCK_N + 63) / 64;
+      const uint32_t stage_stride = (uint32_t)(n_in + 1) * ECH_BYTES;
+      int es = 0;
+      uint32_t eph = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int nt = tile % p.n_nt;
+        const int mt = (tile / p.n_nt) * 2 + (int)rank;
+        const int l0 = (mt % p.n_lt) * p.BL;
+        const int b0 = (mt / p.n_lt) * p.BB;
+        const int n0 = nt * BLOCK_N;
+        // feature-matching partner rows: the other batch half ([real; fake] batch), or -- fake-half launches -- the
+        // same coordinates of a tensor map based fm_half elements earlier
+        const int bp = p.fm_bh > 0 ? (b0 < p.fm_bh ? b0 + p.fm_bh : b0 - p.fm_bh) : b0;
+        for (int c = 0; c < NCHUNK; ++c) {
+          mbar_wait(&eempty_bar[es], eph ^ 1);
+          uint8_t *st = smem + p.epi_off + es * stage_stride;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&efull_bar[es], (uint32_t)n_in * ECH_BYTES);
+            if (p.in0_kind) tma_load_3d(st, &tmap_e0, &efull_bar[es], n0 + c * 64, l0, b0);
+            if (p.in1_kind)
+              tma_load_3d(st + (p.in0_kind ? ECH_BYTES : 0), &tmap_e1, &efull_bar[es], n0 + c * 64, l0,
+                          p.in1_kind == 1 ? bp : b0);
+          }
+          __syncwarp();
+          if (++es == p.e_stages) { es = 0; eph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 2 && p.etma) {
+    // =========================== epilogue, TMA-staged (8 warps: TMEM quadrant x 32-column half of a chunk) ==========
+    constexpr int NCHUNK = (BLOCK_N + 63) / 64;
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t rowoff = (uint32_t)row * 128u, rx = (uint32_t)(row & 7);
+    const int n_in = (p.in0_kind ? 1 : 0) + (p.in1_kind ? 1 : 0);
+    const uint32_t stage_stride = (uint32_t)(n_in + 1) * ECH_BYTES;
+    const bool issuer = threadIdx.x == 64;       // first epilogue thread: issues and tracks the bulk stores
+    int es = 0;
+    uint32_t eph = 0;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = tile % p.n_nt;
+      const int mt = (tile / p.n_nt) * 2 + (int)rank;
+      const int lt = mt % p.n_lt;
+      const int bg = mt / p.n_lt;
+      const int n0 = nt * BLOCK_N;
+      const int l0 = lt * p.BL, b0 = bg * p.BB;
+      const int b = b0 + row / p.BL;
+      const int l = l0 + row % p.BL;
+      const bool valid = (mt < n_mt) && (b < p.B) && (l < p.Lout) && !(p.dbg & 1);
+      const size_t orow = (size_t)b * p.out_rows + (size_t)l;
+      const int fm_side = p.fm_d ? (b < p.fm_bh ? 1 : -1) : 0;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        uint8_t *st = smem + p.epi_off + es * stage_stride;
+        uint8_t *outb = st + n_in * ECH_BYTES;
+        const int ccol = c * 64 + half * 32;
+        const bool active = ccol < BLOCK_N;      // BLOCK_N = 96: the last chunk has one 32-column half
+        uint32_t pk[16];
+        if (n_in) mbar_wait(&efull_bar[es], eph);
+        if (active)
+          tc_epi_chunk_tma(p, taddr + ccol, n0 + ccol, valid, orow, fm_side, st, st + (p.in0_kind ? ECH_BYTES : 0), rowoff,
+                           rx, half, pk);
+        if (c == NCHUNK - 1) {                   // accumulator stage read out: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
+        }
+        if (n_in) {                              // operand chunk consumed (registers hold what is needed)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&eempty_bar[es]);
+        }
+        // the bulk store that last read this output buffer must be done reading it
+        if (issuer) {
+          if (p.e_stages == 2) bulk_wait_read<1>();
+          else bulk_wait_read<0>();
+        }
+        named_bar_sync(1, 256);
+        if (active && !(p.dbg & 1)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sts128(outb + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), pk + 4 * q);
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 256);
+        if (issuer && !(p.dbg & 1)) {
+          tma_store_3d(&tmap_eo, outb, n0 + c * 64, l0, b0);
+          bulk_commit();
+        }
+        if (++es == p.e_stages) { es = 0; eph ^= 1; }
+      }
+    }
+    if (issuer) bulk_wait_all();
   } else if (warp >= 2) {
     // =========================== epilogue (4 warps in each CTA) ===========================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -720,15 +941,18 @@ static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &
   return 0;
 }
 
+constexpr int SMEM_MAX = 227 * 1024;       // dynamic shared memory a CTA may opt into on sm_100
+
 template <int BN, int BK, bool X3>
-static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t stream) {
+static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap *te, const TcParams &p,
+                   cudaStream_t stream) {
   using L = SmemLayout2<BN, BK, X3>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::TOTAL);
+                                         SMEM_MAX);
     if (e != cudaSuccess) {
-      set_error("conv1d_tc(2cta): cudaFuncSetAttribute(%d bytes): %s", L::TOTAL, cudaGetErrorString(e));
+      set_error("conv1d_tc(2cta): cudaFuncSetAttribute(%d bytes): %s", SMEM_MAX, cudaGetErrorString(e));
       return 2;
     }
     attr = true;
@@ -741,32 +965,58 @@ static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams 
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
   TcParams q = p;
-  q.stages = L::STAGES;
+  // shared memory: [pipeline stages][chunk buffers of the TMA-staged epilogue][barriers]
+  int epi_bytes = 0;
+  if (q.etma) {
+    const int n_in = (q.in0_kind ? 1 : 0) + (q.in1_kind ? 1 : 0);
+    const int budget = SMEM_MAX - 1024 - 256;
+    // two chunk buffers unless that leaves the mainloop fewer than 4 stages
+    q.e_stages = 2;
+    if ((budget - 2 * (n_in + 1) * ECH_BYTES) / L::STAGE_BYTES < 4) q.e_stages = 1;
+    {
+      const char *e = getenv("RAVE_TC_ESTAGES");
+      if (e && (atoi(e) == 1 || atoi(e) == 2)) q.e_stages = atoi(e);
+    }
+    epi_bytes = q.e_stages * (n_in + 1) * ECH_BYTES;
+    q.stages = (budget - epi_bytes) / L::STAGE_BYTES;
+    if (q.stages > L::STAGES) q.stages = L::STAGES;
+    if (q.stages < 2) {          // does not fit: per-thread epilogue
+      q.etma = 0;
+      epi_bytes = 0;
+    }
+  }
+  if (!q.etma) q.stages = L::STAGES;
   {
     const char *e = getenv("RAVE_TC_STAGES");
-    if (e && atoi(e) >= 2 && atoi(e) < L::STAGES) q.stages = atoi(e);
+    if (e && atoi(e) >= 2 && atoi(e) < q.stages) q.stages = atoi(e);
   }
+  q.epi_off = q.stages * L::STAGE_BYTES;
+  q.bar_off = q.epi_off + epi_bytes;
+  const int smem_bytes = q.bar_off + 256 + 1024;
   // epilogue warps: 8 (two per TMEM quadrant) when a tile has little MMA work per output column -- those layers are
   // bound by the latency of the TMEM-load / convert / store chain -- else 4 (the extra warps only take issue slots
-  // from the tensor-bound loops); RAVE_TC_EPIWARPS overrides
+  // from the tensor-bound loops); RAVE_TC_EPIWARPS overrides.  The TMA-staged epilogue always runs 8 (+ its loader warp).
   int epi = ((long)p.K * p.Cin <= 1024 || p.dact_src || p.res_bf16 || p.res_act || p.res) ? 8 : 4;
   {
     const char *e = getenv("RAVE_TC_EPIWARPS");
     if (e && (atoi(e) == 4 || atoi(e) == 8)) epi = atoi(e);
   }
-  conv_tc2_kernel<BN, BK, X3><<<2 * pairs, 64 + 32 * epi, L::TOTAL, stream>>>(ta, tb, q);
+  if (q.etma) epi = 8;
+  conv_tc2_kernel<BN, BK, X3><<<2 * pairs, 64 + 32 * epi + (q.etma ? 32 : 0), smem_bytes, stream>>>(ta, tb, te[0], te[1],
+                                                                                                 te[2], q);
   RAVE_CHECK_LAUNCH("conv1d_tc(2cta)");
   return 0;
 }
 
 template <int BK, bool X3>
-static int dispatch_n2(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t s) {
+static int dispatch_n2(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap *te, const TcParams &p,
+                       cudaStream_t s) {
   switch (bn) {
-    case 256: return launch2<256, BK, X3>(ta, tb, p, s);
-    case 192: return launch2<192, BK, X3>(ta, tb, p, s);
-    case 128: return launch2<128, BK, X3>(ta, tb, p, s);
-    case 96: return launch2<96, BK, X3>(ta, tb, p, s);
-    case 64: return launch2<64, BK, X3>(ta, tb, p, s);
+    case 256: return launch2<256, BK, X3>(ta, tb, te, p, s);
+    case 192: return launch2<192, BK, X3>(ta, tb, te, p, s);
+    case 128: return launch2<128, BK, X3>(ta, tb, te, p, s);
+    case 96: return launch2<96, BK, X3>(ta, tb, te, p, s);
+    case 64: return launch2<64, BK, X3>(ta, tb, te, p, s);
   }
   set_error("conv1d_tc(2cta): no kernel for BLOCK_N=%d", bn);
   return 1;
@@ -790,11 +1040,11 @@ static int dispatch_n(int bn, const CUtensorMap &ta, const CUtensorMap &tb, cons
 }
 
 template <bool X3>
-static int dispatch_all(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
-                        cudaStream_t s) {
+static int dispatch_all(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap *te,
+                        const TcParams &p, cudaStream_t s) {
   if (use2)
-    return BK == 64 ? dispatch_n2<64, X3>(BN, ta, tb, p, s) : BK == 32 ? dispatch_n2<32, X3>(BN, ta, tb, p, s)
-                                                                       : dispatch_n2<16, X3>(BN, ta, tb, p, s);
+    return BK == 64 ? dispatch_n2<64, X3>(BN, ta, tb, te, p, s) : BK == 32 ? dispatch_n2<32, X3>(BN, ta, tb, te, p, s)
+                                                                           : dispatch_n2<16, X3>(BN, ta, tb, te, p, s);
   switch (BK) {
     case 64: return dispatch_n<64, X3>(BN, ta, tb, p, s);
     case 32: return dispatch_n<32, X3>(BN, ta, tb, p, s);
@@ -806,12 +1056,12 @@ static int dispatch_all(bool use2, int BK, int BN, const CUtensorMap &ta, const 
 
 // The split-operand (x3) instantiations live in their own translation unit (conv_tc_x3.cu includes this file with
 // RAVE_TC_X3_UNIT defined) so that the two sets of ~40 kernels compile in parallel.
-int conv_tc_dispatch_x3(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
-                        cudaStream_t s);
+int conv_tc_dispatch_x3(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap *te,
+                        const TcParams &p, cudaStream_t s);
 #ifdef RAVE_TC_X3_UNIT
-int conv_tc_dispatch_x3(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
-                        cudaStream_t s) {
-  return dispatch_all<true>(use2, BK, BN, ta, tb, p, s);
+int conv_tc_dispatch_x3(bool use2, int BK, int BN, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap *te,
+                        const TcParams &p, cudaStream_t s) {
+  return dispatch_all<true>(use2, BK, BN, ta, tb, te, p, s);
 }
 #endif
 
@@ -905,8 +1155,8 @@ static int conv1d_tc_fwd_impl(const void *xa, const void *wt, const float *bias,
   p.x3 = x3 ? 1 : 0;
   p.act_ld = x3 ? 2 * Cout : Cout;
   p.act_cs = act_cs > 0 ? act_cs : Cout;
-  RAVE_CHECK_ARG(!x3 || (Cout % p.act_cs == 0 && p.act_cs % 16 == 0 && (p.act_cs % 32 == 0 || p.act_cs == Cout)),
-                 "conv1d_tc(x3): %d channels per position do not tile the %d-column rows in 32-column chunks", p.act_cs,
+  RAVE_CHECK_ARG(!x3 || (Cout % p.act_cs == 0 && p.act_cs % 16 == 0),
+                 "conv1d_tc(x3): %d channels per position do not tile the %d-column rows in 16-column chunks", p.act_cs,
                  Cout);
   RAVE_CHECK_ARG(!x3 || !res_act || p.act_cs == Cout, "conv1d_tc(x3): res_act needs one position per row");
   p.dbg = 0;
@@ -957,9 +1207,43 @@ static int conv1d_tc_fwd_impl(const void *xa, const void *wt, const float *bias,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "conv1d_tc: tensor map B encode failed (%d)", (int)r);
   }
+  // ---- TMA-staged epilogue (see TcParams::etma): bf16 chunk operands and the bf16 output as 3-D maps (c, row, batch)
+  CUtensorMap te[3];
+  memset(te, 0, sizeof(te));
+  p.etma = 0; p.in0_kind = p.in1_kind = 0; p.e_stages = 0; p.epi_off = p.bar_off = 0;
+  {
+    static int want_etma = -1;
+    if (want_etma < 0) {
+      const char *e = getenv("RAVE_TC_ETMA");
+      want_etma = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool slots_ok = !(dact_src && res_act) && !(fm_d && res_bf16);
+    const bool fm_ok = !fm_d || p.fm_bh == 0 || (p.fm_bh % p.BB == 0);
+    if (want_etma && use2 && !x3 && out_act && p.out_row_stride == 1 && p.out_row_offset == 0 && slots_ok && fm_ok &&
+        (BN % 64 == 0 || Cout == BN) && Cout >= 64) {
+      p.etma = 1;
+      p.in0_kind = dact_src ? 1 : res_act ? 2 : 0;
+      p.in1_kind = fm_d ? 1 : res_bf16 ? 2 : 0;
+      const void *base[3] = {dact_src ? dact_src : res_act,
+                             fm_d ? (const void *)((const __nv_bfloat16 *)dact_src - (fm_bh < 0 ? p.fm_half : 0)) : res_bf16,
+                             out_act};
+      for (int i = 0; i < 3 && p.etma; ++i) {
+        if (!base[i]) continue;
+        cuuint64_t dims[3] = {(cuuint64_t)Cout, (cuuint64_t)Lout, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)Cout * 2, (cuuint64_t)Cout * 2 * p.out_rows};
+        cuuint32_t box[3] = {64, (cuuint32_t)p.BL, (cuuint32_t)p.BB};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&te[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base[i]), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) p.etma = 0;        // e.g. a row pitch the TMA unit cannot express: per-thread epilogue
+      }
+      if (!p.etma) p.in0_kind = p.in1_kind = 0;
+    }
+  }
   cudaStream_t s = (cudaStream_t)stream;
-  if (x3) return conv_tc_dispatch_x3(use2, BK, BN, ta, tb, p, s);
-  return dispatch_all<false>(use2, BK, BN, ta, tb, p, s);
+  if (x3) return conv_tc_dispatch_x3(use2, BK, BN, ta, tb, te, p, s);
+  return dispatch_all<false>(use2, BK, BN, ta, tb, te, p, s);
 }
 
 extern "C" int rave_conv1d_tc_fwd(const void *xa, const void *wt, const float *bias, const float *res,

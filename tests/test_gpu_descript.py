@@ -53,8 +53,10 @@ def test_descript_mrd_vs_oracle():
     g_o = torch.autograd.grad(sum((b * p).sum() for b, p in zip(want, probes)), [xo] + [po[k] for k in names])
     pg = dict(mrd.named_parameters())
     g = torch.autograd.grad(sum((a * p.cuda()).sum() for a, p in zip(got, probes)), [xg] + [pg[k] for k in names])
-    for k, a, b in zip(["x"] + names, g, g_o):
-        assert rel_l2(a, b) < 5e-4, (k, rel_l2(a, b))
+    errs = sorted(((rel_l2(a, b), k) for k, a, b in zip(["x"] + names, g, g_o)), reverse=True)
+    print("MRD gradient rel-L2, worst five:", [(k, f"{e:.2e}") for e, k in errs[:5]])
+    for e, k in errs:
+        assert e < 5e-4, (k, e)
 
 
 def test_descript_discriminator_full_vs_oracle():

@@ -463,7 +463,8 @@ def test_training_step_matches_reference_goldens_fp32():
     2e-6 / 1.1e-2 from an fp64 evaluation); post-step parameters by counting elements whose Adam update differs."""
     from tests.test_oracle_golden import GRAD_TOL, UPD_FRAC
     g, out = _run_golden_training_steps("fp32")
-    prev = g["state_dict"]
+    prev = g["state_dict"]           # the reference's parameters before the step ...
+    prev_ours = g["state_dict"]      # ... and ours (the two runs drift apart by the tolerated update differences)
     for st, (logs, grads, sd) in zip(g["steps"], out):
         for k, want in st["logs"].items():
             if k == "beta_factor":
@@ -483,7 +484,7 @@ def test_training_step_matches_reference_goldens_fp32():
             if not want.is_floating_point():
                 continue
             upd_ref = (want - prev[k]).double()
-            upd = (sd[k] - prev[k]).double()
+            upd = (sd[k] - prev_ours[k]).double()
             if upd_ref.abs().max() == 0:
                 assert upd.abs().max() == 0, (st["name"], k)
             else:
@@ -491,6 +492,7 @@ def test_training_step_matches_reference_goldens_fp32():
                 n_all += upd.numel()
         assert n_all > 0 and n_bad <= UPD_FRAC[st["name"]] * n_all, (st["name"], n_bad, n_all)
         prev = st["state_dict"]
+        prev_ours = sd
 
 
 def test_training_step_matches_reference_goldens_bf16():
