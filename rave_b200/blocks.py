@@ -451,13 +451,17 @@ class DiscreteEncoder(nn.Module):
         else:
             diff = torch.zeros_like(z).mean()
         if self.noise_augmentation:
-            noise = torch.randn(z.shape[0], self.noise_augmentation, z.shape[-1]).type_as(z)
+            noise = torch.randn(z.shape[0], self.noise_augmentation, z.shape[-1], device=z.device, dtype=z.dtype)
             z = torch.cat([z, noise], 1)
         return z, diff
 
     def set_warmed_up(self, state: bool):
-        state = torch.tensor(int(state), device=self.warmed_up.device)
-        self.warmed_up = state
+        # host mirror as in VariationalEncoder: the buffer is rewritten only when the flag changes (a tensor built from a
+        # Python int is a pageable host->device copy, which a CUDA-graph capture rejects)
+        state = bool(state)
+        if self.__dict__.get("_warmed_up_host") != state:
+            self.warmed_up = torch.tensor(int(state), device=self.warmed_up.device)
+            self.__dict__["_warmed_up_host"] = state
 
     def forward(self, x):
         return self.encoder(x)

@@ -65,7 +65,8 @@ struct TcParams {
   int e_stages;            // chunk buffers in flight (1 or 2)
   int epi_off, bar_off;    // byte offsets of the chunk buffers / the barriers in (1024-aligned) shared memory
   int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue, 8 = no L2 prefetch, 2 = skip the
-                           // activation TMA loads, 4 = skip the weight TMA loads (results are garbage)
+                           // activation TMA loads, 4 = skip the weight TMA loads (results are garbage); TMA-staged
+                           // epilogue: 16 = do not wait for earlier bulk stores, 32 = no named barriers, 64 = no TMEM load
 };
 
 template <int BLOCK_N, int BLOCK_K, bool X3 = false>
@@ -232,7 +233,7 @@ __device__ __forceinline__ void tc_epi_chunk_tma(const TcParams &p, uint32_t tad
     for (int q = 0; q < 4; ++q) lds128(in1 + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), a1w + 4 * q);
   }
   if (p.res && valid) ld_words<32>(p.res + off, rf);
-  tmem_ld_32x32(taddr, v);
+  if (!(p.dbg & 64)) tmem_ld_32x32(taddr, v);
   if (p.bias) {
     const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + co);
 #pragma unroll
@@ -703,6 +704,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // feature-matching partner rows: the other batch half ([real; fake] batch), or -- fake-half launches -- the
         // same coordinates of a tensor map based fm_half elements earlier
         const int bp = p.fm_bh > 0 ? (b0 < p.fm_bh ? b0 + p.fm_bh : b0 - p.fm_bh) : b0;
+        // With two chunk buffers only ~64 KB of operand rows are in flight per SM: less than HBM latency x bandwidth.
+        // Pull the NEXT tile's chunks into L2 now (one TMA prefetch per box), so that its loads are L2 hits.
+        if (!(p.dbg & 8)) {
+          const int tile2 = tile + num_pairs;
+          if (tile2 < num_tiles && elect_one()) {
+            const int mt2 = (tile2 / p.n_nt) * 2 + (int)rank;
+            const int l2 = (mt2 % p.n_lt) * p.BL, b2 = (mt2 / p.n_lt) * p.BB;
+            const int n2 = (tile2 % p.n_nt) * BLOCK_N;
+            const int bp2 = p.fm_bh > 0 ? (b2 < p.fm_bh ? b2 + p.fm_bh : b2 - p.fm_bh) : b2;
+            for (int c = 0; c < NCHUNK; ++c) {
+              if (p.in0_kind) tma_prefetch_3d(&tmap_e0, n2 + c * 64, l2, b2);
+              if (p.in1_kind) tma_prefetch_3d(&tmap_e1, n2 + c * 64, l2, p.in1_kind == 1 ? bp2 : b2);
+            }
+          }
+          __syncwarp();
+        }
         for (int c = 0; c < NCHUNK; ++c) {
           mbar_wait(&eempty_bar[es], eph ^ 1);
           uint8_t *st = smem + p.epi_off + es * stage_stride;
@@ -769,17 +786,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (lane == 0) mbar_arrive(&eempty_bar[es]);
         }
         // the bulk store that last read this output buffer must be done reading it
-        if (issuer) {
+        if (issuer && !(p.dbg & 16)) {
           if (p.e_stages == 2) bulk_wait_read<1>();
           else bulk_wait_read<0>();
         }
-        named_bar_sync(1, 256);
+        if (!(p.dbg & 32)) named_bar_sync(1, 256);
         if (active && !(p.dbg & 1)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) sts128(outb + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), pk + 4 * q);
         }
         fence_proxy_async();
-        named_bar_sync(1, 256);
+        if (!(p.dbg & 32)) named_bar_sync(1, 256);
         if (issuer && !(p.dbg & 1)) {
           tma_store_3d(&tmap_eo, outb, n0 + c * 64, l0, b0);
           bulk_commit();
@@ -1212,11 +1229,8 @@ static int conv1d_tc_fwd_impl(const void *xa, const void *wt, const float *bias,
   memset(te, 0, sizeof(te));
   p.etma = 0; p.in0_kind = p.in1_kind = 0; p.e_stages = 0; p.epi_off = p.bar_off = 0;
   {
-    static int want_etma = -1;
-    if (want_etma < 0) {
-      const char *e = getenv("RAVE_TC_ETMA");
-      want_etma = (e && e[0] == '0') ? 0 : 1;
-    }
+    const char *e_etma = getenv("RAVE_TC_ETMA");          // read per call: scripts/ablate_tc.py flips it
+    const int want_etma = (e_etma && e_etma[0] == '0') ? 0 : 1;
     const bool slots_ok = !(dact_src && res_act) && !(fm_d && res_bf16);
     const bool fm_ok = !fm_d || p.fm_bh == 0 || (p.fm_bh % p.BB == 0);
     if (want_etma && use2 && !x3 && out_act && p.out_row_stride == 1 && p.out_row_offset == 0 && slots_ok && fm_ok &&

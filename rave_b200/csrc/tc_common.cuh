@@ -111,6 +111,11 @@ __device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *m, ui
       ::"r"(smem_u32(smem)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// pull a box into L2 only (no shared-memory destination, no barrier): hides the HBM latency of a later tma_load_3d
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(m), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *smem, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m),
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)

@@ -244,9 +244,15 @@ class CombineDiscriminators(nn.Module):
             for layer in disc.layers:
                 if not isinstance(layer, ConvNet) or layer._tc_specs() is None:
                     return False
-                first = layer._tc_specs()[0]
+                specs = layer._tc_specs()
+                first = specs[0]
                 if first.Cin != 1 or first.dil != 1:
                     return False
+                # the statistics are read from the bf16 operand a = LeakyReLU(h) of the NEXT layer: every hidden feature
+                # needs a LeakyReLU consumer and un-padded channels (tiny test capacities have Cout % 16 != 0)
+                for s, nxt in zip(specs[:-1], specs[1:]):
+                    if s.cout_pad or nxt.pre_act != ops.ACT_LEAKY:
+                        return False
         return True
 
     def forward_fm(self, x, fake_grad_only: bool = False):

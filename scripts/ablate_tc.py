@@ -4,6 +4,7 @@ shallower ring (RAVE_TC_STAGES) / other L2 promotion.  Results with loads remove
 Usage (GPU box): python scripts/ablate_tc.py"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from rave_b200 import ops
 
@@ -36,8 +37,16 @@ CONFIGS = [
     ("no L2 prefetch of epilogue operands", {"RAVE_TC_DBG": "8"}),
     ("L2 promotion none", {"RAVE_TC_L2PROMO": "0"}),
     ("1-CTA kernel", {"RAVE_TC_2CTA": "0"}),
+    ("per-thread epilogue (no TMA staging)", {"RAVE_TC_ETMA": "0"}),
+    ("etma: 1 chunk buffer", {"RAVE_TC_ESTAGES": "1"}),
+    ("etma: no wait on earlier bulk stores", {"RAVE_TC_DBG": "16"}),
+    ("etma: no named barriers", {"RAVE_TC_DBG": "32"}),
+    ("etma: no barriers, no store wait", {"RAVE_TC_DBG": "48"}),
+    ("etma: no TMEM load", {"RAVE_TC_DBG": "64"}),
+    ("etma: no staging stores, no TMA store", {"RAVE_TC_DBG": "1"}),
+    ("etma: nothing but the loop (1+32+64)", {"RAVE_TC_DBG": "97"}),
 ]
-KEYS = ["RAVE_TC_STAGES", "RAVE_TC_DBG", "RAVE_TC_L2PROMO", "RAVE_TC_EPIWARPS"]
+KEYS = ["RAVE_TC_STAGES", "RAVE_TC_DBG", "RAVE_TC_L2PROMO", "RAVE_TC_EPIWARPS", "RAVE_TC_ETMA", "RAVE_TC_ESTAGES"]
 
 FILTER = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, B, Cin, Cout, Lin, K, stride, dil, pad in SHAPES:
@@ -62,16 +71,8 @@ for name, B, Cin, Cout, Lin, K, stride, dil, pad in SHAPES:
         def run():
             ops.conv1d_tc(x, wt, None, None, stride, dil, (pad, pad), 0 if bwd else 1, 0.2, want_f32=False,
                           want_act=False, out_f32=None, out_act=oa, Lout=Lout, dact_src=dact, fm_d=fmd)
-        for _ in range(3):
-            run()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            run()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 20
+        from _timing import graph_time_us
+        ms = graph_time_us(lambda i: run(), n=10) * 1e-3
         print(f"   {cname:22s} {ms*1e3:8.1f} us  {fl/ms/1e9:6.0f} TFLOP/s", flush=True)
 for k in KEYS:
     os.environ.pop(k, None)
