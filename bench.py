@@ -320,7 +320,7 @@ def dominant_launch_roofline(torch, prof, pk):
         name, ints, ptrs = key
         if name != "rave_conv1d_tc_fwd":
             return name
-        v = _lib.load().rave_conv1d_tc_plan(ints[0], ints[1], ints[4], ints[5])
+        v = _lib.load().rave_conv1d_tc_plan(ints[0], ints[1], ints[4], ints[5], ints[6])
         return f"conv_tc{'2' if v >> 24 else ''}_kernel<{v & 0xfff},{(v >> 12) & 0xfff}>"
     by_inst = {}
     for key, v in tot.items():

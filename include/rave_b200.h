@@ -172,7 +172,7 @@ int rave_dilated_unit_tc_fwd(const void *xa_bf16, const void *w3t_bf16, const vo
                              float slope_in, float slope_mid, int act_out, float slope_out, void *stream);
 /* kernel instance rave_conv1d_tc_fwd selects for a shape: BLOCK_N | BLOCK_K << 12 | (CTA pair ? 1 << 24 : 0), 0 = none
  * (bench.py names the dominant kernel with it) */
-int rave_conv1d_tc_plan(int B, int Cin, int Cout, int Lout);
+int rave_conv1d_tc_plan(int B, int Cin, int Cout, int Lout, int K);
 int rave_conv1d_tc_fwd(const void *xa_bf16, const void *wt_bf16, const float *bias, const float *res,
                        const void *res_bf16, const void *dact_src_bf16, const void *res_act_bf16, float res_slope,
                        float *out_f32, void *out_act_bf16,

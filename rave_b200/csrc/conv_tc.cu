@@ -62,6 +62,7 @@ struct TcParams {
   int etma;                // 0 = per-thread global loads / stores
   int in0_kind;            // chunk operand slot A: 0 none, 1 dact_src, 2 res_act
   int in1_kind;            // chunk operand slot B: 0 none, 1 feature-matching partner rows, 2 res_bf16
+  int emode;               // compiled epilogue specialisation (tc_epi_chunk_tma) or -1: run-time flags
   int e_stages;            // chunk buffers in flight (1 or 2)
   int epi_off, bar_off;    // byte offsets of the chunk buffers / the barriers in (1024-aligned) shared memory
   int dbg;                 // ablation switches for scripts/ablate_tc.py: 1 = no epilogue, 8 = no L2 prefetch, 2 = skip the
@@ -216,40 +217,56 @@ __device__ __forceinline__ void tc_epi_chunk(const TcParams &p, uint32_t taddr, 
 // TMA-staged variant of tc_epi_chunk (32 rows x 32 channels per warp): the bf16 operands come from the chunk buffers
 // the loader warp filled ([128 rows][128 bytes], SWIZZLE_128B: 16-byte unit u of row r sits at r*128 + ((u ^ (r & 7)) << 4),
 // so the 8 lanes of a shared-memory phase hit 8 different bank groups), the activated output is returned packed in
-// `pk` for the caller to stage.  fp32 streams (bias, res, out_f32) are rare and small: per-thread accesses as before.
+// `pk` for the caller to stage.  fp32 streams (res, out_f32) are rare and small: per-thread accesses, generic mode only.
+//
+// The epilogue of the HBM-bound launches is ISSUE-bound (ncu source view, profiles/r2_epilogue_issue.md: ~310
+// instructions per warp and 32 x 32 chunk with runtime flags, 2 warps per scheduler), so the frequent operand
+// combinations are compiled as specialisations (MODE >= 0: bit 0 bias, bit 1 LeakyReLU output, bits 2-3 in0_kind,
+// bits 4-5 in1_kind; no fp32 streams, no ablation switches) and the arithmetic runs on packed pairs: add / mul as
+// f32x2 (sm_100 FADD2 / FMUL2), LeakyReLU as max(bf16x2(t), bf16x2(s t)) -- rounding is monotone, so this equals
+// bf16(max(t, s t)) bit for bit.  MODE = -1 keeps every flag at run time.
 constexpr int ECH_BYTES = 128 * 128;      // one [128 x 64] bf16 chunk
+template <int MODE>
 __device__ __forceinline__ void tc_epi_chunk_tma(const TcParams &p, uint32_t taddr, int co, bool valid, size_t orow,
                                                  int fm_side, const uint8_t *in0, const uint8_t *in1, uint32_t rowoff,
                                                  uint32_t rx, int half, uint32_t *pk) {
+  constexpr bool GEN = MODE < 0;
+  const bool has_bias = GEN ? (p.bias != nullptr) : ((MODE & 1) != 0);
+  const bool leaky = GEN ? (p.act == RAVE_ACT_LEAKY) : ((MODE & 2) != 0);
+  const int k0 = GEN ? p.in0_kind : ((MODE >> 2) & 3);
+  const int k1 = GEN ? p.in1_kind : ((MODE >> 4) & 3);
   float v[32];
   uint32_t a0w[16], a1w[16], rf[32];
   const size_t off = orow * p.Cout + co;
-  if (p.in0_kind) {
+  if (k0) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) lds128(in0 + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), a0w + 4 * q);
   }
-  if (p.in1_kind) {
+  if (k1) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) lds128(in1 + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), a1w + 4 * q);
   }
-  if (p.res && valid) ld_words<32>(p.res + off, rf);
-  if (!(p.dbg & 64)) tmem_ld_32x32(taddr, v);
-  if (p.bias) {
+  if (GEN && p.res && valid) ld_words<32>(p.res + off, rf);
+  if (!GEN || !(p.dbg & 64)) tmem_ld_32x32(taddr, v);
+  if (has_bias) {
     const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + co);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 bb = __ldg(b4 + i);
-      v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+      const float2 t0 = __fadd2_rn(make_float2(v[4 * i], v[4 * i + 1]), make_float2(bb.x, bb.y));
+      const float2 t1 = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(bb.z, bb.w));
+      v[4 * i] = t0.x; v[4 * i + 1] = t0.y; v[4 * i + 2] = t1.x; v[4 * i + 3] = t1.y;
     }
   }
-  if (p.in0_kind == 1) {       // LeakyReLU' from the sign bits of the saved operand
+  if (k0 == 1) {       // LeakyReLU' from the sign bits of the saved operand
 #pragma unroll
     for (int w = 0; w < 16; ++w) {
-      if (a0w[w] & 0x00008000u) v[2 * w] *= p.slope;
-      if (a0w[w] & 0x80000000u) v[2 * w + 1] *= p.slope;
+      const float2 m = make_float2((a0w[w] & 0x00008000u) ? p.slope : 1.f, (a0w[w] & 0x80000000u) ? p.slope : 1.f);
+      const float2 t = __fmul2_rn(make_float2(v[2 * w], v[2 * w + 1]), m);
+      v[2 * w] = t.x; v[2 * w + 1] = t.y;
     }
   }
-  if (p.in1_kind == 1) {       // feature-matching gradient (see tc_epi_chunk)
+  if (k1 == 1) {       // feature-matching gradient (see tc_epi_chunk)
     const float d0 = __ldg(p.fm_d), d1 = fm_side > 0 ? __ldg(p.fm_d + 1) : 0.f;
 #pragma unroll
     for (int w = 0; w < 16; ++w) {
@@ -263,14 +280,14 @@ __device__ __forceinline__ void tc_epi_chunk_tma(const TcParams &p, uint32_t tad
       }
     }
   }
-  if (p.in1_kind == 2) {
+  if (k1 == 2) {
 #pragma unroll
     for (int w = 0; w < 16; ++w) {
-      v[2 * w] += bf_lo(a1w[w]);
-      v[2 * w + 1] += bf_hi(a1w[w]);
+      const float2 t = __fadd2_rn(make_float2(v[2 * w], v[2 * w + 1]), make_float2(bf_lo(a1w[w]), bf_hi(a1w[w])));
+      v[2 * w] = t.x; v[2 * w + 1] = t.y;
     }
   }
-  if (p.in0_kind == 2) {       // residual skip from the unit's own bf16 operand: undo the LeakyReLU
+  if (k0 == 2) {       // residual skip from the unit's own bf16 operand: undo the LeakyReLU
 #pragma unroll
     for (int w = 0; w < 16; ++w) {
       const float a0 = bf_lo(a0w[w]), a1 = bf_hi(a0w[w]);
@@ -278,26 +295,119 @@ __device__ __forceinline__ void tc_epi_chunk_tma(const TcParams &p, uint32_t tad
       v[2 * w + 1] += fminf(a1, a1 * p.res_inv_slope);
     }
   }
-  if (p.res && valid) {
+  if (GEN && p.res && valid) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(rf[i]);
   }
-  if (p.out_f32 && valid) {
+  if (GEN && p.out_f32 && valid) {
     uint32_t o[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(v[i]);
     st_words<32>(p.out_f32 + off, o);
   }
+  if (leaky) {
+    const float2 s2 = make_float2(p.slope, p.slope);
 #pragma unroll
-  for (int w = 0; w < 16; ++w) {
-    float a0 = v[2 * w], a1 = v[2 * w + 1];
-    if (p.act == RAVE_ACT_LEAKY) {
-      a0 = fmaxf(a0, a0 * p.slope);
-      a1 = fmaxf(a1, a1 * p.slope);
+    for (int w = 0; w < 16; ++w) {
+      const float2 t = make_float2(v[2 * w], v[2 * w + 1]);
+      const float2 u = __fmul2_rn(t, s2);
+      const __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(t.x, t.y), __floats2bfloat162_rn(u.x, u.y));
+      pk[w] = *reinterpret_cast<const uint32_t *>(&h);
     }
-    __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-    pk[w] = *reinterpret_cast<uint32_t *>(&h);
+  } else {
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * w], v[2 * w + 1]);
+      pk[w] = *reinterpret_cast<const uint32_t *>(&h);
+    }
   }
+}
+
+// The epilogue warps' whole tile loop of the TMA-staged path (8 warps: TMEM quadrant x 32-column half of a chunk).
+struct EtmaCtx {
+  uint8_t *smem;
+  uint64_t *tfull_bar, *tempty_bar, *efull_bar, *eempty_bar;
+  uint32_t tmem_base, rank;
+  int warp, lane, pair, num_pairs, num_tiles, n_mt;
+  const CUtensorMap *tmap_eo;
+};
+
+template <int BLOCK_N, int MODE>
+__device__ __forceinline__ void etma_epilogue(const TcParams &p, const EtmaCtx &x) {
+  constexpr bool GEN = MODE < 0;
+  constexpr int NCHUNK = (BLOCK_N + 63) / 64;
+  constexpr int ACC2 = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);
+  const int warp = x.warp, lane = x.lane;
+  const int quad = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const int row = quad * 32 + lane;
+  const uint32_t rowoff = (uint32_t)row * 128u, rx = (uint32_t)(row & 7);
+  const int k0 = GEN ? p.in0_kind : ((MODE >> 2) & 3);
+  const int k1 = GEN ? p.in1_kind : ((MODE >> 4) & 3);
+  const int n_in = (k0 ? 1 : 0) + (k1 ? 1 : 0);
+  const uint32_t stage_stride = (uint32_t)(n_in + 1) * ECH_BYTES;
+  const bool issuer = threadIdx.x == 64;       // first epilogue thread: issues and tracks the bulk stores
+  const int dbg = GEN ? p.dbg : 0;
+  int es = 0;
+  uint32_t eph = 0;
+  int it = 0;
+  for (int tile = x.pair; tile < x.num_tiles; tile += x.num_pairs, ++it) {
+    const int acc = it % ACC2;
+    const uint32_t acc_phase = (it / ACC2) & 1;
+    const int nt = tile % p.n_nt;
+    const int mt = (tile / p.n_nt) * 2 + (int)x.rank;
+    const int lt = mt % p.n_lt;
+    const int bg = mt / p.n_lt;
+    const int n0 = nt * BLOCK_N;
+    const int l0 = lt * p.BL, b0 = bg * p.BB;
+    const int b = b0 + row / p.BL;
+    const int l = l0 + row % p.BL;
+    const bool valid = (mt < x.n_mt) && (b < p.B) && (l < p.Lout) && !(dbg & 1);
+    const size_t orow = (size_t)b * p.out_rows + (size_t)l;
+    const int fm_side = k1 == 1 ? (b < p.fm_bh ? 1 : -1) : 0;
+    mbar_wait(&x.tfull_bar[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = x.tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+      uint8_t *st = x.smem + p.epi_off + es * stage_stride;
+      uint8_t *outb = st + n_in * ECH_BYTES;
+      const int ccol = c * 64 + half * 32;
+      const bool active = ccol < BLOCK_N;      // BLOCK_N = 96: the last chunk has one 32-column half
+      uint32_t pk[16];
+      if (n_in) mbar_wait(&x.efull_bar[es], eph);
+      if (active)
+        tc_epi_chunk_tma<MODE>(p, taddr + ccol, n0 + ccol, valid, orow, fm_side, st, st + (k0 ? ECH_BYTES : 0), rowoff, rx,
+                               half, pk);
+      if (c == NCHUNK - 1) {                   // accumulator stage read out: hand it back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&x.tempty_bar[acc], 0);
+      }
+      if (n_in) {                              // operand chunk consumed (registers hold what is needed)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x.eempty_bar[es]);
+      }
+      // the bulk store that last read this output buffer must be done reading it
+      if (issuer && !(dbg & 16)) {
+        if (p.e_stages == 2) bulk_wait_read<1>();
+        else bulk_wait_read<0>();
+      }
+      if (!(dbg & 32)) named_bar_sync(1, 256);
+      if (active && !(dbg & 1)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sts128(outb + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), pk + 4 * q);
+      }
+      fence_proxy_async();
+      if (!(dbg & 32)) named_bar_sync(1, 256);
+      if (issuer && !(dbg & 1)) {
+        tma_store_3d(x.tmap_eo, outb, n0 + c * 64, l0, b0);
+        bulk_commit();
+      }
+      if (++es == p.e_stages) { es = 0; eph ^= 1; }
+    }
+  }
+  if (issuer) bulk_wait_all();
 }
 
 // `part` of `parts` warps share one TMEM lane quadrant and take alternate 32-column chunks (the epilogue is
@@ -514,8 +624,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   constexpr int STAGES = L::STAGES;
   constexpr int UNITS = L::UNITS;
   constexpr int SWZ = BLOCK_K * 2;
-  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
-                                 : (ACC_STAGES * BLOCK_N <= 128) ? 128 : (ACC_STAGES * BLOCK_N <= 256) ? 256 : 512;
+  // accumulator stages: as many as the 512 TMEM columns hold (up to 4).  A tile's accumulator is owned by the epilogue
+  // from the MMAs' commit until its last TMEM read; on the HBM-bound layers (few MMAs per tile) that hand-over chain,
+  // not the tensor pipe, paces the kernel, and its throughput is (stages x BLOCK_N) columns per chain latency.
+  constexpr int ACC2 = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);
+  constexpr uint32_t TMEM_COLS = (ACC2 * BLOCK_N <= 32) ? 32 : (ACC2 * BLOCK_N <= 64) ? 64
+                                 : (ACC2 * BLOCK_N <= 128) ? 128 : (ACC2 * BLOCK_N <= 256) ? 256 : 512;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "cta_group::2 needs N % 32 == 0 (16 rows of B per CTA granule)");
 
   extern __shared__ uint8_t smem_raw[];
@@ -523,8 +637,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + p.bar_off);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *tfull_bar = empty_bar + STAGES;
-  uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
-  uint64_t *efull_bar = tempty_bar + ACC_STAGES;       // chunk operands landed (loader warp -> epilogue)
+  uint64_t *tempty_bar = tfull_bar + ACC2;
+  uint64_t *efull_bar = tempty_bar + ACC2;       // chunk operands landed (loader warp -> epilogue)
   uint64_t *eempty_bar = efull_bar + 2;                // chunk operands consumed (epilogue -> loader warp)
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(eempty_bar + 2);
 
@@ -553,7 +667,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_init(&full_bar[s], 2);        // leader's: its own arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < ACC_STAGES; ++s) {
+    for (int s = 0; s < ACC2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * epi_warps);       // leader's: the epilogue warps of both CTAs
     }
@@ -640,8 +754,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t phase = 0;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % ACC2;
+      const uint32_t acc_phase = (it / ACC2) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + acc * BLOCK_N;
@@ -682,7 +796,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // the peer's last arrivals must land before this CTA's barriers disappear
     if (it > 0) {
       const int last = it - 1;
-      mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);
+      for (int t = (it > ACC2 ? it - ACC2 : 0); t <= last; ++t) mbar_wait(&tempty_bar[t % ACC2], (t / ACC2) & 1);
     }
     __syncwarp();
   } else if (p.etma && warp == 2 + epi_warps) {
@@ -736,75 +850,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
     }
   } else if (warp >= 2 && p.etma) {
-    // =========================== epilogue, TMA-staged (8 warps: TMEM quadrant x 32-column half of a chunk) ==========
-    constexpr int NCHUNK = (BLOCK_N + 63) / 64;
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = quad * 32 + lane;
-    const uint32_t rowoff = (uint32_t)row * 128u, rx = (uint32_t)(row & 7);
-    const int n_in = (p.in0_kind ? 1 : 0) + (p.in1_kind ? 1 : 0);
-    const uint32_t stage_stride = (uint32_t)(n_in + 1) * ECH_BYTES;
-    const bool issuer = threadIdx.x == 64;       // first epilogue thread: issues and tracks the bulk stores
-    int es = 0;
-    uint32_t eph = 0;
-    int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % p.n_nt;
-      const int mt = (tile / p.n_nt) * 2 + (int)rank;
-      const int lt = mt % p.n_lt;
-      const int bg = mt / p.n_lt;
-      const int n0 = nt * BLOCK_N;
-      const int l0 = lt * p.BL, b0 = bg * p.BB;
-      const int b = b0 + row / p.BL;
-      const int l = l0 + row % p.BL;
-      const bool valid = (mt < n_mt) && (b < p.B) && (l < p.Lout) && !(p.dbg & 1);
-      const size_t orow = (size_t)b * p.out_rows + (size_t)l;
-      const int fm_side = p.fm_d ? (b < p.fm_bh ? 1 : -1) : 0;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
-        uint8_t *st = smem + p.epi_off + es * stage_stride;
-        uint8_t *outb = st + n_in * ECH_BYTES;
-        const int ccol = c * 64 + half * 32;
-        const bool active = ccol < BLOCK_N;      // BLOCK_N = 96: the last chunk has one 32-column half
-        uint32_t pk[16];
-        if (n_in) mbar_wait(&efull_bar[es], eph);
-        if (active)
-          tc_epi_chunk_tma(p, taddr + ccol, n0 + ccol, valid, orow, fm_side, st, st + (p.in0_kind ? ECH_BYTES : 0), rowoff,
-                           rx, half, pk);
-        if (c == NCHUNK - 1) {                   // accumulator stage read out: hand it back to the MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
-        }
-        if (n_in) {                              // operand chunk consumed (registers hold what is needed)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&eempty_bar[es]);
-        }
-        // the bulk store that last read this output buffer must be done reading it
-        if (issuer && !(p.dbg & 16)) {
-          if (p.e_stages == 2) bulk_wait_read<1>();
-          else bulk_wait_read<0>();
-        }
-        if (!(p.dbg & 32)) named_bar_sync(1, 256);
-        if (active && !(p.dbg & 1)) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) sts128(outb + rowoff + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), pk + 4 * q);
-        }
-        fence_proxy_async();
-        if (!(p.dbg & 32)) named_bar_sync(1, 256);
-        if (issuer && !(p.dbg & 1)) {
-          tma_store_3d(&tmap_eo, outb, n0 + c * 64, l0, b0);
-          bulk_commit();
-        }
-        if (++es == p.e_stages) { es = 0; eph ^= 1; }
+    // =========================== epilogue, TMA-staged (8 warps) ===========================
+    if constexpr (!X3) {
+      EtmaCtx x;
+      x.smem = smem; x.tfull_bar = tfull_bar; x.tempty_bar = tempty_bar; x.efull_bar = efull_bar;
+      x.eempty_bar = eempty_bar; x.tmem_base = tmem_base; x.rank = rank; x.warp = warp; x.lane = lane; x.pair = pair;
+      x.num_pairs = num_pairs; x.num_tiles = num_tiles; x.n_mt = n_mt; x.tmap_eo = &tmap_eo;
+      switch (p.emode) {       // see tc_epi_chunk_tma: bias | leaky << 1 | in0_kind << 2 | in1_kind << 4
+        case 2: etma_epilogue<BLOCK_N, 2>(p, x); break;                  // forward, LeakyReLU operand out
+        case 3: etma_epilogue<BLOCK_N, 3>(p, x); break;                  // ... with bias (discriminator layers)
+        case 10: etma_epilogue<BLOCK_N, 10>(p, x); break;                // 1x1 conv of a unit: + skip from the operand
+        case 4: etma_epilogue<BLOCK_N, 4>(p, x); break;                  // dgrad: LeakyReLU' mask
+        case 20: etma_epilogue<BLOCK_N, 20>(p, x); break;                // dgrad + feature-matching gradient
+        case 36: etma_epilogue<BLOCK_N, 36>(p, x); break;                // dgrad + gradient skip
+        default: etma_epilogue<BLOCK_N, -1>(p, x); break;
       }
     }
-    if (issuer) bulk_wait_all();
   } else if (warp >= 2) {
     // =========================== epilogue (4 warps in each CTA) ===========================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -813,8 +874,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int row = quad * 32 + lane;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % ACC2;
+      const uint32_t acc_phase = (it / ACC2) & 1;
       const int nt = tile % p.n_nt;
       const int mt = (tile / p.n_nt) * 2 + (int)rank;
       const int lt = mt % p.n_lt;
@@ -919,7 +980,7 @@ static int pick_block_n(int Cout, long m_tiles) {
 //   fill = (16 KB activations + BN*64 B weights per CTA) / ~60 B/clk);  cost = waves * stage clocks.
 // The decoder / encoder blocks with few rows and many channels (768 x 768 at 2048 rows) were given BN = 64 to reach
 // 148 tiles: two waves of fill-bound tiles; BN = 128 does the same work in one wave of better-balanced tiles.
-static int pick_block_n2(int Cout, long m_tiles) {
+static int pick_block_n2(int Cout, long m_tiles, int kblocks = 0) {
   const int cands[] = {256, 192, 128, 96, 64};
   const long n_mp = (m_tiles + 1) / 2;
   int best = 0;
@@ -929,7 +990,15 @@ static int pick_block_n2(int Cout, long m_tiles) {
     const long tiles = n_mp * (Cout / c);
     const long waves = (tiles + 73) / 74;
     const double mma = 2.0 * c, fill = (16384.0 + 64.0 * c) / 60.0;
-    const double cost = (double)waves * (mma > fill ? mma : fill);
+    double tile = (kblocks > 0 ? kblocks : 1) * (mma > fill ? mma : fill);
+    if (kblocks > 0) {
+      // accumulator hand-over chain (commit -> epilogue wake-up -> TMEM reads -> release -> MMA wake-up, ~5000 clk
+      // measured on the K = 1 layers): one tile per chain latency / accumulator stages
+      const int acc = (512 / c) > 4 ? 4 : (512 / c);
+      const double chain = 5000.0 / acc;
+      if (chain > tile) tile = chain;
+    }
+    const double cost = (double)waves * tile;
     if (!best || cost < best_cost) { best = c; best_cost = cost; }
   }
   return best;
@@ -1094,7 +1163,7 @@ extern "C" int rave_conv1d_tc_supported(int Cin, int Cout, int K, int stride, in
 }
 
 // Which kernel instance rave_conv1d_tc_fwd runs for a shape: BLOCK_N | BLOCK_K << 12 | (CTA pair ? 1 << 24 : 0); 0 = none.
-extern "C" int rave_conv1d_tc_plan(int B, int Cin, int Cout, int Lout) {
+extern "C" int rave_conv1d_tc_plan(int B, int Cin, int Cout, int Lout, int K) {
   using namespace rave;
   using namespace rave::tc;
   const int BK = pick_block_k(Cin);
@@ -1105,7 +1174,7 @@ extern "C" int rave_conv1d_tc_plan(int B, int Cin, int Cout, int Lout) {
   const char *e = getenv("RAVE_TC_2CTA");
   const bool want2 = !(e && e[0] == '0');
   int BN = 0;
-  if (want2 && m_tiles >= 2) BN = pick_block_n2(Cout, m_tiles);
+  if (want2 && m_tiles >= 2) BN = pick_block_n2(Cout, m_tiles, K > 0 ? K * ceil_div(Cin, 64) : 0);
   if (!BN) BN = pick_block_n(Cout, m_tiles);
   if (!BN) return 0;
   const bool use2 = want2 && (BN % 32 == 0) && BN >= 64 && m_tiles >= 2;
@@ -1192,7 +1261,7 @@ static int conv1d_tc_fwd_impl(const void *xa, const void *wt, const float *bias,
     want2 = (e && e[0] == '0') ? 0 : 1;
   }
   int BN = 0;
-  if (want2 && (long)p.n_lt * p.n_bg >= 2) BN = pick_block_n2(Cout, (long)p.n_lt * p.n_bg);
+  if (want2 && (long)p.n_lt * p.n_bg >= 2) BN = pick_block_n2(Cout, (long)p.n_lt * p.n_bg, K * ceil_div(Cin, 64));
   if (!BN) BN = pick_block_n(Cout, (long)p.n_lt * p.n_bg);
   RAVE_CHECK_ARG(BN > 0, "conv1d_tc: no BLOCK_N for Cout=%d", Cout);
   p.n_nt = Cout / BN;
@@ -1255,6 +1324,9 @@ static int conv1d_tc_fwd_impl(const void *xa, const void *wt, const float *bias,
       if (!p.etma) p.in0_kind = p.in1_kind = 0;
     }
   }
+  p.emode = -1;
+  if (p.etma && !res && !out_f32 && !p.dbg)
+    p.emode = (bias ? 1 : 0) | (act == RAVE_ACT_LEAKY ? 2 : 0) | (p.in0_kind << 2) | (p.in1_kind << 4);
   cudaStream_t s = (cudaStream_t)stream;
   if (x3) return conv_tc_dispatch_x3(use2, BK, BN, ta, tb, te, p, s);
   return dispatch_all<false>(use2, BK, BN, ta, tb, te, p, s);

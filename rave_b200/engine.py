@@ -264,6 +264,8 @@ class _PreparedWeights:
         self.dgrad_fused = None   # strided conv: all input phases as one conv, wt [J][stride*Cin][Cout]
         self.fused_J = self.fused_pad = 0
         self.need_dgrad = need_dgrad
+        self.need_fwd = need_fwd
+        self.raw = None           # (norm, outA, outB) as produced by the prep kernel (refresh_static_prep rewrites them)
         if spec.kind == "conv":
             self.tapsA = list(range(K)) if need_fwd else []
             if not need_dgrad:
@@ -295,6 +297,48 @@ class _PreparedWeights:
         return self
 
 
+# ---- static prepared weights --------------------------------------------------------------------------------------
+# A captured CUDA graph cannot use the version-keyed cache above (replays change parameters behind autograd's back), so
+# every replay used to re-prepare every chain.  The discriminator's weights only change in D-steps (1 in 4): with
+# `enable_static_prep(model.discriminator)` its prepared layouts live in persistent buffers that the chains read as they
+# are, and that `refresh_static_prep` rewrites IN PLACE right after the discriminator's optimiser step (inside the
+# D-step graph).  Whoever changes those parameters some other way (load_state_dict, an eager optimiser) must refresh.
+
+def enable_static_prep(root: nn.Module) -> None:
+    for m in root.modules():
+        if hasattr(m, "weight_v") or (hasattr(m, "weight") and isinstance(getattr(m, "weight"), nn.Parameter)):
+            m.__dict__.setdefault("_tc_static", {})
+
+
+def disable_static_prep(root: nn.Module) -> None:
+    for m in root.modules():
+        m.__dict__.pop("_tc_static", None)
+
+
+@torch.no_grad()
+def refresh_static_prep(root: nn.Module) -> int:
+    """Recompute every static prepared layout under `root` into its existing buffers; returns how many."""
+    items, into, extra = [], [], []
+    for m in root.modules():
+        st = m.__dict__.get("_tc_static")
+        if not st:
+            continue
+        for key, pw in st.items():
+            if key[0] == "c1":
+                extra.append(pw)
+                continue
+            if pw.raw is None:        # norm-only entry of a Cin = 1 first layer: refreshed through its ("c1", "norm") record
+                continue
+            v, g, _ = _layer_params(pw.spec)
+            items.append((v.detach(), g.detach() if g is not None else None, pw.tapsA, pw.tapsB, pw.C0p, pw.C1p))
+            into.append(pw.raw)
+    if items:
+        ops.weight_prep_tc_multi(items, into=into)
+    for rec in extra:
+        rec["refresh"]()
+    return len(items) + len(extra)
+
+
 def prepare_layers(jobs, x3: bool = False):
     """jobs: list of (spec, v, g, need_dgrad, need_fwd).  Returns the list of _PreparedWeights, re-using the
     per-module cache (keyed on parameter versions; bypassed while a CUDA graph is being captured) and
@@ -303,10 +347,16 @@ def prepare_layers(jobs, x3: bool = False):
     todo = []
     for i, (spec, v, g, need_dgrad, need_fwd) in enumerate(jobs):
         capturing = v.is_cuda and torch.cuda.is_current_stream_capturing()
+        static = spec.module.__dict__.get("_tc_static") if (not x3 and ACT_DTYPE == torch.bfloat16) else None
+        if static is not None:
+            hit = static.get((need_dgrad, need_fwd))
+            if hit is not None:
+                out[i] = hit
+                continue
         key = (v._version, g._version if g is not None else -1, need_dgrad, need_fwd, str(ACT_DTYPE), str(v.device),
                v.data_ptr(), _state["prep_epoch"], x3)
         slot = "_tc_prep_x3" if x3 else "_tc_prep"
-        if not capturing:
+        if not capturing and static is None:
             hit = spec.module.__dict__.get(slot)
             if hit is not None and hit[0] == key:
                 out[i] = hit[1]
@@ -318,12 +368,26 @@ def prepare_layers(jobs, x3: bool = False):
                                        x3=x3)
         for (i, key, cap, pw, v, g), (norm, outA, outB) in zip(work, res):
             out[i] = pw.finalize(norm, outA, outB, 2 if x3 else 1)
-            if not cap:
+            pw.raw = (norm, outA, outB)
+            static = pw.spec.module.__dict__.get("_tc_static") if (not x3 and ACT_DTYPE == torch.bfloat16) else None
+            if static is not None:
+                if not cap:          # buffers of a capture belong to the graph's pool: only eager calls create a slot
+                    static[(pw.need_dgrad, pw.need_fwd)] = out[i]
+            elif not cap:
                 pw.spec.module.__dict__["_tc_prep_x3" if x3 else "_tc_prep"] = (key, out[i])
     for (i, key, cap, pw, v, g) in todo:
         if out[i] is None:            # nothing to re-layout (a c1 layer without dgrad): only the norm
             pw.norm = ops.weight_norm_raw(v, g)[1] if g is not None else None
             out[i] = pw
+            static = pw.spec.module.__dict__.get("_tc_static") if (not x3 and ACT_DTYPE == torch.bfloat16) else None
+            if static is not None and not cap and pw.norm is not None:
+                norm_t, spec_ = pw.norm, pw.spec
+
+                def _refresh(norm_t=norm_t, spec_=spec_):
+                    v_, g_, _ = _layer_params(spec_)
+                    norm_t.copy_(ops.weight_norm_raw(v_.detach(), g_.detach())[1])
+                static[(pw.need_dgrad, pw.need_fwd)] = pw
+                static[("c1", "norm")] = {"refresh": _refresh}
     return out
 
 
@@ -461,21 +525,45 @@ class TcChainFn(torch.autograd.Function):
                 # positions are then read as ONE 64-channel row (X viewed as [R][L/4][64], 128-byte TMA rows
                 # instead of 32-byte ones) against the block-diagonal weight kron(I4, w): the output row holds
                 # the 4 x Cout results of those positions, i.e. the same bytes as out[r][4*l4 + p][co].
-                w_eff = ops.weight_norm_raw(v.detach(), g.detach())[0] if g is not None else v.detach()
-                w_ck = nn.functional.pad(w_eff.reshape(s.Cout, s.K), (0, 16 - s.K, 0, s.cout_pad))   # [Cout_p, 16]
                 G = C1_GROUP if (pitch % C1_GROUP == 0) else 1
                 Xp = (Lout + G - 1) // G * G
                 X = ops.im2col_c1(a, Lin, Lout, Xp, s.K, s.stride, s.pad[0], period, pool)
                 ctx.c1_X = X
                 ctx.c1_group = G
-                if G > 1:
-                    eye = torch.eye(G, dtype=w_ck.dtype, device=dev)
-                    w_blk = (eye[:, None, :, None] * w_ck[None, :, None, :]).reshape(G * cout_p, G * 16)
+
+                def c1_weights(s=s, G=G, cout_p=cout_p):
+                    v_, g_, b_ = _layer_params(s)
+                    w_eff = ops.weight_norm_raw(v_.detach(), g_.detach())[0] if g_ is not None else v_.detach()
+                    w_ck = nn.functional.pad(w_eff.reshape(s.Cout, s.K), (0, 16 - s.K, 0, s.cout_pad))   # [Cout_p, 16]
+                    if G > 1:
+                        eye = torch.eye(G, dtype=w_ck.dtype, device=w_ck.device)
+                        w_blk = (eye[:, None, :, None] * w_ck[None, :, None, :]).reshape(G * cout_p, G * 16)
+                    else:
+                        w_blk = w_ck
+                    bp = b_
+                    if b_ is not None and s.cout_pad:
+                        bp = nn.functional.pad(b_.detach(), (0, s.cout_pad))
+                    bias_g_ = bp.detach().repeat(G) if (bp is not None and G > 1) else (bp.detach() if bp is not None
+                                                                                         else None)
+                    return (w_blk.to(ACT_DTYPE).unsqueeze(0).contiguous(),                     # [1][G*Cout_p][G*16]
+                            w_blk.t().contiguous().to(ACT_DTYPE).unsqueeze(0), bias_g_)        # [1][G*16][G*Cout_p]
+
+                static = s.module.__dict__.get("_tc_static") if ACT_DTYPE == torch.bfloat16 else None
+                rec = static.get(("c1", G, cout_p)) if static is not None else None
+                if rec is None:
+                    w_fwd, w_dg, bias_g = c1_weights()
+                    if static is not None and not torch.cuda.is_current_stream_capturing():
+                        def _refresh(w_fwd=w_fwd, w_dg=w_dg, bias_g=bias_g, fn=c1_weights):
+                            a_, b_, c_ = fn()
+                            w_fwd.copy_(a_)
+                            w_dg.copy_(b_)
+                            if bias_g is not None:
+                                bias_g.copy_(c_)
+                        static[("c1", G, cout_p)] = {"t": (w_fwd, w_dg, bias_g), "refresh": _refresh}
                 else:
-                    w_blk = w_ck
-                ctx.c1_wt_dgrad = w_blk.t().contiguous().to(ACT_DTYPE).unsqueeze(0)       # [1][G*16][G*Cout_p]
-                bias_g = bias_p.detach().repeat(G) if (bias_p is not None and G > 1) else bias_p
-                ops.conv1d_tc(X.view(B, Xp // G, G * 16), w_blk.to(ACT_DTYPE).unsqueeze(0).contiguous(), bias_g,
+                    w_fwd, w_dg, bias_g = rec["t"]
+                ctx.c1_wt_dgrad = w_dg
+                ops.conv1d_tc(X.view(B, Xp // G, G * 16), w_fwd, bias_g,
                               None, 1, 1, (0, 0), act_code, act_slope, want_f32=False, want_act=False,
                               out_f32=out_f32.view(B, pitch // G, G * cout_p) if out_f32 is not None else None,
                               out_act=out_act.view(B, pitch // G, G * cout_p) if out_act is not None else None,

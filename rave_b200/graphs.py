@@ -35,6 +35,16 @@ class GraphedTrainer:
         self._weights_at_capture = dict(model.weights)
         model._beta_dev = torch.tensor(float(model.beta_factor), dtype=torch.float32, device=example_batch.device)
         gen_opt, dis_opt = model.optimizers()
+        # the discriminator only changes in D-steps: its prepared weights become persistent buffers, rewritten in place
+        # after the discriminator's optimiser step (inside the D-step graph) instead of being rebuilt by every replay
+        self.static_prep = engine.precision() == "bf16"
+        if self.static_prep:
+            engine.enable_static_prep(model.discriminator)
+            model._static_disc_prep = True
+            if not getattr(model, "_static_prep_hook", None):
+                model._static_prep_hook = model.register_load_state_dict_post_hook(
+                    lambda m, keys: engine.refresh_static_prep(m.discriminator)
+                    if getattr(m, "_static_disc_prep", False) else None)
         snap_tensors = [(t, t.detach().clone()) for t in list(model.parameters()) + list(model.buffers())]
         snap_opt = [(o, copy.deepcopy(o.state_dict())) for o in (gen_opt, dis_opt)]
         self.graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
@@ -81,6 +91,8 @@ class GraphedTrainer:
                             o = old.get(p)
                             v.copy_(o[k]) if (o is not None and k in o) else v.zero_()
         engine.invalidate_prepared()
+        if self.static_prep:
+            engine.refresh_static_prep(model.discriminator)      # the restore above moved the parameters
 
     def step(self, batch: torch.Tensor, batch_idx: int):
         """Same contract as RAVE.training_step: returns the logged scalars (device tensors)."""

@@ -451,6 +451,11 @@ class RAVE(nn.Module):
             if grad_hook is not None:
                 grad_hook(dis_params)
             dis_opt.step()
+            if getattr(self, "_static_disc_prep", False):
+                # GraphedTrainer keeps the discriminator's prepared (weight-normalised, tap-major bf16) weights in
+                # persistent buffers: rewrite them now that the parameters moved (engine.enable_static_prep)
+                from . import engine
+                engine.refresh_static_prep(self.discriminator)
         else:
             gen_opt.zero_grad(set_to_none=True)
             loss_gen_value = 0.

@@ -789,22 +789,26 @@ def noise_fir(h, M, noise, C):
 # multi-tensor weight preparation / weight-norm backward (one launch pair per chain)
 # ----------------------------------------------------------------------------------------------
 
-def weight_prep_tc_multi(items, x3=False):
+def weight_prep_tc_multi(items, x3=False, into=None):
     """items: list of (v, g, tapsA, tapsB, C0p, C1p).  Returns a list of (norm, outA, outB) exactly like
     weight_prep_tc, using ONE row-norm launch and ONE re-layout launch for (up to 64 of) the layers.
-    x3: split-operand layouts, outA [2 * nA][C0p][C1p] / outB [2 * nB][C1p][C0p] = all hi slabs, then all lo slabs."""
+    x3: split-operand layouts, outA [2 * nA][C0p][C1p] / outB [2 * nB][C1p][C0p] = all hi slabs, then all lo slabs.
+    into: list of (norm, outA, outB) tensors of an earlier call to overwrite in place (same shapes)."""
     P = 2 if x3 else 1
     outs = []
     recs = []
-    for (v, g, tapsA, tapsB, C0p, C1p) in items:
+    for idx, (v, g, tapsA, tapsB, C0p, C1p) in enumerate(items):
         v = _f32c(v)
         g = _f32c(g)
         C0, C1 = v.shape[0], v.shape[1]
         K = v.numel() // (C0 * C1)
         dev = v.device
-        norm = torch.empty(C0, dtype=torch.float32, device=dev) if g is not None else None
-        outA = torch.empty(P * len(tapsA), C0p, C1p, dtype=torch.bfloat16, device=dev) if tapsA else None
-        outB = torch.empty(P * len(tapsB), C1p, C0p, dtype=torch.bfloat16, device=dev) if tapsB else None
+        if into is not None:
+            norm, outA, outB = into[idx]
+        else:
+            norm = torch.empty(C0, dtype=torch.float32, device=dev) if g is not None else None
+            outA = torch.empty(P * len(tapsA), C0p, C1p, dtype=torch.bfloat16, device=dev) if tapsA else None
+            outB = torch.empty(P * len(tapsB), C1p, C0p, dtype=torch.bfloat16, device=dev) if tapsB else None
         outs.append((norm, outA, outB))
         recs.append((v, g, norm, outA, outB, tapsA, tapsB, C0, C1, K, C0p, C1p))
     for i0 in range(0, len(recs), 64):
