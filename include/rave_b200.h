@@ -198,6 +198,15 @@ int rave_conv1d_tc_fwd_x3(const void *xa_bf16, const void *wt_bf16, const float 
  * dbias [Cm] fp32, pre-zeroed, or NULL: += sum_{b,l} P[b][l][m] (the conv bias gradient when P = dy), reduced by the
  * tap-0 CTAs from the tiles they stream anyway (fp32 atomics across row slices). */
 int rave_conv1d_tc_wgrad_splits(int B, int Cm, int Lp, int Cn, int K);
+/* Multi-tap form (csrc/wgrad_mt.cu): one CTA accumulates up to 8 taps from ONE pass over the P rows and haloed Q tiles
+ * shared by the taps of a phase.  rave_conv1d_tc_wgrad_mt_plan returns the split count to allocate dwt with, or 0 when
+ * the layer must run on rave_conv1d_tc_wgrad (tap pattern / very short rows); same dwt / dbias contract. */
+int rave_conv1d_tc_wgrad_mt_supported(int B, int Cm, int Lp, int Cn, int K);
+int rave_conv1d_tc_wgrad_mt_splits(int B, int Cm, int Lp, int Cn, int K);
+int rave_conv1d_tc_wgrad_mt_plan(int B, int Cm, int Lp, int Cn, int K, int stride, int dil, int pad_l);
+int rave_conv1d_tc_wgrad_mt(const void *P_bf16, const void *Q_bf16, float *dwt, float *dbias, int B, int Cm, int Lp,
+                            int p_pitch, int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l,
+                            void *stream);
 int rave_conv1d_tc_wgrad(const void *P_bf16, const void *Q_bf16, float *dwt, float *dbias, int B, int Cm, int Lp,
                          int p_pitch, int Cn, int Lq, int q_pitch, int K, int stride, int dil, int pad_l,
                          void *stream);

@@ -48,6 +48,10 @@ SIGNATURES = {
     "rave_conv1d_tc_wgrad": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rave_tapmajor_to_weight_f32": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "rave_conv1d_tc_wgrad_splits": (c_int, [_I, _I, _I, _I, _I]),
+    "rave_conv1d_tc_wgrad_mt": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rave_conv1d_tc_wgrad_mt_plan": (c_int, [_I, _I, _I, _I, _I, _I, _I, _I]),
+    "rave_conv1d_tc_wgrad_mt_splits": (c_int, [_I, _I, _I, _I, _I]),
+    "rave_conv1d_tc_wgrad_mt_supported": (c_int, [_I, _I, _I, _I, _I]),
     "rave_weight_prep_tc": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rave_weight_norm_bwd_tapmajor": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rave_conv1d_c1_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),

@@ -473,6 +473,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  griddep_launch_dependents();      // dependents may begin their prologue ...
+  griddep_wait();                   // ... and this kernel touches global memory only after its predecessors are done
 
   if (warp == 0) {
     // =========================== TMA producer (warp-uniform loop, elected lane issues) ===========================
@@ -683,6 +685,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  griddep_launch_dependents();      // dependents may begin their prologue ...
+  griddep_wait();                   // ... and this kernel touches global memory only after its predecessors are done
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs; warp-uniform loop) ===========================
@@ -1022,7 +1026,7 @@ static int launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = tiles < sms ? tiles : sms;
-  conv_tc_kernel<BN, BK, X3><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  launch_pdl(conv_tc_kernel<BN, BK, X3>, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, ta, tb, p);
   RAVE_CHECK_LAUNCH("conv1d_tc");
   return 0;
 }
@@ -1088,8 +1092,8 @@ static int launch2(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorM
     if (e && (atoi(e) == 4 || atoi(e) == 8)) epi = atoi(e);
   }
   if (q.etma) epi = 8;
-  conv_tc2_kernel<BN, BK, X3><<<2 * pairs, 64 + 32 * epi + (q.etma ? 32 : 0), smem_bytes, stream>>>(ta, tb, te[0], te[1],
-                                                                                                 te[2], q);
+  launch_pdl(conv_tc2_kernel<BN, BK, X3>, dim3(2 * pairs), dim3(64 + 32 * epi + (q.etma ? 32 : 0)), smem_bytes, stream, ta, tb,
+             te[0], te[1], te[2], q);
   RAVE_CHECK_LAUNCH("conv1d_tc(2cta)");
   return 0;
 }
@@ -1385,16 +1389,6 @@ struct WgParams {
                             // by the tap-0 / n-tile-0 CTAs from the P tiles they stream anyway
 };
 
-__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 64-channel slabs
-  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;        // stride between 8-row groups
-  d |= 1ull << 46;
-  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
-  return d;
-}
-
 template <int BLOCK_N>
 struct WgSmem {
   static constexpr int NS = (BLOCK_N + 63) / 64;
@@ -1454,6 +1448,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  griddep_launch_dependents();      // dependents may begin their prologue ...
+  griddep_wait();                   // ... and this kernel touches global memory only after its predecessors are done
 
   if (my_chunks > 0) {
     if (warp == 0) {
@@ -1615,7 +1611,7 @@ static int launch_wg(const CUtensorMap &tp, const CUtensorMap &tq, const WgParam
     attr = true;
   }
   const int grid = p.K * p.n_mt * p.n_nt * p.splits;
-  wgrad_tc_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tp, tq, p);
+  launch_pdl(wgrad_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, tp, tq, p);
   RAVE_CHECK_LAUNCH("wgrad_tc");
   return 0;
 }

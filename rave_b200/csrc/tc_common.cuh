@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace rave {
 namespace tc {
@@ -279,6 +280,49 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
       : "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every tcgen05 kernel finishes its prologue (barrier init, TMEM allocation, tensor-map prefetch) and then WAITS for the
+// grids it depends on (griddepcontrol.wait: full completion + memory flush of the previous kernels in the stream); it
+// also lets its own dependents start early (launch_dependents).  Launched with the programmatic-stream-serialization
+// attribute (launch_pdl), the next kernel's CTAs take SMs as soon as this one's CTAs leave them, so its launch latency
+// and prologue overlap this kernel's tail -- a chain of ~50 short kernels (the encoder / generator forward) otherwise
+// pays ~3-4 us of ramp per launch.  Nothing before the wait touches global memory another kernel writes.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifndef __CUDA_ARCH__
+#include <stdlib.h>
+#include <utility>
+static inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("RAVE_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+#endif
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args &&...args) {
+#ifndef __CUDA_ARCH__
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+#else
+  return cudaSuccess;
+#endif
+}
+
 // ------------------------------------------------------------------ descriptors
 // layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (cute::UMMA::LayoutType)
 __host__ __device__ constexpr uint32_t umma_layout_for_swizzle(int swizzle_bytes) {
@@ -291,6 +335,17 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int swi
   d |= (uint64_t)(((8u * (uint32_t)swizzle_bytes) >> 4) & 0x3FFF) << 32;  // stride byte offset
   d |= 1ull << 46;                                                         // descriptor version (sm_100)
   d |= (uint64_t)umma_layout_for_swizzle(swizzle_bytes) << 61;
+  return d;
+}
+// MN-major operand (the reduction runs over tile ROWS, channels are contiguous): 64-channel slabs of 128-byte rows,
+// SWIZZLE_128B; LBO = stride between 64-channel slabs, SBO = 8 rows
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 64-channel slabs
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;        // stride between 8-row groups
+  d |= 1ull << 46;
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
   return d;
 }
 // instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile

@@ -116,6 +116,8 @@ dilated_unit_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  griddep_launch_dependents();      // dependents may begin their prologue ...
+  griddep_wait();                   // ... and this kernel touches global memory only after its predecessors are done
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -337,6 +339,276 @@ dilated_unit_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
+// =============================================================================================
+// Weight-stationary variant for the narrow units (C = 96: the six longest launches of the encoder / generator forward).
+// dilated_unit_tc_kernel re-streams, for EVERY 128-row tile, the three tap-shifted copies of the activation rows
+// (3 x 24 KB) and the whole weight set (W3 54 KB + W1 18 KB) from L2: 144 KB per tile, 35 B/clk/SM sustained -- the
+// L2 -> SM path (~42 B/clk/SM), not the tensor pipe (18 % active) or HBM, bounded it (profiles/r2_ncu_unit96.md).
+// Here the weights are loaded ONCE per CTA and stay in shared memory (72 KB), and each tile brings ONE haloed
+// activation tile (128 + 2 dil rows): tap k is the same tile read (k dil) rows further down -- K-major operand, 64-byte
+// swizzle, descriptor start address moved by whole rows (the swizzle is a function of the absolute shared-memory
+// address, which is how TMA wrote it).  29 KB instead of 144 KB per tile.
+// =============================================================================================
+constexpr int UW_AROWS = 152;                       // 128 + 2 * dil rows, dil <= 12
+constexpr int UW_ASLAB = UW_AROWS * 64;             // one 32-channel K block of the haloed tile (64-byte rows)
+constexpr int UW_WSLAB = 96 * 64;                   // one (tap, K block) weight slab: 96 rows x 32 channels
+constexpr int UW_STAGES = 3;
+constexpr int UW_W3_OFF = 0, UW_W1_OFF = 9 * UW_WSLAB, UW_A_OFF = 12 * UW_WSLAB;
+constexpr int UW_A2_OFF = UW_A_OFF + UW_STAGES * 3 * UW_ASLAB;
+constexpr int UW_BAR_OFF = UW_A2_OFF + 3 * (128 * 64);
+constexpr int UW_TOTAL = UW_BAR_OFF + 256 + 1024;
+
+__global__ void __launch_bounds__(U_THREADS, 1)
+dilated_unit_ws96_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w3,
+                         const __grid_constant__ CUtensorMap tmap_w1, const UnitParams p) {
+  constexpr int C = 96, BK = 32, KB = 3, SWZ = 64, A2_SLAB = 128 * 64;
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *a2 = smem + UW_A2_OFF;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + UW_BAR_OFF);
+  uint64_t *empty_bar = full_bar + UW_STAGES;
+  uint64_t *tfull_bar = empty_bar + UW_STAGES;          // [2]
+  uint64_t *tempty_bar = tfull_bar + 2;                 // [2]
+  uint64_t *a2_ready = tempty_bar + 2;
+  uint64_t *a2_free = a2_ready + 1;
+  uint64_t *w_bar = a2_free + 1;                        // the resident weights have landed
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.n_lt * p.n_bg;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w3);
+    tma_prefetch_desc(&tmap_w1);
+    for (int s = 0; s < UW_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], U_EPI_WARPS);
+    }
+    mbar_init(a2_ready, U_EPI_WARPS);
+    mbar_init(a2_free, 1);
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  griddep_launch_dependents();
+  griddep_wait();
+  const int arows = 128 + 2 * p.dil;                    // rows of the haloed tile actually loaded
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {                                   // weights: once
+      mbar_arrive_expect_tx(w_bar, 12 * UW_WSLAB);
+      for (int k = 0; k < 3; ++k)
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(smem + UW_W3_OFF + (k * KB + kb) * UW_WSLAB, &tmap_w3, w_bar, kb * BK, k * C);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem + UW_W1_OFF + kb * UW_WSLAB, &tmap_w1, w_bar, kb * BK, 0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int lt = tile % p.n_lt, b0 = tile / p.n_lt;          // BB == 1
+      const int row0 = lt * 128 - p.pad_l;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t *sa = smem + UW_A_OFF + stage * 3 * UW_ASLAB;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(KB * arows * 64));
+        for (int kb = 0; kb < KB; ++kb) tma_load_4d(sa + kb * UW_ASLAB, &tmap_a, &full_bar[stage], kb * BK, 0, row0, b0);
+      }
+      __syncwarp();
+      if (++stage == UW_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = make_idesc_bf16(128, C);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t a2_base = smem_u32(a2);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    mbar_wait(w_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int job = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      {                                                   // ---- phase 1: conv3 over the haloed tile
+        const int buf = job & 1;
+        mbar_wait(&tempty_bar[buf], ((job >> 1) & 1) ^ 1);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_u + buf * 256;
+        const uint32_t sa = smem_base + UW_A_OFF + stage * 3 * UW_ASLAB;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint64_t adesc = make_kmajor_desc(sa + kb * UW_ASLAB + (uint32_t)(k * p.dil) * 64u, SWZ);
+              const uint64_t bdesc = make_kmajor_desc(smem_base + UW_W3_OFF + (k * KB + kb) * UW_WSLAB, SWZ);
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk)
+                umma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k > 0 || kb > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == UW_STAGES) { stage = 0; phase ^= 1; }
+        ++job;
+      }
+      mbar_wait(a2_ready, it & 1);
+      tc_fence_after();
+      {                                                   // ---- phase 2: 1x1 conv on the resident A2 / W1
+        const int buf = job & 1;
+        mbar_wait(&tempty_bar[buf], ((job >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_u + buf * 256;
+        if (elect_one()) {
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t adesc = make_kmajor_desc(a2_base + kb * A2_SLAB, SWZ);
+            const uint64_t bdesc = make_kmajor_desc(smem_base + UW_W1_OFF + kb * UW_WSLAB, SWZ);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&tfull_bar[buf]);
+          umma_commit(a2_free);
+        }
+        __syncwarp();
+        ++job;
+      }
+    }
+  } else {
+    // =========================== epilogue (8 warps): as dilated_unit_tc_kernel<96, 32> ===========================
+    const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t row_xor = (uint32_t)((row >> 1) & 3);          // 64-byte swizzle
+    int job = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int lt = tile % p.n_lt, b = tile / p.n_lt;
+      const int l = lt * 128 + row;
+      const bool valid = (b < p.B) && (l < p.L);
+      const size_t grow = ((size_t)b * p.pitch + l) * C;
+      if (it > 0) mbar_wait(a2_free, (it - 1) & 1);
+      {   // ---- epilogue 1: acc -> LeakyReLU -> bf16 -> A2 (swizzled K-major rows) [+ HBM copy for the backward]
+        const int buf = job & 1;
+        mbar_wait(&tfull_bar[buf], (job >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
+        const float2 s2 = make_float2(p.slope_mid, p.slope_mid);
+#pragma unroll 1
+        for (int c0 = part * 32; c0 < C; c0 += 64) {
+          float v[32];
+          tmem_ld_32x32(taddr + c0, v);
+          uint32_t pk[16];
+#pragma unroll
+          for (int w = 0; w < 16; ++w) {
+            const float2 t = make_float2(v[2 * w], v[2 * w + 1]);
+            const float2 u = __fmul2_rn(t, s2);
+            const __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(t.x, t.y), __floats2bfloat162_rn(u.x, u.y));
+            pk[w] = *reinterpret_cast<const uint32_t *>(&h);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int cc = c0 + 8 * q;
+            const uint32_t off = (uint32_t)(cc / BK) * A2_SLAB + (uint32_t)row * SWZ + ((((uint32_t)(cc % BK) >> 3) ^ row_xor) << 4);
+            *reinterpret_cast<uint4 *>(a2 + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+          if (p.a1_out && valid) {
+            stg256(p.a1_out + grow + c0, pk);
+            stg256(p.a1_out + grow + c0 + 16, pk + 8);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&tempty_bar[buf]);
+          mbar_arrive(a2_ready);
+        }
+        ++job;
+      }
+      {   // ---- epilogue 2: acc + skip -> outputs
+        const int buf = job & 1;
+        uint32_t sk[2][16];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = part * 32 + 64 * i;
+          if (c0 < C && valid) {
+            ldg256(p.xa + grow + c0, sk[i]);
+            ldg256(p.xa + grow + c0 + 16, sk[i] + 8);
+          }
+        }
+        mbar_wait(&tfull_bar[buf], (job >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = part * 32 + 64 * i;
+          if (c0 < C) {
+            float v[32];
+            tmem_ld_32x32(taddr + c0, v);
+            if (valid) {
+#pragma unroll
+              for (int w = 0; w < 16; ++w) {
+                const float s0 = bfl(sk[i][w]), s1 = bfh(sk[i][w]);
+                v[2 * w] += fminf(s0, s0 * p.slope_in_inv);
+                v[2 * w + 1] += fminf(s1, s1 * p.slope_in_inv);
+              }
+              if (p.out_f32) {
+                uint32_t o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(v[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) stg256(p.out_f32 + grow + c0 + 8 * j, o + 8 * j);
+              }
+              if (p.out_act) {
+                uint32_t pk[16];
+                const float2 so = make_float2(p.slope_out, p.slope_out);
+#pragma unroll
+                for (int w = 0; w < 16; ++w) {
+                  const float2 t = make_float2(v[2 * w], v[2 * w + 1]);
+                  __nv_bfloat162 h = __floats2bfloat162_rn(t.x, t.y);
+                  if (p.act_out == RAVE_ACT_LEAKY) {
+                    const float2 u = __fmul2_rn(t, so);
+                    h = __hmax2(h, __floats2bfloat162_rn(u.x, u.y));
+                  }
+                  pk[w] = *reinterpret_cast<const uint32_t *>(&h);
+                }
+                stg256(p.out_act + grow + c0, pk);
+                stg256(p.out_act + grow + c0 + 16, pk + 8);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        ++job;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 typedef CUresult (*EncodeTiledFnU)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -372,7 +644,7 @@ static int launch_unit(const CUtensorMap &ta, const CUtensorMap &t3, const CUten
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = tiles < sms ? tiles : sms;
-  dilated_unit_tc_kernel<C, BK><<<grid, U_THREADS, L::TOTAL, stream>>>(ta, t3, t1, p);
+  launch_pdl(dilated_unit_tc_kernel<C, BK>, dim3(grid), dim3(U_THREADS), L::TOTAL, stream, ta, t3, t1, p);
   RAVE_CHECK_LAUNCH("dilated_unit_tc");
   return 0;
 }
@@ -441,6 +713,50 @@ extern "C" int rave_dilated_unit_tc_fwd(const void *xa, const void *w3t, const v
     RAVE_CHECK_ARG(r == CUDA_SUCCESS, "dilated_unit_tc: weight tensor map encode failed (%d)", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const char *e = getenv("RAVE_UNIT_WS");
+    if (C == 96 && p.BB == 1 && dil <= 12 && !(e && e[0] == '0')) {
+      // weight-stationary kernel: its activation map carries the haloed box (128 + 2 dil rows), its weight maps one
+      // (tap, K block) slab per box
+      CUtensorMap tah, t3s, t1s;
+      {
+        cuuint64_t dims[4] = {(cuuint64_t)C, 1, (cuuint64_t)L, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2, (cuuint64_t)C * 2 * pitch};
+        cuuint32_t box[4] = {32, 1, (cuuint32_t)(128 + 2 * dil), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tah, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(xa), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RAVE_CHECK_ARG(r == CUDA_SUCCESS, "dilated_unit_tc(ws): tensor map A encode failed (%d)", (int)r);
+      }
+      for (int which = 0; which < 2; ++which) {
+        cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(which == 0 ? 3 : 1) * C};
+        cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+        cuuint32_t box[2] = {32, 96};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(which == 0 ? &t3s : &t1s, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void *>(which == 0 ? w3t : w1t), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RAVE_CHECK_ARG(r == CUDA_SUCCESS, "dilated_unit_tc(ws): weight tensor map encode failed (%d)", (int)r);
+      }
+      static bool attr = false;
+      if (!attr) {
+        cudaError_t er = cudaFuncSetAttribute(dilated_unit_ws96_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UW_TOTAL);
+        if (er != cudaSuccess) {
+          set_error("dilated_unit_tc(ws): cudaFuncSetAttribute(%d bytes): %s", UW_TOTAL, cudaGetErrorString(er));
+          return 2;
+        }
+        attr = true;
+      }
+      const int tiles = p.n_lt * p.n_bg;
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      launch_pdl(dilated_unit_ws96_kernel, dim3(tiles < sms ? tiles : sms), dim3(U_THREADS), UW_TOTAL, s, tah, t3s, t1s, p);
+      RAVE_CHECK_LAUNCH("dilated_unit_tc(ws)");
+      return 0;
+    }
+  }
   switch (C) {
     case 96: return launch_unit<96, 32>(ta, t3, t1, p, s);
     case 192: return launch_unit<192, 64>(ta, t3, t1, p, s);

@@ -318,7 +318,7 @@ def disable_static_prep(root: nn.Module) -> None:
 @torch.no_grad()
 def refresh_static_prep(root: nn.Module) -> int:
     """Recompute every static prepared layout under `root` into its existing buffers; returns how many."""
-    items, into, extra = [], [], []
+    items, into, extra = {False: [], True: []}, {False: [], True: []}, []
     for m in root.modules():
         st = m.__dict__.get("_tc_static")
         if not st:
@@ -330,13 +330,15 @@ def refresh_static_prep(root: nn.Module) -> int:
             if pw.raw is None:        # norm-only entry of a Cin = 1 first layer: refreshed through its ("c1", "norm") record
                 continue
             v, g, _ = _layer_params(pw.spec)
-            items.append((v.detach(), g.detach() if g is not None else None, pw.tapsA, pw.tapsB, pw.C0p, pw.C1p))
-            into.append(pw.raw)
-    if items:
-        ops.weight_prep_tc_multi(items, into=into)
+            x3 = bool(key[2])
+            items[x3].append((v.detach(), g.detach() if g is not None else None, pw.tapsA, pw.tapsB, pw.C0p, pw.C1p))
+            into[x3].append(pw.raw)
+    for x3 in (False, True):
+        if items[x3]:
+            ops.weight_prep_tc_multi(items[x3], x3=x3, into=into[x3])
     for rec in extra:
         rec["refresh"]()
-    return len(items) + len(extra)
+    return len(items[False]) + len(items[True]) + len(extra)
 
 
 def prepare_layers(jobs, x3: bool = False):
@@ -347,9 +349,9 @@ def prepare_layers(jobs, x3: bool = False):
     todo = []
     for i, (spec, v, g, need_dgrad, need_fwd) in enumerate(jobs):
         capturing = v.is_cuda and torch.cuda.is_current_stream_capturing()
-        static = spec.module.__dict__.get("_tc_static") if (not x3 and ACT_DTYPE == torch.bfloat16) else None
+        static = spec.module.__dict__.get("_tc_static") if ACT_DTYPE == torch.bfloat16 else None
         if static is not None:
-            hit = static.get((need_dgrad, need_fwd))
+            hit = static.get((need_dgrad, need_fwd, x3))
             if hit is not None:
                 out[i] = hit
                 continue
@@ -369,24 +371,24 @@ def prepare_layers(jobs, x3: bool = False):
         for (i, key, cap, pw, v, g), (norm, outA, outB) in zip(work, res):
             out[i] = pw.finalize(norm, outA, outB, 2 if x3 else 1)
             pw.raw = (norm, outA, outB)
-            static = pw.spec.module.__dict__.get("_tc_static") if (not x3 and ACT_DTYPE == torch.bfloat16) else None
+            static = pw.spec.module.__dict__.get("_tc_static") if ACT_DTYPE == torch.bfloat16 else None
             if static is not None:
                 if not cap:          # buffers of a capture belong to the graph's pool: only eager calls create a slot
-                    static[(pw.need_dgrad, pw.need_fwd)] = out[i]
+                    static[(pw.need_dgrad, pw.need_fwd, x3)] = out[i]
             elif not cap:
                 pw.spec.module.__dict__["_tc_prep_x3" if x3 else "_tc_prep"] = (key, out[i])
     for (i, key, cap, pw, v, g) in todo:
         if out[i] is None:            # nothing to re-layout (a c1 layer without dgrad): only the norm
             pw.norm = ops.weight_norm_raw(v, g)[1] if g is not None else None
             out[i] = pw
-            static = pw.spec.module.__dict__.get("_tc_static") if (not x3 and ACT_DTYPE == torch.bfloat16) else None
+            static = pw.spec.module.__dict__.get("_tc_static") if ACT_DTYPE == torch.bfloat16 else None
             if static is not None and not cap and pw.norm is not None:
                 norm_t, spec_ = pw.norm, pw.spec
 
                 def _refresh(norm_t=norm_t, spec_=spec_):
                     v_, g_, _ = _layer_params(spec_)
                     norm_t.copy_(ops.weight_norm_raw(v_.detach(), g_.detach())[1])
-                static[(pw.need_dgrad, pw.need_fwd)] = pw
+                static[(pw.need_dgrad, pw.need_fwd, x3)] = pw
                 static[("c1", "norm")] = {"refresh": _refresh}
     return out
 

@@ -475,9 +475,14 @@ def conv1d_tc_wgrad(P_cl, Q_cl, K, stride=1, dil=1, pad_l=0, Lp=None, Lq=None, d
     Lq = q_pitch if Lq is None else Lq
     if P_cl.dtype != torch.bfloat16 or Q_cl.dtype != torch.bfloat16:
         raise _lib.RaveB200Error("conv1d_tc_wgrad: operands must be bf16")
-    splits = _lib.load().rave_conv1d_tc_wgrad_splits(B, Cm, Lp, Cn, K)
+    lib = _lib.load()
+    splits = lib.rave_conv1d_tc_wgrad_mt_plan(B, Cm, Lp, Cn, K, stride, dil, pad_l)
+    entry = "rave_conv1d_tc_wgrad_mt"          # all taps of a group from one pass over P (csrc/wgrad_mt.cu)
+    if splits <= 0:
+        splits = lib.rave_conv1d_tc_wgrad_splits(B, Cm, Lp, Cn, K)
+        entry = "rave_conv1d_tc_wgrad"         # per-tap kernel: tap patterns / row lengths the haloed tiles do not cover
     dwt = torch.empty(splits, K, Cm, Cn, dtype=torch.float32, device=P_cl.device)   # per-slice partial sums
-    call("rave_conv1d_tc_wgrad", ptr(P_cl), ptr(Q_cl), ptr(dwt), dbias.data_ptr() if dbias is not None else None,
+    call(entry, ptr(P_cl), ptr(Q_cl), ptr(dwt), dbias.data_ptr() if dbias is not None else None,
          B, Cm, Lp, p_pitch, Cn, Lq, q_pitch, K, stride, dil, pad_l, stream_ptr())
     return dwt
 

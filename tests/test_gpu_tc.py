@@ -77,9 +77,13 @@ WG_CASES = [
 ]
 
 
+@pytest.mark.parametrize("multi_tap", [False, True])
 @pytest.mark.parametrize("case", WG_CASES)
-def test_conv1d_tc_wgrad_vs_oracle(case):
+def test_conv1d_tc_wgrad_vs_oracle(case, multi_tap, monkeypatch):
+    """multi_tap: the opt-in kernel of csrc/wgrad_mt.cu (all taps of a group from one pass over P, haloed Q tiles); layers it
+    does not take (rows shorter than 16, tap patterns that do not fit) fall back to the per-tap kernel inside ops."""
     from rave_b200 import ops
+    monkeypatch.setenv("RAVE_WG_MT", "1" if multi_tap else "0")
     B, Cm, Cn, L, K, stride, dil, pad_l, pad_r = case
     g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
     x = torch.randn(B, Cn, L, generator=g).bfloat16().float()
