@@ -620,7 +620,7 @@ def run_ours(args):
             cpu = cpu_reference_run(args, 2, 1, args.cpu_seconds)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {
-            "metric": "audio-seconds/s (v2 train step fwd+bwd, 48 kHz)",
+            "metric": f"audio-seconds/s ({args.config} train step fwd+bwd, 48 kHz)",
             "value": value, "unit": "audio-seconds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
