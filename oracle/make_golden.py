@@ -337,6 +337,58 @@ def golden_training_step(R, B=2, T=32768):
                     state_dict=sd0, steps=steps), os.path.join(GOLDEN, "training_step_v2_tiny.pt"))
 
 
+def golden_v1(R, capacity=8, latent_size=16, B=2, T=4096, ratios=(4, 4, 2)):
+    """a12: the reference's v1 Encoder / Generator (rave/blocks.py:322-503) bound like configs/v1.gin (BatchNorm encoder,
+    ResidualStack kernel_sizes [3] / dilations [[1,1],[3,1],[5,1]], NoiseGenerator ratios [4,4,4] / 5 bands), forward in
+    training mode and gradients; the generator is run warmed-up with the uniform noise draw reproduced by re-seeding."""
+    print("v1 encoder / generator")
+    set_padding_mode("centered")
+    blocks = R.blocks
+    orig_rs, orig_ng = blocks.ResidualStack, blocks.NoiseGenerator
+    blocks.ResidualStack = partial(orig_rs, kernel_sizes=[3], dilations_list=[list(d) for d in O.V1_DILATIONS])
+    blocks.NoiseGenerator = partial(orig_ng, ratios=[4, 4, 4], noise_bands=5)
+    try:
+        torch.manual_seed(0)
+        enc = blocks.Encoder(data_size=16, capacity=capacity, latent_size=latent_size, ratios=list(ratios), n_out=2,
+                             sample_norm=False, repeat_layers=1)
+        dec = blocks.Generator(latent_size=latent_size, capacity=capacity, data_size=16, ratios=list(ratios)[::-1],
+                               loud_stride=1, use_noise=True)
+    finally:
+        blocks.ResidualStack, blocks.NoiseGenerator = orig_rs, orig_ng
+    enc.train()
+    dec.train()
+    dec.set_warmed_up(True)
+    sd = {"encoder." + k: v.detach().clone() for k, v in enc.state_dict().items()}
+    sd.update({"decoder." + k: v.detach().clone() for k, v in dec.state_dict().items()})
+    x = make_input(B, 16, T // 16, seed=77)
+    xg = x.clone().requires_grad_(True)
+    z = enc(xg)
+    check("v1 encoder", O.encoder_v1(x, sd, "encoder.", ratios), z, 2e-6)
+    zin = z[:, :latent_size].detach().clone().requires_grad_(True)
+    torch.manual_seed(123)
+    y = dec(zin)
+    # the reference drew torch.rand_like(ir) inside NoiseGenerator.forward: reproduce the draw for the restatement
+    Lz = zin.shape[-1]
+    Lh = Lz
+    for r in ratios:
+        Lh *= r
+    torch.manual_seed(123)
+    noise = torch.rand(B, Lh // 64, 16, 64) * 2 - 1
+    y_o = O.generator_v1(zin.detach(), sd, "decoder.", tuple(ratios)[::-1], warmed_up=True, noise=noise)
+    check("v1 generator", y_o, y, 2e-6)
+    probe_z, probe_y = torch.randn_like(z), torch.randn_like(y)
+    enc_names = [k for k, p in enc.named_parameters()]
+    dec_names = [k for k, p in dec.named_parameters()]
+    ge = torch.autograd.grad((z * probe_z).sum(), [xg] + [p for _, p in enc.named_parameters()])
+    gd = torch.autograd.grad((y * probe_y).sum(), [zin] + [p for _, p in dec.named_parameters()])
+    fx = dict(capacity=capacity, latent_size=latent_size, ratios=tuple(ratios), state_dict=sd, x=x, z=z.detach(),
+              zin=zin.detach(), y=y.detach(), noise=noise, probe_z=probe_z, probe_y=probe_y,
+              grad_x=ge[0].detach(), grad_zin=gd[0].detach(),
+              grads={**{"encoder." + k: g.detach() for k, g in zip(enc_names, ge[1:])},
+                     **{"decoder." + k: g.detach() for k, g in zip(dec_names, gd[1:])}})
+    torch.save(fx, os.path.join(GOLDEN, "autoencoder_v1_tiny.pt"))
+
+
 def golden_losses(R):
     print("spectral distance (core.AudioDistanceV1)")
     core = R.core
@@ -388,6 +440,7 @@ def main():
     golden_autoencoder(R, "v3_tiny", O.ArchConfig(activation="snake", adain=True, **tiny), B=1, T=8192)
     golden_autoencoder(R, "v2_small_tiny", O.ArchConfig(capacity=8, latent_size=16, ratios=(4, 2, 2, 2)), B=1, T=4096)
     golden_discriminator_v2(R)
+    golden_v1(R)
     golden_losses(R)
     golden_training_step(R)
     golden_state_dict_keys(R)

@@ -737,3 +737,95 @@ def noise_generator_v2(x: Tensor, sd, prefix: str, ratios=(2, 2, 2), data_size: 
         noise = torch.rand_like(ir) * 2 - 1
     out = fft_convolve(noise, ir).permute(0, 2, 1, 3)
     return out.reshape(out.shape[0], out.shape[1], -1)
+
+
+# ----------------------------------------------------------------------------------
+# v1 architecture (rave/blocks.py:48-240, 322-503; configs/v1.gin) -------------------
+# ----------------------------------------------------------------------------------
+
+V1_DILATIONS = ((1, 1), (3, 1), (5, 1))        # configs/v1.gin:63-65 (ResidualStack.dilations_list, kernel_sizes [3])
+
+
+def encoder_v1(x: Tensor, sd, prefix: str, ratios=(4, 4, 4, 2), n_out: int = 2, mode: str = "centered",
+               training: bool = True) -> Tensor:
+    """Encoder.forward (rave/blocks.py:426-503) with sample_norm=False, repeat_layers=1 (v1.gin:44-50): conv k7, then per
+    ratio BatchNorm1d -> LeakyReLU(.2) -> Conv1d(k = 2r+1, stride r), LeakyReLU, grouped Conv1d(k5, groups = n_out).
+    BatchNorm uses batch statistics in training mode (nn.BatchNorm1d defaults: eps 1e-5)."""
+    p = prefix + "net."
+    h = conv1d(x, sd[p + "0.weight"], sd.get(p + "0.bias"), pad=get_padding(7, mode=mode))
+    i = 1
+    for r in ratios:
+        h = F.batch_norm(h, sd[f"{p}{i}.running_mean"].clone(), sd[f"{p}{i}.running_var"].clone(),
+                         sd[f"{p}{i}.weight"], sd[f"{p}{i}.bias"], training, 0.1, 1e-5)
+        h = leaky_relu(h, 0.2)
+        h = conv1d(h, sd[f"{p}{i + 2}.weight"], sd.get(f"{p}{i + 2}.bias"), r, 1, get_padding(2 * r + 1, r, mode=mode))
+        i += 3
+    h = leaky_relu(h, 0.2)
+    w, b = sd[f"{p}{i + 1}.weight"], sd.get(f"{p}{i + 1}.bias")
+    return F.conv1d(F.pad(h, get_padding(5, mode=mode)), w, b, 1, 0, 1, n_out)
+
+
+def residual_stack_v1(x: Tensor, sd, prefix: str, mode: str = "centered") -> Tensor:
+    """ResidualStack (rave/blocks.py:144-160) with kernel_sizes [3]: one ResidualBlock of three ResidualLayers
+    x + conv(act(conv(act(x)))) (48-80, 115-141); the single branch is stacked and summed (158-159)."""
+    h = x
+    for li, dil in enumerate(V1_DILATIONS):
+        q = f"{prefix}net.branches.0.net.{li}.net.aligned.branches.0."
+        y = h
+        for j, d in enumerate(dil):
+            y = leaky_relu(y, 0.2)
+            y = conv1d(y, wn_weight(sd, f"{q}{2 * j + 1}."), sd.get(f"{q}{2 * j + 1}.bias"), 1, d,
+                       get_padding(3, dilation=d, mode=mode))
+        h = h + y
+    return h
+
+
+def noise_generator_v1(x: Tensor, sd, prefix: str, ratios=(4, 4, 4), data_size: int = 16,
+                       noise: Optional[Tensor] = None, mode: str = "centered") -> Tensor:
+    """NoiseGenerator.forward (rave/blocks.py:195-240): strided convs -> mod_sigmoid(. - 5) -> impulse responses ->
+    FFT convolution with uniform noise (injected, like noise_generator_v2)."""
+    h = x
+    for i, r in enumerate(ratios):
+        h = conv1d(h, sd[f"{prefix}net.{2 * i}.weight"], sd.get(f"{prefix}net.{2 * i}.bias"), r, 1,
+                   get_padding(3, r, mode=mode))
+        if i != len(ratios) - 1:
+            h = leaky_relu(h, 0.2)
+    amp = mod_sigmoid(h - 5).permute(0, 2, 1)
+    amp = amp.reshape(amp.shape[0], amp.shape[1], data_size, -1)
+    target = 1
+    for r in ratios:
+        target *= r
+    ir = amp_to_impulse_response(amp, target)
+    if noise is None:
+        noise = torch.rand_like(ir) * 2 - 1
+    out = fft_convolve(noise, ir).permute(0, 2, 1, 3)
+    return out.reshape(out.shape[0], out.shape[1], -1)
+
+
+def generator_v1(z: Tensor, sd, prefix: str, ratios=(4, 4, 4, 2), data_size: int = 16, loud_stride: int = 1,
+                 use_noise: bool = True, warmed_up: bool = False, noise: Optional[Tensor] = None,
+                 mode: str = "centered") -> Tensor:
+    """Generator.forward (rave/blocks.py:322-423): conv k7, per ratio UpsampleLayer (act -> ConvTranspose1d(2r, r, r//2),
+    163-192) + ResidualStack, then tanh(waveform) * mod_sigmoid(loudness) (+ noise once warmed up)."""
+    p = prefix + "net."
+    h = conv1d(z, wn_weight(sd, p + "0."), sd.get(p + "0.bias"), pad=get_padding(7, mode=mode))
+    i = 1
+    for r in ratios:
+        h = leaky_relu(h, 0.2)
+        if r > 1:
+            h = conv_transpose1d(h, wn_weight(sd, f"{p}{i}.net.1."), sd.get(f"{p}{i}.net.1.bias"), r, r // 2)
+        else:
+            h = conv1d(h, wn_weight(sd, f"{p}{i}.net.1."), sd.get(f"{p}{i}.net.1.bias"), pad=get_padding(3, mode=mode))
+        h = residual_stack_v1(h, sd, f"{p}{i + 1}.", mode)
+        i += 2
+    q = prefix + "synth.branches."
+    wave = conv1d(h, wn_weight(sd, q + "0."), sd.get(q + "0.bias"), pad=get_padding(7, mode=mode))
+    loud = conv1d(h, wn_weight(sd, q + "1."), sd.get(q + "1.bias"), loud_stride, 1,
+                  get_padding(2 * loud_stride + 1, loud_stride, mode=mode))
+    if loud_stride != 1:
+        loud = loud.repeat_interleave(loud_stride)
+    loud = loud.reshape(h.shape[0], 1, -1)
+    wave = torch.tanh(wave) * mod_sigmoid(loud)
+    if warmed_up and use_noise:
+        wave = wave + noise_generator_v1(h, sd, q + "2.", data_size=data_size, noise=noise, mode=mode)
+    return wave

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 from torch.nn.utils.weight_norm import WeightNorm
 
-from . import cc, ops
+from . import cc, core, ops
 from ._lib import RaveB200Error
 
 
@@ -179,6 +179,198 @@ class DilatedUnit(nn.Module):
 
     def forward(self, x: torch.Tensor, res: Optional[torch.Tensor] = None) -> torch.Tensor:
         return self.net(x, res=res)
+
+
+# ---------------------------------------------------------------------------------------------
+# v1 architecture (rave/blocks.py:48-240, 322-503; configs/v1.gin).  Not in any BASELINE config: the blocks run on the
+# generic library kernels (activation fused into the following conv's operand load, residual add into its epilogue);
+# BatchNorm1d / repeat_interleave / stack-sum are the reference's own torch calls.  Same constructor arguments,
+# sub-module layout and state_dict keys as the reference.
+# ---------------------------------------------------------------------------------------------
+
+class SampleNorm(nn.Module):
+    """rave/blocks.py:25-28."""
+
+    def forward(self, x):
+        return x / torch.norm(x, 2, 1, keepdim=True)
+
+
+class ResidualLayer(nn.Module):
+    """rave/blocks.py:48-80: x + [act -> Conv1d(dim, dim, k, dilation d)] for d in dilations."""
+
+    def __init__(self, dim, kernel_size, dilations, cumulative_delay=0,
+                 activation: Callable[[int], nn.Module] = _default_activation):
+        super().__init__()
+        net = []
+        for d in dilations:
+            net.append(activation(dim))
+            net.append(normalization(cc.Conv1d(dim, dim, kernel_size, dilation=d,
+                                               padding=cc.get_padding(kernel_size, dilation=d))))
+        self.net = Residual(cc.CachedSequential(*net), cumulative_delay=cumulative_delay)
+        self.cumulative_delay = self.net.cumulative_delay
+
+    def forward(self, x):
+        # the skip add rides on the epilogue of the last conv (CachedSequential.forward(x, res=x))
+        return self.net.aligned.branches[0](x, res=x)
+
+
+class ResidualBlock(nn.Module):
+    """rave/blocks.py:115-141."""
+
+    def __init__(self, dim, kernel_size, dilations_list, cumulative_delay=0) -> None:
+        super().__init__()
+        layers = [ResidualLayer(dim, kernel_size, dilations) for dilations in dilations_list]
+        self.net = cc.CachedSequential(*layers, cumulative_delay=cumulative_delay)
+        self.cumulative_delay = self.net.cumulative_delay
+
+    def forward(self, x):
+        for layer in self.net:
+            x = layer(x)
+        return x
+
+
+class ResidualStack(nn.Module):
+    """rave/blocks.py:144-160 (v1.gin:63-65: kernel_sizes [3], dilations_list [[1, 1], [3, 1], [5, 1]])."""
+
+    def __init__(self, dim, kernel_sizes=(3,), dilations_list=((1, 1), (3, 1), (5, 1)), cumulative_delay=0) -> None:
+        super().__init__()
+        blocks = [ResidualBlock(dim, k, dilations_list) for k in kernel_sizes]
+        self.net = cc.AlignBranches(*blocks, cumulative_delay=cumulative_delay)
+        self.cumulative_delay = self.net.cumulative_delay
+
+    def forward(self, x):
+        x = self.net(x)
+        return torch.stack(x, 0).sum(0)
+
+
+class UpsampleLayer(nn.Module):
+    """rave/blocks.py:163-192."""
+
+    def __init__(self, in_dim, out_dim, ratio, cumulative_delay=0,
+                 activation: Callable[[int], nn.Module] = _default_activation):
+        super().__init__()
+        net = [activation(in_dim)]
+        if ratio > 1:
+            net.append(normalization(cc.ConvTranspose1d(in_dim, out_dim, 2 * ratio, stride=ratio, padding=ratio // 2)))
+        else:
+            net.append(normalization(cc.Conv1d(in_dim, out_dim, 3, padding=cc.get_padding(3))))
+        self.net = cc.CachedSequential(*net)
+        self.cumulative_delay = self.net.cumulative_delay + cumulative_delay * ratio
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class NoiseGenerator(nn.Module):
+    """rave/blocks.py:195-240 (v1.gin:67-70: ratios [4, 4, 4], noise_bands 5)."""
+
+    def __init__(self, in_size, data_size, ratios=(4, 4, 4), noise_bands=5):
+        super().__init__()
+        net = []
+        channels = [in_size] * len(ratios) + [data_size * noise_bands]
+        for i, r in enumerate(ratios):
+            net.append(cc.Conv1d(channels[i], channels[i + 1], 3, padding=cc.get_padding(3, r), stride=r))
+            if i != len(ratios) - 1:
+                net.append(nn.LeakyReLU(.2))
+        self.net = cc.CachedSequential(*net)
+        self.data_size = data_size
+        self.cumulative_delay = 0
+        self.register_buffer("target_size", torch.tensor(np.prod(ratios)).long())
+        self._target_size = int(np.prod(ratios))          # host copy: no device sync per forward
+
+    def forward(self, x, noise: Optional[torch.Tensor] = None):
+        """`noise` (optional, uniform in [-1, 1), shape of the impulse responses) lets a parity test inject the draw."""
+        amp = core.mod_sigmoid(self.net(x) - 5)
+        amp = amp.permute(0, 2, 1)
+        amp = amp.reshape(amp.shape[0], amp.shape[1], self.data_size, -1)
+        ir = core.amp_to_impulse_response(amp, self._target_size)
+        if noise is None:
+            noise = self.__dict__.get("_noise_override")          # parity tests inject the draw (Generator calls forward(x))
+        if noise is None:
+            noise = torch.rand_like(ir) * 2 - 1
+        noise = core.fft_convolve(noise, ir).permute(0, 2, 1, 3)
+        return noise.reshape(noise.shape[0], noise.shape[1], -1)
+
+
+class Generator(nn.Module):
+    """rave/blocks.py:322-423 (v1 decoder: upsampling stacks, then waveform / loudness / filtered-noise branches)."""
+
+    def __init__(self, latent_size, capacity, data_size, ratios, loud_stride, use_noise, n_channels: int = 1,
+                 recurrent_layer: Optional[Callable[[], nn.Module]] = None):
+        super().__init__()
+        net = [normalization(cc.Conv1d(latent_size, 2 ** len(ratios) * capacity, 7, padding=cc.get_padding(7)))]
+        if recurrent_layer is not None:
+            net.append(recurrent_layer(dim=2 ** len(ratios) * capacity, cumulative_delay=0))
+        for i, r in enumerate(ratios):
+            in_dim = 2 ** (len(ratios) - i) * capacity
+            out_dim = 2 ** (len(ratios) - i - 1) * capacity
+            net.append(UpsampleLayer(in_dim, out_dim, r))
+            net.append(ResidualStack(out_dim))
+        self.net = cc.CachedSequential(*net)
+        wave_gen = normalization(cc.Conv1d(out_dim, data_size * n_channels, 7, padding=cc.get_padding(7)))
+        loud_gen = normalization(cc.Conv1d(out_dim, 1, 2 * loud_stride + 1, stride=loud_stride,
+                                           padding=cc.get_padding(2 * loud_stride + 1, loud_stride)))
+        branches = [wave_gen, loud_gen]
+        if use_noise:
+            branches.append(NoiseGenerator(out_dim, data_size * n_channels))
+        self.synth = cc.AlignBranches(*branches, cumulative_delay=self.net.cumulative_delay)
+        self.use_noise = use_noise
+        self.loud_stride = loud_stride
+        self.cumulative_delay = self.synth.cumulative_delay
+        self.register_buffer("warmed_up", torch.tensor(0))
+
+    def set_warmed_up(self, state: bool):
+        state = bool(state)
+        if self.__dict__.get("_warmed_up_host") != state:
+            self.warmed_up = torch.tensor(int(state), device=self.warmed_up.device)
+            self.__dict__["_warmed_up_host"] = state
+
+    def forward(self, x):
+        x = self.net(x)
+        if self.use_noise:
+            waveform, loudness, noise = self.synth(x)
+        else:
+            waveform, loudness = self.synth(x)
+            noise = torch.zeros_like(waveform)
+        if self.loud_stride != 1:
+            loudness = loudness.repeat_interleave(self.loud_stride)
+        loudness = loudness.reshape(x.shape[0], 1, -1)
+        waveform = torch.tanh(waveform) * core.mod_sigmoid(loudness)
+        if self.__dict__.get("_warmed_up_host", None) is None:
+            self.__dict__["_warmed_up_host"] = bool(self.warmed_up)
+        if self.__dict__["_warmed_up_host"] and self.use_noise:
+            waveform = waveform + noise
+        return waveform
+
+
+class Encoder(nn.Module):
+    """rave/blocks.py:426-503 (v1 encoder: BatchNorm1d / SampleNorm, strided convs k = 2 r + 1, grouped output conv)."""
+
+    def __init__(self, data_size, capacity, latent_size, ratios, n_out, sample_norm, repeat_layers, n_channels: int = 1,
+                 recurrent_layer: Optional[Callable[[], nn.Module]] = None, spectrogram=None):
+        super().__init__()
+        data_size = data_size or n_channels
+        net = [cc.Conv1d(data_size * n_channels, capacity, 7, padding=cc.get_padding(7))]
+        for i, r in enumerate(ratios):
+            in_dim = 2 ** i * capacity
+            out_dim = 2 ** (i + 1) * capacity
+            net.append(SampleNorm() if sample_norm else nn.BatchNorm1d(in_dim))
+            net.append(nn.LeakyReLU(.2))
+            net.append(cc.Conv1d(in_dim, out_dim, 2 * r + 1, padding=cc.get_padding(2 * r + 1, r), stride=r))
+            for _ in range(repeat_layers - 1):
+                net.append(SampleNorm() if sample_norm else nn.BatchNorm1d(out_dim))
+                net.append(nn.LeakyReLU(.2))
+                net.append(cc.Conv1d(out_dim, out_dim, 3, padding=cc.get_padding(3)))
+        net.append(nn.LeakyReLU(.2))
+        if recurrent_layer is not None:
+            net.append(recurrent_layer(dim=out_dim, cumulative_delay=0))
+            net.append(nn.LeakyReLU(.2))
+        net.append(cc.Conv1d(out_dim, latent_size * n_out, 5, padding=cc.get_padding(5), groups=n_out))
+        self.net = cc.CachedSequential(*net)
+        self.cumulative_delay = self.net.cumulative_delay
+
+    def forward(self, x):
+        return self.net(x)
 
 
 class NoiseGeneratorV2(nn.Module):

@@ -89,8 +89,6 @@ class Conv1d(nn.Conv1d):
         if "bias" not in kwargs and len(args) < 8:
             kwargs["bias"] = config.conv_bias
         super().__init__(*args, **kwargs)
-        if self.groups != 1:
-            raise NotImplementedError("grouped convolutions are not on the hot path")
         self.cumulative_delay = 0
 
     def script_cache(self):
@@ -102,6 +100,20 @@ class Conv1d(nn.Conv1d):
             x = act(x)
             code = (ops.ACT_NONE, 0.0, None)
         alpha = code[2].reshape(-1) if code[2] is not None else None
+        if self.groups != 1:
+            # grouped conv (the v1 Encoder's last layer, rave/blocks.py:489-497: groups = n_out): one launch per group on
+            # its slice of the input / weight channels, same nn.Conv1d parameter layout [Cout, Cin / groups, K]
+            g = self.groups
+            cin, cout = self.in_channels // g, self.out_channels // g
+            outs = []
+            for i in range(g):
+                xi = x[:, i * cin:(i + 1) * cin].contiguous()
+                ai = alpha[i * cin:(i + 1) * cin].contiguous() if alpha is not None else None
+                bi = self.bias[i * cout:(i + 1) * cout] if self.bias is not None else None
+                ri = res[:, i * cout:(i + 1) * cout].contiguous() if res is not None else None
+                outs.append(ops.conv1d(xi, self.weight[i * cout:(i + 1) * cout], bi, ri, self.stride[0],
+                                       self.dilation[0], self._pad, code[0], code[1], ai))
+            return torch.cat(outs, 1)
         return ops.conv1d(x, self.weight, self.bias, res, self.stride[0], self.dilation[0], self._pad,
                           code[0], code[1], alpha)
 

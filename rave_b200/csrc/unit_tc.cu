@@ -355,12 +355,14 @@ constexpr int UW_WSLAB = 96 * 64;                   // one (tap, K block) weight
 constexpr int UW_STAGES = 3;
 constexpr int UW_W3_OFF = 0, UW_W1_OFF = 9 * UW_WSLAB, UW_A_OFF = 12 * UW_WSLAB;
 constexpr int UW_A2_OFF = UW_A_OFF + UW_STAGES * 3 * UW_ASLAB;
-constexpr int UW_BAR_OFF = UW_A2_OFF + 3 * (128 * 64);
+constexpr int UW_OUT_OFF = UW_A2_OFF + 3 * (128 * 64);      // staging tile of the bf16 output (TMA store source)
+constexpr int UW_BAR_OFF = UW_OUT_OFF + 3 * (128 * 64);
 constexpr int UW_TOTAL = UW_BAR_OFF + 256 + 1024;
 
 __global__ void __launch_bounds__(U_THREADS, 1)
 dilated_unit_ws96_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w3,
-                         const __grid_constant__ CUtensorMap tmap_w1, const UnitParams p) {
+                         const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_out,
+                         const __grid_constant__ CUtensorMap tmap_a1, const UnitParams p) {
   constexpr int C = 96, BK = 32, KB = 3, SWZ = 64, A2_SLAB = 128 * 64;
   constexpr uint32_t TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
@@ -385,7 +387,7 @@ dilated_unit_ws96_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tma_prefetch_desc(&tmap_w1);
     for (int s = 0; s < UW_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], U_EPI_WARPS);     // released by the epilogue: it reads the skip rows from the tile
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -459,7 +461,6 @@ dilated_unit_ws96_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 umma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k > 0 || kb > 0 || kk > 0) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);
           umma_commit(&tfull_bar[buf]);
         }
         __syncwarp();
@@ -490,19 +491,37 @@ dilated_unit_ws96_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else {
-    // =========================== epilogue (8 warps): as dilated_unit_tc_kernel<96, 32> ===========================
+    // =========================== epilogue (8 warps) ===========================
+    // Per-thread row accesses to global memory touch 32 different 128-byte lines per instruction (L1 wavefront bound:
+    // the skip read and the output write were ~1.6k clocks each per tile).  Here the skip comes from the haloed tile
+    // that is already in shared memory (its centre rows), and both bf16 outputs leave through TMA: a1 straight from
+    // the A2 tile (same K-major swizzled layout as its tensor map's boxes), the unit's output from a staging tile.
     const int quad = warp & 3;
     const int part = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    const uint32_t row_xor = (uint32_t)((row >> 1) & 3);          // 64-byte swizzle
+    const uint32_t row_xor = (uint32_t)((row >> 1) & 3);          // 64-byte swizzle of tile row `row`
+    const int srow = row + p.pad_l;                               // the same position inside the haloed tile
+    const uint32_t srow_off = (uint32_t)srow * 64u, srow_xor = (uint32_t)((srow >> 1) & 3);
+    const bool issuer = threadIdx.x == 64;
+    uint8_t *outb = smem + UW_OUT_OFF;
     int job = 0, it = 0;
+    int stage = 0;
+    uint32_t sphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int lt = tile % p.n_lt, b = tile / p.n_lt;
-      const int l = lt * 128 + row;
+      const int l0 = lt * 128;
+      const int l = l0 + row;
       const bool valid = (b < p.B) && (l < p.L);
       const size_t grow = ((size_t)b * p.pitch + l) * C;
       if (it > 0) mbar_wait(a2_free, (it - 1) & 1);
-      {   // ---- epilogue 1: acc -> LeakyReLU -> bf16 -> A2 (swizzled K-major rows) [+ HBM copy for the backward]
+      if (p.a1_out && it > 0) {                                   // the a1 store of the previous tile has read A2
+        if (issuer) {                                             // (bulk groups complete in order: a1, out, a1, out ...)
+          if (p.out_act) bulk_wait_read<1>();
+          else bulk_wait_read<0>();
+        }
+        named_bar_sync(2, 256);
+      }
+      {   // ---- epilogue 1: acc -> LeakyReLU -> bf16 -> A2 (swizzled K-major rows)
         const int buf = job & 1;
         mbar_wait(&tfull_bar[buf], (job >> 1) & 1);
         tc_fence_after();
@@ -521,15 +540,8 @@ dilated_unit_ws96_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             pk[w] = *reinterpret_cast<const uint32_t *>(&h);
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int cc = c0 + 8 * q;
-            const uint32_t off = (uint32_t)(cc / BK) * A2_SLAB + (uint32_t)row * SWZ + ((((uint32_t)(cc % BK) >> 3) ^ row_xor) << 4);
-            *reinterpret_cast<uint4 *>(a2 + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
-          if (p.a1_out && valid) {
-            stg256(p.a1_out + grow + c0, pk);
-            stg256(p.a1_out + grow + c0 + 16, pk + 8);
-          }
+          for (int q = 0; q < 4; ++q)      // chunk c0 = K block c0 / 32: 16-byte unit q of this row
+            sts128(a2 + (uint32_t)(c0 / BK) * A2_SLAB + (uint32_t)row * SWZ + (((uint32_t)q ^ row_xor) << 4), pk + 4 * q);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -538,67 +550,89 @@ dilated_unit_ws96_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           mbar_arrive(&tempty_bar[buf]);
           mbar_arrive(a2_ready);
         }
+        if (p.a1_out) {                                           // training: keep a1 for the backward (write-only)
+          named_bar_sync(2, 256);
+          if (issuer) {
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) tma_store_4d(&tmap_a1, a2 + kb * A2_SLAB, kb * BK, 0, l0, b);
+            bulk_commit();
+          }
+        }
         ++job;
       }
       {   // ---- epilogue 2: acc + skip -> outputs
         const int buf = job & 1;
-        uint32_t sk[2][16];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = part * 32 + 64 * i;
-          if (c0 < C && valid) {
-            ldg256(p.xa + grow + c0, sk[i]);
-            ldg256(p.xa + grow + c0 + 16, sk[i] + 8);
-          }
-        }
         mbar_wait(&tfull_bar[buf], (job >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256;
+        const uint8_t *sa = smem + UW_A_OFF + stage * 3 * UW_ASLAB;      // this tile's haloed activation rows
+        mbar_wait(&full_bar[stage], sphase);                     // (long complete: makes the TMA writes visible here)
+        if (p.out_act) {                                          // the previous tile's output store has read `outb`
+          if (issuer) {
+            if (p.a1_out) bulk_wait_read<1>();                    // ... this tile's a1 store may still be running
+            else bulk_wait_read<0>();
+          }
+          named_bar_sync(1, 256);
+        }
+#pragma unroll 1
+        for (int c0 = part * 32; c0 < C; c0 += 64) {
+          uint32_t sk[16];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = part * 32 + 64 * i;
-          if (c0 < C) {
-            float v[32];
-            tmem_ld_32x32(taddr + c0, v);
-            if (valid) {
+          for (int q = 0; q < 4; ++q)
+            lds128(sa + (uint32_t)(c0 / BK) * UW_ASLAB + srow_off + (((uint32_t)q ^ srow_xor) << 4), sk + 4 * q);
+          float v[32];
+          tmem_ld_32x32(taddr + c0, v);
 #pragma unroll
-              for (int w = 0; w < 16; ++w) {
-                const float s0 = bfl(sk[i][w]), s1 = bfh(sk[i][w]);
-                v[2 * w] += fminf(s0, s0 * p.slope_in_inv);
-                v[2 * w + 1] += fminf(s1, s1 * p.slope_in_inv);
+          for (int w = 0; w < 16; ++w) {
+            const float s0 = bfl(sk[w]), s1 = bfh(sk[w]);
+            v[2 * w] += fminf(s0, s0 * p.slope_in_inv);          // inverse LeakyReLU of the input operand
+            v[2 * w + 1] += fminf(s1, s1 * p.slope_in_inv);
+          }
+          if (p.out_f32 && valid) {
+            uint32_t o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(v[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) stg256(p.out_f32 + grow + c0 + 8 * j, o + 8 * j);
+          }
+          if (p.out_act) {
+            uint32_t pk[16];
+            const float2 so = make_float2(p.slope_out, p.slope_out);
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+              const float2 t = make_float2(v[2 * w], v[2 * w + 1]);
+              __nv_bfloat162 h = __floats2bfloat162_rn(t.x, t.y);
+              if (p.act_out == RAVE_ACT_LEAKY) {
+                const float2 u = __fmul2_rn(t, so);
+                h = __hmax2(h, __floats2bfloat162_rn(u.x, u.y));
               }
-              if (p.out_f32) {
-                uint32_t o[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(v[j]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) stg256(p.out_f32 + grow + c0 + 8 * j, o + 8 * j);
-              }
-              if (p.out_act) {
-                uint32_t pk[16];
-                const float2 so = make_float2(p.slope_out, p.slope_out);
-#pragma unroll
-                for (int w = 0; w < 16; ++w) {
-                  const float2 t = make_float2(v[2 * w], v[2 * w + 1]);
-                  __nv_bfloat162 h = __floats2bfloat162_rn(t.x, t.y);
-                  if (p.act_out == RAVE_ACT_LEAKY) {
-                    const float2 u = __fmul2_rn(t, so);
-                    h = __hmax2(h, __floats2bfloat162_rn(u.x, u.y));
-                  }
-                  pk[w] = *reinterpret_cast<const uint32_t *>(&h);
-                }
-                stg256(p.out_act + grow + c0, pk);
-                stg256(p.out_act + grow + c0 + 16, pk + 8);
-              }
+              pk[w] = *reinterpret_cast<const uint32_t *>(&h);
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              sts128(outb + (uint32_t)(c0 / BK) * A2_SLAB + (uint32_t)row * SWZ + (((uint32_t)q ^ row_xor) << 4), pk + 4 * q);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) {
+          mbar_arrive(&tempty_bar[buf]);
+          mbar_arrive(&empty_bar[stage]);                          // skip rows read: the producer may refill this stage
+        }
+        if (p.out_act) {
+          fence_proxy_async();
+          named_bar_sync(1, 256);
+          if (issuer) {
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) tma_store_4d(&tmap_out, outb + kb * A2_SLAB, kb * BK, 0, l0, b);
+            bulk_commit();
+          }
+        }
         ++job;
       }
+      if (++stage == UW_STAGES) { stage = 0; sphase ^= 1; }
     }
+    if (issuer) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -752,7 +786,25 @@ extern "C" int rave_dilated_unit_tc_fwd(const void *xa, const void *w3t, const v
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      launch_pdl(dilated_unit_ws96_kernel, dim3(tiles < sms ? tiles : sms), dim3(U_THREADS), UW_TOTAL, s, tah, t3s, t1s, p);
+      // bf16 outputs leave through TMA: [B][pitch][96] viewed as (c, 1, row, b) boxes of one 32-channel K block x 128 rows
+      // (rows >= L and batches >= B are clipped by the TMA unit)
+      CUtensorMap tout, ta1;
+      memset(&tout, 0, sizeof(tout));
+      memset(&ta1, 0, sizeof(ta1));
+      for (int which = 0; which < 2; ++which) {
+        void *base = which == 0 ? out_act : a1_out;
+        if (!base) continue;
+        cuuint64_t dims[4] = {(cuuint64_t)C, 1, (cuuint64_t)L, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2, (cuuint64_t)C * 2 * pitch};
+        cuuint32_t box[4] = {32, 1, 128, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(which == 0 ? &tout : &ta1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RAVE_CHECK_ARG(r == CUDA_SUCCESS, "dilated_unit_tc(ws): output tensor map encode failed (%d)", (int)r);
+      }
+      launch_pdl(dilated_unit_ws96_kernel, dim3(tiles < sms ? tiles : sms), dim3(U_THREADS), UW_TOTAL, s, tah, t3s, t1s,
+                 tout, ta1, p);
       RAVE_CHECK_LAUNCH("dilated_unit_tc(ws)");
       return 0;
     }

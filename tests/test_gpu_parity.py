@@ -576,3 +576,41 @@ def test_noise_generator_v2_vs_oracle():
     g = torch.autograd.grad((y * probe.cuda()).sum(), [xg] + [pg[k] for k in names])
     for k, a, b in zip(["x"] + names, g, g_o):
         assert rel_l2(a, b) < 5e-4, (k, rel_l2(a, b))
+
+
+def test_v1_encoder_generator_match_reference_golden():
+    """a12: the v1 blocks -- Encoder (BatchNorm1d, strided convs, grouped output conv) and Generator
+    (UpsampleLayer / ResidualStack, waveform x loudness, filtered-noise branch) -- on the library kernels against the
+    reference's own modules (tests/golden/autoencoder_v1_tiny.pt): strict state_dict load, forward and gradients."""
+    from rave_b200 import blocks, cc
+    g = load("autoencoder_v1_tiny.pt")
+    ratios = list(g["ratios"])
+    with cc.configure(conv_bias=False):
+        enc = blocks.Encoder(data_size=16, capacity=g["capacity"], latent_size=g["latent_size"], ratios=ratios, n_out=2,
+                             sample_norm=False, repeat_layers=1)
+        dec = blocks.Generator(latent_size=g["latent_size"], capacity=g["capacity"], data_size=16, ratios=ratios[::-1],
+                               loud_stride=1, use_noise=True)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in g["state_dict"].items() if k.startswith("encoder.")},
+                        strict=True)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in g["state_dict"].items() if k.startswith("decoder.")},
+                        strict=True)
+    enc.cuda().train()
+    dec.cuda().train()
+    dec.set_warmed_up(True)
+    dec.synth.branches[2].__dict__["_noise_override"] = g["noise"].cuda()
+    x = g["x"].cuda().requires_grad_(True)
+    z = enc(x)
+    assert rel_l2(z, g["z"]) < 2e-5
+    zin = g["zin"].cuda().requires_grad_(True)
+    y = dec(zin)
+    assert rel_l2(y, g["y"]) < 2e-5
+    pe, pd = dict(enc.named_parameters()), dict(dec.named_parameters())
+    ne = sorted(k[len("encoder."):] for k in g["grads"] if k.startswith("encoder."))
+    nd = sorted(k[len("decoder."):] for k in g["grads"] if k.startswith("decoder."))
+    ge = torch.autograd.grad((z * g["probe_z"].cuda()).sum(), [x] + [pe[k] for k in ne])
+    gd = torch.autograd.grad((y * g["probe_y"].cuda()).sum(), [zin] + [pd[k] for k in nd])
+    assert rel_l2(ge[0], g["grad_x"]) < 1e-4 and rel_l2(gd[0], g["grad_zin"]) < 1e-4
+    worst = max([(rel_l2(a, g["grads"]["encoder." + k]), "encoder." + k) for k, a in zip(ne, ge[1:])] +
+                [(rel_l2(a, g["grads"]["decoder." + k]), "decoder." + k) for k, a in zip(nd, gd[1:])])
+    print(f"v1 parameter gradients, worst rel-L2 {worst[0]:.2e} ({worst[1]})")
+    assert worst[0] < 5e-4, worst

@@ -221,3 +221,26 @@ def test_noise_generator_oracle_matches_live_reference():
     y = O.noise_generator_v2(x, sd, "n.", (2, 2, 2), 16, 1, noise)
     assert y.shape == y_ref.shape == (2, 16, 256)
     assert rel_l2(y, y_ref) < 1e-6
+
+
+def test_v1_restatement_matches_reference_golden():
+    """a12: O.encoder_v1 / O.generator_v1 (BatchNorm encoder, ResidualStack generator with loudness and filtered-noise
+    branches) against tests/golden/autoencoder_v1_tiny.pt, forward and every gradient."""
+    g = load("autoencoder_v1_tiny.pt")
+    sd = g["state_dict"]
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and "running_" not in k and "target_size" not in k)
+          for k, v in sd.items()}
+    x = g["x"].clone().requires_grad_(True)
+    z = O.encoder_v1(x, po, "encoder.", g["ratios"])
+    assert rel_l2(z, g["z"]) < 2e-6
+    zin = g["zin"].clone().requires_grad_(True)
+    y = O.generator_v1(zin, po, "decoder.", tuple(g["ratios"])[::-1], warmed_up=True, noise=g["noise"])
+    assert rel_l2(y, g["y"]) < 2e-6
+    names = sorted(g["grads"])
+    ge = torch.autograd.grad((z * g["probe_z"]).sum(), [x] + [po[k] for k in names if k.startswith("encoder.")])
+    gd = torch.autograd.grad((y * g["probe_y"]).sum(), [zin] + [po[k] for k in names if k.startswith("decoder.")])
+    assert rel_l2(ge[0], g["grad_x"]) < 1e-5 and rel_l2(gd[0], g["grad_zin"]) < 1e-5
+    for k, a in zip([k for k in names if k.startswith("encoder.")], ge[1:]):
+        assert rel_l2(a, g["grads"][k]) < 1e-5, k
+    for k, a in zip([k for k in names if k.startswith("decoder.")], gd[1:]):
+        assert rel_l2(a, g["grads"][k]) < 1e-5, k
