@@ -524,6 +524,18 @@ def run_ours(args):
         model.on_train_batch_end()
     barrier()
 
+    # which parts actually ran on the tcgen05 engine (v3's Snake chains and the Descript discriminator do not)
+    on_engine = None
+    try:
+        if prec == "bf16" and model is not None:
+            enc_net = getattr(getattr(model.encoder, "encoder", model.encoder), "net", None)
+            on_engine = dict(
+                encoder=bool(enc_net is not None and enc_net._tc_plan() is not None),
+                decoder=bool(model.decoder.net._tc_plan() is not None),
+                discriminator=bool(hasattr(model.discriminator, "supports_fused_fm")
+                                   and model.discriminator.supports_fused_fm(x_dev)))
+    except Exception:
+        on_engine = None
     # ---- device-resident timed region -------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -629,7 +641,7 @@ def run_ours(args):
                        "global_batch": world * B, "samples": T, "parallelism": f"dp{world}",
                        "precision": ("bf16 operands / fp32 accumulate (tcgen05 engine); PQMF + losses fp32"
                                      if prec == "bf16" else "fp32 parity kernels (CUDA-core FMA)"),
-                       "launch": graph_note,
+                       "tcgen05_engine": on_engine, "launch": graph_note,
                        "l2_policy": "working set per step (>10 GB of activations) exceeds the 126 MB L2; "
                                     "two alternating input batches"},
             "roofline": roof, "step_roofline": step_roof, "forward_pqmf_enc_gen": fwd, "stock_cudnn_tf32": stock,

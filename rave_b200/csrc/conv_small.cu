@@ -246,45 +246,59 @@ __device__ __forceinline__ void ldg256_nc(const void *p, uint32_t *r) {     // 3
                : "l"(p));
 }
 
+// grid (blocks per batch entry, Bh): a batch entry's valid rows [L][C] are one contiguous range, so the index is linear
+// (no 64-bit divisions per element); two 256-bit loads per half in flight per thread; packed f32x2 arithmetic.
 __global__ void __launch_bounds__(256)
 fm_stats_kernel(const __nv_bfloat16 *__restrict__ a, float *__restrict__ stats, int Bh, int L, int pitch, int C,
                 float inv_slope) {
-  // one thread = 16 channels (one 256-bit load per batch half); C % 16 == 0
   __shared__ float red0[8], red1[8];
-  const int vecs = C >> 4;
-  const long total = (long)Bh * L * vecs;
+  const long n_vec = (long)L * (C >> 4);                    // 16-channel vectors of one batch entry
   const size_t half = (size_t)Bh * pitch * C;
-  float s0 = 0.f, s1 = 0.f;
-  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-    const int v = (int)(i % vecs);
-    const long bl = i / vecs;
-    const int l = (int)(bl % L);
-    const int b = (int)(bl / L);
-    const size_t o = ((size_t)b * pitch + l) * C + v * 16;
-    uint32_t rw[8], fw[8];
-    ldg256_nc(a + o, rw);
-    ldg256_nc(a + o + half, fw);
+  const __nv_bfloat16 *ar = a + (size_t)blockIdx.y * pitch * C;
+  const float2 inv2 = make_float2(inv_slope, inv_slope);
+  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+  const long stride = (long)gridDim.x * 256;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n_vec; i += 2 * stride) {
+    uint32_t rw[2][8], fw[2][8];
+    const long i2 = i + stride;
+    ldg256_nc(ar + i * 16, rw[0]);
+    ldg256_nc(ar + i * 16 + half, fw[0]);
+    const bool two = i2 < n_vec;
+    if (two) {
+      ldg256_nc(ar + i2 * 16, rw[1]);
+      ldg256_nc(ar + i2 * 16 + half, fw[1]);
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float hr0 = unleaky(bf16_lo(rw[j]), inv_slope), hr1 = unleaky(bf16_hi(rw[j]), inv_slope);
-      const float hf0 = unleaky(bf16_lo(fw[j]), inv_slope), hf1 = unleaky(bf16_hi(fw[j]), inv_slope);
-      s0 += fabsf(hr0 - hf0) + fabsf(hr1 - hf1);
-      s1 += fabsf(hr0) + fabsf(hr1);
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 r = make_float2(bf16_lo(rw[u][j]), bf16_hi(rw[u][j]));
+        const float2 f = make_float2(bf16_lo(fw[u][j]), bf16_hi(fw[u][j]));
+        const float2 rs = __fmul2_rn(r, inv2), fs = __fmul2_rn(f, inv2);
+        // inverse LeakyReLU (1 / slope >= 1): h = min(a, a / slope)
+        const float2 hr = make_float2(fminf(r.x, rs.x), fminf(r.y, rs.y));
+        const float2 hf = make_float2(fminf(f.x, fs.x), fminf(f.y, fs.y));
+        const float2 d = __fadd2_rn(hr, make_float2(-hf.x, -hf.y));
+        s0 = __fadd2_rn(s0, make_float2(fabsf(d.x), fabsf(d.y)));
+        s1 = __fadd2_rn(s1, make_float2(fabsf(hr.x), fabsf(hr.y)));
+      }
     }
   }
+  float t0 = s0.x + s0.y, t1 = s1.x + s1.y;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
   }
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { red0[wid] = s0; red1[wid] = s1; }
+  if (lane == 0) { red0[wid] = t0; red1[wid] = t1; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t0 = 0.f, t1 = 0.f;
-    for (int i = 0; i < 8; ++i) { t0 += red0[i]; t1 += red1[i]; }
-    atomicAdd(stats, t0);
-    atomicAdd(stats + 1, t1);
+    float u0 = 0.f, u1 = 0.f;
+    for (int i = 0; i < 8; ++i) { u0 += red0[i]; u1 += red1[i]; }
+    atomicAdd(stats, u0);
+    atomicAdd(stats + 1, u1);
   }
 }
 
@@ -424,11 +438,14 @@ extern "C" int rave_fm_stats(const void *a_bf16, float *stats, int Bh, int L, in
   RAVE_CHECK_ARG(a_bf16 && stats && Bh > 0 && L > 0 && pitch >= L && C > 0 && C % 16 == 0 && slope > 0.f &&
                      ((uintptr_t)a_bf16 & 31) == 0,
                  "fm_stats: bad argument (C %% 16 == 0, 32-byte aligned operand)");
-  const long total = (long)Bh * L * (C / 16);
-  long blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  fm_stats_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a_bf16, stats, Bh, L, pitch,
-                                                                 C, 1.f / slope);
+  RAVE_CHECK_ARG(Bh <= 65535, "fm_stats: %d batch entries per half > 65535", Bh);
+  const long per_b = (long)L * (C / 16);
+  long bx = (per_b + 511) / 512;                     // two vectors per thread and pass
+  const long cap = (148L * 8 + Bh - 1) / Bh;         // ~8 blocks per SM over the whole grid
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  fm_stats_kernel<<<dim3((unsigned)bx, (unsigned)Bh), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a_bf16, stats,
+                                                                                    Bh, L, pitch, C, 1.f / slope);
   RAVE_CHECK_LAUNCH("fm_stats");
   return 0;
 }
