@@ -198,6 +198,12 @@ int rave_conv1d_tc_fwd_x3(const void *xa_bf16, const void *wt_bf16, const float 
  * dbias [Cm] fp32, pre-zeroed, or NULL: += sum_{b,l} P[b][l][m] (the conv bias gradient when P = dy), reduced by the
  * tap-0 CTAs from the tiles they stream anyway (fp32 atomics across row slices). */
 int rave_conv1d_tc_wgrad_splits(int B, int Cm, int Lp, int Cn, int K);
+/* Snake (rave/blocks.py:852-860) on the engine's channel-last bf16 streams [rows][C] (v3 chains on the tcgen05 kernels):
+ * a = h + sin^2(alpha h) / (alpha + 1e-9);  backward: gh = ga * da/dh + add (add may be null), dalpha[c] += sum_rows
+ * ga * da/dalpha (dalpha zeroed by the caller). */
+int rave_snake_cl_fwd(const void *h_bf16, const float *alpha, void *a_bf16, long rows, int C, void *stream);
+int rave_snake_cl_bwd(const void *ga_bf16, const void *h_bf16, const float *alpha, const void *add_bf16, void *gh_bf16,
+                      float *dalpha, long rows, int C, void *stream);
 /* Multi-tap form (csrc/wgrad_mt.cu): one CTA accumulates up to 8 taps from ONE pass over the P rows and haloed Q tiles
  * shared by the taps of a phase.  rave_conv1d_tc_wgrad_mt_plan returns the split count to allocate dwt with, or 0 when
  * the layer must run on rave_conv1d_tc_wgrad (tap pattern / very short rows); same dwt / dbias contract. */

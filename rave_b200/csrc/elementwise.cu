@@ -675,6 +675,129 @@ __global__ void __launch_bounds__(1024) mt_wn_bwd_kernel(const __grid_constant__
 
 }  // namespace rave
 
+// ---------------------------------------------------------------------------------------------
+// Snake on the engine's channel-last bf16 streams (v3 chains on the tcgen05 kernels): the producing conv writes the
+// pre-activation h as bf16, these kernels turn it into the operand a = h + sin^2(alpha h) / (alpha + 1e-9) of the next
+// conv (rave/blocks.py:852-860; alpha per channel) and back: g_h = g_a (1 + alpha sin(2 alpha h) / (alpha + 1e-9)) + add,
+// dalpha[c] += sum_rows g_a (h sin(2 alpha h) / (alpha+eps) - sin^2(alpha h) / (alpha+eps)^2).  Rows = B * pitch (slack
+// rows are zero on both sides: snake(0) = 0).
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+__global__ void __launch_bounds__(256)
+snake_cl_fwd_kernel(const __nv_bfloat16 *__restrict__ h, const float *__restrict__ alpha, __nv_bfloat16 *__restrict__ a,
+                    long n_vec, int cv) {
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n_vec; i += (long)gridDim.x * 256) {
+    const int c0 = (int)(i % cv) * 8;
+    const uint4 q = *reinterpret_cast<const uint4 *>(h + i * 8);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x0 = __uint_as_float(w[j] << 16), x1 = __uint_as_float(w[j] & 0xFFFF0000u);
+      const float a0 = __ldg(alpha + c0 + 2 * j), a1 = __ldg(alpha + c0 + 2 * j + 1);
+      const float s0 = sinf(a0 * x0), s1 = sinf(a1 * x1);
+      const __nv_bfloat162 r = __floats2bfloat162_rn(x0 + s0 * s0 / (a0 + 1e-9f), x1 + s1 * s1 / (a1 + 1e-9f));
+      o[j] = *reinterpret_cast<const uint32_t *>(&r);
+    }
+    *reinterpret_cast<uint4 *>(a + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// grid (ceil(C / 64), row blocks); block = 8 channel vectors x 32 row lanes
+__global__ void __launch_bounds__(256)
+snake_cl_bwd_kernel(const __nv_bfloat16 *__restrict__ ga, const __nv_bfloat16 *__restrict__ h,
+                    const float *__restrict__ alpha, const __nv_bfloat16 *__restrict__ add,
+                    __nv_bfloat16 *__restrict__ gh, float *__restrict__ dalpha, long rows, int C, int rows_per_block) {
+  __shared__ float red[32][64 + 1];
+  const int cvl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cvl * 8;
+  const bool live = c0 < C;
+  float al[8], ae[8], part[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    al[j] = live ? alpha[c0 + j] : 1.f;
+    ae[j] = al[j] + 1e-9f;
+    part[j] = 0.f;
+  }
+  const long r0 = (long)blockIdx.y * rows_per_block;
+  const long r1 = min(rows, r0 + rows_per_block);
+  if (live) {
+    for (long r = r0 + rl; r < r1; r += 32) {
+      const size_t o = (size_t)r * C + c0;
+      const uint4 qg = *reinterpret_cast<const uint4 *>(ga + o);
+      const uint4 qh = *reinterpret_cast<const uint4 *>(h + o);
+      uint4 qa = make_uint4(0, 0, 0, 0);
+      if (add) qa = *reinterpret_cast<const uint4 *>(add + o);
+      const uint32_t wg[4] = {qg.x, qg.y, qg.z, qg.w}, wh[4] = {qh.x, qh.y, qh.z, qh.w}, wa[4] = {qa.x, qa.y, qa.z, qa.w};
+      uint32_t out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float res[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float g = e ? __uint_as_float(wg[j] & 0xFFFF0000u) : __uint_as_float(wg[j] << 16);
+          const float x = e ? __uint_as_float(wh[j] & 0xFFFF0000u) : __uint_as_float(wh[j] << 16);
+          const float ad = e ? __uint_as_float(wa[j] & 0xFFFF0000u) : __uint_as_float(wa[j] << 16);
+          const int k = 2 * j + e;
+          const float sn = sinf(al[k] * x), s2 = sinf(2.f * al[k] * x);
+          res[e] = g * (1.f + al[k] * s2 / ae[k]) + ad;
+          part[k] += g * (x * s2 / ae[k] - sn * sn / (ae[k] * ae[k]));
+        }
+        const __nv_bfloat162 rr = __floats2bfloat162_rn(res[0], res[1]);
+        out[j] = *reinterpret_cast<const uint32_t *>(&rr);
+      }
+      *reinterpret_cast<uint4 *>(gh + o) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+  }
+  if (!dalpha) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cvl * 8 + j] = part[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < C) atomicAdd(dalpha + c, t);
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_snake_cl_fwd(const void *h_bf16, const float *alpha, void *a_bf16, long rows, int C, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(h_bf16 && alpha && a_bf16 && rows > 0 && C > 0 && C % 8 == 0 &&
+                     (((uintptr_t)h_bf16 | (uintptr_t)a_bf16) & 15) == 0, "snake_cl_fwd: bad argument (C %% 8, 16-byte rows)");
+  const long n_vec = rows * (C / 8);
+  long blocks = (n_vec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  snake_cl_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)h_bf16, alpha,
+                                                                     (__nv_bfloat16 *)a_bf16, n_vec, C / 8);
+  RAVE_CHECK_LAUNCH("snake_cl_fwd");
+  return 0;
+}
+
+// dalpha [C] fp32 must be zeroed by the caller (accumulated with atomics); `add` (bf16, same shape) may be null.
+extern "C" int rave_snake_cl_bwd(const void *ga_bf16, const void *h_bf16, const float *alpha, const void *add_bf16,
+                                 void *gh_bf16, float *dalpha, long rows, int C, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(ga_bf16 && h_bf16 && alpha && gh_bf16 && rows > 0 && C > 0 && C % 8 == 0 &&
+                     (((uintptr_t)ga_bf16 | (uintptr_t)h_bf16 | (uintptr_t)gh_bf16 | (uintptr_t)add_bf16) & 15) == 0,
+                 "snake_cl_bwd: bad argument (C %% 8, 16-byte rows)");
+  const int gx = (C + 63) / 64;
+  long gy = (rows + 255) / 256;                 // >= 256 rows per block
+  const long cap = (148L * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  const int rpb = (int)((rows + gy - 1) / gy);
+  snake_cl_bwd_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16 *)ga_bf16, (const __nv_bfloat16 *)h_bf16, alpha, (const __nv_bfloat16 *)add_bf16,
+      (__nv_bfloat16 *)gh_bf16, dalpha, rows, C, rpb);
+  RAVE_CHECK_LAUNCH("snake_cl_bwd");
+  return 0;
+}
+
 // Host-side description of one layer (plain C struct of the ABI)
 static int weight_prep_tc_multi_impl(int n, const rave_wprep_layer *layers, void *stream, int x3) {
   using namespace rave;

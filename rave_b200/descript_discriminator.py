@@ -80,10 +80,46 @@ class MPD(nn.Module):
         # quirk D8: a FULL extra period is appended when t % period == 0
         return F.pad(x, (0, self.period - t % self.period), mode="reflect")
 
+    def _tc_specs(self):
+        """Plan of the whole MPD as ONE tensor-core chain (bf16 mode): conv -> LeakyReLU(0.1) -> ... -> conv_post, every
+        conv's fp32 output kept (the features are its activation).  The period axis folds into the batch, the Cin = 1
+        first layer reads the folded signal in place (engine.TcChainFn)."""
+        from . import engine
+        if "_tc_specs_cache" not in self.__dict__:
+            mods = []
+            for layer in self.convs:
+                mods += [layer[0], layer[1]]
+            mods.append(self.conv_post)
+            specs = engine.plan_convnet(nn.Sequential(*mods))
+            if specs is not None and not engine.chain_supported(specs):
+                specs = None
+            self.__dict__["_tc_specs_cache"] = specs
+        return self.__dict__["_tc_specs_cache"]
+
+    def _forward_tc(self, x, specs):
+        from . import engine
+        from .discriminator import ConvNet
+        B, C, L, W = x.shape
+        xa, _, _, _ = ConvNet._chain_input(None, x, specs)
+        outs = engine.run_chain(xa, specs, L)
+        lens = engine.chain_lengths(specs, L)
+        fmap = []
+        for i, (s, o, Lo) in enumerate(zip(specs, outs, lens)):
+            h = o[:, :Lo, :s.Cout].reshape(B, W, Lo, s.Cout).permute(0, 3, 2, 1)
+            if i < len(self.convs):          # features are POST-activation (descript_discriminator.py:59-61)
+                h = ops.activation(h.contiguous(), ops.ACT_LEAKY, self.convs[i][1].negative_slope)
+            fmap.append(h)
+        return fmap
+
     def forward(self, x):
+        from . import engine
         fmap = []
         x = self.pad_to_period(x)
         x = x.reshape(x.shape[0], x.shape[1], -1, self.period)
+        if engine.precision() == "bf16" and x.is_cuda and x.shape[1] == 1:
+            specs = self._tc_specs()
+            if specs is not None:
+                return self._forward_tc(x, specs)
         pre = None          # activation of the previous layer, fused into the next conv's operand load
         for layer in self.convs:
             conv, act = layer[0], layer[1]

@@ -78,11 +78,13 @@ class LayerSpec:
     cout_pad: int = 0
     res_opnd: Optional[int] = None # index of the layer whose INPUT operand a = LeakyReLU(h_src) carries the
                                    # residual stream: the skip is recovered from it (no fp32 copy of h_src)
+    pre_mod: Optional[nn.Module] = None   # the Snake module (owner of alpha) when pre_act == ACT_SNAKE
+    res_raw: Optional[int] = None  # Snake units: index of the layer whose raw (pre-Snake) bf16 input IS the skip stream
 
 
 def chain_supported(specs: List[LayerSpec]) -> bool:
     for s in specs:
-        if s.pre_act not in (ops.ACT_NONE, ops.ACT_LEAKY):
+        if s.pre_act not in (ops.ACT_NONE, ops.ACT_LEAKY, ops.ACT_SNAKE):
             return False
         cin = s.Cin + s.cin_pad
         cout = s.Cout + s.cout_pad
@@ -102,16 +104,28 @@ def _act_of(m):
 
 
 def plan_sequential(mods: List[nn.Module]) -> Optional[List[LayerSpec]]:
-    """EncoderV2.net / GeneratorV2.net style sequences: activations, cc.Conv1d, cc.ConvTranspose1d,
-    Residual(DilatedUnit), AdaIN (identity in training).  Returns None if something is unsupported."""
+    """EncoderV2.net / GeneratorV2.net style sequences: activations (LeakyReLU or Snake), cc.Conv1d, cc.ConvTranspose1d,
+    Residual(DilatedUnit), AdaIN (identity in training).  Returns None if something is unsupported.
+    Snake (v3): the producer writes its pre-activation as bf16, a channel-last Snake kernel turns it into the next conv's
+    operand (and keeps the raw stream for the backward and for the unit's skip)."""
     from . import blocks, cc
     specs: List[LayerSpec] = []
-    pending = (ops.ACT_NONE, 0.0)
+    NONE = (ops.ACT_NONE, 0.0, None)
+    pending = NONE
     last_idx = -1            # index of the layer producing the current stream (-1 = chain input)
+
+    def act_of(m):
+        if isinstance(m, nn.LeakyReLU):
+            return (ops.ACT_LEAKY, float(m.negative_slope), None)
+        if isinstance(m, blocks.Snake):
+            return (ops.ACT_SNAKE, 0.0, m)
+        return None
 
     def add_conv(conv, res_src=None):
         nonlocal pending, last_idx
         if isinstance(conv, cc.Conv1d):
+            if conv.groups != 1:
+                return False
             Cout, Cin, K = conv.out_channels, conv.in_channels, conv.kernel_size[0]
             spec = LayerSpec("conv", conv, Cin, Cout, K, conv.stride[0], conv.dilation[0], conv._pad,
                              pending[0], pending[1], res_src)
@@ -119,22 +133,24 @@ def plan_sequential(mods: List[nn.Module]) -> Optional[List[LayerSpec]]:
             Cin, Cout, K = conv.in_channels, conv.out_channels, conv.kernel_size[0]
             spec = LayerSpec("convT", conv, Cin, Cout, K, conv.stride[0], 1,
                              (conv.padding[0], conv.padding[0]), pending[0], pending[1], None)
+        spec.pre_mod = pending[2]
         specs.append(spec)
-        pending = (ops.ACT_NONE, 0.0)
+        pending = NONE
         last_idx = len(specs) - 1
+        return True
 
     for m in mods:
         if isinstance(m, blocks.AdaptiveInstanceNormalization):
             if not m.training:
                 return None
             continue
-        if isinstance(m, nn.LeakyReLU):
-            pending = (ops.ACT_LEAKY, float(m.negative_slope))
+        a = act_of(m)
+        if a is not None:
+            pending = a
             continue
-        if isinstance(m, blocks.Snake):
-            return None            # Snake epilogue not on the tensor-core path yet
         if isinstance(m, (cc.Conv1d, cc.ConvTranspose1d)):
-            add_conv(m)
+            if not add_conv(m):
+                return None
             continue
         if isinstance(m, blocks.Residual):
             unit = m.aligned.branches[0]
@@ -146,15 +162,20 @@ def plan_sequential(mods: List[nn.Module]) -> Optional[List[LayerSpec]]:
             if src < 0:
                 return None
             a0, c3, a1, c1 = list(unit.net)
-            for a in (a0, a1):
-                if not isinstance(a, nn.LeakyReLU):
-                    return None
-            pending = (ops.ACT_LEAKY, float(a0.negative_slope))
-            add_conv(c3)
+            acts = [act_of(a0), act_of(a1)]
+            if acts[0] is None or acts[1] is None or acts[0][0] != acts[1][0]:
+                return None
+            pending = acts[0]
+            if not add_conv(c3):
+                return None
             c3_idx = last_idx
-            pending = (ops.ACT_LEAKY, float(a1.negative_slope))
-            add_conv(c1, res_src=src)
-            specs[-1].res_opnd = c3_idx       # h_src = unleaky(operand of conv3): no fp32 stream needed
+            pending = acts[1]
+            if not add_conv(c1, res_src=src):
+                return None
+            if acts[0][0] == ops.ACT_LEAKY:
+                specs[-1].res_opnd = c3_idx       # h_src = unleaky(operand of conv3): no fp32 stream needed
+            else:
+                specs[-1].res_raw = c3_idx        # Snake is not invertible: the raw bf16 input of conv3 is the skip
             continue
         return None
     if pending[0] != ops.ACT_NONE or not specs:
@@ -431,6 +452,14 @@ class TcChainFn(torch.autograd.Function):
                 raise _lib.RaveB200Error("bf16x3: discriminator chains are not run in the split-operand mode")
             need_dgrad = False
         AW = 2 if x3 else 1                    # operand row width multiplier
+        # Snake layers (v3): their alpha parameters follow the 3n (v, g, bias) entries of `flat`
+        alpha_idx: Dict[int, int] = {}
+        for i, s in enumerate(specs):
+            if s.pre_act == ops.ACT_SNAKE:
+                alpha_idx[i] = 3 * n + len(alpha_idx)
+        if alpha_idx and (x3 or fm):
+            raise _lib.RaveB200Error("Snake chains run in the plain bf16 mode only (no split operands, no fused fm)")
+        hraw: Dict[int, torch.Tensor] = {}     # raw (pre-Snake) bf16 input stream of layer i
         c1 = x_in.dim() == 2
         period, pool = src if (c1 and src is not None) else (1, 1)
         B = x_in.shape[0] * period
@@ -501,6 +530,9 @@ class TcChainFn(torch.autograd.Function):
             want_act = nxt is not None
             act_code = nxt.pre_act if nxt is not None else ops.ACT_NONE
             act_slope = nxt.pre_slope if nxt is not None else 0.0
+            snake_next = act_code == ops.ACT_SNAKE
+            if snake_next:              # the epilogue writes h as bf16; ops.snake_cl_fwd makes the operand (below)
+                act_code = ops.ACT_NONE
             want_f32 = s.want_f32 and not (fm and nxt is not None)
             # rows allocated per batch: the consumer's 4-D tensor map needs a multiple of its stride
             s_next = nxt.stride if (nxt is not None and nxt.kind == "conv") else 1
@@ -509,10 +541,12 @@ class TcChainFn(torch.autograd.Function):
             bias_p = bias
             if bias is not None and s.cout_pad:
                 bias_p = nn.functional.pad(bias.detach(), (0, s.cout_pad))
-            res = res_act = None
+            res = res_act = res_b16 = None
             res_slope = 0.2
             if s.res_opnd is not None:
                 res_act, res_slope = acts[s.res_opnd], specs[s.res_opnd].pre_slope
+            elif s.res_raw is not None:
+                res_b16 = hraw[s.res_raw]
             elif s.res_src is not None:
                 res = f32[s.res_src]
             out_f32 = torch.empty(B, pitch, cout_p, dtype=torch.float32, device=dev) if want_f32 else None
@@ -577,7 +611,7 @@ class TcChainFn(torch.autograd.Function):
             elif s.kind == "conv":
                 ops.conv1d_tc(a, pw.fwd, bias_p, res, s.stride, s.dil, s.pad, act_code, act_slope,
                               want_f32=False, want_act=False, out_f32=out_f32, out_act=out_act, Lout=Lout,
-                              Lin=Lin, out_rows=pitch, res_act=res_act, res_slope=res_slope, x3=x3)
+                              Lin=Lin, out_rows=pitch, res_act=res_act, res_slope=res_slope, x3=x3, res_bf16=res_b16)
             else:
                 # transposed conv: the `stride` output phases side by side in one stride-1 conv (output row q =
                 # positions q*stride .. q*stride + stride-1: the same bytes as the [B][pitch][Cout] tensor)
@@ -595,6 +629,9 @@ class TcChainFn(torch.autograd.Function):
                     for t in (out_f32, out_act):
                         if t is not None:
                             t[:, Lout:].zero_()
+            if snake_next:
+                hraw[i + 1] = out_act
+                out_act = ops.snake_cl_fwd(out_act, flat[alpha_idx[i + 1]])
             if fm and nxt is not None:
                 if act_code != ops.ACT_LEAKY or s.cout_pad:
                     raise _lib.RaveB200Error("feature-matching mode needs LeakyReLU between the layers")
@@ -612,6 +649,8 @@ class TcChainFn(torch.autograd.Function):
                 ops.score_stats(outputs[-1], score_stats, lens[-1])
                 ctx.score_f32 = outputs[-1]
         ctx.specs = specs
+        ctx.hraw = hraw
+        ctx.alpha_idx = alpha_idx
         ctx.acts = acts
         ctx.prepared = prepared
         ctx.lens = lens
@@ -748,6 +787,8 @@ class TcChainFn(torch.autograd.Function):
             if e is not None:
                 add = e if add is None else (add + e)
             dact = a_in if s.pre_act == ops.ACT_LEAKY else None
+            snake_here = s.pre_act == ops.ACT_SNAKE
+            add_conv = None if snake_here else add       # Snake: the skip / external gradient joins after dSnake
             fm_partner = a_full[:Bh] if (fo and fm_d is not None) else None
             in_pitch = a_in.shape[1]
             if use_c1:                  # P[r][l][k] = <g[r][l][:], w[:][k]> on the tensor cores, then a gather
@@ -775,7 +816,7 @@ class TcChainFn(torch.autograd.Function):
                     padp = (s.K - 1) * s.dil - s.pad[0]
                     ops.conv1d_tc(g, pw.dgrad, None, None, 1, s.dil, (padp, 0), ops.ACT_NONE, s.pre_slope,
                                   want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout,
-                                  out_rows=in_pitch, res_bf16=add, dact_src=dact, fm_d=fm_d,
+                                  out_rows=in_pitch, res_bf16=add_conv, dact_src=dact, fm_d=fm_d,
                                   fm_partner=fm_partner)
                 else:
                     # strided conv: the `stride` input phases side by side in one stride-1 conv over g (row q of the
@@ -790,14 +831,19 @@ class TcChainFn(torch.autograd.Function):
                         return t.view(B, rows_q, wide) if t is not None else None
                     ops.conv1d_tc(g, pw.dgrad_fused, None, None, 1, 1, (pw.fused_pad, 0), ops.ACT_NONE, s.pre_slope,
                                   want_f32=False, want_act=False, out_act=v4(gp), out_rows=rows_q, Lout=rows_q,
-                                  Lin=Lout, res_bf16=v4(add), dact_src=v4(dact), fm_d=fm_d,
+                                  Lin=Lout, res_bf16=v4(add_conv), dact_src=v4(dact), fm_d=fm_d,
                                   fm_partner=v4(fm_partner))
                     if in_pitch > Lin:
                         gp[:, Lin:].zero_()
             else:
                 ops.conv1d_tc(g, pw.dgrad, None, None, s.stride, 1, (s.pad[0], 0), ops.ACT_NONE, s.pre_slope,
                               want_f32=False, want_act=False, out_act=gp, Lout=Lin, Lin=Lout, out_rows=in_pitch,
-                              res_bf16=add, dact_src=dact, fm_d=fm_d, fm_partner=fm_partner)
+                              res_bf16=add_conv, dact_src=dact, fm_d=fm_d, fm_partner=fm_partner)
+            if snake_here:
+                al = flat[ctx.alpha_idx[i]]
+                gp, dal = ops.snake_cl_bwd(gp, ctx.hraw[i], al, add, want_dalpha=bool(al.requires_grad))
+                if dal is not None:
+                    grads[ctx.alpha_idx[i]] = dal.reshape(al.shape)
             g_cur = gp
             if i == 0:
                 gx = gp
@@ -819,6 +865,7 @@ def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int]
     for s in specs:
         v, g, b = _layer_params(s)
         flat += [v, g, b]
+    flat += [s.pre_mod.alpha for s in specs if s.pre_act == ops.ACT_SNAKE]      # after the 3n weight entries
     if L0 is None:
         L0 = x_cl_bf16.shape[1]
     return TcChainFn.apply(x_cl_bf16, specs, L0, fm, src, fake_grad_only, x3, *flat)

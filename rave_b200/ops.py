@@ -445,6 +445,30 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     return out_f32, out_act
 
 
+def snake_cl_fwd(h_cl, alpha):
+    """Channel-last Snake on an engine stream: h_cl [B, pitch, C] (ACT dtype) -> a = h + sin^2(alpha h) / (alpha + 1e-9)."""
+    h_cl = h_cl.contiguous()
+    C = h_cl.shape[-1]
+    a = torch.empty_like(h_cl)
+    al = _f32c(alpha.detach().reshape(-1))
+    call("rave_snake_cl_fwd", ptr(h_cl), ptr(al), ptr(a), h_cl.numel() // C, C, stream_ptr())
+    return a
+
+
+def snake_cl_bwd(ga_cl, h_cl, alpha, add=None, want_dalpha=True):
+    """g_h = g_a * dsnake/dh (+ add), dalpha [C] fp32 = sum over rows of g_a * dsnake/dalpha (None if not wanted)."""
+    ga_cl, h_cl = ga_cl.contiguous(), h_cl.contiguous()
+    C = h_cl.shape[-1]
+    gh = torch.empty_like(ga_cl)
+    al = _f32c(alpha.detach().reshape(-1))
+    dal = torch.zeros(C, dtype=torch.float32, device=h_cl.device) if want_dalpha else None
+    if add is not None:
+        add = add.contiguous()
+    call("rave_snake_cl_bwd", ptr(ga_cl), ptr(h_cl), ptr(al), ptr(add), ptr(gh), ptr(dal), h_cl.numel() // C, C,
+         stream_ptr())
+    return gh, dal
+
+
 def dilated_unit_tc_supported(C, L):
     return bool(_lib.load().rave_dilated_unit_tc_supported(C, L))
 

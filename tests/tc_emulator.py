@@ -388,10 +388,38 @@ def weight_norm_bwd_multi(items):
     return out
 
 
+def snake_cl_fwd(h_cl, alpha):
+    al = alpha.detach().reshape(-1).float()
+    x = h_cl.float()
+    return _bf16(x + torch.sin(al * x) ** 2 / (al + 1e-9))
+
+
+def snake_cl_bwd(ga_cl, h_cl, alpha, add=None, want_dalpha=True):
+    al = alpha.detach().reshape(-1).float()
+    ae = al + 1e-9
+    x, g = h_cl.float(), ga_cl.float()
+    s2 = torch.sin(2 * al * x)
+    gh = g * (1 + al * s2 / ae)
+    if add is not None:
+        gh = gh + add.float()
+    dal = (g * (x * s2 / ae - torch.sin(al * x) ** 2 / (ae * ae))).reshape(-1, x.shape[-1]).sum(0) if want_dalpha else None
+    return _bf16(gh), dal
+
+
+def activation(x, act, slope=0.2, alpha=None):
+    """ops.activation (fp32 elementwise kernel with its own autograd): plain torch here."""
+    if act == 1:
+        return F.leaky_relu(x, slope)
+    if act == 2:
+        al = alpha.reshape(1, -1, *([1] * (x.dim() - 2)))
+        return x + torch.sin(al * x) ** 2 / (al + 1e-9)
+    return x
+
+
 def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
                  "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1", "weight_prep_tc_multi",
                  "weight_norm_bwd_multi", "score_stats", "score_grad", "ncl_to_cl_x3", "dilated_unit_tc",
-                 "dilated_unit_tc_supported"):
+                 "dilated_unit_tc_supported", "snake_cl_fwd", "snake_cl_bwd", "activation"):
         monkeypatch.setattr(ops, name, globals()[name])

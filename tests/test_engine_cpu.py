@@ -46,20 +46,26 @@ def test_phase_taps_cover_every_tap_once():
         assert sorted(seen) == list(range(K))
 
 
-@pytest.mark.parametrize("ratios", [[4, 4, 4, 2], [4, 2, 2, 2]])
-def test_encoder_generator_chain_vs_oracle(emu, ratios):
+@pytest.mark.parametrize("name,ratios", [("v2", [4, 4, 4, 2]), ("v2", [4, 2, 2, 2]), ("v3", [4, 4, 4, 2])])
+def test_encoder_generator_chain_vs_oracle(emu, name, ratios):
+    """v3 = Snake activations (channel-last Snake kernels between the convs, alpha gradients, raw-stream skips) + AdaIN
+    (identity in training)."""
     from rave_b200 import configs, engine
     torch.manual_seed(1)
-    _, enc, dec = configs.make_autoencoder("v2", capacity=16, latent_size=16, ratios=ratios)
+    _, enc, dec = configs.make_autoencoder(name, capacity=16, latent_size=16, ratios=ratios)
+    enc.train()
+    dec.train()
     sd = {"encoder." + k: v.detach().clone() for k, v in enc.state_dict().items()}
     sd.update({"decoder." + k: v.detach().clone() for k, v in dec.state_dict().items()})
-    cfg = O.ArchConfig(capacity=16, latent_size=16, ratios=ratios)
+    cfg = O.ArchConfig(capacity=16, latent_size=16, ratios=ratios, activation="snake" if name == "v3" else "leaky",
+                       adain=name == "v3")
+    trainable = {"encoder." + k for k, _ in enc.named_parameters()} | {"decoder." + k for k, _ in dec.named_parameters()}
     B, L = 2, 512
     x_mb = torch.randn(B, 16, L)
     # ---------------- encoder
     specs = enc.encoder.net._tc_plan()
     assert specs is not None
-    po = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    po = {k: v.clone().requires_grad_(k in trainable) for k, v in sd.items()}
     xo = x_mb.clone().requires_grad_(True)
     z_o = O.encoder_v2(xo, po, "encoder.encoder.", cfg)
     xe = x_mb.clone().requires_grad_(True)
@@ -292,3 +298,39 @@ def test_fused_units_are_planned_and_match_the_two_launch_form(emu, monkeypatch)
             assert torch.equal(a, b)
     else:
         assert outs[True][2] == 0               # fp32 operand emulation: the fused kernel is a bf16 kernel
+
+
+def test_descript_mpd_chain_vs_oracle(emu):
+    """v3 discriminator, MPD half: the whole period net as one engine chain (stride-3 k5 convs, slope 0.1, features =
+    activation of each conv's output, Cin = 1 first layer reading the reflect-padded folded signal) against
+    O.descript_mpd, features and gradients."""
+    from rave_b200.descript_discriminator import MPD
+    from rave_b200 import engine
+    torch.manual_seed(4)
+    period = 3
+    mpd = MPD(period)
+    # small channel counts keep the CPU test quick; same code path as the 1024-channel nets
+    sd = {k: v.detach().clone() for k, v in mpd.state_dict().items()}
+    x = (0.5 * torch.randn(2, 1, 2000)).clamp(-1, 1)
+    po = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    want = O.descript_mpd(xo, po, "", period)
+    specs = mpd._tc_specs()
+    assert specs is not None
+    xe = x.clone().requires_grad_(True)
+    xp = mpd.pad_to_period(xe)
+    got = mpd._forward_tc(xp.reshape(xp.shape[0], 1, -1, period), specs)
+    assert len(got) == len(want) == 6
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and rel_l2(a, b) < tol(emu, 1e-5, 3e-2), (a.shape, rel_l2(a, b))
+    probes = [torch.randn_like(b) for b in want]
+    names = sorted(po)
+    g_o = torch.autograd.grad(sum((b * p).sum() for b, p in zip(want, probes)), [xo] + [po[k] for k in names])
+    pg = dict(mpd.named_parameters())
+    g_e = torch.autograd.grad(sum((a * p).sum() for a, p in zip(got, probes)), [xe] + [pg[k] for k in names])
+    assert rel_l2(g_e[0], g_o[0]) < tol(emu, 2e-5, 0.15)
+    for k, a, b in zip(names, g_e[1:], g_o[1:]):
+        assert a.shape == b.shape
+        if emu == "exact_fp32" or a.numel() >= 64:       # (the 1-element weight_g of conv_post is noise in bf16)
+            assert rel_l2(a, b) < tol(emu, 5e-5, 0.2), (k, rel_l2(a, b))
+    assert cos(torch.cat([a.reshape(-1) for a in g_e[1:]]), torch.cat([b.reshape(-1) for b in g_o[1:]])) > 0.99

@@ -80,3 +80,42 @@ def test_descript_discriminator_full_vs_oracle():
     fm, ld, la = O.gan_losses([[f.cpu() for f in s] for s in got], 1, True)
     fm_o, ld_o, la_o = O.gan_losses(want, 1, True)
     assert rel_l2(fm, fm_o) < 1e-4 and rel_l2(ld, ld_o) < 1e-4
+
+
+def test_descript_mpd_bf16_engine_vs_oracle():
+    """Descript MPD (1024-channel (5,1) convs: 77 % of the v3 discriminator FLOPs) as ONE tcgen05 chain in bf16 mode
+    against the fp32 oracle: features within the bf16-mode tolerance, gradient direction of every large tensor."""
+    import rave_b200
+    from rave_b200.descript_discriminator import MPD
+    torch.manual_seed(5)
+    period = 5
+    mpd = MPD(period)
+    sd = {k: v.detach().clone() for k, v in mpd.state_dict().items()}
+    x = (0.5 * torch.randn(2, 1, 12000 + 3)).clamp(-1, 1)
+    po = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    want = O.descript_mpd(xo, po, "", period)
+    probes = [torch.randn_like(b) for b in want]
+    names = sorted(po)
+    g_o = torch.autograd.grad(sum((b * p).sum() for b, p in zip(want, probes)), [xo] + [po[k] for k in names])
+    mpd.cuda()
+    rave_b200.set_precision("bf16")
+    try:
+        assert mpd._tc_specs() is not None
+        xg = x.cuda().requires_grad_(True)
+        got = mpd(xg)
+        assert len(got) == 6
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and rel_l2(a, b) < 3e-2, (a.shape, rel_l2(a, b))
+        pg = dict(mpd.named_parameters())
+        g = torch.autograd.grad(sum((a * p.cuda()).sum() for a, p in zip(got, probes)), [xg] + [pg[k] for k in names])
+    finally:
+        rave_b200.set_precision("fp32")
+
+    def cos(a, b):
+        a, b = a.detach().double().cpu().reshape(-1), b.detach().double().reshape(-1)
+        return float(a @ b / (a.norm() * b.norm()).clamp_min(1e-30))
+    assert cos(g[0], g_o[0]) > 0.98, cos(g[0], g_o[0])
+    for k, a, b in zip(names, g[1:], g_o[1:]):
+        if a.numel() >= 64:
+            assert cos(a, b) > 0.97, (k, cos(a, b))

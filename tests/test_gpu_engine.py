@@ -30,26 +30,31 @@ def bf16_mode():
     rave_b200.set_precision("fp32")
 
 
-@pytest.mark.parametrize("ratios", [[4, 4, 4, 2], [4, 2, 2, 2]])
-def test_autoencoder_bf16_vs_oracle(ratios):
+@pytest.mark.parametrize("name,ratios", [("v2", [4, 4, 4, 2]), ("v2", [4, 2, 2, 2]), ("v3", [4, 4, 4, 2])])
+def test_autoencoder_bf16_vs_oracle(name, ratios):
+    """v3: Snake + AdaIN chains on the tcgen05 kernels (rave_snake_cl_fwd / _bwd between the convs)."""
     from rave_b200 import configs
     from rave_b200.model import _pqmf_decode, _pqmf_encode
     torch.manual_seed(3)
-    pq, enc, dec = configs.make_autoencoder("v2", capacity=16, latent_size=16, ratios=ratios)
+    pq, enc, dec = configs.make_autoencoder(name, capacity=16, latent_size=16, ratios=ratios)
+    enc.train()
+    dec.train()
     assert enc.encoder.net._tc_plan() is not None and dec.net._tc_plan() is not None
     holder = nn.Module()
     holder.pqmf, holder.encoder, holder.decoder = pq, enc, dec
     sd = {k: v.detach().clone() for k, v in holder.state_dict().items()}
     T = 16384
     x = (0.5 * torch.randn(2, 1, T)).clamp(-1, 1)
-    cfg = O.ArchConfig(capacity=16, latent_size=16, ratios=ratios)
+    cfg = O.ArchConfig(capacity=16, latent_size=16, ratios=ratios, activation="snake" if name == "v3" else "leaky",
+                       adain=name == "v3")
+    trainable = {k for k, _ in holder.named_parameters()}
     Lz = T // 16
     for r in ratios:
         Lz //= r
     eps = torch.randn(2, 16, Lz)
     probe = torch.randn(2, 1, T)
     # oracle forward/backward (fp32 CPU)
-    params_o = {k: v.clone().requires_grad_(v.is_floating_point() and not k.startswith("pqmf")) for k, v in sd.items()}
+    params_o = {k: v.clone().requires_grad_(k in trainable and not k.startswith("pqmf")) for k, v in sd.items()}
     xo = x.clone().requires_grad_(True)
     taps = {}
     y_o = O.rave_forward(xo, params_o, cfg, eps, taps)
