@@ -119,3 +119,43 @@ def test_descript_mpd_bf16_engine_vs_oracle():
     for k, a, b in zip(names, g[1:], g_o[1:]):
         if a.numel() >= 64:
             assert cos(a, b) > 0.97, (k, cos(a, b))
+
+
+def test_descript_mrd_bf16_engine_vs_oracle():
+    """MRD in bf16 mode: every (kt, kf) Conv2d as a one-layer tcgen05 chain (conv along frequency, time taps folded into
+    channels) against the fp32 oracle: features within the bf16-mode tolerance, gradient direction."""
+    import rave_b200
+    from rave_b200.descript_discriminator import MRD
+    torch.manual_seed(6)
+    mrd = MRD(512)
+    sd = {k: v.detach().clone() for k, v in mrd.state_dict().items()}
+    x = torch.randn(2, 1, 6000)
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and "window" not in k) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    want = O.descript_mrd(xo, po, "", 512)
+    probes = [torch.randn_like(b) for b in want]
+    names = sorted(k for k, v in po.items() if v.requires_grad)
+    g_o = torch.autograd.grad(sum((b * p).sum() for b, p in zip(want, probes)), [xo] + [po[k] for k in names])
+    mrd.cuda()
+    rave_b200.set_precision("bf16")
+    try:
+        xg = x.cuda().requires_grad_(True)
+        got = mrd(xg)
+        assert len(got) == len(want) == 26
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and rel_l2(a, b) < 3e-2, (a.shape, rel_l2(a, b))
+        pg = dict(mrd.named_parameters())
+        g = torch.autograd.grad(sum((a * p.cuda()).sum() for a, p in zip(got, probes)), [xg] + [pg[k] for k in names])
+    finally:
+        rave_b200.set_precision("fp32")
+
+    def cos(a, b):
+        a, b = a.detach().double().cpu().reshape(-1), b.detach().double().reshape(-1)
+        return float(a @ b / (a.norm() * b.norm()).clamp_min(1e-30))
+    assert cos(g[0], g_o[0]) > 0.98, cos(g[0], g_o[0])
+    ga = torch.cat([a.detach().cpu().reshape(-1) for a in g[1:]])
+    gb = torch.cat([b.reshape(-1) for b in g_o[1:]])
+    assert cos(ga, gb) > 0.99, cos(ga, gb)
+    for k, a, b in zip(names, g[1:], g_o[1:]):
+        if a.numel() >= 64:
+            assert cos(a, b) > 0.95, (k, cos(a, b))
