@@ -48,6 +48,8 @@ def parse():
                     help="skip `stock_cudnn_tf32`: the SAME step arithmetic through stock torch/cuDNN (TF32, as "
                          "scripts/train.py:135-136 configures the reference) on this GPU")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--quick", action="store_true", help="timed region only (parameter sweeps): no roofline / forward / "
+                                                         "baseline sections")
     return ap.parse_args()
 
 
@@ -621,7 +623,7 @@ def run_ours(args):
     if rank == 0:
         roof = step_roof = fwd = stock = cpu = None
         try:
-            if prec == "bf16":
+            if prec == "bf16" and not args.quick:
                 prof = profile_step(torch, model, x_dev, pk)
                 roof = dominant_launch_roofline(torch, prof, pk)
                 cyc_roof = (3 * prof["G"]["roofline_ms"] + prof["D"]["roofline_ms"]) / 4
@@ -636,19 +638,19 @@ def run_ours(args):
                                       "`frac_alone` by the same launches each timed alone")
         except Exception as e:
             roof = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
-        if args.config in ("v2", "v2_small"):
+        if args.config in ("v2", "v2_small") and not args.quick:
             try:
                 fwd = forward_roofline(torch, model, x_dev, pk)
             except Exception as e:
                 fwd = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
-        if not args.no_cudnn_baseline and world == 1 and args.config in ("v2", "v2_small"):
+        if not args.no_cudnn_baseline and not args.quick and world == 1 and args.config in ("v2", "v2_small"):
             del model, trainer
             torch.cuda.empty_cache()
             try:
                 stock = stock_cudnn_step(torch, args, B)
             except Exception as e:
                 stock = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
-        if not args.no_cpu_baseline and world == 1 and args.config in ("v2", "v2_small"):
+        if not args.no_cpu_baseline and not args.quick and world == 1 and args.config in ("v2", "v2_small"):
             cpu = cpu_reference_run(args, 2, 1, args.cpu_seconds)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {

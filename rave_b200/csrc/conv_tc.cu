@@ -999,7 +999,12 @@ static int pick_block_n2(int Cout, long m_tiles, int kblocks = 0) {
       // accumulator hand-over chain (commit -> epilogue wake-up -> TMEM reads -> release -> MMA wake-up, ~5000 clk
       // measured on the K = 1 layers): one tile per chain latency / accumulator stages
       const int acc = (512 / c) > 4 ? 4 : (512 / c);
-      const double chain = 5000.0 / acc;
+      static double chain_clk = -1.0;
+      if (chain_clk < 0) {
+        const char *e = getenv("RAVE_TC_CHAIN");
+        chain_clk = (e && atof(e) > 0) ? atof(e) : 5000.0;
+      }
+      const double chain = chain_clk / acc;
       if (chain > tile) tile = chain;
     }
     const double cost = (double)waves * tile;
