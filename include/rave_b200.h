@@ -198,6 +198,11 @@ int rave_conv1d_tc_fwd_x3(const void *xa_bf16, const void *wt_bf16, const float 
  * dbias [Cm] fp32, pre-zeroed, or NULL: += sum_{b,l} P[b][l][m] (the conv bias gradient when P = dy), reduced by the
  * tap-0 CTAs from the tiles they stream anyway (fp32 atomics across row slices). */
 int rave_conv1d_tc_wgrad_splits(int B, int Cm, int Lp, int Cn, int K);
+/* L1 feature matching on fp32 features (core.mean_difference, rave/core.py:236-252): stats[0] += sum|t - v|,
+ * stats[1] += sum|t| (stats zeroed by the caller); gradient of d[0] * stats[0] + d[1] * stats[1]: gt = d0 sgn(t - v) +
+ * d1 sgn(t), gv = -d0 sgn(t - v) (either may be null). */
+int rave_l1_stats_f32(const float *t, const float *v, float *stats, long n, void *stream);
+int rave_l1_grad_f32(const float *t, const float *v, const float *d, float *gt, float *gv, long n, void *stream);
 /* Snake (rave/blocks.py:852-860) on the engine's channel-last bf16 streams [rows][C] (v3 chains on the tcgen05 kernels):
  * a = h + sin^2(alpha h) / (alpha + 1e-9);  backward: gh = ga * da/dh + add (add may be null), dalpha[c] += sum_rows
  * ga * da/dalpha (dalpha zeroed by the caller). */

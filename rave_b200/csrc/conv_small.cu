@@ -669,3 +669,91 @@ extern "C" int rave_gather_c1(const float *P, float *dsrc, int R, int src_pitch,
   RAVE_CHECK_LAUNCH("gather_c1");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// L1 feature-matching statistics of two fp32 tensors (core.mean_difference, norm = L1: rave/core.py:236-252, called
+// once per discriminator feature at rave/model.py:356-361): stats[0] += sum |t - v|, stats[1] += sum |t| in ONE pass
+// (the torch form is sub, abs, mean, abs, mean, div + their backward: ~16 launches per feature, 108 features in a v3
+// step), and the gradient of d0 * stats[0] + d1 * stats[1] in one pass.
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+__global__ void __launch_bounds__(256)
+l1_stats_f32_kernel(const float *__restrict__ t, const float *__restrict__ v, float *__restrict__ stats, long n,
+                    int vec) {
+  __shared__ float red0[8], red1[8];
+  float s0 = 0.f, s1 = 0.f;
+  if (!vec) {           // operands not 16-byte aligned (odd-sized slices): scalar pass
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+      s0 += fabsf(t[i] - v[i]);
+      s1 += fabsf(t[i]);
+    }
+    n = 0;
+  }
+  const long n4 = n >> 2;
+  const float4 *t4 = reinterpret_cast<const float4 *>(t), *v4 = reinterpret_cast<const float4 *>(v);
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n4; i += (long)gridDim.x * 256) {
+    const float4 a = __ldg(t4 + i), b = __ldg(v4 + i);
+    s0 += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+    s1 += fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(a.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long i = (n4 << 2) + threadIdx.x;
+    s0 += fabsf(t[i] - v[i]);
+    s1 += fabsf(t[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red0[wid] = s0; red1[wid] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float u0 = 0.f, u1 = 0.f;
+    for (int i = 0; i < 8; ++i) { u0 += red0[i]; u1 += red1[i]; }
+    atomicAdd(stats, u0);
+    atomicAdd(stats + 1, u1);
+  }
+}
+
+__device__ __forceinline__ float sgnf(float x) { return (x > 0.f ? 1.f : 0.f) - (x < 0.f ? 1.f : 0.f); }
+
+// gt = d0 sgn(t - v) + d1 sgn(t) (or null), gv = -d0 sgn(t - v) (or null)
+__global__ void __launch_bounds__(256)
+l1_grad_f32_kernel(const float *__restrict__ t, const float *__restrict__ v, const float *__restrict__ d,
+                   float *__restrict__ gt, float *__restrict__ gv, long n) {
+  const float d0 = d[0], d1 = d[1];
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const float a = t[i], b = v[i];
+    const float s = d0 * sgnf(a - b);
+    if (gt) gt[i] = s + d1 * sgnf(a);
+    if (gv) gv[i] = -s;
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_l1_stats_f32(const float *t, const float *v, float *stats, long n, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(t && v && stats && n > 0, "l1_stats: bad argument");
+  const int vec = ((((uintptr_t)t | (uintptr_t)v) & 15) == 0) ? 1 : 0;
+  long blocks = ((vec ? (n >> 2) : n) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  l1_stats_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(t, v, stats, n, vec);
+  RAVE_CHECK_LAUNCH("l1_stats");
+  return 0;
+}
+
+extern "C" int rave_l1_grad_f32(const float *t, const float *v, const float *d, float *gt, float *gv, long n,
+                                void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(t && v && d && (gt || gv) && n > 0, "l1_grad: bad argument");
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  l1_grad_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(t, v, d, gt, gv, n);
+  RAVE_CHECK_LAUNCH("l1_grad");
+  return 0;
+}

@@ -445,6 +445,33 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     return out_f32, out_act
 
 
+class L1StatsFn(torch.autograd.Function):
+    """(sum |t - v|, sum |t|) of two fp32 CUDA tensors in one pass, gradient in one pass (rave_l1_stats_f32 / _grad)."""
+
+    @staticmethod
+    def forward(ctx, t, v):
+        t, v = _f32c(t), _f32c(v)
+        stats = torch.zeros(2, dtype=torch.float32, device=t.device)
+        call("rave_l1_stats_f32", ptr(t), ptr(v), ptr(stats), t.numel(), stream_ptr())
+        ctx.save_for_backward(t, v)
+        return stats
+
+    @staticmethod
+    def backward(ctx, d):
+        t, v = ctx.saved_tensors
+        d = _f32c(d)
+        gt = torch.empty_like(t) if ctx.needs_input_grad[0] else None
+        gv = torch.empty_like(v) if ctx.needs_input_grad[1] else None
+        if gt is None and gv is None:
+            return None, None
+        call("rave_l1_grad_f32", ptr(t), ptr(v), ptr(d), ptr(gt), ptr(gv), t.numel(), stream_ptr())
+        return gt, gv
+
+
+def l1_stats(t, v):
+    return L1StatsFn.apply(t, v)
+
+
 def snake_cl_fwd(h_cl, alpha):
     """Channel-last Snake on an engine stream: h_cl [B, pitch, C] (ACT dtype) -> a = h + sin^2(alpha h) / (alpha + 1e-9)."""
     h_cl = h_cl.contiguous()

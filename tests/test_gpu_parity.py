@@ -614,3 +614,26 @@ def test_v1_encoder_generator_match_reference_golden():
                 [(rel_l2(a, g["grads"]["decoder." + k]), "decoder." + k) for k, a in zip(nd, gd[1:])])
     print(f"v1 parameter gradients, worst rel-L2 {worst[0]:.2e} ({worst[1]})")
     assert worst[0] < 5e-4, worst
+
+
+def test_l1_feature_matching_stats_match_torch():
+    """core.mean_difference (norm L1, relative or not) on CUDA goes through rave_l1_stats_f32 / rave_l1_grad_f32: same
+    value and gradients as the torch arithmetic of rave/core.py:236-252, also on slices that are not 16-byte aligned."""
+    from rave_b200 import core
+    torch.manual_seed(11)
+    for shape, off in [((4, 32, 1000), 0), ((3, 7, 333), 1), ((2, 1, 5), 0)]:
+        base_t = torch.randn(shape[0] * shape[1] * shape[2] + off, device="cuda")
+        base_v = torch.randn_like(base_t)
+        for relative in (True, False):
+            t = base_t[off:].view(shape).clone().requires_grad_(True) if off == 0 else \
+                base_t[off:].view(shape).detach().requires_grad_(True)
+            v = base_v[off:].view(shape).detach().requires_grad_(True)
+            got = core.mean_difference(t, v, "L1", relative)
+            gt, gv = torch.autograd.grad(got, [t, v])
+            t2, v2 = t.detach().cpu().double().requires_grad_(True), v.detach().cpu().double().requires_grad_(True)
+            want = (t2 - v2).abs().mean()
+            if relative:
+                want = want / t2.abs().mean()
+            wt, wv = torch.autograd.grad(want, [t2, v2])
+            assert abs(float(got) - float(want)) <= 2e-6 * abs(float(want))
+            assert rel_l2(gt, wt) < 1e-5 and rel_l2(gv, wv) < 1e-5
