@@ -198,6 +198,13 @@ int rave_conv1d_tc_fwd_x3(const void *xa_bf16, const void *wt_bf16, const float 
  * dbias [Cm] fp32, pre-zeroed, or NULL: += sum_{b,l} P[b][l][m] (the conv bias gradient when P = dy), reduced by the
  * tap-0 CTAs from the tiles they stream anyway (fp32 atomics across row slices). */
 int rave_conv1d_tc_wgrad_splits(int B, int Cm, int Lp, int Cn, int K);
+/* Operand of a (kt, kf) Conv2d evaluated as a conv along frequency (Descript MRD, rave/descript_discriminator.py:118-184):
+ * x [B][C][T][F] fp32 -> out [(b,t)][Fp][Cp] bf16 with out[.][f][dt*C + c] = x[b][c][t + dt - pt][f] (zero elsewhere), and
+ * the adjoint gx [B][C][T][F] += (written once) from g [(b,t)][Fp][Cp]. */
+int rave_time_stack_cl(const float *x, void *out_bf16, int B, int C, int T, int F, int Fp, int Cp, int kt, int pt,
+                       void *stream);
+int rave_time_stack_cl_bwd(const void *g_bf16, float *gx, int B, int C, int T, int F, int Fp, int Cp, int kt, int pt,
+                           void *stream);
 /* L1 feature matching on fp32 features (core.mean_difference, rave/core.py:236-252): stats[0] += sum|t - v|,
  * stats[1] += sum|t| (stats zeroed by the caller); gradient of d[0] * stats[0] + d[1] * stats[1]: gt = d0 sgn(t - v) +
  * d1 sgn(t), gv = -d0 sgn(t - v) (either may be null). */

@@ -757,3 +757,82 @@ extern "C" int rave_l1_grad_f32(const float *t, const float *v, const float *d, 
   RAVE_CHECK_LAUNCH("l1_grad");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Operand of a (kt, kf) Conv2d run as a conv along frequency (descript_discriminator.DiscConv2d, MRD of
+// rave/descript_discriminator.py:118-184): x [B][C][T][F] fp32 -> channel-last bf16 rows
+//   out[(b, t)][f][dt * C + c] = x[b][c][t + dt - pt][f]      (zero outside 0 <= t + dt - pt < T, f >= F, channel >= kt C)
+// i.e. the kt time-shifted copies of the input channels side by side, and its adjoint.  One pass each instead of
+// pad + stack + permute + reshape + pad + cast + contiguous (and their autograd).
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+constexpr int TS_CP_MAX = 128;
+
+__global__ void __launch_bounds__(256)
+time_stack_cl_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, int C, int T, int F, int Fp, int Cp,
+                     int kt, int pt) {
+  __shared__ __nv_bfloat16 tile[32][TS_CP_MAX + 2];
+  const int f0 = blockIdx.x * 32, t = blockIdx.y, b = blockIdx.z;
+  const int fl = threadIdx.x & 31, cl = threadIdx.x >> 5;
+  const int f = f0 + fl;
+  for (int ch = cl; ch < Cp; ch += 8) {
+    float v = 0.f;
+    if (ch < kt * C && f < F) {
+      const int dt = ch / C, c = ch - dt * C;
+      const int ts = t + dt - pt;
+      if (ts >= 0 && ts < T) v = __ldg(x + (((size_t)b * C + c) * T + ts) * F + f);
+    }
+    tile[fl][ch] = __float2bfloat16(v);
+  }
+  __syncthreads();
+  const int rows = min(32, Fp - f0);
+  __nv_bfloat16 *dst = out + (((size_t)b * T + t) * Fp + f0) * Cp;      // the [rows][Cp] block is contiguous
+  for (int i = threadIdx.x; i < rows * Cp; i += 256) dst[i] = tile[i / Cp][i % Cp];
+}
+
+__global__ void __launch_bounds__(256)
+time_stack_cl_bwd_kernel(const __nv_bfloat16 *__restrict__ g, float *__restrict__ gx, int C, int T, int F, int Fp,
+                         int Cp, int kt, int pt) {
+  __shared__ float acc[32][TS_CP_MAX / 2 + 1];        // [f][c], C <= 64
+  const int f0 = blockIdx.x * 32, tp = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 32 * C; i += 256) acc[i / C][i % C] = 0.f;
+  __syncthreads();
+  for (int dt = 0; dt < kt; ++dt) {
+    const int t = tp + pt - dt;             // the output row whose slot dt read x[.., tp, ..]
+    if (t < 0 || t >= T) continue;
+    const __nv_bfloat16 *src = g + (((size_t)b * T + t) * Fp + f0) * Cp + dt * C;
+    for (int i = threadIdx.x; i < 32 * C; i += 256) {
+      const int fl = i / C, c = i - fl * C;
+      if (f0 + fl < F) acc[fl][c] += __bfloat162float(src[(size_t)fl * Cp + c]);
+    }
+  }
+  __syncthreads();
+  const int fl = threadIdx.x & 31, cl = threadIdx.x >> 5;
+  if (f0 + fl < F)
+    for (int c = cl; c < C; c += 8) gx[(((size_t)b * C + c) * T + tp) * F + f0 + fl] = acc[fl][c];
+}
+
+}  // namespace rave
+
+extern "C" int rave_time_stack_cl(const float *x, void *out_bf16, int B, int C, int T, int F, int Fp, int Cp, int kt,
+                                  int pt, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && out_bf16 && B > 0 && C > 0 && T > 0 && F > 0 && Fp >= F && kt >= 1 && Cp >= kt * C &&
+                     Cp <= TS_CP_MAX && C <= TS_CP_MAX / 2 && B <= 65535 && T <= 65535, "time_stack_cl: bad shape");
+  time_stack_cl_kernel<<<dim3(ceil_div(Fp, 32), T, B), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16 *)out_bf16, C, T, F, Fp, Cp, kt, pt);
+  RAVE_CHECK_LAUNCH("time_stack_cl");
+  return 0;
+}
+
+extern "C" int rave_time_stack_cl_bwd(const void *g_bf16, float *gx, int B, int C, int T, int F, int Fp, int Cp, int kt,
+                                      int pt, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(g_bf16 && gx && B > 0 && C > 0 && T > 0 && F > 0 && Fp >= F && kt >= 1 && Cp >= kt * C &&
+                     Cp <= TS_CP_MAX && C <= TS_CP_MAX / 2 && B <= 65535 && T <= 65535, "time_stack_cl_bwd: bad shape");
+  time_stack_cl_bwd_kernel<<<dim3(ceil_div(F, 32), T, B), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16 *)g_bf16, gx, C, T, F, Fp, Cp, kt, pt);
+  RAVE_CHECK_LAUNCH("time_stack_cl_bwd");
+  return 0;
+}

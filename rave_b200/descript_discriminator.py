@@ -44,16 +44,16 @@ class DiscConv2d(nn.Conv2d):
         B, C, T, Fq = x.shape
         kt, kf = self.kernel_size
         pt, pf = self.padding
+        if engine.precision() == "bf16" and x.is_cuda and engine.ACT_DTYPE == torch.bfloat16 and kt * C <= 112:
+            return self._forward_tc(x, B, C, T, Fq)
         xp = F.pad(x, (0, 0, pt, pt))
         xi = torch.stack([xp[:, :, dt:dt + T] for dt in range(kt)], 1)            # [B, kt, C, T, F]
-        if engine.precision() == "bf16" and x.is_cuda and engine.ACT_DTYPE == torch.bfloat16:
-            return self._forward_tc(xi, B, C, T, Fq)
         xi = xi.permute(0, 3, 1, 2, 4).reshape(B * T, kt * C, Fq)                 # rows (b, t), channels (dt, c)
         w = self.weight.permute(0, 2, 1, 3).reshape(self.out_channels, kt * C, kf)
         y = ops.conv1d(xi, w, self.bias, None, self.stride[1], 1, (pf, pf), ops.ACT_NONE, 0.0, None)
         return y.view(B, T, self.out_channels, y.shape[-1]).permute(0, 2, 1, 3)
 
-    def _forward_tc(self, xi, B, C, T, Fq):
+    def _forward_tc(self, x, B, C, T, Fq):
         """bf16 mode: the same conv along frequency as a one-layer chain of the tcgen05 engine (forward, dgrad and wgrad
         on the tensor cores; 23 % of the v3 discriminator FLOPs ran on the fp32 CUDA-core kernels: 176 ms of a 280 ms
         G-step).  The (dt, c) channel order is a permuted VIEW of the parameter, so the weight-norm backward of the chain
@@ -78,10 +78,9 @@ class DiscConv2d(nn.Conv2d):
         else:
             proxy.weight = self.weight.permute(0, 2, 1, 3).reshape(co, cin, kf)
         proxy.bias = self.bias
-        # rows (b, t), positions f, channels (dt, c): channel-last operand of the engine
-        x_cl = xi.permute(0, 3, 4, 1, 2).reshape(B * T, Fq, cin)
+        # rows (b, t), positions f, channels (dt, c): channel-last bf16 operand of the engine, in one library pass
         rpad = (-Fq) % spec.stride
-        x_cl = F.pad(x_cl, (0, spec.cin_pad, 0, rpad)).to(engine.ACT_DTYPE).contiguous()
+        x_cl = ops.time_stack_cl(x, kt, pt, cin + spec.cin_pad, Fq + rpad)
         (out,) = engine.run_chain(x_cl, [spec], Fq)
         Fo = engine.chain_lengths([spec], Fq)[0]
         return out[:, :Fo, :co].reshape(B, T, Fo, co).permute(0, 3, 1, 2)

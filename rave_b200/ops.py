@@ -445,6 +445,32 @@ def conv1d_tc(xa_cl, wt, bias=None, res_cl=None, stride=1, dil=1, pad=(0, 0), ac
     return out_f32, out_act
 
 
+class TimeStackFn(torch.autograd.Function):
+    """x [B, C, T, F] fp32 -> [(b t), Fp, Cp] bf16 rows holding the kt time-shifted copies of the channels side by side
+    (rave_time_stack_cl); backward = the adjoint gather."""
+
+    @staticmethod
+    def forward(ctx, x, kt, pt, Cp, Fp):
+        x = _f32c(x)
+        B, C, T, F_ = x.shape
+        out = torch.empty(B * T, Fp, Cp, dtype=torch.bfloat16, device=x.device)
+        call("rave_time_stack_cl", ptr(x), ptr(out), B, C, T, F_, Fp, Cp, kt, pt, stream_ptr())
+        ctx.cfg = (B, C, T, F_, Fp, Cp, kt, pt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, T, F_, Fp, Cp, kt, pt = ctx.cfg
+        g = g.contiguous()
+        gx = torch.empty(B, C, T, F_, dtype=torch.float32, device=g.device)
+        call("rave_time_stack_cl_bwd", ptr(g), ptr(gx), B, C, T, F_, Fp, Cp, kt, pt, stream_ptr())
+        return gx, None, None, None, None
+
+
+def time_stack_cl(x, kt, pt, Cp, Fp):
+    return TimeStackFn.apply(x, kt, pt, Cp, Fp)
+
+
 class L1StatsFn(torch.autograd.Function):
     """(sum |t - v|, sum |t|) of two fp32 CUDA tensors in one pass, gradient in one pass (rave_l1_stats_f32 / _grad)."""
 
