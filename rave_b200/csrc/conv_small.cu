@@ -768,17 +768,21 @@ extern "C" int rave_l1_grad_f32(const float *t, const float *v, const float *d, 
 namespace rave {
 
 constexpr int TS_CP_MAX = 128;
+constexpr int TS_PITCH = TS_CP_MAX + 8;      // bf16 elements per staged row (16-byte multiple)
 
+// block = one (b, t) row x 32 frequency positions: loads coalesced along f (x is [.., T, F]), the [32][Cp] output block
+// is contiguous in memory and leaves as 16-byte vectors
 __global__ void __launch_bounds__(256)
 time_stack_cl_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, int C, int T, int F, int Fp, int Cp,
                      int kt, int pt) {
-  __shared__ __nv_bfloat16 tile[32][TS_CP_MAX + 2];
+  __shared__ __align__(16) __nv_bfloat16 tile[32][TS_PITCH];
   const int f0 = blockIdx.x * 32, t = blockIdx.y, b = blockIdx.z;
   const int fl = threadIdx.x & 31, cl = threadIdx.x >> 5;
   const int f = f0 + fl;
+  const int nch = kt * C;
   for (int ch = cl; ch < Cp; ch += 8) {
     float v = 0.f;
-    if (ch < kt * C && f < F) {
+    if (ch < nch && f < F) {
       const int dt = ch / C, c = ch - dt * C;
       const int ts = t + dt - pt;
       if (ts >= 0 && ts < T) v = __ldg(x + (((size_t)b * C + c) * T + ts) * F + f);
@@ -787,30 +791,53 @@ time_stack_cl_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ ou
   }
   __syncthreads();
   const int rows = min(32, Fp - f0);
-  __nv_bfloat16 *dst = out + (((size_t)b * T + t) * Fp + f0) * Cp;      // the [rows][Cp] block is contiguous
-  for (int i = threadIdx.x; i < rows * Cp; i += 256) dst[i] = tile[i / Cp][i % Cp];
+  const int vpr = Cp >> 3;                                      // 16-byte vectors per row (Cp % 8 == 0)
+  uint4 *dst = reinterpret_cast<uint4 *>(out + (((size_t)b * T + t) * Fp + f0) * Cp);
+  for (int i = threadIdx.x; i < rows * vpr; i += 256) {
+    const int r = i / vpr, q = i - r * vpr;
+    dst[i] = *reinterpret_cast<const uint4 *>(&tile[r][q * 8]);
+  }
 }
 
+// adjoint: gx[b][c][tp][f] = sum_dt g[(b, tp + pt - dt)][f][dt * C + c]; the kt [32][Cp] blocks are staged through shared
+// memory as 16-byte vectors, the result leaves coalesced along f
 __global__ void __launch_bounds__(256)
 time_stack_cl_bwd_kernel(const __nv_bfloat16 *__restrict__ g, float *__restrict__ gx, int C, int T, int F, int Fp,
                          int Cp, int kt, int pt) {
-  __shared__ float acc[32][TS_CP_MAX / 2 + 1];        // [f][c], C <= 64
+  __shared__ __align__(16) __nv_bfloat16 tile[32][TS_PITCH];
   const int f0 = blockIdx.x * 32, tp = blockIdx.y, b = blockIdx.z;
-  for (int i = threadIdx.x; i < 32 * C; i += 256) acc[i / C][i % C] = 0.f;
-  __syncthreads();
+  const int fl = threadIdx.x & 31, cl = threadIdx.x >> 5;
+  const int rows = min(32, Fp - f0);
+  const int vpr = Cp >> 3;
+  float acc[TS_CP_MAX / 2 / 8];                                 // channels cl, cl + 8, ... of this thread's f
+#pragma unroll
+  for (int j = 0; j < TS_CP_MAX / 2 / 8; ++j) acc[j] = 0.f;
   for (int dt = 0; dt < kt; ++dt) {
     const int t = tp + pt - dt;             // the output row whose slot dt read x[.., tp, ..]
-    if (t < 0 || t >= T) continue;
-    const __nv_bfloat16 *src = g + (((size_t)b * T + t) * Fp + f0) * Cp + dt * C;
-    for (int i = threadIdx.x; i < 32 * C; i += 256) {
-      const int fl = i / C, c = i - fl * C;
-      if (f0 + fl < F) acc[fl][c] += __bfloat162float(src[(size_t)fl * Cp + c]);
+    if (t >= 0 && t < T) {                  // (uniform per block)
+      const uint4 *src = reinterpret_cast<const uint4 *>(g + (((size_t)b * T + t) * Fp + f0) * Cp);
+      for (int i = threadIdx.x; i < rows * vpr; i += 256) {
+        const int r = i / vpr, q = i - r * vpr;
+        *reinterpret_cast<uint4 *>(&tile[r][q * 8]) = src[i];
+      }
+      __syncthreads();
+      if (fl < rows) {
+#pragma unroll
+        for (int j = 0; j < TS_CP_MAX / 2 / 8; ++j) {
+          const int c = cl + 8 * j;
+          if (c < C) acc[j] += __bfloat162float(tile[fl][dt * C + c]);
+        }
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
-  const int fl = threadIdx.x & 31, cl = threadIdx.x >> 5;
-  if (f0 + fl < F)
-    for (int c = cl; c < C; c += 8) gx[(((size_t)b * C + c) * T + tp) * F + f0 + fl] = acc[fl][c];
+  if (f0 + fl < F) {
+#pragma unroll
+    for (int j = 0; j < TS_CP_MAX / 2 / 8; ++j) {
+      const int c = cl + 8 * j;
+      if (c < C) gx[(((size_t)b * C + c) * T + tp) * F + f0 + fl] = acc[j];
+    }
+  }
 }
 
 }  // namespace rave
@@ -819,7 +846,8 @@ extern "C" int rave_time_stack_cl(const float *x, void *out_bf16, int B, int C, 
                                   int pt, void *stream) {
   using namespace rave;
   RAVE_CHECK_ARG(x && out_bf16 && B > 0 && C > 0 && T > 0 && F > 0 && Fp >= F && kt >= 1 && Cp >= kt * C &&
-                     Cp <= TS_CP_MAX && C <= TS_CP_MAX / 2 && B <= 65535 && T <= 65535, "time_stack_cl: bad shape");
+                     Cp <= TS_CP_MAX && Cp % 8 == 0 && C <= TS_CP_MAX / 2 && B <= 65535 && T <= 65535 &&
+                     ((uintptr_t)out_bf16 & 15) == 0, "time_stack_cl: bad shape");
   time_stack_cl_kernel<<<dim3(ceil_div(Fp, 32), T, B), 256, 0, (cudaStream_t)stream>>>(
       x, (__nv_bfloat16 *)out_bf16, C, T, F, Fp, Cp, kt, pt);
   RAVE_CHECK_LAUNCH("time_stack_cl");
@@ -830,8 +858,9 @@ extern "C" int rave_time_stack_cl_bwd(const void *g_bf16, float *gx, int B, int 
                                       int pt, void *stream) {
   using namespace rave;
   RAVE_CHECK_ARG(g_bf16 && gx && B > 0 && C > 0 && T > 0 && F > 0 && Fp >= F && kt >= 1 && Cp >= kt * C &&
-                     Cp <= TS_CP_MAX && C <= TS_CP_MAX / 2 && B <= 65535 && T <= 65535, "time_stack_cl_bwd: bad shape");
-  time_stack_cl_bwd_kernel<<<dim3(ceil_div(F, 32), T, B), 256, 0, (cudaStream_t)stream>>>(
+                     Cp <= TS_CP_MAX && Cp % 8 == 0 && C <= TS_CP_MAX / 2 && B <= 65535 && T <= 65535 &&
+                     ((uintptr_t)g_bf16 & 15) == 0, "time_stack_cl_bwd: bad shape");
+  time_stack_cl_bwd_kernel<<<dim3(ceil_div(Fp, 32), T, B), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16 *)g_bf16, gx, C, T, F, Fp, Cp, kt, pt);
   RAVE_CHECK_LAUNCH("time_stack_cl_bwd");
   return 0;
