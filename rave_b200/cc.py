@@ -25,6 +25,7 @@ USE_BUFFER_CONV = False
 class _Config:
     conv_bias = False          # cc.Conv1d.bias / cc.ConvTranspose1d.bias
     padding_mode = "centered"  # cc.get_padding.mode
+    cached = False             # cc.use_cached_conv: modules constructed afterwards are streaming (ring-buffer) variants
 
 
 config = _Config()
@@ -44,10 +45,14 @@ def configure(conv_bias=None, padding_mode=None):
 
 
 def use_cached_conv(state: bool):
-    if state:
-        raise NotImplementedError(
-            "streaming (cached) convolutions are out of scope (SURVEY.md 8f.4); training uses the "
-            "non-cached mode (scripts/train.py never enables it)")
+    """cached_conv.use_cached_conv: modules constructed AFTER this call are the streaming variants (the
+    reference flips it in export / real-time scripts only, `scripts/export.py:436`): every conv keeps the last
+    `padding` input samples of each call in a ring buffer instead of zero-padding, so that consecutive calls on consecutive
+    chunks reproduce the offline (non-cached, causal-shifted) result, delayed by `cumulative_delay` samples.
+    [EXT: cached-conv 2.5.0 is not installable here; the arithmetic below follows its published design (left-only cached
+    padding, stride alignment delay, overlap-add cache of the transposed conv, delay lines in AlignBranches) and is pinned
+    by the property the reference's own tests check (tests/test_residual.py): streaming == offline up to the delay.]"""
+    config.cached = bool(state)
 
 
 def get_padding(kernel_size: int, stride: int = 1, dilation: int = 1, mode: str = None) -> Tuple[int, int]:
@@ -85,11 +90,22 @@ class Conv1d(nn.Conv1d):
             pad = (pad, pad)
         self._pad = tuple(pad)
         kwargs["padding"] = 0
-        kwargs.pop("cumulative_delay", None)
+        cd = kwargs.pop("cumulative_delay", 0) or 0
         if "bias" not in kwargs and len(args) < 8:
             kwargs["bias"] = config.conv_bias
         super().__init__(*args, **kwargs)
         self.cumulative_delay = 0
+        self._cached = bool(config.cached)
+        if self._cached:
+            # streaming variant: ALL the padding on the left, served from the previous call's tail; a strided conv first
+            # delays its input so that chunk boundaries stay aligned with the stride grid
+            r_pad = self._pad[1]
+            total = self._pad[0] + self._pad[1]
+            st = self.stride[0]
+            stride_delay = (st - ((r_pad + cd) % st)) % st
+            self.cumulative_delay = (r_pad + stride_delay + cd) // st
+            self.cache = CachedPadding1d(total)
+            self.downsampling_delay = CachedPadding1d(stride_delay, crop=True)
 
     def script_cache(self):
         pass
@@ -100,33 +116,48 @@ class Conv1d(nn.Conv1d):
             x = act(x)
             code = (ops.ACT_NONE, 0.0, None)
         alpha = code[2].reshape(-1) if code[2] is not None else None
+        if self._cached:
+            # (the fused activation is applied on the operand load, after the cache was prepended: pointwise, act(0) = 0)
+            x = self.cache(self.downsampling_delay(x))
+            w = self.weight
+            return ops.conv1d(x, w, self.bias, res, self.stride[0], self.dilation[0], (0, 0), code[0], code[1], alpha) \
+                if self.groups == 1 else self._grouped(x, res, (0, 0), code, alpha)
         if self.groups != 1:
-            # grouped conv (the v1 Encoder's last layer, rave/blocks.py:489-497: groups = n_out): one launch per group on
-            # its slice of the input / weight channels, same nn.Conv1d parameter layout [Cout, Cin / groups, K]
-            g = self.groups
-            cin, cout = self.in_channels // g, self.out_channels // g
-            outs = []
-            for i in range(g):
-                xi = x[:, i * cin:(i + 1) * cin].contiguous()
-                ai = alpha[i * cin:(i + 1) * cin].contiguous() if alpha is not None else None
-                bi = self.bias[i * cout:(i + 1) * cout] if self.bias is not None else None
-                ri = res[:, i * cout:(i + 1) * cout].contiguous() if res is not None else None
-                outs.append(ops.conv1d(xi, self.weight[i * cout:(i + 1) * cout], bi, ri, self.stride[0],
-                                       self.dilation[0], self._pad, code[0], code[1], ai))
-            return torch.cat(outs, 1)
+            return self._grouped(x, res, self._pad, code, alpha)
         return ops.conv1d(x, self.weight, self.bias, res, self.stride[0], self.dilation[0], self._pad,
                           code[0], code[1], alpha)
+
+    def _grouped(self, x, res, pad, code, alpha):
+        """grouped conv (the v1 Encoder's last layer, rave/blocks.py:489-497: groups = n_out): one launch per group on
+        its slice of the input / weight channels, same nn.Conv1d parameter layout [Cout, Cin / groups, K]"""
+        g = self.groups
+        cin, cout = self.in_channels // g, self.out_channels // g
+        outs = []
+        for i in range(g):
+            xi = x[:, i * cin:(i + 1) * cin].contiguous()
+            ai = alpha[i * cin:(i + 1) * cin].contiguous() if alpha is not None else None
+            bi = self.bias[i * cout:(i + 1) * cout] if self.bias is not None else None
+            ri = res[:, i * cout:(i + 1) * cout].contiguous() if res is not None else None
+            outs.append(ops.conv1d(xi, self.weight[i * cout:(i + 1) * cout], bi, ri, self.stride[0],
+                                   self.dilation[0], pad, code[0], code[1], ai))
+        return torch.cat(outs, 1)
 
 
 class ConvTranspose1d(nn.ConvTranspose1d):
     def __init__(self, *args, **kwargs):
-        kwargs.pop("cumulative_delay", None)
+        cd = kwargs.pop("cumulative_delay", 0) or 0
         if "bias" not in kwargs and len(args) < 8:
             kwargs["bias"] = config.conv_bias
         super().__init__(*args, **kwargs)
         if self.groups != 1 or self.output_padding[0] != 0 or self.dilation[0] != 1:
             raise NotImplementedError("only plain ConvTranspose1d is on the hot path")
         self.cumulative_delay = 0
+        self._cached = bool(config.cached)
+        if self._cached:
+            # streaming variant: the un-cropped transposed conv of a chunk overlaps the next chunk's by K - stride samples
+            # (overlap-add cache); the symmetric `padding` crop becomes a delay
+            self.cumulative_delay = self.padding[0] + cd * self.stride[0]
+            self.register_buffer("_tail", torch.zeros(0), persistent=False)
 
     def script_cache(self):
         pass
@@ -137,6 +168,19 @@ class ConvTranspose1d(nn.ConvTranspose1d):
             x = act(x)
             code = (ops.ACT_NONE, 0.0, None)
         alpha = code[2].reshape(-1) if code[2] is not None else None
+        if self._cached:
+            y = ops.conv_transpose1d(x, self.weight, None, self.stride[0], 0, code[0], code[1], alpha)
+            ov = self.kernel_size[0] - self.stride[0]
+            if ov > 0:
+                B = y.shape[0]
+                if self._tail.numel() == 0 or self._tail.shape[0] < B or self._tail.shape[1:] != (y.shape[1], ov):
+                    self._tail = torch.zeros(max(B, 1), y.shape[1], ov, dtype=y.dtype, device=y.device)
+                head = y[..., :ov] + self._tail[:B]
+                self._tail[:B] = y[..., -ov:].detach()
+                y = torch.cat([head, y[..., ov:-ov]], -1)
+            if self.bias is not None:
+                y = y + self.bias.reshape(1, -1, 1)
+            return y
         return ops.conv_transpose1d(x, self.weight, self.bias, self.stride[0], self.padding[0], code[0],
                                     code[1], alpha)
 
@@ -153,6 +197,7 @@ class CachedSequential(nn.Sequential):
         cumulative_delay = kwargs.pop("cumulative_delay", 0)
         stride = kwargs.pop("stride", 1)
         super().__init__(*args, **kwargs)
+        self._cached = bool(config.cached)        # streaming variant: module by module (the ring buffers live in the convs)
         last = 0
         for m in reversed(list(self)):
             if hasattr(m, "cumulative_delay"):
@@ -178,7 +223,7 @@ class CachedSequential(nn.Sequential):
         x3 = mode == "bf16x3"
         if x3 and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             mode = "fp32"          # the split-operand mode is a forward path: gradients run on the fp32 kernels
-        if res is None and mode in ("bf16", "bf16x3") and x.is_cuda and x.dim() == 3:
+        if res is None and mode in ("bf16", "bf16x3") and x.is_cuda and x.dim() == 3 and not self._cached:
             specs = self._tc_plan()
             if specs is not None and (specs[0].kind != "conv" or x.shape[-1] % specs[0].stride == 0):
                 (out,) = engine.run_chain(engine.to_channel_last(x, x3=x3), specs, x3=x3)
@@ -217,21 +262,48 @@ Sequential = CachedSequential
 
 
 class AlignBranches(nn.Module):
-    """All delays are 0 outside the streaming mode: a plain fan-out."""
+    """Fan-out; in the streaming mode every branch input is delayed so that all branches come out aligned with the
+    slowest one (`delays` = each branch's own cumulative delay)."""
 
     def __init__(self, *branches, delays=None, cumulative_delay=0, stride=1):
         super().__init__()
         self.branches = nn.ModuleList(branches)
         self.cumulative_delay = cumulative_delay
+        self._cached = bool(config.cached)
+        if self._cached:
+            if delays is None:
+                delays = [getattr(b, "cumulative_delay", 0) for b in branches]
+            max_delay = max(delays) if len(delays) else 0
+            self.paddings = nn.ModuleList([CachedPadding1d(max_delay - d, crop=True) for d in delays])
+            self.cumulative_delay = int(cumulative_delay * stride) + max_delay
 
     def forward(self, x):
+        if self._cached:
+            return [b(p(x)) for b, p in zip(self.branches, self.paddings)]
         return [b(x) for b in self.branches]
 
 
 class CachedPadding1d(nn.Module):
+    """Ring buffer of the last `padding` samples of the previous call, prepended to the next one (zeros before the first
+    call); `crop` drops the same number of samples at the end, i.e. a pure delay line.  Identity outside the streaming
+    mode or when padding == 0."""
+
     def __init__(self, padding, crop=False):
         super().__init__()
-        self.padding = padding
+        self.padding = int(padding)
+        self.crop = crop
+        self._on = bool(config.cached) and self.padding > 0
+        if self._on:
+            self.register_buffer("pad", torch.zeros(0), persistent=False)
 
     def forward(self, x):
-        return x
+        if not self._on:
+            return x
+        B, C, _ = x.shape
+        if self.pad.numel() == 0 or self.pad.shape[0] < B or self.pad.shape[1] != C or self.pad.device != x.device:
+            self.pad = torch.zeros(max(B, MAX_BATCH_SIZE), C, self.padding, dtype=x.dtype, device=x.device)
+        y = torch.cat([self.pad[:B], x], -1)
+        self.pad[:B] = y[..., -self.padding:].detach()
+        if self.crop:
+            y = y[..., :-self.padding]
+        return y

@@ -637,3 +637,67 @@ def test_l1_feature_matching_stats_match_torch():
             wt, wv = torch.autograd.grad(want, [t2, v2])
             assert abs(float(got) - float(want)) <= 2e-6 * abs(float(want))
             assert rel_l2(gt, wt) < 1e-5 and rel_l2(gv, wv) < 1e-5
+
+
+def _stream_vs_offline(build, x, chunk):
+    from rave_b200 import cc
+    torch.manual_seed(12)
+    off = build()
+    cc.use_cached_conv(True)
+    try:
+        on = build()
+    finally:
+        cc.use_cached_conv(False)
+    on.load_state_dict(off.state_dict(), strict=True)
+    off.cuda()
+    on.cuda()
+    with torch.no_grad():
+        y_off = off(x)
+        y_on = torch.cat([on(c) for c in x.split(chunk, -1)], -1)
+    assert y_on.shape == y_off.shape
+    return y_on, y_off, on.cumulative_delay
+
+
+def test_streaming_cached_convs_reproduce_offline():
+    """SURVEY 8f.4 / the property the reference's tests/test_residual.py checks for cached_conv: modules built under
+    cc.use_cached_conv(True) and fed consecutive chunks reproduce the offline (non-cached) output, delayed by their
+    `cumulative_delay`.  Causal padding (what streaming models are trained with, configs/causal.gin): a whole
+    encoder / decoder style stack with zero delay; centred padding: each module kind with its own delay."""
+    from rave_b200 import blocks, cc
+
+    def stack(mode):
+        def build():
+            with cc.configure(conv_bias=True, padding_mode=mode):
+                return cc.CachedSequential(
+                    blocks.normalization(cc.Conv1d(16, 32, 7, padding=cc.get_padding(7))),
+                    blocks.Residual(blocks.DilatedUnit(32, 3, 1)),
+                    blocks.Residual(blocks.DilatedUnit(32, 3, 3)),
+                    nn.LeakyReLU(.2),
+                    blocks.normalization(cc.Conv1d(32, 64, 8, stride=4, padding=cc.get_padding(8, 4))),
+                    blocks.Residual(blocks.DilatedUnit(64, 3, 9)),
+                    nn.LeakyReLU(.2),
+                    blocks.normalization(cc.ConvTranspose1d(64, 32, 8, stride=4, padding=2)),
+                    blocks.Residual(blocks.DilatedUnit(32, 3, 1)))
+        return build
+
+    x = torch.randn(2, 16, 2048, device="cuda")
+    # the transposed conv's symmetric crop is a 2-sample delay even with causal convs around it
+    y_on, y_off, _ = _stream_vs_offline(stack("causal"), x, 256)
+    assert rel_l2(y_on[..., 2:], y_off[..., :-2]) < 1e-5
+
+    def one(mod):
+        def build():
+            with cc.configure(conv_bias=True, padding_mode="centered"):
+                return mod()
+        return build
+
+    cases = [
+        (one(lambda: blocks.Residual(blocks.DilatedUnit(16, 3, 3))), 3),
+        (one(lambda: blocks.normalization(cc.Conv1d(16, 32, 8, stride=4, padding=cc.get_padding(8, 4)))), 1),
+        (one(lambda: blocks.normalization(cc.ConvTranspose1d(16, 8, 8, stride=4, padding=2))), 2),
+        (one(lambda: blocks.normalization(cc.Conv1d(16, 16, 7, padding=cc.get_padding(7)))), 3),
+    ]
+    for build, want_d in cases:
+        y_on, y_off, d = _stream_vs_offline(build, x, 128)
+        assert d == want_d, (d, want_d)
+        assert rel_l2(y_on[..., d:], y_off[..., :y_off.shape[-1] - d]) < 1e-5, (want_d, rel_l2(y_on[..., d:], y_off[..., :-d]))
