@@ -358,7 +358,15 @@ def score_grad(score_cl, dstats6, L):
     return g.to(engine.ACT_DTYPE)
 
 
-def weight_prep_tc_multi(items, x3=False):
+def weight_prep_tc_multi(items, x3=False, into=None):
+    """`into`: overwrite the (norm, outA, outB) tensors of an earlier call in place (engine.refresh_static_prep)."""
+    if into is not None:
+        fresh = weight_prep_tc_multi(items, x3=x3)
+        for new, old in zip(fresh, into):
+            for a, b in zip(new, old):
+                if b is not None:
+                    b.copy_(a)
+        return into
     if not x3:
         return [weight_prep_tc(*it) for it in items]
     out = []

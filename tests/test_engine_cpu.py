@@ -334,3 +334,39 @@ def test_descript_mpd_chain_vs_oracle(emu):
         if emu == "exact_fp32" or a.numel() >= 64:       # (the 1-element weight_g of conv_post is noise in bf16)
             assert rel_l2(a, b) < tol(emu, 5e-5, 0.2), (k, rel_l2(a, b))
     assert cos(torch.cat([a.reshape(-1) for a in g_e[1:]]), torch.cat([b.reshape(-1) for b in g_o[1:]])) > 0.99
+
+
+def test_static_prepared_weights_follow_refresh(emu):
+    """engine.enable_static_prep: a chain keeps using its persistent prepared weights until refresh_static_prep rewrites
+    them in place (what GraphedTrainer relies on for the discriminator between D-steps, and the forward bench for the
+    encoder / generator)."""
+    from rave_b200 import configs, engine
+    if emu != "bf16":
+        pytest.skip("static prepared weights exist for the bf16 operand mode only")
+    torch.manual_seed(7)
+    _, enc, _ = configs.make_autoencoder("v2", capacity=16, latent_size=16)
+    net = enc.encoder.net
+    specs = net._tc_plan()
+    x = torch.randn(2, 16, 256)
+
+    def run():
+        with torch.no_grad():
+            (out,) = engine.run_chain(engine.to_channel_last(x), specs)
+        return out.clone()
+    y0 = run()
+    engine.enable_static_prep(net)
+    try:
+        assert torch.equal(run(), y0)                      # first static call prepares from the current parameters
+        with torch.no_grad():
+            for n, p in net.named_parameters():
+                if not n.endswith("bias"):                 # biases are read live by the epilogue, not prepared
+                    p.mul_(1.5)
+        assert torch.equal(run(), y0)                      # parameters moved, the static buffers did not
+        n = engine.refresh_static_prep(net)
+        assert n > 0
+        y1 = run()
+        assert not torch.equal(y1, y0)
+    finally:
+        engine.disable_static_prep(net)
+    engine.invalidate_prepared()
+    assert torch.equal(run(), y1)                          # same as a cold preparation from the moved parameters

@@ -681,9 +681,12 @@ def test_streaming_cached_convs_reproduce_offline():
         return build
 
     x = torch.randn(2, 16, 2048, device="cuda")
-    # the transposed conv's symmetric crop is a 2-sample delay even with causal convs around it
+    # the transposed conv's symmetric crop is a 2-sample delay even with causal convs around it.  The first samples are
+    # a start-up transient in ANY cached-conv implementation: offline, the layers after the transposed conv see zero
+    # padding where the stream carries the two cropped-away samples (measured on B200: only outputs 0..1 differ, 7e-4).
     y_on, y_off, _ = _stream_vs_offline(stack("causal"), x, 256)
-    assert rel_l2(y_on[..., 2:], y_off[..., :-2]) < 1e-5
+    warm = 16
+    assert rel_l2(y_on[..., 2 + warm:], y_off[..., warm:-2]) < 1e-5
 
     def one(mod):
         def build():
@@ -700,4 +703,6 @@ def test_streaming_cached_convs_reproduce_offline():
     for build, want_d in cases:
         y_on, y_off, d = _stream_vs_offline(build, x, 128)
         assert d == want_d, (d, want_d)
+        # centred padding: offline pads zeros on the left where the stream has its (zero) cache -> identical from 0 on
+        # for a single module, up to the right edge the delayed stream has not produced yet
         assert rel_l2(y_on[..., d:], y_off[..., :y_off.shape[-1] - d]) < 1e-5, (want_d, rel_l2(y_on[..., d:], y_off[..., :-d]))
