@@ -205,6 +205,12 @@ int rave_time_stack_cl(const float *x, void *out_bf16, int B, int C, int T, int 
                        void *stream);
 int rave_time_stack_cl_bwd(const void *g_bf16, float *gx, int B, int C, int T, int F, int Fp, int Cp, int kt, int pt,
                            void *stream);
+/* The same operand from a CHANNEL-LAST source x[b][t][f][c] (element strides sb, st; f-stride C): the MRD keeps its
+ * activations channel-last between layers, so no NCHW copy exists (rave/descript_discriminator.py:118-184). */
+int rave_time_stack_nhwc(const float *x, void *out_bf16, int B, int C, int T, int F, long sb, long st, int Fp, int Cp, int kt,
+                         int pt, void *stream);
+int rave_time_stack_nhwc_bwd(const void *g_bf16, float *gx, int B, int C, int T, int F, int Fp, int Cp, int kt, int pt,
+                             void *stream);
 /* L1 feature matching on fp32 features (core.mean_difference, rave/core.py:236-252): stats[0] += sum|t - v|,
  * stats[1] += sum|t| (stats zeroed by the caller); gradient of d[0] * stats[0] + d[1] * stats[1]: gt = d0 sgn(t - v) +
  * d1 sgn(t), gv = -d0 sgn(t - v) (either may be null). */

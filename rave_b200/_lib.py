@@ -50,6 +50,8 @@ SIGNATURES = {
     "rave_conv1d_tc_wgrad_splits": (c_int, [_I, _I, _I, _I, _I]),
     "rave_time_stack_cl": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rave_time_stack_cl_bwd": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rave_time_stack_nhwc": (c_int, [_P, _P, _I, _I, _I, _I, ctypes.c_long, ctypes.c_long, _I, _I, _I, _I, _P]),
+    "rave_time_stack_nhwc_bwd": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rave_l1_stats_f32": (c_int, [_P, _P, _P, ctypes.c_long, _P]),
     "rave_l1_grad_f32": (c_int, [_P, _P, _P, _P, _P, ctypes.c_long, _P]),
     "rave_snake_cl_fwd": (c_int, [_P, _P, _P, ctypes.c_long, _I, _P]),

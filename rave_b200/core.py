@@ -67,6 +67,15 @@ def mean_difference(target, value, norm: str = "L1", relative: bool = False):
     raise Exception(f"Norm must be either L1 or L2, got {norm}")
 
 
+def mean_difference_halves(base, n_true: int, relative: bool = False):
+    """mean_difference(real, fake, 'L1', relative) where real / fake are the two halves (dim 0) of ONE dense fp32 buffer
+    whose padding (if any) is zero in both halves; `n_true` = the number of real feature elements (the mean's
+    denominator, rave/core.py:244)."""
+    from . import ops
+    st = ops.l1_halves(base)
+    return st[0] / st[1] if relative else st[0] / n_true
+
+
 class _StftWindow(nn.Module):
     """Holder of one scale's hann window (`stfts.<i>.window`, the key torchaudio.transforms.Spectrogram contributes)."""
 

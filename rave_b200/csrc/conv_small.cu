@@ -840,6 +840,108 @@ time_stack_cl_bwd_kernel(const __nv_bfloat16 *__restrict__ g, float *__restrict_
   }
 }
 
+// Channel-last source (the MRD keeps its activations channel-last between layers: the conv output [(b, t)][f][c] IS the
+// next layer's [b][t][f][c]): x[b][t][f][c] fp32 with element strides (sb, st), f-stride C, channels contiguous.
+//   out[(b, t)][f][dt * C + c] = x[b][t + dt - pt][f][c]
+// One thread = 8 output channels = one 16-byte store; with C % 8 == 0 its 8 sources are two 16-byte loads of one tap.
+__global__ void __launch_bounds__(256)
+time_stack_nhwc_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, long sb, long st, int C, int T, int F,
+                       int Fp, int Cp, int kt, int pt, long total_vec, int vec) {
+  const int vpr = Cp >> 3;
+  const int nch = kt * C;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total_vec; i += (long)gridDim.x * 256) {
+    const int cv = (int)(i % vpr);
+    const long r = i / vpr;
+    const int f = (int)(r % Fp);
+    const long bt = r / Fp;
+    const int t = (int)(bt % T);
+    const long b = bt / T;
+    const int ch0 = cv * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (f < F && ch0 < nch) {
+      if (vec) {
+        const int dt = ch0 / C, c = ch0 - dt * C;
+        const int ts = t + dt - pt;
+        if (ts >= 0 && ts < T) {
+          const float4 *p = reinterpret_cast<const float4 *>(x + b * sb + ts * st + (long)f * C + c);
+          const float4 a0 = __ldg(p), a1 = __ldg(p + 1);
+          v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+          v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ch = ch0 + j;
+          if (ch < nch) {
+            const int dt = ch / C, c = ch - dt * C;
+            const int ts = t + dt - pt;
+            if (ts >= 0 && ts < T) v[j] = __ldg(x + b * sb + ts * st + (long)f * C + c);
+          }
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t *>(&h);
+    h = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t *>(&h);
+    h = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t *>(&h);
+    h = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t *>(&h);
+    reinterpret_cast<uint4 *>(out)[i] = o;
+  }
+}
+
+// adjoint into a contiguous [B][T][F][C] fp32 gradient: gx[b][tp][f][c] = sum_dt g[(b, tp + pt - dt)][f][dt * C + c]
+__global__ void __launch_bounds__(256)
+time_stack_nhwc_bwd_kernel(const __nv_bfloat16 *__restrict__ g, float *__restrict__ gx, int C, int T, int F, int Fp,
+                           int Cp, int kt, int pt, long total, int vec) {
+  if (vec) {           // one thread = 8 channels: kt 16-byte loads, two 16-byte stores
+    const int cvn = C >> 3;
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+      const int cv = (int)(i % cvn);
+      const long r = i / cvn;
+      const int f = (int)(r % F);
+      const long bt = r / F;
+      const int tp = (int)(bt % T);
+      const long b = bt / T;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int dt = 0; dt < kt; ++dt) {
+        const int t = tp + pt - dt;
+        if (t < 0 || t >= T) continue;
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(g + ((b * T + t) * Fp + f) * Cp + dt * C + cv * 8));
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 w = __bfloat1622float2(h[j]);
+          acc[2 * j] += w.x;
+          acc[2 * j + 1] += w.y;
+        }
+      }
+      float4 *dst = reinterpret_cast<float4 *>(gx + i * 8);
+      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    return;
+  }
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int c = (int)(i % C);
+    const long r = i / C;
+    const int f = (int)(r % F);
+    const long bt = r / F;
+    const int tp = (int)(bt % T);
+    const long b = bt / T;
+    float acc = 0.f;
+    for (int dt = 0; dt < kt; ++dt) {
+      const int t = tp + pt - dt;
+      if (t >= 0 && t < T) acc += __bfloat162float(g[((b * T + t) * Fp + f) * Cp + dt * C + c]);
+    }
+    gx[i] = acc;
+  }
+}
+
 }  // namespace rave
 
 extern "C" int rave_time_stack_cl(const float *x, void *out_bf16, int B, int C, int T, int F, int Fp, int Cp, int kt,
@@ -863,5 +965,35 @@ extern "C" int rave_time_stack_cl_bwd(const void *g_bf16, float *gx, int B, int 
   time_stack_cl_bwd_kernel<<<dim3(ceil_div(Fp, 32), T, B), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16 *)g_bf16, gx, C, T, F, Fp, Cp, kt, pt);
   RAVE_CHECK_LAUNCH("time_stack_cl_bwd");
+  return 0;
+}
+
+extern "C" int rave_time_stack_nhwc(const float *x, void *out_bf16, int B, int C, int T, int F, long sb, long st, int Fp,
+                                    int Cp, int kt, int pt, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && out_bf16 && B > 0 && C > 0 && T > 0 && F > 0 && Fp >= F && kt >= 1 && Cp >= kt * C &&
+                     Cp % 8 == 0 && ((uintptr_t)out_bf16 & 15) == 0, "time_stack_nhwc: bad shape");
+  const int vec = (C % 8 == 0) && ((uintptr_t)x & 15) == 0 && sb % 4 == 0 && st % 4 == 0;
+  const long total = (long)B * T * Fp * (Cp / 8);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  time_stack_nhwc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)out_bf16, sb, st, C, T, F, Fp,
+                                                                        Cp, kt, pt, total, vec);
+  RAVE_CHECK_LAUNCH("time_stack_nhwc");
+  return 0;
+}
+
+extern "C" int rave_time_stack_nhwc_bwd(const void *g_bf16, float *gx, int B, int C, int T, int F, int Fp, int Cp, int kt,
+                                        int pt, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(g_bf16 && gx && B > 0 && C > 0 && T > 0 && F > 0 && Fp >= F && kt >= 1 && Cp >= kt * C &&
+                     Cp % 8 == 0 && ((uintptr_t)g_bf16 & 15) == 0, "time_stack_nhwc_bwd: bad shape");
+  const int vec = (C % 8 == 0) && ((uintptr_t)gx & 15) == 0;
+  const long total = vec ? (long)B * T * F * (C / 8) : (long)B * T * F * C;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  time_stack_nhwc_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)g_bf16, gx, C, T, F, Fp,
+                                                                            Cp, kt, pt, total, vec);
+  RAVE_CHECK_LAUNCH("time_stack_nhwc_bwd");
   return 0;
 }

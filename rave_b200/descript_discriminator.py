@@ -44,7 +44,7 @@ class DiscConv2d(nn.Conv2d):
         B, C, T, Fq = x.shape
         kt, kf = self.kernel_size
         pt, pf = self.padding
-        if engine.precision() == "bf16" and x.is_cuda and engine.ACT_DTYPE == torch.bfloat16 and kt * C <= 112:
+        if self.tc_ready(x, C):
             return self._forward_tc(x, B, C, T, Fq)
         xp = F.pad(x, (0, 0, pt, pt))
         xi = torch.stack([xp[:, :, dt:dt + T] for dt in range(kt)], 1)            # [B, kt, C, T, F]
@@ -53,11 +53,9 @@ class DiscConv2d(nn.Conv2d):
         y = ops.conv1d(xi, w, self.bias, None, self.stride[1], 1, (pf, pf), ops.ACT_NONE, 0.0, None)
         return y.view(B, T, self.out_channels, y.shape[-1]).permute(0, 2, 1, 3)
 
-    def _forward_tc(self, x, B, C, T, Fq):
-        """bf16 mode: the same conv along frequency as a one-layer chain of the tcgen05 engine (forward, dgrad and wgrad
-        on the tensor cores; 23 % of the v3 discriminator FLOPs ran on the fp32 CUDA-core kernels: 176 ms of a 280 ms
-        G-step).  The (dt, c) channel order is a permuted VIEW of the parameter, so the weight-norm backward of the chain
-        reaches weight_v / weight_g through autograd."""
+    def _tc_chain_spec(self, C):
+        """One-layer engine chain of this conv along frequency; the (dt, c) channel order is a permuted VIEW of the
+        parameter, so the weight-norm backward of the chain reaches weight_v / weight_g through autograd."""
         from . import engine
         kt, kf = self.kernel_size
         pt, pf = self.padding
@@ -78,12 +76,45 @@ class DiscConv2d(nn.Conv2d):
         else:
             proxy.weight = self.weight.permute(0, 2, 1, 3).reshape(co, cin, kf)
         proxy.bias = self.bias
+        return spec
+
+    def _forward_tc(self, x, B, C, T, Fq):
+        """bf16 mode: the same conv along frequency as a one-layer chain of the tcgen05 engine (forward, dgrad and wgrad
+        on the tensor cores; 23 % of the v3 discriminator FLOPs ran on the fp32 CUDA-core kernels: 176 ms of a 280 ms
+        G-step).  NCHW in, NCHW (view) out; the MRD itself stays channel-last between layers (`forward_cl`)."""
+        from . import engine
+        spec = self._tc_chain_spec(C)
+        kt, pt, co = self.kernel_size[0], self.padding[0], self.out_channels
         # rows (b, t), positions f, channels (dt, c): channel-last bf16 operand of the engine, in one library pass
         rpad = (-Fq) % spec.stride
-        x_cl = ops.time_stack_cl(x, kt, pt, cin + spec.cin_pad, Fq + rpad)
+        x_cl = ops.time_stack_cl(x, kt, pt, kt * C + spec.cin_pad, Fq + rpad)
         (out,) = engine.run_chain(x_cl, [spec], Fq)
         Fo = engine.chain_lengths([spec], Fq)[0]
         return out[:, :Fo, :co].reshape(B, T, Fo, co).permute(0, 3, 1, 2)
+
+    def cout_ok(self) -> bool:
+        return self.out_channels % 16 == 0
+
+    def tc_ready(self, x, C) -> bool:
+        from . import engine
+        return (engine.precision() == "bf16" and x.is_cuda and engine.ACT_DTYPE == torch.bfloat16
+                and self.kernel_size[0] * C <= 112)
+
+    def forward_cl(self, x_cl):
+        """Channel-last in, channel-last out: x_cl [B, T, F, C] fp32 (a view with dense (f, c) rows) -> the chain's own
+        output buffer [(b t), Fo, Cout(+pad to 16)] fp32, which IS [B, T, Fo, Cout] channel-last: no layout pass on
+        either side of the conv."""
+        from . import engine
+        B, T, Fq, C = x_cl.shape
+        spec = self._tc_chain_spec(C)
+        kt, pt = self.kernel_size[0], self.padding[0]
+        rpad = (-Fq) % spec.stride
+        xs = ops.time_stack_nhwc(x_cl, kt, pt, kt * C + spec.cin_pad, Fq + rpad)
+        (out,) = engine.run_chain(xs, [spec], Fq)
+        Fo = engine.chain_lengths([spec], Fq)[0]
+        if out.shape[1] != Fo:
+            raise _lib.RaveB200Error("DiscConv2d: the one-layer chain's output pitch is its length")
+        return out
 
 
 class _ParamView:
@@ -145,9 +176,12 @@ class MPD(nn.Module):
         lens = engine.chain_lengths(specs, L)
         fmap = []
         for i, (s, o, Lo) in enumerate(zip(specs, outs, lens)):
-            h = o[:, :Lo, :s.Cout].reshape(B, W, Lo, s.Cout).permute(0, 3, 2, 1)
-            if i < len(self.convs):          # features are POST-activation (descript_discriminator.py:59-61)
-                h = ops.activation(h.contiguous(), ops.ACT_LEAKY, self.convs[i][1].negative_slope)
+            # features are POST-activation (descript_discriminator.py:59-61): one elementwise pass over the chain's own
+            # [(b w), pitch, C] buffer (rows beyond Lo stay zero), the [B, C, L, W] feature is a VIEW of it
+            a = ops.activation(o, ops.ACT_LEAKY, self.convs[i][1].negative_slope) if i < len(self.convs) else o
+            h = a[:, :Lo, :s.Cout].unflatten(0, (B, W)).permute(0, 3, 2, 1)
+            if i < len(self.convs) and not s.cout_pad:
+                h._cl_base = a          # dense buffer behind the view (core.feature_matching_halves)
             fmap.append(h)
         return fmap
 
@@ -214,7 +248,35 @@ class MRD(nn.Module):
         x = z.reshape(B, C, t, f, 2).permute(0, 1, 4, 2, 3).reshape(B, 2 * C, t, f)   # "b c f t p -> b (c p) t f"
         return [x[..., lo:hi] for lo, hi in self.bands]
 
+    def _forward_cl(self, x):
+        """bf16 engine mode: the whole MRD channel-last.  The complex spectrogram [B, t, f, (re, im)] is already the
+        channel-last input of the first conv; every conv's output buffer is the next conv's input and -- after the one
+        LeakyReLU pass -- the feature (an NCHW *view*, torch's channels_last layout)."""
+        B, C, T = x.shape
+        st = self.stft
+        z = ops.rfft(ops.stft_frames(x.reshape(B * C, T), st.window, st.n_fft, st.hop), st.rfft_bw)
+        x0 = torch.view_as_real(z)                                          # [B, t, f, 2]: "b (c p) t f" for c = 1
+        t = x0.shape[1]
+        fmap, outs = [], []
+        for (lo, hi), stack in zip(self.bands, self.band_convs):
+            cur = x0[:, :, lo:hi, :]
+            for layer in stack:
+                conv = layer[0]
+                out = conv.forward_cl(cur)                                   # [(b t), Fo, 32]
+                a = ops.activation(out, ops.ACT_LEAKY, layer[1].negative_slope)
+                cur = a.view(B, t, out.shape[1], out.shape[2])
+                feat = cur.permute(0, 3, 1, 2)
+                feat._cl_base = a
+                fmap.append(feat)
+            outs.append(cur)
+        out = self.conv_post.forward_cl(torch.cat(outs, dim=2))              # [(b t), F, 16]: one score channel + padding
+        fmap.append(out.view(B, t, out.shape[1], out.shape[2])[..., :self.conv_post.out_channels].permute(0, 3, 1, 2))
+        return fmap
+
     def forward(self, x):
+        if (x.is_cuda and x.shape[1] == 1 and x.shape[-1] > self.stft.n_fft // 2
+                and self.conv_post.tc_ready(x, 32) and self.band_convs[0][0][0].cout_ok()):
+            return self._forward_cl(x)
         fmap = []
         outs = []
         for band, stack in zip(self.spectrogram(x), self.band_convs):

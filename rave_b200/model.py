@@ -315,10 +315,21 @@ class RAVE(nn.Module):
             loss_adv = 0
             pred_real = 0
             pred_fake = 0
-            for scale_real, scale_fake in zip(feature_real, feature_fake):
-                current = sum(map(self.feature_matching_fun, scale_real[self.num_skipped_features:],
-                                  scale_fake[self.num_skipped_features:])) / len(
-                                      scale_real[self.num_skipped_features:])
+            # Features that are views of a dense channel-last buffer holding [real; fake] (the Descript discriminator on
+            # the engine) are matched on that buffer: one pass, gradient written in the buffer's own layout.
+            kw = getattr(self.feature_matching_fun, "keywords", None)
+            on_bases = (kw is not None and getattr(self.feature_matching_fun, "func", None) is core.mean_difference
+                        and kw.get("norm", "L1") == "L1")
+            skip = self.num_skipped_features
+            for scale, scale_real, scale_fake in zip(features, feature_real, feature_fake):
+                terms = []
+                for full, real, fake in zip(scale[skip:], scale_real[skip:], scale_fake[skip:]):
+                    base = getattr(full, "_cl_base", None) if on_bases else None
+                    if base is not None:
+                        terms.append(core.mean_difference_halves(base, real.numel(), bool(kw.get("relative", False))))
+                    else:
+                        terms.append(self.feature_matching_fun(real, fake))
+                current = sum(terms) / len(terms)
                 feature_matching_distance = feature_matching_distance + current
                 _dis, _adv = self.gan_loss(scale_real[-1], scale_fake[-1])
                 pred_real = pred_real + scale_real[-1].mean()

@@ -471,6 +471,71 @@ def time_stack_cl(x, kt, pt, Cp, Fp):
     return TimeStackFn.apply(x, kt, pt, Cp, Fp)
 
 
+class TimeStackNhwcFn(torch.autograd.Function):
+    """x [B, T, F, C] fp32 channel-last (any batch / time strides, channels and positions dense) -> the same
+    [(b t), Fp, Cp] bf16 operand (rave_time_stack_nhwc); backward = the adjoint into a contiguous [B, T, F, C]."""
+
+    @staticmethod
+    def forward(ctx, x, kt, pt, Cp, Fp):
+        if x.dtype != torch.float32:
+            x = x.float()
+        B, T, F_, C = x.shape
+        if x.stride(3) != 1 or x.stride(2) != C:
+            x = x.contiguous()
+        out = torch.empty(B * T, Fp, Cp, dtype=torch.bfloat16, device=x.device)
+        if not x.is_cuda:
+            raise _lib.RaveB200Error("rave_b200 ops need CUDA tensors (there is no CPU path)")
+        call("rave_time_stack_nhwc", x.data_ptr(), ptr(out), B, C, T, F_, x.stride(0), x.stride(1), Fp, Cp, kt, pt,
+             stream_ptr())          # x: a strided view (band slice of the spectrogram / rows of the previous output)
+        ctx.cfg = (B, C, T, F_, Fp, Cp, kt, pt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, T, F_, Fp, Cp, kt, pt = ctx.cfg
+        g = g.contiguous()
+        gx = torch.empty(B, T, F_, C, dtype=torch.float32, device=g.device)
+        call("rave_time_stack_nhwc_bwd", ptr(g), ptr(gx), B, C, T, F_, Fp, Cp, kt, pt, stream_ptr())
+        return gx, None, None, None, None
+
+
+def time_stack_nhwc(x, kt, pt, Cp, Fp):
+    return TimeStackNhwcFn.apply(x, kt, pt, Cp, Fp)
+
+
+class L1HalvesFn(torch.autograd.Function):
+    """(sum |real - fake|, sum |real|) where real / fake are the first / second half (along dim 0) of ONE contiguous fp32
+    buffer -- the discriminator ran on cat([real, fake]) -- and the gradient written into one buffer of the same layout
+    (no split / cat passes).  Zero padding inside the buffer, identical in both halves, contributes nothing."""
+
+    @staticmethod
+    def forward(ctx, base):
+        if base.dtype != torch.float32 or not base.is_contiguous() or base.shape[0] % 2:
+            raise _lib.RaveB200Error("l1_halves: contiguous fp32 buffer with an even leading dimension expected")
+        half = base.numel() // 2
+        flat = base.view(-1)
+        stats = torch.zeros(2, dtype=torch.float32, device=base.device)
+        call("rave_l1_stats_f32", ptr(flat[:half]), ptr(flat[half:]), ptr(stats), half, stream_ptr())
+        ctx.save_for_backward(base)
+        return stats
+
+    @staticmethod
+    def backward(ctx, d):
+        (base,) = ctx.saved_tensors
+        d = _f32c(d)
+        half = base.numel() // 2
+        flat = base.view(-1)
+        g = torch.empty_like(base)
+        gf = g.view(-1)
+        call("rave_l1_grad_f32", ptr(flat[:half]), ptr(flat[half:]), ptr(d), ptr(gf[:half]), ptr(gf[half:]), half,
+             stream_ptr())
+        return g
+
+
+def l1_halves(base):
+    return L1HalvesFn.apply(base)
+
+
 class L1StatsFn(torch.autograd.Function):
     """(sum |t - v|, sum |t|) of two fp32 CUDA tensors in one pass, gradient in one pass (rave_l1_stats_f32 / _grad)."""
 

@@ -159,3 +159,71 @@ def test_descript_mrd_bf16_engine_vs_oracle():
     for k, a, b in zip(names, g[1:], g_o[1:]):
         if a.numel() >= 64:
             assert cos(a, b) > 0.95, (k, cos(a, b))
+
+
+def test_time_stack_nhwc_and_l1_halves_vs_torch():
+    """The channel-last MRD plumbing: rave_time_stack_nhwc (+ adjoint) on a strided band slice and on dense rows, and
+    the one-buffer L1 feature matching (rave_l1_* on the two halves of a buffer)."""
+    from rave_b200 import ops
+    torch.manual_seed(3)
+    for (B, T, Ftot, C, lo, hi, kt, Cp, Fp) in [(3, 9, 40, 2, 5, 31, 3, 16, 26), (2, 7, 33, 32, 0, 33, 3, 96, 34),
+                                                (2, 5, 20, 32, 3, 20, 3, 112, 17), (2, 4, 12, 8, 0, 12, 1, 16, 12)]:
+        pt = (kt - 1) // 2
+        base = torch.randn(B, T, Ftot, C, device="cuda")
+        x = base[:, :, lo:hi, :].detach().requires_grad_(True)
+        F_ = hi - lo
+        out = ops.time_stack_nhwc(x, kt, pt, Cp, Fp)
+        xp = torch.nn.functional.pad(x, (0, 0, 0, 0, pt, pt))
+        want = torch.cat([xp[:, dt:dt + T] for dt in range(kt)], -1)                      # [B, T, F, kt C]
+        want = torch.nn.functional.pad(want, (0, Cp - kt * C, 0, Fp - F_)).reshape(B * T, Fp, Cp)
+        assert torch.equal(out, want.bfloat16())
+        g = torch.randn_like(out)
+        (gx,) = torch.autograd.grad(out, x, g)
+        (gw,) = torch.autograd.grad(want, x, g.float())
+        assert rel_l2(gx, gw) < 1e-6
+    buf = torch.randn(6, 50, 32, device="cuda")
+    buf[:, 45:] = 0.
+    b1 = buf.clone().requires_grad_(True)
+    b2 = buf.clone().requires_grad_(True)
+    st = ops.l1_halves(b1)
+    want = torch.stack([(b2[:3] - b2[3:]).abs().sum(), b2[:3].abs().sum()])
+    assert rel_l2(st, want) < 1e-6
+    d = torch.tensor([0.7, -0.3], device="cuda")
+    (g1,) = torch.autograd.grad((st * d).sum(), b1)
+    (g2,) = torch.autograd.grad((want * d).sum(), b2)
+    assert torch.allclose(g1, g2, atol=1e-6)
+
+
+def test_descript_feature_matching_on_dense_buffers_matches_generic():
+    """model.compute_losses' feature matching on the `_cl_base` buffers == core.mean_difference on the split feature
+    views (values and the gradient reaching the discriminator input)."""
+    import rave_b200
+    from rave_b200 import core
+    from rave_b200.descript_discriminator import DescriptDiscriminator
+    torch.manual_seed(2)
+    dd = DescriptDiscriminator().cuda()
+    x = (0.5 * torch.randn(4, 1, 16384, device="cuda")).clamp(-1, 1)
+    rave_b200.set_precision("bf16")
+    try:
+        res = []
+        for fast in (True, False):
+            xg = x.clone().requires_grad_(True)
+            feats = dd(xg)
+            total = 0.
+            n_bases = 0
+            for scale in feats:
+                for f in scale[:-1]:
+                    assert f.shape[0] == 4
+                    base = getattr(f, "_cl_base", None)
+                    n_bases += base is not None
+                    if fast and base is not None:
+                        total = total + core.mean_difference_halves(base, f.numel() // 2, False)
+                    else:
+                        total = total + core.mean_difference(f[:2], f[2:], "L1", False)
+            assert n_bases == 5 * 5 + 3 * 25
+            (gx,) = torch.autograd.grad(total, xg)
+            res.append((total.detach(), gx))
+    finally:
+        rave_b200.set_precision("fp32")
+    assert rel_l2(res[0][0], res[1][0]) < 1e-5
+    assert rel_l2(res[0][1], res[1][1]) < 1e-3          # bf16 gradient streams, different accumulation order
