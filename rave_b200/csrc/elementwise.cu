@@ -100,6 +100,38 @@ act_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float 
   }
 }
 
+// Activations without a per-channel parameter (LeakyReLU) do not care about the [B][C][L] shape: flat 16-byte passes
+// (the Descript discriminator's channel-last features have L = 32: one (b, c) row per CTA used 32 of 256 threads).
+__global__ void __launch_bounds__(256)
+act_flat_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, long n, int act, float slope, int vec) {
+  const long n4 = vec ? (n >> 2) : 0;
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  float4 *y4 = reinterpret_cast<float4 *>(y);
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n4; i += (long)gridDim.x * 256) {
+    float4 a = __ldg(x4 + i);
+    a.x = act_apply(a.x, act, slope, 0.f); a.y = act_apply(a.y, act, slope, 0.f);
+    a.z = act_apply(a.z, act, slope, 0.f); a.w = act_apply(a.w, act, slope, 0.f);
+    y4[i] = a;
+  }
+  for (long i = (n4 << 2) + blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256)
+    y[i] = act_apply(x[i], act, slope, 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+act_flat_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dx, long n, int act,
+                    float slope, int vec) {
+  const long n4 = vec ? (n >> 2) : 0;
+  const float4 *x4 = reinterpret_cast<const float4 *>(x), *g4 = reinterpret_cast<const float4 *>(dy);
+  float4 *d4 = reinterpret_cast<float4 *>(dx);
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n4; i += (long)gridDim.x * 256) {
+    const float4 a = __ldg(x4 + i), g = __ldg(g4 + i);
+    d4[i] = make_float4(g.x * act_grad(a.x, act, slope, 0.f), g.y * act_grad(a.y, act, slope, 0.f),
+                        g.z * act_grad(a.z, act, slope, 0.f), g.w * act_grad(a.w, act, slope, 0.f));
+  }
+  for (long i = (n4 << 2) + blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256)
+    dx[i] = dy[i] * act_grad(x[i], act, slope, 0.f);
+}
+
 // y[b][c][t] = tanh(x[b][c][t] * sigmoid(x[b][C+c][t]))
 __global__ void __launch_bounds__(256)
 am_tanh_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int L, long total) {
@@ -188,6 +220,15 @@ extern "C" int rave_act_fwd(const float *x, float *y, int B, int C, int L, int a
   RAVE_CHECK_ARG(x && y, "act_fwd: null pointer");
   RAVE_CHECK_ARG(B > 0 && C > 0 && L > 0 && B <= 65535 && C <= 65535, "act_fwd: bad shape");
   RAVE_CHECK_ARG(act != RAVE_ACT_SNAKE || alpha, "act_fwd: snake needs alpha");
+  if (act != RAVE_ACT_SNAKE) {
+    const long n = (long)B * C * L;
+    const int vec = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+    long blocks = ((vec ? n / 4 : n) + 255) / 256;
+    blocks = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
+    act_flat_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n, act, slope, vec);
+    RAVE_CHECK_LAUNCH("act_fwd");
+    return 0;
+  }
   dim3 grid(ceil_div(L, 1024), C, B);
   act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, C, L, act, slope, alpha);
   RAVE_CHECK_LAUNCH("act_fwd");
@@ -200,6 +241,15 @@ extern "C" int rave_act_bwd(const float *dy, const float *x, float *dx, float *d
   RAVE_CHECK_ARG(dy && x && dx, "act_bwd: null pointer");
   RAVE_CHECK_ARG(B > 0 && C > 0 && L > 0 && B <= 65535 && C <= 65535, "act_bwd: bad shape");
   RAVE_CHECK_ARG(act != RAVE_ACT_SNAKE || alpha, "act_bwd: snake needs alpha");
+  if (act != RAVE_ACT_SNAKE) {
+    const long n = (long)B * C * L;
+    const int vec = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0;
+    long blocks = ((vec ? n / 4 : n) + 255) / 256;
+    blocks = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
+    act_flat_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, dx, n, act, slope, vec);
+    RAVE_CHECK_LAUNCH("act_bwd");
+    return 0;
+  }
   if (act == RAVE_ACT_SNAKE && dalpha) cudaMemsetAsync(dalpha, 0, sizeof(float) * C, (cudaStream_t)stream);
   dim3 grid(ceil_div(L, 1024), C, B);
   act_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, x, dx, dalpha, C, L, act, slope, alpha);

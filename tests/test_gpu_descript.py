@@ -220,6 +220,7 @@ def test_descript_feature_matching_on_dense_buffers_matches_generic():
                         total = total + core.mean_difference_halves(base, f.numel() // 2, False)
                     else:
                         total = total + core.mean_difference(f[:2], f[2:], "L1", False)
+                total = total + scale[-1].mean()          # the score: every chain's last layer needs a gradient
             assert n_bases == 5 * 5 + 3 * 25
             (gx,) = torch.autograd.grad(total, xg)
             res.append((total.detach(), gx))

@@ -226,6 +226,16 @@ def test_am_tanh_and_snake():
     sg = ops.activation(xg, ops.ACT_SNAKE, 0.0, ag)
     gxg, gag = torch.autograd.grad(sg, [xg, ag], gs.cuda())
     assert rel_l2(sg, so) < 1e-6 and rel_l2(gxg, gxo) < 1e-5 and rel_l2(gag, gao) < 1e-4
+    # LeakyReLU: the flat 16-byte kernels, including a tail and a buffer that is not 16-byte aligned
+    for shape, off in [((3, 5, 7), 0), ((2, 32, 100), 0), ((1, 3, 1001), 1)]:
+        n = int(np.prod(shape))
+        buf = torch.randn(n + off, device="cuda")
+        xl = buf[off:].view(shape).detach().requires_grad_(True)
+        yl = ops.activation(xl, ops.ACT_LEAKY, 0.1)
+        gl = torch.randn_like(yl)
+        (gxl,) = torch.autograd.grad(yl, xl, gl)
+        assert torch.equal(yl, torch.nn.functional.leaky_relu(xl.detach(), 0.1))
+        assert torch.equal(gxl, gl * torch.where(xl.detach() > 0, 1.0, 0.1))
 
 
 # ---------------------------------------------------------------------------- model-level goldens
