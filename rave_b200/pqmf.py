@@ -242,3 +242,25 @@ class CachedPQMF(PQMF):
 
     def _synthesis_weight(self):
         return self.inverse_conv.weight, self.inverse_conv._pad[0]
+
+    # -- streaming (cc.use_cached_conv(True) at construction): the two convs carry ring buffers; the bank is
+    #    evaluated chunk by chunk through them exactly as rave/pqmf.py:279-294 does (the offline kernels above fuse the
+    #    sign flips / x16 / interleave, the streaming path keeps them as separate small passes: chunks are short).
+    @property
+    def streaming(self) -> bool:
+        return bool(getattr(self.forward_conv, "_cached", False))
+
+    def forward(self, x):
+        if not self.streaming or self.n_band == 1:
+            return super().forward(x)
+        return reverse_half(self.forward_conv(x))
+
+    def inverse(self, x):
+        if not self.streaming or self.n_band == 1:
+            return super().inverse(x)
+        m = self.hk.shape[0]
+        y = self.inverse_conv(reverse_half(x)) * m                  # [B, m, t]
+        y = y.flip(1).permute(0, 2, 1)                              # [B, t, m]
+        y = y.reshape(y.shape[0], y.shape[1], -1, m).permute(0, 2, 1, 3)
+        return y.reshape(y.shape[0], y.shape[1], -1)
+

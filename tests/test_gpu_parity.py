@@ -228,7 +228,7 @@ def test_am_tanh_and_snake():
     assert rel_l2(sg, so) < 1e-6 and rel_l2(gxg, gxo) < 1e-5 and rel_l2(gag, gao) < 1e-4
     # LeakyReLU: the flat 16-byte kernels, including a tail and a buffer that is not 16-byte aligned
     for shape, off in [((3, 5, 7), 0), ((2, 32, 100), 0), ((1, 3, 1001), 1)]:
-        n = int(np.prod(shape))
+        n = shape[0] * shape[1] * shape[2]
         buf = torch.randn(n + off, device="cuda")
         xl = buf[off:].view(shape).detach().requires_grad_(True)
         yl = ops.activation(xl, ops.ACT_LEAKY, 0.1)
@@ -716,3 +716,29 @@ def test_streaming_cached_convs_reproduce_offline():
         # centred padding: offline pads zeros on the left where the stream has its (zero) cache -> identical from 0 on
         # for a single module, up to the right edge the delayed stream has not produced yet
         assert rel_l2(y_on[..., d:], y_off[..., :y_off.shape[-1] - d]) < 1e-5, (want_d, rel_l2(y_on[..., d:], y_off[..., :-d]))
+
+
+def test_streaming_cached_pqmf_vs_offline_kernels():
+    """CachedPQMF under cc.use_cached_conv(True), chunk by chunk through the cached library convs, against the fused
+    offline PQMF kernels (golden-pinned above) delayed by the convs' cumulative delays."""
+    from rave_b200 import cc
+    from rave_b200.pqmf import CachedPQMF
+    off = CachedPQMF(100, 16).cuda()
+    cc.use_cached_conv(True)
+    try:
+        on = CachedPQMF(100, 16).cuda()
+    finally:
+        cc.use_cached_conv(False)
+    assert on.streaming and not off.streaming
+    x = torch.randn(2, 1, 16 * 1024, device="cuda")
+    with torch.no_grad():
+        mb_off = off(x)
+        mb_on = torch.cat([on(c) for c in x.split(4096, -1)], -1)
+        d_f = on.forward_conv.cumulative_delay
+        assert mb_on.shape == mb_off.shape
+        assert rel_l2(mb_on[..., d_f + 64:], mb_off[..., 64:mb_off.shape[-1] - d_f]) < 1e-5
+        y_off = off.inverse(mb_off)
+        y_on = torch.cat([on.inverse(c) for c in mb_off.split(256, -1)], -1)
+        d_i = on.inverse_conv.cumulative_delay * 16
+        assert y_on.shape == y_off.shape
+        assert rel_l2(y_on[..., d_i + 1024:], y_off[..., 1024:y_off.shape[-1] - d_i]) < 1e-5

@@ -128,3 +128,49 @@ def test_stream_is_chunk_size_invariant(torch_ops):
     x = torch.randn(1, 8, 1024)
     outs = [_stream_vs_offline(build, x, c)[0] for c in (64, 256, 1024)]
     assert rel_l2(outs[0], outs[1]) < 1e-6 and rel_l2(outs[0], outs[2]) < 1e-6
+
+
+def test_streaming_cached_pqmf_reproduces_offline_operator(torch_ops):
+    """CachedPQMF built under cc.use_cached_conv(True) (rave/pqmf.py:245-294 in streaming mode): analysis and synthesis fed
+    chunk by chunk reproduce the offline operator (golden-pinned: tests/golden/pqmf.pt; here restated with torch convs
+    on the module's own taps) delayed by the convs' cumulative delays."""
+    from rave_b200 import cc
+    from rave_b200.pqmf import CachedPQMF, reverse_half
+    cc.use_cached_conv(True)
+    try:
+        pq = CachedPQMF(100, 16)
+    finally:
+        cc.use_cached_conv(False)
+    assert pq.streaming
+    x = torch.randn(2, 1, 16 * 512)
+    # offline restatement on the same taps: rave/pqmf.py:279-294 with zero-padded (non-cached) convs
+    wf, wi = pq.forward_conv.weight, pq.inverse_conv.weight
+    pf = (wf.shape[-1] - 1) // 2
+    mb_off = reverse_half(F.conv1d(x, wf, None, 16, pf))
+    pi = (wi.shape[-1] - 1) // 2
+    y = F.conv1d(reverse_half(mb_off), wi, None, 1, pi) * 16
+    y = y.flip(1).permute(0, 2, 1)
+    y = y.reshape(y.shape[0], y.shape[1], -1, 16).permute(0, 2, 1, 3)
+    y_off = y.reshape(y.shape[0], y.shape[1], -1)
+    with torch.no_grad():
+        mb_on = torch.cat([pq(c) for c in x.split(2048, -1)], -1)
+        d_f = pq.forward_conv.cumulative_delay            # in multiband samples
+        assert mb_on.shape == mb_off.shape
+        assert rel_l2(mb_on[..., d_f:], mb_off[..., :mb_off.shape[-1] - d_f]) < 1e-5
+        pq2 = pq                                            # synthesis on the OFFLINE bands: isolates the inverse's delay
+        y_on = torch.cat([pq2.inverse(c) for c in mb_off.split(128, -1)], -1)
+    d_i = pq.inverse_conv.cumulative_delay * 16             # band samples -> audio samples
+    assert y_on.shape == y_off.shape
+    assert rel_l2(y_on[..., d_i:], y_off[..., :y_off.shape[-1] - d_i]) < 1e-5
+    # and the pair is a (delayed) near-perfect reconstruction of the input
+    total = d_f * 16 + d_i
+    with torch.no_grad():
+        cc.use_cached_conv(True)
+        try:
+            pq3 = CachedPQMF(100, 16)
+        finally:
+            cc.use_cached_conv(False)
+        rec = torch.cat([pq3.inverse(pq3(c)) for c in x.split(2048, -1)], -1)
+    lo, hi = total + 1024, x.shape[-1] - 1024
+    best = min(rel_l2(rec[..., lo + s:hi + s], x[..., lo - total:hi - total]) for s in (-16, -1, 0, 1, 16))
+    assert best < 2e-2, best
