@@ -216,6 +216,13 @@ int rave_time_stack_nhwc_bwd(const void *g_bf16, float *gx, int B, int C, int T,
  * d1 sgn(t), gv = -d0 sgn(t - v) (either may be null). */
 int rave_l1_stats_f32(const float *t, const float *v, float *stats, long n, void *stream);
 int rave_l1_grad_f32(const float *t, const float *v, const float *d, float *gt, float *gv, long n, void *stream);
+/* Post-activation feature tap of the Descript discriminator with its L1 feature matching (rave/descript_discriminator.py:
+ * 59-61, rave/model.py:353-361): x = [real; fake] halves of H elements each (one contiguous buffer, identical zero padding).
+ * fwd: a = LeakyReLU(x), stats[0] += sum|a_r - a_f|, stats[1] += sum|a_r| (stats zeroed by the caller).
+ * bwd: gx_r = (g_r + d0 sgn(a_r - a_f) + d1 sgn(a_r)) leaky'(a_r), gx_f = (g_f - d0 sgn(a_r - a_f)) leaky'(a_f);
+ * g (gradient from the feature's other consumers) or d (gradient of the two sums) may be null, not both. */
+int rave_leaky_fm_fwd(const float *x, float *a, float *stats, long H, float slope, void *stream);
+int rave_leaky_fm_bwd(const float *a, const float *g, const float *d, float *gx, long H, float slope, void *stream);
 /* Snake (rave/blocks.py:852-860) on the engine's channel-last bf16 streams [rows][C] (v3 chains on the tcgen05 kernels):
  * a = h + sin^2(alpha h) / (alpha + 1e-9);  backward: gh = ga * da/dh + add (add may be null), dalpha[c] += sum_rows
  * ga * da/dalpha (dalpha zeroed by the caller). */

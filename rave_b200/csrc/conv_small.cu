@@ -997,3 +997,116 @@ extern "C" int rave_time_stack_nhwc_bwd(const void *g_bf16, float *gx, int B, in
   RAVE_CHECK_LAUNCH("time_stack_nhwc_bwd");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Post-activation feature tap of the Descript discriminator (rave/descript_discriminator.py:59-61, 172-176 + the L1
+// feature matching of rave/model.py:353-361 on it): x = chain output holding [real; fake] halves (contiguous, H elements
+// each, identical zero padding).  ONE pass: a = LeakyReLU(x) (the feature, and the next layer's input) and
+// stats += (sum |a_r - a_f|, sum |a_r|); ONE backward pass:
+//   gx_r = (g_r + d0 sgn(a_r - a_f) + d1 sgn(a_r)) * leaky'(a_r),   gx_f = (g_f - d0 sgn(a_r - a_f)) * leaky'(a_f)
+// (g = gradient arriving at the feature from its other consumers, or null; d = gradient of the two sums, or null).
+// ---------------------------------------------------------------------------------------------
+namespace rave {
+
+__device__ __forceinline__ float lk(float x, float slope) { return x > 0.f ? x : slope * x; }
+__device__ __forceinline__ float dlk(float a, float slope) { return a > 0.f ? 1.f : slope; }
+
+__global__ void __launch_bounds__(256)
+leaky_fm_fwd_kernel(const float *__restrict__ x, float *__restrict__ a, float *__restrict__ stats, long H, float slope,
+                    int vec) {
+  __shared__ float red0[8], red1[8];
+  float s0 = 0.f, s1 = 0.f;
+  const long H4 = vec ? (H >> 2) : 0;
+  const float4 *xr4 = reinterpret_cast<const float4 *>(x), *xf4 = reinterpret_cast<const float4 *>(x + H);
+  float4 *ar4 = reinterpret_cast<float4 *>(a), *af4 = reinterpret_cast<float4 *>(a + H);
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < H4; i += (long)gridDim.x * 256) {
+    float4 r = __ldg(xr4 + i), f = __ldg(xf4 + i);
+    r.x = lk(r.x, slope); r.y = lk(r.y, slope); r.z = lk(r.z, slope); r.w = lk(r.w, slope);
+    f.x = lk(f.x, slope); f.y = lk(f.y, slope); f.z = lk(f.z, slope); f.w = lk(f.w, slope);
+    ar4[i] = r;
+    af4[i] = f;
+    s0 += fabsf(r.x - f.x) + fabsf(r.y - f.y) + fabsf(r.z - f.z) + fabsf(r.w - f.w);
+    s1 += fabsf(r.x) + fabsf(r.y) + fabsf(r.z) + fabsf(r.w);
+  }
+  for (long i = (H4 << 2) + blockIdx.x * 256L + threadIdx.x; i < H; i += (long)gridDim.x * 256) {
+    const float r = lk(x[i], slope), f = lk(x[H + i], slope);
+    a[i] = r;
+    a[H + i] = f;
+    s0 += fabsf(r - f);
+    s1 += fabsf(r);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red0[wid] = s0; red1[wid] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float u0 = 0.f, u1 = 0.f;
+    for (int i = 0; i < 8; ++i) { u0 += red0[i]; u1 += red1[i]; }
+    atomicAdd(stats, u0);
+    atomicAdd(stats + 1, u1);
+  }
+}
+
+__device__ __forceinline__ void leaky_fm_bwd_one(float ar, float af, float gr, float gf, float d0, float d1, float slope,
+                                                 float &or_, float &of_) {
+  const float s = d0 * sgnf(ar - af);
+  or_ = (gr + s + d1 * sgnf(ar)) * dlk(ar, slope);
+  of_ = (gf - s) * dlk(af, slope);
+}
+
+__global__ void __launch_bounds__(256)
+leaky_fm_bwd_kernel(const float *__restrict__ a, const float *__restrict__ g, const float *__restrict__ d,
+                    float *__restrict__ gx, long H, float slope, int vec) {
+  const float d0 = d ? d[0] : 0.f, d1 = d ? d[1] : 0.f;
+  const long H4 = vec ? (H >> 2) : 0;
+  const float4 *ar4 = reinterpret_cast<const float4 *>(a), *af4 = reinterpret_cast<const float4 *>(a + H);
+  const float4 *gr4 = reinterpret_cast<const float4 *>(g), *gf4 = reinterpret_cast<const float4 *>(g + H);
+  float4 *or4 = reinterpret_cast<float4 *>(gx), *of4 = reinterpret_cast<float4 *>(gx + H);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < H4; i += (long)gridDim.x * 256) {
+    const float4 r = __ldg(ar4 + i), f = __ldg(af4 + i);
+    const float4 pr = g ? __ldg(gr4 + i) : z, pf = g ? __ldg(gf4 + i) : z;
+    float4 o, q;
+    leaky_fm_bwd_one(r.x, f.x, pr.x, pf.x, d0, d1, slope, o.x, q.x);
+    leaky_fm_bwd_one(r.y, f.y, pr.y, pf.y, d0, d1, slope, o.y, q.y);
+    leaky_fm_bwd_one(r.z, f.z, pr.z, pf.z, d0, d1, slope, o.z, q.z);
+    leaky_fm_bwd_one(r.w, f.w, pr.w, pf.w, d0, d1, slope, o.w, q.w);
+    or4[i] = o;
+    of4[i] = q;
+  }
+  for (long i = (H4 << 2) + blockIdx.x * 256L + threadIdx.x; i < H; i += (long)gridDim.x * 256) {
+    float o, q;
+    leaky_fm_bwd_one(a[i], a[H + i], g ? g[i] : 0.f, g ? g[H + i] : 0.f, d0, d1, slope, o, q);
+    gx[i] = o;
+    gx[H + i] = q;
+  }
+}
+
+}  // namespace rave
+
+extern "C" int rave_leaky_fm_fwd(const float *x, float *a, float *stats, long H, float slope, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && a && stats && H > 0 && slope > 0.f, "leaky_fm_fwd: bad argument");
+  const int vec = (H % 4 == 0) && (((uintptr_t)x | (uintptr_t)a) & 15) == 0;
+  long blocks = ((vec ? H / 4 : H) + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+  leaky_fm_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, a, stats, H, slope, vec);
+  RAVE_CHECK_LAUNCH("leaky_fm_fwd");
+  return 0;
+}
+
+extern "C" int rave_leaky_fm_bwd(const float *a, const float *g, const float *d, float *gx, long H, float slope,
+                                 void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(a && gx && (g || d) && H > 0 && slope > 0.f, "leaky_fm_bwd: bad argument");
+  const int vec = (H % 4 == 0) && (((uintptr_t)a | (uintptr_t)gx | (uintptr_t)g) & 15) == 0;
+  long blocks = ((vec ? H / 4 : H) + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
+  leaky_fm_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a, g, d, gx, H, slope, vec);
+  RAVE_CHECK_LAUNCH("leaky_fm_bwd");
+  return 0;
+}

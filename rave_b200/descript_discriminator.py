@@ -117,6 +117,14 @@ class DiscConv2d(nn.Conv2d):
         return out
 
 
+def _feature_tap(out, slope, B):
+    """Post-activation feature of a chain output (rows = [real; fake] when the batch B is even): LeakyReLU and the two L1
+    feature-matching sums in one pass (ops.leaky_fm), or the plain activation for an unpaired batch."""
+    if B % 2 == 0 and out.dtype == torch.float32 and out.is_contiguous():
+        return ops.leaky_fm(out, slope)
+    return ops.activation(out, ops.ACT_LEAKY, slope), None
+
+
 class _ParamView:
     """Attribute holder standing in for a conv module inside a one-layer engine chain (engine._layer_params reads
     weight_v / weight_g / bias or weight / bias; the prepared-weight cache lives in its __dict__)."""
@@ -178,10 +186,11 @@ class MPD(nn.Module):
         for i, (s, o, Lo) in enumerate(zip(specs, outs, lens)):
             # features are POST-activation (descript_discriminator.py:59-61): one elementwise pass over the chain's own
             # [(b w), pitch, C] buffer (rows beyond Lo stay zero), the [B, C, L, W] feature is a VIEW of it
-            a = ops.activation(o, ops.ACT_LEAKY, self.convs[i][1].negative_slope) if i < len(self.convs) else o
+            a, st = _feature_tap(o, self.convs[i][1].negative_slope, B) if i < len(self.convs) else (o, None)
             h = a[:, :Lo, :s.Cout].unflatten(0, (B, W)).permute(0, 3, 2, 1)
             if i < len(self.convs) and not s.cout_pad:
-                h._cl_base = a          # dense buffer behind the view (core.feature_matching_halves)
+                h._cl_base = a          # dense buffer behind the view (core.mean_difference_halves)
+                h._fm_stats = st        # (sum |real - fake|, sum |real|) of this feature, when B is even
             fmap.append(h)
         return fmap
 
@@ -263,10 +272,11 @@ class MRD(nn.Module):
             for layer in stack:
                 conv = layer[0]
                 out = conv.forward_cl(cur)                                   # [(b t), Fo, 32]
-                a = ops.activation(out, ops.ACT_LEAKY, layer[1].negative_slope)
+                a, st = _feature_tap(out, layer[1].negative_slope, B)
                 cur = a.view(B, t, out.shape[1], out.shape[2])
                 feat = cur.permute(0, 3, 1, 2)
                 feat._cl_base = a
+                feat._fm_stats = st
                 fmap.append(feat)
             outs.append(cur)
         out = self.conv_post.forward_cl(torch.cat(outs, dim=2))              # [(b t), F, 16]: one score channel + padding

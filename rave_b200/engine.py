@@ -465,7 +465,11 @@ class TcChainFn(torch.autograd.Function):
         B = x_in.shape[0] * period
         ctx.c1_src = (period, pool, tuple(x_in.shape))
         ctx.B = B
-        ctx.fake_grad_only = bool(fake_grad_only) and fm
+        # backward on the fake half only (see backward): always available to the fused feature-matching chains, and to
+        # plain conv stacks (no residuals, no Snake: the Descript discriminator) whose caller asked for it
+        plain = all(s.kind == "conv" and s.res_src is None and s.res_opnd is None and s.res_raw is None
+                    and s.pre_act != ops.ACT_SNAKE for s in specs)
+        ctx.fake_grad_only = bool(fake_grad_only) and (fm or (plain and B % 2 == 0 and not x3))
         if c1 and not (specs[0].kind == "conv" and specs[0].Cin == 1 and specs[0].dil == 1):
             raise _lib.RaveB200Error("raw fp32 rows are only accepted by a Cin = 1 first conv")
         dev = x_in.device
@@ -694,7 +698,7 @@ class TcChainFn(torch.autograd.Function):
         else:
             for i, g in zip(ctx.out_index, gouts):
                 if g is not None:
-                    ext[i] = g.to(ACT_DTYPE).contiguous()
+                    ext[i] = half(g).to(ACT_DTYPE).contiguous()
         skip: Dict[int, torch.Tensor] = {}     # residual pass-through gradient for layer idx (or -1)
         g_cur: Optional[torch.Tensor] = None   # gradient (h-space) of layer i's output
         grads = [None] * len(flat)
@@ -852,7 +856,33 @@ class TcChainFn(torch.autograd.Function):
             for job, (dv, dg) in zip(wn_jobs, res):
                 i = job[0]
                 grads[3 * i], grads[3 * i + 1] = dv, dg
+        if fo and gx is not None and not ctx.c1 and gx.shape[0] == Bh:
+            full = torch.zeros((ctx.B,) + tuple(gx.shape[1:]), dtype=gx.dtype, device=gx.device)
+            full[Bh:] = gx                   # the real rows' gradient is identically unused: zeros
+            gx = full
         return (gx, None, None, None, None, None, None) + tuple(grads)
+
+
+_FAKE_ROWS_ONLY = False
+
+
+class fake_rows_only:
+    """Context: chains run inside it hold [real; fake] rows and their caller only ever uses the gradient reaching the
+    FAKE rows (generator step through a frozen discriminator, rave/model.py:348-379): their backward runs on that half.
+    No effect on chains with trainable parameters, residuals or Snake."""
+
+    def __init__(self, state: bool = True):
+        self.state = bool(state)
+
+    def __enter__(self):
+        global _FAKE_ROWS_ONLY
+        self.prev, _FAKE_ROWS_ONLY = _FAKE_ROWS_ONLY, self.state
+        return self
+
+    def __exit__(self, *exc):
+        global _FAKE_ROWS_ONLY
+        _FAKE_ROWS_ONLY = self.prev
+        return False
 
 
 def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int] = None, fm: bool = False,
@@ -868,7 +898,7 @@ def run_chain(x_cl_bf16: torch.Tensor, specs: List[LayerSpec], L0: Optional[int]
     flat += [s.pre_mod.alpha for s in specs if s.pre_act == ops.ACT_SNAKE]      # after the 3n weight entries
     if L0 is None:
         L0 = x_cl_bf16.shape[1]
-    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, src, fake_grad_only, x3, *flat)
+    return TcChainFn.apply(x_cl_bf16, specs, L0, fm, src, fake_grad_only or _FAKE_ROWS_ONLY, x3, *flat)
 
 
 def chain_lengths(specs: List[LayerSpec], L0: int) -> List[int]:

@@ -309,7 +309,11 @@ class RAVE(nn.Module):
         if fused is not None:
             feature_matching_distance, loss_dis, loss_adv, pred_real, pred_fake = fused
         elif self.warmed_up:
-            features = self.discriminator(xy)
+            from . import engine
+            # generator step: the discriminator is frozen and only the fake half's input gradient is used -> its
+            # engine chains run their backward on the fake rows only
+            with engine.fake_rows_only(not is_dis_step):
+                features = self.discriminator(xy)
             feature_real, feature_fake = self.split_features(features)
             loss_dis = 0
             loss_adv = 0
@@ -325,7 +329,10 @@ class RAVE(nn.Module):
                 terms = []
                 for full, real, fake in zip(scale[skip:], scale_real[skip:], scale_fake[skip:]):
                     base = getattr(full, "_cl_base", None) if on_bases else None
-                    if base is not None:
+                    st = getattr(full, "_fm_stats", None) if on_bases else None
+                    if st is not None:       # the sums came out of the feature's own activation pass (ops.leaky_fm)
+                        terms.append(st[0] / st[1] if kw.get("relative", False) else st[0] / real.numel())
+                    elif base is not None:
                         terms.append(core.mean_difference_halves(base, real.numel(), bool(kw.get("relative", False))))
                     else:
                         terms.append(self.feature_matching_fun(real, fake))

@@ -536,6 +536,39 @@ def l1_halves(base):
     return L1HalvesFn.apply(base)
 
 
+class LeakyFmFn(torch.autograd.Function):
+    """Feature tap of the Descript discriminator: x = a chain's fp32 output holding [real; fake] halves along dim 0 ->
+    (a = LeakyReLU(x), stats = (sum |a_r - a_f|, sum |a_r|)) in one pass; one backward pass folds the gradient of the
+    two sums, the gradient arriving at `a` and LeakyReLU' together (rave_leaky_fm_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, slope):
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.shape[0] % 2:
+            raise _lib.RaveB200Error("leaky_fm: contiguous fp32 buffer with an even leading dimension expected")
+        ctx.set_materialize_grads(False)
+        a = torch.empty_like(x)
+        stats = torch.zeros(2, dtype=torch.float32, device=x.device)
+        call("rave_leaky_fm_fwd", ptr(x), ptr(a), ptr(stats), x.numel() // 2, float(slope), stream_ptr())
+        ctx.save_for_backward(a)
+        ctx.slope = float(slope)
+        return a, stats
+
+    @staticmethod
+    def backward(ctx, ga, dstats):
+        (a,) = ctx.saved_tensors
+        if ga is None and dstats is None:
+            return None, None
+        ga = _f32c(ga)
+        dstats = _f32c(dstats)
+        gx = torch.empty_like(a)
+        call("rave_leaky_fm_bwd", ptr(a), ptr(ga), ptr(dstats), ptr(gx), a.numel() // 2, ctx.slope, stream_ptr())
+        return gx, None
+
+
+def leaky_fm(x, slope):
+    return LeakyFmFn.apply(x, slope)
+
+
 class L1StatsFn(torch.autograd.Function):
     """(sum |t - v|, sum |t|) of two fp32 CUDA tensors in one pass, gradient in one pass (rave_l1_stats_f32 / _grad)."""
 

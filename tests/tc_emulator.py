@@ -424,10 +424,17 @@ def activation(x, act, slope=0.2, alpha=None):
     return x
 
 
+def leaky_fm(x, slope):
+    """ops.leaky_fm: LeakyReLU + the L1 feature-matching sums of the [real; fake] halves, plain torch autograd here."""
+    a = F.leaky_relu(x, slope)
+    h = a.shape[0] // 2
+    return a, torch.stack([(a[:h] - a[h:]).abs().sum(), a[:h].abs().sum()])
+
+
 def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
                  "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1", "weight_prep_tc_multi",
                  "weight_norm_bwd_multi", "score_stats", "score_grad", "ncl_to_cl_x3", "dilated_unit_tc",
-                 "dilated_unit_tc_supported", "snake_cl_fwd", "snake_cl_bwd", "activation"):
+                 "dilated_unit_tc_supported", "snake_cl_fwd", "snake_cl_bwd", "activation", "leaky_fm"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -370,3 +370,41 @@ def test_static_prepared_weights_follow_refresh(emu):
         engine.disable_static_prep(net)
     engine.invalidate_prepared()
     assert torch.equal(run(), y1)                          # same as a cold preparation from the moved parameters
+
+
+def test_fake_rows_only_backward_on_a_frozen_plain_chain(emu):
+    """engine.fake_rows_only: a frozen plain conv chain over [real; fake] rows (Descript MPD in a generator step) runs
+    its backward on the fake half: same input gradient on the fake rows, zeros on the real rows; trainable parameters
+    switch the shortcut off; the feature-matching sums of the feature taps match torch."""
+    from rave_b200.descript_discriminator import MPD
+    from rave_b200 import engine
+    torch.manual_seed(9)
+    period = 2
+    mpd = MPD(period)
+    specs = mpd._tc_specs()
+    x = (0.5 * torch.randn(4, 1, 1200)).clamp(-1, 1)
+
+    def run(flag, frozen):
+        for p in mpd.parameters():
+            p.requires_grad_(not frozen)
+        xe = x.clone().requires_grad_(True)
+        xp = mpd.pad_to_period(xe)
+        with engine.fake_rows_only(flag):
+            feats = mpd._forward_tc(xp.reshape(xp.shape[0], 1, -1, period), specs)
+        loss = 0.
+        for f in feats[:-1]:
+            st = f._fm_stats
+            want = torch.stack([(f[:2] - f[2:]).abs().sum(), f[:2].abs().sum()])
+            assert rel_l2(st, want) < 1e-5
+            loss = loss + st[0] / f[:2].numel() + 0.1 * st[1] / f[:2].numel()
+        loss = loss - feats[-1][2:].mean()
+        (g,) = torch.autograd.grad(loss, xe)
+        return g
+    g_full = run(False, True)
+    g_half = run(True, True)
+    assert torch.count_nonzero(g_half[:2]) == 0 and torch.count_nonzero(g_full[:2]) > 0
+    assert rel_l2(g_half[2:], g_full[2:]) < 1e-6
+    g_train = run(True, False)                       # trainable parameters: the full backward runs
+    assert rel_l2(g_train, g_full) < 1e-6
+    for p in mpd.parameters():
+        p.requires_grad_(True)

@@ -195,36 +195,73 @@ def test_time_stack_nhwc_and_l1_halves_vs_torch():
 
 
 def test_descript_feature_matching_on_dense_buffers_matches_generic():
-    """model.compute_losses' feature matching on the `_cl_base` buffers == core.mean_difference on the split feature
-    views (values and the gradient reaching the discriminator input)."""
+    """model.compute_losses' feature matching from the feature taps' own sums (`_fm_stats`, ops.leaky_fm) and on the
+    `_cl_base` buffers == core.mean_difference on the split feature views (values and the gradient reaching the
+    discriminator input); engine.fake_rows_only (generator step, frozen discriminator) leaves the fake half's
+    gradient unchanged."""
     import rave_b200
-    from rave_b200 import core
+    from rave_b200 import core, engine
     from rave_b200.descript_discriminator import DescriptDiscriminator
     torch.manual_seed(2)
     dd = DescriptDiscriminator().cuda()
     x = (0.5 * torch.randn(4, 1, 16384, device="cuda")).clamp(-1, 1)
     rave_b200.set_precision("bf16")
     try:
-        res = []
-        for fast in (True, False):
+        res = {}
+        for mode in ("stats", "bases", "generic", "stats_fake_only"):
+            frozen = mode == "stats_fake_only"
+            for p in dd.parameters():
+                p.requires_grad_(not frozen)
             xg = x.clone().requires_grad_(True)
-            feats = dd(xg)
+            with engine.fake_rows_only(frozen):
+                feats = dd(xg)
             total = 0.
             n_bases = 0
             for scale in feats:
                 for f in scale[:-1]:
                     assert f.shape[0] == 4
-                    base = getattr(f, "_cl_base", None)
-                    n_bases += base is not None
-                    if fast and base is not None:
+                    base, st = getattr(f, "_cl_base", None), getattr(f, "_fm_stats", None)
+                    n_bases += base is not None and st is not None
+                    if mode.startswith("stats"):
+                        total = total + st[0] / (f.numel() // 2)
+                    elif mode == "bases":
                         total = total + core.mean_difference_halves(base, f.numel() // 2, False)
                     else:
                         total = total + core.mean_difference(f[:2], f[2:], "L1", False)
-                total = total + scale[-1].mean()          # the score: every chain's last layer needs a gradient
+                total = total - scale[-1][2:].mean()      # the score: every chain's last layer needs a gradient
             assert n_bases == 5 * 5 + 3 * 25
             (gx,) = torch.autograd.grad(total, xg)
-            res.append((total.detach(), gx))
+            res[mode] = (total.detach(), gx)
     finally:
         rave_b200.set_precision("fp32")
-    assert rel_l2(res[0][0], res[1][0]) < 1e-5
-    assert rel_l2(res[0][1], res[1][1]) < 1e-3          # bf16 gradient streams, different accumulation order
+        for p in dd.parameters():
+            p.requires_grad_(True)
+    for mode in ("stats", "bases", "stats_fake_only"):
+        assert rel_l2(res[mode][0], res["generic"][0]) < 1e-5, mode
+    # bf16 gradient streams, different accumulation order between the fused and the generic backward
+    assert rel_l2(res["stats"][1], res["generic"][1]) < 2e-3
+    assert rel_l2(res["bases"][1], res["generic"][1]) < 2e-3
+    assert rel_l2(res["stats_fake_only"][1][2:], res["stats"][1][2:]) < 1e-4
+    assert torch.count_nonzero(res["stats_fake_only"][1][:2]) == 0
+
+
+def test_leaky_fm_tap_vs_torch():
+    from rave_b200 import ops
+    torch.manual_seed(4)
+    for shape in [(6, 50, 32), (2, 7, 3), (4, 33, 16)]:
+        x = torch.randn(*shape, device="cuda")
+        x1 = x.clone().requires_grad_(True)
+        x2 = x.clone().requires_grad_(True)
+        a, st = ops.leaky_fm(x1, 0.1)
+        h = shape[0] // 2
+        a2 = torch.nn.functional.leaky_relu(x2, 0.1)
+        st2 = torch.stack([(a2[:h] - a2[h:]).abs().sum(), a2[:h].abs().sum()])
+        assert torch.equal(a, a2) and rel_l2(st, st2) < 1e-6
+        probe = torch.randn_like(a)
+        d = torch.tensor([0.7, -0.3], device="cuda")
+        for use_a, use_d in [(True, True), (True, False), (False, True)]:
+            l1 = (a * probe).sum() * use_a + (st * d).sum() * use_d
+            l2 = (a2 * probe).sum() * use_a + (st2 * d).sum() * use_d
+            (g1,) = torch.autograd.grad(l1, x1, retain_graph=True)
+            (g2,) = torch.autograd.grad(l2, x2, retain_graph=True)
+            assert torch.allclose(g1, g2, atol=1e-6), (shape, use_a, use_d)
