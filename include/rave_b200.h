@@ -132,6 +132,9 @@ int rave_act_bwd(const float *dy, const float *x, float *dx, float *dalpha, int 
 /* GeneratorV2 tail (rave/blocks.py:704-711): y[b][c][t] = tanh(x[b][c][t] * sigmoid(x[b][C+c][t])); x: [B][2C][L] */
 int rave_am_tanh_fwd(const float *x, float *y, int B, int C, int L, void *stream);
 int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int B, int C, int L, void *stream);
+/* VariationalEncoder.reparametrize (rave/blocks.py:725-737) in one pass: z [B][2C][L] = (mean | scale);
+ * zs[b][c][t] = eps * (softplus(scale) + 1e-4) + mean;  *kl_sum += sum (mean^2 + var - log var - 1)  (zero it first) */
+int rave_reparam_fwd(const float *z, const float *eps, float *zs, float *kl_sum, int B, int C, int L, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * tensor-core conv engine (tcgen05 + TMEM + TMA), implicit GEMM, time on the MMA M axis:

@@ -76,6 +76,28 @@ def mean_difference_halves(base, n_true: int, relative: bool = False):
     return st[0] / st[1] if relative else st[0] / n_true
 
 
+_STACKED_WEIGHTS = {}
+
+
+def stacked_l1_terms(tapped, relative: bool = False):
+    """sum_i w_i * mean_difference_i for features whose (sum |real - fake|, sum |real|) pairs already exist:
+    `tapped` = [(sums[2], n_true, w)].  One stack, one multiply (or divide + multiply), one sum -- instead of a scalar
+    division and an addition (and their backward launches) per feature.  The constant weight vector lives on the device,
+    built once per (device, weights) outside any stream capture."""
+    S = torch.stack([t[0] for t in tapped])                                  # [n, 2]
+    key = (str(S.device), bool(relative), tuple((int(t[1]), float(t[2])) for t in tapped))
+    w = _STACKED_WEIGHTS.get(key)
+    if w is None:
+        if S.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("stacked_l1_terms: first call for these features inside a stream capture (run one eager "
+                               "step first: the weight vector is uploaded once)")
+        vals = [t[2] if relative else t[2] / t[1] for t in tapped]
+        w = _STACKED_WEIGHTS[key] = torch.tensor(vals, dtype=torch.float64).to(S.dtype).to(S.device)
+    if relative:
+        return ((S[:, 0] / S[:, 1]) * w).sum()
+    return (S[:, 0] * w).sum()
+
+
 class _StftWindow(nn.Module):
     """Holder of one scale's hann window (`stfts.<i>.window`, the key torchaudio.transforms.Spectrogram contributes)."""
 

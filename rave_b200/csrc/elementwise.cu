@@ -163,6 +163,28 @@ am_tanh_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, fl
   }
 }
 
+// VariationalEncoder.reparametrize (rave/blocks.py:725-737), one pass: z [B][2C][L] = (mean | scale),
+//   std = softplus(scale) + 1e-4, zs = eps * std + mean, kl_sum += sum (mean^2 + std^2 - log(std^2) - 1)
+// (the reference's ~14 elementwise / reduction launches on a 0.26 M element tensor).  kl_sum must be zeroed by the caller.
+__global__ void __launch_bounds__(256)
+reparam_fwd_kernel(const float *__restrict__ z, const float *__restrict__ eps, float *__restrict__ zs,
+                   float *__restrict__ kl_sum, long CL, long total) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const long b = i / CL;
+    const long zo = i + b * CL;                       // b * 2CL + (i - b * CL)
+    const float mean = z[zo], scale = z[zo + CL];
+    const float sp = scale > 20.f ? scale : log1pf(expf(scale));      // F.softplus (beta 1, threshold 20)
+    const float sd = sp + 1e-4f;
+    const float var = sd * sd;
+    zs[i] = eps[i] * sd + mean;
+    acc += mean * mean + var - logf(var) - 1.f;
+  }
+  const float tot = block_reduce_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(kl_sum, tot);
+}
+
 // y = bf16(act(x)); grid (ceil(L/2048), C, B), 2 elements per thread-iteration
 __global__ void __launch_bounds__(256)
 act_to_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, int C, int L, int act,
@@ -277,6 +299,19 @@ extern "C" int rave_am_tanh_bwd(const float *dy, const float *x, float *dx, int 
   if (blocks > 148 * 16) blocks = 148 * 16;
   am_tanh_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, dx, C, L, total);
   RAVE_CHECK_LAUNCH("am_tanh_bwd");
+  return 0;
+}
+
+extern "C" int rave_reparam_fwd(const float *z, const float *eps, float *zs, float *kl_sum, int B, int C, int L,
+                                void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(z && eps && zs && kl_sum && B > 0 && C > 0 && L > 0, "reparam_fwd: bad argument");
+  const long total = (long)B * C * L;
+  int blocks = (int)((total + 1023) / 1024);            // ~4 elements per thread: few atomics, still every SM busy
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  reparam_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, eps, zs, kl_sum, (long)C * L, total);
+  RAVE_CHECK_LAUNCH("reparam_fwd");
   return 0;
 }
 

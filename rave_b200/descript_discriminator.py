@@ -63,20 +63,32 @@ class DiscConv2d(nn.Conv2d):
         proxy = self.__dict__.get("_tc_proxy")
         if proxy is None:
             proxy = self.__dict__["_tc_proxy"] = _ParamView()
+            if self.__dict__.get("_tc_proxy_static"):       # engine.enable_static_prep ran before the first forward
+                proxy.__dict__["_tc_static"] = {}
             spec = engine.LayerSpec("conv", proxy, cin, self.out_channels, kf, self.stride[1], 1, (pf, pf),
                                     ops.ACT_NONE, 0.0, None, True, True)
             spec.cin_pad = (-cin) % 16
             spec.cout_pad = (-self.out_channels) % 16
             self.__dict__["_tc_spec"] = spec
         spec = self.__dict__["_tc_spec"]
+        if spec.Cin != cin:
+            raise _lib.RaveB200Error(f"DiscConv2d: planned for {spec.Cin // kt} input channels, called with {C}")
+        self._tc_refresh_proxy()
+        return spec
+
+    def _tc_refresh_proxy(self):
+        """(Re)build the proxy's (dt, c)-ordered views of the parameters (a permuted reshape is a copy: it goes stale
+        when the parameters move, so engine.refresh_static_prep calls this before it rewrites the static layouts)."""
+        proxy = self.__dict__["_tc_proxy"]
+        kf = self.kernel_size[1]
         co = self.out_channels
+        cin = self.__dict__["_tc_spec"].Cin
         if hasattr(self, "weight_v"):
             proxy.weight_v = self.weight_v.permute(0, 2, 1, 3).reshape(co, cin, kf)
             proxy.weight_g = self.weight_g.reshape(co, 1, 1)
         else:
             proxy.weight = self.weight.permute(0, 2, 1, 3).reshape(co, cin, kf)
         proxy.bias = self.bias
-        return spec
 
     def _forward_tc(self, x, B, C, T, Fq):
         """bf16 mode: the same conv along frequency as a one-layer chain of the tcgen05 engine (forward, dgrad and wgrad

@@ -325,15 +325,31 @@ class _PreparedWeights:
 # are, and that `refresh_static_prep` rewrites IN PLACE right after the discriminator's optimiser step (inside the
 # D-step graph).  Whoever changes those parameters some other way (load_state_dict, an eager optimiser) must refresh.
 
+def _static_holders(root: nn.Module):
+    """Modules under `root` that own prepared weights, plus the parameter-view proxies of one-layer chains (the MRD's
+    DiscConv2d plans its conv on a `_ParamView` holding permuted views of its parameters: descript_discriminator.py)."""
+    for m in root.modules():
+        yield m
+        proxy = m.__dict__.get("_tc_proxy")
+        if proxy is not None:
+            yield proxy
+
+
 def enable_static_prep(root: nn.Module) -> None:
     for m in root.modules():
         if hasattr(m, "weight_v") or (hasattr(m, "weight") and isinstance(getattr(m, "weight"), nn.Parameter)):
             m.__dict__.setdefault("_tc_static", {})
+            if hasattr(m, "_tc_chain_spec"):          # proxy of a one-layer chain: created lazily, marked here or there
+                m.__dict__["_tc_proxy_static"] = True
+                proxy = m.__dict__.get("_tc_proxy")
+                if proxy is not None:
+                    proxy.__dict__.setdefault("_tc_static", {})
 
 
 def disable_static_prep(root: nn.Module) -> None:
-    for m in root.modules():
+    for m in _static_holders(root):
         m.__dict__.pop("_tc_static", None)
+        m.__dict__.pop("_tc_proxy_static", None)
 
 
 @torch.no_grad()
@@ -341,6 +357,9 @@ def refresh_static_prep(root: nn.Module) -> int:
     """Recompute every static prepared layout under `root` into its existing buffers; returns how many."""
     items, into, extra = {False: [], True: []}, {False: [], True: []}, []
     for m in root.modules():
+        if "_tc_proxy" in m.__dict__ and m.__dict__["_tc_proxy"].__dict__.get("_tc_static"):
+            m._tc_refresh_proxy()        # the proxy's permuted parameter copies are stale once the parameters moved
+    for m in _static_holders(root):
         st = m.__dict__.get("_tc_static")
         if not st:
             continue
@@ -703,6 +722,7 @@ class TcChainFn(torch.autograd.Function):
         g_cur: Optional[torch.Tensor] = None   # gradient (h-space) of layer i's output
         grads = [None] * len(flat)
         gx = None
+        gx_full = None
         wn_jobs = []       # (layer, dwt partials, v, g, norm): one multi-tensor launch at the end
         # bias gradients accumulated by the wgrad kernels: ONE zero-filled buffer for the whole chain
         db_off, db_total = {}, 0
@@ -812,7 +832,14 @@ class TcChainFn(torch.autograd.Function):
                 gx = ops.gather_c1(P, src_shape, Lin, Lout, s.K, s.stride, s.pad[0], period, pool,
                                    batch0=src_shape[0] // 2 if fo else 0)
                 break
-            gp = torch.empty(B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)
+            if fo and i == 0:
+                # fake-rows-only backward: the chain's input gradient is [zeros; gx_fake] -- the last dgrad writes its
+                # rows straight into the second half of the full buffer (no zeros + copy pass afterwards)
+                gx_full = torch.empty(ctx.B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)
+                gx_full[:Bh].zero_()
+                gp = gx_full[Bh:]
+            else:
+                gp = torch.empty(B, in_pitch, cin_p, dtype=ACT_DTYPE, device=g.device)
             if in_pitch > Lin:
                 gp[:, Lin:].zero_()
             if s.kind == "conv":
@@ -857,9 +884,12 @@ class TcChainFn(torch.autograd.Function):
                 i = job[0]
                 grads[3 * i], grads[3 * i + 1] = dv, dg
         if fo and gx is not None and not ctx.c1 and gx.shape[0] == Bh:
-            full = torch.zeros((ctx.B,) + tuple(gx.shape[1:]), dtype=gx.dtype, device=gx.device)
-            full[Bh:] = gx                   # the real rows' gradient is identically unused: zeros
-            gx = full
+            if gx_full is not None and gx.data_ptr() == gx_full[Bh:].data_ptr() and gx.shape == gx_full[Bh:].shape:
+                gx = gx_full                 # the real rows' gradient is identically unused: zeros
+            else:
+                full = torch.zeros((ctx.B,) + tuple(gx.shape[1:]), dtype=gx.dtype, device=gx.device)
+                full[Bh:] = gx
+                gx = full
         return (gx, None, None, None, None, None, None) + tuple(grads)
 
 

@@ -325,25 +325,32 @@ class RAVE(nn.Module):
             on_bases = (kw is not None and getattr(self.feature_matching_fun, "func", None) is core.mean_difference
                         and kw.get("norm", "L1") == "L1")
             skip = self.num_skipped_features
+            # features whose two L1 sums came out of their own activation pass (ops.leaky_fm): all of them are turned
+            # into terms by ONE stacked division + weighted sum (a Descript discriminator has ~100 such features:
+            # one scalar division, one addition and their backward launches each, otherwise)
+            tapped = []
             for scale, scale_real, scale_fake in zip(features, feature_real, feature_fake):
                 terms = []
+                n_terms = len(scale[skip:])
                 for full, real, fake in zip(scale[skip:], scale_real[skip:], scale_fake[skip:]):
                     base = getattr(full, "_cl_base", None) if on_bases else None
                     st = getattr(full, "_fm_stats", None) if on_bases else None
-                    if st is not None:       # the sums came out of the feature's own activation pass (ops.leaky_fm)
-                        terms.append(st[0] / st[1] if kw.get("relative", False) else st[0] / real.numel())
+                    if st is not None:
+                        tapped.append((st, real.numel(), 1.0 / (n_terms * len(feature_real))))
                     elif base is not None:
                         terms.append(core.mean_difference_halves(base, real.numel(), bool(kw.get("relative", False))))
                     else:
                         terms.append(self.feature_matching_fun(real, fake))
-                current = sum(terms) / len(terms)
-                feature_matching_distance = feature_matching_distance + current
+                if terms:
+                    feature_matching_distance = feature_matching_distance + sum(terms) / (n_terms * len(feature_real))
                 _dis, _adv = self.gan_loss(scale_real[-1], scale_fake[-1])
                 pred_real = pred_real + scale_real[-1].mean()
                 pred_fake = pred_fake + scale_fake[-1].mean()
                 loss_dis = loss_dis + _dis
                 loss_adv = loss_adv + _adv
-            feature_matching_distance = feature_matching_distance / len(feature_real)
+            if tapped:
+                feature_matching_distance = feature_matching_distance + core.stacked_l1_terms(
+                    tapped, bool(kw.get("relative", False)))
         else:
             pred_real = torch.tensor(0.).to(x_raw)
             pred_fake = torch.tensor(0.).to(x_raw)

@@ -255,6 +255,39 @@ class AmTanhFn(torch.autograd.Function):
         return dx
 
 
+class ReparamFn(torch.autograd.Function):
+    """VariationalEncoder.reparametrize (rave/blocks.py:725-737) as one library pass: (zs, kl_sum) from z = (mean | scale)
+    and eps; kl_sum = sum over every element of mean^2 + var - log var - 1.  The backward (phase 1 only: phase 2 detaches
+    z) is the closed form on the saved inputs."""
+
+    @staticmethod
+    def forward(ctx, z, eps):
+        z, eps = _f32c(z), _f32c(eps)
+        B, C2, L = z.shape
+        C = C2 // 2
+        zs = torch.empty(B, C, L, dtype=torch.float32, device=z.device)
+        kl_sum = torch.zeros((), dtype=torch.float32, device=z.device)
+        call("rave_reparam_fwd", ptr(z), ptr(eps), ptr(zs), ptr(kl_sum), B, C, L, stream_ptr())
+        ctx.save_for_backward(z, eps)
+        return zs, kl_sum
+
+    @staticmethod
+    def backward(ctx, g_zs, g_kl):
+        z, eps = ctx.saved_tensors
+        mean, scale = z.chunk(2, 1)
+        std = torch.nn.functional.softplus(scale) + 1e-4
+        d_mean = torch.zeros_like(mean) if g_zs is None else g_zs.clone()
+        d_std = torch.zeros_like(mean) if g_zs is None else g_zs * eps
+        if g_kl is not None:
+            d_mean = d_mean + g_kl * 2.0 * mean
+            d_std = d_std + g_kl * (2.0 * std - 2.0 / std)
+        return torch.cat([d_mean, d_std * torch.sigmoid(scale)], 1), None
+
+
+def reparam(z, eps):
+    return ReparamFn.apply(z, eps)
+
+
 def am_tanh(x):
     """tanh(x[:, :C] * sigmoid(x[:, C:])) -- GeneratorV2 tail, rave/blocks.py:704-711."""
     return AmTanhFn.apply(x)

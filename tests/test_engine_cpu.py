@@ -372,6 +372,45 @@ def test_static_prepared_weights_follow_refresh(emu):
     assert torch.equal(run(), y1)                          # same as a cold preparation from the moved parameters
 
 
+def test_static_prepared_weights_of_a_one_layer_proxy_chain(emu):
+    """The MRD's DiscConv2d plans its conv on a proxy holding permuted COPIES of its parameters: static preparation must
+    reach that proxy (enabled before or after the first forward) and the refresh must rebuild the copies first."""
+    from rave_b200 import engine
+    from rave_b200.descript_discriminator import WNConv2d
+    if emu != "bf16":
+        pytest.skip("static prepared weights exist for the bf16 operand mode only")
+    torch.manual_seed(11)
+    for enable_first in (True, False):
+        conv = WNConv2d(32, 32, (3, 9), (1, 2), padding=(1, 4))[0]
+        root = torch.nn.Sequential(conv)
+        xs = torch.randn(6, 40, 96).to(engine.ACT_DTYPE)
+
+        def run():
+            with torch.no_grad():
+                (out,) = engine.run_chain(xs, [conv._tc_chain_spec(32)], 40)
+            return out.clone()
+        if enable_first:
+            engine.enable_static_prep(root)
+            y0 = run()
+        else:
+            y0 = run()
+            engine.enable_static_prep(root)
+        try:
+            assert torch.equal(run(), y0)
+            assert conv.__dict__["_tc_proxy"].__dict__.get("_tc_static"), "the proxy holds the static layouts"
+            with torch.no_grad():
+                conv.weight_v.mul_(torch.linspace(0.5, 2.0, 9).view(1, 1, 1, 9))
+                conv.weight_g.mul_(1.5)
+            assert torch.equal(run(), y0)                  # parameters moved, the static buffers did not
+            assert engine.refresh_static_prep(root) == 1
+            y1 = run()
+            assert not torch.equal(y1, y0)
+        finally:
+            engine.disable_static_prep(root)
+        engine.invalidate_prepared()
+        assert torch.equal(run(), y1)                      # same as a cold preparation from the moved parameters
+
+
 def test_fake_rows_only_backward_on_a_frozen_plain_chain(emu):
     """engine.fake_rows_only: a frozen plain conv chain over [real; fake] rows (Descript MPD in a generator step) runs
     its backward on the fake half: same input gradient on the fake rows, zeros on the real rows; trainable parameters
@@ -408,3 +447,28 @@ def test_fake_rows_only_backward_on_a_frozen_plain_chain(emu):
     assert rel_l2(g_train, g_full) < 1e-6
     for p in mpd.parameters():
         p.requires_grad_(True)
+
+
+def test_fake_rows_only_backward_of_a_plain_operand_chain(emu):
+    """Chains whose first layer reads a bf16 operand (the MRD's one-layer chains): under engine.fake_rows_only the last
+    dgrad writes the fake rows' gradient straight into the second half of the full [zeros; fake] buffer."""
+    from rave_b200 import engine
+    from rave_b200.descript_discriminator import WNConv2d
+    torch.manual_seed(13)
+    for stride in (1, 2):
+        conv = WNConv2d(32, 32, (3, 9), (1, stride), padding=(1, 4))[0]
+        for p in conv.parameters():
+            p.requires_grad_(False)
+        xs0 = torch.randn(8, 40, 96).to(engine.ACT_DTYPE)
+        probe = torch.randn(8, engine.chain_lengths([conv._tc_chain_spec(32)], 40)[0], 32)
+
+        def run(flag):
+            xs = xs0.clone().requires_grad_(True)
+            with engine.fake_rows_only(flag):
+                (out,) = engine.run_chain(xs, [conv._tc_chain_spec(32)], 40)
+            (g,) = torch.autograd.grad((out[:, :probe.shape[1]] * probe).sum(), xs)
+            return g.float()
+        g_full, g_half = run(False), run(True)
+        assert g_half.shape == g_full.shape
+        assert torch.count_nonzero(g_half[:4]) == 0 and torch.count_nonzero(g_full[:4]) > 0
+        assert torch.equal(g_half[4:], g_full[4:])

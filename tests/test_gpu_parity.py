@@ -203,6 +203,31 @@ def test_weight_norm_fwd_bwd():
         assert rel_l2(dvg, dvo) < 1e-5 and rel_l2(dgg, dgo) < 1e-5
 
 
+def test_reparametrize_kernel_vs_reference_formula():
+    """VariationalEncoder.reparametrize on the device (one library pass, rave_reparam_fwd) against the reference's
+    formula (rave/blocks.py:725-737) evaluated on the CPU: sample, KL term and the gradients of both."""
+    from rave_b200.blocks import VariationalEncoder
+    torch.manual_seed(5)
+    ve = VariationalEncoder(lambda n_channels=1: torch.nn.Identity(), beta=0.7)
+    for shape in [(2, 32, 100), (3, 256, 32), (1, 6, 5)]:
+        z = 3.0 * torch.randn(*shape)
+        z[0, shape[1] // 2:, 0] = 25.0                                   # softplus threshold branch
+        eps = torch.randn(shape[0], shape[1] // 2, shape[2])
+        zo = z.clone().requires_grad_(True)
+        mean, scale = zo.chunk(2, 1)
+        std = torch.nn.functional.softplus(scale) + 1e-4
+        var = std * std
+        so = eps * std + mean
+        klo = 0.7 * (mean * mean + var - torch.log(var) - 1).sum(1).mean()
+        probe = torch.randn_like(so)
+        (go,) = torch.autograd.grad((so * probe).sum() + 1.3 * klo, zo)
+        zg = z.cuda().requires_grad_(True)
+        sg, klg = ve.reparametrize(zg, eps.cuda())
+        (gg,) = torch.autograd.grad((sg * probe.cuda()).sum() + 1.3 * klg, zg)
+        assert rel_l2(sg, so) < 1e-6 and abs(float(klg) - float(klo)) < 2e-6 * abs(float(klo))
+        assert rel_l2(gg, go) < 1e-5
+
+
 def test_am_tanh_and_snake():
     from rave_b200 import ops
     x = torch.randn(2, 32, 100)

@@ -167,3 +167,37 @@ def test_rave_model_builds_and_schedules():
     b = rave_b200.BetaWarmupCallback(initial_value=1e-6, target_value=5e-2, warmup_len=20000)
     b.on_train_batch_start(None, m, None, 0)
     assert 1e-6 < m.beta_factor < 1.1e-6
+
+
+def test_stacked_l1_terms_match_the_per_feature_loop():
+    """core.stacked_l1_terms (the Descript feature taps' sums turned into feature-matching terms by one stacked pass)
+    == the reference's per-feature loop: mean over a scale's features of mean|r - f| (/ mean|r|), mean over scales
+    (rave/model.py:353-361, rave/core.py:220-252)."""
+    import torch
+    from rave_b200 import core
+    torch.manual_seed(0)
+    scales = [[(torch.randn(2, 5, 7), torch.randn(2, 5, 7)) for _ in range(n)] for n in (3, 5, 2)]
+    for relative in (False, True):
+        leaves, tapped = [], []
+        want = 0.
+        for feats in scales:
+            terms = []
+            for r, f in feats:
+                r1, f1 = r.clone().requires_grad_(True), f.clone().requires_grad_(True)
+                leaves += [r1, f1]
+                st = torch.stack([(r1 - f1).abs().sum(), r1.abs().sum()])
+                tapped.append((st, r.numel(), 1.0 / (len(feats) * len(scales))))
+                terms.append(core.mean_difference(r, f, "L1", relative))
+            want = want + sum(terms) / len(terms)
+        want = want / len(scales)
+        got = core.stacked_l1_terms(tapped, relative)
+        assert abs(float(got) - float(want)) < 1e-6 * abs(float(want))
+        grads = torch.autograd.grad(got, leaves)
+        k = 0
+        for feats in scales:
+            for r, f in feats:
+                r2, f2 = r.clone().requires_grad_(True), f.clone().requires_grad_(True)
+                t = core.mean_difference(r2, f2, "L1", relative) / (len(feats) * len(scales))
+                gr, gf = torch.autograd.grad(t, [r2, f2])
+                assert torch.allclose(grads[k], gr, atol=1e-7) and torch.allclose(grads[k + 1], gf, atol=1e-7)
+                k += 2
