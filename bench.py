@@ -327,6 +327,25 @@ def profile_step(torch, model, x, pk):
     return out
 
 
+def _disc_on_engine(disc, x_dev):
+    """True when every sub-discriminator runs as tcgen05 chains: the v2 nets through the fused feature-matching path, the
+    Descript MPDs as one chain each and the MRD convs as one-layer chains (rave_b200/descript_discriminator.py)."""
+    if hasattr(disc, "supports_fused_fm"):
+        return bool(disc.supports_fused_fm(x_dev))
+    subs = getattr(disc, "discriminators", None)
+    if subs is None:
+        return False
+    ok = True
+    for d in subs:
+        if hasattr(d, "_tc_specs"):                        # Descript MPD
+            ok = ok and d._tc_specs() is not None
+        elif hasattr(d, "band_convs"):                     # Descript MRD
+            ok = ok and d.conv_post.tc_ready(x_dev, 32) and d.band_convs[0][0][0].cout_ok()
+        else:
+            ok = False
+    return bool(ok)
+
+
 def dominant_launch_roofline(torch, prof, pk):
     """`roofline`: the tcgen05 launch shape with the largest share of the step (3 G-steps + 1 D-step per cycle),
     re-timed alone over rotating buffers (> L2), against max(bytes / HBM, flops / tensor) of THAT launch."""
@@ -546,7 +565,7 @@ def run_ours(args):
         model.on_train_batch_end()
     barrier()
 
-    # which parts actually ran on the tcgen05 engine (v3's Snake chains and the Descript discriminator do not)
+    # which parts actually ran on the tcgen05 engine
     on_engine = None
     try:
         if prec == "bf16" and model is not None:
@@ -554,8 +573,7 @@ def run_ours(args):
             on_engine = dict(
                 encoder=bool(enc_net is not None and enc_net._tc_plan() is not None),
                 decoder=bool(model.decoder.net._tc_plan() is not None),
-                discriminator=bool(hasattr(model.discriminator, "supports_fused_fm")
-                                   and model.discriminator.supports_fused_fm(x_dev)))
+                discriminator=_disc_on_engine(model.discriminator, x_dev))
     except Exception:
         on_engine = None
     # ---- device-resident timed region -------------------------------------------------------

@@ -718,6 +718,54 @@ __global__ void __launch_bounds__(256) mt_prep_kernel(const __grid_constant__ Mt
   }
 }
 
+// Shared-memory variant (default when a row fits): the split-K partials are read coalesced along c1 and transposed
+// into the parameter's own (c1, k) order in SHARED memory, so that v is read and dv written with unit stride, once.  The
+// global-memory version below walks v / dv with stride K (K = 15: 60 sectors per warp access for 128 useful bytes) and
+// writes dv twice: 0.84 ms of a D-step at ~0.65 TB/s.  Index padding i + i/32 keeps the transposing store conflict-free
+// for K = 4, 8, 16 as well as for the odd kernel sizes.
+__device__ __forceinline__ int wn_pad(int i) { return i + (i >> 5); }
+
+__global__ void __launch_bounds__(1024) mt_wn_bwd_smem_kernel(const __grid_constant__ MtTable t) {
+  extern __shared__ float sh[];
+  __shared__ float red[32];
+  const int li = mt_find_row(t, blockIdx.x);
+  const MtLayer &L = t.L[li];
+  if (!L.dwt) return;
+  const int c0 = blockIdx.x - L.row_begin;
+  const int C1 = L.C1, K = L.K, C0p = L.C0p, C1p = L.C1p;
+  const int R = C1 * K;
+  const float *vr = L.v + (size_t)c0 * R;
+  float *dr = L.dv + (size_t)c0 * R;
+  const int wide = L.wide > 1 ? L.wide : 1;
+  const size_t split_stride = (size_t)(L.wide > 1 ? L.J : K) * C0p * C1p * wide;
+  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+    const int k = j / C1, c1 = j - k * C1;
+    const int slot = L.wide > 1 ? (int)L.tapsA[k] : k;
+    const float *src = L.dwt + ((size_t)(slot / wide) * C0p + c0) * ((size_t)C1p * wide) + (size_t)(slot % wide) * C1p + c1;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int sp = 0;
+    for (; sp + 8 <= L.splits; sp += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += __ldg(src + (size_t)(sp + u) * split_stride);
+    }
+    for (; sp < L.splits; ++sp) acc[sp & 7] += __ldg(src + (size_t)sp * split_stride);
+    sh[wn_pad(c1 * K + k)] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  }
+  __syncthreads();
+  if (!L.g) {
+    for (int i = threadIdx.x; i < R; i += blockDim.x) dr[i] = sh[wn_pad(i)];
+    return;
+  }
+  float s = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) s = fmaf(sh[wn_pad(i)], vr[i], s);
+  const float dot = block_reduce_sum(s, red);
+  const float n = L.norm[c0];
+  const float gn = L.g[c0] / n;
+  const float coef = dot / (n * n);
+  for (int i = threadIdx.x; i < R; i += blockDim.x) dr[i] = gn * (sh[wn_pad(i)] - vr[i] * coef);
+  if (threadIdx.x == 0) L.dg[c0] = dot / n;
+}
+
 // block size: RAVE_WN_THREADS (default 256; 1024 threads per row measured slower in the step: 10.39 vs 9.98 ms)
 __global__ void __launch_bounds__(1024) mt_wn_bwd_kernel(const __grid_constant__ MtTable t) {
   __shared__ float red[32];
@@ -945,7 +993,7 @@ extern "C" int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers,
   MtTable t;
   memset(&t, 0, sizeof(t));
   t.n = n;
-  int rows = 0;
+  int rows = 0, max_row = 0;
   for (int i = 0; i < n; ++i) {
     const rave_wprep_layer &h = layers[i];
     RAVE_CHECK_ARG(h.v && h.dwt && h.dv && h.C0 > 0 && h.C1 > 0 && h.K > 0 && h.splits >= 1 && (!h.g || (h.norm && h.dg)),
@@ -964,12 +1012,26 @@ extern "C" int rave_weight_norm_bwd_multi(int n, const rave_wprep_layer *layers,
     }
     L.row_begin = rows;
     rows += h.C0;
+    if (h.C1 * h.K > max_row) max_row = h.C1 * h.K;
   }
   t.total_rows = rows;
-  static int wn_threads = 0;
+  static int wn_threads = 0, wn_smem = -1;
   if (!wn_threads) {
     const char *e = getenv("RAVE_WN_THREADS");
     wn_threads = (e && atoi(e) >= 64 && atoi(e) <= 1024) ? atoi(e) / 32 * 32 : 256;
+    const char *m = getenv("RAVE_WN_SMEM");             // 0: the global-memory kernel (debug / ablation)
+    wn_smem = (m && atoi(m) == 0) ? 0 : 1;
+  }
+  const size_t smem = (size_t)(max_row + (max_row >> 5) + 1) * sizeof(float);
+  if (wn_smem && smem <= 96 * 1024) {                    // a row of <= ~23.8 k weights; >= 2 CTAs per SM
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(mt_wn_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    mt_wn_bwd_smem_kernel<<<rows, wn_threads, smem, (cudaStream_t)stream>>>(t);
+    RAVE_CHECK_LAUNCH("mt_wn_bwd_smem");
+    return 0;
   }
   mt_wn_bwd_kernel<<<rows, wn_threads, 0, (cudaStream_t)stream>>>(t);
   RAVE_CHECK_LAUNCH("mt_wn_bwd");

@@ -22,6 +22,20 @@ import torch
 from . import _lib, engine
 
 
+def _encoder_is_frozen(model) -> bool:
+    from .blocks import VariationalEncoder
+    enc = model.encoder
+    # compute_losses sets the encoder's own flag from model.warmed_up before every forward
+    return isinstance(enc, VariationalEncoder) and bool(model.warmed_up)
+
+
+def _refresh_static_after_load(m, keys):
+    if getattr(m, "_static_disc_prep", False):
+        engine.refresh_static_prep(m.discriminator)
+    if getattr(m, "_static_enc_prep", False):
+        engine.refresh_static_prep(m.encoder)
+
+
 class GraphedTrainer:
     def __init__(self, model, example_batch: torch.Tensor, grad_hook=None, warmup_steps: int = 3):
         if not example_batch.is_cuda:
@@ -38,13 +52,17 @@ class GraphedTrainer:
         # the discriminator only changes in D-steps: its prepared weights become persistent buffers, rewritten in place
         # after the discriminator's optimiser step (inside the D-step graph) instead of being rebuilt by every replay
         self.static_prep = engine.precision() == "bf16"
+        # phase 2 of a VariationalEncoder model: the encoder output is detached (rave/blocks.py:739-743), no gradient
+        # ever reaches the encoder, Adam skips it -- its prepared weights are constants of the captured graphs too
+        self.static_encoder = bool(self.static_prep and _encoder_is_frozen(model))
         if self.static_prep:
             engine.enable_static_prep(model.discriminator)
             model._static_disc_prep = True
+            if self.static_encoder:
+                engine.enable_static_prep(model.encoder)
+                model._static_enc_prep = True
             if not getattr(model, "_static_prep_hook", None):
-                model._static_prep_hook = model.register_load_state_dict_post_hook(
-                    lambda m, keys: engine.refresh_static_prep(m.discriminator)
-                    if getattr(m, "_static_disc_prep", False) else None)
+                model._static_prep_hook = model.register_load_state_dict_post_hook(_refresh_static_after_load)
         snap_tensors = [(t, t.detach().clone()) for t in list(model.parameters()) + list(model.buffers())]
         snap_opt = [(o, copy.deepcopy(o.state_dict())) for o in (gen_opt, dis_opt)]
         self.graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
@@ -93,6 +111,8 @@ class GraphedTrainer:
         engine.invalidate_prepared()
         if self.static_prep:
             engine.refresh_static_prep(model.discriminator)      # the restore above moved the parameters
+            if self.static_encoder:
+                engine.refresh_static_prep(model.encoder)
 
     def step(self, batch: torch.Tensor, batch_idx: int):
         """Same contract as RAVE.training_step: returns the logged scalars (device tensors)."""

@@ -252,6 +252,11 @@ class RAVE(nn.Module):
         """Forward part of training_step (rave/model.py:292-399).  Returns (loss_gen dict, loss_dis,
         aux)."""
         batch_size = x_raw.shape[:-2]
+        if getattr(self, "_static_enc_prep", False) and not self.warmed_up:
+            # back in phase 1 after a GraphedTrainer froze the encoder's prepared weights: the encoder trains again
+            from . import engine
+            engine.disable_static_prep(self.encoder)
+            self._static_enc_prep = False
         self.encoder.set_warmed_up(self.warmed_up)
         self.decoder.set_warmed_up(self.warmed_up)
 

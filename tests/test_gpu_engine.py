@@ -161,6 +161,7 @@ def test_cuda_graph_training_matches_eager(streams, monkeypatch):
     for m in (m1, m2):
         m.encoder.reparametrize = (lambda z, eps=None, enc=m.encoder: type(enc).reparametrize(enc, z, torch.zeros_like(z[:, :z.shape[1] // 2])))
     w_before = m2.decoder.net[0].weight_v.detach().clone()
+    enc_before = [p.detach().clone() for p in m2.encoder.parameters()]
     tr = GraphedTrainer(m2, x, warmup_steps=2)
     # the trainer's eager warm-up is undone (parameters, buffers, optimiser state restored) and capture itself executes
     # nothing: the twin starts from the same state without any catching up
@@ -176,6 +177,13 @@ def test_cuda_graph_training_matches_eager(streams, monkeypatch):
     w1 = m1.decoder.net[0].weight_v
     w2 = m2.decoder.net[0].weight_v
     assert rel_l2(w2, w1) < 1e-2
+    # phase 2 never moves the encoder (detached latent: rave/blocks.py:739-743) -- what lets the trainer keep the encoder's
+    # prepared weights in static buffers
+    assert tr.static_encoder
+    for (n, p), q in zip(m2.encoder.named_parameters(), enc_before):
+        assert torch.equal(p, q), n
+    for (n, p), q in zip(m1.encoder.named_parameters(), enc_before):
+        assert torch.equal(p, q), n
 
 
 # ------------------------------------------------------------------------------------ the benched configuration
