@@ -618,6 +618,60 @@ im2col_c1_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ X, int
   dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
 }
 
+// Staged variant (the default): the per-thread gather above issues 16 strided loads per output row -- a warp access
+// touches 32 addresses (stride * period) floats apart, 8-44 sectors for 128 useful bytes, and the L1 wavefront queue,
+// not HBM, set its pace (40 us for a 33 MB operand).  Here one CTA serves IC_NL output positions of ALL `period` rows
+// of one source batch entry: the contiguous source span is read once, coalesced, and de-interleaved into shared memory
+// (one padded line per fold row w; the index skew i + i/32 makes the stride-`stride` tap reads conflict-free for
+// stride 1, 2, 4); every thread then assembles 32-byte rows from shared memory and stores them back to back.
+constexpr int IC_NL = 128;
+__device__ __forceinline__ int ic_skew(int i) { return i + (i >> 5); }
+
+__global__ void __launch_bounds__(256)
+im2col_c1_staged_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ X, int src_pitch, int src_len, int Lin,
+                        int Lout, int out_pitch, int K, int stride, int pad_l, int period, int pool, int line) {
+  extern __shared__ float sm[];                      // [period][line]
+  const int b = blockIdx.y;
+  const int l0 = blockIdx.x * IC_NL;
+  const int p_lo = l0 * stride - pad_l;
+  const int n_p = (IC_NL - 1) * stride + K;
+  const float *xb = x + (size_t)b * src_pitch;
+  if (period > 1) {                                  // fold: element (p, w) lives at p * period + w
+    const long e_lo = (long)p_lo * period;
+    for (int q = threadIdx.x; q < n_p * period; q += blockDim.x) {
+      const int pp = q / period, w = q - pp * period;
+      const int pos = p_lo + pp;
+      const long e = e_lo + q;
+      sm[w * line + ic_skew(pp)] = (pos >= 0 && pos < Lin && e < src_len) ? __ldg(xb + e) : 0.f;
+    }
+  } else {                                           // average pooling: position p = mean of `pool` consecutive samples
+    for (int pp = threadIdx.x; pp < n_p; pp += blockDim.x) {
+      const int pos = p_lo + pp;
+      sm[ic_skew(pp)] = (pos >= 0 && pos < Lin) ? c1_src_value(xb, pos, 0, 1, pool, src_len) : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < IC_NL * period; idx += blockDim.x) {
+    const int w = idx / IC_NL, ll = idx - w * IC_NL;
+    const int l = l0 + ll;
+    if (l >= out_pitch) continue;
+    uint32_t wds[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (l < Lout) {
+      const float *row = sm + w * line;
+      const int q0 = ll * stride;
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        const float v0 = (2 * k2 < K) ? row[ic_skew(q0 + 2 * k2)] : 0.f;
+        const float v1 = (2 * k2 + 1 < K) ? row[ic_skew(q0 + 2 * k2 + 1)] : 0.f;
+        wds[k2] = pack_bf16(v0, v1);
+      }
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(X + ((size_t)(b * period + w) * out_pitch + l) * 16);
+    dst[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+  }
+}
+
 // dsrc[b][(t*pool + j)*period + w] += (1/pool) * sum_k P[r][(t + pad - k)/stride][k]; P fp32 channel-last [R][p_pitch][16].
 // Every source element is touched by at most one (r, t, j): plain read-modify-write, launches are stream-ordered.
 __global__ void __launch_bounds__(256)
@@ -645,12 +699,35 @@ gather_c1_kernel(const float *__restrict__ P, float *__restrict__ dx, int src_pi
 
 }  // namespace rave
 
+static inline int ic_skew_host(int i) { return i + (i >> 5); }
+
 extern "C" int rave_im2col_c1(const float *x, void *X_bf16, int R, int src_pitch, int src_len, int Lin, int Lout,
                               int out_pitch, int K, int stride, int pad_l, int period, int pool, void *stream) {
   using namespace rave;
   RAVE_CHECK_ARG(x && X_bf16 && R > 0 && R <= 65535 && K > 0 && K <= 16 && out_pitch >= Lout && period >= 1 &&
                      pool >= 1 && (period == 1 || pool == 1) && R % period == 0,
                  "im2col_c1: bad argument");
+  static int staged = -1;
+  if (staged < 0) {
+    const char *e = getenv("RAVE_C1_STAGED");          // 0: the per-thread gather (debug / ablation)
+    staged = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const int n_p = (IC_NL - 1) * stride + K;
+  const int line = (ic_skew_host(n_p - 1) + 1) | 1;    // odd pitch: the de-interleaving stores spread over the banks
+  const size_t smem = (size_t)period * line * sizeof(float);
+  if (staged && stride >= 1 && smem <= 96 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(im2col_c1_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    dim3 grid(ceil_div(out_pitch, IC_NL), R / period);
+    // period 1: 128 rows per CTA -> 128 threads (one row each); folds: 128 * period rows over 256 threads
+    im2col_c1_staged_kernel<<<grid, period == 1 ? 128 : 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)X_bf16, src_pitch, src_len, Lin,
+                                                                      Lout, out_pitch, K, stride, pad_l, period, pool, line);
+    RAVE_CHECK_LAUNCH("im2col_c1_staged");
+    return 0;
+  }
   dim3 grid(ceil_div(out_pitch, 256), R);
   im2col_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)X_bf16, src_pitch, src_len, Lin, Lout,
                                                            out_pitch, K, stride, pad_l, period, pool);

@@ -738,18 +738,28 @@ __global__ void __launch_bounds__(1024) mt_wn_bwd_smem_kernel(const __grid_const
   float *dr = L.dv + (size_t)c0 * R;
   const int wide = L.wide > 1 ? L.wide : 1;
   const size_t split_stride = (size_t)(L.wide > 1 ? L.J : K) * C0p * C1p * wide;
-  for (int j = threadIdx.x; j < R; j += blockDim.x) {
-    const int k = j / C1, c1 = j - k * C1;
-    const int slot = L.wide > 1 ? (int)L.tapsA[k] : k;
-    const float *src = L.dwt + ((size_t)(slot / wide) * C0p + c0) * ((size_t)C1p * wide) + (size_t)(slot % wide) * C1p + c1;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int sp = 0;
-    for (; sp + 8 <= L.splits; sp += 8) {
+  // four row elements per thread and pass: with 1-2 split-K slices (the large layers) a thread otherwise has a single
+  // load in flight and the kernel runs at DRAM latency, not bandwidth
+  const int bd = blockDim.x;
+  for (int j0 = threadIdx.x; j0 < R; j0 += 4 * bd) {
+    const float *src[4];
+    int dst[4];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += __ldg(src + (size_t)(sp + u) * split_stride);
+    for (int u = 0; u < 4; ++u) {
+      const int j = min(j0 + u * bd, R - 1);                  // (clamped lanes recompute element R-1: same value)
+      const int k = j / C1, c1 = j - k * C1;
+      const int slot = L.wide > 1 ? (int)L.tapsA[k] : k;
+      src[u] = L.dwt + ((size_t)(slot / wide) * C0p + c0) * ((size_t)C1p * wide) + (size_t)(slot % wide) * C1p + c1;
+      dst[u] = wn_pad(c1 * K + k);
     }
-    for (; sp < L.splits; ++sp) acc[sp & 7] += __ldg(src + (size_t)sp * split_stride);
-    sh[wn_pad(c1 * K + k)] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    for (int sp = 0; sp < L.splits; ++sp) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __ldg(src[u] + (size_t)sp * split_stride);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0 + u * bd < R) sh[dst[u]] = acc[u];
   }
   __syncthreads();
   if (!L.g) {
