@@ -423,6 +423,20 @@ def dominant_launch_roofline(torch, prof, pk):
         ach, peak, unit = fl / (ms * 1e-3) / 1e12, pk["bf16_tflops"], "TFLOP/s"
     res.update(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
                ms_per_launch=ms, peak_source=pk["source"] + " burst", timing=f"{n} launches over {nb} rotating buffer sets")
+    # DRAM bytes of the same launch from the committed `ncu --set full` capture (scripts/ncu_dominant.py -> ncu_traffic.py)
+    try:
+        import json as _json
+        tf = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ncu_traffic.json")
+        if os.path.exists(tf):
+            for k, v in _json.load(open(tf)).items():
+                kk = k.replace(" ", "")
+                kk = kk[:kk.rfind(",")] + ">" if kk.count(",") == 2 else kk          # drop the X3 template flag
+                if kk == inst and (Bc, Cin, Lin, Cout, Lout, K, stride) == (64, 192, 4096, 384, 1024, 15, 4):
+                    res["traffic"] = v["traffic_bytes"]
+                    res["traffic_source"] = ("profiles/r2_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per "
+                                             f"launch, ncu --set full of this launch shape ({v['launches']} launches)")
+    except Exception:
+        pass
     return res
 
 

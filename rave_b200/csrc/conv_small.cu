@@ -682,71 +682,18 @@ gather_c1_kernel(const float *__restrict__ P, float *__restrict__ dx, int src_pi
   if (t >= Lin) return;
   float acc = 0.f;
   const float *Pr = P + (size_t)r * p_pitch * 16;
-  for (int k = (t + pad_l) % stride; k < K; k += stride) {
-    const int q = t + pad_l - k;
-    if (q < 0) break;
-    const int l = q / stride;
+  // taps k = k0 + m stride hit output rows l0 - m: ONE integer division per thread (the loop used to divide twice per
+  // tap by the run-time stride: ~125 of the thread's ~150 instructions)
+  const int l0 = (t + pad_l) / stride;
+  const int k0 = (t + pad_l) - l0 * stride;
+  for (int k = k0, l = l0; k < K && l >= 0; k += stride, --l)
     if (l < Lout) acc += __ldg(Pr + (size_t)l * 16 + k);
-  }
   const int b = r / period, w = r - b * period;
   float *db = dx + (size_t)b * src_pitch;
   if (pool > 1) acc /= (float)pool;
   for (int j = 0; j < pool; ++j) {
     const long e = ((long)t * pool + j) * period + w;
     if (e < src_len) db[e] += acc;
-  }
-}
-
-// Staged adjoint (the default): the per-thread form above reads P with 25 % sector efficiency (four 4-byte loads per
-// thread out of 64-byte rows) and updates the source with stride `period` (a fold by 11: 44 sectors per warp access, read
-// and written).  Here one CTA owns GC_NT source positions of ALL `period` fold rows of a batch entry: the P rows they need
-// are one contiguous span per fold row (float4 loads into shared memory, pitch 20: conflict-free tap reads), and the
-// result leaves as ONE contiguous span of the source gradient (coalesced read-modify-write).
-constexpr int GC_NT = 256;
-constexpr int GC_PITCH = 20;
-
-__global__ void __launch_bounds__(256)
-gather_c1_staged_kernel(const float *__restrict__ P, float *__restrict__ dx, int src_pitch, int src_len, int Lin, int Lout,
-                        int p_pitch, int K, int stride, int pad_l, int period, int pool, int nl) {
-  extern __shared__ __align__(16) float gsm[];       // [period][nl][GC_PITCH] P rows, then [GC_NT * pool * period] results
-  float *ps = gsm;
-  float *outs = gsm + (size_t)period * nl * GC_PITCH;
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * GC_NT;
-  const int lo_num = t0 + pad_l - (K - 1);
-  const int l_lo = lo_num > 0 ? lo_num / stride : 0;
-  for (int idx = threadIdx.x; idx < period * nl * 4; idx += 256) {
-    const int w = idx / (nl * 4);
-    const int rem = idx - w * (nl * 4);
-    const int i = rem >> 2, c4 = rem & 3;
-    const int l = l_lo + i;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (l < Lout) v = __ldg(reinterpret_cast<const float4 *>(P + ((size_t)(b * period + w) * p_pitch + l) * 16) + c4);
-    *reinterpret_cast<float4 *>(ps + (size_t)(w * nl + i) * GC_PITCH + c4 * 4) = v;
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < period * GC_NT; idx += 256) {
-    const int w = idx / GC_NT, tl = idx - w * GC_NT;
-    const int t = t0 + tl;
-    float acc = 0.f;
-    if (t < Lin) {
-      const float *pw = ps + (size_t)w * nl * GC_PITCH;
-      for (int k = (t + pad_l) % stride; k < K; k += stride) {
-        const int q = t + pad_l - k;
-        if (q < 0) break;
-        const int l = q / stride;
-        if (l < Lout) acc += pw[(l - l_lo) * GC_PITCH + k];
-      }
-      if (pool > 1) acc /= (float)pool;
-    }
-    for (int j = 0; j < pool; ++j) outs[(tl * pool + j) * period + w] = acc;
-  }
-  __syncthreads();
-  float *db = dx + (size_t)b * src_pitch;
-  const long e0 = (long)t0 * pool * period;
-  for (int i = threadIdx.x; i < GC_NT * pool * period; i += 256) {
-    const long e = e0 + i;
-    if (e < src_len) db[e] += outs[i];
   }
 }
 
@@ -793,25 +740,6 @@ extern "C" int rave_gather_c1(const float *P, float *dsrc, int R, int src_pitch,
   RAVE_CHECK_ARG(P && dsrc && R > 0 && R <= 65535 && K > 0 && K <= 16 && p_pitch >= Lout && period >= 1 && pool >= 1 &&
                      (period == 1 || pool == 1) && R % period == 0,
                  "gather_c1: bad argument");
-  static int staged = -1;
-  if (staged < 0) {
-    const char *e = getenv("RAVE_C1_STAGED");          // 0: the per-thread gather (debug / ablation)
-    staged = (e && atoi(e) == 0) ? 0 : 1;
-  }
-  const int nl = (GC_NT + K - 2) / stride + 2;
-  const size_t smem = ((size_t)period * nl * GC_PITCH + (size_t)GC_NT * pool * period) * sizeof(float);
-  if (staged && smem <= 96 * 1024 && ((uintptr_t)P & 15) == 0) {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(gather_c1_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr = true;
-    }
-    dim3 grid(ceil_div(Lin, GC_NT), R / period);
-    gather_c1_staged_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(P, dsrc, src_pitch, src_len, Lin, Lout, p_pitch, K,
-                                                                      stride, pad_l, period, pool, nl);
-    RAVE_CHECK_LAUNCH("gather_c1_staged");
-    return 0;
-  }
   dim3 grid(ceil_div(Lin, 256), R);
   gather_c1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, dsrc, src_pitch, src_len, Lin, Lout, p_pitch, K, stride,
                                                            pad_l, period, pool);
