@@ -201,3 +201,37 @@ def test_stacked_l1_terms_match_the_per_feature_loop():
                 gr, gf = torch.autograd.grad(t, [r2, f2])
                 assert torch.allclose(grads[k], gr, atol=1e-7) and torch.allclose(grads[k + 1], gf, atol=1e-7)
                 k += 2
+
+
+def test_integration_table_names_every_entry_point():
+    """INTEGRATION.md section 3 maps every C entry point of include/rave_b200.h onto the reference call site it replaces."""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "rave_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(rave_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) > 60
+    missing = []
+    for n in names:
+        base = re.sub(r"_(fwd|bwd)$", "", n)
+        if n not in doc and base not in doc:
+            missing.append(n)
+    assert not missing, missing
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's
+    keys, the oracle port as `cpu_baseline`, zero host<->device bytes."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "audio-seconds/s" and line["higher_is_better"] is True
+    for k in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["value"] > 0
