@@ -226,6 +226,10 @@ int rave_l1_grad_f32(const float *t, const float *v, const float *d, float *gt, 
  * g (gradient from the feature's other consumers) or d (gradient of the two sums) may be null, not both. */
 int rave_leaky_fm_fwd(const float *x, float *a, float *stats, long H, float slope, void *stream);
 int rave_leaky_fm_bwd(const float *a, const float *g, const float *d, float *gx, long H, float slope, void *stream);
+/* the same tap that also writes the NEXT MRD conv's operand: x rows are (b, t) pairs [2 Rh][F][C] (first Rh rows real);
+ * xs [2 Rh][Fp][3 C] bf16 = rave_time_stack_nhwc(a, kt = 3, pt = 1) incl. the zero borders / pad columns f >= F */
+int rave_leaky_fm_stack_fwd(const float *x, float *a, float *stats, void *xs_bf16, long Rh, int T, int F, int C, int Fp,
+                            float slope, void *stream);
 /* Snake (rave/blocks.py:852-860) on the engine's channel-last bf16 streams [rows][C] (v3 chains on the tcgen05 kernels):
  * a = h + sin^2(alpha h) / (alpha + 1e-9);  backward: gh = ga * da/dh + add (add may be null), dalpha[c] += sum_rows
  * ga * da/dalpha (dalpha zeroed by the caller). */

@@ -1128,6 +1128,77 @@ leaky_fm_fwd_kernel(const float *__restrict__ x, float *__restrict__ a, float *_
   }
 }
 
+// The same tap that ALSO writes the next MRD conv's operand (rave_time_stack_nhwc of its own output, kt = 3, pt = 1):
+// x rows are (b, t) pairs [2 Rh][F][C]; xs [2 Rh][Fp][3 C] bf16 with xs[(b, t)][f][dt C + c] = a[b][t + dt - 1][f][c], zero
+// outside the T time steps of a batch entry and in the pad columns f >= F.  The element at time t lands in slot 0 of row
+// t + 1, slot 1 of row t and slot 2 of row t - 1; the threads of the first / last time step and of the last column write
+// the zeros.  Saves the stand-alone time-stack pass (read 4 N, write 6 N bytes per layer, 78 launches per step).
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+}
+
+__global__ void __launch_bounds__(256)
+leaky_fm_stack_fwd_kernel(const float *__restrict__ x, float *__restrict__ a, float *__restrict__ stats,
+                          __nv_bfloat16 *__restrict__ xs, long Rh, int T, int F, int C, int Fp, float slope) {
+  __shared__ float red0[8], red1[8];
+  float s0 = 0.f, s1 = 0.f;
+  const int C4 = C >> 2;
+  const int Cp = 3 * C;
+  const long H4 = Rh * F * C4;
+  const float4 *xr4 = reinterpret_cast<const float4 *>(x), *xf4 = xr4 + H4;
+  float4 *ar4 = reinterpret_cast<float4 *>(a), *af4 = ar4 + H4;
+  const uint2 zero2 = make_uint2(0u, 0u);
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < H4; i += (long)gridDim.x * 256) {
+    const int c4 = (int)(i % C4);
+    const long rf = i / C4;
+    const int f = (int)(rf % F);
+    const long r = rf / F;                           // row (b, t) inside a half
+    const int t = (int)(r % T);
+    float4 rv = __ldg(xr4 + i), fv = __ldg(xf4 + i);
+    rv.x = lk(rv.x, slope); rv.y = lk(rv.y, slope); rv.z = lk(rv.z, slope); rv.w = lk(rv.w, slope);
+    fv.x = lk(fv.x, slope); fv.y = lk(fv.y, slope); fv.z = lk(fv.z, slope); fv.w = lk(fv.w, slope);
+    ar4[i] = rv;
+    af4[i] = fv;
+    s0 += fabsf(rv.x - fv.x) + fabsf(rv.y - fv.y) + fabsf(rv.z - fv.z) + fabsf(rv.w - fv.w);
+    s1 += fabsf(rv.x) + fabsf(rv.y) + fabsf(rv.z) + fabsf(rv.w);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint2 pk = pack_bf16x4(h ? fv : rv);
+      const long row = r + (h ? Rh : 0);
+      __nv_bfloat16 *base = xs + ((size_t)row * Fp + f) * Cp + 4 * c4;         // slot 0 of this (row, f)
+      const size_t row_stride = (size_t)Fp * Cp;
+      *reinterpret_cast<uint2 *>(base + C) = pk;                                    // slot 1 of row t
+      if (t + 1 < T) *reinterpret_cast<uint2 *>(base + row_stride) = pk;            // slot 0 of row t + 1
+      else *reinterpret_cast<uint2 *>(base + 2 * C) = zero2;                        // last step: its slot 2 reads t + 1
+      if (t > 0) *reinterpret_cast<uint2 *>(base - row_stride + 2 * C) = pk;        // slot 2 of row t - 1
+      else *reinterpret_cast<uint2 *>(base) = zero2;                                // first step: its slot 0 reads t - 1
+      if (f == F - 1) {                                                             // pad columns of this row: zeros
+        for (int fp = F; fp < Fp; ++fp) {
+          __nv_bfloat16 *pz = base + (size_t)(fp - f) * Cp;
+          *reinterpret_cast<uint2 *>(pz) = zero2;
+          *reinterpret_cast<uint2 *>(pz + C) = zero2;
+          *reinterpret_cast<uint2 *>(pz + 2 * C) = zero2;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red0[wid] = s0; red1[wid] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float u0 = 0.f, u1 = 0.f;
+    for (int i = 0; i < 8; ++i) { u0 += red0[i]; u1 += red1[i]; }
+    atomicAdd(stats, u0);
+    atomicAdd(stats + 1, u1);
+  }
+}
+
 __device__ __forceinline__ void leaky_fm_bwd_one(float ar, float af, float gr, float gf, float d0, float d1, float slope,
                                                  float &or_, float &of_) {
   const float s = d0 * sgnf(ar - af);
@@ -1173,6 +1244,20 @@ extern "C" int rave_leaky_fm_fwd(const float *x, float *a, float *stats, long H,
   blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
   leaky_fm_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, a, stats, H, slope, vec);
   RAVE_CHECK_LAUNCH("leaky_fm_fwd");
+  return 0;
+}
+
+extern "C" int rave_leaky_fm_stack_fwd(const float *x, float *a, float *stats, void *xs_bf16, long Rh, int T, int F, int C,
+                                       int Fp, float slope, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(x && a && stats && xs_bf16 && Rh > 0 && T > 0 && Rh % T == 0 && F > 0 && Fp >= F && C > 0 && C % 4 == 0 &&
+                     slope > 0.f && (((uintptr_t)x | (uintptr_t)a) & 15) == 0 && ((uintptr_t)xs_bf16 & 7) == 0,
+                 "leaky_fm_stack_fwd: bad argument (C %% 4 == 0, rows = whole batch entries of T steps, aligned buffers)");
+  long blocks = (Rh * F * (C / 4) + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+  leaky_fm_stack_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, a, stats, (__nv_bfloat16 *)xs_bf16, Rh, T, F, C,
+                                                                          Fp, slope);
+  RAVE_CHECK_LAUNCH("leaky_fm_stack_fwd");
   return 0;
 }
 

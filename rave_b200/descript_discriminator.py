@@ -9,6 +9,8 @@ time stride is ONE library conv1d along frequency over rows [(b, t)] whose chann
 the input channels (`DiscConv2d`): out[b,:,t,:] = sum_dt conv1d_f(x[b,:,t+dt-pt,:], W[:,:,dt,:]).
 Features are POST-activation (descript_discriminator.py:59-61).  No cuDNN on this path.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -112,16 +114,25 @@ class DiscConv2d(nn.Conv2d):
         return (engine.precision() == "bf16" and x.is_cuda and engine.ACT_DTYPE == torch.bfloat16
                 and self.kernel_size[0] * C <= 112)
 
-    def forward_cl(self, x_cl):
+    def stacked_geometry(self, Fq: int, C: int):
+        """(Fp, Cp) of this conv's time-stacked operand for an input of Fq positions and C channels."""
+        spec = self._tc_chain_spec(C)
+        return Fq + (-Fq) % spec.stride, self.kernel_size[0] * C + spec.cin_pad
+
+    def forward_cl(self, x_cl, xs=None):
         """Channel-last in, channel-last out: x_cl [B, T, F, C] fp32 (a view with dense (f, c) rows) -> the chain's own
         output buffer [(b t), Fo, Cout(+pad to 16)] fp32, which IS [B, T, Fo, Cout] channel-last: no layout pass on
-        either side of the conv."""
+        either side of the conv.  `xs`: the time-stacked bf16 operand when the producer already wrote it
+        (ops.leaky_fm_stack: the previous layer's feature tap)."""
         from . import engine
         B, T, Fq, C = x_cl.shape
         spec = self._tc_chain_spec(C)
         kt, pt = self.kernel_size[0], self.padding[0]
-        rpad = (-Fq) % spec.stride
-        xs = ops.time_stack_nhwc(x_cl, kt, pt, kt * C + spec.cin_pad, Fq + rpad)
+        Fp, Cp = self.stacked_geometry(Fq, C)
+        if xs is None:
+            xs = ops.time_stack_nhwc(x_cl, kt, pt, Cp, Fp)
+        elif tuple(xs.shape) != (B * T, Fp, Cp) or xs.dtype != torch.bfloat16:
+            raise _lib.RaveB200Error("DiscConv2d.forward_cl: the pre-stacked operand does not match this conv's geometry")
         (out,) = engine.run_chain(xs, [spec], Fq)
         Fo = engine.chain_lengths([spec], Fq)[0]
         if out.shape[1] != Fo:
@@ -135,6 +146,20 @@ def _feature_tap(out, slope, B):
     if B % 2 == 0 and out.dtype == torch.float32 and out.is_contiguous():
         return ops.leaky_fm(out, slope)
     return ops.activation(out, ops.ACT_LEAKY, slope), None
+
+
+def _feature_tap_stack(out, slope, B, T, nxt):
+    """_feature_tap that also writes the time-stacked operand of the next MRD conv `nxt` (a DiscConv2d) in the same pass,
+    when the geometry allows it (kt = 3, pt = 1, no channel padding on either side): returns (a, stats, xs | None)."""
+    C = out.shape[2]
+    if (nxt is not None and B % 2 == 0 and out.dtype == torch.float32 and out.is_contiguous() and os.environ.get(
+            "RAVE_FUSE_TAP_STACK", "1") != "0" and nxt.kernel_size[0] == 3 and nxt.padding[0] == 1
+            and nxt.in_channels == C and C % 4 == 0 and out.shape[0] == B * T):
+        Fp, Cp = nxt.stacked_geometry(out.shape[1], C)
+        if Cp == 3 * C:
+            return ops.leaky_fm_stack(out, slope, T, Fp)
+    a, st = _feature_tap(out, slope, B)
+    return a, st, None
 
 
 class _ParamView:
@@ -281,10 +306,13 @@ class MRD(nn.Module):
         fmap, outs = [], []
         for (lo, hi), stack in zip(self.bands, self.band_convs):
             cur = x0[:, :, lo:hi, :]
-            for layer in stack:
+            xs_next = None
+            for li, layer in enumerate(stack):
                 conv = layer[0]
-                out = conv.forward_cl(cur)                                   # [(b t), Fo, 32]
-                a, st = _feature_tap(out, layer[1].negative_slope, B)
+                out = conv.forward_cl(cur, xs_next)                          # [(b t), Fo, 32]
+                # the tap of every layer but the stack's last also writes the next conv's time-stacked operand
+                nxt = stack[li + 1][0] if li + 1 < len(stack) else None
+                a, st, xs_next = _feature_tap_stack(out, layer[1].negative_slope, B, t, nxt)
                 cur = a.view(B, t, out.shape[1], out.shape[2])
                 feat = cur.permute(0, 3, 1, 2)
                 feat._cl_base = a

@@ -602,6 +602,51 @@ def leaky_fm(x, slope):
     return LeakyFmFn.apply(x, slope)
 
 
+class LeakyFmStackFn(torch.autograd.Function):
+    """LeakyFmFn that also writes the NEXT MRD conv's operand in the same pass: x [(b t), F, C] fp32 with whole batch
+    entries of T steps (first half of the rows real) -> (a, stats, xs) with xs [(b t), Fp, 3 C] bf16 =
+    time_stack_nhwc(a.view(B, T, F, C), kt = 3, pt = 1) (rave_leaky_fm_stack_fwd).  The backward is the composition of the
+    two stand-alone backward kernels (adjoint of the time stack, then the tap's fused backward)."""
+
+    @staticmethod
+    def forward(ctx, x, slope, T, Fp):
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 3 or x.shape[0] % (2 * T) or x.shape[2] % 4:
+            raise _lib.RaveB200Error("leaky_fm_stack: contiguous fp32 [(b t), F, C] rows, even batch, C % 4 == 0 expected")
+        R2, F_, C = x.shape
+        ctx.set_materialize_grads(False)
+        a = torch.empty_like(x)
+        stats = torch.zeros(2, dtype=torch.float32, device=x.device)
+        xs = torch.empty(R2, Fp, 3 * C, dtype=torch.bfloat16, device=x.device)
+        call("rave_leaky_fm_stack_fwd", ptr(x), ptr(a), ptr(stats), ptr(xs), R2 // 2, T, F_, C, Fp, float(slope),
+             stream_ptr())
+        ctx.save_for_backward(a)
+        ctx.slope = float(slope)
+        ctx.cfg = (R2 // T, C, T, F_, Fp, 3 * C)
+        return a, stats, xs
+
+    @staticmethod
+    def backward(ctx, ga, dstats, gxs):
+        (a,) = ctx.saved_tensors
+        if ga is None and dstats is None and gxs is None:
+            return None, None, None, None
+        if gxs is not None:
+            B, C, T, F_, Fp, Cp = ctx.cfg
+            g_st = torch.empty(B, T, F_, C, dtype=torch.float32, device=a.device)
+            gxs = gxs.contiguous()
+            call("rave_time_stack_nhwc_bwd", ptr(gxs), ptr(g_st), B, C, T, F_, Fp, Cp, 3, 1, stream_ptr())
+            g_st = g_st.view_as(a)
+            ga = g_st if ga is None else g_st.add_(_f32c(ga))
+        ga = _f32c(ga)
+        dstats = _f32c(dstats)
+        gx = torch.empty_like(a)
+        call("rave_leaky_fm_bwd", ptr(a), ptr(ga), ptr(dstats), ptr(gx), a.numel() // 2, ctx.slope, stream_ptr())
+        return gx, None, None, None
+
+
+def leaky_fm_stack(x, slope, T, Fp):
+    return LeakyFmStackFn.apply(x, slope, T, Fp)
+
+
 class L1StatsFn(torch.autograd.Function):
     """(sum |t - v|, sum |t|) of two fp32 CUDA tensors in one pass, gradient in one pass (rave_l1_stats_f32 / _grad)."""
 

@@ -245,6 +245,33 @@ def test_descript_feature_matching_on_dense_buffers_matches_generic():
     assert torch.count_nonzero(res["stats_fake_only"][1][:2]) == 0
 
 
+def test_leaky_fm_stack_equals_tap_plus_time_stack():
+    """ops.leaky_fm_stack (the feature tap that also writes the next MRD conv's time-stacked operand) == ops.leaky_fm
+    followed by ops.time_stack_nhwc, bit for bit in the forward (borders, pad columns, both halves) and through the
+    backward (with and without a gradient arriving at the feature itself)."""
+    from rave_b200 import ops
+    torch.manual_seed(6)
+    for (B, T, F_, C, stride) in [(4, 5, 9, 32, 2), (2, 3, 8, 32, 1), (2, 1, 5, 16, 2), (6, 7, 33, 32, 2), (2, 2, 1, 8, 2)]:
+        Fp = F_ + (-F_) % stride
+        x = torch.randn(B * T, F_, C, device="cuda")
+        x1 = x.clone().requires_grad_(True)
+        x2 = x.clone().requires_grad_(True)
+        a1, st1, xs1 = ops.leaky_fm_stack(x1, 0.1, T, Fp)
+        a2, st2 = ops.leaky_fm(x2, 0.1)
+        xs2 = ops.time_stack_nhwc(a2.view(B, T, F_, C), 3, 1, 3 * C, Fp)
+        assert xs1.shape == xs2.shape == (B * T, Fp, 3 * C)
+        assert torch.equal(a1, a2) and torch.equal(xs1, xs2) and rel_l2(st1, st2) < 1e-6
+        pa = torch.randn_like(a1)
+        px = torch.randn(xs1.shape, device="cuda")
+        d = torch.tensor([0.7, -0.3], device="cuda")
+        for with_a in (True, False):
+            l1 = (st1 * d).sum() + (xs1.float() * px).sum() + ((a1 * pa).sum() if with_a else 0.)
+            l2 = (st2 * d).sum() + (xs2.float() * px).sum() + ((a2 * pa).sum() if with_a else 0.)
+            (g1,) = torch.autograd.grad(l1, x1, retain_graph=True)
+            (g2,) = torch.autograd.grad(l2, x2, retain_graph=True)
+            assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-5), (B, T, F_, C, with_a)
+
+
 def test_leaky_fm_tap_vs_torch():
     from rave_b200 import ops
     torch.manual_seed(4)
