@@ -230,6 +230,10 @@ int rave_leaky_fm_bwd(const float *a, const float *g, const float *d, float *gx,
  * xs [2 Rh][Fp][3 C] bf16 = rave_time_stack_nhwc(a, kt = 3, pt = 1) incl. the zero borders / pad columns f >= F */
 int rave_leaky_fm_stack_fwd(const float *x, float *a, float *stats, void *xs_bf16, long Rh, int T, int F, int C, int Fp,
                             float slope, void *stream);
+/* its backward in one pass: gx = (adjoint of the time stack applied to gxs [2 Rh][Fp][3 C] bf16 (+ ga, nullable) + the
+ * feature-matching terms d (nullable)) * LeakyReLU'(a) */
+int rave_leaky_fm_stack_bwd(const float *a, const void *gxs_bf16, const float *ga, const float *d, float *gx, long Rh, int T,
+                            int F, int C, int Fp, float slope, void *stream);
 /* Snake (rave/blocks.py:852-860) on the engine's channel-last bf16 streams [rows][C] (v3 chains on the tcgen05 kernels):
  * a = h + sin^2(alpha h) / (alpha + 1e-9);  backward: gh = ga * da/dh + add (add may be null), dalpha[c] += sum_rows
  * ga * da/dalpha (dalpha zeroed by the caller). */

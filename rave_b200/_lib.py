@@ -57,6 +57,7 @@ SIGNATURES = {
     "rave_leaky_fm_fwd": (c_int, [_P, _P, _P, ctypes.c_long, ctypes.c_float, _P]),
     "rave_leaky_fm_bwd": (c_int, [_P, _P, _P, _P, ctypes.c_long, ctypes.c_float, _P]),
     "rave_leaky_fm_stack_fwd": (c_int, [_P, _P, _P, _P, ctypes.c_long, _I, _I, _I, _I, ctypes.c_float, _P]),
+    "rave_leaky_fm_stack_bwd": (c_int, [_P, _P, _P, _P, _P, ctypes.c_long, _I, _I, _I, _I, ctypes.c_float, _P]),
     "rave_l1_grad_f32": (c_int, [_P, _P, _P, _P, _P, ctypes.c_long, _P]),
     "rave_snake_cl_fwd": (c_int, [_P, _P, _P, ctypes.c_long, _I, _P]),
     "rave_snake_cl_bwd": (c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_long, _I, _P]),

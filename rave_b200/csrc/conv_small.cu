@@ -1234,6 +1234,57 @@ leaky_fm_bwd_kernel(const float *__restrict__ a, const float *__restrict__ g, co
   }
 }
 
+// Backward of leaky_fm_stack_fwd in one pass: the gradient reaching a[(b, t)][f][c] through the stacked operand is
+//   gxs[(b, t + 1)][f][c] + gxs[(b, t)][f][C + c] + gxs[(b, t - 1)][f][2 C + c]      (rows inside the batch entry only)
+// (the adjoint rave_time_stack_nhwc_bwd computes, same summation order), plus `ga` (gradient arriving at the feature
+// itself, or null); the feature-matching terms and LeakyReLU' follow as in leaky_fm_bwd_kernel.
+__device__ __forceinline__ float4 bf16x4_to_f32(uint2 p) {
+  return make_float4(__uint_as_float(p.x << 16), __uint_as_float(p.x & 0xFFFF0000u), __uint_as_float(p.y << 16),
+                     __uint_as_float(p.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ void add4(float4 &a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+__global__ void __launch_bounds__(256)
+leaky_fm_stack_bwd_kernel(const float *__restrict__ a, const __nv_bfloat16 *__restrict__ gxs, const float *__restrict__ ga,
+                          const float *__restrict__ d, float *__restrict__ gx, long Rh, int T, int F, int C, int Fp,
+                          float slope) {
+  const float d0 = d ? d[0] : 0.f, d1 = d ? d[1] : 0.f;
+  const int C4 = C >> 2;
+  const int Cp = 3 * C;
+  const long H4 = Rh * F * C4;
+  const size_t row_stride = (size_t)Fp * Cp;
+  const float4 *ar4 = reinterpret_cast<const float4 *>(a), *af4 = ar4 + H4;
+  const float4 *gr4 = reinterpret_cast<const float4 *>(ga), *gf4 = gr4 + H4;
+  float4 *or4 = reinterpret_cast<float4 *>(gx), *of4 = or4 + H4;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < H4; i += (long)gridDim.x * 256) {
+    const int c4 = (int)(i % C4);
+    const long rf = i / C4;
+    const int f = (int)(rf % F);
+    const long r = rf / F;
+    const int t = (int)(r % T);
+    float4 g2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long row = r + (h ? Rh : 0);
+      const __nv_bfloat16 *base = gxs + ((size_t)row * Fp + f) * Cp + 4 * c4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t + 1 < T) add4(acc, bf16x4_to_f32(__ldg(reinterpret_cast<const uint2 *>(base + row_stride))));
+      add4(acc, bf16x4_to_f32(__ldg(reinterpret_cast<const uint2 *>(base + C))));
+      if (t > 0) add4(acc, bf16x4_to_f32(__ldg(reinterpret_cast<const uint2 *>(base - row_stride + 2 * C))));
+      if (ga) add4(acc, __ldg((h ? gf4 : gr4) + i));
+      g2[h] = acc;
+    }
+    const float4 rv = __ldg(ar4 + i), fv = __ldg(af4 + i);
+    float4 o, q;
+    leaky_fm_bwd_one(rv.x, fv.x, g2[0].x, g2[1].x, d0, d1, slope, o.x, q.x);
+    leaky_fm_bwd_one(rv.y, fv.y, g2[0].y, g2[1].y, d0, d1, slope, o.y, q.y);
+    leaky_fm_bwd_one(rv.z, fv.z, g2[0].z, g2[1].z, d0, d1, slope, o.z, q.z);
+    leaky_fm_bwd_one(rv.w, fv.w, g2[0].w, g2[1].w, d0, d1, slope, o.w, q.w);
+    or4[i] = o;
+    of4[i] = q;
+  }
+}
+
 }  // namespace rave
 
 extern "C" int rave_leaky_fm_fwd(const float *x, float *a, float *stats, long H, float slope, void *stream) {
@@ -1258,6 +1309,21 @@ extern "C" int rave_leaky_fm_stack_fwd(const float *x, float *a, float *stats, v
   leaky_fm_stack_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, a, stats, (__nv_bfloat16 *)xs_bf16, Rh, T, F, C,
                                                                           Fp, slope);
   RAVE_CHECK_LAUNCH("leaky_fm_stack_fwd");
+  return 0;
+}
+
+extern "C" int rave_leaky_fm_stack_bwd(const float *a, const void *gxs_bf16, const float *ga, const float *d, float *gx,
+                                       long Rh, int T, int F, int C, int Fp, float slope, void *stream) {
+  using namespace rave;
+  RAVE_CHECK_ARG(a && gxs_bf16 && gx && Rh > 0 && T > 0 && Rh % T == 0 && F > 0 && Fp >= F && C > 0 && C % 4 == 0 &&
+                     slope > 0.f && (((uintptr_t)a | (uintptr_t)gx | (uintptr_t)ga) & 15) == 0 &&
+                     ((uintptr_t)gxs_bf16 & 7) == 0,
+                 "leaky_fm_stack_bwd: bad argument (C %% 4 == 0, rows = whole batch entries of T steps, aligned buffers)");
+  long blocks = (Rh * F * (C / 4) + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+  leaky_fm_stack_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16 *)gxs_bf16, ga, d, gx, Rh,
+                                                                          T, F, C, Fp, slope);
+  RAVE_CHECK_LAUNCH("leaky_fm_stack_bwd");
   return 0;
 }
 

@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns the device memory, the stream and the autograd
 arithmetic operation of the hot path is one of the library's sm_100a kernels.  There is no
 fallback implementation: host tensors or a missing library raise (`_lib.RaveB200Error`).
 """
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -606,7 +607,8 @@ class LeakyFmStackFn(torch.autograd.Function):
     """LeakyFmFn that also writes the NEXT MRD conv's operand in the same pass: x [(b t), F, C] fp32 with whole batch
     entries of T steps (first half of the rows real) -> (a, stats, xs) with xs [(b t), Fp, 3 C] bf16 =
     time_stack_nhwc(a.view(B, T, F, C), kt = 3, pt = 1) (rave_leaky_fm_stack_fwd).  The backward is the composition of the
-    two stand-alone backward kernels (adjoint of the time stack, then the tap's fused backward)."""
+    two stand-alone backward kernels (adjoint of the time stack, then the tap's fused backward) in ONE kernel
+    (rave_leaky_fm_stack_bwd); RAVE_FUSE_TAP_STACK_BWD=0 runs the two kernels."""
 
     @staticmethod
     def forward(ctx, x, slope, T, Fp):
@@ -629,8 +631,16 @@ class LeakyFmStackFn(torch.autograd.Function):
         (a,) = ctx.saved_tensors
         if ga is None and dstats is None and gxs is None:
             return None, None, None, None
+        B, C, T, F_, Fp, Cp = ctx.cfg
+        if gxs is not None and os.environ.get("RAVE_FUSE_TAP_STACK_BWD", "1") != "0":
+            # one pass: adjoint of the time stack + gradient at the feature + feature-matching terms + LeakyReLU'
+            gxs = gxs.contiguous()
+            ga, dstats = _f32c(ga), _f32c(dstats)
+            gx = torch.empty_like(a)
+            call("rave_leaky_fm_stack_bwd", ptr(a), ptr(gxs), ptr(ga), ptr(dstats), ptr(gx), a.shape[0] // 2, T, F_, C, Fp,
+                 ctx.slope, stream_ptr())
+            return gx, None, None, None
         if gxs is not None:
-            B, C, T, F_, Fp, Cp = ctx.cfg
             g_st = torch.empty(B, T, F_, C, dtype=torch.float32, device=a.device)
             gxs = gxs.contiguous()
             call("rave_time_stack_nhwc_bwd", ptr(gxs), ptr(g_st), B, C, T, F_, Fp, Cp, 3, 1, stream_ptr())
