@@ -131,7 +131,7 @@ class DiscConv2d(nn.Conv2d):
         Fp, Cp = self.stacked_geometry(Fq, C)
         if xs is None:
             xs = ops.time_stack_nhwc(x_cl, kt, pt, Cp, Fp)
-        elif tuple(xs.shape) != (B * T, Fp, Cp) or xs.dtype != torch.bfloat16:
+        elif tuple(xs.shape) != (B * T, Fp, Cp) or xs.dtype != engine.ACT_DTYPE:
             raise _lib.RaveB200Error("DiscConv2d.forward_cl: the pre-stacked operand does not match this conv's geometry")
         (out,) = engine.run_chain(xs, [spec], Fq)
         Fo = engine.chain_lengths([spec], Fq)[0]

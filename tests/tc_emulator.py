@@ -431,10 +431,35 @@ def leaky_fm(x, slope):
     return a, torch.stack([(a[:h] - a[h:]).abs().sum(), a[:h].abs().sum()])
 
 
+def time_stack_nhwc(x, kt, pt, Cp, Fp):
+    """ops.time_stack_nhwc: x [B, T, F, C] fp32 channel-last -> [(b t), Fp, Cp] operand rows holding the kt time-shifted
+    copies of the channels side by side (zero outside the T steps, in the pad columns / channels); torch autograd."""
+    B, T, Fq, C = x.shape
+    xp = F.pad(x, (0, 0, 0, 0, pt, kt - 1 - pt))                             # zero time steps on both sides
+    st = torch.cat([xp[:, dt:dt + T] for dt in range(kt)], dim=-1)          # [B, T, F, kt*C], channel = dt*C + c
+    st = F.pad(st, (0, Cp - kt * C, 0, Fp - Fq))
+    return _bf16(st.reshape(B * T, Fp, Cp))
+
+
+def leaky_fm_stack(x, slope, T, Fp):
+    """ops.leaky_fm_stack = leaky_fm + the next conv's time-stacked operand (kt = 3, pt = 1) from its output."""
+    a, st = leaky_fm(x, slope)
+    R2, Fq, C = x.shape
+    return a, st, time_stack_nhwc(a.view(R2 // T, T, Fq, C), 3, 1, 3 * C, Fp)
+
+
+def stft_frames(x, window, n_fft, hop):
+    """ops.stft_frames: reflect pad (centred STFT) + frame + window, [N, T] -> [N, frames, n_fft]; torch autograd."""
+    p = n_fft // 2
+    xp = F.pad(x[:, None], (p, p), mode="reflect")[:, 0]
+    return xp.unfold(-1, n_fft, hop) * window
+
+
 def install(monkeypatch):
     from rave_b200 import ops
     for name in ("conv1d_tc", "conv1d_tc_wgrad", "weight_prep_tc", "weight_norm_bwd_tapmajor", "ncl_to_cl",
                  "cl_to_ncl", "weight_norm_raw", "conv1d_c1", "conv1d_c1_wgrad", "fm_stats", "fm_grad", "conv1d_c1_dgrad", "colsum_bf16", "im2col_c1", "gather_c1", "weight_prep_tc_multi",
                  "weight_norm_bwd_multi", "score_stats", "score_grad", "ncl_to_cl_x3", "dilated_unit_tc",
-                 "dilated_unit_tc_supported", "snake_cl_fwd", "snake_cl_bwd", "activation", "leaky_fm"):
+                 "dilated_unit_tc_supported", "snake_cl_fwd", "snake_cl_bwd", "activation", "leaky_fm", "time_stack_nhwc",
+                 "leaky_fm_stack", "stft_frames"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -472,3 +472,37 @@ def test_fake_rows_only_backward_of_a_plain_operand_chain(emu):
         assert g_half.shape == g_full.shape
         assert torch.count_nonzero(g_half[:4]) == 0 and torch.count_nonzero(g_full[:4]) > 0
         assert torch.equal(g_half[4:], g_full[4:])
+
+
+def test_mrd_channel_last_engine_path_vs_oracle(emu, monkeypatch):
+    """The MRD's engine path (channel-last end to end, one-layer chains, feature taps that also write the next conv's
+    time-stacked operand) against the oracle's Conv2d form of rave/descript_discriminator.py:118-184: every feature and
+    the input gradient; the fused tap + stack and the separate passes give the same numbers."""
+    from rave_b200.descript_discriminator import MRD
+    torch.manual_seed(21)
+    mrd = MRD(256)
+    sd = {k: v.detach().clone() for k, v in mrd.state_dict().items()}
+    x = (0.5 * torch.randn(4, 1, 2048)).clamp(-1, 1)
+    xo = x.clone().requires_grad_(True)
+    want = O.descript_mrd(xo, sd, "", 256)
+    probes = [torch.randn_like(f) for f in want]
+    (g_o,) = torch.autograd.grad(sum((f * p).sum() for f, p in zip(want, probes)), xo)
+    res = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("RAVE_FUSE_TAP_STACK", fuse)
+        xe = x.clone().requires_grad_(True)
+        got = mrd._forward_cl(xe)
+        assert len(got) == len(want) == 26
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert a.shape == b.shape, (i, a.shape, b.shape)
+            assert rel_l2(a, b) < tol(emu, 2e-5, 3e-2), (fuse, i, rel_l2(a, b))
+        for f in got[:-1]:                                   # the taps' own feature-matching sums
+            st = f._fm_stats
+            ref = torch.stack([(f[:2] - f[2:]).abs().sum(), f[:2].abs().sum()])
+            assert rel_l2(st, ref) < 1e-5
+        (g_e,) = torch.autograd.grad(sum((f * p).sum() for f, p in zip(got, probes)), xe)
+        assert rel_l2(g_e, g_o) < tol(emu, 5e-5, 0.1), (fuse, rel_l2(g_e, g_o))
+        res[fuse] = ([f.detach().clone() for f in got], g_e)
+    for a, b in zip(res["1"][0], res["0"][0]):
+        assert torch.equal(a, b)
+    assert rel_l2(res["1"][1], res["0"][1]) < 1e-6
