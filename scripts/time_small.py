@@ -20,7 +20,7 @@ for name, K, stride, pad, period, pool in [("msd0", 15, 4, 7, 1, 1), ("msd2", 15
     pitch = (Lout + 3) // 4 * 4
     us = graph_time_us(lambda i: ops.im2col_c1(src[i % 3], Lin, Lout, pitch, K, stride, pad, period, pool), n=9)
     mb = (Bs * T * 4 + Bs * period * pitch * 32) / 1e6
-    print(f"{tag} im2col_c1 {name:6s} {us:7.1f} us  {mb / us * 1e-3 * 1e3:7.0f} GB/s", flush=True)
+    print(f"{tag} im2col_c1 {name:6s} {us:7.1f} us  {mb / us * 1e3:7.0f} GB/s", flush=True)      # MB / us = TB/s
     P = [torch.randn(Bs * period, pitch, 16, device=dev) for _ in range(3)]
     us = graph_time_us(lambda i: ops.gather_c1(P[i % 3], (Bs, T), Lin, Lout, K, stride, pad, period, pool), n=9)
     print(f"{tag} gather_c1 {name:6s} {us:7.1f} us", flush=True)
